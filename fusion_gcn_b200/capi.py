@@ -1,0 +1,69 @@
+"""ctypes binding of libagcn_b200.so (the C ABI declared in include/agcn_b200.h).
+
+There is no CPU fallback: if the shared library is missing or does not load, every
+kernel entry point raises ``RuntimeError``.  Build it with ``python -m fusion_gcn_b200.build``
+(or ``__graft_entry__.build()``).
+"""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libagcn_b200.so")
+
+PREC_FP32 = 0
+PREC_TF32 = 1
+MIX_AGG_FWD, MIX_AGG_BWD, MIX_SCORE_BWD = 0, 1, 2
+RES_NONE, RES_TENSOR, RES_AFFINE = 0, 1, 2
+
+_c_int, _c_ll, _c_float, _c_void_p, _c_size_t = ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
+
+# name -> (restype, argtypes); mirrors include/agcn_b200.h one to one
+SIGNATURES = {
+    "agcn_version": (_c_int, []),
+    "agcn_last_error_string": (ctypes.c_char_p, []),
+    "agcn_conv_fwd": (_c_int, [_c_void_p] * 4 + [_c_int] * 12 + [_c_void_p]),
+    "agcn_conv_wgrad_workspace_bytes": (_c_size_t, [_c_int] * 7),
+    "agcn_conv_wgrad": (_c_int, [_c_void_p] * 4 + [_c_int] * 9 + [_c_void_p, _c_size_t, _c_int, _c_void_p]),
+    "agcn_joint_gram": (_c_int, [_c_void_p] * 3 + [_c_int] * 12 + [_c_void_p]),
+    "agcn_attention_fwd": (_c_int, [_c_void_p] * 5 + [_c_int] * 4 + [_c_float, _c_void_p]),
+    "agcn_attention_bwd": (_c_int, [_c_void_p] * 5 + [_c_int] * 4 + [_c_float, _c_void_p]),
+    "agcn_joint_mix": (_c_int, [_c_void_p] * 3 + [_c_int] * 8 + [_c_void_p]),
+    "agcn_bn_workspace_bytes": (_c_size_t, [_c_int]),
+    "agcn_bn_stats": (_c_int, [_c_void_p, _c_int, _c_int, _c_ll, _c_int] + [_c_void_p] * 5 + [_c_float, _c_float, _c_int]
+                      + [_c_void_p] * 4 + [_c_void_p, _c_size_t, _c_void_p]),
+    "agcn_bn_apply": (_c_int, [_c_void_p] * 3 + [_c_int] + [_c_void_p] * 3 + [_c_int, _c_void_p, _c_int, _c_int, _c_ll, _c_int, _c_void_p]),
+    "agcn_bn_bwd": (_c_int, [_c_void_p] * 10 + [_c_int, _c_int, _c_int, _c_ll, _c_int, _c_void_p, _c_size_t, _c_void_p]),
+    "agcn_pool_fwd": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
+    "agcn_pool_bwd": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
+}
+
+_lock = threading.Lock()
+_lib = None
+launch_count = 0          # kernels-entry calls issued through this binding (bench.py reports it)
+
+
+def lib():
+    """The loaded library; raises loudly when it is absent (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.isfile(LIB_PATH):
+                raise RuntimeError(
+                    f"{LIB_PATH} not found: the CUDA extension is not built. Run `python -m fusion_gcn_b200.build` "
+                    "(needs nvcc with sm_100a support). fusion_gcn_b200 has no CPU or PyTorch fallback.")
+            handle = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(handle, name)       # AttributeError here = header/library mismatch
+                fn.restype = res
+                fn.argtypes = args
+            _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().agcn_last_error_string().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed with status {rc}: {msg}")

@@ -1,0 +1,425 @@
+// BatchNorm statistics / apply / backward, and the global mean pool, on channels-last tensors.
+// Reference arithmetic: nn.BatchNorm2d / nn.BatchNorm1d in training mode (torch_src/models/mmargcn/agcn.py:44,78,83,150),
+// ReLU + residual adds (:113-115, :135-136), mean pooling (:194-196).
+// Reductions are two-phase and deterministic: per-CTA fp32 partials in a fixed row partition, combined in fp64.
+#include "common.cuh"
+#include <initializer_list>
+
+namespace agcn {
+
+constexpr int kMaxPartials = 4 * kNumSMs;   // 592
+
+struct RowMap {
+    int outer, inner; long long outer_stride; int channels;
+    __device__ __forceinline__ long long row_offset(long long r) const {
+        if (outer == 1) return r * channels;
+        long long o = r / inner;
+        return o * outer_stride + (r - o * inner) * channels;
+    }
+};
+
+static int num_partials(long long rows) {
+    long long p = (rows + 63) / 64;
+    if (p > kMaxPartials) p = kMaxPartials;
+    if (p < 1) p = 1;
+    return (int)p;
+}
+
+// NS sums per channel.  MODE 0: (x, x^2).  MODE 1: (g, g*xhat) with g = dout * [mask > 0].
+// grid = (P, column strips of 32); block = 32 columns x 8 row lanes.
+template <int MODE>
+__global__ void __launch_bounds__(256) colsum_strip_kernel(const float* x, const float* dout, const float* mask,
+                                                           const float* mean, const float* invstd,
+                                                           RowMap m, long long rows, float* part) {
+    __shared__ float sm[2][8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.y * 32 + tx;
+    const int P = gridDim.x;
+    const long long per = (rows + P - 1) / P;
+    const long long r0 = (long long)blockIdx.x * per;
+    long long r1 = r0 + per; if (r1 > rows) r1 = rows;
+    float s0 = 0.f, s1 = 0.f;
+    if (c < m.channels) {
+        float mu = 0.f, is = 0.f;
+        if (MODE == 1) { mu = mean[c]; is = invstd[c]; }
+        for (long long r = r0 + ty; r < r1; r += 8) {
+            const long long off = m.row_offset(r) + c;
+            if (MODE == 0) {
+                float v = __ldg(x + off);
+                s0 += v; s1 = fmaf(v, v, s1);
+            } else {
+                float g = __ldg(dout + off);
+                if (mask != nullptr && !(__ldg(mask + off) > 0.f)) g = 0.f;
+                float xh = (__ldg(x + off) - mu) * is;
+                s0 += g; s1 = fmaf(g, xh, s1);
+            }
+        }
+    }
+    sm[0][ty][tx] = s0; sm[1][ty][tx] = s1;
+    __syncthreads();
+    if (ty == 0 && c < m.channels) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { a += sm[0][i][tx]; b += sm[1][i][tx]; }
+        part[((long long)blockIdx.x * 2 + 0) * m.channels + c] = a;
+        part[((long long)blockIdx.x * 2 + 1) * m.channels + c] = b;
+    }
+}
+
+// Vectorised variant for channels % 4 == 0 and 256 % (channels/4) == 0 (64, 128, 256, ...; outer == 1 or not).
+template <int MODE>
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const float* x, const float* dout, const float* mask,
+                                                         const float* mean, const float* invstd,
+                                                         RowMap m, long long rows, float* part) {
+    extern __shared__ __align__(16) float smv[];   // [2][lanes_r][channels]
+    const int cq = m.channels >> 2;
+    const int lanes_r = 256 / cq;
+    const int q = threadIdx.x % cq, rl = threadIdx.x / cq;
+    const int P = gridDim.x;
+    const long long per = (rows + P - 1) / P;
+    const long long r0 = (long long)blockIdx.x * per;
+    long long r1 = r0 + per; if (r1 > rows) r1 = rows;
+    float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+    float4 mu = s0, is = s0;
+    if (MODE == 1) {
+        mu = *reinterpret_cast<const float4*>(mean + q * 4);
+        is = *reinterpret_cast<const float4*>(invstd + q * 4);
+    }
+    for (long long r = r0 + rl; r < r1; r += lanes_r) {
+        const long long off = m.row_offset(r) + q * 4;
+        if (MODE == 0) {
+            float4 v = __ldg(reinterpret_cast<const float4*>(x + off));
+            s0.x += v.x; s0.y += v.y; s0.z += v.z; s0.w += v.w;
+            s1.x = fmaf(v.x, v.x, s1.x); s1.y = fmaf(v.y, v.y, s1.y); s1.z = fmaf(v.z, v.z, s1.z); s1.w = fmaf(v.w, v.w, s1.w);
+        } else {
+            float4 g = __ldg(reinterpret_cast<const float4*>(dout + off));
+            if (mask != nullptr) {
+                float4 k = __ldg(reinterpret_cast<const float4*>(mask + off));
+                if (!(k.x > 0.f)) g.x = 0.f;
+                if (!(k.y > 0.f)) g.y = 0.f;
+                if (!(k.z > 0.f)) g.z = 0.f;
+                if (!(k.w > 0.f)) g.w = 0.f;
+            }
+            float4 v = __ldg(reinterpret_cast<const float4*>(x + off));
+            s0.x += g.x; s0.y += g.y; s0.z += g.z; s0.w += g.w;
+            s1.x = fmaf(g.x, (v.x - mu.x) * is.x, s1.x); s1.y = fmaf(g.y, (v.y - mu.y) * is.y, s1.y);
+            s1.z = fmaf(g.z, (v.z - mu.z) * is.z, s1.z); s1.w = fmaf(g.w, (v.w - mu.w) * is.w, s1.w);
+        }
+    }
+    float4* a = reinterpret_cast<float4*>(smv);
+    a[(0 * lanes_r + rl) * cq + q] = s0;
+    a[(1 * lanes_r + rl) * cq + q] = s1;
+    __syncthreads();
+    // 2 * channels outputs, each summed over lanes_r
+    for (int o = threadIdx.x; o < 2 * m.channels; o += 256) {
+        const int which = o / m.channels, c = o % m.channels;
+        float acc = 0.f;
+        for (int i = 0; i < lanes_r; ++i) acc += smv[(which * lanes_r + i) * m.channels + c];
+        part[((long long)blockIdx.x * 2 + which) * m.channels + c] = acc;
+    }
+}
+
+__global__ void bn_finalize_kernel(const float* part, int P, int C, double count,
+                                   const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                   long long* nbt, float momentum, float eps, int training,
+                                   float* scale, float* shift, float* save_mean, float* save_invstd) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && training && nbt != nullptr) *nbt += 1;
+    if (c >= C) return;
+    double mean, var;
+    if (training) {
+        double s = 0.0, q = 0.0;
+        for (int b = 0; b < P; ++b) {
+            s += (double)part[((long long)b * 2 + 0) * C + c];
+            q += (double)part[((long long)b * 2 + 1) * C + c];
+        }
+        mean = s / count;
+        var = q / count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        if (running_mean != nullptr) {
+            const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+            running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mean);
+            running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
+        }
+    } else {
+        mean = running_mean[c];
+        var = running_var[c];
+    }
+    const double invstd = 1.0 / sqrt(var + (double)eps);
+    const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+    const float sc = (float)(g * invstd);
+    scale[c] = sc;
+    shift[c] = (float)(b - mean * g * invstd);
+    if (save_mean) save_mean[c] = (float)mean;
+    if (save_invstd) save_invstd[c] = (float)invstd;
+}
+
+// out = act(scale*y + shift + R)
+template <bool VEC>
+__global__ void __launch_bounds__(256) bn_apply_kernel(const float* y, const float* scale, const float* shift, int res_mode,
+                                                       const float* res, const float* scale2, const float* shift2, int relu,
+                                                       float* out, RowMap m, long long rows) {
+    constexpr int W = VEC ? 4 : 1;
+    const int cq = m.channels / W;
+    const long long total = rows * cq;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx / cq;
+        const int c = (int)(idx - r * cq) * W;
+        const long long off = m.row_offset(r) + c;
+        if (VEC) {
+            float4 v = __ldg(reinterpret_cast<const float4*>(y + off));
+            const float4 sc = *reinterpret_cast<const float4*>(scale + c), sh = *reinterpret_cast<const float4*>(shift + c);
+            float4 o = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
+            if (res_mode == AGCN_RES_TENSOR) {
+                float4 q = __ldg(reinterpret_cast<const float4*>(res + off));
+                o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
+            } else if (res_mode == AGCN_RES_AFFINE) {
+                float4 q = __ldg(reinterpret_cast<const float4*>(res + off));
+                const float4 s2 = *reinterpret_cast<const float4*>(scale2 + c), h2 = *reinterpret_cast<const float4*>(shift2 + c);
+                o.x += fmaf(q.x, s2.x, h2.x); o.y += fmaf(q.y, s2.y, h2.y); o.z += fmaf(q.z, s2.z, h2.z); o.w += fmaf(q.w, s2.w, h2.w);
+            }
+            if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            *reinterpret_cast<float4*>(out + off) = o;
+        } else {
+            float o = fmaf(__ldg(y + off), scale[c], shift[c]);
+            if (res_mode == AGCN_RES_TENSOR) o += __ldg(res + off);
+            else if (res_mode == AGCN_RES_AFFINE) o += fmaf(__ldg(res + off), scale2[c], shift2[c]);
+            if (relu) o = fmaxf(o, 0.f);
+            out[off] = o;
+        }
+    }
+}
+
+// coef[0][c] = gamma*invstd, coef[1][c] = s1/m, coef[2][c] = s2/m * invstd, coef[3][c] = mean;  dgamma = s2, dbeta = s1
+__global__ void bn_bwd_finalize_kernel(const float* part, int P, int C, double count, const float* gamma,
+                                       const float* mean, const float* invstd, float* dgamma, float* dbeta, float* coef) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s1 = 0.0, s2 = 0.0;
+    for (int b = 0; b < P; ++b) {
+        s1 += (double)part[((long long)b * 2 + 0) * C + c];
+        s2 += (double)part[((long long)b * 2 + 1) * C + c];
+    }
+    if (dbeta) dbeta[c] = (float)s1;
+    if (dgamma) dgamma[c] = (float)s2;
+    const float is = invstd[c];
+    coef[0 * C + c] = (gamma ? gamma[c] : 1.f) * is;
+    coef[1 * C + c] = (float)(s1 / count);
+    coef[2 * C + c] = (float)(s2 / count) * is;
+    coef[3 * C + c] = mean[c];
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* dout, const float* mask, const float* y, const float* coef,
+                                                           float* dy, float* dres, int dres_acc, RowMap m, long long rows) {
+    constexpr int W = VEC ? 4 : 1;
+    const int C = m.channels;
+    const int cq = C / W;
+    const long long total = rows * cq;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx / cq;
+        const int c = (int)(idx - r * cq) * W;
+        const long long off = m.row_offset(r) + c;
+        float g[4] = {0.f, 0.f, 0.f, 0.f}, yv[4] = {0.f, 0.f, 0.f, 0.f}, mk[4] = {1.f, 1.f, 1.f, 1.f};
+        if constexpr (VEC) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(dout + off));
+            g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w;
+            if (mask) {
+                const float4 k = __ldg(reinterpret_cast<const float4*>(mask + off));
+                mk[0] = k.x; mk[1] = k.y; mk[2] = k.z; mk[3] = k.w;
+            }
+            if (dy) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(y + off));
+                yv[0] = b.x; yv[1] = b.y; yv[2] = b.z; yv[3] = b.w;
+            }
+        } else {
+            g[0] = __ldg(dout + off);
+            if (mask) mk[0] = __ldg(mask + off);
+            if (dy) yv[0] = __ldg(y + off);
+        }
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int e = 0; e < W; ++e) {
+            if (!(mk[e] > 0.f)) g[e] = 0.f;
+            if (dy) o[e] = coef[c + e] * (g[e] - coef[C + c + e] - (yv[e] - coef[3 * C + c + e]) * coef[2 * C + c + e]);
+        }
+        if constexpr (VEC) {
+            if (dy) *reinterpret_cast<float4*>(dy + off) = make_float4(o[0], o[1], o[2], o[3]);
+            if (dres) {
+                float4 q = make_float4(g[0], g[1], g[2], g[3]);
+                if (dres_acc) {
+                    const float4 old = *reinterpret_cast<const float4*>(dres + off);
+                    q.x += old.x; q.y += old.y; q.z += old.z; q.w += old.w;
+                }
+                *reinterpret_cast<float4*>(dres + off) = q;
+            }
+        } else {
+            if (dy) dy[off] = o[0];
+            if (dres) dres[off] = dres_acc ? dres[off] + g[0] : g[0];
+        }
+    }
+}
+
+// pooling: grid = (groups, column strips of 32); block = 32 x 8
+__global__ void __launch_bounds__(256) pool_fwd_kernel(const float* x, float* out, int rows_per_group, int C) {
+    __shared__ float sm[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.y * 32 + tx;
+    const float* base = x + (long long)blockIdx.x * rows_per_group * C;
+    float s = 0.f;
+    if (c < C)
+        for (int r = ty; r < rows_per_group; r += 8) s += __ldg(base + (long long)r * C + c);
+    sm[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+        float a = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a += sm[i][tx];
+        out[(long long)blockIdx.x * C + c] = a / (float)rows_per_group;
+    }
+}
+
+__global__ void pool_bwd_kernel(const float* dout, float* dx, int rows_per_group, int C, long long total) {
+    const float inv = 1.f / (float)rows_per_group;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % C);
+        const long long g = idx / ((long long)rows_per_group * C);
+        dx[idx] = dout[g * C + c] * inv;
+    }
+}
+
+static bool vec_ok(const RowMap& m, std::initializer_list<const void*> ptrs) {
+    if (m.channels % 4) return false;
+    if (m.outer != 1 && (m.outer_stride % 4)) return false;
+    for (const void* p : ptrs) if (p != nullptr && !aligned16(p)) return false;
+    return true;
+}
+
+template <int MODE>
+static int launch_colsum(const float* x, const float* dout, const float* mask, const float* mean, const float* invstd,
+                         const RowMap& m, long long rows, float* part, int P, cudaStream_t s) {
+    const int cq = m.channels / 4;
+    const bool vec = vec_ok(m, {x, dout, mask, mean, invstd}) && cq <= 256 && (256 % cq) == 0 && m.channels <= 1024;
+    if (vec) {
+        const int lanes_r = 256 / cq;
+        size_t smem = (size_t)2 * lanes_r * m.channels * sizeof(float);
+        colsum_vec_kernel<MODE><<<P, 256, smem, s>>>(x, dout, mask, mean, invstd, m, rows, part);
+    } else {
+        dim3 grid((unsigned)P, (unsigned)ceil_div(m.channels, 32));
+        colsum_strip_kernel<MODE><<<grid, 256, 0, s>>>(x, dout, mask, mean, invstd, m, rows, part);
+    }
+    return check_launch("bn column sums");
+}
+
+static int elementwise_blocks(long long work_items) {
+    long long b = (work_items + 255) / 256;
+    const long long cap = (long long)kNumSMs * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+}  // namespace agcn
+
+using namespace agcn;
+
+extern "C" size_t agcn_bn_workspace_bytes(int channels) {
+    if (channels <= 0) return 0;
+    // partial sums [kMaxPartials][2][C] followed by the backward coefficients [4][C]
+    return ((size_t)kMaxPartials * 2 + 4) * (size_t)channels * sizeof(float);
+}
+
+static int check_map(const char* who, int outer, int inner, long long outer_stride, int channels) {
+    AGCN_REQUIRE(outer > 0 && inner > 0 && channels > 0, AGCN_ERR_BAD_SHAPE, "%s: bad shape outer=%d inner=%d channels=%d", who, outer, inner, channels);
+    AGCN_REQUIRE(outer == 1 || outer_stride >= (long long)inner * channels, AGCN_ERR_BAD_SHAPE, "%s: outer_stride too small", who);
+    return AGCN_OK;
+}
+
+extern "C" int agcn_bn_stats(const float* x, int outer, int inner, long long outer_stride, int channels,
+                             const float* gamma, const float* beta, float* running_mean, float* running_var,
+                             long long* num_batches_tracked, float momentum, float eps, int training,
+                             float* scale, float* shift, float* save_mean, float* save_invstd,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_map("agcn_bn_stats", outer, inner, outer_stride, channels);
+    if (rc) return rc;
+    AGCN_REQUIRE(scale && shift, AGCN_ERR_NULL, "agcn_bn_stats: scale/shift are required");
+    AGCN_REQUIRE(training || (running_mean && running_var), AGCN_ERR_NULL, "agcn_bn_stats: eval mode needs running statistics");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    RowMap m{outer, inner, outer_stride, channels};
+    const long long rows = (long long)outer * inner;
+    int P = 0;
+    float* part = static_cast<float*>(workspace);
+    if (training) {
+        AGCN_REQUIRE(x && workspace, AGCN_ERR_NULL, "agcn_bn_stats: null pointer");
+        AGCN_REQUIRE(workspace_bytes >= agcn_bn_workspace_bytes(channels), AGCN_ERR_WORKSPACE, "agcn_bn_stats: workspace too small");
+        P = num_partials(rows);
+        rc = launch_colsum<0>(x, nullptr, nullptr, nullptr, nullptr, m, rows, part, P, s);
+        if (rc) return rc;
+    }
+    bn_finalize_kernel<<<ceil_div(channels, 128), 128, 0, s>>>(part, P, channels, (double)rows, gamma, beta, running_mean, running_var,
+                                                              num_batches_tracked, momentum, eps, training, scale, shift, save_mean, save_invstd);
+    return check_launch("agcn_bn_stats(finalize)");
+}
+
+extern "C" int agcn_bn_apply(const float* y, const float* scale, const float* shift,
+                             int res_mode, const float* res, const float* scale2, const float* shift2,
+                             int relu, float* out, int outer, int inner, long long outer_stride, int channels, void* stream) {
+    int rc = check_map("agcn_bn_apply", outer, inner, outer_stride, channels);
+    if (rc) return rc;
+    AGCN_REQUIRE(y && scale && shift && out, AGCN_ERR_NULL, "agcn_bn_apply: null pointer");
+    AGCN_REQUIRE(res_mode == AGCN_RES_NONE || res, AGCN_ERR_NULL, "agcn_bn_apply: residual tensor missing");
+    AGCN_REQUIRE(res_mode != AGCN_RES_AFFINE || (scale2 && shift2), AGCN_ERR_NULL, "agcn_bn_apply: scale2/shift2 missing");
+    AGCN_REQUIRE(res_mode >= 0 && res_mode <= 2, AGCN_ERR_UNSUPPORTED, "agcn_bn_apply: res_mode %d", res_mode);
+    RowMap m{outer, inner, outer_stride, channels};
+    const long long rows = (long long)outer * inner;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (vec_ok(m, {y, scale, shift, res, scale2, shift2, out}))
+        bn_apply_kernel<true><<<elementwise_blocks(rows * (channels / 4)), 256, 0, s>>>(y, scale, shift, res_mode, res, scale2, shift2, relu, out, m, rows);
+    else
+        bn_apply_kernel<false><<<elementwise_blocks(rows * channels), 256, 0, s>>>(y, scale, shift, res_mode, res, scale2, shift2, relu, out, m, rows);
+    return check_launch("agcn_bn_apply");
+}
+
+extern "C" int agcn_bn_bwd(const float* dout, const float* mask_out, const float* y,
+                           const float* save_mean, const float* save_invstd, const float* gamma,
+                           float* dy, float* dgamma, float* dbeta, float* dres, int dres_accumulate,
+                           int outer, int inner, long long outer_stride, int channels,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_map("agcn_bn_bwd", outer, inner, outer_stride, channels);
+    if (rc) return rc;
+    AGCN_REQUIRE(dout && y && save_mean && save_invstd && workspace, AGCN_ERR_NULL, "agcn_bn_bwd: null pointer");
+    AGCN_REQUIRE(workspace_bytes >= agcn_bn_workspace_bytes(channels), AGCN_ERR_WORKSPACE, "agcn_bn_bwd: workspace too small");
+    RowMap m{outer, inner, outer_stride, channels};
+    const long long rows = (long long)outer * inner;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    float* part = static_cast<float*>(workspace);
+    float* coef = part + (size_t)kMaxPartials * 2 * channels;
+    const int P = num_partials(rows);
+    rc = launch_colsum<1>(y, dout, mask_out, save_mean, save_invstd, m, rows, part, P, s);
+    if (rc) return rc;
+    bn_bwd_finalize_kernel<<<ceil_div(channels, 128), 128, 0, s>>>(part, P, channels, (double)rows, gamma, save_mean, save_invstd, dgamma, dbeta, coef);
+    rc = check_launch("agcn_bn_bwd(finalize)");
+    if (rc) return rc;
+    if (dy == nullptr && dres == nullptr) return AGCN_OK;
+    if (vec_ok(m, {dout, mask_out, y, dy, dres, coef}))
+        bn_bwd_apply_kernel<true><<<elementwise_blocks(rows * (channels / 4)), 256, 0, s>>>(dout, mask_out, y, coef, dy, dres, dres_accumulate, m, rows);
+    else
+        bn_bwd_apply_kernel<false><<<elementwise_blocks(rows * channels), 256, 0, s>>>(dout, mask_out, y, coef, dy, dres, dres_accumulate, m, rows);
+    return check_launch("agcn_bn_bwd(apply)");
+}
+
+extern "C" int agcn_pool_fwd(const float* x, float* out, int groups, int rows_per_group, int channels, void* stream) {
+    AGCN_REQUIRE(x && out, AGCN_ERR_NULL, "agcn_pool_fwd: null pointer");
+    AGCN_REQUIRE(groups > 0 && rows_per_group > 0 && channels > 0, AGCN_ERR_BAD_SHAPE, "agcn_pool_fwd: bad shape");
+    dim3 grid((unsigned)groups, (unsigned)ceil_div(channels, 32));
+    pool_fwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, out, rows_per_group, channels);
+    return check_launch("agcn_pool_fwd");
+}
+
+extern "C" int agcn_pool_bwd(const float* dout, float* dx, int groups, int rows_per_group, int channels, void* stream) {
+    AGCN_REQUIRE(dout && dx, AGCN_ERR_NULL, "agcn_pool_bwd: null pointer");
+    AGCN_REQUIRE(groups > 0 && rows_per_group > 0 && channels > 0, AGCN_ERR_BAD_SHAPE, "agcn_pool_bwd: bad shape");
+    const long long total = (long long)groups * rows_per_group * channels;
+    pool_bwd_kernel<<<elementwise_blocks(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(dout, dx, rows_per_group, channels, total);
+    return check_launch("agcn_pool_bwd");
+}

@@ -1,0 +1,29 @@
+// Shared helpers for libagcn_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/agcn_b200.h"
+
+namespace agcn {
+
+// thread-local error text, returned by agcn_last_error_string()
+char* error_buffer();
+int fail(int code, const char* fmt, ...);
+
+inline int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(AGCN_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    return AGCN_OK;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+constexpr int kNumSMs = 148;   // B200
+
+}  // namespace agcn
+
+#define AGCN_REQUIRE(cond, code, ...) do { if (!(cond)) return agcn::fail(code, __VA_ARGS__); } while (0)

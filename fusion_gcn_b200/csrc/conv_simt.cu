@@ -1,0 +1,372 @@
+// FP32 FFMA implicit-GEMM kernels (parity mode + fallback for shapes the tcgen05 path does not take):
+//   agcn_conv_fwd   : y[rows][cout] (+)= bias + sum_tap x[gather(row,tap)][cin] . w[cout][tap][cin]
+//   agcn_conv_wgrad : dw[cout][tap][cin] = sum_rows dy[row][cout] * x[gather(row,tap)][cin]
+// Channels-last activations, rows = (nb, t, v).  Reference arithmetic: nn.Conv2d at
+// torch_src/models/mmargcn/agcn.py:41-42,71-73,77 and its autograd backward.
+#include "common.cuh"
+
+namespace agcn {
+
+struct ConvArgs {
+    const float* x; const float* w; const float* bias; float* y;
+    int nb, t_in, t_out, v, cin, cout, taps, stride, pad, transposed, accumulate;
+    long long rows_out;
+};
+
+__device__ __forceinline__ int gather_t(int to, int tap, const ConvArgs& a) {
+    // returns input time index or -1
+    if (!a.transposed) {
+        int ti = a.stride * to + tap - a.pad;
+        return (ti >= 0 && ti < a.t_in) ? ti : -1;
+    }
+    int num = to + a.pad - tap;
+    if (num < 0) return -1;
+    if (a.stride != 1) {
+        if (num % a.stride) return -1;
+        num /= a.stride;
+    }
+    return num < a.t_in ? num : -1;
+}
+
+// 128 x 64 output tile, K step 16, 256 threads, 8x4 outputs per thread, register-prefetch double buffering.
+template <bool VEC>
+__global__ void __launch_bounds__(256) conv_fwd_kernel(ConvArgs a) {
+    constexpr int BM = 128, BN = 64, BK = 16, LDA = BM + 4, LDB = BN + 4;
+    __shared__ __align__(16) float As[2][BK][LDA];
+    __shared__ __align__(16) float Bs[2][BK][LDB];
+    const int tid = threadIdx.x;
+    const long long m0 = (long long)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+    const int lrow = tid >> 2, lkq = tid & 3;
+
+    int rn[2], rt[2], rv[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        long long r = m0 + lrow + i * 64;
+        if (r < a.rows_out) {
+            rv[i] = (int)(r % a.v);
+            long long q = r / a.v;
+            rt[i] = (int)(q % a.t_out);
+            rn[i] = (int)(q / a.t_out);
+        } else {
+            rn[i] = -1; rt[i] = 0; rv[i] = 0;
+        }
+    }
+    const int wcol = n0 + lrow;          // weight row (output channel) this thread loads
+    const int kchunks = (a.cin + BK - 1) / BK;
+    const int total = a.taps * kchunks;
+
+    float ra[2][4], rb[4];
+    auto load_global = [&](int it) {
+        const int tap = it / kchunks;
+        const int k0 = (it - tap * kchunks) * BK + lkq * 4;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            ra[i][0] = ra[i][1] = ra[i][2] = ra[i][3] = 0.f;
+            if (rn[i] >= 0) {
+                int ti = gather_t(rt[i], tap, a);
+                if (ti >= 0) {
+                    const float* p = a.x + (((long long)rn[i] * a.t_in + ti) * a.v + rv[i]) * a.cin + k0;
+                    if (VEC) {
+                        if (k0 < a.cin) {
+                            float4 q = __ldg(reinterpret_cast<const float4*>(p));
+                            ra[i][0] = q.x; ra[i][1] = q.y; ra[i][2] = q.z; ra[i][3] = q.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) if (k0 + j < a.cin) ra[i][j] = __ldg(p + j);
+                    }
+                }
+            }
+        }
+        rb[0] = rb[1] = rb[2] = rb[3] = 0.f;
+        if (wcol < a.cout) {
+            const float* p = a.w + ((long long)wcol * a.taps + tap) * a.cin + k0;
+            if (VEC) {
+                if (k0 < a.cin) {
+                    float4 q = __ldg(reinterpret_cast<const float4*>(p));
+                    rb[0] = q.x; rb[1] = q.y; rb[2] = q.z; rb[3] = q.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (k0 + j < a.cin) rb[j] = __ldg(p + j);
+            }
+        }
+    };
+    auto store_smem = [&](int buf) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            As[buf][lkq * 4 + j][lrow] = ra[0][j];
+            As[buf][lkq * 4 + j][lrow + 64] = ra[1][j];
+            Bs[buf][lkq * 4 + j][lrow] = rb[j];
+        }
+    };
+
+    const int tx = tid & 15, ty = tid >> 4;
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    load_global(0);
+    store_smem(0);
+    __syncthreads();
+    for (int it = 0; it < total; ++it) {
+        const int buf = it & 1;
+        if (it + 1 < total) load_global(it + 1);
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8]);
+            float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8 + 4]);
+            float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (it + 1 < total) store_smem(buf ^ 1);
+        __syncthreads();
+    }
+
+    const int col = n0 + tx * 4;
+    float bias[4] = {0.f, 0.f, 0.f, 0.f};
+    if (a.bias) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (col + j < a.cout) bias[j] = __ldg(a.bias + col + j);
+    }
+    const bool vec_out = ((a.cout & 3) == 0) && (col + 3 < a.cout);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        long long r = m0 + ty * 8 + i;
+        if (r >= a.rows_out) continue;
+        float* p = a.y + r * a.cout + col;
+        if (vec_out) {
+            float4 o = make_float4(acc[i][0] + bias[0], acc[i][1] + bias[1], acc[i][2] + bias[2], acc[i][3] + bias[3]);
+            if (a.accumulate) {
+                float4 old = *reinterpret_cast<const float4*>(p);
+                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            }
+            *reinterpret_cast<float4*>(p) = o;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (col + j < a.cout) {
+                    float o = acc[i][j] + bias[j];
+                    if (a.accumulate) o += p[j];
+                    p[j] = o;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ wgrad
+struct WgradArgs {
+    const float* dy; const float* x; float* ws_w; float* ws_b;
+    int nb, t_in, t_out, v, cin, cout, taps, stride, pad;
+    long long rows_out, rows_per_split;
+    int ntiles, ktiles;
+};
+
+// one CTA: 64 (cout) x 64 (cin) tile of one tap, over one row split; thread tile 4x4.
+template <bool VEC>
+__global__ void __launch_bounds__(256) conv_wgrad_kernel(WgradArgs a) {
+    constexpr int BR = 32, TN = 64, TK = 64, LD = 68;
+    __shared__ __align__(16) float Ds[BR][LD];
+    __shared__ __align__(16) float Xs[BR][LD];
+    const int tid = threadIdx.x;
+    int tile = blockIdx.x;
+    const int tap = tile % a.taps; tile /= a.taps;
+    const int ktile = tile % a.ktiles;
+    const int ntile = tile / a.ktiles;
+    const int n0 = ntile * TN, k0 = ktile * TK;
+    const int split = blockIdx.y;
+    const long long r_begin = (long long)split * a.rows_per_split;
+    long long r_end = r_begin + a.rows_per_split;
+    if (r_end > a.rows_out) r_end = a.rows_out;
+
+    const int lr = tid >> 4, lc = (tid & 15) * 4;
+    const int tx = tid & 15, ty = tid >> 4;
+    const bool do_bias = (a.ws_b != nullptr) && ktile == 0 && tap == 0 && tid < TN;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    float bsum = 0.f;
+
+    for (long long rb = r_begin; rb < r_end; rb += BR) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int rr = lr + h * 16;
+            const long long r = rb + rr;
+            float d[4] = {0.f, 0.f, 0.f, 0.f}, xv[4] = {0.f, 0.f, 0.f, 0.f};
+            if (r < r_end) {
+                const float* pd = a.dy + r * a.cout + n0 + lc;
+                if (VEC) {
+                    if (n0 + lc < a.cout) {
+                        float4 q = __ldg(reinterpret_cast<const float4*>(pd));
+                        d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (n0 + lc + j < a.cout) d[j] = __ldg(pd + j);
+                }
+                const int vv = (int)(r % a.v);
+                const long long q2 = r / a.v;
+                const int to = (int)(q2 % a.t_out);
+                const int n = (int)(q2 / a.t_out);
+                const int ti = a.stride * to + tap - a.pad;
+                if (ti >= 0 && ti < a.t_in) {
+                    const float* px = a.x + (((long long)n * a.t_in + ti) * a.v + vv) * a.cin + k0 + lc;
+                    if (VEC) {
+                        if (k0 + lc < a.cin) {
+                            float4 q = __ldg(reinterpret_cast<const float4*>(px));
+                            xv[0] = q.x; xv[1] = q.y; xv[2] = q.z; xv[3] = q.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) if (k0 + lc + j < a.cin) xv[j] = __ldg(px + j);
+                    }
+                }
+            }
+            *reinterpret_cast<float4*>(&Ds[rr][lc]) = make_float4(d[0], d[1], d[2], d[3]);
+            *reinterpret_cast<float4*>(&Xs[rr][lc]) = make_float4(xv[0], xv[1], xv[2], xv[3]);
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int r = 0; r < BR; ++r) {
+            float4 d4 = *reinterpret_cast<const float4*>(&Ds[r][ty * 4]);
+            float4 x4 = *reinterpret_cast<const float4*>(&Xs[r][tx * 4]);
+            const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+            const float xw[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(dv[i], xw[j], acc[i][j]);
+        }
+        if (do_bias) {
+#pragma unroll 8
+            for (int r = 0; r < BR; ++r) bsum += Ds[r][tid];
+        }
+        __syncthreads();
+    }
+    const long long wsize = (long long)a.cout * a.taps * a.cin;
+    float* out = a.ws_w + (long long)split * wsize;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int n = n0 + ty * 4 + i;
+        if (n >= a.cout) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = k0 + tx * 4 + j;
+            if (k < a.cin) out[((long long)n * a.taps + tap) * a.cin + k] = acc[i][j];
+        }
+    }
+    if (do_bias && n0 + tid < a.cout) a.ws_b[(long long)split * a.cout + n0 + tid] = bsum;
+}
+
+__global__ void wgrad_reduce_kernel(const float* ws_w, const float* ws_b, float* dw, float* db,
+                                    long long wsize, int cout, int splits) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < wsize) {
+        float s = 0.f;
+        for (int k = 0; k < splits; ++k) s += ws_w[(long long)k * wsize + i];
+        dw[i] = s;
+    } else if (db != nullptr && i < wsize + cout) {
+        long long c = i - wsize;
+        float s = 0.f;
+        for (int k = 0; k < splits; ++k) s += ws_b[(long long)k * cout + c];
+        db[c] = s;
+    }
+}
+
+static int wgrad_splits(long long rows, int cin, int cout, int taps) {
+    long long tiles = (long long)((cout + 63) / 64) * ((cin + 63) / 64) * taps;
+    long long s = (4LL * kNumSMs + tiles - 1) / tiles;
+    long long max_s = rows / 256;
+    if (s > max_s) s = max_s;
+    if (s > 64) s = 64;
+    if (s < 1) s = 1;
+    return (int)s;
+}
+
+}  // namespace agcn
+
+using namespace agcn;
+
+// implemented in conv_tc.cu; returns AGCN_ERR_UNSUPPORTED when the shape is outside the tensor-core path
+int agcn_conv_fwd_tc(const float* x, const float* w, const float* bias, float* y,
+                     int nb, int t_in, int t_out, int v, int cin, int cout,
+                     int taps, int stride, int pad, int transposed, int accumulate, void* stream);
+
+extern "C" int agcn_conv_fwd(const float* x, const float* w, const float* bias, float* y,
+                             int nb, int t_in, int t_out, int v, int cin, int cout,
+                             int taps, int stride, int pad, int transposed, int accumulate,
+                             int precision, void* stream) {
+    AGCN_REQUIRE(x && w && y, AGCN_ERR_NULL, "agcn_conv_fwd: null pointer");
+    AGCN_REQUIRE(nb > 0 && t_in > 0 && t_out > 0 && v > 0 && cin > 0 && cout > 0 && taps > 0 && stride > 0 && pad >= 0,
+                 AGCN_ERR_BAD_SHAPE, "agcn_conv_fwd: bad shape nb=%d t_in=%d t_out=%d v=%d cin=%d cout=%d taps=%d stride=%d pad=%d",
+                 nb, t_in, t_out, v, cin, cout, taps, stride, pad);
+    AGCN_REQUIRE(precision == AGCN_PREC_FP32 || precision == AGCN_PREC_TF32, AGCN_ERR_UNSUPPORTED,
+                 "agcn_conv_fwd: unknown precision %d", precision);
+    if (precision == AGCN_PREC_TF32) {
+        int rc = agcn_conv_fwd_tc(x, w, bias, y, nb, t_in, t_out, v, cin, cout, taps, stride, pad, transposed,
+                                  accumulate, stream);
+        if (rc != AGCN_ERR_UNSUPPORTED) return rc;   // unsupported shapes fall through to the FFMA kernel
+    }
+    ConvArgs a{x, w, bias, y, nb, t_in, t_out, v, cin, cout, taps, stride, pad, transposed, accumulate,
+               (long long)nb * t_out * v};
+    dim3 grid((unsigned)ceil_div(a.rows_out, 128), (unsigned)ceil_div(cout, 64));
+    const bool vec = (cin % 4 == 0) && aligned16(x) && aligned16(w);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (vec) conv_fwd_kernel<true><<<grid, 256, 0, s>>>(a);
+    else conv_fwd_kernel<false><<<grid, 256, 0, s>>>(a);
+    return check_launch("agcn_conv_fwd");
+}
+
+extern "C" size_t agcn_conv_wgrad_workspace_bytes(int nb, int t_in, int t_out, int v, int cin, int cout, int taps) {
+    (void)t_in;
+    long long rows = (long long)nb * t_out * v;
+    int splits = wgrad_splits(rows, cin, cout, taps);
+    return (size_t)splits * ((size_t)cout * taps * cin + (size_t)cout) * sizeof(float);
+}
+
+extern "C" int agcn_conv_wgrad(const float* dy, const float* x, float* dw, float* dbias,
+                               int nb, int t_in, int t_out, int v, int cin, int cout,
+                               int taps, int stride, int pad,
+                               void* workspace, size_t workspace_bytes, int precision, void* stream) {
+    (void)precision;
+    AGCN_REQUIRE(dy && x && dw && workspace, AGCN_ERR_NULL, "agcn_conv_wgrad: null pointer");
+    AGCN_REQUIRE(nb > 0 && t_in > 0 && t_out > 0 && v > 0 && cin > 0 && cout > 0 && taps > 0 && stride > 0 && pad >= 0,
+                 AGCN_ERR_BAD_SHAPE, "agcn_conv_wgrad: bad shape");
+    const size_t need = agcn_conv_wgrad_workspace_bytes(nb, t_in, t_out, v, cin, cout, taps);
+    AGCN_REQUIRE(workspace_bytes >= need, AGCN_ERR_WORKSPACE, "agcn_conv_wgrad: workspace %zu < %zu", workspace_bytes, need);
+    AGCN_REQUIRE(aligned16(workspace), AGCN_ERR_MISALIGNED, "agcn_conv_wgrad: workspace not 16-byte aligned");
+    WgradArgs a;
+    a.dy = dy; a.x = x;
+    a.nb = nb; a.t_in = t_in; a.t_out = t_out; a.v = v; a.cin = cin; a.cout = cout;
+    a.taps = taps; a.stride = stride; a.pad = pad;
+    a.rows_out = (long long)nb * t_out * v;
+    const int splits = wgrad_splits(a.rows_out, cin, cout, taps);
+    long long rps = (a.rows_out + splits - 1) / splits;
+    rps = (rps + 31) / 32 * 32;
+    a.rows_per_split = rps;
+    a.ntiles = (cout + 63) / 64; a.ktiles = (cin + 63) / 64;
+    const long long wsize = (long long)cout * taps * cin;
+    a.ws_w = static_cast<float*>(workspace);
+    a.ws_b = dbias ? a.ws_w + (long long)splits * wsize : nullptr;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    dim3 grid((unsigned)(a.ntiles * a.ktiles * taps), (unsigned)splits);
+    const bool vec = (cin % 4 == 0) && (cout % 4 == 0) && aligned16(x) && aligned16(dy);
+    if (vec) conv_wgrad_kernel<true><<<grid, 256, 0, s>>>(a);
+    else conv_wgrad_kernel<false><<<grid, 256, 0, s>>>(a);
+    int rc = check_launch("agcn_conv_wgrad");
+    if (rc) return rc;
+    const long long total = wsize + (dbias ? cout : 0);
+    wgrad_reduce_kernel<<<ceil_div(total, 256), 256, 0, s>>>(a.ws_w, a.ws_b, dw, dbias, wsize, cout, splits);
+    return check_launch("agcn_conv_wgrad(reduce)");
+}

@@ -1,0 +1,376 @@
+"""Host-side composition of the AGCN unit from the C-ABI kernels, forward and backward.
+
+Activations are channels-last ``[nb, t, v, c]`` (nb = N*M person-sequences).  The module
+parameters keep the reference's shapes and names; they are packed here, inside the autograd
+Functions, into the layouts the kernels want and the gradients are unpacked on the way back:
+
+  wab  [6*Ci, 1, Cin]    rows = theta_0 | phi_0 | theta_1 | phi_1 | theta_2 | phi_2   (conv_a / conv_b, agcn.py:71-72)
+  wd   [Cout, 1, 3*Cin]  columns = subset 0 | 1 | 2 (conv_d, agcn.py:73): sum_k Wd_k (X G_k) = [Wd_0 Wd_1 Wd_2] . [X G_0; X G_1; X G_2]
+  wt   [Cout, 9, Cout]   temporal taps (tcn1.conv, agcn.py:41-42)
+
+Maths: SURVEY.md Appendix A.  Reference: torch_src/models/mmargcn/agcn.py:49-51,96-115,134-136.
+"""
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import torch
+
+from . import ops as K      # tests swap this for oracle.stages on CPU; the package has no fallback
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+@dataclass
+class BnBuffers:
+    running_mean: torch.Tensor
+    running_var: torch.Tensor
+    num_batches_tracked: Optional[torch.Tensor]
+
+
+@dataclass
+class UnitSpec:
+    """Static description of one SpatialTemporalConv (or of its gcn / tcn half)."""
+    cin: int
+    cout: int
+    stride: int = 1
+    residual: str = "none"          # 'none' | 'identity' | 'conv'
+    has_down: bool = False
+    kernel_size: int = 9
+    relu_out: bool = True
+    training: bool = True
+    precision: int = 0
+    bn_gcn: Optional[BnBuffers] = None
+    bn_down: Optional[BnBuffers] = None
+    bn_tcn: Optional[BnBuffers] = None
+    bn_res: Optional[BnBuffers] = None
+    attention_out: Optional[List[torch.Tensor]] = field(default=None)   # receives adj_c (3 x [nb,V,V], detached)
+
+
+def _bn_forward(y, gamma, beta, buf: BnBuffers, training: bool):
+    return K.bn_stats(y, gamma, beta, buf.running_mean, buf.running_var, buf.num_batches_tracked,
+                      BN_MOMENTUM, BN_EPS, training)
+
+
+def _t(w):
+    """[cout, taps, cin] -> [cin, taps, cout] (weight of the input-gradient contraction)."""
+    return w.permute(2, 1, 0).contiguous()
+
+
+# =============================================================================== gcn half
+def gcn_forward(x, adj_a, adj_b, wa, ba, wb, bb, wd, bd, bn_w, bn_b, down_w, down_b, dbn_w, dbn_b, spec: UnitSpec, ctx):
+    nb, t, v, cin = x.shape
+    cout = spec.cout
+    ci = wa[0].shape[0]
+    prec = spec.precision
+    wab = torch.cat([w.reshape(ci, 1, cin) for pair in zip(wa, wb) for w in pair], dim=0)
+    bab = torch.cat([b for pair in zip(ba, bb) for b in pair], dim=0)
+    wdc = torch.cat([w.reshape(cout, 1, cin) for w in wd], dim=2).contiguous()
+    bdc = bd[0] + bd[1] + bd[2]
+
+    e = K.conv_fwd(x, wab, bab, precision=prec)                                        # theta / phi embeddings
+    nchunk = K.pick_nchunk(nb, t)
+    s_part = K.joint_gram(e, e, groups=3, offa=0, stridea=2 * ci, offb=ci, strideb=2 * ci, width=ci, nchunk=nchunk)
+    scale = 1.0 / float(ci * t)
+    p, g = K.attention_fwd(s_part, adj_a.contiguous(), adj_b.contiguous(), scale)
+    z = K.joint_mix(x, g, width=cin, mode=K.MIX_AGG_FWD)                               # [nb,t,v,3*cin]
+    y = K.conv_fwd(z, wdc, bdc, precision=prec)
+    sc, sh, mean, invstd = _bn_forward(y, bn_w, bn_b, spec.bn_gcn, spec.training)
+    if spec.has_down:
+        yd = K.conv_fwd(x, down_w.reshape(cout, 1, cin), down_b, precision=prec)
+        sc2, sh2, mean2, invstd2 = _bn_forward(yd, dbn_w, dbn_b, spec.bn_down, spec.training)
+        o = K.bn_apply(y, sc, sh, res_mode=K.RES_AFFINE, res=yd, scale2=sc2, shift2=sh2, relu=True)
+    else:
+        yd = mean2 = invstd2 = None
+        o = K.bn_apply(y, sc, sh, res_mode=K.RES_TENSOR, res=x, relu=True)
+    if spec.attention_out is not None:
+        spec.attention_out[:] = [p[:, k] for k in range(3)]
+    if ctx is not None:
+        ctx.update(x=x, e=e, p=p, g=g, z=z, y=y, yd=yd, o=o.detach(), mean=mean, invstd=invstd, mean2=mean2, invstd2=invstd2,
+                   wab=wab, wdc=wdc, nchunk=nchunk, scale=scale, ci=ci)
+    return o
+
+
+def gcn_backward(d_o, ctx, bn_w, dbn_w, down_w, spec: UnitSpec, dx=None, need_dx=True):
+    """Returns (dx, grads) where grads follows the parameter order of gcn_forward.  ``dx`` may carry
+    an already-written gradient buffer to accumulate into."""
+    x, e, p, g, z, y, o = ctx["x"], ctx["e"], ctx["p"], ctx["g"], ctx["z"], ctx["y"], ctx["o"]
+    nb, t, v, cin = x.shape
+    cout, ci, prec = spec.cout, ctx["ci"], spec.precision
+    have = dx is not None
+    if spec.has_down:
+        dy, dgam, dbet = K.bn_bwd(d_o, o, y, ctx["mean"], ctx["invstd"], bn_w)
+        dyd, dgam2, dbet2 = K.bn_bwd(d_o, o, ctx["yd"], ctx["mean2"], ctx["invstd2"], dbn_w)
+        wdown = down_w.reshape(cout, 1, cin)
+        d_down_w, d_down_b = K.conv_wgrad(dyd, x, precision=prec)
+        if need_dx:
+            dx = K.conv_fwd(dyd, _t(wdown), out=dx, accumulate=have, precision=prec)
+            have = True
+    else:
+        if need_dx and dx is None:
+            dx = torch.empty_like(x)
+        dy, dgam, dbet = K.bn_bwd(d_o, o, y, ctx["mean"], ctx["invstd"], bn_w,
+                                  dres=dx if need_dx else None, dres_accumulate=have)
+        have = have or need_dx
+        dgam2 = dbet2 = d_down_w = d_down_b = None
+    d_wdc, d_bdc = K.conv_wgrad(dy, z, precision=prec)
+    dz = K.conv_fwd(dy, _t(ctx["wdc"]), precision=prec)                                # [nb,t,v,3*cin]
+    dg_part = K.joint_gram(x, dz, groups=3, offa=0, stridea=0, offb=0, strideb=cin, width=cin, nchunk=ctx["nchunk"])
+    ds, d_adj_b = K.attention_bwd(dg_part, p, ctx["scale"])
+    if need_dx:
+        dx = K.joint_mix(dz, g, width=cin, mode=K.MIX_AGG_BWD, out=dx, accumulate=have)
+        have = True
+    de = K.joint_mix(e, ds, width=ci, mode=K.MIX_SCORE_BWD)
+    d_wab, d_bab = K.conv_wgrad(de, x, precision=prec)
+    if need_dx:
+        dx = K.conv_fwd(de, _t(ctx["wab"]), out=dx, accumulate=have, precision=prec)
+    # unpack
+    d_wa = [d_wab[(2 * k) * ci:(2 * k + 1) * ci].reshape(ci, cin, 1, 1) for k in range(3)]
+    d_wb = [d_wab[(2 * k + 1) * ci:(2 * k + 2) * ci].reshape(ci, cin, 1, 1) for k in range(3)]
+    d_ba = [d_bab[(2 * k) * ci:(2 * k + 1) * ci] for k in range(3)]
+    d_bb = [d_bab[(2 * k + 1) * ci:(2 * k + 2) * ci] for k in range(3)]
+    d_wd = [d_wdc[:, 0, k * cin:(k + 1) * cin].reshape(cout, cin, 1, 1) for k in range(3)]
+    d_bd = [d_bdc, d_bdc, d_bdc]
+    grads = dict(adj_b=d_adj_b, wa=d_wa, ba=d_ba, wb=d_wb, bb=d_bb, wd=d_wd, bd=d_bd, bn_w=dgam, bn_b=dbet,
+                 down_w=None if d_down_w is None else d_down_w.reshape(cout, cin, 1, 1), down_b=d_down_b,
+                 dbn_w=dgam2, dbn_b=dbet2)
+    return dx, grads
+
+
+# =============================================================================== tcn half
+def _pack_taps(w):
+    """[cout, cin, k, 1] -> [cout, k, cin]."""
+    return w.squeeze(-1).permute(0, 2, 1).contiguous()
+
+
+def tcn_forward(o, x_res, wt, bt, bn_w, bn_b, wr, br, rbn_w, rbn_b, spec: UnitSpec, ctx):
+    nb, t, v, c = o.shape
+    s, ksz = spec.stride, spec.kernel_size
+    pad = (ksz - 1) // 2
+    t_out = (t + 2 * pad - ksz) // s + 1
+    prec = spec.precision
+    wtp = _pack_taps(wt)
+    u = K.conv_fwd(o, wtp, bt, t_out=t_out, stride=s, pad=pad, precision=prec)
+    sc, sh, mean, invstd = _bn_forward(u, bn_w, bn_b, spec.bn_tcn, spec.training)
+    ur = mean2 = invstd2 = wrp = None
+    if spec.residual == "identity":
+        out = K.bn_apply(u, sc, sh, res_mode=K.RES_TENSOR, res=x_res, relu=spec.relu_out)
+    elif spec.residual == "conv":
+        wrp = _pack_taps(wr)
+        ur = K.conv_fwd(x_res, wrp, br, t_out=t_out, stride=s, pad=0, precision=prec)
+        sc2, sh2, mean2, invstd2 = _bn_forward(ur, rbn_w, rbn_b, spec.bn_res, spec.training)
+        out = K.bn_apply(u, sc, sh, res_mode=K.RES_AFFINE, res=ur, scale2=sc2, shift2=sh2, relu=spec.relu_out)
+    else:
+        out = K.bn_apply(u, sc, sh, relu=spec.relu_out)
+    if ctx is not None:
+        ctx.update(t_o=o.detach(), t_x=x_res, u=u, ur=ur, out=out.detach(), t_mean=mean, t_invstd=invstd, t_mean2=mean2, t_invstd2=invstd2,
+                   wtp=wtp, wrp=wrp, pad=pad)
+    return out
+
+
+def tcn_backward(d_out, ctx, bn_w, rbn_w, spec: UnitSpec, need_dres=True, need_do=True):
+    """Returns (d_o, d_xres, grads)."""
+    o, x_res, u, out = ctx["t_o"], ctx["t_x"], ctx["u"], ctx["out"]
+    s, pad, prec = spec.stride, ctx["pad"], spec.precision
+    ksz = spec.kernel_size
+    mask = out if spec.relu_out else None
+    d_xres = None
+    d_wr = d_br = dgam2 = dbet2 = None
+    if spec.residual == "identity":
+        d_xres = torch.empty_like(x_res) if need_dres else None
+        du, dgam, dbet = K.bn_bwd(d_out, mask, u, ctx["t_mean"], ctx["t_invstd"], bn_w, dres=d_xres, dres_accumulate=False)
+    elif spec.residual == "conv":
+        du, dgam, dbet = K.bn_bwd(d_out, mask, u, ctx["t_mean"], ctx["t_invstd"], bn_w)
+        dur, dgam2, dbet2 = K.bn_bwd(d_out, mask, ctx["ur"], ctx["t_mean2"], ctx["t_invstd2"], rbn_w)
+        d_wrp, d_br = K.conv_wgrad(dur, x_res, taps=1, stride=s, pad=0, precision=prec)
+        d_wr = d_wrp.permute(0, 2, 1).unsqueeze(-1)
+        if need_dres:
+            d_xres = K.conv_fwd(dur, _t(ctx["wrp"]), t_out=x_res.shape[1], stride=s, pad=0, transposed=True, precision=prec)
+    else:
+        du, dgam, dbet = K.bn_bwd(d_out, mask, u, ctx["t_mean"], ctx["t_invstd"], bn_w)
+    d_wtp, d_bt = K.conv_wgrad(du, o, taps=ksz, stride=s, pad=pad, precision=prec)
+    d_o = None
+    if need_do:
+        d_o = K.conv_fwd(du, _t(ctx["wtp"]), t_out=o.shape[1], stride=s, pad=pad, transposed=True, precision=prec)
+    grads = dict(wt=d_wtp.permute(0, 2, 1).unsqueeze(-1), bt=d_bt, bn_w=dgam, bn_b=dbet, wr=d_wr, br=d_br, rbn_w=dgam2, rbn_b=dbet2)
+    return d_o, d_xres, grads
+
+
+# =============================================================================== autograd wrappers
+GCN_NPARAMS = 1 + 1 + 18 + 2 + 4      # adj_a, adj_b, (wa,ba,wb,bb,wd,bd)x3, bn w/b, down w/b + its bn w/b
+TCN_NPARAMS = 4 + 4                   # wt, bt, bn w/b, wr, br, rbn w/b
+
+
+def _split_gcn(params):
+    adj_a, adj_b = params[0], params[1]
+    wa, ba, wb, bb, wd, bd = [], [], [], [], [], []
+    for k in range(3):
+        a = params[2 + 6 * k: 8 + 6 * k]
+        wa.append(a[0]); ba.append(a[1]); wb.append(a[2]); bb.append(a[3]); wd.append(a[4]); bd.append(a[5])
+    bn_w, bn_b, down_w, down_b, dbn_w, dbn_b = params[20:26]
+    return adj_a, adj_b, wa, ba, wb, bb, wd, bd, bn_w, bn_b, down_w, down_b, dbn_w, dbn_b
+
+
+def _gcn_grad_tuple(g):
+    out = [None, g["adj_b"]]
+    for k in range(3):
+        out += [g["wa"][k], g["ba"][k], g["wb"][k], g["bb"][k], g["wd"][k], g["bd"][k]]
+    out += [g["bn_w"], g["bn_b"], g["down_w"], g["down_b"], g["dbn_w"], g["dbn_b"]]
+    return out
+
+
+def _tcn_grad_tuple(g):
+    return [g["wt"], g["bt"], g["bn_w"], g["bn_b"], g["wr"], g["br"], g["rbn_w"], g["rbn_b"]]
+
+
+def _need_backward(spec):
+    if not spec.training:
+        raise NotImplementedError("fusion_gcn_b200: backward through eval-mode BatchNorm is not implemented "
+                                  "(use model.train() for training, torch.no_grad() for evaluation)")
+
+
+class GcnFn(torch.autograd.Function):
+    """SpatialGraphConv.forward (agcn.py:96-115) on a channels-last tensor."""
+
+    @staticmethod
+    def forward(ctx, x, spec, *params):
+        store = {}
+        o = gcn_forward(x, *_split_gcn(params), spec, store)
+        ctx.spec, ctx.store, ctx.params = spec, store, params
+        return o
+
+    @staticmethod
+    def backward(ctx, d_o):
+        spec, p = ctx.spec, ctx.params
+        _need_backward(spec)
+        dx, g = gcn_backward(d_o.contiguous(), ctx.store, p[20], p[24], p[22], spec, need_dx=ctx.needs_input_grad[0])
+        ctx.store = None
+        return (dx, None, *_gcn_grad_tuple(g))
+
+
+class TcnFn(torch.autograd.Function):
+    """TemporalConv.forward (agcn.py:49-51), optionally with the unit's residual add and ReLU (agcn.py:135-136)."""
+
+    @staticmethod
+    def forward(ctx, o, x_res, spec, *params):
+        store = {}
+        out = tcn_forward(o, x_res, *params, spec, store)
+        ctx.spec, ctx.store, ctx.params = spec, store, params
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        spec, p = ctx.spec, ctx.params
+        _need_backward(spec)
+        d_o, d_xres, g = tcn_backward(d_out.contiguous(), ctx.store, p[2], p[6], spec,
+                                      need_dres=ctx.needs_input_grad[1], need_do=ctx.needs_input_grad[0])
+        ctx.store = None
+        return (d_o, d_xres, None, *_tcn_grad_tuple(g))
+
+
+class UnitFn(torch.autograd.Function):
+    """SpatialTemporalConv.forward (agcn.py:134-136): relu(tcn1(gcn1(x)) + residual(x)), one autograd node so the
+    three gradient contributions to x are accumulated in place by the kernels."""
+
+    @staticmethod
+    def forward(ctx, x, spec, *params):
+        store = {}
+        gp, tp = params[:GCN_NPARAMS], params[GCN_NPARAMS:]
+        o = gcn_forward(x, *_split_gcn(gp), spec, store)
+        out = tcn_forward(o, x if spec.residual != "none" else None, *tp, spec, store)
+        ctx.spec, ctx.store, ctx.params = spec, store, params
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        spec, params = ctx.spec, ctx.params
+        _need_backward(spec)
+        gp, tp = params[:GCN_NPARAMS], params[GCN_NPARAMS:]
+        need_dx = ctx.needs_input_grad[0]
+        d_o, d_xres, tg = tcn_backward(d_out.contiguous(), ctx.store, tp[2], tp[6], spec, need_dres=need_dx, need_do=True)
+        dx, gg = gcn_backward(d_o, ctx.store, gp[20], gp[24], gp[22], spec, dx=d_xres, need_dx=need_dx)
+        ctx.store = None
+        return (dx, None, *_gcn_grad_tuple(gg), *_tcn_grad_tuple(tg))
+
+
+# =============================================================================== model-level pieces
+class DataBnFn(torch.autograd.Function):
+    """data_bn of Model.forward (agcn.py:186-188) without the two permute copies: the input (N,M,T,V,C) is already
+    channels-last, BatchNorm1d channel (m, v, c) has its statistics over (n, t)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, buf: BnBuffers, training: bool):
+        n, m, t, v, c = x.shape
+        vc = v * c
+        out = torch.empty_like(x)
+        saved = []
+        for mi in range(m):
+            sl = slice(mi * vc, (mi + 1) * vc)
+            rowmap = (n, t, m * t * vc, vc)
+            xv = x[:, mi]
+            sc, sh, mean, invstd = K.bn_stats(xv, gamma[sl], beta[sl], buf.running_mean[sl], buf.running_var[sl],
+                                              buf.num_batches_tracked if mi == 0 else None, BN_MOMENTUM, BN_EPS, training,
+                                              rowmap=rowmap)
+            K.bn_apply(xv, sc, sh, rowmap=rowmap, out=out[:, mi])
+            saved.append((mean, invstd))
+        ctx.x, ctx.gamma, ctx.saved, ctx.training = x, gamma, saved, training
+        return out.view(n * m, t, v, c)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        if not ctx.training:
+            raise NotImplementedError("fusion_gcn_b200: backward through eval-mode BatchNorm is not implemented")
+        x, gamma = ctx.x, ctx.gamma
+        n, m, t, v, c = x.shape
+        vc = v * c
+        d_out = d_out.contiguous().view(n, m, t, v, c)
+        need_dx = ctx.needs_input_grad[0]
+        dx = torch.empty_like(x) if need_dx else None
+        dgamma = torch.empty_like(gamma)
+        dbeta = torch.empty_like(gamma)
+        for mi in range(m):
+            sl = slice(mi * vc, (mi + 1) * vc)
+            rowmap = (n, t, m * t * vc, vc)
+            mean, invstd = ctx.saved[mi]
+            _, dg, db = K.bn_bwd(d_out[:, mi], None, x[:, mi], mean, invstd, gamma[sl], want_dy=need_dx,
+                                 dy=dx[:, mi] if need_dx else None, rowmap=rowmap)
+            dgamma[sl] = dg
+            dbeta[sl] = db
+        return dx, dgamma, dbeta, None, None
+
+
+class PoolFn(torch.autograd.Function):
+    """x.view(N, M, C, -1).mean(3).mean(1) (agcn.py:194-196) on a channels-last tensor [N*M, T, V, C] -> [N, C]."""
+
+    @staticmethod
+    def forward(ctx, x, groups: int):
+        ctx.shape = tuple(x.shape)
+        return K.pool_fwd(x, groups)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        return K.pool_bwd(d_out.contiguous(), ctx.shape), None
+
+
+class LinearFn(torch.autograd.Function):
+    """fc (agcn.py:198-199) through the same contraction kernel (rows = batch)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, precision: int):
+        n, cin = x.shape
+        ctx.save_for_backward(x, w)
+        ctx.precision = precision
+        y = K.conv_fwd(x.view(1, 1, n, cin), w.view(w.shape[0], 1, cin), b, precision=precision)
+        return y.view(n, w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        n, cin = x.shape
+        cout = w.shape[0]
+        dy4 = dy.contiguous().view(1, 1, n, cout)
+        dw, db = K.conv_wgrad(dy4, x.view(1, 1, n, cin), precision=ctx.precision)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = K.conv_fwd(dy4, _t(w.view(cout, 1, cin)), precision=ctx.precision).view(n, cin)
+        return dx, dw.view(cout, cin), db, None

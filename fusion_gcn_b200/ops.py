@@ -1,0 +1,217 @@
+"""Tensor-level wrappers over the C ABI (one function per entry point of include/agcn_b200.h).
+
+Every function takes/returns fp32 CUDA tensors in the channels-last activation layout
+``[nb, t, v, c]`` and launches on ``torch.cuda.current_stream()``.  PyTorch only provides the
+device memory and the stream.  ``oracle/stages.py`` restates each function in plain torch for
+the tests; nothing here falls back to it.
+"""
+from typing import Optional, Tuple
+
+import torch
+
+from . import capi
+from .capi import (MIX_AGG_BWD, MIX_AGG_FWD, MIX_SCORE_BWD, PREC_FP32, PREC_TF32, RES_AFFINE, RES_NONE,  # noqa: F401
+                   RES_TENSOR)
+
+NUM_SMS = 148
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _check(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("fusion_gcn_b200 kernels need CUDA tensors (there is no CPU path)")
+        if t.dtype != torch.float32:
+            raise RuntimeError(f"fp32 tensor expected, got {t.dtype}")
+        if not t.is_contiguous():
+            raise RuntimeError("contiguous tensor expected")
+
+
+def _check_strided(*tensors):
+    """Device / dtype check for tensors addressed through a rowmap (need not be contiguous)."""
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("fusion_gcn_b200 kernels need CUDA tensors (there is no CPU path)")
+        if t.dtype != torch.float32:
+            raise RuntimeError(f"fp32 tensor expected, got {t.dtype}")
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _call(name, *args):
+    capi.launch_count += 1
+    capi.check(getattr(capi.lib(), name)(*args), name)
+
+
+# ----------------------------------------------------------------------------- dense contractions
+def conv_fwd(x, w, bias=None, *, t_out=None, stride=1, pad=0, transposed=False, out=None, accumulate=False,
+             precision=PREC_FP32):
+    """x [nb,t_in,v,cin], w [cout,taps,cin] -> y [nb,t_out,v,cout]; see agcn_conv_fwd."""
+    nb, t_in, v, cin = x.shape
+    cout, taps, cin_w = w.shape
+    if cin_w != cin:
+        raise RuntimeError(f"conv_fwd: weight expects {cin_w} input channels, tensor has {cin}")
+    if t_out is None:
+        t_out = t_in
+    if out is None:
+        if accumulate:
+            raise RuntimeError("conv_fwd: accumulate needs an output tensor")
+        out = torch.empty((nb, t_out, v, cout), device=x.device, dtype=torch.float32)
+    elif tuple(out.shape) != (nb, t_out, v, cout):
+        raise RuntimeError(f"conv_fwd: out has shape {tuple(out.shape)}, expected {(nb, t_out, v, cout)}")
+    _check(x, w, bias, out)
+    _call("agcn_conv_fwd", _ptr(x), _ptr(w), _ptr(bias), _ptr(out), nb, t_in, t_out, v, cin, cout, taps, stride, pad,
+          int(transposed), int(accumulate), precision, _stream())
+    return out
+
+
+def conv_wgrad(dy, x, *, taps=1, stride=1, pad=0, want_bias=True, precision=PREC_FP32):
+    """dy [nb,t_out,v,cout], x [nb,t_in,v,cin] -> dw [cout,taps,cin], dbias [cout] | None."""
+    nb, t_out, v, cout = dy.shape
+    nb2, t_in, v2, cin = x.shape
+    if nb2 != nb or v2 != v:
+        raise RuntimeError("conv_wgrad: dy / x batch or joint mismatch")
+    _check(dy, x)
+    L = capi.lib()
+    ws_bytes = L.agcn_conv_wgrad_workspace_bytes(nb, t_in, t_out, v, cin, cout, taps)
+    ws = torch.empty((ws_bytes + 3) // 4, device=x.device, dtype=torch.float32)
+    dw = torch.empty((cout, taps, cin), device=x.device, dtype=torch.float32)
+    db = torch.empty((cout,), device=x.device, dtype=torch.float32) if want_bias else None
+    _call("agcn_conv_wgrad", _ptr(dy), _ptr(x), _ptr(dw), _ptr(db), nb, t_in, t_out, v, cin, cout, taps, stride, pad,
+          _ptr(ws), ws_bytes, precision, _stream())
+    return dw, db
+
+
+# ----------------------------------------------------------------------------- V x V attention
+def pick_nchunk(nb: int, t: int) -> int:
+    """Chunks of the t axis so that nb*nchunk CTAs cover the 148 SMs about four times."""
+    n = max(1, min((4 * NUM_SMS + nb - 1) // nb, max(1, t // 4)))
+    return min(n, t)
+
+
+def joint_gram(a, b, *, groups, offa, stridea, offb, strideb, width, nchunk):
+    nb, t, v, lda = a.shape
+    ldb = b.shape[3]
+    _check(a, b)
+    out = torch.empty((nb, nchunk, groups, v, v), device=a.device, dtype=torch.float32)
+    _call("agcn_joint_gram", _ptr(a), _ptr(b), _ptr(out), nb, t, v, lda, ldb, groups, offa, stridea, offb, strideb, width,
+          nchunk, _stream())
+    return out
+
+
+def attention_fwd(s_part, adj_a, adj_b, scale: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    nb, nchunk, groups, v, _ = s_part.shape
+    _check(s_part, adj_a, adj_b)
+    p = torch.empty((nb, groups, v, v), device=s_part.device, dtype=torch.float32)
+    g = torch.empty_like(p)
+    _call("agcn_attention_fwd", _ptr(s_part), _ptr(adj_a), _ptr(adj_b), _ptr(p), _ptr(g), nb, nchunk, groups, v, float(scale),
+          _stream())
+    return p, g
+
+
+def attention_bwd(dg_part, p, scale: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    nb, nchunk, groups, v, _ = dg_part.shape
+    _check(dg_part, p)
+    dg_sum = torch.empty_like(p)
+    ds = torch.empty_like(p)
+    dadj_b = torch.empty((groups, v, v), device=p.device, dtype=torch.float32)
+    _call("agcn_attention_bwd", _ptr(dg_part), _ptr(p), _ptr(dg_sum), _ptr(ds), _ptr(dadj_b), nb, nchunk, groups, v,
+          float(scale), _stream())
+    return ds, dadj_b
+
+
+def joint_mix(inp, mats, *, width, mode, out=None, accumulate=False):
+    nb, t, v, ldin = inp.shape
+    ldout = {MIX_AGG_FWD: 3 * width, MIX_AGG_BWD: width, MIX_SCORE_BWD: 6 * width}[mode]
+    if out is None:
+        if accumulate:
+            raise RuntimeError("joint_mix: accumulate needs an output tensor")
+        out = torch.empty((nb, t, v, ldout), device=inp.device, dtype=torch.float32)
+    _check(inp, mats, out)
+    _call("agcn_joint_mix", _ptr(inp), _ptr(mats), _ptr(out), nb, t, v, ldin, ldout, width, mode, int(accumulate), _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------- batch norm
+def _rowmap(x, rowmap):
+    """rowmap = (outer, inner, outer_stride, channels) or None for a plain [rows, channels] view."""
+    if rowmap is not None:
+        return rowmap
+    c = x.shape[-1]
+    return (1, x.numel() // c, 0, c)
+
+
+def _bn_ws(channels, device):
+    nbytes = capi.lib().agcn_bn_workspace_bytes(channels)
+    return torch.empty((nbytes + 3) // 4, device=device, dtype=torch.float32), nbytes
+
+
+def bn_stats(x, gamma, beta, running_mean, running_var, nbt, momentum, eps, training, rowmap=None):
+    """-> scale, shift, save_mean, save_invstd (each [channels]); running statistics updated in place."""
+    outer, inner, ostride, c = _rowmap(x, rowmap)
+    scale = torch.empty((4, c), device=x.device, dtype=torch.float32)
+    ws, nbytes = _bn_ws(c, x.device)
+    _check(gamma, beta, running_mean, running_var)
+    _check_strided(x)
+    if nbt is not None and nbt.dtype != torch.int64:
+        raise RuntimeError("num_batches_tracked must be int64")
+    _call("agcn_bn_stats", x.data_ptr(), outer, inner, ostride, c, _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var),
+          _ptr(nbt), float(momentum), float(eps), int(training), scale[0].data_ptr(), scale[1].data_ptr(),
+          scale[2].data_ptr(), scale[3].data_ptr(), _ptr(ws), nbytes, _stream())
+    return scale[0], scale[1], scale[2], scale[3]
+
+
+def bn_apply(y, scale, shift, *, res_mode=RES_NONE, res=None, scale2=None, shift2=None, relu=False, rowmap=None, out=None):
+    outer, inner, ostride, c = _rowmap(y, rowmap)
+    if out is None:
+        out = torch.empty_like(y)
+    _check_strided(y, res, out)
+    _check(scale, shift, scale2, shift2)
+    _call("agcn_bn_apply", y.data_ptr(), _ptr(scale), _ptr(shift), res_mode, _ptr(res), _ptr(scale2), _ptr(shift2), int(relu),
+          out.data_ptr(), outer, inner, ostride, c, _stream())
+    return out
+
+
+def bn_bwd(dout, mask_out, y, save_mean, save_invstd, gamma, *, want_dy=True, dy=None, dres=None, dres_accumulate=False,
+           rowmap=None):
+    """-> dy | None, dgamma, dbeta; optionally writes / accumulates the masked gradient into ``dres``.
+    ``dy`` may be a preallocated tensor addressed with the same rowmap as ``y``."""
+    outer, inner, ostride, c = _rowmap(y, rowmap)
+    if want_dy and dy is None:
+        dy = torch.empty_like(y)
+    _check_strided(dout, mask_out, y, dy, dres)
+    _check(save_mean, save_invstd, gamma)
+    dgb = torch.empty((2, c), device=y.device, dtype=torch.float32)
+    ws, nbytes = _bn_ws(c, y.device)
+    _call("agcn_bn_bwd", dout.data_ptr(), _ptr(mask_out), y.data_ptr(), _ptr(save_mean), _ptr(save_invstd), _ptr(gamma),
+          _ptr(dy), dgb[0].data_ptr(), dgb[1].data_ptr(), _ptr(dres), int(dres_accumulate), outer, inner, ostride, c,
+          _ptr(ws), nbytes, _stream())
+    return dy, dgb[0], dgb[1]
+
+
+# ----------------------------------------------------------------------------- pooling
+def pool_fwd(x, groups: int):
+    c = x.shape[-1]
+    rows = x.numel() // c // groups
+    _check(x)
+    out = torch.empty((groups, c), device=x.device, dtype=torch.float32)
+    _call("agcn_pool_fwd", _ptr(x), _ptr(out), groups, rows, c, _stream())
+    return out
+
+
+def pool_bwd(dout, shape):
+    groups, c = dout.shape
+    dx = torch.empty(shape, device=dout.device, dtype=torch.float32)
+    rows = dx.numel() // c // groups
+    _check(dout)
+    _call("agcn_pool_bwd", _ptr(dout), _ptr(dx), groups, rows, c, _stream())
+    return dx

@@ -1,0 +1,151 @@
+/*
+ * agcn_b200.h -- C ABI of the B200-native AGCN / MMARGCN hot path (libagcn_b200.so).
+ *
+ * The reference (mduhme/fusion-gcn) is pure Python on top of ATen; it has no FFI of its own.
+ * The boundary this library replaces is therefore the set of ATen calls made by
+ *   torch_src/models/mmargcn/agcn.py:37-136  (TemporalConv, SpatialGraphConv, SpatialTemporalConv)
+ *   torch_src/models/agcn/agcn.py:38-133     (unit_tcn, unit_gcn, TCN_GCN_unit)
+ *   torch_src/models/mmargcn/agcn.py:183-200 (Model.forward: data_bn, pooling, fc)
+ * Each entry point below cites the reference lines whose arithmetic it performs.  A maintainer
+ * binds them with ctypes; fusion_gcn_b200/capi.py is that binding.
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer to fp32 data owned by the caller (PyTorch); the library
+ *     borrows it for the duration of the stream-ordered call.  It never allocates, never
+ *     synchronises the device and never changes the current device.  Scratch space is passed in as
+ *     (workspace, workspace_bytes); the *_workspace_bytes functions say how much is needed.
+ *   - Activations are channels-last: x[nb][t][v][c], c contiguous.  nb = N*M person-sequences.
+ *     "rows" means the flattened (nb, t, v) index.
+ *   - `stream` is a cudaStream_t passed as void*.
+ *   - Return value: 0 on success, otherwise an agcn_status code; agcn_last_error_string() gives a
+ *     thread-local description.  Entry points are thread-safe (no global mutable state other than
+ *     the thread-local error string) and CUDA-graph-capture safe (no allocation, no host sync).
+ *   - `precision`: AGCN_PREC_FP32 = exact fp32 FFMA (parity mode, <=1e-4 vs the reference);
+ *     AGCN_PREC_TF32 = tcgen05 kind::tf32 tensor-core path (own tolerance, reported separately).
+ */
+#ifndef AGCN_B200_H
+#define AGCN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    AGCN_OK = 0,
+    AGCN_ERR_BAD_SHAPE = 1,    /* non-positive or inconsistent dimensions                       */
+    AGCN_ERR_UNSUPPORTED = 2,  /* valid but outside what the kernels cover (e.g. V > 32)         */
+    AGCN_ERR_MISALIGNED = 3,   /* pointer not aligned for the vector width the shape implies     */
+    AGCN_ERR_WORKSPACE = 4,    /* workspace_bytes smaller than *_workspace_bytes(...)            */
+    AGCN_ERR_CUDA = 5,         /* a CUDA runtime call or launch failed                           */
+    AGCN_ERR_NULL = 6          /* required pointer is NULL                                       */
+} agcn_status;
+
+typedef enum { AGCN_PREC_FP32 = 0, AGCN_PREC_TF32 = 1 } agcn_precision;
+
+/* joint-mix modes (agcn_joint_mix) */
+typedef enum {
+    AGCN_MIX_AGG_FWD = 0,   /* out[.,v,k*w+c]  = sum_u in[.,u,c]      * mat[nb,k,u,v]     (agcn.py:110 forward)  */
+    AGCN_MIX_AGG_BWD = 1,   /* out[.,u,c]     (+)= sum_k sum_v in[.,v,k*w+c] * mat[nb,k,u,v] (its input gradient) */
+    AGCN_MIX_SCORE_BWD = 2  /* in = [theta_0,phi_0,theta_1,...] (6 groups of w), mat = dS:
+                               dtheta_k[.,u,c] = sum_v mat[k,u,v]*phi_k[.,v,c];  dphi_k[.,v,c] = sum_u mat[k,u,v]*theta_k[.,u,c]
+                               (gradient of agcn.py:104-106)                                                     */
+} agcn_mix_mode;
+
+/* residual modes of agcn_bn_apply */
+typedef enum { AGCN_RES_NONE = 0, AGCN_RES_TENSOR = 1, AGCN_RES_AFFINE = 2 } agcn_res_mode;
+
+int agcn_version(void);
+const char* agcn_last_error_string(void);
+
+/* ---- dense contractions over the channel dimension ------------------------------------------------
+ * Implicit GEMM with an optional temporal tap structure:
+ *   y[nb][to][v][co] (+)= bias[co] + sum_{tap<taps} sum_{ci<cin} x[nb][ti(to,tap)][v][ci] * w[co][tap][ci]
+ *   forward gather    (transposed=0): ti = stride*to + tap - pad
+ *   transposed gather (transposed=1): ti = (to + pad - tap)/stride, used only when divisible
+ * out-of-range ti contribute zero.  x: [nb][t_in][v][cin], y: [nb][t_out][v][cout], w: [cout][taps][cin].
+ * Replaces nn.Conv2d forward / input-gradient at agcn.py:41-42 (9x1 temporal conv, residual 1x1 with
+ * stride), :71-73 (conv_a / conv_b / conv_d 1x1), :77 (down) and nn.Linear at :178 (taps=1, v=1, t=1).
+ * bias may be NULL.  accumulate!=0 adds into y instead of overwriting it.                              */
+int agcn_conv_fwd(const float* x, const float* w, const float* bias, float* y,
+                  int nb, int t_in, int t_out, int v, int cin, int cout,
+                  int taps, int stride, int pad, int transposed, int accumulate,
+                  int precision, void* stream);
+
+/* Weight / bias gradient of the forward-gather contraction above:
+ *   dw[co][tap][ci] = sum_rows dy[nb][to][v][co] * x[nb][stride*to+tap-pad][v][ci];   dbias[co] = sum_rows dy
+ * Deterministic (two-phase split reduction, no atomics).  dbias may be NULL.                            */
+size_t agcn_conv_wgrad_workspace_bytes(int nb, int t_in, int t_out, int v, int cin, int cout, int taps);
+int agcn_conv_wgrad(const float* dy, const float* x, float* dw, float* dbias,
+                    int nb, int t_in, int t_out, int v, int cin, int cout,
+                    int taps, int stride, int pad,
+                    void* workspace, size_t workspace_bytes, int precision, void* stream);
+
+/* ---- joint x joint products (the V x V attention) --------------------------------------------------
+ * out[nb][chunk][g][u][v] = sum_{t in chunk} sum_{c<width} a[nb][t][u][offa+g*stridea+c] * b[nb][t][v][offb+g*strideb+c]
+ * a: [nb][t][v][lda], b: [nb][t][v][ldb].  The t axis is split into nchunk contiguous chunks so that a
+ * grid of nb*nchunk CTAs fills the GPU; the consumer sums the chunks in a fixed order.
+ * Used for the score theta^T phi (agcn.py:104-106, a = b = [theta|phi] embedding) and for
+ * dG = X^T dZ (gradient of agcn.py:110).  V <= 32.                                                     */
+int agcn_joint_gram(const float* a, const float* b, float* out,
+                    int nb, int t, int v, int lda, int ldb, int groups,
+                    int offa, int stridea, int offb, int strideb, int width, int nchunk, void* stream);
+
+/* p[nb][k][:, v] = softmax_u(scale * sum_chunk s_part[nb][chunk][k][u][v]);  g = p + adj_a[k] + adj_b[k]
+ * (agcn.py:98-100,106-108; softmax over dim -2, i.e. columns sum to one).                               */
+int agcn_attention_fwd(const float* s_part, const float* adj_a, const float* adj_b, float* p, float* g,
+                       int nb, int nchunk, int groups, int v, float scale, void* stream);
+
+/* dG = sum_chunk dg_part;  ds = scale * p * (dG - colsum_u(p*dG));  dadj_b[k] = sum_nb dG[nb][k]
+ * dg_sum: [nb][k][v][v] scratch output (the summed dG).                                                 */
+int agcn_attention_bwd(const float* dg_part, const float* p, float* dg_sum, float* ds, float* dadj_b,
+                       int nb, int nchunk, int groups, int v, float scale, void* stream);
+
+/* Per-sample mixing over the joint axis, see agcn_mix_mode.  in: [nb][t][v][ldin], out: [nb][t][v][ldout],
+ * mats: [nb][3][v][v], width = channels per group.  V <= 32.                                            */
+int agcn_joint_mix(const float* in, const float* mats, float* out,
+                   int nb, int t, int v, int ldin, int ldout, int width, int mode, int accumulate, void* stream);
+
+/* ---- BatchNorm (training-mode batch statistics; nn.BatchNorm2d/1d at agcn.py:44,78,83,150) ----------
+ * The tensor is addressed as x[outer][inner][c] with element offset outer*outer_stride + inner*c_total...
+ * precisely: offset(o, i, ch) = o*outer_stride + i*channels + ch, rows = outer*inner.  For unit tensors
+ * outer=1... (outer_stride ignored when outer==1); data_bn uses outer=N, inner=T, channels=V*C per body.
+ *
+ * training!=0: batch mean / biased variance over rows (eps as given), running statistics updated in
+ *   place with `momentum` and the unbiased variance, *num_batches_tracked incremented (may be NULL).
+ * training==0: scale/shift from the running statistics.
+ * Outputs: scale[c] = gamma*invstd, shift[c] = beta - mean*scale, save_mean[c], save_invstd[c].          */
+size_t agcn_bn_workspace_bytes(int channels);
+int agcn_bn_stats(const float* x, int outer, int inner, long long outer_stride, int channels,
+                  const float* gamma, const float* beta, float* running_mean, float* running_var,
+                  long long* num_batches_tracked, float momentum, float eps, int training,
+                  float* scale, float* shift, float* save_mean, float* save_invstd,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* out = act(scale*y + shift + R),  R = 0 | res | scale2*res + shift2;  act = ReLU when relu!=0.
+ * (agcn.py:113-115 and :135-136).  Same addressing as agcn_bn_stats for y / res / out.                   */
+int agcn_bn_apply(const float* y, const float* scale, const float* shift,
+                  int res_mode, const float* res, const float* scale2, const float* shift2,
+                  int relu, float* out, int outer, int inner, long long outer_stride, int channels, void* stream);
+
+/* BatchNorm backward through an optional ReLU mask:
+ *   g = dout * [mask_out > 0]  (g = dout when mask_out == NULL)
+ *   dbeta = sum g;  dgamma = sum g*xhat;  dy = gamma*invstd*(g - dbeta/m - xhat*dgamma/m),  xhat = (y-mean)*invstd
+ * If dres != NULL the masked gradient g is also written (dres_accumulate==0) or added to dres
+ * (gradient of an identity residual / of the tensor R above).  dy may be NULL (only sums wanted).       */
+int agcn_bn_bwd(const float* dout, const float* mask_out, const float* y,
+                const float* save_mean, const float* save_invstd, const float* gamma,
+                float* dy, float* dgamma, float* dbeta, float* dres, int dres_accumulate,
+                int outer, int inner, long long outer_stride, int channels,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- pooling (agcn.py:194-196): out[g][c] = mean over rows_per_group rows of x[g][row][c] ------------ */
+int agcn_pool_fwd(const float* x, float* out, int groups, int rows_per_group, int channels, void* stream);
+int agcn_pool_bwd(const float* dout, float* dx, int groups, int rows_per_group, int channels, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGCN_B200_H */

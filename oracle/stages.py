@@ -1,0 +1,209 @@
+"""TEST INFRASTRUCTURE ONLY -- plain-torch restatement of every entry point of
+include/agcn_b200.h, with the signatures of ``fusion_gcn_b200/ops.py``.
+
+Two uses, both from ``tests/``:
+  * ``-m gpu``: each CUDA kernel is compared with its function here on the same inputs;
+  * ``-m "not gpu"``: the tests swap this module in for ``fusion_gcn_b200.functional.K`` so the
+    host-side composition (forward order, every backward formula, parameter packing, state-dict
+    handling) is checked against ``oracle/agcn_oracle.py`` / the golden fixtures on CPU.
+The package itself never imports this file.  Works in fp32 or fp64 (dtype follows the inputs).
+
+Maths: SURVEY.md Appendix A; reference lines torch_src/models/mmargcn/agcn.py:37-51,96-115,134-136.
+"""
+import torch
+
+PREC_FP32, PREC_TF32 = 0, 1
+MIX_AGG_FWD, MIX_AGG_BWD, MIX_SCORE_BWD = 0, 1, 2
+RES_NONE, RES_TENSOR, RES_AFFINE = 0, 1, 2
+NUM_SMS = 148
+
+
+def _gather_index(t_in, t_out, taps, stride, pad, transposed, device):
+    """[t_out, taps] input time index, -1 where the tap falls outside / is not divisible."""
+    to = torch.arange(t_out, device=device).view(-1, 1)
+    tap = torch.arange(taps, device=device).view(1, -1)
+    if not transposed:
+        ti = stride * to + tap - pad
+        ok = (ti >= 0) & (ti < t_in)
+    else:
+        num = to + pad - tap
+        ok = (num >= 0) & (num % stride == 0)
+        ti = torch.div(num, stride, rounding_mode="floor")
+        ok = ok & (ti < t_in)
+    return torch.where(ok, ti, torch.full_like(ti, -1))
+
+
+def _gathered(x, t_out, taps, stride, pad, transposed):
+    """x [nb,t_in,v,c] -> [nb,t_out,taps,v,c] with zeros for invalid taps."""
+    nb, t_in, v, c = x.shape
+    idx = _gather_index(t_in, t_out, taps, stride, pad, transposed, x.device)
+    xp = torch.cat([x, x.new_zeros(nb, 1, v, c)], dim=1)           # index -1 -> zero row
+    return xp[:, idx.reshape(-1)].reshape(nb, t_out, taps, v, c)
+
+
+def conv_fwd(x, w, bias=None, *, t_out=None, stride=1, pad=0, transposed=False, out=None, accumulate=False,
+             precision=PREC_FP32):
+    nb, t_in, v, cin = x.shape
+    cout, taps, _ = w.shape
+    t_out = t_in if t_out is None else t_out
+    g = _gathered(x, t_out, taps, stride, pad, transposed)
+    y = torch.einsum("ntkvc,okc->ntvo", g, w)
+    if bias is not None:
+        y = y + bias
+    if out is None:
+        return y.contiguous()
+    if accumulate:
+        out += y
+    else:
+        out.copy_(y)
+    return out
+
+
+def conv_wgrad(dy, x, *, taps=1, stride=1, pad=0, want_bias=True, precision=PREC_FP32):
+    t_out = dy.shape[1]
+    g = _gathered(x, t_out, taps, stride, pad, False)
+    dw = torch.einsum("ntvo,ntkvc->okc", dy, g).contiguous()
+    db = dy.sum(dim=(0, 1, 2)) if want_bias else None
+    return dw, db
+
+
+def pick_nchunk(nb, t):
+    n = max(1, min((4 * NUM_SMS + nb - 1) // nb, max(1, t // 4)))
+    return min(n, t)
+
+
+def joint_gram(a, b, *, groups, offa, stridea, offb, strideb, width, nchunk):
+    nb, t, v, _ = a.shape
+    t_per = (t + nchunk - 1) // nchunk
+    out = a.new_zeros(nb, nchunk, groups, v, v)
+    for c in range(nchunk):
+        t0, t1 = c * t_per, min(t, (c + 1) * t_per)
+        if t0 >= t1:
+            continue
+        for g in range(groups):
+            aa = a[:, t0:t1, :, offa + g * stridea: offa + g * stridea + width]
+            bb = b[:, t0:t1, :, offb + g * strideb: offb + g * strideb + width]
+            out[:, c, g] = torch.einsum("ntuc,ntvc->nuv", aa, bb)
+    return out
+
+
+def attention_fwd(s_part, adj_a, adj_b, scale):
+    s = s_part.sum(dim=1) * scale
+    p = torch.softmax(s, dim=-2)
+    return p.contiguous(), (p + adj_a + adj_b).contiguous()
+
+
+def attention_bwd(dg_part, p, scale):
+    dg = dg_part.sum(dim=1)
+    dot = (p * dg).sum(dim=-2, keepdim=True)
+    ds = scale * p * (dg - dot)
+    return ds.contiguous(), dg.sum(dim=0).contiguous()
+
+
+def joint_mix(inp, mats, *, width, mode, out=None, accumulate=False):
+    nb, t, v, _ = inp.shape
+    w = width
+    if mode == MIX_AGG_FWD:
+        res = torch.einsum("ntuc,nkuv->ntvkc", inp, mats).reshape(nb, t, v, 3 * w)
+    elif mode == MIX_AGG_BWD:
+        res = torch.einsum("ntvkc,nkuv->ntuc", inp.reshape(nb, t, v, 3, w), mats)
+    elif mode == MIX_SCORE_BWD:
+        e = inp.reshape(nb, t, v, 3, 2, w)
+        theta, phi = e[..., 0, :], e[..., 1, :]                       # [nb,t,v,3,w]
+        dtheta = torch.einsum("nkuv,ntvkc->ntukc", mats, phi)
+        dphi = torch.einsum("nkuv,ntukc->ntvkc", mats, theta)
+        res = torch.stack([dtheta, dphi], dim=4).reshape(nb, t, v, 6 * w)
+    else:
+        raise RuntimeError("unknown mode")
+    if out is None:
+        return res.contiguous()
+    if accumulate:
+        out += res
+    else:
+        out.copy_(res)
+    return out
+
+
+def _rows_view(x, rowmap):
+    """[..., channels] view honouring rowmap = (outer, inner, outer_stride, channels)."""
+    if rowmap is None:
+        return x.view(-1, x.shape[-1])
+    outer, inner, ostride, c = rowmap
+    return torch.as_strided(x, (outer, inner, c), (ostride if outer > 1 else inner * c, c, 1), x.storage_offset())
+
+
+def bn_stats(x, gamma, beta, running_mean, running_var, nbt, momentum, eps, training, rowmap=None):
+    xv = _rows_view(x, rowmap)
+    xv = xv.reshape(-1, xv.shape[-1])
+    m = xv.shape[0]
+    if training:
+        mean = xv.mean(dim=0)
+        var = xv.var(dim=0, unbiased=False)
+        if running_mean is not None:
+            unbiased = var * m / (m - 1) if m > 1 else var
+            running_mean.mul_(1 - momentum).add_(momentum * mean.to(running_mean.dtype))
+            running_var.mul_(1 - momentum).add_(momentum * unbiased.to(running_var.dtype))
+        if nbt is not None:
+            nbt += 1
+    else:
+        mean, var = running_mean.to(x.dtype), running_var.to(x.dtype)
+    invstd = torch.rsqrt(var + eps)
+    g = gamma if gamma is not None else torch.ones_like(mean)
+    b = beta if beta is not None else torch.zeros_like(mean)
+    scale = g * invstd
+    return scale, b - mean * scale, mean, invstd
+
+
+def bn_apply(y, scale, shift, *, res_mode=RES_NONE, res=None, scale2=None, shift2=None, relu=False, rowmap=None, out=None):
+    if out is None:
+        out = torch.empty_like(y)
+    yv = _rows_view(y, rowmap)
+    o = yv * scale + shift
+    if res_mode == RES_TENSOR:
+        o = o + _rows_view(res, rowmap)
+    elif res_mode == RES_AFFINE:
+        o = o + _rows_view(res, rowmap) * scale2 + shift2
+    if relu:
+        o = torch.relu(o)
+    _rows_view(out, rowmap).copy_(o)
+    return out
+
+
+def bn_bwd(dout, mask_out, y, save_mean, save_invstd, gamma, *, want_dy=True, dy=None, dres=None, dres_accumulate=False,
+           rowmap=None):
+    g = _rows_view(dout, rowmap)
+    if mask_out is not None:
+        g = g * (_rows_view(mask_out, rowmap) > 0).to(g.dtype)
+    yv = _rows_view(y, rowmap)
+    c = yv.shape[-1]
+    xhat = (yv - save_mean) * save_invstd
+    red = tuple(range(g.dim() - 1))
+    m = g.numel() // c
+    dbeta = g.sum(dim=red)
+    dgamma = (g * xhat).sum(dim=red)
+    if want_dy:
+        gam = gamma if gamma is not None else torch.ones_like(save_mean)
+        if dy is None:
+            dy = torch.empty_like(y)
+        _rows_view(dy, rowmap).copy_(gam * save_invstd * (g - dbeta / m - xhat * dgamma / m))
+    if dres is not None:
+        dv = _rows_view(dres, rowmap)
+        if dres_accumulate:
+            dv += g
+        else:
+            dv.copy_(g)
+    return dy, dgamma, dbeta
+
+
+def pool_fwd(x, groups):
+    c = x.shape[-1]
+    return x.reshape(groups, -1, c).mean(dim=1)
+
+
+def pool_bwd(dout, shape):
+    groups, c = dout.shape
+    rows = 1
+    for s in shape:
+        rows *= s
+    rows = rows // c // groups
+    return (dout / rows).reshape(groups, 1, c).expand(groups, rows, c).reshape(shape).contiguous()
