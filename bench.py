@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""AGCN fwd+bwd sequences/s on B200 (BASELINE.json metric), one process per GPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ntu|utd|mmact_imu|utd_rgb]
+  torchrun ... bench.py --gpus N ...        (N > 1: batch-sharded replicas + NCCL gradient all-reduce)
+
+A step = zero_grad + forward + cross-entropy + backward (+ gradient all-reduce when N > 1) of the full 10-unit AGCN
+model on one synthetic batch; the optimizer step is excluded.  Default workload: BASELINE configs[1], the
+2s-AGCN joint stream at NTU shape (64 sequences per GPU, M=2, T=300, V=25, C=3, 60 classes), train mode, fp32 parity mode.
+Rank 0 prints ONE JSON line (see the task contract): value = device-resident throughput, e2e = through the public
+module API from pinned HOST buffers with the H2D/D2H copies inside the timed region, roofline = the dominant kernel
+timed live with CUDA events, cpu_baseline = the oracle port of the reference on the host cores (bounded sample).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {   # name: (M, T, V, C, classes, graph)
+    "ntu": (2, 300, 25, 3, 60, "ntu"),
+    "utd": (1, 100, 20, 3, 27, "utd"),
+    "mmact_imu": (2, 300, 22, 3, 35, "mmact_imu"),
+    "utd_rgb": (1, 100, 25, 515, 27, "ntu"),
+}
+# algorithmic work per sequence, fwd+bwd: GFLOP and MB (model M1, fp32 activations)
+WORK = {"ntu": (116.44, 1441.0), "utd": (15.39, 192.0), "mmact_imu": (101.92, 1268.0), "utd_rgb": (22.69, 271.0)}
+
+
+def make_graph(kind):
+    from fusion_gcn_b200 import graph as G
+    if kind == "ntu":
+        return G.SkeletonGraph(G.NTU_EDGES, center_joint=G.NTU_CENTER)
+    if kind == "utd":
+        return G.SkeletonGraph(G.UTD_EDGES, center_joint=G.UTD_CENTER)
+    return G.imu_fusion_graph(G.SkeletonGraph(G.MMACT_EDGES, center_joint=G.MMACT_CENTER), 4, "append_center")
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained"),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_model(workload, precision, device):
+    from fusion_gcn_b200 import modules as M
+    m, t, v, c, ncls, gk = WORKLOADS[workload]
+    torch.manual_seed(1)
+    model = M.Model((m, t, v, c), ncls, make_graph(gk))
+    M.set_precision(model, precision)
+    return model.to(device).train()
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from fusion_gcn_b200 import capi, ops
+    from fusion_gcn_b200.distributed import GradientAllReducer
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch N>1 with torch.distributed.run")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    m, t, v, c, ncls, _ = WORKLOADS[args.workload]
+    n_local = args.batch                      # weak scaling: fixed per-GPU batch
+    model = build_model(args.workload, args.precision, dev)
+    reducer = GradientAllReducer(model.parameters()) if world > 1 else None
+    gen = torch.Generator().manual_seed(1234 + rank)
+    x_host = torch.randn(n_local, m, t, v, c, generator=gen).pin_memory()
+    y_host = torch.randint(ncls, (n_local,), generator=gen).pin_memory()
+    x_dev, y_dev = x_host.to(dev), y_host.to(dev)
+    loss_fn = torch.nn.CrossEntropyLoss()
+
+    def step(x, y):
+        model.zero_grad(set_to_none=True)
+        loss = loss_fn(model(x), y)
+        loss.backward()
+        if reducer is not None:
+            reducer()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(x_dev, y_dev)
+    # ---- device-resident timed region, with per-launch CUDA events on the conv entry points (roofline evidence)
+    ops.start_timing(("agcn_conv_fwd", "agcn_conv_wgrad"))
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    l0 = capi.lib().agcn_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(x_dev, y_dev)
+    e1.record()
+    barrier()
+    launches = capi.lib().agcn_launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    timings = ops.stop_timing()
+    ms = e0.elapsed_time(e1)
+    # ---- end-to-end: host pinned buffers -> device every step, loss read back every step
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        xb = x_host.to(dev, non_blocking=True)
+        yb = y_host.to(dev, non_blocking=True)
+        loss_val = step(xb, yb).item()
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    t_all = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t_all[0]), float(t_all[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    n_global = n_local * world
+    value = n_global * args.steps / (ms / 1e3)
+    e2e_value = n_global * args.steps / (ms_e2e / 1e3)
+    # dominant kernel: the conv launch signature with the largest summed device time
+    roof = None
+    if timings:
+        key, (tot_ms, cnt) = max(timings.items(), key=lambda kv: kv[1][0])
+        name, nb, t_in, t_out, vv, cin, cout, taps = key
+        flops = 2.0 * nb * t_out * vv * cin * cout * taps
+        avg_s = tot_ms / cnt / 1e3
+        achieved = flops / avg_s / 1e12
+        peak = pk["bf16_tflops_sustained"] or pk["bf16_tflops"]
+        roof = {"bound": "tensor", "achieved": round(achieved, 3), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 5),
+                "traffic": None, "kernel": f"{name}[nb={nb},t={t_in}->{t_out},v={vv},cin={cin},cout={cout},taps={taps}]",
+                "avg_launch_ms": round(avg_s * 1e3, 4), "launches_timed": cnt, "share_of_step": round(tot_ms / ms, 4),
+                "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
+                "note": "fp32 parity mode runs this contraction on FFMA; the tensor-core peak is the denominator by contract"}
+    gflop, mbytes = WORK[args.workload]
+    line = {
+        "metric": "AGCN fwd+bwd sequences/sec", "value": round(value, 2), "unit": "sequences/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "tf32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: AGCN 10 units, N={n_local}/GPU (global {n_global}), M={m}, T={t}, V={v}, C={c}, "
+                               f"{ncls} classes, train mode, fwd+CE+bwd, random init", "precision_mode": args.precision,
+                   "l2_policy": "activations per step (GBs) exceed the 126 MB L2; no explicit flush",
+                   "parallelism": f"dp{world} (batch shards, NCCL gradient all-reduce)" if world > 1 else "single GPU"},
+        "e2e": {"value": round(e2e_value, 2), "unit": "sequences/s", "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8,
+                "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3), "last_loss": round(loss_val, 5)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roof,
+        "model_roofline": {"hbm_seq_s": round(pk["hbm_gbs"] * 1e3 / mbytes, 1), "achieved_frac_of_hbm_ceiling": round(value / world / (pk["hbm_gbs"] * 1e3 / mbytes), 4),
+                           "algorithmic_gflop_per_seq": gflop, "algorithmic_mb_per_seq": mbytes,
+                           "achieved_tflops": round(value * gflop / 1e3, 2), "achieved_gbs": round(value / world * mbytes / 1e3, 1)},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_reference(args.workload, steps=3, warmup=1)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_reference(workload, steps, warmup, n=None):
+    """The reference's CPU path on the host cores: oracle/agcn_oracle.py (a port that calls the same ATen ops as
+    torch_src/models/mmargcn/agcn.py; the Python reference itself cannot travel to the GPU box), all host threads,
+    bounded sample of the same workload (N=4 sequences per step at NTU/MMAct shape, N=16 at UTD shape)."""
+    from oracle import agcn_oracle as O
+    from fusion_gcn_b200 import graph as G
+    m, t, v, c, ncls, gk = WORKLOADS[workload]
+    n = n or (16 if t * v * m <= 4000 else 4)
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    adj = G.adjacency_from_graph(make_graph(gk))
+    p = O.as_leaves(O.init_state(adj, (m, t, v, c), ncls, seed=1))
+    gen = torch.Generator().manual_seed(1234)
+    x = torch.randn(n, m, t, v, c, generator=gen)
+    y = torch.randint(ncls, (n,), generator=gen)
+    leaves = [a for a in p.values() if a.requires_grad]
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        for a in leaves:
+            a.grad = None
+        loss = torch.nn.functional.cross_entropy(O.model_forward(x, p, c, True), y)
+        loss.backward()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return {"value": round(n * len(times) / total, 3), "unit": "sequences/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{len(times)} steps of N={n} sequences at the {workload} shape (same model, fwd+CE+bwd, fp32, train mode)",
+            "ms_per_step": round(total / len(times) * 1e3, 1)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    m, t, v, c, ncls, _ = WORKLOADS[args.workload]
+    steps = max(1, min(args.steps, 5))
+    base = cpu_reference(args.workload, steps=steps, warmup=max(1, min(args.warmup, 2)))
+    line = {"impl": "reference", "metric": "AGCN fwd+bwd sequences/sec", "value": base["value"], "unit": "sequences/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": base["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: AGCN 10 units, M={m}, T={t}, V={v}, C={c}, {ncls} classes, train mode, fwd+CE+bwd; "
+                                   "reference CPU path (oracle port) on the host cores, bounded sample"},
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ntu", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=64, help="sequences per GPU")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -22,6 +22,7 @@ _c_int, _c_ll, _c_float, _c_void_p, _c_size_t = ctypes.c_int, ctypes.c_longlong,
 SIGNATURES = {
     "agcn_version": (_c_int, []),
     "agcn_last_error_string": (ctypes.c_char_p, []),
+    "agcn_launch_count": (_c_ll, []),
     "agcn_conv_fwd": (_c_int, [_c_void_p] * 4 + [_c_int] * 12 + [_c_void_p]),
     "agcn_conv_wgrad_workspace_bytes": (_c_size_t, [_c_int] * 7),
     "agcn_conv_wgrad": (_c_int, [_c_void_p] * 4 + [_c_int] * 9 + [_c_void_p, _c_size_t, _c_int, _c_void_p]),
@@ -40,7 +41,7 @@ SIGNATURES = {
 
 _lock = threading.Lock()
 _lib = None
-launch_count = 0          # kernels-entry calls issued through this binding (bench.py reports it)
+launch_count = 0          # C-ABI calls issued through this binding; kernel launches: lib().agcn_launch_count()
 
 
 def lib():

@@ -323,7 +323,7 @@ static int elementwise_blocks(long long work_items) {
 
 using namespace agcn;
 
-extern "C" size_t agcn_bn_workspace_bytes(int channels) {
+extern "C" AGCN_API size_t agcn_bn_workspace_bytes(int channels) {
     if (channels <= 0) return 0;
     // partial sums [kMaxPartials][2][C] followed by the backward coefficients [4][C]
     return ((size_t)kMaxPartials * 2 + 4) * (size_t)channels * sizeof(float);
@@ -335,7 +335,7 @@ static int check_map(const char* who, int outer, int inner, long long outer_stri
     return AGCN_OK;
 }
 
-extern "C" int agcn_bn_stats(const float* x, int outer, int inner, long long outer_stride, int channels,
+extern "C" AGCN_API int agcn_bn_stats(const float* x, int outer, int inner, long long outer_stride, int channels,
                              const float* gamma, const float* beta, float* running_mean, float* running_var,
                              long long* num_batches_tracked, float momentum, float eps, int training,
                              float* scale, float* shift, float* save_mean, float* save_invstd,
@@ -361,7 +361,7 @@ extern "C" int agcn_bn_stats(const float* x, int outer, int inner, long long out
     return check_launch("agcn_bn_stats(finalize)");
 }
 
-extern "C" int agcn_bn_apply(const float* y, const float* scale, const float* shift,
+extern "C" AGCN_API int agcn_bn_apply(const float* y, const float* scale, const float* shift,
                              int res_mode, const float* res, const float* scale2, const float* shift2,
                              int relu, float* out, int outer, int inner, long long outer_stride, int channels, void* stream) {
     int rc = check_map("agcn_bn_apply", outer, inner, outer_stride, channels);
@@ -380,7 +380,7 @@ extern "C" int agcn_bn_apply(const float* y, const float* scale, const float* sh
     return check_launch("agcn_bn_apply");
 }
 
-extern "C" int agcn_bn_bwd(const float* dout, const float* mask_out, const float* y,
+extern "C" AGCN_API int agcn_bn_bwd(const float* dout, const float* mask_out, const float* y,
                            const float* save_mean, const float* save_invstd, const float* gamma,
                            float* dy, float* dgamma, float* dbeta, float* dres, int dres_accumulate,
                            int outer, int inner, long long outer_stride, int channels,
@@ -408,7 +408,7 @@ extern "C" int agcn_bn_bwd(const float* dout, const float* mask_out, const float
     return check_launch("agcn_bn_bwd(apply)");
 }
 
-extern "C" int agcn_pool_fwd(const float* x, float* out, int groups, int rows_per_group, int channels, void* stream) {
+extern "C" AGCN_API int agcn_pool_fwd(const float* x, float* out, int groups, int rows_per_group, int channels, void* stream) {
     AGCN_REQUIRE(x && out, AGCN_ERR_NULL, "agcn_pool_fwd: null pointer");
     AGCN_REQUIRE(groups > 0 && rows_per_group > 0 && channels > 0, AGCN_ERR_BAD_SHAPE, "agcn_pool_fwd: bad shape");
     dim3 grid((unsigned)groups, (unsigned)ceil_div(channels, 32));
@@ -416,7 +416,7 @@ extern "C" int agcn_pool_fwd(const float* x, float* out, int groups, int rows_pe
     return check_launch("agcn_pool_fwd");
 }
 
-extern "C" int agcn_pool_bwd(const float* dout, float* dx, int groups, int rows_per_group, int channels, void* stream) {
+extern "C" AGCN_API int agcn_pool_bwd(const float* dout, float* dx, int groups, int rows_per_group, int channels, void* stream) {
     AGCN_REQUIRE(dout && dx, AGCN_ERR_NULL, "agcn_pool_bwd: null pointer");
     AGCN_REQUIRE(groups > 0 && rows_per_group > 0 && channels > 0, AGCN_ERR_BAD_SHAPE, "agcn_pool_bwd: bad shape");
     const long long total = (long long)groups * rows_per_group * channels;

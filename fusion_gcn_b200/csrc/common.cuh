@@ -6,13 +6,18 @@
 #include <stdarg.h>
 #include "../../include/agcn_b200.h"
 
+#define AGCN_API __attribute__((visibility("default")))
+
 namespace agcn {
 
 // thread-local error text, returned by agcn_last_error_string()
 char* error_buffer();
 int fail(int code, const char* fmt, ...);
 
+void count_launch();
+
 inline int check_launch(const char* what) {
+    count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(AGCN_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
     return AGCN_OK;

@@ -303,7 +303,7 @@ int agcn_conv_fwd_tc(const float* x, const float* w, const float* bias, float* y
                      int nb, int t_in, int t_out, int v, int cin, int cout,
                      int taps, int stride, int pad, int transposed, int accumulate, void* stream);
 
-extern "C" int agcn_conv_fwd(const float* x, const float* w, const float* bias, float* y,
+extern "C" AGCN_API int agcn_conv_fwd(const float* x, const float* w, const float* bias, float* y,
                              int nb, int t_in, int t_out, int v, int cin, int cout,
                              int taps, int stride, int pad, int transposed, int accumulate,
                              int precision, void* stream) {
@@ -328,14 +328,14 @@ extern "C" int agcn_conv_fwd(const float* x, const float* w, const float* bias, 
     return check_launch("agcn_conv_fwd");
 }
 
-extern "C" size_t agcn_conv_wgrad_workspace_bytes(int nb, int t_in, int t_out, int v, int cin, int cout, int taps) {
+extern "C" AGCN_API size_t agcn_conv_wgrad_workspace_bytes(int nb, int t_in, int t_out, int v, int cin, int cout, int taps) {
     (void)t_in;
     long long rows = (long long)nb * t_out * v;
     int splits = wgrad_splits(rows, cin, cout, taps);
     return (size_t)splits * ((size_t)cout * taps * cin + (size_t)cout) * sizeof(float);
 }
 
-extern "C" int agcn_conv_wgrad(const float* dy, const float* x, float* dw, float* dbias,
+extern "C" AGCN_API int agcn_conv_wgrad(const float* dy, const float* x, float* dw, float* dbias,
                                int nb, int t_in, int t_out, int v, int cin, int cout,
                                int taps, int stride, int pad,
                                void* workspace, size_t workspace_bytes, int precision, void* stream) {

@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(256) joint_mix_kernel(MixArgs p) {
 
 using namespace agcn;
 
-extern "C" int agcn_joint_gram(const float* a, const float* b, float* out,
+extern "C" AGCN_API int agcn_joint_gram(const float* a, const float* b, float* out,
                                int nb, int t, int v, int lda, int ldb, int groups,
                                int offa, int stridea, int offb, int strideb, int width, int nchunk, void* stream) {
     AGCN_REQUIRE(a && b && out, AGCN_ERR_NULL, "agcn_joint_gram: null pointer");
@@ -311,7 +311,7 @@ extern "C" int agcn_joint_gram(const float* a, const float* b, float* out,
     return check_launch("agcn_joint_gram");
 }
 
-extern "C" int agcn_attention_fwd(const float* s_part, const float* adj_a, const float* adj_b, float* p, float* g,
+extern "C" AGCN_API int agcn_attention_fwd(const float* s_part, const float* adj_a, const float* adj_b, float* p, float* g,
                                   int nb, int nchunk, int groups, int v, float scale, void* stream) {
     AGCN_REQUIRE(s_part && adj_a && adj_b && p && g, AGCN_ERR_NULL, "agcn_attention_fwd: null pointer");
     AGCN_REQUIRE(nb > 0 && nchunk > 0 && groups > 0 && v > 0, AGCN_ERR_BAD_SHAPE, "agcn_attention_fwd: bad shape");
@@ -321,7 +321,7 @@ extern "C" int agcn_attention_fwd(const float* s_part, const float* adj_a, const
     return check_launch("agcn_attention_fwd");
 }
 
-extern "C" int agcn_attention_bwd(const float* dg_part, const float* p, float* dg_sum, float* ds, float* dadj_b,
+extern "C" AGCN_API int agcn_attention_bwd(const float* dg_part, const float* p, float* dg_sum, float* ds, float* dadj_b,
                                   int nb, int nchunk, int groups, int v, float scale, void* stream) {
     AGCN_REQUIRE(dg_part && p && dg_sum && ds && dadj_b, AGCN_ERR_NULL, "agcn_attention_bwd: null pointer");
     AGCN_REQUIRE(nb > 0 && nchunk > 0 && groups > 0 && v > 0, AGCN_ERR_BAD_SHAPE, "agcn_attention_bwd: bad shape");
@@ -336,7 +336,7 @@ extern "C" int agcn_attention_bwd(const float* dg_part, const float* p, float* d
     return check_launch("agcn_attention_bwd(dadj_b)");
 }
 
-extern "C" int agcn_joint_mix(const float* in, const float* mats, float* out,
+extern "C" AGCN_API int agcn_joint_mix(const float* in, const float* mats, float* out,
                               int nb, int t, int v, int ldin, int ldout, int width, int mode, int accumulate, void* stream) {
     AGCN_REQUIRE(in && mats && out, AGCN_ERR_NULL, "agcn_joint_mix: null pointer");
     AGCN_REQUIRE(nb > 0 && t > 0 && v > 0 && width > 0, AGCN_ERR_BAD_SHAPE, "agcn_joint_mix: bad shape");

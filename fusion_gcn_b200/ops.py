@@ -47,9 +47,42 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+_timing = None            # (set of entry-point names, list of (key, start_event, end_event)) while bench.py is timing
+
+
+def start_timing(names):
+    """Record a CUDA-event pair on the launching stream around every call of the named conv entry points."""
+    global _timing
+    _timing = (set(names), [])
+
+
+def stop_timing():
+    """-> {(name, nb, t_in, t_out, v, cin, cout, taps): (total_ms, launches)}; synchronises the device."""
+    global _timing
+    if _timing is None:
+        return {}
+    _, records = _timing
+    _timing = None
+    torch.cuda.synchronize()
+    out = {}
+    for key, e0, e1 in records:
+        tot, cnt = out.get(key, (0.0, 0))
+        out[key] = (tot + e0.elapsed_time(e1), cnt + 1)
+    return out
+
+
 def _call(name, *args):
     capi.launch_count += 1
-    capi.check(getattr(capi.lib(), name)(*args), name)
+    fn = getattr(capi.lib(), name)
+    if _timing is not None and name in _timing[0]:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        _timing[1].append(((name,) + tuple(args[4:11]), e0, e1))
+    else:
+        rc = fn(*args)
+    capi.check(rc, name)
 
 
 # ----------------------------------------------------------------------------- dense contractions

@@ -59,6 +59,8 @@ typedef enum { AGCN_RES_NONE = 0, AGCN_RES_TENSOR = 1, AGCN_RES_AFFINE = 2 } agc
 
 int agcn_version(void);
 const char* agcn_last_error_string(void);
+/* Number of CUDA kernels this library has launched in this process (monotonic; used by bench.py's gpu_launches). */
+long long agcn_launch_count(void);
 
 /* ---- dense contractions over the channel dimension ------------------------------------------------
  * Implicit GEMM with an optional temporal tap structure:

@@ -1,0 +1,180 @@
+"""-m gpu: every C-ABI entry point against its plain-torch restatement (oracle/stages.py) on the same seeded
+inputs, including ragged / odd shapes (V = 5..25, odd T, channel counts that are not multiples of 4)."""
+import pytest
+import torch
+
+from helpers import rel_err
+from oracle import stages as S
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def K():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from fusion_gcn_b200 import ops
+    return ops
+
+
+def rnd(*shape, seed=0):
+    g = torch.Generator().manual_seed(seed + sum(shape))
+    return torch.randn(*shape, generator=g)
+
+
+def both(fn_name, K, tensors, **kw):
+    ref = getattr(S, fn_name)(*[None if t is None else t.double() for t in tensors], **kw)
+    out = getattr(K, fn_name)(*[None if t is None else t.cuda() for t in tensors], **kw)
+    return out, ref
+
+
+CONV_CASES = [  # nb, t_in, v, cin, cout, taps, stride
+    (2, 12, 25, 3, 96, 1, 1), (2, 12, 25, 64, 64, 9, 1), (3, 13, 20, 16, 32, 9, 2), (2, 13, 20, 16, 32, 1, 2),
+    (1, 7, 5, 515, 64, 1, 1), (2, 9, 22, 9, 16, 1, 1), (1, 1, 37, 256, 60, 1, 1), (2, 30, 25, 128, 256, 9, 2),
+    (1, 300, 25, 64, 64, 9, 1)]
+
+
+@pytest.mark.parametrize("nb,t_in,v,cin,cout,taps,stride", CONV_CASES)
+def test_conv_fwd_dgrad_wgrad(K, nb, t_in, v, cin, cout, taps, stride):
+    pad = (taps - 1) // 2
+    t_out = (t_in + 2 * pad - taps) // stride + 1
+    x, w, b = rnd(nb, t_in, v, cin), rnd(cout, taps, cin, seed=1) * 0.1, rnd(cout, seed=2)
+    y, y_ref = both("conv_fwd", K, (x, w, b), t_out=t_out, stride=stride, pad=pad)
+    assert rel_err(y, y_ref) <= 2e-6
+    # accumulate into an existing tensor
+    base = rnd(nb, t_out, v, cout, seed=3)
+    acc = K.conv_fwd(x.cuda(), w.cuda(), None, t_out=t_out, stride=stride, pad=pad, out=base.cuda().clone(), accumulate=True)
+    assert rel_err(acc, S.conv_fwd(x.double(), w.double(), None, t_out=t_out, stride=stride, pad=pad) + base.double()) <= 2e-6
+    # input gradient = transposed gather with the transposed weight
+    dy = rnd(nb, t_out, v, cout, seed=4)
+    wt = w.permute(2, 1, 0).contiguous()
+    dx, dx_ref = both("conv_fwd", K, (dy, wt, None), t_out=t_in, stride=stride, pad=pad, transposed=True)
+    xg = x.double().requires_grad_(True)
+    (S.conv_fwd(xg, w.double(), b.double(), t_out=t_out, stride=stride, pad=pad) * dy.double()).sum().backward()
+    assert rel_err(dx_ref, xg.grad) <= 1e-12            # the stage oracle itself is consistent with autograd
+    assert rel_err(dx, xg.grad) <= 2e-6
+    (dw, db), (dw_ref, db_ref) = both("conv_wgrad", K, (dy, x), taps=taps, stride=stride, pad=pad)
+    assert rel_err(dw, dw_ref) <= 5e-6 and rel_err(db, db_ref) <= 5e-6
+
+
+@pytest.mark.parametrize("nb,t,v,ci,nchunk", [(2, 12, 25, 16, 3), (3, 7, 20, 4, 7), (1, 30, 22, 64, 4), (2, 5, 5, 2, 1), (2, 9, 18, 3, 2)])
+def test_joint_gram_score_and_dg(K, nb, t, v, ci, nchunk):
+    e = rnd(nb, t, v, 6 * ci)
+    kw = dict(groups=3, offa=0, stridea=2 * ci, offb=ci, strideb=2 * ci, width=ci, nchunk=nchunk)
+    s, s_ref = both("joint_gram", K, (e, e), **kw)
+    assert s.shape == (nb, nchunk, 3, v, v) and rel_err(s, s_ref) <= 2e-6
+    x, dz = rnd(nb, t, v, ci, seed=5), rnd(nb, t, v, 3 * ci, seed=6)
+    kw = dict(groups=3, offa=0, stridea=0, offb=0, strideb=ci, width=ci, nchunk=nchunk)
+    dg, dg_ref = both("joint_gram", K, (x, dz), **kw)
+    assert rel_err(dg, dg_ref) <= 2e-6
+
+
+def test_joint_gram_wide_channels(K):
+    x, dz = rnd(2, 6, 25, 256), rnd(2, 6, 25, 768, seed=1)
+    kw = dict(groups=3, offa=0, stridea=0, offb=0, strideb=256, width=256, nchunk=2)
+    dg, dg_ref = both("joint_gram", K, (x, dz), **kw)
+    assert rel_err(dg, dg_ref) <= 2e-6
+
+
+@pytest.mark.parametrize("nb,v,nchunk", [(3, 25, 4), (2, 20, 1), (5, 5, 2), (2, 32, 3)])
+def test_attention_fwd_bwd(K, nb, v, nchunk):
+    sp, a, b = rnd(nb, nchunk, 3, v, v) * 3, rnd(3, v, v, seed=1), rnd(3, v, v, seed=2) * 0.1
+    (p, g), (p_ref, g_ref) = both("attention_fwd", K, (sp, a, b), scale=0.37)
+    assert rel_err(p, p_ref) <= 2e-6 and rel_err(g, g_ref) <= 2e-6
+    assert torch.allclose(p.sum(dim=-2).cpu(), torch.ones(nb, 3, v), atol=1e-5)
+    dgp = rnd(nb, nchunk, 3, v, v, seed=3)
+    (ds, db), (ds_ref, db_ref) = both("attention_bwd", K, (dgp, p_ref.float()), scale=0.37)
+    assert rel_err(ds, ds_ref) <= 5e-6 and rel_err(db, db_ref) <= 5e-6
+    # autograd cross-check of the softmax backward formula
+    spd = sp.double().requires_grad_(True)
+    pp, gg = S.attention_fwd(spd, a.double(), b.double(), 0.37)
+    dG = dgp.double().sum(1)
+    (gg * dG).sum().backward()
+    assert rel_err(ds_ref.unsqueeze(1).expand_as(spd.grad), spd.grad) <= 1e-10
+
+
+@pytest.mark.parametrize("nb,t,v,w", [(2, 9, 25, 64), (2, 5, 20, 3), (1, 4, 22, 256), (3, 7, 5, 8), (2, 3, 18, 9), (1, 11, 25, 16)])
+def test_joint_mix_modes(K, nb, t, v, w):
+    mats = rnd(nb, 3, v, v, seed=1)
+    x = rnd(nb, t, v, w)
+    z, z_ref = both("joint_mix", K, (x, mats), width=w, mode=S.MIX_AGG_FWD)
+    assert rel_err(z, z_ref) <= 2e-6
+    dz = rnd(nb, t, v, 3 * w, seed=2)
+    dx, dx_ref = both("joint_mix", K, (dz, mats), width=w, mode=S.MIX_AGG_BWD)
+    assert rel_err(dx, dx_ref) <= 2e-6
+    base = rnd(nb, t, v, w, seed=3)
+    acc = K.joint_mix(dz.cuda(), mats.cuda(), width=w, mode=K.MIX_AGG_BWD, out=base.cuda().clone(), accumulate=True)
+    assert rel_err(acc, dx_ref + base.double()) <= 2e-6
+    e = rnd(nb, t, v, 6 * w, seed=4)
+    de, de_ref = both("joint_mix", K, (e, mats), width=w, mode=S.MIX_SCORE_BWD)
+    assert rel_err(de, de_ref) <= 2e-6
+
+
+@pytest.mark.parametrize("rows,c", [(1000, 64), (777, 3), (4099, 256), (300, 515), (50, 12), (9000, 128), (64, 8)])
+def test_bn_stats_apply_bwd(K, rows, c):
+    x = rnd(rows, c) * 2 + 0.5
+    gamma, beta = rnd(c, seed=1) * 0.3 + 1, rnd(c, seed=2) * 0.1
+    rm, rv = rnd(c, seed=3) * 0.1, rnd(c, seed=4).abs() + 0.5
+    nbt = torch.zeros((), dtype=torch.long)
+    d = lambda t: t.double().clone()
+    c_ = lambda t: t.cuda().clone()
+    rm_c, rv_c, nbt_c = c_(rm), c_(rv), nbt.cuda()
+    rm_d, rv_d, nbt_d = d(rm), d(rv), nbt.clone()
+    out = K.bn_stats(c_(x), c_(gamma), c_(beta), rm_c, rv_c, nbt_c, 0.1, 1e-5, True)
+    ref = S.bn_stats(d(x), d(gamma), d(beta), rm_d, rv_d, nbt_d, 0.1, 1e-5, True)
+    for a, b in zip(out, ref):
+        assert rel_err(a, b) <= 5e-6
+    assert rel_err(rm_c, rm_d) <= 2e-6 and rel_err(rv_c, rv_d) <= 2e-6 and int(nbt_c) == 1
+    ev = K.bn_stats(c_(x), c_(gamma), c_(beta), rm_c, rv_c, nbt_c, 0.1, 1e-5, False)
+    ev_ref = S.bn_stats(d(x), d(gamma), d(beta), rm_d, rv_d, nbt_d, 0.1, 1e-5, False)
+    assert rel_err(ev[0], ev_ref[0]) <= 5e-6 and rel_err(ev[1], ev_ref[1]) <= 5e-6 and int(nbt_c) == 1
+    sc, sh, mean, invstd = ref
+    res = rnd(rows, c, seed=5)
+    sc2, sh2 = rnd(c, seed=6), rnd(c, seed=7)
+    for mode, relu in ((S.RES_NONE, False), (S.RES_TENSOR, True), (S.RES_AFFINE, True)):
+        kw = dict(res_mode=mode, res=res, scale2=sc2, shift2=sh2, relu=relu)
+        o = K.bn_apply(c_(x), sc.float().cuda(), sh.float().cuda(), **{k: (v.cuda() if torch.is_tensor(v) else v) for k, v in kw.items()})
+        o_ref = S.bn_apply(d(x), sc, sh, **{k: (v.double() if torch.is_tensor(v) else v) for k, v in kw.items()})
+        assert rel_err(o, o_ref) <= 2e-6
+    dout, mask = rnd(rows, c, seed=8), rnd(rows, c, seed=9)
+    dres0 = rnd(rows, c, seed=10)
+    for use_mask, acc in ((True, False), (False, True)):
+        dres_c, dres_d = c_(dres0), d(dres0)
+        mk = mask if use_mask else None
+        dy, dg, db = K.bn_bwd(c_(dout), None if mk is None else c_(mk), c_(x), mean.float().cuda(), invstd.float().cuda(), c_(gamma),
+                              dres=dres_c, dres_accumulate=acc)
+        dy_r, dg_r, db_r = S.bn_bwd(d(dout), None if mk is None else d(mk), d(x), mean, invstd, d(gamma), dres=dres_d, dres_accumulate=acc)
+        assert rel_err(dy, dy_r) <= 1e-5 and rel_err(dg, dg_r) <= 1e-5 and rel_err(db, db_r) <= 1e-5
+        assert rel_err(dres_c, dres_d) <= 1e-6
+
+
+def test_bn_rowmap_data_bn_addressing(K):
+    n, m, t, v, c = 3, 2, 7, 5, 3
+    x = rnd(n, m, t, v, c)
+    vc = v * c
+    xc = x.cuda()
+    for mi in range(m):
+        rowmap = (n, t, m * t * vc, vc)
+        out = K.bn_stats(xc[:, mi], None, None, None, None, None, 0.1, 1e-5, True, rowmap=rowmap)
+        ref = S.bn_stats(x.double()[:, mi], None, None, None, None, None, 0.1, 1e-5, True, rowmap=rowmap)
+        for a, b in zip(out, ref):
+            assert rel_err(a, b) <= 5e-6
+        flat = x[:, mi].reshape(n * t, vc).double()
+        assert rel_err(out[2], flat.mean(0)) <= 5e-6
+
+
+@pytest.mark.parametrize("groups,rows,c", [(4, 100, 256), (3, 37, 60), (2, 1, 8)])
+def test_pool(K, groups, rows, c):
+    x = rnd(groups * rows, c).view(groups, rows, c)
+    o, o_ref = both("pool_fwd", K, (x,), groups=groups)
+    assert rel_err(o, o_ref) <= 2e-6
+    dout = rnd(groups, c, seed=1)
+    dx = K.pool_bwd(dout.cuda(), (groups, rows, c))
+    assert rel_err(dx, S.pool_bwd(dout.double(), (groups, rows, c))) <= 2e-6
+
+
+def test_error_paths_raise(K):
+    with pytest.raises(RuntimeError, match="CUDA"):
+        K.conv_fwd(torch.randn(1, 2, 3, 4), torch.randn(4, 1, 4).cuda())
+    with pytest.raises(RuntimeError, match="status 2"):
+        K.joint_mix(torch.randn(1, 2, 40, 8).cuda(), torch.randn(1, 3, 40, 40).cuda(), width=8, mode=K.MIX_AGG_FWD)

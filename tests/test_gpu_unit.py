@@ -1,0 +1,156 @@
+"""-m gpu: the CUDA path (through the drop-in modules and the C ABI) against the golden vectors produced by the
+unmodified reference, against the CPU oracle on larger seeded inputs, and size-independent properties at the
+BASELINE shapes.  Tolerance (north_star): fp32 mode max relative error <= 1e-4 on outputs and gradients, with the
+SURVEY D8 metric maxabs(diff)/maxabs(ref) and the zero-gradient families checked on an absolute scale."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import (MODEL_FIXTURES, RESIDUAL_KINDS, UNIT_FIXTURES, check_grads, load_golden, rel_err, stat_err, sub, to_t)
+from oracle import agcn_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import fusion_gcn_b200
+    from fusion_gcn_b200 import capi
+    capi.lib()                     # fail loudly if the extension is missing
+    return fusion_gcn_b200
+
+
+@pytest.mark.parametrize("name", UNIT_FIXTURES)
+def test_unit_vs_reference_golden(pkg, name):
+    from fusion_gcn_b200 import modules as M
+    g = load_golden("unit_" + name)
+    cin, cout, stride, res = [int(v) for v in g["meta"]]
+    state = {k: to_t(v) for k, v in sub(g, "state.").items()}
+    unit = M.SpatialTemporalConv(cin, cout, state["gcn1.adj_a"].numpy().astype(np.float64), stride=stride, residual=(res != 0))
+    unit.load_state_dict(state, strict=True)
+    unit.cuda().train()
+    x = to_t(g["x"], device="cuda").requires_grad_(True)
+    y = unit(x)
+    (y * to_t(g["w"], device="cuda")).sum().backward()
+    assert rel_err(y, g["f64.y"]) <= TOL
+    assert rel_err(x.grad, g["f64.dx"]) <= TOL
+    for k in range(3):
+        assert rel_err(unit.gcn1.adj_c[k], g[f"f64.adj_c.{k}"]) <= TOL
+    worst = check_grads({k: p.grad for k, p in unit.named_parameters()}, sub(g, "f64.grad."), TOL, name)
+    for k, v in sub(g, "f64.after.").items():
+        assert stat_err(unit.state_dict()[k], v) <= TOL, k
+    print(f"{name}: y {rel_err(y, g['f64.y']):.2e} (reference fp32 itself: {rel_err(g['f32.y'], g['f64.y']):.2e}), worst grad {worst}")
+
+
+@pytest.mark.parametrize("name", MODEL_FIXTURES)
+def test_model_vs_reference_golden(pkg, name):
+    from fusion_gcn_b200 import graph as G, modules as M
+    g = load_golden("model_" + name)
+    m, t, v, c, ncls, start = [int(a) for a in g["meta"]]
+    model = M.Model((m, t, v, c), ncls, G.SkeletonGraph(G.UTD_EDGES if v == 20 else G.NTU_EDGES), start_feature_size=start)
+    model.load_state_dict({k: to_t(a) for k, a in sub(g, "state.").items()}, strict=True)
+    model.cuda().train()
+    x = to_t(g["x"], device="cuda")
+    y = model(x)
+    (y * to_t(g["w"], device="cuda")).sum().backward()
+    assert rel_err(y, g["f64.y"]) <= TOL
+    check_grads({k: p.grad for k, p in model.named_parameters()}, sub(g, "f64.grad."), 2 * TOL if "default" in name else TOL, name)
+    for k, v_ in sub(g, "f64.after.").items():
+        assert stat_err(model.state_dict()[k], v_) <= TOL, k
+    model.eval()
+    with torch.no_grad():
+        assert rel_err(model(x), g["f64.y_eval"]) <= TOL
+
+
+@pytest.mark.parametrize("shape,edges,start,n", [
+    ((1, 100, 20, 3), "utd", 64, 4),          # config C1 shape (UTD-MHAD skeleton)
+    ((2, 60, 25, 3), "ntu", 64, 2),           # NTU graph, two bodies, full channel widths
+    ((2, 33, 22, 3), "mmact_imu", 32, 2),     # config C3 graph: COCO-18 + 4 IMU joints, odd T through two stride-2 layers
+    ((1, 20, 20, 9), "utd", 16, 3),           # channel fusion C = 9
+])
+def test_model_vs_cpu_oracle_seeded(pkg, shape, edges, start, n):
+    from fusion_gcn_b200 import graph as G, modules as M
+    if edges == "utd":
+        graph = G.SkeletonGraph(G.UTD_EDGES, center_joint=G.UTD_CENTER)
+    elif edges == "ntu":
+        graph = G.SkeletonGraph(G.NTU_EDGES, center_joint=G.NTU_CENTER)
+    else:
+        graph = G.imu_fusion_graph(G.SkeletonGraph(G.MMACT_EDGES, center_joint=G.MMACT_CENTER), 4, "append_center", interconnect=True)
+    adj = G.adjacency_from_graph(graph)
+    m, t, v, c = shape
+    state = O.init_state(adj, shape, 27, start=start, seed=21, loud=True)
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(n, m, t, v, c, generator=gen)
+    w = torch.randn(n, 27, generator=gen)
+    p = O.as_leaves(state, torch.float64)
+    y_ref = O.model_forward(x.double(), p, c, True, start=start)
+    (y_ref * w.double()).sum().backward()
+    model = M.Model(shape, 27, graph, start_feature_size=start)
+    model.load_state_dict(state, strict=True)
+    model.cuda().train()
+    y = model(x.cuda())
+    (y * w.cuda()).sum().backward()
+    assert rel_err(y, y_ref) <= TOL
+    check_grads({k: q.grad for k, q in model.named_parameters()}, {k: a.grad for k, a in p.items() if a.requires_grad}, TOL, str(shape))
+
+
+def test_properties_at_ntu_batch_shape(pkg):
+    """Size-independent properties on the BASELINE NTU shape (N=8 here keeps the test short; same kernels/tiles as N=64):
+    attention columns sum to one, bit-identical reruns (deterministic reductions), batch-permutation equivariance in
+    eval mode, and zero gradients for the bias families that training-mode BN cancels."""
+    from fusion_gcn_b200 import graph as G, modules as M
+    torch.manual_seed(0)
+    model = M.Model((2, 300, 25, 3), 60, G.SkeletonGraph(G.NTU_EDGES, center_joint=G.NTU_CENTER)).cuda()
+    for name, prm in model.named_parameters():          # loud values so that every branch matters
+        if name.endswith("bn.weight") or name.endswith("down.1.weight"):
+            prm.data.uniform_(0.5, 1.5)
+        if "adj_b" in name:
+            prm.data.normal_(0, 0.1)
+    x = torch.randn(8, 2, 300, 25, 3, device="cuda")
+    model.train()
+    y1 = model(x)
+    y1.square().sum().backward()
+    g1 = {k: p.grad.clone() for k, p in model.named_parameters()}
+    for blk in (model.l0, model.l4, model.l9):
+        for a in blk.gcn1.adj_c:
+            assert a.shape == (16, 25, 25)
+            assert torch.allclose(a.sum(dim=-2), torch.ones_like(a.sum(dim=-2)), atol=1e-5)
+    model.zero_grad()
+    y2 = model(x)
+    y2.square().sum().backward()
+    assert torch.equal(y1, y2)
+    for k, p in model.named_parameters():
+        assert torch.equal(g1[k], p.grad), k
+    scale = max(float(v.abs().max()) for v in g1.values())
+    for k, v in g1.items():
+        if k.endswith("tcn1.conv.bias") or "conv_d" in k and k.endswith("bias") or k.endswith("down.0.bias"):
+            assert float(v.abs().max()) <= 1e-4 * scale, k
+    model.eval()
+    with torch.no_grad():
+        perm = torch.randperm(8, device="cuda")
+        assert rel_err(model(x[perm]), model(x)[perm]) <= 1e-5
+
+
+def test_standalone_modules_reference_layout(pkg):
+    from fusion_gcn_b200 import graph as G, modules as M
+    adj = G.partition_adjacency(G.UTD_EDGES)
+    torch.manual_seed(1)
+    tcn = M.TemporalConv(8, 12, stride=2).cuda()
+    ref = torch.nn.Sequential(torch.nn.Conv2d(8, 12, (9, 1), padding=(4, 0), stride=(2, 1)), torch.nn.BatchNorm2d(12)).cuda()
+    ref[0].load_state_dict(tcn.conv.state_dict())
+    x = torch.randn(2, 8, 11, 20, device="cuda")
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        assert rel_err(tcn(x), ref(x)) <= 1e-5
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    unit = M.SpatialTemporalConv(8, 8, adj).cuda()
+    y = unit(x)
+    assert y.shape == x.shape and y.is_contiguous()
+    with pytest.raises(NotImplementedError):
+        unit.eval()
+        unit(x.requires_grad_(True)).sum().backward()

@@ -1,0 +1,144 @@
+"""Host-side logic on CPU: the autograd composition in fusion_gcn_b200.functional (forward order, every
+backward formula, parameter packing), the drop-in modules' state-dict compatibility and layouts.
+The kernels are replaced by oracle/stages.py through the TEST-ONLY ``torch_stage_backend`` fixture."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import MODEL_FIXTURES, RESIDUAL_KINDS, UNIT_FIXTURES, check_grads, load_golden, rel_err, stat_err, sub, to_t
+from fusion_gcn_b200 import graph as G
+from fusion_gcn_b200 import modules as M
+from fusion_gcn_b200 import modules_original as MO
+
+
+def test_graph_builder_matches_reference_golden():
+    g = load_golden("adjacency")
+    for name, edges in (("ntu", G.NTU_EDGES), ("utd", G.UTD_EDGES), ("mmact", G.MMACT_EDGES)):
+        assert np.array_equal(np.unique(np.asarray(edges), axis=0), np.unique(g[name + "_edges"], axis=0))
+        assert np.array_equal(G.partition_adjacency(edges), g[name + "_adj"]), name
+    base = G.SkeletonGraph(G.MMACT_EDGES, center_joint=G.MMACT_CENTER)
+    for inter in (False, True):
+        fused = G.imu_fusion_graph(base, 4, "append_center", interconnect=inter)
+        assert fused.num_vertices == 22
+        assert np.array_equal(G.adjacency_from_graph(fused), g["mmact_imu4_" + ("inter" if inter else "plain") + "_adj"])
+    with pytest.raises(NotImplementedError):
+        G.partition_adjacency(G.NTU_EDGES, strategy="distance")
+    with pytest.raises(ValueError):
+        G.imu_fusion_graph(base, 2, "append_left")
+
+
+def test_cuda_path_has_no_cpu_fallback():
+    """Without the test backend the modules must refuse CPU tensors loudly."""
+    unit = M.SpatialTemporalConv(4, 8, G.partition_adjacency(G.UTD_EDGES))
+    with pytest.raises(RuntimeError, match="CUDA|libagcn_b200"):
+        unit(torch.randn(1, 4, 6, 20))
+
+
+@pytest.mark.parametrize("name", UNIT_FIXTURES)
+def test_unit_module_vs_golden(name, torch_stage_backend):
+    g = load_golden("unit_" + name)
+    cin, cout, stride, res = [int(v) for v in g["meta"]]
+    state = {k: to_t(v) for k, v in sub(g, "state.").items()}
+    adj = state["gcn1.adj_a"].numpy().astype(np.float64)
+    unit = M.SpatialTemporalConv(cin, cout, adj, stride=stride, residual=(res != 0))
+    assert sorted(unit.state_dict().keys()) == sorted(state.keys())
+    unit.load_state_dict(state, strict=True)
+    unit.train()
+    x = to_t(g["x"]).requires_grad_(True)            # reference layout (N', C, T, V)
+    y = unit(x)
+    assert y.shape == g["f64.y"].shape and y.is_contiguous()
+    (y * to_t(g["w"])).sum().backward()
+    assert rel_err(y, g["f64.y"]) <= 2e-5
+    assert rel_err(x.grad, g["f64.dx"]) <= 1e-4
+    for k in range(3):
+        assert rel_err(unit.gcn1.adj_c[k], g[f"f64.adj_c.{k}"]) <= 1e-5
+        assert not unit.gcn1.adj_c[k].requires_grad
+    check_grads({k: p.grad for k, p in unit.named_parameters()}, sub(g, "f64.grad."), 1e-4, name)
+    for k, v in sub(g, "f64.after.").items():
+        assert stat_err(unit.state_dict()[k], v) <= 1e-5, k
+
+
+@pytest.mark.parametrize("name", MODEL_FIXTURES)
+def test_model_module_vs_golden(name, torch_stage_backend):
+    g = load_golden("model_" + name)
+    m, t, v, c, ncls, start = [int(a) for a in g["meta"]]
+    state = {k: to_t(a) for k, a in sub(g, "state.").items()}
+    graph = G.SkeletonGraph(G.UTD_EDGES if v == 20 else G.NTU_EDGES)
+    model = M.Model((m, t, v, c), ncls, graph, start_feature_size=start)
+    assert sorted(model.state_dict().keys()) == sorted(state.keys())
+    model.load_state_dict(state, strict=True)
+    model.train()
+    y = model(to_t(g["x"]))
+    (y * to_t(g["w"])).sum().backward()
+    assert rel_err(y, g["f64.y"]) <= 1e-4
+    check_grads({k: p.grad for k, p in model.named_parameters()}, sub(g, "f64.grad."), 1e-4 if "default" not in name else 2e-4, name)
+    for k, v_ in sub(g, "f64.after.").items():
+        assert stat_err(model.state_dict()[k], v_) <= 1e-4, k
+    assert int(model.data_bn.num_batches_tracked) == 1 and int(model.l3.tcn1.bn.num_batches_tracked) == 1
+    model.eval()
+    with torch.no_grad():
+        assert rel_err(model(to_t(g["x"])), g["f64.y_eval"]) <= 1e-4
+
+
+def test_standalone_halves_and_kwargs(torch_stage_backend):
+    torch.manual_seed(0)
+    adj = G.partition_adjacency(G.UTD_EDGES)
+    tcn = M.TemporalConv(8, 12, kernel_size=9, stride=2)
+    ref_tcn = torch.nn.Sequential(torch.nn.Conv2d(8, 12, (9, 1), padding=(4, 0), stride=(2, 1)), torch.nn.BatchNorm2d(12))
+    ref_tcn[0].load_state_dict(tcn.conv.state_dict())
+    x = torch.randn(2, 8, 11, 20)
+    assert rel_err(tcn(x), ref_tcn(x)) <= 1e-5                     # no activation inside TemporalConv
+    gcn = M.SpatialGraphConv(8, 8, adj)
+    y = gcn(x)
+    assert y.shape == x.shape and float(y.min()) >= 0.0
+    assert all(a.shape == (2, 20, 20) for a in gcn.adj_c)
+    assert torch.allclose(gcn.adj_c[0].sum(dim=-2), torch.ones(2, 20), atol=1e-5)      # columns sum to one
+    model = M.Model((1, 12, 20, 3), 5, G.SkeletonGraph(G.UTD_EDGES), num_layers=3, start_feature_size=8, without_fc=True, dropout=0.25)
+    assert model.fc is None and model.out_channels == 8
+    assert isinstance(model.l1, torch.nn.Dropout) and isinstance(model.l2, M.SpatialTemporalConv)      # agcn.py:166-172 naming
+    assert model(torch.randn(2, 1, 12, 20, 3)).shape == (2, 8)
+    with pytest.raises(ValueError):
+        M.SpatialGraphConv(8, 8, adj[:1], num_subsets=1)
+
+
+def test_original_variant_state_dict_and_parity(torch_stage_backend):
+    """models/agcn/agcn.py: layers l1..l10, parameter PA, adjacency not in the state dict, dict data_shape."""
+    g = load_golden("model_ntu_s8_m2")
+    m, t, v, c, ncls, start = [int(a) for a in g["meta"]]
+    graph = G.SkeletonGraph(G.NTU_EDGES)
+    model = MO.Model({"skeleton": (m, t, v, c)}, ncls, graph, start_feature_size=start)
+    keys = list(model.state_dict().keys())
+    assert "l1.gcn1.PA" in keys and "l10.tcn1.conv.weight" in keys and not any("adj_a" in k or k.startswith("l0.") for k in keys)
+    state = {}
+    for k, a in sub(g, "state.").items():
+        if k.endswith("adj_a"):
+            continue
+        if k[0] == "l" and k[1].isdigit():
+            idx, rest = k[1:].split(".", 1)
+            k = f"l{int(idx) + 1}.{rest}"
+        state[k.replace("adj_b", "PA")] = to_t(a)
+    model.load_state_dict(state, strict=True)
+    model.train()
+    y = model(to_t(g["x"]))
+    assert rel_err(y, g["f64.y"]) <= 1e-4
+    assert isinstance(model.l1, MO.TCN_GCN_unit) and isinstance(model.l1.gcn1, MO.unit_gcn) and isinstance(model.l1.tcn1, MO.unit_tcn)
+
+
+def test_state_dict_order_matches_live_reference():
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("/root/reference not present (GPU box)")
+    R = ref_loader.load()
+    rg = R["Graph"](R["ntu"].skeleton_edges, center_joint=R["ntu"].center_joint)
+    ref = R["agcn"].Model((2, 16, 25, 3), 60, rg, start_feature_size=8)
+    ours = M.Model((2, 16, 25, 3), 60, rg, start_feature_size=8)          # accepts the reference's own Graph object
+    assert list(ours.state_dict().keys()) == list(ref.state_dict().keys())
+    assert [tuple(v.shape) for v in ours.state_dict().values()] == [tuple(v.shape) for v in ref.state_dict().values()]
+    assert len(ours.state_dict()) == 362 and sum(p.numel() for p in ours.parameters()) == sum(p.numel() for p in ref.parameters())
+    # same initial distributions: identical tensors under the same seed
+    torch.manual_seed(4)
+    a = R["agcn"].SpatialTemporalConv(8, 16, np.asarray(ours.l0.gcn1.adj_a.numpy(), dtype=np.float64), stride=2)
+    torch.manual_seed(4)
+    b = M.SpatialTemporalConv(8, 16, np.asarray(ours.l0.gcn1.adj_a.numpy(), dtype=np.float64), stride=2)
+    for (ka, va), (kb, vb) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert ka == kb and torch.equal(va, vb), ka
