@@ -1,7 +1,349 @@
-// tcgen05 / TMA tensor-core path of the implicit GEMM (AGCN_PREC_TF32).  Placeholder until the kernel lands:
-// reports "unsupported" so that agcn_conv_fwd falls back to the FFMA kernel.
+// tcgen05 / TMA tensor-core path of the implicit GEMM (AGCN_PREC_TF32), sm_100a only.
+//
+//   y[nb][to][v][co] (+)= bias[co] + sum_tap sum_ci x[nb][ti(to,tap)][v][ci] * w[co][tap][ci]
+//
+// Tiling: one CTA tile = `tt` consecutive output timesteps x all V joints (tt*V <= 128 rows, the UMMA M=128 atom)
+// x BN output channels.  The temporal taps are not materialised: for tap `tap` the A operand is the same TMA box
+// shifted along the T coordinate of a 4-D tensor map (cin, V, T, nb); out-of-range timesteps are zero-filled by
+// TMA, which is exactly the conv's zero padding.  Stride-2 convs use the tensor map's elementStrides; the
+// transposed (input-gradient) gather of a stride-s conv is split into s parity classes of output timesteps, each
+// of which is a plain shifted box again.
+//
+// Pipeline (192 threads, 1 CTA / SM, persistent over tiles):
+//   warp 0      TMA producer: A box (<=128 rows x 32 fp32, 128B swizzle) + B box (BN x 32) per (tap, k-chunk) stage
+//   warp 1      MMA issuer: 4 x tcgen05.mma.kind::tf32 (M128, N=BN, K8) per stage, fp32 accumulators in TMEM,
+//               tcgen05.commit releases the smem stage / publishes the accumulator
+//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 16 columns) -> +bias (+old) -> coalesced-per-row st.global
+// TMEM: 2 x 128 columns, so the epilogue of tile i overlaps the main loop of tile i+1.
 #include "common.cuh"
+#include <cuda.h>
 
-int agcn_conv_fwd_tc(const float*, const float*, const float*, float*, int, int, int, int, int, int, int, int, int, int, int, void*) {
-    return AGCN_ERR_UNSUPPORTED;
+namespace agcn {
+namespace tc {
+
+constexpr int kStages = 6;
+constexpr int kStageBytes = 32 * 1024;      // A 16 KB + B 16 KB
+constexpr int kABytes = 16 * 1024;
+constexpr int kKChunk = 32;                 // fp32 elements per 128-byte swizzle row
+constexpr int kThreads = 192;
+constexpr int kTmemCols = 256;
+constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+
+struct TcArgs {
+    float* y; const float* bias;
+    int nb, t_in, t_out, v, cin, cout, taps, stride, pad, transposed, accumulate;
+    int tt, bn, n_tiles_n, kchunks, tiles_t, nparity;
+    long long total_tiles;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (rows at 128 B pitch, 8-row atoms at 1024 B pitch)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);        // start address, 16-byte units
+    d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset between 8-row atoms
+    d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+    return d;
+}
+
+// number of (tap) iterations and their A-box T coordinate for one tile
+struct TapIter {
+    int tap, tcoord;
+};
+__device__ __forceinline__ bool tap_valid(const TcArgs& a, int par, int tap, int jt, int& tcoord) {
+    if (!a.transposed) {
+        tcoord = a.stride * (jt * a.tt) + tap - a.pad;
+        return true;
+    }
+    int num = par + a.pad - tap;
+    if (num % a.stride) return false;      // C++ remainder of a negative multiple of stride is 0 as well
+    tcoord = jt * a.tt + num / a.stride;
+    return true;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + kStages * kStageBytes;
+    // barriers: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]; then the TMEM base address word
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const int rows_box = a.v * a.tt;
+    const uint32_t stage_tx = (uint32_t)(rows_box * 128 + a.bn * 128);
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+                long long r = tile;
+                const int nt = (int)(r % a.n_tiles_n); r /= a.n_tiles_n;
+                const int jt = (int)(r % a.tiles_t); r /= a.tiles_t;
+                const int par = (int)(r % a.nparity);
+                const int n = (int)(r / a.nparity);
+                for (int tap = 0; tap < a.taps; ++tap) {
+                    int tcoord;
+                    if (!tap_valid(a, par, tap, jt, tcoord)) continue;
+                    for (int kc = 0; kc < a.kchunks; ++kc) {
+                        mbar_wait(empty_bar(stage), phase ^ 1u);
+                        mbar_expect_tx(full_bar(stage), stage_tx);
+                        const uint32_t sa = smem_base + stage * kStageBytes;
+                        tma_load_4d(sa, &map_a, full_bar(stage), kc * kKChunk, 0, tcoord, n);
+                        tma_load_3d(sa + kABytes, &map_b, full_bar(stage), kc * kKChunk, tap, nt * a.bn);
+                        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.bn >> 3) << 17) | ((128u >> 4) << 24);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+                long long r = tile;
+                r /= a.n_tiles_n;
+                const int jt = (int)(r % a.tiles_t); r /= a.tiles_t;
+                const int par = (int)(r % a.nparity);
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
+                uint32_t first = 1;
+                for (int tap = 0; tap < a.taps; ++tap) {
+                    int tcoord;
+                    if (!tap_valid(a, par, tap, jt, tcoord)) continue;
+                    for (int kc = 0; kc < a.kchunks; ++kc) {
+                        mbar_wait(full_bar(stage), phase);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t sa = smem_base + stage * kStageBytes;
+                        const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + kABytes);
+#pragma unroll
+                        for (int k = 0; k < kKChunk / 8; ++k) {
+                            umma_tf32(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, first ? 0u : 1u);
+                            first = 0;
+                        }
+                        umma_commit(empty_bar(stage));          // smem stage reusable once these MMAs retire
+                        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+                umma_commit(tfull_bar(acc));                     // accumulator complete
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else {
+        // ===================================================== epilogue warps (TMEM lane quarter = warp % 4)
+        const int q = warp & 3;
+        const int row_local = q * 32 + lane;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+            long long r = tile;
+            const int nt = (int)(r % a.n_tiles_n); r /= a.n_tiles_n;
+            const int jt = (int)(r % a.tiles_t); r /= a.tiles_t;
+            const int par = (int)(r % a.nparity);
+            const int n = (int)(r / a.nparity);
+            const int tl = row_local / a.v, vv = row_local - tl * a.v;
+            const int j = jt * a.tt + tl;
+            const int to = a.transposed ? a.stride * j + par : j;
+            const bool row_ok = (tl < a.tt) && (to < a.t_out);
+            float* yrow = a.y + (((long long)n * a.t_out + to) * a.v + vv) * a.cout + nt * a.bn;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + (uint32_t)(acc * 128) + ((uint32_t)(q * 32) << 16);
+            for (int c = 0; c < a.bn; c += 16) {
+                float vals[16];
+                tmem_ld16(taddr + (uint32_t)c, vals);
+                const int col = nt * a.bn + c;
+                if (row_ok) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        if (col + g * 4 >= a.cout) break;
+                        float4 o = make_float4(vals[g * 4], vals[g * 4 + 1], vals[g * 4 + 2], vals[g * 4 + 3]);
+                        if (a.bias) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + col + g * 4));
+                            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                        }
+                        float4* p = reinterpret_cast<float4*>(yrow + c + g * 4);
+                        if (a.accumulate) {
+                            const float4 old = *p;
+                            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                        }
+                        *p = o;
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+}  // namespace tc
+}  // namespace agcn
+
+using namespace agcn;
+
+// returns AGCN_ERR_UNSUPPORTED (without touching the error string's meaning) when the shape is outside this path
+int agcn_conv_fwd_tc(const float* x, const float* w, const float* bias, float* y,
+                     int nb, int t_in, int t_out, int v, int cin, int cout,
+                     int taps, int stride, int pad, int transposed, int accumulate, void* stream) {
+    using namespace agcn::tc;
+    if (cin % 4 || cout % 16 || v > 128 || stride > 4) return AGCN_ERR_UNSUPPORTED;
+    if (transposed && stride > 1 && taps < stride) return AGCN_ERR_UNSUPPORTED;       // some parity classes would have no taps
+    if (!aligned16(x) || !aligned16(w) || !aligned16(y) || (bias && !aligned16(bias))) return AGCN_ERR_UNSUPPORTED;
+    int bn;
+    if (cout % 128 == 0) bn = 128;
+    else if (cout % 96 == 0) bn = 96;
+    else if (cout % 64 == 0) bn = 64;
+    else if (cout <= 128) bn = cout;
+    else return AGCN_ERR_UNSUPPORTED;
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc: cuTensorMapEncodeTiled is not available from the driver");
+
+    TcArgs a;
+    a.y = y; a.bias = bias;
+    a.nb = nb; a.t_in = t_in; a.t_out = t_out; a.v = v; a.cin = cin; a.cout = cout;
+    a.taps = taps; a.stride = stride; a.pad = pad; a.transposed = transposed; a.accumulate = accumulate;
+    a.tt = 128 / v;
+    const int es = transposed ? 1 : stride;          // element stride of the A box along T
+    while (a.tt * es > 256) --a.tt;
+    a.bn = bn;
+    a.n_tiles_n = cout / bn;
+    a.kchunks = (cin + kKChunk - 1) / kKChunk;
+    a.nparity = transposed ? stride : 1;
+    const int t_per_class = transposed ? (t_out + stride - 1) / stride : t_out;
+    a.tiles_t = (t_per_class + a.tt - 1) / a.tt;
+    a.total_tiles = (long long)nb * a.nparity * a.tiles_t * a.n_tiles_n;
+
+    CUtensorMap map_a, map_b;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)v, (cuuint64_t)t_in, (cuuint64_t)nb};
+        cuuint64_t strides[3] = {(cuuint64_t)cin * 4, (cuuint64_t)v * cin * 4, (cuuint64_t)t_in * v * cin * 4};
+        cuuint32_t box[4] = {(cuuint32_t)kKChunk, (cuuint32_t)v, (cuuint32_t)(a.tt * es), 1};
+        cuuint32_t estr[4] = {1, 1, (cuuint32_t)es, 1};
+        CUresult r = enc(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)taps, (cuuint64_t)cout};
+        cuuint64_t strides[2] = {(cuuint64_t)cin * 4, (cuuint64_t)taps * cin * 4};
+        cuuint32_t box[3] = {(cuuint32_t)kKChunk, 1, (cuuint32_t)bn};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(w), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        if (e != cudaSuccess) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    long long grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
+    conv_tc_kernel<<<(unsigned)grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(map_a, map_b, a);
+    return check_launch("agcn_conv_fwd_tc");
 }

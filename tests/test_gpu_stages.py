@@ -90,7 +90,7 @@ def test_attention_fwd_bwd(K, nb, v, nchunk):
     pp, gg = S.attention_fwd(spd, a.double(), b.double(), 0.37)
     dG = dgp.double().sum(1)
     (gg * dG).sum().backward()
-    assert rel_err(ds_ref.unsqueeze(1).expand_as(spd.grad), spd.grad) <= 1e-10
+    assert rel_err(ds_ref.unsqueeze(1).expand_as(spd.grad), spd.grad) <= 1e-6      # p was rounded to fp32 for the kernel
 
 
 @pytest.mark.parametrize("nb,t,v,w", [(2, 9, 25, 64), (2, 5, 20, 3), (1, 4, 22, 256), (3, 7, 5, 8), (2, 3, 18, 9), (1, 11, 25, 16)])

@@ -88,13 +88,16 @@ def test_model_vs_cpu_oracle_seeded(pkg, shape, edges, start, n):
     p = O.as_leaves(state, torch.float64)
     y_ref = O.model_forward(x.double(), p, c, True, start=start)
     (y_ref * w.double()).sum().backward()
+    p32 = O.as_leaves(state, torch.float32)              # the reference arithmetic in fp32: its own noise floor
+    (O.model_forward(x, p32, c, True, start=start) * w).sum().backward()
     model = M.Model(shape, 27, graph, start_feature_size=start)
     model.load_state_dict(state, strict=True)
     model.cuda().train()
     y = model(x.cuda())
     (y * w.cuda()).sum().backward()
     assert rel_err(y, y_ref) <= TOL
-    check_grads({k: q.grad for k, q in model.named_parameters()}, {k: a.grad for k, a in p.items() if a.requires_grad}, TOL, str(shape))
+    check_grads({k: q.grad for k, q in model.named_parameters()}, {k: a.grad for k, a in p.items() if a.requires_grad}, TOL, str(shape),
+                ref32={k: a.grad for k, a in p32.items() if a.requires_grad})
 
 
 def test_properties_at_ntu_batch_shape(pkg):
