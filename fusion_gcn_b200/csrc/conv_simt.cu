@@ -284,6 +284,29 @@ __global__ void wgrad_reduce_kernel(const float* ws_w, const float* ws_b, float*
     }
 }
 
+// column sums of dy for the bias gradient when the weight gradient runs on tensor cores: part[P][cout]
+__global__ void __launch_bounds__(256) bias_partial_kernel(const float* dy, long long rows, int cout, float* part) {
+    __shared__ float sm[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.y * 32 + tx;
+    const long long per = (rows + gridDim.x - 1) / gridDim.x;
+    const long long r0 = (long long)blockIdx.x * per;
+    long long r1 = r0 + per; if (r1 > rows) r1 = rows;
+    float s = 0.f;
+    if (c < cout)
+        for (long long r = r0 + ty; r < r1; r += 8) s += __ldg(dy + r * cout + c);
+    sm[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && c < cout) {
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc += sm[i][tx];
+        part[(long long)blockIdx.x * cout + c] = acc;
+    }
+}
+
+constexpr int kBiasPartials = 2 * kNumSMs;
+
 static int wgrad_splits(long long rows, int cin, int cout, int taps) {
     long long tiles = (long long)((cout + 63) / 64) * ((cin + 63) / 64) * taps;
     long long s = (4LL * kNumSMs + tiles - 1) / tiles;
@@ -302,6 +325,10 @@ using namespace agcn;
 int agcn_conv_fwd_tc(const float* x, const float* w, const float* bias, float* y,
                      int nb, int t_in, int t_out, int v, int cin, int cout,
                      int taps, int stride, int pad, int transposed, int accumulate, void* stream);
+
+size_t agcn_conv_wgrad_tc_workspace_floats(int nb, int t_in, int t_out, int v, int cin, int cout, int taps, int stride, int pad);
+int agcn_conv_wgrad_tc(const float* dy, const float* x, float* ws, int* splits_out,
+                       int nb, int t_in, int t_out, int v, int cin, int cout, int taps, int stride, int pad, void* stream);
 
 extern "C" AGCN_API int agcn_conv_fwd(const float* x, const float* w, const float* bias, float* y,
                              int nb, int t_in, int t_out, int v, int cin, int cout,
@@ -329,23 +356,54 @@ extern "C" AGCN_API int agcn_conv_fwd(const float* x, const float* w, const floa
 }
 
 extern "C" AGCN_API size_t agcn_conv_wgrad_workspace_bytes(int nb, int t_in, int t_out, int v, int cin, int cout, int taps) {
-    (void)t_in;
     long long rows = (long long)nb * t_out * v;
     int splits = wgrad_splits(rows, cin, cout, taps);
-    return (size_t)splits * ((size_t)cout * taps * cin + (size_t)cout) * sizeof(float);
+    size_t simt = (size_t)splits * ((size_t)cout * taps * cin + (size_t)cout);
+    const int pad = (taps - 1) / 2;
+    size_t tc1 = agcn_conv_wgrad_tc_workspace_floats(nb, t_in, t_out, v, cin, cout, taps, 1, pad);
+    size_t tc2 = agcn_conv_wgrad_tc_workspace_floats(nb, t_in, t_out, v, cin, cout, taps, 2, pad);
+    size_t tc = (tc1 > tc2 ? tc1 : tc2) + (size_t)kBiasPartials * cout;
+    return (simt > tc ? simt : tc) * sizeof(float);
 }
 
 extern "C" AGCN_API int agcn_conv_wgrad(const float* dy, const float* x, float* dw, float* dbias,
                                int nb, int t_in, int t_out, int v, int cin, int cout,
                                int taps, int stride, int pad,
                                void* workspace, size_t workspace_bytes, int precision, void* stream) {
-    (void)precision;
     AGCN_REQUIRE(dy && x && dw && workspace, AGCN_ERR_NULL, "agcn_conv_wgrad: null pointer");
     AGCN_REQUIRE(nb > 0 && t_in > 0 && t_out > 0 && v > 0 && cin > 0 && cout > 0 && taps > 0 && stride > 0 && pad >= 0,
                  AGCN_ERR_BAD_SHAPE, "agcn_conv_wgrad: bad shape");
     const size_t need = agcn_conv_wgrad_workspace_bytes(nb, t_in, t_out, v, cin, cout, taps);
     AGCN_REQUIRE(workspace_bytes >= need, AGCN_ERR_WORKSPACE, "agcn_conv_wgrad: workspace %zu < %zu", workspace_bytes, need);
     AGCN_REQUIRE(aligned16(workspace), AGCN_ERR_MISALIGNED, "agcn_conv_wgrad: workspace not 16-byte aligned");
+    AGCN_REQUIRE(precision == AGCN_PREC_FP32 || precision == AGCN_PREC_TF32, AGCN_ERR_UNSUPPORTED, "agcn_conv_wgrad: unknown precision %d", precision);
+    const size_t tc_floats = agcn_conv_wgrad_tc_workspace_floats(nb, t_in, t_out, v, cin, cout, taps, stride, pad);
+    if (precision == AGCN_PREC_TF32 && tc_floats > 0 && (tc_floats + (size_t)kBiasPartials * cout) * sizeof(float) <= workspace_bytes) {
+        float* ws = static_cast<float*>(workspace);
+        int tc_splits = 0;
+        int rc = agcn_conv_wgrad_tc(dy, x, ws, &tc_splits, nb, t_in, t_out, v, cin, cout, taps, stride, pad, stream);
+        if (rc == AGCN_OK) {
+            cudaStream_t s = static_cast<cudaStream_t>(stream);
+            const long long wsize = (long long)cout * taps * cin;
+            wgrad_reduce_kernel<<<ceil_div(wsize, 256), 256, 0, s>>>(ws, nullptr, dw, nullptr, wsize, cout, tc_splits);
+            rc = check_launch("agcn_conv_wgrad(tc reduce)");
+            if (rc) return rc;
+            if (dbias) {
+                float* part = ws + (size_t)tc_splits * wsize;
+                const long long rows = (long long)nb * t_out * v;
+                int P = (int)((rows + 255) / 256);
+                if (P > kBiasPartials) P = kBiasPartials;
+                dim3 grid((unsigned)P, (unsigned)ceil_div(cout, 32));
+                bias_partial_kernel<<<grid, 256, 0, s>>>(dy, rows, cout, part);
+                rc = check_launch("agcn_conv_wgrad(bias partial)");
+                if (rc) return rc;
+                wgrad_reduce_kernel<<<ceil_div(cout, 256), 256, 0, s>>>(nullptr, part, nullptr, dbias, 0, cout, P);
+                rc = check_launch("agcn_conv_wgrad(bias reduce)");
+            }
+            return rc;
+        }
+        if (rc != AGCN_ERR_UNSUPPORTED) return rc;      // unsupported shapes fall through to the FFMA kernel
+    }
     WgradArgs a;
     a.dy = dy; a.x = x;
     a.nb = nb; a.t_in = t_in; a.t_out = t_out; a.v = v; a.cin = cin; a.cout = cout;

@@ -279,6 +279,207 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
+
+// ================================================================================================ weight gradient
+//   dw[co][tap][ci] = sum_rows dy[row][co] * x[gather(row, tap)][ci]
+// UMMA view: D[M = co (128)][N = ci (<=256)] += A[M x K] * B[N x K]^T with K = rows.  Both operands are MN-major in
+// shared memory: a TMA box of 32 channels x R rows lands as R rows of 128 bytes (128B swizzle), which is exactly the
+// canonical MN-major "128B swizzle, 32-byte atom" layout that tf32 MN-major operands require (32 fp32 along MN,
+// 4 rows along K per 512-byte atom; TMA swizzle CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).  One MMA (K = 8) consumes two
+// 4-row groups (SBO = 512 B) of every 32-channel sub-box; sub-boxes are LBO = rpad*128 bytes apart.
+// Split-K over row chunks across CTAs; partial tiles go to the workspace and are summed by wgrad_reduce_kernel
+// (deterministic).  Rows [rows_box, rpad) of every sub-box are zero (shared memory is cleared once, TMA never writes them).
+struct WgArgs {
+    float* ws;
+    int nb, t_in, t_out, v, cin, cout, taps, stride, pad;
+    int flat, rows_box, rpad, tt, chunks_per_sample;
+    long long chunks_total, chunks_per_split;
+    int n_tile, n_tiles, m_tiles, stages;
+};
+
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;   // leading byte offset: between 32-channel (MN) atoms
+    d |= (uint64_t)(512 >> 4) << 32;                     // stride byte offset: between 4-row (K) groups of the 32B-atom swizzle
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;                              // SWIZZLE_128B_BASE32B: the only layout for MN-major tf32 operands
+    return d;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, WgArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sub_bytes = (uint32_t)a.rpad * 128u;
+    const uint32_t nsub_b = (uint32_t)a.n_tile / 32u;
+    const uint32_t stage_bytes = (4u + nsub_b) * sub_bytes;
+    const uint32_t bar_base = smem_base + (uint32_t)a.stages * stage_bytes;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+    const uint32_t tfull_bar = bar_base + 8u * (2 * kStages);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // clear the operand stages once: rows the TMA boxes never write must read as zero in the K reduction
+    {
+        uint8_t* base_ptr = smem_raw + (smem_base - smem_u32(smem_raw));
+        uint4* p4 = reinterpret_cast<uint4*>(base_ptr);
+        const uint32_t n16 = (uint32_t)a.stages * stage_bytes / 16u;
+        for (uint32_t i = threadIdx.x; i < n16; i += kThreads) p4[i] = make_uint4(0, 0, 0, 0);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy zeros visible to TMA / UMMA
+    }
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dy) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(tfull_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    int tile = blockIdx.x;
+    const int nt = tile % a.n_tiles; tile /= a.n_tiles;
+    const int mt = tile % a.m_tiles;
+    const int tap = tile / a.m_tiles;
+    const int m0 = mt * 128, k0 = nt * a.n_tile;
+    const int split = blockIdx.y;
+    const long long c_begin = (long long)split * a.chunks_per_split;
+    long long c_end = c_begin + a.chunks_per_split;
+    if (c_end > a.chunks_total) c_end = a.chunks_total;
+    const int a_boxes = (a.cout - m0 + 31) / 32 < 4 ? (a.cout - m0 + 31) / 32 : 4;
+    const int b_boxes = (a.cin - k0 + 31) / 32 < (int)nsub_b ? (a.cin - k0 + 31) / 32 : (int)nsub_b;
+    const uint32_t stage_tx = (uint32_t)(a_boxes + b_boxes) * (uint32_t)a.rows_box * 128u;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (long long c = c_begin; c < c_end; ++c) {
+                const int n = (int)(c / a.chunks_per_sample);
+                const int cs = (int)(c - (long long)n * a.chunks_per_sample);
+                int a1, a2, b1, b2;
+                if (a.flat) { a1 = cs * a.rows_box; a2 = 0; b1 = a1 + (tap - a.pad) * a.v; b2 = 0; }
+                else { a1 = 0; a2 = cs * a.tt; b1 = 0; b2 = a.stride * a2 + tap - a.pad; }
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                mbar_expect_tx(full_bar(stage), stage_tx);
+                const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
+                for (int i = 0; i < a_boxes; ++i) tma_load_4d(sa + i * sub_bytes, &map_dy, full_bar(stage), m0 + 32 * i, a1, a2, n);
+                const uint32_t sb = sa + 4u * sub_bytes;
+                for (int j = 0; j < b_boxes; ++j) tma_load_4d(sb + j * sub_bytes, &map_x, full_bar(stage), k0 + 32 * j, b1, b2, n);
+                if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // tf32 x tf32 -> f32, A and B MN-major, M = 128, N = n_tile
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                                   ((uint32_t)(a.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+            int stage = 0; uint32_t phase = 0;
+            uint32_t first = 1;
+            for (long long c = c_begin; c < c_end; ++c) {
+                mbar_wait(full_bar(stage), phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
+                const uint64_t da = make_smem_desc_mn(sa, sub_bytes), db = make_smem_desc_mn(sa + 4u * sub_bytes, sub_bytes);
+                for (int kg = 0; kg < a.rpad / 8; ++kg) {
+                    umma_tf32(tmem_base, da + (uint64_t)(kg * 64), db + (uint64_t)(kg * 64), idesc, first ? 0u : 1u);
+                    first = 0;
+                }
+                umma_commit(empty_bar(stage));
+                if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+            }
+            umma_commit(tfull_bar);
+        }
+    } else {
+        const int q = warp & 3;
+        const int co = m0 + q * 32 + lane;
+        mbar_wait(tfull_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        float* out = a.ws + (((long long)split * a.cout + co) * a.taps + tap) * a.cin + k0;
+        for (int c = 0; c < a.n_tile; c += 16) {
+            float vals[16];
+            tmem_ld16(taddr + (uint32_t)c, vals);
+            if (co < a.cout) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    if (k0 + c + g * 4 < a.cin)
+                        *reinterpret_cast<float4*>(out + c + g * 4) = make_float4(vals[g * 4], vals[g * 4 + 1], vals[g * 4 + 2], vals[g * 4 + 3]);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    }
+}
+
+struct WgPlan {
+    bool ok;
+    WgArgs a;
+    int splits;
+    size_t smem;
+};
+
+static WgPlan plan_wgrad(int nb, int t_in, int t_out, int v, int cin, int cout, int taps, int stride, int pad) {
+    WgPlan p;
+    p.ok = false;
+    if (cin % 4 || cout % 4 || v > 128 || stride > 4) return p;
+    WgArgs& a = p.a;
+    a.ws = nullptr;
+    a.nb = nb; a.t_in = t_in; a.t_out = t_out; a.v = v; a.cin = cin; a.cout = cout; a.taps = taps; a.stride = stride; a.pad = pad;
+    a.n_tile = ((cin + 31) / 32) * 32;
+    if (a.n_tile > 256) a.n_tile = 256;
+    a.n_tiles = (cin + a.n_tile - 1) / a.n_tile;
+    a.m_tiles = (cout + 127) / 128;
+    const int nsub = 4 + a.n_tile / 32;
+    int rmax = (48 * 1024) / (nsub * 128);           // rows per stage so that a stage stays <= 48 KB
+    rmax = rmax / 8 * 8;
+    if (rmax > 128) rmax = 128;
+    a.flat = (stride == 1 && t_in == t_out) ? 1 : 0;
+    if (a.flat) {
+        a.rows_box = rmax;
+        a.rpad = rmax;
+        a.tt = 0;
+        a.chunks_per_sample = (t_out * v + a.rows_box - 1) / a.rows_box;
+    } else {
+        a.tt = rmax / v;
+        if (a.tt < 1) { a.tt = 1; }
+        while (a.tt * stride > 256) --a.tt;
+        a.rows_box = a.tt * v;
+        a.rpad = (a.rows_box + 7) / 8 * 8;
+        if ((size_t)nsub * a.rpad * 128 > 96 * 1024) return p;
+        a.chunks_per_sample = (t_out + a.tt - 1) / a.tt;
+    }
+    a.chunks_total = (long long)nb * a.chunks_per_sample;
+    const size_t stage_bytes = (size_t)nsub * a.rpad * 128;
+    int stages = (int)((192 * 1024) / stage_bytes);
+    if (stages > kStages) stages = kStages;
+    if (stages < 2) return p;
+    a.stages = stages;
+    const long long tiles = (long long)taps * a.m_tiles * a.n_tiles;
+    long long splits = (2LL * kNumSMs + tiles - 1) / tiles;
+    if (splits > kNumSMs) splits = kNumSMs;
+    if (splits > a.chunks_total) splits = a.chunks_total;
+    if (splits < 1) splits = 1;
+    a.chunks_per_split = (a.chunks_total + splits - 1) / splits;
+    splits = (a.chunks_total + a.chunks_per_split - 1) / a.chunks_per_split;
+    p.splits = (int)splits;
+    p.smem = (size_t)stages * stage_bytes + 1024 + 256;
+    p.ok = true;
+    return p;
+}
+
 }  // namespace tc
 }  // namespace agcn
 
@@ -346,4 +547,54 @@ int agcn_conv_fwd_tc(const float* x, const float* w, const float* bias, float* y
     long long grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
     conv_tc_kernel<<<(unsigned)grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(map_a, map_b, a);
     return check_launch("agcn_conv_fwd_tc");
+}
+
+// ---- weight gradient on tensor cores; returns AGCN_ERR_UNSUPPORTED for shapes outside the path
+size_t agcn_conv_wgrad_tc_workspace_floats(int nb, int t_in, int t_out, int v, int cin, int cout, int taps, int stride, int pad) {
+    agcn::tc::WgPlan p = agcn::tc::plan_wgrad(nb, t_in, t_out, v, cin, cout, taps, stride, pad);
+    if (!p.ok) return 0;
+    return (size_t)p.splits * cout * taps * cin;
+}
+
+int agcn_conv_wgrad_tc(const float* dy, const float* x, float* ws, int* splits_out,
+                       int nb, int t_in, int t_out, int v, int cin, int cout, int taps, int stride, int pad, void* stream) {
+    using namespace agcn::tc;
+    if (!aligned16(dy) || !aligned16(x) || !aligned16(ws)) return AGCN_ERR_UNSUPPORTED;
+    WgPlan p = plan_wgrad(nb, t_in, t_out, v, cin, cout, taps, stride, pad);
+    if (!p.ok) return AGCN_ERR_UNSUPPORTED;
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return fail(AGCN_ERR_CUDA, "agcn_conv_wgrad_tc: cuTensorMapEncodeTiled is not available from the driver");
+    WgArgs& a = p.a;
+    a.ws = ws;
+    CUtensorMap map_dy, map_x;
+    auto encode = [&](CUtensorMap* m, const float* ptr, int c, int t, int box1, int box2, int es2) -> CUresult {
+        cuuint64_t dims[4]; cuuint64_t strides[3]; cuuint32_t box[4]; cuuint32_t estr[4] = {1, 1, 1, 1};
+        if (a.flat) {
+            dims[0] = c; dims[1] = (cuuint64_t)t * v; dims[2] = 1; dims[3] = nb;
+            strides[0] = (cuuint64_t)c * 4; strides[1] = (cuuint64_t)t * v * c * 4; strides[2] = (cuuint64_t)t * v * c * 4;
+            box[0] = 32; box[1] = box1; box[2] = 1; box[3] = 1;
+        } else {
+            dims[0] = c; dims[1] = v; dims[2] = t; dims[3] = nb;
+            strides[0] = (cuuint64_t)c * 4; strides[1] = (cuuint64_t)v * c * 4; strides[2] = (cuuint64_t)t * v * c * 4;
+            box[0] = 32; box[1] = v; box[2] = box2; box[3] = 1;
+            estr[2] = es2;
+        }
+        return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    };
+    CUresult r = encode(&map_dy, dy, cout, t_out, a.rows_box, a.tt, 1);
+    if (r != CUDA_SUCCESS) return fail(AGCN_ERR_CUDA, "agcn_conv_wgrad_tc: cuTensorMapEncodeTiled(dy) failed with %d", (int)r);
+    r = encode(&map_x, x, cin, t_in, a.rows_box, a.tt * stride, stride);
+    if (r != CUDA_SUCCESS) return fail(AGCN_ERR_CUDA, "agcn_conv_wgrad_tc: cuTensorMapEncodeTiled(x) failed with %d", (int)r);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return fail(AGCN_ERR_CUDA, "agcn_conv_wgrad_tc: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    dim3 grid((unsigned)(taps * a.m_tiles * a.n_tiles), (unsigned)p.splits);
+    wgrad_tc_kernel<<<grid, kThreads, p.smem, static_cast<cudaStream_t>(stream)>>>(map_dy, map_x, a);
+    *splits_out = p.splits;
+    return check_launch("agcn_conv_wgrad_tc");
 }

@@ -178,3 +178,36 @@ def test_error_paths_raise(K):
         K.conv_fwd(torch.randn(1, 2, 3, 4), torch.randn(4, 1, 4).cuda())
     with pytest.raises(RuntimeError, match="status 2"):
         K.joint_mix(torch.randn(1, 2, 40, 8).cuda(), torch.randn(1, 3, 40, 40).cuda(), width=8, mode=K.MIX_AGG_FWD)
+
+
+def _trunc_tf32(t):
+    return (t.view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
+TC_CASES = [  # nb, t_in, v, cin, cout, taps, stride  (shapes the tcgen05 path takes; others fall back to FFMA)
+    (2, 20, 25, 64, 64, 9, 1), (2, 21, 25, 64, 128, 9, 2), (2, 12, 25, 16, 96, 1, 1), (2, 14, 20, 64, 128, 9, 1),
+    (1, 10, 25, 768, 256, 1, 1), (2, 14, 22, 32, 32, 9, 1), (2, 20, 18, 128, 256, 1, 2)]
+
+
+@pytest.mark.parametrize("nb,t_in,v,cin,cout,taps,stride", TC_CASES)
+def test_tf32_tensor_core_path(K, nb, t_in, v, cin, cout, taps, stride):
+    """AGCN_PREC_TF32 (tcgen05.mma kind::tf32): the hardware truncates fp32 operands to TF32, so against an fp64
+    contraction of TF32-truncated inputs the result must be fp32-accumulation exact (1e-5); against the raw inputs the
+    stated TF32 tolerance is 3e-3."""
+    pad = (taps - 1) // 2
+    t_out = (t_in + 2 * pad - taps) // stride + 1
+    x, w, b = rnd(nb, t_in, v, cin), rnd(cout, taps, cin, seed=1) * 0.1, rnd(cout, seed=2)
+    kw = dict(t_out=t_out, stride=stride, pad=pad)
+    y = K.conv_fwd(x.cuda(), w.cuda(), b.cuda(), precision=K.PREC_TF32, **kw)
+    assert rel_err(y, S.conv_fwd(_trunc_tf32(x).double(), _trunc_tf32(w).double(), b.double(), **kw)) <= 1e-5
+    assert rel_err(y, S.conv_fwd(x.double(), w.double(), b.double(), **kw)) <= 3e-3
+    dy = rnd(nb, t_out, v, cout, seed=4)
+    wt = w.permute(2, 1, 0).contiguous()
+    kw_t = dict(t_out=t_in, stride=stride, pad=pad, transposed=True)
+    base = rnd(nb, t_in, v, cin, seed=5)
+    dx = K.conv_fwd(dy.cuda(), wt.cuda(), None, out=base.cuda().clone(), accumulate=True, precision=K.PREC_TF32, **kw_t)
+    assert rel_err(dx, S.conv_fwd(_trunc_tf32(dy).double(), _trunc_tf32(wt).double(), None, **kw_t) + base.double()) <= 1e-5
+    dw, db = K.conv_wgrad(dy.cuda(), x.cuda(), taps=taps, stride=stride, pad=pad, precision=K.PREC_TF32)
+    dw_ref, db_ref = S.conv_wgrad(_trunc_tf32(dy).double(), _trunc_tf32(x).double(), taps=taps, stride=stride, pad=pad)
+    assert rel_err(dw, dw_ref) <= 2e-5
+    assert rel_err(db, S.conv_wgrad(dy.double(), x.double(), taps=taps, stride=stride, pad=pad)[1]) <= 5e-6

@@ -157,3 +157,29 @@ def test_standalone_modules_reference_layout(pkg):
     with pytest.raises(NotImplementedError):
         unit.eval()
         unit(x.requires_grad_(True)).sum().backward()
+
+
+def test_tf32_mode_model_tolerance(pkg):
+    """TF32 mode (tcgen05 tensor cores, operands truncated to TF32) is reported separately from the fp32 parity mode.
+    Stated tolerance: 2e-2 on logits and non-degenerate gradients of a 10-unit model (measured ~1e-3..1e-2)."""
+    from fusion_gcn_b200 import graph as G, modules as M
+    shape, start, n = (2, 40, 25, 3), 32, 2
+    graph = G.SkeletonGraph(G.NTU_EDGES, center_joint=G.NTU_CENTER)
+    state = O.init_state(G.adjacency_from_graph(graph), shape, 60, start=start, seed=3, loud=True)
+    gen = torch.Generator().manual_seed(6)
+    x = torch.randn(n, *shape, generator=gen)
+    w = torch.randn(n, 60, generator=gen)
+    p = O.as_leaves(state, torch.float64)
+    y_ref = O.model_forward(x.double(), p, 3, True, start=start)
+    (y_ref * w.double()).sum().backward()
+    p32 = O.as_leaves(state, torch.float32)
+    (O.model_forward(x, p32, 3, True, start=start) * w).sum().backward()
+    model = M.set_precision(M.Model(shape, 60, graph, start_feature_size=start), "tf32")
+    model.load_state_dict(state, strict=True)
+    model.cuda().train()
+    y = model(x.cuda())
+    (y * w.cuda()).sum().backward()
+    assert rel_err(y, y_ref) <= 2e-2
+    worst = check_grads({k: q.grad for k, q in model.named_parameters()}, {k: a.grad for k, a in p.items() if a.requires_grad}, 2e-2,
+                        "tf32", ref32={k: a.grad for k, a in p32.items() if a.requires_grad})
+    print("tf32 mode: logits err", rel_err(y, y_ref), "worst grad", worst)

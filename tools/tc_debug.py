@@ -28,7 +28,77 @@ CASES = {  # name: nb, t_in, v, cin, cout, taps, stride, transposed, bias, accum
 }
 
 
+WG_CASES = {  # name: nb, t_in, v, cin, cout, taps, stride
+    "wg_1x1": (2, 12, 25, 64, 64, 1, 1),
+    "wg_1x1_odd": (3, 13, 20, 48, 96, 1, 1),
+    "wg_taps9": (2, 20, 25, 64, 64, 9, 1),
+    "wg_c256": (2, 20, 25, 256, 256, 9, 1),
+    "wg_k768": (2, 10, 25, 768, 256, 1, 1),
+    "wg_m384": (2, 10, 25, 256, 384, 1, 1),
+    "wg_stride2": (2, 21, 25, 64, 128, 9, 2),
+    "wg_res_stride2": (2, 20, 22, 64, 128, 1, 2),
+    "wg_fc": (1, 1, 64, 256, 60, 1, 1),
+    "wg_big": (128, 300, 25, 64, 64, 9, 1),
+    "wg_big256": (128, 75, 25, 256, 256, 9, 1),
+}
+
+
+def run_wg_case(name):
+    import torch
+    from fusion_gcn_b200 import ops as K
+    from oracle import stages as S
+    nb, t_in, v, cin, cout, taps, stride = WG_CASES[name]
+    pad = (taps - 1) // 2
+    t_out = (t_in + 2 * pad - taps) // stride + 1
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(nb, t_in, v, cin, generator=g)
+    dy = torch.randn(nb, t_out, v, cout, generator=g)
+    kw = dict(taps=taps, stride=stride, pad=pad)
+    xc, dyc = x.cuda(), dy.cuda()
+    dw, db = K.conv_wgrad(dyc, xc, precision=K.PREC_TF32, **kw)
+    torch.cuda.synchronize()
+    big = nb * t_out * v > 100000
+
+    def trunc(t_):
+        return (t_.view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+    if big:
+        ref_raw, db_ref = K.conv_wgrad(dyc, xc, precision=K.PREC_FP32, **kw)
+        ref_raw, db_ref = ref_raw.double().cpu(), db_ref.double().cpu()
+        ref_tr = K.conv_wgrad(trunc(dy).cuda(), trunc(x).cuda(), precision=K.PREC_FP32, **kw)[0].double().cpu()
+    else:
+        ref_raw, db_ref = S.conv_wgrad(dy.double(), x.double(), **kw)
+        ref_tr = S.conv_wgrad(trunc(dy).double(), trunc(x).double(), **kw)[0]
+    d = dw.double().cpu()
+    e_raw = ((d - ref_raw).abs().max() / ref_raw.abs().max()).item()
+    e_tr = ((d - ref_tr).abs().max() / ref_tr.abs().max()).item()
+    e_b = ((db.double().cpu() - db_ref).abs().max() / db_ref.abs().max()).item()
+    print(f"[{name}] dw rel err vs raw {e_raw:.3e} | vs truncated-TF32 {e_tr:.3e} | dbias {e_b:.3e}")
+    if e_raw > 5e-3:
+        err = (d - ref_raw).abs() > 1e-2 * ref_raw.abs().max()
+        print("   bad co:", err.any(dim=2).any(dim=1).nonzero().flatten()[:32].tolist())
+        print("   bad tap:", err.any(dim=2).any(dim=0).nonzero().flatten().tolist())
+        print("   bad ci:", err.any(dim=1).any(dim=0).nonzero().flatten()[:32].tolist())
+        print("   dw[0,0,:8] ", d[0, 0, :8].tolist())
+        print("   ref[0,0,:8]", ref_raw[0, 0, :8].tolist())
+    if big:
+        for prec, label in ((K.PREC_TF32, "tf32 tcgen05"), (K.PREC_FP32, "fp32 FFMA")):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for _ in range(2):
+                K.conv_wgrad(dyc, xc, precision=prec, **kw)
+            e0.record()
+            for _ in range(5):
+                K.conv_wgrad(dyc, xc, precision=prec, **kw)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+            fl = 2.0 * nb * t_out * v * cin * cout * taps
+            print(f"   {label}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s")
+
+
 def run_case(name):
+    if name in WG_CASES:
+        return run_wg_case(name)
     import torch
     from fusion_gcn_b200 import ops as K
     from oracle import stages as S
@@ -101,7 +171,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 2 and sys.argv[1] == "--one":
         run_case(sys.argv[2])
         sys.exit(0)
-    names = sys.argv[1:] or list(CASES)
+    names = sys.argv[1:] or (list(CASES) + list(WG_CASES))
     for n in names:
         try:
             p = subprocess.run([sys.executable, os.path.abspath(__file__), "--one", n], timeout=90, capture_output=True, text=True)
