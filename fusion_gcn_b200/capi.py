@@ -11,8 +11,9 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libagcn_b200.so")
 
-PREC_FP32 = 0
-PREC_TF32 = 1
+PREC_FP32 = 0          # fp32 parity: 3xTF32 tensor cores where possible, FFMA otherwise
+PREC_TF32 = 1          # single-pass TF32 tensor cores
+PREC_FP32_FFMA = 2     # force FFMA
 MIX_AGG_FWD, MIX_AGG_BWD, MIX_SCORE_BWD = 0, 1, 2
 RES_NONE, RES_TENSOR, RES_AFFINE = 0, 1, 2
 
@@ -23,7 +24,8 @@ SIGNATURES = {
     "agcn_version": (_c_int, []),
     "agcn_last_error_string": (ctypes.c_char_p, []),
     "agcn_launch_count": (_c_ll, []),
-    "agcn_conv_fwd": (_c_int, [_c_void_p] * 4 + [_c_int] * 12 + [_c_void_p]),
+    "agcn_conv_fwd_workspace_bytes": (_c_size_t, [_c_int] * 4),
+    "agcn_conv_fwd": (_c_int, [_c_void_p] * 4 + [_c_int] * 12 + [_c_void_p, _c_size_t, _c_void_p]),
     "agcn_conv_wgrad_workspace_bytes": (_c_size_t, [_c_int] * 7),
     "agcn_conv_wgrad": (_c_int, [_c_void_p] * 4 + [_c_int] * 9 + [_c_void_p, _c_size_t, _c_int, _c_void_p]),
     "agcn_joint_gram": (_c_int, [_c_void_p] * 3 + [_c_int] * 12 + [_c_void_p]),

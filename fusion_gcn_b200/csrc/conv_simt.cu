@@ -321,29 +321,38 @@ static int wgrad_splits(long long rows, int cin, int cout, int taps) {
 
 using namespace agcn;
 
-// implemented in conv_tc.cu; returns AGCN_ERR_UNSUPPORTED when the shape is outside the tensor-core path
+// implemented in conv_tc.cu; return AGCN_ERR_UNSUPPORTED when the shape is outside the tensor-core path
 int agcn_conv_fwd_tc(const float* x, const float* w, const float* bias, float* y,
                      int nb, int t_in, int t_out, int v, int cin, int cout,
-                     int taps, int stride, int pad, int transposed, int accumulate, void* stream);
-
-size_t agcn_conv_wgrad_tc_workspace_floats(int nb, int t_in, int t_out, int v, int cin, int cout, int taps, int stride, int pad);
+                     int taps, int stride, int pad, int transposed, int accumulate, int split, float* w_lo, void* stream);
+size_t agcn_conv_wgrad_tc_workspace_floats(int nb, int t_in, int t_out, int v, int cin, int cout, int taps, int stride, int pad, int split);
 int agcn_conv_wgrad_tc(const float* dy, const float* x, float* ws, int* splits_out,
-                       int nb, int t_in, int t_out, int v, int cin, int cout, int taps, int stride, int pad, void* stream);
+                       int nb, int t_in, int t_out, int v, int cin, int cout, int taps, int stride, int pad, int split, void* stream);
+
+static bool known_precision(int p) { return p == AGCN_PREC_FP32 || p == AGCN_PREC_TF32 || p == AGCN_PREC_FP32_FFMA; }
+
+extern "C" AGCN_API size_t agcn_conv_fwd_workspace_bytes(int cin, int cout, int taps, int precision) {
+    if (precision != AGCN_PREC_FP32 || cin <= 0 || cout <= 0 || taps <= 0) return 0;
+    return (size_t)2 * cout * taps * cin * sizeof(float);   // TF32 hi | lo split of the weights for the 3xTF32 path
+}
 
 extern "C" AGCN_API int agcn_conv_fwd(const float* x, const float* w, const float* bias, float* y,
                              int nb, int t_in, int t_out, int v, int cin, int cout,
                              int taps, int stride, int pad, int transposed, int accumulate,
-                             int precision, void* stream) {
+                             int precision, void* workspace, size_t workspace_bytes, void* stream) {
     AGCN_REQUIRE(x && w && y, AGCN_ERR_NULL, "agcn_conv_fwd: null pointer");
     AGCN_REQUIRE(nb > 0 && t_in > 0 && t_out > 0 && v > 0 && cin > 0 && cout > 0 && taps > 0 && stride > 0 && pad >= 0,
                  AGCN_ERR_BAD_SHAPE, "agcn_conv_fwd: bad shape nb=%d t_in=%d t_out=%d v=%d cin=%d cout=%d taps=%d stride=%d pad=%d",
                  nb, t_in, t_out, v, cin, cout, taps, stride, pad);
-    AGCN_REQUIRE(precision == AGCN_PREC_FP32 || precision == AGCN_PREC_TF32, AGCN_ERR_UNSUPPORTED,
-                 "agcn_conv_fwd: unknown precision %d", precision);
-    if (precision == AGCN_PREC_TF32) {
-        int rc = agcn_conv_fwd_tc(x, w, bias, y, nb, t_in, t_out, v, cin, cout, taps, stride, pad, transposed,
-                                  accumulate, stream);
-        if (rc != AGCN_ERR_UNSUPPORTED) return rc;   // unsupported shapes fall through to the FFMA kernel
+    AGCN_REQUIRE(known_precision(precision), AGCN_ERR_UNSUPPORTED, "agcn_conv_fwd: unknown precision %d", precision);
+    if (precision == AGCN_PREC_TF32 || precision == AGCN_PREC_FP32) {
+        const int split = precision == AGCN_PREC_FP32;
+        const bool ws_ok = !split || (workspace != nullptr && workspace_bytes >= agcn_conv_fwd_workspace_bytes(cin, cout, taps, precision));
+        if (ws_ok) {
+            int rc = agcn_conv_fwd_tc(x, w, bias, y, nb, t_in, t_out, v, cin, cout, taps, stride, pad, transposed,
+                                      accumulate, split, static_cast<float*>(workspace), stream);
+            if (rc != AGCN_ERR_UNSUPPORTED) return rc;   // unsupported shapes fall through to the FFMA kernel
+        }
     }
     ConvArgs a{x, w, bias, y, nb, t_in, t_out, v, cin, cout, taps, stride, pad, transposed, accumulate,
                (long long)nb * t_out * v};
@@ -360,9 +369,13 @@ extern "C" AGCN_API size_t agcn_conv_wgrad_workspace_bytes(int nb, int t_in, int
     int splits = wgrad_splits(rows, cin, cout, taps);
     size_t simt = (size_t)splits * ((size_t)cout * taps * cin + (size_t)cout);
     const int pad = (taps - 1) / 2;
-    size_t tc1 = agcn_conv_wgrad_tc_workspace_floats(nb, t_in, t_out, v, cin, cout, taps, 1, pad);
-    size_t tc2 = agcn_conv_wgrad_tc_workspace_floats(nb, t_in, t_out, v, cin, cout, taps, 2, pad);
-    size_t tc = (tc1 > tc2 ? tc1 : tc2) + (size_t)kBiasPartials * cout;
+    size_t tc = 0;
+    for (int stride = 1; stride <= 2; ++stride)
+        for (int split = 0; split <= 1; ++split) {
+            size_t f = agcn_conv_wgrad_tc_workspace_floats(nb, t_in, t_out, v, cin, cout, taps, stride, pad, split);
+            if (f > tc) tc = f;
+        }
+    tc += (size_t)kBiasPartials * cout;
     return (simt > tc ? simt : tc) * sizeof(float);
 }
 
@@ -376,12 +389,14 @@ extern "C" AGCN_API int agcn_conv_wgrad(const float* dy, const float* x, float* 
     const size_t need = agcn_conv_wgrad_workspace_bytes(nb, t_in, t_out, v, cin, cout, taps);
     AGCN_REQUIRE(workspace_bytes >= need, AGCN_ERR_WORKSPACE, "agcn_conv_wgrad: workspace %zu < %zu", workspace_bytes, need);
     AGCN_REQUIRE(aligned16(workspace), AGCN_ERR_MISALIGNED, "agcn_conv_wgrad: workspace not 16-byte aligned");
-    AGCN_REQUIRE(precision == AGCN_PREC_FP32 || precision == AGCN_PREC_TF32, AGCN_ERR_UNSUPPORTED, "agcn_conv_wgrad: unknown precision %d", precision);
-    const size_t tc_floats = agcn_conv_wgrad_tc_workspace_floats(nb, t_in, t_out, v, cin, cout, taps, stride, pad);
-    if (precision == AGCN_PREC_TF32 && tc_floats > 0 && (tc_floats + (size_t)kBiasPartials * cout) * sizeof(float) <= workspace_bytes) {
+    AGCN_REQUIRE(known_precision(precision), AGCN_ERR_UNSUPPORTED, "agcn_conv_wgrad: unknown precision %d", precision);
+    const int tc_split = precision == AGCN_PREC_FP32;
+    const size_t tc_floats = precision == AGCN_PREC_FP32_FFMA ? 0 :
+        agcn_conv_wgrad_tc_workspace_floats(nb, t_in, t_out, v, cin, cout, taps, stride, pad, tc_split);
+    if (tc_floats > 0 && (tc_floats + (size_t)kBiasPartials * cout) * sizeof(float) <= workspace_bytes) {
         float* ws = static_cast<float*>(workspace);
         int tc_splits = 0;
-        int rc = agcn_conv_wgrad_tc(dy, x, ws, &tc_splits, nb, t_in, t_out, v, cin, cout, taps, stride, pad, stream);
+        int rc = agcn_conv_wgrad_tc(dy, x, ws, &tc_splits, nb, t_in, t_out, v, cin, cout, taps, stride, pad, tc_split, stream);
         if (rc == AGCN_OK) {
             cudaStream_t s = static_cast<cudaStream_t>(stream);
             const long long wsize = (long long)cout * taps * cin;

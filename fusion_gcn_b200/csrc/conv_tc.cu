@@ -15,19 +15,67 @@
 //               tcgen05.commit releases the smem stage / publishes the accumulator
 //   warps 2..5  epilogue: tcgen05.ld (32 lanes x 16 columns) -> +bias (+old) -> coalesced-per-row st.global
 // TMEM: 2 x 128 columns, so the epilogue of tile i overlaps the main loop of tile i+1.
+//
+// Precision.  tcgen05.mma kind::tf32 reads fp32 words from shared memory and uses their upper 19 bits (measured on
+// B200: results match an fp64 contraction of TF32-TRUNCATED operands to 1e-6).  SPLIT = false is that single pass
+// (AGCN_PREC_TF32).  SPLIT = true is the fp32-parity mode (AGCN_PREC_FP32, "3xTF32"): with hi = rna_tf32(x) (round to
+// nearest, so the split is unbiased) and lo = x - hi (exact in fp32), it issues
+//   lo_a*hi_b + hi_a*lo_b + hi_a*hi_b  =  a*b - lo_a*lo_b  (relative error ~2^-22 per product)
+// The activation hi/lo tiles are produced in shared memory by four transform warps (ld.shared -> cvt.rna -> st.shared in
+// place + lo tile -> fence.proxy.async -> mbarrier arrive); the weight hi/lo tensors are precomputed into the caller's
+// workspace and TMA-loaded.
 #include "common.cuh"
 #include <cuda.h>
 
 namespace agcn {
 namespace tc {
 
-constexpr int kStages = 6;
-constexpr int kStageBytes = 32 * 1024;      // A 16 KB + B 16 KB
+constexpr int kStages = 6;                  // barrier slots; SPLIT kernels use 3 stages of twice the size
 constexpr int kABytes = 16 * 1024;
 constexpr int kKChunk = 32;                 // fp32 elements per 128-byte swizzle row
-constexpr int kThreads = 192;
+constexpr int kThreads = 192;               // TMA warp, MMA warp, 4 epilogue warps
+constexpr int kThreadsSplit = 320;          // + 4 transform warps
 constexpr int kTmemCols = 256;
-constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr size_t kSmemBytes = (size_t)192 * 1024 + 1024 /*alignment slack*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// 3xTF32 operand split of `bytes` bytes at src: hi = rna_tf32(x) overwrites src in place, lo = x - hi (exact) goes to dst
+// at the same offsets, so any swizzle is preserved.  Called by the 128 transform threads.
+__device__ __forceinline__ void transform_split(uint32_t src, uint32_t dst, uint32_t bytes, int tid128) {
+    for (uint32_t off = (uint32_t)tid128 * 16u; off < bytes; off += 128u * 16u) {
+        const float4 v = lds128(src + off);
+        const float4 hi = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+        sts128(src + off, hi);
+        sts128(dst + off, make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w));
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// weights: w_split[0 .. n) = rna_tf32(w), w_split[n .. 2n) = w - hi
+constexpr int kSegment = 4;       // 3xTF32: promote the TMEM accumulator to fp32 registers every 4 k-chunks (K = 128)
+constexpr int kWgSegment = 4;     // 3xTF32 weight gradient: promote every 4 row chunks
+
+__global__ void split_weights_kernel(const float* w, float* w_split, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float v = w[i];
+        const float hi = tf32_rna(v);
+        w_split[i] = hi;
+        w_split[n + i] = v - hi;
+    }
+}
 
 struct TcArgs {
     float* y; const float* bias;
@@ -115,24 +163,39 @@ __device__ __forceinline__ bool tap_valid(const TcArgs& a, int par, int tap, int
     return true;
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcArgs a) {
+// (tap, k-chunk) iterations of one tile
+__device__ __forceinline__ int tile_iters(const TcArgs& a, int par) {
+    int taps = a.taps;
+    if (a.transposed && a.stride > 1) {
+        taps = 0;
+        for (int tap = 0; tap < a.taps; ++tap) taps += ((par + a.pad - tap) % a.stride == 0) ? 1 : 0;
+    }
+    return taps * a.kchunks;
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_blo, TcArgs a) {
+    constexpr int NST = SPLIT ? 3 : 6;
+    constexpr uint32_t STAGE = SPLIT ? 64u * 1024u : 32u * 1024u;     // A raw | B raw | (A lo | B lo)
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar_base = smem_base + kStages * kStageBytes;
-    // barriers: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]; then the TMEM base address word
+    const uint32_t bar_base = smem_base + NST * STAGE;
+    // barriers: full[6], empty[6], lo[6], tmem_full[2], tmem_empty[2]; then the TMEM base address word
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
-    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
-    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
-    const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+    auto lo_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (3 * kStages + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (3 * kStages + 2 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (3 * kStages + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
-        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < NST; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); mbar_init(lo_bar(s), 4); }
         for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -147,7 +210,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
     const int rows_box = a.v * a.tt;
-    const uint32_t stage_tx = (uint32_t)(rows_box * 128 + a.bn * 128);
+    const uint32_t stage_tx = (uint32_t)(rows_box * 128 + a.bn * 128 * (SPLIT ? 2 : 1));
 
     if (warp == 0) {
         // ===================================================== TMA producer
@@ -165,10 +228,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     for (int kc = 0; kc < a.kchunks; ++kc) {
                         mbar_wait(empty_bar(stage), phase ^ 1u);
                         mbar_expect_tx(full_bar(stage), stage_tx);
-                        const uint32_t sa = smem_base + stage * kStageBytes;
+                        const uint32_t sa = smem_base + stage * STAGE;
                         tma_load_4d(sa, &map_a, full_bar(stage), kc * kKChunk, 0, tcoord, n);
-                        tma_load_3d(sa + kABytes, &map_b, full_bar(stage), kc * kKChunk, tap, nt * a.bn);
-                        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                        tma_load_3d(sa + kABytes, &map_b, full_bar(stage), kc * kKChunk, tap, nt * a.bn);        // W (or W hi)
+                        if (SPLIT) tma_load_3d(sa + 3 * kABytes, &map_blo, full_bar(stage), kc * kKChunk, tap, nt * a.bn);
+                        if (++stage == NST) { stage = 0; phase ^= 1u; }
                     }
                 }
             }
@@ -184,32 +248,55 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 r /= a.n_tiles_n;
                 const int jt = (int)(r % a.tiles_t); r /= a.tiles_t;
                 const int par = (int)(r % a.nparity);
+                const int iters = tile_iters(a, par);
+                int it = 0;
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
+                uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
                 uint32_t first = 1;
                 for (int tap = 0; tap < a.taps; ++tap) {
                     int tcoord;
                     if (!tap_valid(a, par, tap, jt, tcoord)) continue;
                     for (int kc = 0; kc < a.kchunks; ++kc) {
                         mbar_wait(full_bar(stage), phase);
+                        if (SPLIT) mbar_wait(lo_bar(stage), phase);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t sa = smem_base + stage * kStageBytes;
+                        const uint32_t sa = smem_base + stage * STAGE;
                         const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + kABytes);
+                        const uint64_t dalo = make_smem_desc(sa + 2 * kABytes), dblo = make_smem_desc(sa + 3 * kABytes);
 #pragma unroll
                         for (int k = 0; k < kKChunk / 8; ++k) {
-                            umma_tf32(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, first ? 0u : 1u);
+                            const uint64_t ko = (uint64_t)(k * 2);
+                            if (SPLIT) {
+                                umma_tf32(d_tmem, dalo + ko, db + ko, idesc, first ? 0u : 1u);
+                                umma_tf32(d_tmem, da + ko, dblo + ko, idesc, 1u);
+                                umma_tf32(d_tmem, da + ko, db + ko, idesc, 1u);
+                            } else {
+                                umma_tf32(d_tmem, da + ko, db + ko, idesc, first ? 0u : 1u);
+                            }
                             first = 0;
                         }
                         umma_commit(empty_bar(stage));          // smem stage reusable once these MMAs retire
-                        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                        if (++stage == NST) { stage = 0; phase ^= 1u; }
+                        ++it;
+                        if (SPLIT && (it % kSegment) == 0 && it < iters) {
+                            // promote: hand this partial accumulator to the epilogue (it adds segments in fp32 registers,
+                            // round-to-nearest) and continue in the other TMEM buffer.  Keeps the chain of truncating
+                            // tensor-core accumulations short (<= kSegment*4*3 MMAs).
+                            umma_commit(tfull_bar(acc));
+                            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                            mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                            d_tmem = tmem_base + (uint32_t)(acc * 128);
+                            first = 1;
+                        }
                     }
                 }
                 umma_commit(tfull_bar(acc));                     // accumulator complete
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         }
-    } else {
+    } else if (warp < 6) {
         // ===================================================== epilogue warps (TMEM lane quarter = warp % 4)
         const int q = warp & 3;
         const int row_local = q * 32 + lane;
@@ -225,35 +312,72 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int to = a.transposed ? a.stride * j + par : j;
             const bool row_ok = (tl < a.tt) && (to < a.t_out);
             float* yrow = a.y + (((long long)n * a.t_out + to) * a.v + vv) * a.cout + nt * a.bn;
-            mbar_wait(tfull_bar(acc), acc_phase);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t taddr = tmem_base + (uint32_t)(acc * 128) + ((uint32_t)(q * 32) << 16);
-            for (int c = 0; c < a.bn; c += 16) {
-                float vals[16];
-                tmem_ld16(taddr + (uint32_t)c, vals);
-                const int col = nt * a.bn + c;
-                if (row_ok) {
+            const int iters = tile_iters(a, par);
+            const int nseg = SPLIT ? (iters + kSegment - 1) / kSegment : 1;
+            float sum[SPLIT ? 128 : 1];              // SPLIT: fp32 running sum of the promoted segments (bn <= 128)
+            for (int sg = 0; sg < nseg; ++sg) {
+                mbar_wait(tfull_bar(acc), acc_phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t taddr = tmem_base + (uint32_t)(acc * 128) + ((uint32_t)(q * 32) << 16);
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        if (col + g * 4 >= a.cout) break;
-                        float4 o = make_float4(vals[g * 4], vals[g * 4 + 1], vals[g * 4 + 2], vals[g * 4 + 3]);
-                        if (a.bias) {
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + col + g * 4));
-                            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                for (int cg = 0; cg < 8; ++cg) {
+                    const int c = cg * 16;
+                    if (c < a.bn) {
+                        float vals[16];
+                        tmem_ld16(taddr + (uint32_t)c, vals);
+                        if (SPLIT) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) sum[SPLIT ? c + i : 0] = (sg == 0) ? vals[i] : sum[SPLIT ? c + i : 0] + vals[i];
                         }
-                        float4* p = reinterpret_cast<float4*>(yrow + c + g * 4);
-                        if (a.accumulate) {
-                            const float4 old = *p;
-                            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                        if (sg == nseg - 1 && row_ok) {
+                            const int col = nt * a.bn + c;
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                if (col + g * 4 >= a.cout) break;
+                                float4 o;
+                                if (SPLIT) o = make_float4(sum[SPLIT ? c + g * 4 : 0], sum[SPLIT ? c + g * 4 + 1 : 0], sum[SPLIT ? c + g * 4 + 2 : 0], sum[SPLIT ? c + g * 4 + 3 : 0]);
+                                else o = make_float4(vals[g * 4], vals[g * 4 + 1], vals[g * 4 + 2], vals[g * 4 + 3]);
+                                if (a.bias) {
+                                    const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + col + g * 4));
+                                    o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                                }
+                                float4* p = reinterpret_cast<float4*>(yrow + c + g * 4);
+                                if (a.accumulate) {
+                                    const float4 old = *p;
+                                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                                }
+                                *p = o;
+                            }
                         }
-                        *p = o;
                     }
                 }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(acc));
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
-            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    } else if (SPLIT) {
+        // ===================================================== transform warps: A -> (hi in place, lo tile)
+        const int tid128 = threadIdx.x - 6 * 32;
+        int stage = 0; uint32_t phase = 0;
+        for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+            long long r = tile;
+            r /= a.n_tiles_n;
+            const int jt = (int)(r % a.tiles_t); r /= a.tiles_t;
+            const int par = (int)(r % a.nparity);
+            for (int tap = 0; tap < a.taps; ++tap) {
+                int tcoord;
+                if (!tap_valid(a, par, tap, jt, tcoord)) continue;
+                for (int kc = 0; kc < a.kchunks; ++kc) {
+                    mbar_wait(full_bar(stage), phase);
+                    const uint32_t sa = smem_base + stage * STAGE;
+                    transform_split(sa, sa + 2 * kABytes, (uint32_t)rows_box * 128u, tid128);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(lo_bar(stage));
+                    if (++stage == NST) { stage = 0; phase ^= 1u; }
+                }
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -307,18 +431,22 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t l
     return d;
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+template <bool SPLIT>
+__global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, WgArgs a) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sub_bytes = (uint32_t)a.rpad * 128u;
     const uint32_t nsub_b = (uint32_t)a.n_tile / 32u;
-    const uint32_t stage_bytes = (4u + nsub_b) * sub_bytes;
+    const uint32_t raw_bytes = (4u + nsub_b) * sub_bytes;
+    const uint32_t stage_bytes = raw_bytes * (SPLIT ? 2u : 1u);          // raw sub-boxes, then (SPLIT) their lo residuals
     const uint32_t bar_base = smem_base + (uint32_t)a.stages * stage_bytes;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
-    const uint32_t tfull_bar = bar_base + 8u * (2 * kStages);
-    const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 1);
+    auto lo_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (3 * kStages + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (3 * kStages + 2 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (3 * kStages + 4);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     // clear the operand stages once: rows the TMA boxes never write must read as zero in the K reduction
@@ -326,14 +454,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
         uint8_t* base_ptr = smem_raw + (smem_base - smem_u32(smem_raw));
         uint4* p4 = reinterpret_cast<uint4*>(base_ptr);
         const uint32_t n16 = (uint32_t)a.stages * stage_bytes / 16u;
-        for (uint32_t i = threadIdx.x; i < n16; i += kThreads) p4[i] = make_uint4(0, 0, 0, 0);
+        for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) p4[i] = make_uint4(0, 0, 0, 0);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy zeros visible to TMA / UMMA
     }
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dy) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
-        for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        mbar_init(tfull_bar, 1);
+        for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); mbar_init(lo_bar(s), 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -383,38 +511,95 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                                    ((uint32_t)(a.n_tile >> 3) << 17) | ((128u >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            uint32_t d_tmem = tmem_base;
             uint32_t first = 1;
+            long long done = 0;
+            const long long nchunks = c_end - c_begin;
             for (long long c = c_begin; c < c_end; ++c) {
                 mbar_wait(full_bar(stage), phase);
+                if (SPLIT) mbar_wait(lo_bar(stage), phase);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
                 const uint64_t da = make_smem_desc_mn(sa, sub_bytes), db = make_smem_desc_mn(sa + 4u * sub_bytes, sub_bytes);
+                const uint64_t dalo = make_smem_desc_mn(sa + raw_bytes, sub_bytes);
+                const uint64_t dblo = make_smem_desc_mn(sa + raw_bytes + 4u * sub_bytes, sub_bytes);
                 for (int kg = 0; kg < a.rpad / 8; ++kg) {
-                    umma_tf32(tmem_base, da + (uint64_t)(kg * 64), db + (uint64_t)(kg * 64), idesc, first ? 0u : 1u);
+                    const uint64_t ko = (uint64_t)(kg * 64);
+                    if (SPLIT) {
+                        umma_tf32(d_tmem, dalo + ko, db + ko, idesc, first ? 0u : 1u);
+                        umma_tf32(d_tmem, da + ko, dblo + ko, idesc, 1u);
+                        umma_tf32(d_tmem, da + ko, db + ko, idesc, 1u);
+                    } else {
+                        umma_tf32(d_tmem, da + ko, db + ko, idesc, first ? 0u : 1u);
+                    }
                     first = 0;
                 }
                 umma_commit(empty_bar(stage));
                 if (++stage == a.stages) { stage = 0; phase ^= 1u; }
-            }
-            umma_commit(tfull_bar);
-        }
-    } else {
-        const int q = warp & 3;
-        const int co = m0 + q * 32 + lane;
-        mbar_wait(tfull_bar, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-        float* out = a.ws + (((long long)split * a.cout + co) * a.taps + tap) * a.cin + k0;
-        for (int c = 0; c < a.n_tile; c += 16) {
-            float vals[16];
-            tmem_ld16(taddr + (uint32_t)c, vals);
-            if (co < a.cout) {
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    if (k0 + c + g * 4 < a.cin)
-                        *reinterpret_cast<float4*>(out + c + g * 4) = make_float4(vals[g * 4], vals[g * 4 + 1], vals[g * 4 + 2], vals[g * 4 + 3]);
+                ++done;
+                if (SPLIT && (done % kWgSegment) == 0 && done < nchunks) {
+                    // promote this partial accumulator to the epilogue's fp32 registers, continue in the other TMEM buffer
+                    umma_commit(tfull_bar(acc));
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                    mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    d_tmem = tmem_base + (uint32_t)(acc * 128);
+                    first = 1;
                 }
             }
+            umma_commit(tfull_bar(acc));
+        }
+    } else if (warp < 6) {
+        const int q = warp & 3;
+        const int co = m0 + q * 32 + lane;
+        float* out = a.ws + (((long long)split * a.cout + co) * a.taps + tap) * a.cin + k0;
+        const long long nchunks = c_end - c_begin;
+        const int nseg = SPLIT ? (int)((nchunks + kWgSegment - 1) / kWgSegment) : 1;
+        int acc = 0; uint32_t acc_phase = 0;
+        float sum[SPLIT ? 128 : 1];              // SPLIT: n_tile <= 128
+        for (int sg = 0; sg < nseg; ++sg) {
+            mbar_wait(tfull_bar(acc), acc_phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + (uint32_t)(acc * 128) + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+            for (int cg = 0; cg < (SPLIT ? 8 : 16); ++cg) {
+                const int c = cg * 16;
+                if (c < a.n_tile) {
+                    float vals[16];
+                    tmem_ld16(taddr + (uint32_t)c, vals);
+                    if (SPLIT) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) sum[SPLIT ? c + i : 0] = (sg == 0) ? vals[i] : sum[SPLIT ? c + i : 0] + vals[i];
+                    }
+                    if (sg == nseg - 1 && co < a.cout) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            if (k0 + c + g * 4 < a.cin) {
+                                float4 o;
+                                if (SPLIT) o = make_float4(sum[SPLIT ? c + g * 4 : 0], sum[SPLIT ? c + g * 4 + 1 : 0], sum[SPLIT ? c + g * 4 + 2 : 0], sum[SPLIT ? c + g * 4 + 3 : 0]);
+                                else o = make_float4(vals[g * 4], vals[g * 4 + 1], vals[g * 4 + 2], vals[g * 4 + 3]);
+                                *reinterpret_cast<float4*>(out + c + g * 4) = o;
+                            }
+                        }
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    } else if (SPLIT) {
+        const int tid128 = threadIdx.x - 6 * 32;
+        int stage = 0; uint32_t phase = 0;
+        for (long long c = c_begin; c < c_end; ++c) {
+            mbar_wait(full_bar(stage), phase);
+            const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
+            transform_split(sa, sa + raw_bytes, raw_bytes, tid128);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(lo_bar(stage));
+            if (++stage == a.stages) { stage = 0; phase ^= 1u; }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -431,7 +616,7 @@ struct WgPlan {
     size_t smem;
 };
 
-static WgPlan plan_wgrad(int nb, int t_in, int t_out, int v, int cin, int cout, int taps, int stride, int pad) {
+static WgPlan plan_wgrad(int nb, int t_in, int t_out, int v, int cin, int cout, int taps, int stride, int pad, bool split) {
     WgPlan p;
     p.ok = false;
     if (cin % 4 || cout % 4 || v > 128 || stride > 4) return p;
@@ -439,11 +624,12 @@ static WgPlan plan_wgrad(int nb, int t_in, int t_out, int v, int cin, int cout, 
     a.ws = nullptr;
     a.nb = nb; a.t_in = t_in; a.t_out = t_out; a.v = v; a.cin = cin; a.cout = cout; a.taps = taps; a.stride = stride; a.pad = pad;
     a.n_tile = ((cin + 31) / 32) * 32;
-    if (a.n_tile > 256) a.n_tile = 256;
+    const int n_cap = split ? 128 : 256;          // split: two 128-column TMEM buffers + 128 fp32 promotion registers per thread
+    if (a.n_tile > n_cap) a.n_tile = n_cap;
     a.n_tiles = (cin + a.n_tile - 1) / a.n_tile;
     a.m_tiles = (cout + 127) / 128;
     const int nsub = 4 + a.n_tile / 32;
-    int rmax = (48 * 1024) / (nsub * 128);           // rows per stage so that a stage stays <= 48 KB
+    int rmax = ((split ? 32 : 48) * 1024) / (nsub * 128);   // rows per stage: raw operands <= 48 KB (32 KB + 32 KB lo when split)
     rmax = rmax / 8 * 8;
     if (rmax > 128) rmax = 128;
     a.flat = (stride == 1 && t_in == t_out) ? 1 : 0;
@@ -458,11 +644,12 @@ static WgPlan plan_wgrad(int nb, int t_in, int t_out, int v, int cin, int cout, 
         while (a.tt * stride > 256) --a.tt;
         a.rows_box = a.tt * v;
         a.rpad = (a.rows_box + 7) / 8 * 8;
-        if ((size_t)nsub * a.rpad * 128 > 96 * 1024) return p;
+        if ((size_t)nsub * a.rpad * 128 * (split ? 2 : 1) > 96 * 1024) return p;
         a.chunks_per_sample = (t_out + a.tt - 1) / a.tt;
     }
     a.chunks_total = (long long)nb * a.chunks_per_sample;
-    const size_t stage_bytes = (size_t)nsub * a.rpad * 128;
+    if (rmax < 8) return p;
+    const size_t stage_bytes = (size_t)nsub * a.rpad * 128 * (split ? 2 : 1);
     int stages = (int)((192 * 1024) / stage_bytes);
     if (stages > kStages) stages = kStages;
     if (stages < 2) return p;
@@ -485,14 +672,16 @@ static WgPlan plan_wgrad(int nb, int t_in, int t_out, int v, int cin, int cout, 
 
 using namespace agcn;
 
-// returns AGCN_ERR_UNSUPPORTED (without touching the error string's meaning) when the shape is outside this path
+// returns AGCN_ERR_UNSUPPORTED (without touching the error string's meaning) when the shape is outside this path.
+// split != 0: 3xTF32 (fp32 parity); w_split must then point to 2*cout*taps*cin floats of scratch (hi | lo).
 int agcn_conv_fwd_tc(const float* x, const float* w, const float* bias, float* y,
                      int nb, int t_in, int t_out, int v, int cin, int cout,
-                     int taps, int stride, int pad, int transposed, int accumulate, void* stream) {
+                     int taps, int stride, int pad, int transposed, int accumulate, int split, float* w_split, void* stream) {
     using namespace agcn::tc;
     if (cin % 4 || cout % 16 || v > 128 || stride > 4) return AGCN_ERR_UNSUPPORTED;
     if (transposed && stride > 1 && taps < stride) return AGCN_ERR_UNSUPPORTED;       // some parity classes would have no taps
     if (!aligned16(x) || !aligned16(w) || !aligned16(y) || (bias && !aligned16(bias))) return AGCN_ERR_UNSUPPORTED;
+    if (split && (w_split == nullptr || !aligned16(w_split) || ((long long)cout * taps * cin) % 4)) return AGCN_ERR_UNSUPPORTED;
     int bn;
     if (cout % 128 == 0) bn = 128;
     else if (cout % 96 == 0) bn = 96;
@@ -501,6 +690,7 @@ int agcn_conv_fwd_tc(const float* x, const float* w, const float* bias, float* y
     else return AGCN_ERR_UNSUPPORTED;
     EncodeTiledFn enc = encode_fn();
     if (!enc) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc: cuTensorMapEncodeTiled is not available from the driver");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
 
     TcArgs a;
     a.y = y; a.bias = bias;
@@ -517,7 +707,7 @@ int agcn_conv_fwd_tc(const float* x, const float* w, const float* bias, float* y
     a.tiles_t = (t_per_class + a.tt - 1) / a.tt;
     a.total_tiles = (long long)nb * a.nparity * a.tiles_t * a.n_tiles_n;
 
-    CUtensorMap map_a, map_b;
+    CUtensorMap map_a, map_b, map_blo;
     {
         cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)v, (cuuint64_t)t_in, (cuuint64_t)nb};
         cuuint64_t strides[3] = {(cuuint64_t)cin * 4, (cuuint64_t)v * cin * 4, (cuuint64_t)t_in * v * cin * 4};
@@ -528,39 +718,51 @@ int agcn_conv_fwd_tc(const float* x, const float* w, const float* bias, float* y
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
     }
-    {
+    auto encode_w = [&](CUtensorMap* m, const float* ptr) -> CUresult {
         cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)taps, (cuuint64_t)cout};
         cuuint64_t strides[2] = {(cuuint64_t)cin * 4, (cuuint64_t)taps * cin * 4};
         cuuint32_t box[3] = {(cuuint32_t)kKChunk, 1, (cuuint32_t)bn};
         cuuint32_t estr[3] = {1, 1, 1};
-        CUresult r = enc(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(w), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+        return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    };
+    const long long nw = (long long)cout * taps * cin;
+    CUresult r = encode_w(&map_b, split ? w_split : w);
+    if (r != CUDA_SUCCESS) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+    map_blo = map_b;
+    if (split) {
+        r = encode_w(&map_blo, w_split + nw);
+        if (r != CUDA_SUCCESS) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc: cuTensorMapEncodeTiled(B lo) failed with %d", (int)r);
+        split_weights_kernel<<<ceil_div(nw, 256), 256, 0, st>>>(w, w_split, nw);
+        int rc = check_launch("agcn_conv_fwd_tc(split weights)");
+        if (rc) return rc;
     }
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
         if (e != cudaSuccess) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc: %s", cudaGetErrorString(e));
         attr_set = true;
     }
     long long grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
-    conv_tc_kernel<<<(unsigned)grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(map_a, map_b, a);
+    if (split) conv_tc_kernel<true><<<(unsigned)grid, kThreadsSplit, kSmemBytes, st>>>(map_a, map_b, map_blo, a);
+    else conv_tc_kernel<false><<<(unsigned)grid, kThreads, kSmemBytes, st>>>(map_a, map_b, map_blo, a);
     return check_launch("agcn_conv_fwd_tc");
 }
 
 // ---- weight gradient on tensor cores; returns AGCN_ERR_UNSUPPORTED for shapes outside the path
-size_t agcn_conv_wgrad_tc_workspace_floats(int nb, int t_in, int t_out, int v, int cin, int cout, int taps, int stride, int pad) {
-    agcn::tc::WgPlan p = agcn::tc::plan_wgrad(nb, t_in, t_out, v, cin, cout, taps, stride, pad);
+size_t agcn_conv_wgrad_tc_workspace_floats(int nb, int t_in, int t_out, int v, int cin, int cout, int taps, int stride, int pad, int split) {
+    agcn::tc::WgPlan p = agcn::tc::plan_wgrad(nb, t_in, t_out, v, cin, cout, taps, stride, pad, split != 0);
     if (!p.ok) return 0;
     return (size_t)p.splits * cout * taps * cin;
 }
 
 int agcn_conv_wgrad_tc(const float* dy, const float* x, float* ws, int* splits_out,
-                       int nb, int t_in, int t_out, int v, int cin, int cout, int taps, int stride, int pad, void* stream) {
+                       int nb, int t_in, int t_out, int v, int cin, int cout, int taps, int stride, int pad, int split, void* stream) {
     using namespace agcn::tc;
     if (!aligned16(dy) || !aligned16(x) || !aligned16(ws)) return AGCN_ERR_UNSUPPORTED;
-    WgPlan p = plan_wgrad(nb, t_in, t_out, v, cin, cout, taps, stride, pad);
+    WgPlan p = plan_wgrad(nb, t_in, t_out, v, cin, cout, taps, stride, pad, split != 0);
     if (!p.ok) return AGCN_ERR_UNSUPPORTED;
     EncodeTiledFn enc = encode_fn();
     if (!enc) return fail(AGCN_ERR_CUDA, "agcn_conv_wgrad_tc: cuTensorMapEncodeTiled is not available from the driver");
@@ -589,12 +791,15 @@ int agcn_conv_wgrad_tc(const float* dy, const float* x, float* ws, int* splits_o
     if (r != CUDA_SUCCESS) return fail(AGCN_ERR_CUDA, "agcn_conv_wgrad_tc: cuTensorMapEncodeTiled(x) failed with %d", (int)r);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return fail(AGCN_ERR_CUDA, "agcn_conv_wgrad_tc: %s", cudaGetErrorString(e));
         attr_set = true;
     }
     dim3 grid((unsigned)(taps * a.m_tiles * a.n_tiles), (unsigned)p.splits);
-    wgrad_tc_kernel<<<grid, kThreads, p.smem, static_cast<cudaStream_t>(stream)>>>(map_dy, map_x, a);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (split) wgrad_tc_kernel<true><<<grid, kThreadsSplit, p.smem, st>>>(map_dy, map_x, a);
+    else wgrad_tc_kernel<false><<<grid, kThreads, p.smem, st>>>(map_dy, map_x, a);
     *splits_out = p.splits;
     return check_launch("agcn_conv_wgrad_tc");
 }

@@ -20,14 +20,16 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import functional as FN
-from .capi import PREC_FP32, PREC_TF32
+from .capi import PREC_FP32, PREC_FP32_FFMA, PREC_TF32
 from .graph import adjacency_from_graph
 
-_PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, PREC_FP32: PREC_FP32, PREC_TF32: PREC_TF32}
+_PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "fp32_ffma": PREC_FP32_FFMA,
+               PREC_FP32: PREC_FP32, PREC_TF32: PREC_TF32, PREC_FP32_FFMA: PREC_FP32_FFMA}
 
 
 def set_precision(module: nn.Module, precision) -> nn.Module:
-    """'fp32' (FFMA, parity mode) or 'tf32' (tcgen05 tensor cores) for every unit under ``module``."""
+    """'fp32' (parity mode: 3xTF32 tensor cores + FFMA), 'tf32' (single-pass tensor cores) or 'fp32_ffma' (FFMA only)
+    for every unit under ``module``."""
     code = _PRECISIONS[precision]
     for m in module.modules():
         if hasattr(m, "_agcn_precision"):

@@ -10,8 +10,8 @@ from typing import Optional, Tuple
 import torch
 
 from . import capi
-from .capi import (MIX_AGG_BWD, MIX_AGG_FWD, MIX_SCORE_BWD, PREC_FP32, PREC_TF32, RES_AFFINE, RES_NONE,  # noqa: F401
-                   RES_TENSOR)
+from .capi import (MIX_AGG_BWD, MIX_AGG_FWD, MIX_SCORE_BWD, PREC_FP32, PREC_FP32_FFMA, PREC_TF32, RES_AFFINE,  # noqa: F401
+                   RES_NONE, RES_TENSOR)
 
 NUM_SMS = 148
 
@@ -102,8 +102,10 @@ def conv_fwd(x, w, bias=None, *, t_out=None, stride=1, pad=0, transposed=False, 
     elif tuple(out.shape) != (nb, t_out, v, cout):
         raise RuntimeError(f"conv_fwd: out has shape {tuple(out.shape)}, expected {(nb, t_out, v, cout)}")
     _check(x, w, bias, out)
+    ws_bytes = capi.lib().agcn_conv_fwd_workspace_bytes(cin, cout, taps, precision)
+    ws = torch.empty((ws_bytes + 3) // 4, device=x.device, dtype=torch.float32) if ws_bytes else None
     _call("agcn_conv_fwd", _ptr(x), _ptr(w), _ptr(bias), _ptr(out), nb, t_in, t_out, v, cin, cout, taps, stride, pad,
-          int(transposed), int(accumulate), precision, _stream())
+          int(transposed), int(accumulate), precision, _ptr(ws), ws_bytes, _stream())
     return out
 
 

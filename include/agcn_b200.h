@@ -20,8 +20,8 @@
  *   - Return value: 0 on success, otherwise an agcn_status code; agcn_last_error_string() gives a
  *     thread-local description.  Entry points are thread-safe (no global mutable state other than
  *     the thread-local error string) and CUDA-graph-capture safe (no allocation, no host sync).
- *   - `precision`: AGCN_PREC_FP32 = exact fp32 FFMA (parity mode, <=1e-4 vs the reference);
- *     AGCN_PREC_TF32 = tcgen05 kind::tf32 tensor-core path (own tolerance, reported separately).
+ *   - `precision`: see agcn_precision.  AGCN_PREC_FP32 meets the 1e-4 parity tolerance against the reference;
+ *     AGCN_PREC_TF32 has its own tolerance and is reported separately.
  */
 #ifndef AGCN_B200_H
 #define AGCN_B200_H
@@ -43,7 +43,11 @@ typedef enum {
     AGCN_ERR_NULL = 6          /* required pointer is NULL                                       */
 } agcn_status;
 
-typedef enum { AGCN_PREC_FP32 = 0, AGCN_PREC_TF32 = 1 } agcn_precision;
+typedef enum {
+    AGCN_PREC_FP32 = 0,       /* fp32 parity mode: 3xTF32 error-compensated tcgen05 MMAs where the shape allows, FFMA otherwise */
+    AGCN_PREC_TF32 = 1,       /* single-pass tcgen05 kind::tf32 (operands truncated to TF32); own tolerance             */
+    AGCN_PREC_FP32_FFMA = 2   /* force the FFMA kernels (reference path for tests)                                       */
+} agcn_precision;
 
 /* joint-mix modes (agcn_joint_mix) */
 typedef enum {
@@ -70,11 +74,14 @@ long long agcn_launch_count(void);
  * out-of-range ti contribute zero.  x: [nb][t_in][v][cin], y: [nb][t_out][v][cout], w: [cout][taps][cin].
  * Replaces nn.Conv2d forward / input-gradient at agcn.py:41-42 (9x1 temporal conv, residual 1x1 with
  * stride), :71-73 (conv_a / conv_b / conv_d 1x1), :77 (down) and nn.Linear at :178 (taps=1, v=1, t=1).
- * bias may be NULL.  accumulate!=0 adds into y instead of overwriting it.                              */
+ * bias may be NULL.  accumulate!=0 adds into y instead of overwriting it.
+ * workspace: agcn_conv_fwd_workspace_bytes(...) bytes of scratch (holds the TF32 hi/lo split of the weights in the
+ * 3xTF32 path); may be NULL / 0, in which case AGCN_PREC_FP32 runs on the FFMA kernel.                  */
+size_t agcn_conv_fwd_workspace_bytes(int cin, int cout, int taps, int precision);
 int agcn_conv_fwd(const float* x, const float* w, const float* bias, float* y,
                   int nb, int t_in, int t_out, int v, int cin, int cout,
                   int taps, int stride, int pad, int transposed, int accumulate,
-                  int precision, void* stream);
+                  int precision, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Weight / bias gradient of the forward-gather contraction above:
  *   dw[co][tap][ci] = sum_rows dy[nb][to][v][co] * x[nb][stride*to+tap-pad][v][ci];   dbias[co] = sum_rows dy

@@ -12,7 +12,7 @@ Maths: SURVEY.md Appendix A; reference lines torch_src/models/mmargcn/agcn.py:37
 """
 import torch
 
-PREC_FP32, PREC_TF32 = 0, 1
+PREC_FP32, PREC_TF32, PREC_FP32_FFMA = 0, 1, 2
 MIX_AGG_FWD, MIX_AGG_BWD, MIX_SCORE_BWD = 0, 1, 2
 RES_NONE, RES_TENSOR, RES_AFFINE = 0, 1, 2
 NUM_SMS = 148
@@ -207,3 +207,35 @@ def pool_bwd(dout, shape):
         rows *= s
     rows = rows // c // groups
     return (dout / rows).reshape(groups, 1, c).expand(groups, rows, c).reshape(shape).contiguous()
+
+
+# --------------------------------------------------------------------------- TF32-mode emulation (tests only)
+def _trunc_tf32(t):
+    return (t.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
+class Tf32Emulation:
+    """Stage backend that restates AGCN_PREC_TF32: on the shapes the tcgen05 path takes, tcgen05.mma kind::tf32 reads the
+    upper 19 bits of each fp32 operand (measured on B200), i.e. operands are TRUNCATED to TF32 and products are
+    accumulated in fp32.  Everything else is the plain fp32 stage.  fp32 tensors only."""
+
+    def __getattr__(self, name):
+        return globals()[name]
+
+    @staticmethod
+    def _fwd_on_tc(x, w, transposed, stride):
+        cout, taps, cin = w.shape
+        ok = cin % 4 == 0 and cout % 16 == 0 and (cout <= 128 or cout % 64 == 0 or cout % 96 == 0)
+        return ok and not (transposed and stride > 1 and taps < stride)
+
+    def conv_fwd(self, x, w, bias=None, *, stride=1, transposed=False, precision=PREC_FP32, **kw):
+        if precision == PREC_TF32 and self._fwd_on_tc(x, w, transposed, stride):
+            x, w = _trunc_tf32(x), _trunc_tf32(w)
+        return conv_fwd(x, w, bias, stride=stride, transposed=transposed, **kw)
+
+    def conv_wgrad(self, dy, x, *, precision=PREC_FP32, **kw):
+        _, db = conv_wgrad(dy, x, **kw)
+        if precision == PREC_TF32 and x.shape[-1] % 4 == 0 and dy.shape[-1] % 4 == 0:
+            dy, x = _trunc_tf32(dy), _trunc_tf32(x)
+        dw, _ = conv_wgrad(dy, x, **kw)
+        return dw, db

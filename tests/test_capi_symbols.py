@@ -28,17 +28,19 @@ def test_header_symbols_exported_and_bound():
     assert lib.agcn_version() >= 100
     assert lib.agcn_bn_workspace_bytes(64) > 0
     assert lib.agcn_conv_wgrad_workspace_bytes(2, 8, 8, 25, 64, 64, 9) > 0
+    assert lib.agcn_conv_fwd_workspace_bytes(64, 64, 9, capi.PREC_FP32) == 2 * 64 * 64 * 9 * 4
+    assert lib.agcn_conv_fwd_workspace_bytes(64, 64, 9, capi.PREC_TF32) == 0
 
 
 def test_argument_validation_without_gpu():
     """Shape / null checks run before any CUDA call, so the error paths are testable on a CPU box."""
     from fusion_gcn_b200 import capi
     lib = capi.lib()
-    rc = lib.agcn_conv_fwd(None, None, None, None, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, None)
+    rc = lib.agcn_conv_fwd(None, None, None, None, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, None, 0, None)
     assert rc == 6 and b"null" in lib.agcn_last_error_string()
     rc = lib.agcn_joint_mix(1, 1, 1, 1, 4, 40, 8, 24, 8, 0, 0, None)       # V = 40 > 32
     assert rc == 2 and b"V=40" in lib.agcn_last_error_string()
-    rc = lib.agcn_conv_fwd(1, 1, None, 1, 0, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, None)
+    rc = lib.agcn_conv_fwd(1, 1, None, 1, 0, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, None, 0, None)
     assert rc == 1
     with pytest.raises(RuntimeError, match="status 1"):
         capi.check(rc, "agcn_conv_fwd")

@@ -34,27 +34,31 @@ CONV_CASES = [  # nb, t_in, v, cin, cout, taps, stride
     (1, 300, 25, 64, 64, 9, 1)]
 
 
+@pytest.mark.parametrize("mode", ["ffma", "fp32"])
 @pytest.mark.parametrize("nb,t_in,v,cin,cout,taps,stride", CONV_CASES)
-def test_conv_fwd_dgrad_wgrad(K, nb, t_in, v, cin, cout, taps, stride):
+def test_conv_fwd_dgrad_wgrad(K, nb, t_in, v, cin, cout, taps, stride, mode):
+    """mode 'ffma' = AGCN_PREC_FP32_FFMA (pure FFMA kernels); mode 'fp32' = AGCN_PREC_FP32, the parity mode, which runs
+    3xTF32 error-compensated tcgen05 MMAs on the shapes the tensor-core path takes (and FFMA on the rest)."""
+    prec, tol = (K.PREC_FP32_FFMA, 2e-6) if mode == "ffma" else (K.PREC_FP32, 1e-5)
     pad = (taps - 1) // 2
     t_out = (t_in + 2 * pad - taps) // stride + 1
     x, w, b = rnd(nb, t_in, v, cin), rnd(cout, taps, cin, seed=1) * 0.1, rnd(cout, seed=2)
-    y, y_ref = both("conv_fwd", K, (x, w, b), t_out=t_out, stride=stride, pad=pad)
-    assert rel_err(y, y_ref) <= 2e-6
+    y, y_ref = both("conv_fwd", K, (x, w, b), t_out=t_out, stride=stride, pad=pad, precision=prec)
+    assert rel_err(y, y_ref) <= tol
     # accumulate into an existing tensor
     base = rnd(nb, t_out, v, cout, seed=3)
-    acc = K.conv_fwd(x.cuda(), w.cuda(), None, t_out=t_out, stride=stride, pad=pad, out=base.cuda().clone(), accumulate=True)
-    assert rel_err(acc, S.conv_fwd(x.double(), w.double(), None, t_out=t_out, stride=stride, pad=pad) + base.double()) <= 2e-6
+    acc = K.conv_fwd(x.cuda(), w.cuda(), None, t_out=t_out, stride=stride, pad=pad, out=base.cuda().clone(), accumulate=True, precision=prec)
+    assert rel_err(acc, S.conv_fwd(x.double(), w.double(), None, t_out=t_out, stride=stride, pad=pad) + base.double()) <= tol
     # input gradient = transposed gather with the transposed weight
     dy = rnd(nb, t_out, v, cout, seed=4)
     wt = w.permute(2, 1, 0).contiguous()
-    dx, dx_ref = both("conv_fwd", K, (dy, wt, None), t_out=t_in, stride=stride, pad=pad, transposed=True)
+    dx, dx_ref = both("conv_fwd", K, (dy, wt, None), t_out=t_in, stride=stride, pad=pad, transposed=True, precision=prec)
     xg = x.double().requires_grad_(True)
     (S.conv_fwd(xg, w.double(), b.double(), t_out=t_out, stride=stride, pad=pad) * dy.double()).sum().backward()
     assert rel_err(dx_ref, xg.grad) <= 1e-12            # the stage oracle itself is consistent with autograd
-    assert rel_err(dx, xg.grad) <= 2e-6
-    (dw, db), (dw_ref, db_ref) = both("conv_wgrad", K, (dy, x), taps=taps, stride=stride, pad=pad)
-    assert rel_err(dw, dw_ref) <= 5e-6 and rel_err(db, db_ref) <= 5e-6
+    assert rel_err(dx, xg.grad) <= tol
+    (dw, db), (dw_ref, db_ref) = both("conv_wgrad", K, (dy, x), taps=taps, stride=stride, pad=pad, precision=prec)
+    assert rel_err(dw, dw_ref) <= 2.5 * tol and rel_err(db, db_ref) <= 5e-6
 
 
 @pytest.mark.parametrize("nb,t,v,ci,nchunk", [(2, 12, 25, 16, 3), (3, 7, 20, 4, 7), (1, 30, 22, 64, 4), (2, 5, 5, 2, 1), (2, 9, 18, 3, 2)])
@@ -206,7 +210,9 @@ def test_tf32_tensor_core_path(K, nb, t_in, v, cin, cout, taps, stride):
     kw_t = dict(t_out=t_in, stride=stride, pad=pad, transposed=True)
     base = rnd(nb, t_in, v, cin, seed=5)
     dx = K.conv_fwd(dy.cuda(), wt.cuda(), None, out=base.cuda().clone(), accumulate=True, precision=K.PREC_TF32, **kw_t)
-    assert rel_err(dx, S.conv_fwd(_trunc_tf32(dy).double(), _trunc_tf32(wt).double(), None, **kw_t) + base.double()) <= 1e-5
+    if taps >= stride:      # a 1x1 stride-2 input gradient has empty parity classes and is left to the FFMA kernel
+        assert rel_err(dx, S.conv_fwd(_trunc_tf32(dy).double(), _trunc_tf32(wt).double(), None, **kw_t) + base.double()) <= 1e-5
+    assert rel_err(dx, S.conv_fwd(dy.double(), wt.double(), None, **kw_t) + base.double()) <= 3e-3
     dw, db = K.conv_wgrad(dy.cuda(), x.cuda(), taps=taps, stride=stride, pad=pad, precision=K.PREC_TF32)
     dw_ref, db_ref = S.conv_wgrad(_trunc_tf32(dy).double(), _trunc_tf32(x).double(), taps=taps, stride=stride, pad=pad)
     assert rel_err(dw, dw_ref) <= 2e-5

@@ -57,15 +57,17 @@ def run_wg_case(name):
     xc, dyc = x.cuda(), dy.cuda()
     dw, db = K.conv_wgrad(dyc, xc, precision=K.PREC_TF32, **kw)
     torch.cuda.synchronize()
+    dw3, db3 = K.conv_wgrad(dyc, xc, precision=K.PREC_FP32, **kw)
+    torch.cuda.synchronize()
     big = nb * t_out * v > 100000
 
     def trunc(t_):
         return (t_.view(torch.int32) & ~0x1FFF).view(torch.float32)
 
     if big:
-        ref_raw, db_ref = K.conv_wgrad(dyc, xc, precision=K.PREC_FP32, **kw)
+        ref_raw, db_ref = K.conv_wgrad(dyc, xc, precision=K.PREC_FP32_FFMA, **kw)
         ref_raw, db_ref = ref_raw.double().cpu(), db_ref.double().cpu()
-        ref_tr = K.conv_wgrad(trunc(dy).cuda(), trunc(x).cuda(), precision=K.PREC_FP32, **kw)[0].double().cpu()
+        ref_tr = K.conv_wgrad(trunc(dy).cuda(), trunc(x).cuda(), precision=K.PREC_FP32_FFMA, **kw)[0].double().cpu()
     else:
         ref_raw, db_ref = S.conv_wgrad(dy.double(), x.double(), **kw)
         ref_tr = S.conv_wgrad(trunc(dy).double(), trunc(x).double(), **kw)[0]
@@ -73,7 +75,8 @@ def run_wg_case(name):
     e_raw = ((d - ref_raw).abs().max() / ref_raw.abs().max()).item()
     e_tr = ((d - ref_tr).abs().max() / ref_tr.abs().max()).item()
     e_b = ((db.double().cpu() - db_ref).abs().max() / db_ref.abs().max()).item()
-    print(f"[{name}] dw rel err vs raw {e_raw:.3e} | vs truncated-TF32 {e_tr:.3e} | dbias {e_b:.3e}")
+    e3 = ((dw3.double().cpu() - ref_raw).abs().max() / ref_raw.abs().max()).item()
+    print(f"[{name}] tf32 dw: vs raw {e_raw:.3e} | vs truncated-TF32 {e_tr:.3e} | dbias {e_b:.3e} || 3xTF32 dw vs raw {e3:.3e}")
     if e_raw > 5e-3:
         err = (d - ref_raw).abs() > 1e-2 * ref_raw.abs().max()
         print("   bad co:", err.any(dim=2).any(dim=1).nonzero().flatten()[:32].tolist())
@@ -82,7 +85,7 @@ def run_wg_case(name):
         print("   dw[0,0,:8] ", d[0, 0, :8].tolist())
         print("   ref[0,0,:8]", ref_raw[0, 0, :8].tolist())
     if big:
-        for prec, label in ((K.PREC_TF32, "tf32 tcgen05"), (K.PREC_FP32, "fp32 FFMA")):
+        for prec, label in ((K.PREC_TF32, "tf32 tcgen05"), (K.PREC_FP32, "3xTF32 tcgen05"), (K.PREC_FP32_FFMA, "fp32 FFMA")):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             for _ in range(2):
                 K.conv_wgrad(dyc, xc, precision=prec, **kw)
@@ -120,11 +123,14 @@ def run_case(name):
     out = base.cuda().clone() if acc else None
     y = K.conv_fwd(xc, wc, None if b is None else b.cuda(), out=out, accumulate=bool(acc), precision=K.PREC_TF32, **kw)
     torch.cuda.synchronize()
+    out3 = base.cuda().clone() if acc else None
+    y3 = K.conv_fwd(xc, wc, None if b is None else b.cuda(), out=out3, accumulate=bool(acc), precision=K.PREC_FP32, **kw)
+    torch.cuda.synchronize()
     big = nb * t_out * v * cout > 5e7
 
     def ref(xx, ww):
         if big:   # fp32 FFMA kernel as the reference for the big shapes
-            r = K.conv_fwd(xx.float().cuda(), ww.float().cuda(), None if b is None else b.cuda(), **kw).double().cpu()
+            r = K.conv_fwd(xx.float().cuda(), ww.float().cuda(), None if b is None else b.cuda(), precision=K.PREC_FP32_FFMA, **kw).double().cpu()
         else:
             r = S.conv_fwd(xx.double(), ww.double(), None if b is None else b.double(), **kw)
         return r + base.double() if acc else r
@@ -143,7 +149,8 @@ def run_case(name):
         if tag == "raw":
             err = (yd - r).abs()
             rr = r
-    print(f"[{name}] rel err vs raw {res['raw']:.3e} | vs truncated-TF32 {res['trunc']:.3e} | vs rounded-TF32 {res['round']:.3e}")
+    e3 = ((y3.double().cpu() - rr).abs().max() / rr.abs().max()).item()
+    print(f"[{name}] tf32: vs raw {res['raw']:.3e} | vs truncated-TF32 {res['trunc']:.3e} || 3xTF32 (fp32 mode): vs raw {e3:.3e}")
     if res["raw"] > 5e-3:
         flat = err.reshape(-1, cout)
         bad_rows = (flat.max(dim=1).values > 1e-2 * rr.abs().max()).nonzero().flatten()
@@ -153,7 +160,7 @@ def run_case(name):
         print("   y[0,:8]  ", yd.reshape(-1, cout)[0, :8].tolist())
         print("   ref[0,:8]", rr.reshape(-1, cout)[0, :8].tolist())
     if big:
-        for prec, label in ((K.PREC_TF32, "tf32 tcgen05"), (K.PREC_FP32, "fp32 FFMA")):
+        for prec, label in ((K.PREC_TF32, "tf32 tcgen05"), (K.PREC_FP32, "3xTF32 tcgen05"), (K.PREC_FP32_FFMA, "fp32 FFMA")):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             for _ in range(2):
                 K.conv_fwd(xc, wc, None, precision=prec, **kw)
