@@ -119,20 +119,36 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const float* x, const f
     }
 }
 
-__global__ void bn_finalize_kernel(const float* part, int P, int C, double count,
-                                   const float* gamma, const float* beta, float* running_mean, float* running_var,
-                                   long long* nbt, float momentum, float eps, int training,
-                                   float* scale, float* shift, float* save_mean, float* save_invstd) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c == 0 && training && nbt != nullptr) *nbt += 1;
-    if (c >= C) return;
-    double mean, var;
-    if (training) {
-        double s = 0.0, q = 0.0;
-        for (int b = 0; b < P; ++b) {
+// Sum of the P per-CTA partials of channel c (fp64, fixed order): 8 lanes per channel stride over the partials, then a
+// fixed-order shared-memory combine.  block = 32 channels x 8 lanes.
+__device__ __forceinline__ void reduce_partials(const float* part, int P, int C, int c, double& s_out, double& q_out) {
+    __shared__ double red[2][8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    double s = 0.0, q = 0.0;
+    if (c < C)
+        for (int b = ty; b < P; b += 8) {
             s += (double)part[((long long)b * 2 + 0) * C + c];
             q += (double)part[((long long)b * 2 + 1) * C + c];
         }
+    red[0][ty][tx] = s; red[1][ty][tx] = q;
+    __syncthreads();
+    s = 0.0; q = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s += red[0][i][tx]; q += red[1][i][tx]; }
+    s_out = s; q_out = q;
+}
+
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* part, int P, int C, double count,
+                                   const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                   long long* nbt, float momentum, float eps, int training,
+                                   float* scale, float* shift, float* save_mean, float* save_invstd) {
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && training && nbt != nullptr) *nbt += 1;
+    double s = 0.0, q = 0.0;
+    if (training) reduce_partials(part, P, C, c, s, q);
+    if (c >= C || (threadIdx.x >> 5) != 0) return;
+    double mean, var;
+    if (training) {
         mean = s / count;
         var = q / count - mean * mean;
         if (var < 0.0) var = 0.0;
@@ -191,15 +207,12 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* y, const flo
 }
 
 // coef[0][c] = gamma*invstd, coef[1][c] = s1/m, coef[2][c] = s2/m * invstd, coef[3][c] = mean;  dgamma = s2, dbeta = s1
-__global__ void bn_bwd_finalize_kernel(const float* part, int P, int C, double count, const float* gamma,
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* part, int P, int C, double count, const float* gamma,
                                        const float* mean, const float* invstd, float* dgamma, float* dbeta, float* coef) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    double s1 = 0.0, s2 = 0.0;
-    for (int b = 0; b < P; ++b) {
-        s1 += (double)part[((long long)b * 2 + 0) * C + c];
-        s2 += (double)part[((long long)b * 2 + 1) * C + c];
-    }
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    double s1, s2;
+    reduce_partials(part, P, C, c, s1, s2);
+    if (c >= C || (threadIdx.x >> 5) != 0) return;
     if (dbeta) dbeta[c] = (float)s1;
     if (dgamma) dgamma[c] = (float)s2;
     const float is = invstd[c];
@@ -356,7 +369,7 @@ extern "C" AGCN_API int agcn_bn_stats(const float* x, int outer, int inner, long
         rc = launch_colsum<0>(x, nullptr, nullptr, nullptr, nullptr, m, rows, part, P, s);
         if (rc) return rc;
     }
-    bn_finalize_kernel<<<ceil_div(channels, 128), 128, 0, s>>>(part, P, channels, (double)rows, gamma, beta, running_mean, running_var,
+    bn_finalize_kernel<<<ceil_div(channels, 32), 256, 0, s>>>(part, P, channels, (double)rows, gamma, beta, running_mean, running_var,
                                                               num_batches_tracked, momentum, eps, training, scale, shift, save_mean, save_invstd);
     return check_launch("agcn_bn_stats(finalize)");
 }
@@ -397,7 +410,7 @@ extern "C" AGCN_API int agcn_bn_bwd(const float* dout, const float* mask_out, co
     const int P = num_partials(rows);
     rc = launch_colsum<1>(y, dout, mask_out, save_mean, save_invstd, m, rows, part, P, s);
     if (rc) return rc;
-    bn_bwd_finalize_kernel<<<ceil_div(channels, 128), 128, 0, s>>>(part, P, channels, (double)rows, gamma, save_mean, save_invstd, dgamma, dbeta, coef);
+    bn_bwd_finalize_kernel<<<ceil_div(channels, 32), 256, 0, s>>>(part, P, channels, (double)rows, gamma, save_mean, save_invstd, dgamma, dbeta, coef);
     rc = check_launch("agcn_bn_bwd(finalize)");
     if (rc) return rc;
     if (dy == nullptr && dres == nullptr) return AGCN_OK;

@@ -284,6 +284,110 @@ __global__ void wgrad_reduce_kernel(const float* ws_w, const float* ws_b, float*
     }
 }
 
+// ------------------------------------------------------------------------------------------ skinny shapes (first unit)
+// The first unit has 2..9 input channels (C = 3 joints coordinates, 9 after aggregation): a 64-wide GEMM tile would waste
+// >90 % of its FMAs there, and these contractions are plain HBM streams.  Two dedicated kernels:
+//   conv_skinny_out_kernel : y[row][co] (+)= bias + sum_ci x[row][ci] w[co][ci],  cout <= 16, cin % 4 == 0   (input gradients)
+//   wgrad_skinny_kernel    : part[b][co][ci] = sum_{rows of b} dy[row][co] x[row][ci],  cin <= 16            (weight gradients)
+constexpr int kSkinnyRows = 128;
+
+__global__ void __launch_bounds__(256) conv_skinny_out_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                              const float* __restrict__ bias, float* __restrict__ y,
+                                                              long long rows, int cin, int cout, int accumulate) {
+    extern __shared__ __align__(16) float sm[];
+    const int ld = cin + 4;
+    float* xs = sm;                                   // [128][ld]
+    float* ws = xs + kSkinnyRows * ld;                // [cout][cin]
+    float* os = ws + cout * cin;                      // [128][cout]
+    const int tid = threadIdx.x;
+    for (int i = tid; i < cout * cin; i += 256) ws[i] = __ldg(w + i);
+    const int cq = cin >> 2;
+    for (long long r0 = (long long)blockIdx.x * kSkinnyRows; r0 < rows; r0 += (long long)gridDim.x * kSkinnyRows) {
+        const int rn = (rows - r0) < kSkinnyRows ? (int)(rows - r0) : kSkinnyRows;
+        __syncthreads();
+        const float4* src = reinterpret_cast<const float4*>(x + r0 * cin);
+        for (int i = tid; i < rn * cq; i += 256) {
+            const int r = i / cq, c4 = i - r * cq;
+            *reinterpret_cast<float4*>(xs + r * ld + c4 * 4) = __ldg(src + i);
+        }
+        __syncthreads();
+        // thread = (row, half of the channel quads); the two halves are adjacent lanes
+        const int r = tid >> 1, h = tid & 1;
+        float acc[16];
+#pragma unroll
+        for (int o = 0; o < 16; ++o) acc[o] = 0.f;
+        if (r < rn) {
+            for (int c4 = h; c4 < cq; c4 += 2) {
+                const float4 v = *reinterpret_cast<const float4*>(xs + r * ld + c4 * 4);
+#pragma unroll
+                for (int o = 0; o < 16; ++o) {
+                    if (o < cout) {
+                        const float4 q = *reinterpret_cast<const float4*>(ws + o * cin + c4 * 4);
+                        acc[o] = fmaf(v.x, q.x, fmaf(v.y, q.y, fmaf(v.z, q.z, fmaf(v.w, q.w, acc[o]))));
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < 16; ++o) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 1);
+        if (r < rn && h == 0) {
+#pragma unroll
+            for (int o = 0; o < 16; ++o) if (o < cout) os[r * cout + o] = acc[o] + (bias ? __ldg(bias + o) : 0.f);
+        }
+        __syncthreads();
+        float* dst = y + r0 * cout;
+        for (int i = tid; i < rn * cout; i += 256) dst[i] = accumulate ? dst[i] + os[i] : os[i];
+    }
+}
+
+// block = 256 threads = `lanes` row lanes x cpad output channels (cpad = cout rounded up to 32); each thread keeps dw[co][0..cin)
+// for its co in registers.  part: [gridDim.x][cout][cin], bpart: [gridDim.x][cout] (may be null).
+__global__ void __launch_bounds__(256) wgrad_skinny_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                           float* __restrict__ part, float* __restrict__ bpart,
+                                                           long long rows, int cin, int cout, int cpad) {
+    extern __shared__ __align__(16) float sm[];
+    float* xs = sm;                                  // [128][cin]
+    float* red = xs + kSkinnyRows * 16;              // [lanes][cpad][17]
+    const int tid = threadIdx.x;
+    const int lanes = 256 / cpad;
+    const int co = tid % cpad, rl = tid / cpad;
+    const bool on = (co < cout) && (rl < lanes);
+    float acc[16], bsum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    const long long per = ((rows + gridDim.x - 1) / gridDim.x + kSkinnyRows - 1) / kSkinnyRows * kSkinnyRows;
+    const long long rb = (long long)blockIdx.x * per;
+    long long re = rb + per; if (re > rows) re = rows;
+    for (long long r0 = rb; r0 < re; r0 += kSkinnyRows) {
+        const int rn = (re - r0) < kSkinnyRows ? (int)(re - r0) : kSkinnyRows;
+        __syncthreads();
+        for (int i = tid; i < rn * cin; i += 256) xs[i] = __ldg(x + r0 * cin + i);
+        __syncthreads();
+        if (on) {
+            for (int r = rl; r < rn; r += lanes) {
+                const float d = __ldg(dy + (r0 + r) * cout + co);
+                bsum += d;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) if (i < cin) acc[i] = fmaf(d, xs[r * cin + i], acc[i]);
+            }
+        }
+    }
+    __syncthreads();
+    if (rl < lanes) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) red[(rl * cpad + co) * 17 + i] = acc[i];
+        red[(rl * cpad + co) * 17 + 16] = bsum;
+    }
+    __syncthreads();
+    for (int o = tid; o < cout * 17; o += 256) {
+        const int c = o / 17, i = o - c * 17;
+        float s = 0.f;
+        for (int l = 0; l < lanes; ++l) s += red[(l * cpad + c) * 17 + i];
+        if (i < cin) part[((long long)blockIdx.x * cout + c) * cin + i] = s;
+        else if (i == 16 && bpart != nullptr) bpart[(long long)blockIdx.x * cout + c] = s;
+    }
+}
+
 // column sums of dy for the bias gradient when the weight gradient runs on tensor cores: part[P][cout]
 __global__ void __launch_bounds__(256) bias_partial_kernel(const float* dy, long long rows, int cout, float* part) {
     __shared__ float sm[8][33];
@@ -354,6 +458,19 @@ extern "C" AGCN_API int agcn_conv_fwd(const float* x, const float* w, const floa
             if (rc != AGCN_ERR_UNSUPPORTED) return rc;   // unsupported shapes fall through to the FFMA kernel
         }
     }
+    if (taps == 1 && stride == 1 && pad == 0 && t_in == t_out && cout <= 16 && cin % 4 == 0 && cin <= 1024 && aligned16(x) && aligned16(w)) {
+        // skinny output (input gradients of the first unit): one HBM pass, no GEMM tiling
+        const long long rows = (long long)nb * t_out * v;
+        const size_t smem = ((size_t)kSkinnyRows * (cin + 4) + (size_t)cout * cin + (size_t)kSkinnyRows * cout) * sizeof(float);
+        if (smem <= 200 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(conv_skinny_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e != cudaSuccess) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd: %s", cudaGetErrorString(e));
+            long long blocks = (rows + kSkinnyRows - 1) / kSkinnyRows;
+            if (blocks > 8LL * kNumSMs) blocks = 8LL * kNumSMs;
+            conv_skinny_out_kernel<<<(unsigned)blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(x, w, bias, y, rows, cin, cout, accumulate);
+            return check_launch("agcn_conv_fwd(skinny)");
+        }
+    }
     ConvArgs a{x, w, bias, y, nb, t_in, t_out, v, cin, cout, taps, stride, pad, transposed, accumulate,
                (long long)nb * t_out * v};
     dim3 grid((unsigned)ceil_div(a.rows_out, 128), (unsigned)ceil_div(cout, 64));
@@ -376,7 +493,10 @@ extern "C" AGCN_API size_t agcn_conv_wgrad_workspace_bytes(int nb, int t_in, int
             if (f > tc) tc = f;
         }
     tc += (size_t)kBiasPartials * cout;
-    return (simt > tc ? simt : tc) * sizeof(float);
+    const size_t skinny = (taps == 1 && cin <= 16) ? (size_t)4 * kNumSMs * ((size_t)cout * cin + cout) : 0;
+    size_t need = simt > tc ? simt : tc;
+    if (skinny > need) need = skinny;
+    return need * sizeof(float);
 }
 
 extern "C" AGCN_API int agcn_conv_wgrad(const float* dy, const float* x, float* dw, float* dbias,
@@ -418,6 +538,28 @@ extern "C" AGCN_API int agcn_conv_wgrad(const float* dy, const float* x, float* 
             return rc;
         }
         if (rc != AGCN_ERR_UNSUPPORTED) return rc;      // unsupported shapes fall through to the FFMA kernel
+    }
+    if (taps == 1 && stride == 1 && pad == 0 && t_in == t_out && cin <= 16 && cout <= 256) {
+        // skinny input (weight gradients of the first unit)
+        const long long rows = (long long)nb * t_out * v;
+        const int cpad = (cout + 31) / 32 * 32;
+        const int lanes = 256 / cpad;
+        long long P = (rows + 4 * kSkinnyRows - 1) / (4 * kSkinnyRows);
+        if (P > 4LL * kNumSMs) P = 4LL * kNumSMs;
+        if (P < 1) P = 1;
+        const long long wsize = (long long)cout * cin;
+        if ((size_t)P * (wsize + cout) * sizeof(float) <= workspace_bytes) {
+            float* part = static_cast<float*>(workspace);
+            float* bpart = dbias ? part + P * wsize : nullptr;
+            const size_t smem = ((size_t)kSkinnyRows * 16 + (size_t)lanes * cpad * 17) * sizeof(float);
+            cudaStream_t s = static_cast<cudaStream_t>(stream);
+            wgrad_skinny_kernel<<<(unsigned)P, 256, smem, s>>>(dy, x, part, bpart, rows, cin, cout, cpad);
+            int rc = check_launch("agcn_conv_wgrad(skinny)");
+            if (rc) return rc;
+            const long long total = wsize + (dbias ? cout : 0);
+            wgrad_reduce_kernel<<<ceil_div(total, 256), 256, 0, s>>>(part, bpart, dw, dbias, wsize, cout, (int)P);
+            return check_launch("agcn_conv_wgrad(skinny reduce)");
+        }
     }
     WgradArgs a;
     a.dy = dy; a.x = x;

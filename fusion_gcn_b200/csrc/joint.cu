@@ -9,106 +9,160 @@ constexpr int kMaxV = 32;
 
 // ------------------------------------------------------------------------------------------ joint gram
 // out[n][chunk][g][u][v] = sum_{t in chunk, c<width} a[n][t][u][offa+g*sa+c] * b[n][t][v][offb+g*sb+c]
-// CTA = (n, chunk).  Thread tile: 5x5 block of (u,v) for one group, over one of 4 interleaved channel slices.
+// CTA = (n, chunk), 12 warps.  The (g, u, v) outputs are cut into 5x5 register tiles; tile ids run along the lanes of
+// `ntw` "tile warps", and the remaining warp index is a slice of the reduction axis (t, c), so every lane of a warp
+// reads the same channel quad: the five distinct joint rows a warp touches per operand are shared-memory broadcasts
+// (row pitch ld = cw+4 floats keeps them in distinct bank groups), giving 100 FMAs per 10 LDS.128.
+// Operands stay channels-contiguous in shared memory exactly as they lie in HBM: staging is straight 16-byte
+// cp.async (double buffered); the k-slices are summed through shared memory in a fixed order (deterministic).
 struct GramArgs {
     const float* a; const float* b; float* out;
-    int nb, t, v, lda, ldb, groups, offa, sa, offb, sb, width, nchunk;
+    int nb, t, v, lda, ldb, groups, offa, sa, offb, sb, width, nchunk, tt, vec;
 };
 
 constexpr int kGramCW = 64;     // channels staged per pass
-constexpr int kGramThreads = 320;
+constexpr int kGramWarps = 12;
+constexpr int kGramThreads = kGramWarps * 32;
 
-__global__ void __launch_bounds__(kGramThreads) joint_gram_kernel(GramArgs p) {
+__device__ __forceinline__ void cp_async16(float* dst, const float* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(kGramThreads, 2) joint_gram_kernel(GramArgs p) {
     extern __shared__ __align__(16) float smem[];
     const int V = p.v;
-    const int cw = p.width < kGramCW ? p.width : kGramCW;
-    const int ld = cw + 4;
-    // A tile: groups_a x V x ld  (groups_a = 1 when sa == 0), B tile: groups x V x ld
+    const int cwp = ((p.width < kGramCW ? p.width : kGramCW) + 3) & ~3;      // staged channels, padded to a quad
+    const int ld = cwp + 4;
+    const int cq = cwp >> 2;
     const int ga = (p.sa == 0) ? 1 : p.groups;
-    float* As = smem;
-    float* Bs = smem + (size_t)ga * V * ld;
+    const int rows_a = ga * V, rows_b = p.groups * V;
+    const int stage_floats = p.tt * (rows_a + rows_b) * ld;
     const int n = blockIdx.x / p.nchunk, chunk = blockIdx.x % p.nchunk;
     const int t_per = (p.t + p.nchunk - 1) / p.nchunk;
     const int t0 = chunk * t_per;
     int t1 = t0 + t_per; if (t1 > p.t) t1 = p.t;
 
-    const int nblk = (V + 4) / 5;                 // 5-wide blocks per axis
+    const int nblk = (V + 4) / 5;
     const int tiles = p.groups * nblk * nblk;
-    const int tid = threadIdx.x;
-    const int cs = tid & 3;                       // channel slice
-    // each thread owns up to 2 tiles (tiles <= 3*7*7 = 147 <= 2 * 80)
-    int tile_id[2]; int tg[2], tu[2], tv[2];
+    const int ntw = (tiles + 31) >> 5;
+    const int nks = kGramWarps / ntw;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tw = warp % ntw, ks = warp / ntw;
+    const int tile = tw * 32 + lane;
+    const bool active = (ks < nks) && (tile < tiles);
+    int g = 0, u0 = 0, v0 = 0;
+    if (tile < tiles) { g = tile / (nblk * nblk); const int r = tile % (nblk * nblk); u0 = (r / nblk) * 5; v0 = (r % nblk) * 5; }
+    int offu[5], offv[5];
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
-        int id = (tid >> 2) + s * (kGramThreads / 4);
-        tile_id[s] = id < tiles ? id : -1;
-        int g = id / (nblk * nblk); int r = id % (nblk * nblk);
-        tg[s] = g; tu[s] = (r / nblk) * 5; tv[s] = (r % nblk) * 5;
+    for (int i = 0; i < 5; ++i) {
+        const int u = (u0 + i < V) ? u0 + i : V - 1;          // clamped rows compute values that are never stored
+        const int w = (v0 + i < V) ? v0 + i : V - 1;
+        offu[i] = ((p.sa == 0 ? 0 : g) * V + u) * ld;
+        offv[i] = (rows_a * p.tt) * ld + (g * V + w) * ld;
     }
-    float acc[2][5][5];
+    float acc[5][5];
 #pragma unroll
-    for (int s = 0; s < 2; ++s)
+    for (int i = 0; i < 5; ++i)
 #pragma unroll
-        for (int i = 0; i < 5; ++i)
-#pragma unroll
-            for (int j = 0; j < 5; ++j) acc[s][i][j] = 0.f;
+        for (int j = 0; j < 5; ++j) acc[i][j] = 0.f;
 
-    for (int t = t0; t < t1; ++t) {
-        const float* arow = p.a + ((long long)n * p.t + t) * V * p.lda;
-        const float* brow = p.b + ((long long)n * p.t + t) * V * p.ldb;
-        for (int c0 = 0; c0 < p.width; c0 += cw) {
-            const int cn = (p.width - c0) < cw ? (p.width - c0) : cw;
-            __syncthreads();
-            // stage A
-            for (int idx = tid; idx < ga * V * cw; idx += kGramThreads) {
-                int c = idx % cw; int r = idx / cw; int u = r % V; int g = r / V;
-                float val = 0.f;
-                if (c < cn) val = __ldg(arow + (long long)u * p.lda + p.offa + g * p.sa + c0 + c);
-                As[(g * V + u) * ld + c] = val;
+    // stage list: (timestep block, channel pass)
+    const int npass = (p.width + kGramCW - 1) / kGramCW;
+    const int ntb = (t1 - t0 + p.tt - 1) / p.tt;
+    const int nstage = ntb * npass;
+
+    auto issue = [&](int s, float* dst) {
+        const int tb = s / npass, ps = s - tb * npass;
+        const int ts = t0 + tb * p.tt;
+        const int ttn = (t1 - ts) < p.tt ? (t1 - ts) : p.tt;
+        const int c0 = ps * kGramCW;
+        const int cn = (p.width - c0) < cwp ? (p.width - c0) : cwp;      // valid channels in this pass
+        float* As = dst;
+        float* Bs = dst + p.tt * rows_a * ld;
+        if (p.vec) {
+            const int cqn = cn >> 2;
+            for (int idx = tid; idx < ttn * rows_a * cq; idx += kGramThreads) {
+                const int c4 = idx % cq; const int r = idx / cq; const int row = r % rows_a; const int tl = r / rows_a;
+                const int gg = row / V, u = row - gg * V;
+                float* d = As + (tl * rows_a + row) * ld + c4 * 4;
+                if (c4 < cqn) cp_async16(d, p.a + (((long long)n * p.t + ts + tl) * V + u) * p.lda + p.offa + gg * p.sa + c0 + c4 * 4);
+                else *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            for (int idx = tid; idx < p.groups * V * cw; idx += kGramThreads) {
-                int c = idx % cw; int r = idx / cw; int u = r % V; int g = r / V;
-                float val = 0.f;
-                if (c < cn) val = __ldg(brow + (long long)u * p.ldb + p.offb + g * p.sb + c0 + c);
-                Bs[(g * V + u) * ld + c] = val;
+            for (int idx = tid; idx < ttn * rows_b * cq; idx += kGramThreads) {
+                const int c4 = idx % cq; const int r = idx / cq; const int row = r % rows_b; const int tl = r / rows_b;
+                const int gg = row / V, u = row - gg * V;
+                float* d = Bs + (tl * rows_b + row) * ld + c4 * 4;
+                if (c4 < cqn) cp_async16(d, p.b + (((long long)n * p.t + ts + tl) * V + u) * p.ldb + p.offb + gg * p.sb + c0 + c4 * 4);
+                else *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            __syncthreads();
+        } else {
+            for (int idx = tid; idx < ttn * rows_a * cwp; idx += kGramThreads) {
+                const int c = idx % cwp; const int r = idx / cwp; const int row = r % rows_a; const int tl = r / rows_a;
+                const int gg = row / V, u = row - gg * V;
+                As[(tl * rows_a + row) * ld + c] = (c < cn) ? __ldg(p.a + (((long long)n * p.t + ts + tl) * V + u) * p.lda + p.offa + gg * p.sa + c0 + c) : 0.f;
+            }
+            for (int idx = tid; idx < ttn * rows_b * cwp; idx += kGramThreads) {
+                const int c = idx % cwp; const int r = idx / cwp; const int row = r % rows_b; const int tl = r / rows_b;
+                const int gg = row / V, u = row - gg * V;
+                Bs[(tl * rows_b + row) * ld + c] = (c < cn) ? __ldg(p.b + (((long long)n * p.t + ts + tl) * V + u) * p.ldb + p.offb + gg * p.sb + c0 + c) : 0.f;
+            }
+        }
+        cp_async_commit();
+    };
+
+    if (nstage > 0) issue(0, smem);
+    for (int s = 0; s < nstage; ++s) {
+        float* cur = smem + (s & 1) * stage_floats;
+        if (s + 1 < nstage) { issue(s + 1, smem + ((s + 1) & 1) * stage_floats); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncthreads();
+        if (active) {
+            const int tb = s / npass;
+            const int ts = t0 + tb * p.tt;
+            const int ttn = (t1 - ts) < p.tt ? (t1 - ts) : p.tt;
+            for (int j = ks; j < ttn * cq; j += nks) {
+                const int tl = j / cq, c4 = j - tl * cq;
+                const float* ab = cur + tl * rows_a * ld + c4 * 4;
+                const float* bb = cur + tl * rows_b * ld + c4 * 4;
+                float4 av[5];
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                if (tile_id[s] < 0) continue;
-                const float* Ab = As + (size_t)((p.sa == 0 ? 0 : tg[s]) * V) * ld;
-                const float* Bb = Bs + (size_t)(tg[s] * V) * ld;
-                for (int c = cs; c < cn; c += 4) {
-                    float av[5], bv[5];
+                for (int i = 0; i < 5; ++i) av[i] = *reinterpret_cast<const float4*>(ab + offu[i]);
+#pragma unroll
+                for (int jj = 0; jj < 5; ++jj) {
+                    const float4 bv = *reinterpret_cast<const float4*>(bb + offv[jj]);
 #pragma unroll
                     for (int i = 0; i < 5; ++i) {
-                        int u = tu[s] + i; av[i] = (u < V) ? Ab[u * ld + c] : 0.f;
-                        int w = tv[s] + i; bv[i] = (w < V) ? Bb[w * ld + c] : 0.f;
+                        float x = acc[i][jj];
+                        x = fmaf(av[i].x, bv.x, x); x = fmaf(av[i].y, bv.y, x);
+                        x = fmaf(av[i].z, bv.z, x); x = fmaf(av[i].w, bv.w, x);
+                        acc[i][jj] = x;
                     }
-#pragma unroll
-                    for (int i = 0; i < 5; ++i)
-#pragma unroll
-                        for (int j = 0; j < 5; ++j) acc[s][i][j] = fmaf(av[i], bv[j], acc[s][i][j]);
                 }
             }
         }
+        __syncthreads();            // everyone is done with `cur` before the next issue overwrites it
     }
-    // reduce the 4 channel slices (adjacent lanes) and store
-    float* o = p.out + ((long long)n * p.nchunk + chunk) * p.groups * V * V;
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
+    // sum the k-slices in a fixed order through shared memory: red[ks][tile][25]
+    float* red = smem;
+    if (active) {
+        float* r = red + ((size_t)ks * tiles + tile) * 25;
 #pragma unroll
         for (int i = 0; i < 5; ++i)
 #pragma unroll
-            for (int j = 0; j < 5; ++j) {
-                float x = acc[s][i][j];
-                x += __shfl_xor_sync(0xffffffffu, x, 1);
-                x += __shfl_xor_sync(0xffffffffu, x, 2);
-                if (cs == 0 && tile_id[s] >= 0) {
-                    int u = tu[s] + i, w = tv[s] + j;
-                    if (u < V && w < V) o[((long long)tg[s] * V + u) * V + w] = x;
-                }
-            }
+            for (int j = 0; j < 5; ++j) r[i * 5 + j] = acc[i][j];
+    }
+    __syncthreads();
+    float* o = p.out + ((long long)n * p.nchunk + chunk) * p.groups * V * V;
+    for (int idx = tid; idx < tiles * 25; idx += kGramThreads) {
+        float sum = 0.f;
+        for (int k = 0; k < nks; ++k) sum += red[(size_t)k * tiles * 25 + idx];
+        const int tl = idx / 25, e = idx - tl * 25;
+        const int gg = tl / (nblk * nblk), r = tl % (nblk * nblk);
+        const int u = (r / nblk) * 5 + e / 5, w = (r % nblk) * 5 + e % 5;
+        if (u < V && w < V) o[((long long)gg * V + u) * V + w] = sum;
     }
 }
 
@@ -302,11 +356,27 @@ extern "C" AGCN_API int agcn_joint_gram(const float* a, const float* b, float* o
     AGCN_REQUIRE(v <= kMaxV && groups <= 3, AGCN_ERR_UNSUPPORTED, "agcn_joint_gram: V=%d > %d or groups=%d > 3", v, kMaxV, groups);
     AGCN_REQUIRE(offa >= 0 && offb >= 0 && offa + (groups - 1) * stridea + width <= lda && offb + (groups - 1) * strideb + width <= ldb,
                  AGCN_ERR_BAD_SHAPE, "agcn_joint_gram: channel window outside the row");
-    GramArgs p{a, b, out, nb, t, v, lda, ldb, groups, offa, stridea, offb, strideb, width, nchunk};
-    const int cw = width < kGramCW ? width : kGramCW;
+    GramArgs p{a, b, out, nb, t, v, lda, ldb, groups, offa, stridea, offb, strideb, width, nchunk, 1, 0};
+    const int cwp = ((width < kGramCW ? width : kGramCW) + 3) & ~3;
+    const int ld = cwp + 4;
     const int ga = stridea == 0 ? 1 : groups;
-    size_t smem = (size_t)(ga + groups) * v * (cw + 4) * sizeof(float);
+    const size_t step_bytes = (size_t)(ga + groups) * v * ld * sizeof(float);     // one staged timestep
+    const int t_per = (t + nchunk - 1) / nchunk;
+    int tt = (int)((28 * 1024) / step_bytes);
+    if (tt < 1) tt = 1;
+    if (tt > t_per) tt = t_per;
+    p.tt = tt;
+    p.vec = (width % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && offa % 4 == 0 && offb % 4 == 0 && stridea % 4 == 0 && strideb % 4 == 0 &&
+             aligned16(a) && aligned16(b)) ? 1 : 0;
+    const int nblk = (v + 4) / 5, tiles = groups * nblk * nblk;
+    size_t smem = 2 * (size_t)tt * step_bytes;
+    const int ntw = (tiles + 31) / 32;
+    const size_t red_bytes = (size_t)(kGramWarps / ntw) * tiles * 25 * sizeof(float);   // k-slice partials
+    if (smem < red_bytes) smem = red_bytes;
+    AGCN_REQUIRE(smem <= 200 * 1024, AGCN_ERR_UNSUPPORTED, "agcn_joint_gram: staged rows need %zu bytes of shared memory", smem);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaFuncSetAttribute(joint_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return fail(AGCN_ERR_CUDA, "agcn_joint_gram: %s", cudaGetErrorString(e));
     joint_gram_kernel<<<nb * nchunk, kGramThreads, smem, s>>>(p);
     return check_launch("agcn_joint_gram");
 }

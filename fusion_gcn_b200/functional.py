@@ -52,6 +52,13 @@ def _bn_forward(y, gamma, beta, buf: BnBuffers, training: bool):
                       BN_MOMENTUM, BN_EPS, training)
 
 
+def _zero_bias(like, n):
+    """Gradient of a conv bias that feeds a training-mode BatchNorm: BN subtracts the batch mean, so the loss does not
+    depend on the bias and its gradient is identically zero (the reference's autograd produces ~1e-9 rounding
+    noise here).  Returned analytically instead of summing dy over all rows."""
+    return torch.zeros((n,), device=like.device, dtype=torch.float32)
+
+
 def _t(w):
     """[cout, taps, cin] -> [cin, taps, cout] (weight of the input-gradient contraction)."""
     return w.permute(2, 1, 0).contiguous()
@@ -102,7 +109,8 @@ def gcn_backward(d_o, ctx, bn_w, dbn_w, down_w, spec: UnitSpec, dx=None, need_dx
         dy, dgam, dbet = K.bn_bwd(d_o, o, y, ctx["mean"], ctx["invstd"], bn_w)
         dyd, dgam2, dbet2 = K.bn_bwd(d_o, o, ctx["yd"], ctx["mean2"], ctx["invstd2"], dbn_w)
         wdown = down_w.reshape(cout, 1, cin)
-        d_down_w, d_down_b = K.conv_wgrad(dyd, x, precision=prec)
+        d_down_w, _ = K.conv_wgrad(dyd, x, want_bias=False, precision=prec)
+        d_down_b = _zero_bias(x, cout)
         if need_dx:
             dx = K.conv_fwd(dyd, _t(wdown), out=dx, accumulate=have, precision=prec)
             have = True
@@ -113,7 +121,8 @@ def gcn_backward(d_o, ctx, bn_w, dbn_w, down_w, spec: UnitSpec, dx=None, need_dx
                                   dres=dx if need_dx else None, dres_accumulate=have)
         have = have or need_dx
         dgam2 = dbet2 = d_down_w = d_down_b = None
-    d_wdc, d_bdc = K.conv_wgrad(dy, z, precision=prec)
+    d_wdc, _ = K.conv_wgrad(dy, z, want_bias=False, precision=prec)
+    d_bdc = _zero_bias(x, cout)
     dz = K.conv_fwd(dy, _t(ctx["wdc"]), precision=prec)                                # [nb,t,v,3*cin]
     dg_part = K.joint_gram(x, dz, groups=3, offa=0, stridea=0, offb=0, strideb=cin, width=cin, nchunk=ctx["nchunk"])
     ds, d_adj_b = K.attention_bwd(dg_part, p, ctx["scale"])
@@ -182,13 +191,15 @@ def tcn_backward(d_out, ctx, bn_w, rbn_w, spec: UnitSpec, need_dres=True, need_d
     elif spec.residual == "conv":
         du, dgam, dbet = K.bn_bwd(d_out, mask, u, ctx["t_mean"], ctx["t_invstd"], bn_w)
         dur, dgam2, dbet2 = K.bn_bwd(d_out, mask, ctx["ur"], ctx["t_mean2"], ctx["t_invstd2"], rbn_w)
-        d_wrp, d_br = K.conv_wgrad(dur, x_res, taps=1, stride=s, pad=0, precision=prec)
+        d_wrp, _ = K.conv_wgrad(dur, x_res, taps=1, stride=s, pad=0, want_bias=False, precision=prec)
+        d_br = _zero_bias(d_out, d_wrp.shape[0])
         d_wr = d_wrp.permute(0, 2, 1).unsqueeze(-1)
         if need_dres:
             d_xres = K.conv_fwd(dur, _t(ctx["wrp"]), t_out=x_res.shape[1], stride=s, pad=0, transposed=True, precision=prec)
     else:
         du, dgam, dbet = K.bn_bwd(d_out, mask, u, ctx["t_mean"], ctx["t_invstd"], bn_w)
-    d_wtp, d_bt = K.conv_wgrad(du, o, taps=ksz, stride=s, pad=pad, precision=prec)
+    d_wtp, _ = K.conv_wgrad(du, o, taps=ksz, stride=s, pad=pad, want_bias=False, precision=prec)
+    d_bt = _zero_bias(d_out, d_wtp.shape[0])
     d_o = None
     if need_do:
         d_o = K.conv_fwd(du, _t(ctx["wtp"]), t_out=o.shape[1], stride=s, pad=pad, transposed=True, precision=prec)

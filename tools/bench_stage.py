@@ -1,0 +1,123 @@
+"""Per-kernel timing at the NTU layer shapes (run on the GPU box):  python tools/bench_stage.py [name ...] [--tf32] [--once]
+
+Times single C-ABI entry points with CUDA events (L2 flushed between repetitions by the sheer tensor sizes) and prints the
+algorithmic GB/s and TFLOP/s of each.  ``--once`` runs each case a single time (for use under ncu).
+Cases are (unit width, T) pairs of the 10-unit NTU model at N'=128 person-sequences.
+"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from fusion_gcn_b200 import ops as K  # noqa: E402
+
+NB, V = 128, 25
+SHAPES = {"c64": (64, 300), "c128": (128, 150), "c256": (256, 75)}
+
+
+def timeit(fn, once):
+    if once:
+        fn()
+        torch.cuda.synchronize()
+        return float("nan")
+    for _ in range(2):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    reps = 5
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def report(name, ms, nbytes, flops):
+    print(f"{name:34s} {ms:8.3f} ms  {nbytes / ms / 1e6:8.1f} GB/s  {flops / ms / 1e9:8.1f} TFLOP/s", flush=True)
+
+
+def main():
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    once = "--once" in sys.argv
+    prec = K.PREC_TF32 if "--tf32" in sys.argv else K.PREC_FP32
+    want = lambda n: not args or any(a in n for a in args)   # noqa: E731
+    dev = "cuda"
+    for tag, (c, t) in SHAPES.items():
+        ci = c // 4
+        rows = NB * t * V
+        x = torch.randn(NB, t, V, c, device=dev)
+        act = rows * c * 4
+        if want(f"gram_score_{tag}"):
+            e = torch.randn(NB, t, V, 6 * ci, device=dev)
+            nchunk = K.pick_nchunk(NB, t)
+            ms = timeit(lambda: K.joint_gram(e, e, groups=3, offa=0, stridea=2 * ci, offb=ci, strideb=2 * ci, width=ci, nchunk=nchunk), once)
+            report(f"gram_score_{tag}", ms, e.numel() * 4, 3 * 2.0 * rows * V * ci)
+            del e
+        if want(f"gram_dg_{tag}"):
+            dz = torch.randn(NB, t, V, 3 * c, device=dev)
+            nchunk = K.pick_nchunk(NB, t)
+            ms = timeit(lambda: K.joint_gram(x, dz, groups=3, offa=0, stridea=0, offb=0, strideb=c, width=c, nchunk=nchunk), once)
+            report(f"gram_dg_{tag}", ms, act * 4, 3 * 2.0 * rows * V * c)
+            del dz
+        if want(f"mix_fwd_{tag}") or want(f"mix_bwd_{tag}"):
+            g = torch.randn(NB, 3, V, V, device=dev)
+            if want(f"mix_fwd_{tag}"):
+                ms = timeit(lambda: K.joint_mix(x, g, width=c, mode=K.MIX_AGG_FWD), once)
+                report(f"mix_fwd_{tag}", ms, act * 4, 3 * 2.0 * rows * V * c)
+            if want(f"mix_bwd_{tag}"):
+                dz = torch.randn(NB, t, V, 3 * c, device=dev)
+                dx = torch.randn(NB, t, V, c, device=dev)
+                ms = timeit(lambda: K.joint_mix(dz, g, width=c, mode=K.MIX_AGG_BWD, out=dx, accumulate=True), once)
+                report(f"mix_bwd_{tag}", ms, act * 5, 3 * 2.0 * rows * V * c)
+                del dz, dx
+        if want(f"mix_score_bwd_{tag}"):
+            e = torch.randn(NB, t, V, 6 * ci, device=dev)
+            ds = torch.randn(NB, 3, V, V, device=dev)
+            ms = timeit(lambda: K.joint_mix(e, ds, width=ci, mode=K.MIX_SCORE_BWD), once)
+            report(f"mix_score_bwd_{tag}", ms, e.numel() * 8, 6 * 2.0 * rows * V * ci)
+            del e, ds
+        for nm, cin, cout, taps in (("emb", c, 6 * ci, 1), ("proj", 3 * c, c, 1), ("dproj", c, 3 * c, 1), ("tconv", c, c, 9)):
+            if want(f"conv_{nm}_{tag}"):
+                xi = torch.randn(NB, t, V, cin, device=dev)
+                w = torch.randn(cout, taps, cin, device=dev) * 0.05
+                b = torch.randn(cout, device=dev)
+                ms = timeit(lambda: K.conv_fwd(xi, w, b, pad=(taps - 1) // 2, precision=prec), once)
+                report(f"conv_{nm}_{tag}", ms, rows * (cin + cout) * 4, 2.0 * rows * cin * cout * taps)
+                del xi
+            if want(f"wgrad_{nm}_{tag}"):
+                xi = torch.randn(NB, t, V, cin, device=dev)
+                dy = torch.randn(NB, t, V, cout, device=dev)
+                ms = timeit(lambda: K.conv_wgrad(dy, xi, taps=taps, pad=(taps - 1) // 2, want_bias=False, precision=prec), once)
+                report(f"wgrad_{nm}_{tag}", ms, rows * (cin + cout) * 4, 2.0 * rows * cin * cout * taps)
+                del xi, dy
+        if want(f"bn_{tag}"):
+            gamma, beta = torch.ones(c, device=dev), torch.zeros(c, device=dev)
+            rm, rv = torch.zeros(c, device=dev), torch.ones(c, device=dev)
+            ms = timeit(lambda: K.bn_stats(x, gamma, beta, rm, rv, None, 0.1, 1e-5, True), once)
+            report(f"bn_stats_{tag}", ms, act, 0)
+            sc, sh, mean, invstd = K.bn_stats(x, gamma, beta, rm, rv, None, 0.1, 1e-5, True)
+            ms = timeit(lambda: K.bn_apply(x, sc, sh, res_mode=K.RES_TENSOR, res=x, relu=True), once)
+            report(f"bn_apply_res_{tag}", ms, act * 3, 0)
+            ms = timeit(lambda: K.bn_bwd(x, x, x, mean, invstd, gamma), once)
+            report(f"bn_bwd_{tag}", ms, act * 6, 0)
+        del x
+        torch.cuda.empty_cache()
+    if want("skinny"):
+        t = 300
+        rows = NB * t * V
+        for cin, cout in ((64, 3), (96, 3), (64, 9)):
+            xi = torch.randn(NB, t, V, cin, device=dev)
+            w = torch.randn(cout, 1, cin, device=dev)
+            ms = timeit(lambda: K.conv_fwd(xi, w, None, precision=prec), once)
+            report(f"skinny_out_{cin}_{cout}", ms, rows * (cin + cout) * 4, 2.0 * rows * cin * cout)
+            dy = torch.randn(NB, t, V, cin, device=dev)
+            xs = torch.randn(NB, t, V, cout, device=dev)
+            ms = timeit(lambda: K.conv_wgrad(dy, xs, want_bias=True, precision=prec), once)
+            report(f"skinny_wgrad_{cout}_{cin}", ms, rows * (cin + cout) * 4, 2.0 * rows * cin * cout)
+
+
+if __name__ == "__main__":
+    main()
