@@ -429,6 +429,9 @@ using namespace agcn;
 int agcn_conv_fwd_tc(const float* x, const float* w, const float* bias, float* y,
                      int nb, int t_in, int t_out, int v, int cin, int cout,
                      int taps, int stride, int pad, int transposed, int accumulate, int split, float* w_lo, void* stream);
+int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* y,
+                      int nb, int t_in, int t_out, int v, int cin, int cout,
+                      int taps, int stride, int pad, int transposed, int accumulate, int split, float* w_split, void* stream);
 size_t agcn_conv_wgrad_tc_workspace_floats(int nb, int t_in, int t_out, int v, int cin, int cout, int taps, int stride, int pad, int split);
 int agcn_conv_wgrad_tc(const float* dy, const float* x, float* ws, int* splits_out,
                        int nb, int t_in, int t_out, int v, int cin, int cout, int taps, int stride, int pad, int split, void* stream);
@@ -453,12 +456,15 @@ extern "C" AGCN_API int agcn_conv_fwd(const float* x, const float* w, const floa
         const int split = precision == AGCN_PREC_FP32;
         const bool ws_ok = !split || (workspace != nullptr && workspace_bytes >= agcn_conv_fwd_workspace_bytes(cin, cout, taps, precision));
         if (ws_ok) {
+            int rc2 = agcn_conv_fwd_tc2(x, w, bias, y, nb, t_in, t_out, v, cin, cout, taps, stride, pad, transposed, accumulate, split,
+                                        static_cast<float*>(workspace), stream);
+            if (rc2 != AGCN_ERR_UNSUPPORTED) return rc2;
             int rc = agcn_conv_fwd_tc(x, w, bias, y, nb, t_in, t_out, v, cin, cout, taps, stride, pad, transposed,
                                       accumulate, split, static_cast<float*>(workspace), stream);
             if (rc != AGCN_ERR_UNSUPPORTED) return rc;   // unsupported shapes fall through to the FFMA kernel
         }
     }
-    if (taps == 1 && stride == 1 && pad == 0 && t_in == t_out && cout <= 16 && cin % 4 == 0 && cin <= 1024 && aligned16(x) && aligned16(w)) {
+    if (taps == 1 && stride == 1 && pad == 0 && t_in == t_out && cout < 16 && cin % 4 == 0 && cin <= 1024 && aligned16(x) && aligned16(w)) {
         // skinny output (input gradients of the first unit): one HBM pass, no GEMM tiling
         const long long rows = (long long)nb * t_out * v;
         const size_t smem = ((size_t)kSkinnyRows * (cin + 4) + (size_t)cout * cin + (size_t)kSkinnyRows * cout) * sizeof(float);
@@ -539,7 +545,8 @@ extern "C" AGCN_API int agcn_conv_wgrad(const float* dy, const float* x, float* 
         }
         if (rc != AGCN_ERR_UNSUPPORTED) return rc;      // unsupported shapes fall through to the FFMA kernel
     }
-    if (taps == 1 && stride == 1 && pad == 0 && t_in == t_out && cin <= 16 && cout <= 256) {
+    if (taps == 1 && stride == 1 && pad == 0 && t_in == t_out && cin <= 16 && cout <= 256 &&
+        (cin % 4 != 0 || cout % 4 != 0 || precision != AGCN_PREC_TF32)) {      // TF32 mode keeps tensor-core-eligible shapes on the tensor cores
         // skinny input (weight gradients of the first unit)
         const long long rows = (long long)nb * t_out * v;
         const int cpad = (cout + 31) / 32 * 32;

@@ -24,58 +24,18 @@
 // The activation hi/lo tiles are produced in shared memory by four transform warps (ld.shared -> cvt.rna -> st.shared in
 // place + lo tile -> fence.proxy.async -> mbarrier arrive); the weight hi/lo tensors are precomputed into the caller's
 // workspace and TMA-loaded.
-#include "common.cuh"
-#include <cuda.h>
+#include "tc_common.cuh"
 
 namespace agcn {
 namespace tc {
 
 constexpr int kStages = 6;                  // barrier slots; SPLIT kernels use 3 stages of twice the size
 constexpr int kABytes = 16 * 1024;
-constexpr int kKChunk = 32;                 // fp32 elements per 128-byte swizzle row
 constexpr int kThreads = 192;               // TMA warp, MMA warp, 4 epilogue warps
 constexpr int kThreadsSplit = 320;          // + 4 transform warps
-constexpr int kTmemCols = 256;
 constexpr size_t kSmemBytes = (size_t)192 * 1024 + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
-__device__ __forceinline__ float tf32_rna(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
-    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-// 3xTF32 operand split of `bytes` bytes at src: hi = rna_tf32(x) overwrites src in place, lo = x - hi (exact) goes to dst
-// at the same offsets, so any swizzle is preserved.  Called by the 128 transform threads.
-__device__ __forceinline__ void transform_split(uint32_t src, uint32_t dst, uint32_t bytes, int tid128) {
-    for (uint32_t off = (uint32_t)tid128 * 16u; off < bytes; off += 128u * 16u) {
-        const float4 v = lds128(src + off);
-        const float4 hi = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
-        sts128(src + off, hi);
-        sts128(dst + off, make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w));
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-
-// weights: w_split[0 .. n) = rna_tf32(w), w_split[n .. 2n) = w - hi
-constexpr int kSegment = 4;       // 3xTF32: promote the TMEM accumulator to fp32 registers every 4 k-chunks (K = 128)
 constexpr int kWgSegment = 4;     // 3xTF32 weight gradient: promote every 4 row chunks
-
-__global__ void split_weights_kernel(const float* w, float* w_split, long long n) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        const float v = w[i];
-        const float hi = tf32_rna(v);
-        w_split[i] = hi;
-        w_split[n + i] = v - hi;
-    }
-}
 
 struct TcArgs {
     float* y; const float* bias;
@@ -83,70 +43,6 @@ struct TcArgs {
     int tt, bn, n_tiles_n, kchunks, tiles_t, nparity;
     long long total_tiles;
 };
-
-// ---------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra WAIT_DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t"
-        "}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-    uint32_t r[16];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                 : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// K-major, 128-byte swizzle shared-memory matrix descriptor (rows at 128 B pitch, 8-row atoms at 1024 B pitch)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);        // start address, 16-byte units
-    d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset between 8-row atoms
-    d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
-    return d;
-}
 
 // number of (tap) iterations and their A-box T coordinate for one tile
 struct TapIter {
@@ -388,22 +284,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 }
 
 // ---------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = []() -> EncodeTiledFn {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
-            return nullptr;
-        return reinterpret_cast<EncodeTiledFn>(p);
-    }();
-    return fn;
-}
-
-
 // ================================================================================================ weight gradient
 //   dw[co][tap][ci] = sum_rows dy[row][co] * x[gather(row, tap)][ci]
 // UMMA view: D[M = co (128)][N = ci (<=256)] += A[M x K] * B[N x K]^T with K = rows.  Both operands are MN-major in

@@ -1,0 +1,446 @@
+// tcgen05 / TMA implicit GEMM, second generation: halo-resident activations.
+//
+//   y[nb][to][v][co] (+)= bias[co] + sum_tap sum_ci x[nb][ti(to,tap)][v][ci] * w[co][tap][ci]
+//
+// One CTA tile = tt consecutive output timesteps x all V joints (tt*V <= 128 rows = the UMMA M atom) x BN channels.
+// For every 32-channel K chunk the activation rows of ALL temporal taps of the tile are brought in ONCE: a TMA box of
+// tt+taps-1 timesteps (stride 1; two boxes of even / odd timesteps for the stride-2 forward gather; one box per parity
+// class for the transposed stride-2 gather).  Tap `d` is then the same shared-memory tile read d*V rows further down:
+// the UMMA descriptor start address is simply advanced by whole 128-byte rows.  tcgen05 applies the 128B swizzle to
+// absolute shared-memory address bits, so a start address that is not a multiple of the 8-row swizzle repeat is fine
+// (probed on B200 with tools/umma_rowoff_test.cu; the descriptor's base-offset field must stay 0).  Compared with
+// re-loading a shifted box per tap this divides the L2->SMEM activation traffic (and, in 3xTF32 mode, the hi/lo
+// operand-split work) of the 9x1 temporal conv by ~3.5.
+//
+// Warp roles (7 warps, +4 in 3xTF32 mode), persistent over tiles, 1 CTA / SM:
+//   warp 0      activation producer: TMA boxes of one K chunk -> A ring (NA stages)
+//   warp 1      MMA issuer: per (K chunk, tap): 4 x tcgen05.mma.kind::tf32 (M128, N=BN, K8), x3 in 3xTF32 mode
+//   warps 2..5  epilogue: tcgen05.ld -> (+bias, +old) -> st.global; in 3xTF32 mode also the fp32 promotion of segments
+//   warp 6      weight producer: one (tap, K chunk) BN x 32 box -> B ring (NB stages)
+//   warps 7..10 (3xTF32) split the A stage once per K chunk: hi = rna_tf32(x) in place, lo = x - hi into the stage's second
+//               half (the weights' hi / lo tensors are precomputed into the caller's workspace and TMA-loaded)
+// TMEM: 2 x 128 fp32 columns (epilogue of tile i overlaps the main loop of tile i+1; 3xTF32 segments ping-pong).
+#include "tc_common.cuh"
+#include <stdlib.h>
+
+namespace agcn {
+namespace tc2 {
+using namespace agcn::tc;
+
+constexpr int kMaxTaps = 9;
+constexpr int kMaxA = 4, kMaxB = 8;
+constexpr int kThreads2 = 7 * 32;
+constexpr int kThreads2Split = 11 * 32;
+constexpr uint32_t kBarBytes = 512;
+constexpr uint32_t kSmemBudget = 222u * 1024u;
+
+struct Tc2Args {
+    float* y; const float* bias;
+    int nb, t_out, v, cin, cout, stride, transposed, accumulate;
+    int tt, bn, n_tiles_n, kchunks, tiles_t, nparity;
+    long long total_tiles;
+    int na, nbst;                 // ring depths
+    int nblk;                     // activation boxes per stage
+    uint32_t blk_rows_bytes;      // bytes TMA writes per box
+    uint32_t blk_bytes;           // box slot (1024-aligned, >= the rows the last tap's MMA touches)
+    uint32_t a_stage_bytes;       // nblk * blk_bytes  (3xTF32: the lo copy follows)
+    uint32_t b_stage_bytes;       // bn * 128          (3xTF32: the lo copy follows)
+    int tmul;                     // box time coordinate = tmul * jt * tt + blk_t0[par][box]
+    int ntap[2];
+    signed char tap_id[2][kMaxTaps], tap_blk[2][kMaxTaps], tap_off[2][kMaxTaps];
+    int blk_t0[2][2];
+};
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(SPLIT ? kThreads2Split : kThreads2, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                const __grid_constant__ CUtensorMap map_blo, Tc2Args a) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_slot = a.a_stage_bytes * (SPLIT ? 2u : 1u);
+    const uint32_t b_slot = a.b_stage_bytes * (SPLIT ? 2u : 1u);
+    const uint32_t b_ring = smem_base + (uint32_t)a.na * a_slot;
+    const uint32_t bar_base = b_ring + (uint32_t)a.nbst * b_slot;
+    auto a_full = [&](int s) { return bar_base + 8u * s; };
+    auto a_empty = [&](int s) { return bar_base + 8u * (kMaxA + s); };
+    auto a_lo = [&](int s) { return bar_base + 8u * (2 * kMaxA + s); };
+    auto b_full = [&](int s) { return bar_base + 8u * (3 * kMaxA + s); };
+    auto b_empty = [&](int s) { return bar_base + 8u * (3 * kMaxA + kMaxB + s); };
+    auto b_lo = [&](int s) { return bar_base + 8u * (3 * kMaxA + 2 * kMaxB + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (3 * kMaxA + 3 * kMaxB + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (3 * kMaxA + 3 * kMaxB + 2 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (3 * kMaxA + 3 * kMaxB + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+        for (int s = 0; s < kMaxA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); mbar_init(a_lo(s), 4); }
+        for (int s = 0; s < kMaxB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); mbar_init(b_lo(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const uint32_t a_tx = (uint32_t)a.nblk * a.blk_rows_bytes;
+    const uint32_t b_tx = (uint32_t)a.bn * 128u * (SPLIT ? 2u : 1u);
+
+    if (warp == 0) {
+        // ===================================================== activation producer
+        if (lane == 0) {
+            int sa = 0; uint32_t pa = 0;
+            for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+                long long r = tile / a.n_tiles_n;
+                const int jt = (int)(r % a.tiles_t); r /= a.tiles_t;
+                const int par = (int)(r % a.nparity);
+                const int n = (int)(r / a.nparity);
+                const int tb = a.tmul * jt * a.tt;
+                for (int kc = 0; kc < a.kchunks; ++kc) {
+                    mbar_wait(a_empty(sa), pa ^ 1u);
+                    mbar_expect_tx(a_full(sa), a_tx);
+                    const uint32_t dst = smem_base + (uint32_t)sa * a_slot;
+                    for (int b = 0; b < a.nblk; ++b)
+                        tma_load_4d(dst + (uint32_t)b * a.blk_bytes, &map_a, a_full(sa), kc * kKChunk, 0, tb + a.blk_t0[par][b], n);
+                    if (++sa == a.na) { sa = 0; pa ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 6) {
+        // ===================================================== weight producer
+        if (lane == 0) {
+            int sb = 0; uint32_t pb = 0;
+            for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+                const int nt = (int)(tile % a.n_tiles_n);
+                const int par = (int)((tile / a.n_tiles_n / a.tiles_t) % a.nparity);
+                for (int kc = 0; kc < a.kchunks; ++kc) {
+                    for (int i = 0; i < a.ntap[par]; ++i) {
+                        mbar_wait(b_empty(sb), pb ^ 1u);
+                        mbar_expect_tx(b_full(sb), b_tx);
+                        tma_load_3d(b_ring + (uint32_t)sb * b_slot, &map_b, b_full(sb), kc * kKChunk, a.tap_id[par][i], nt * a.bn);
+                        if (SPLIT) tma_load_3d(b_ring + (uint32_t)sb * b_slot + a.b_stage_bytes, &map_blo, b_full(sb), kc * kKChunk, a.tap_id[par][i], nt * a.bn);
+                        if (++sb == a.nbst) { sb = 0; pb ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.bn >> 3) << 17) | ((128u >> 4) << 24);
+            int sa = 0; uint32_t pa = 0;
+            int sb = 0; uint32_t pb = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            const uint32_t row_bytes_v = (uint32_t)a.v * 128u;
+            for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+                const int par = (int)((tile / a.n_tiles_n / a.tiles_t) % a.nparity);
+                const int ntap = a.ntap[par];
+                const int iters = ntap * a.kchunks;
+                int it = 0;
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
+                uint32_t first = 1;
+                for (int kc = 0; kc < a.kchunks; ++kc) {
+                    mbar_wait(a_full(sa), pa);
+                    if (SPLIT) mbar_wait(a_lo(sa), pa);
+                    const uint32_t abase = smem_base + (uint32_t)sa * a_slot;
+                    for (int i = 0; i < ntap; ++i) {
+                        mbar_wait(b_full(sb), pb);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t aaddr = abase + (uint32_t)a.tap_blk[par][i] * a.blk_bytes + (uint32_t)a.tap_off[par][i] * row_bytes_v;
+                        const uint32_t baddr = b_ring + (uint32_t)sb * b_slot;
+                        const uint64_t da = make_smem_desc(aaddr), db = make_smem_desc(baddr);
+                        const uint64_t dalo = make_smem_desc(aaddr + a.a_stage_bytes), dblo = make_smem_desc(baddr + a.b_stage_bytes);
+#pragma unroll
+                        for (int k = 0; k < kKChunk / 8; ++k) {
+                            const uint64_t ko = (uint64_t)(k * 2);
+                            if (SPLIT) {
+                                umma_tf32(d_tmem, dalo + ko, db + ko, idesc, first ? 0u : 1u);
+                                umma_tf32(d_tmem, da + ko, dblo + ko, idesc, 1u);
+                                umma_tf32(d_tmem, da + ko, db + ko, idesc, 1u);
+                            } else {
+                                umma_tf32(d_tmem, da + ko, db + ko, idesc, first ? 0u : 1u);
+                            }
+                            first = 0;
+                        }
+                        umma_commit(b_empty(sb));
+                        if (++sb == a.nbst) { sb = 0; pb ^= 1u; }
+                        ++it;
+                        if (SPLIT && (it % kSegment) == 0 && it < iters) {
+                            // promote the partial accumulator to the epilogue's fp32 registers, continue in the other buffer
+                            umma_commit(tfull_bar(acc));
+                            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                            mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                            d_tmem = tmem_base + (uint32_t)(acc * 128);
+                            first = 1;
+                        }
+                    }
+                    umma_commit(a_empty(sa));
+                    if (++sa == a.na) { sa = 0; pa ^= 1u; }
+                }
+                umma_commit(tfull_bar(acc));
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else if (warp < 6) {
+        // ===================================================== epilogue warps (TMEM lane quarter = warp % 4)
+        const int q = warp & 3;
+        const int row_local = q * 32 + lane;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+            long long r = tile;
+            const int nt = (int)(r % a.n_tiles_n); r /= a.n_tiles_n;
+            const int jt = (int)(r % a.tiles_t); r /= a.tiles_t;
+            const int par = (int)(r % a.nparity);
+            const int n = (int)(r / a.nparity);
+            const int tl = row_local / a.v, vv = row_local - tl * a.v;
+            const int j = jt * a.tt + tl;
+            const int to = a.transposed ? a.stride * j + par : j;
+            const bool row_ok = (tl < a.tt) && (to < a.t_out);
+            float* yrow = a.y + (((long long)n * a.t_out + to) * a.v + vv) * a.cout + nt * a.bn;
+            const int iters = a.ntap[par] * a.kchunks;
+            const int nseg = SPLIT ? (iters + kSegment - 1) / kSegment : 1;
+            float sum[SPLIT ? 128 : 1];
+            for (int sg = 0; sg < nseg; ++sg) {
+                mbar_wait(tfull_bar(acc), acc_phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t taddr = tmem_base + (uint32_t)(acc * 128) + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+                for (int cg = 0; cg < 8; ++cg) {
+                    const int c = cg * 16;
+                    if (c < a.bn) {
+                        float vals[16];
+                        tmem_ld16(taddr + (uint32_t)c, vals);
+                        if (SPLIT) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) sum[SPLIT ? c + i : 0] = (sg == 0) ? vals[i] : sum[SPLIT ? c + i : 0] + vals[i];
+                        }
+                        if (sg == nseg - 1 && row_ok) {
+                            const int col = nt * a.bn + c;
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                if (col + g * 4 >= a.cout) break;
+                                float4 o;
+                                if (SPLIT) o = make_float4(sum[SPLIT ? c + g * 4 : 0], sum[SPLIT ? c + g * 4 + 1 : 0], sum[SPLIT ? c + g * 4 + 2 : 0], sum[SPLIT ? c + g * 4 + 3 : 0]);
+                                else o = make_float4(vals[g * 4], vals[g * 4 + 1], vals[g * 4 + 2], vals[g * 4 + 3]);
+                                if (a.bias) {
+                                    const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + col + g * 4));
+                                    o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                                }
+                                float4* p = reinterpret_cast<float4*>(yrow + c + g * 4);
+                                if (a.accumulate) {
+                                    const float4 old = *p;
+                                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                                }
+                                *p = o;
+                            }
+                        }
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(acc));
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else if (SPLIT) {
+        // ===================================================== operand split of the activation stage (128 threads)
+        const int tid128 = threadIdx.x - 7 * 32;
+        int sa = 0; uint32_t pa = 0;
+        for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+            for (int kc = 0; kc < a.kchunks; ++kc) {
+                mbar_wait(a_full(sa), pa);
+                const uint32_t src = smem_base + (uint32_t)sa * a_slot;
+                for (int b = 0; b < a.nblk; ++b) {
+                    const uint32_t s0 = src + (uint32_t)b * a.blk_bytes;
+                    // two 16-byte quads per thread per step: both loads are issued before the dependent converts
+                    for (uint32_t off = (uint32_t)tid128 * 16u; off < a.blk_rows_bytes; off += 256u * 16u) {
+                        const uint32_t off2 = off + 128u * 16u;
+                        const bool two = off2 < a.blk_rows_bytes;
+                        const float4 v0 = lds128(s0 + off);
+                        float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (two) v1 = lds128(s0 + off2);
+                        const float4 h0 = make_float4(tf32_rna(v0.x), tf32_rna(v0.y), tf32_rna(v0.z), tf32_rna(v0.w));
+                        const float4 h1 = make_float4(tf32_rna(v1.x), tf32_rna(v1.y), tf32_rna(v1.z), tf32_rna(v1.w));
+                        sts128(s0 + off, h0);
+                        sts128(s0 + a.a_stage_bytes + off, make_float4(v0.x - h0.x, v0.y - h0.y, v0.z - h0.z, v0.w - h0.w));
+                        if (two) {
+                            sts128(s0 + off2, h1);
+                            sts128(s0 + a.a_stage_bytes + off2, make_float4(v1.x - h1.x, v1.y - h1.y, v1.z - h1.z, v1.w - h1.w));
+                        }
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_lo(sa));
+                if (++sa == a.na) { sa = 0; pa ^= 1u; }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    }
+}
+
+}  // namespace tc2
+}  // namespace agcn
+
+using namespace agcn;
+
+// Returns AGCN_ERR_UNSUPPORTED for shapes outside this path (the caller then tries the older kernels).
+// split != 0: 3xTF32 (fp32 parity mode).
+int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* y,
+                      int nb, int t_in, int t_out, int v, int cin, int cout,
+                      int taps, int stride, int pad, int transposed, int accumulate, int split, float* w_split, void* stream) {
+    using namespace agcn::tc;
+    using namespace agcn::tc2;
+    static const bool disabled = getenv("AGCN_TC_V1") != nullptr;
+    if (disabled) return AGCN_ERR_UNSUPPORTED;
+    if (cin % 4 || cout % 16 || v > 128 || stride > 2 || taps > kMaxTaps) return AGCN_ERR_UNSUPPORTED;
+    if (transposed && stride > 1 && taps < stride) return AGCN_ERR_UNSUPPORTED;
+    if (!aligned16(x) || !aligned16(w) || !aligned16(y) || (bias && !aligned16(bias))) return AGCN_ERR_UNSUPPORTED;
+    if (split && (w_split == nullptr || !aligned16(w_split) || ((long long)cout * taps * cin) % 4)) return AGCN_ERR_UNSUPPORTED;
+    int bn;
+    if (cout % 128 == 0) bn = 128;
+    else if (cout % 96 == 0) bn = 96;
+    else if (cout % 64 == 0) bn = 64;
+    else if (cout <= 128) bn = cout;
+    else return AGCN_ERR_UNSUPPORTED;
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc2: cuTensorMapEncodeTiled is not available from the driver");
+
+    Tc2Args a;
+    a.y = y; a.bias = bias;
+    a.nb = nb; a.t_out = t_out; a.v = v; a.cin = cin; a.cout = cout; a.stride = stride; a.transposed = transposed; a.accumulate = accumulate;
+    a.tt = 128 / v;
+    a.bn = bn;
+    a.n_tiles_n = cout / bn;
+    a.kchunks = (cin + kKChunk - 1) / kKChunk;
+    a.nparity = transposed ? stride : 1;
+    const int t_per_class = transposed ? (t_out + stride - 1) / stride : t_out;
+    a.tiles_t = (t_per_class + a.tt - 1) / a.tt;
+    a.total_tiles = (long long)nb * a.nparity * a.tiles_t * a.n_tiles_n;
+
+    // ---- tap tables: which box and which timestep offset inside it every (parity, tap) reads
+    const int es = transposed ? 1 : stride;          // element stride of the activation box along T
+    a.tmul = transposed ? 1 : stride;
+    int nt_max = 0;                                  // timesteps per box
+    a.nblk = 1;
+    for (int p = 0; p < 2; ++p) { a.ntap[p] = 0; a.blk_t0[p][0] = a.blk_t0[p][1] = 0; }
+    if (!transposed) {
+        a.nblk = (stride == 2 && taps > 1) ? 2 : 1;
+        for (int tap = 0; tap < taps; ++tap) {
+            const int b = a.nblk == 2 ? (tap & 1) : 0;
+            const int off = a.nblk == 2 ? tap / 2 : (stride == 1 ? tap : 0);
+            const int i = a.ntap[0]++;
+            a.tap_id[0][i] = (signed char)tap; a.tap_blk[0][i] = (signed char)b; a.tap_off[0][i] = (signed char)off;
+            if (a.tt + off > nt_max) nt_max = a.tt + off;
+        }
+        if (stride == 2 && taps == 1) { /* 1x1 strided: single box, offset 0 */ }
+        a.blk_t0[0][0] = -pad;
+        a.blk_t0[0][1] = 1 - pad;
+        if (stride != 1 && stride != 2 && taps > 1) return AGCN_ERR_UNSUPPORTED;
+    } else {
+        for (int par = 0; par < a.nparity; ++par) {
+            int qmin = 1 << 30, qmax = -(1 << 30);
+            for (int tap = 0; tap < taps; ++tap) {
+                const int num = par + pad - tap;
+                if (num % stride) continue;
+                const int q = num / stride;
+                if (q < qmin) qmin = q;
+                if (q > qmax) qmax = q;
+            }
+            if (qmin > qmax) return AGCN_ERR_UNSUPPORTED;          // a parity class without taps
+            for (int tap = 0; tap < taps; ++tap) {
+                const int num = par + pad - tap;
+                if (num % stride) continue;
+                const int i = a.ntap[par]++;
+                a.tap_id[par][i] = (signed char)tap; a.tap_blk[par][i] = 0; a.tap_off[par][i] = (signed char)(num / stride - qmin);
+            }
+            a.blk_t0[par][0] = qmin;
+            if (a.tt + qmax - qmin > nt_max) nt_max = a.tt + qmax - qmin;
+        }
+    }
+    if (nt_max * es > 256) return AGCN_ERR_UNSUPPORTED;
+    a.blk_rows_bytes = (uint32_t)nt_max * v * 128u;
+    uint32_t need = ((uint32_t)(nt_max - a.tt) * v + 128u) * 128u;       // rows the last tap's M=128 operand touches
+    if (need < a.blk_rows_bytes) need = a.blk_rows_bytes;
+    a.blk_bytes = (need + 1023u) & ~1023u;
+    a.a_stage_bytes = (uint32_t)a.nblk * a.blk_bytes;
+    a.b_stage_bytes = (uint32_t)bn * 128u;
+    const uint32_t a_slot = a.a_stage_bytes * (split ? 2u : 1u), b_slot = a.b_stage_bytes * (split ? 2u : 1u);
+    const uint32_t budget = kSmemBudget - 1024u - kBarBytes;
+    a.na = 0; a.nbst = 0;
+    for (int min_b = 3; min_b >= 2 && a.na == 0; --min_b)
+        for (int na = kMaxA; na >= 1; --na) {
+            if ((uint64_t)na * a_slot + (uint64_t)min_b * b_slot > budget) continue;
+            int nbst = (int)((budget - (uint32_t)na * a_slot) / b_slot);
+            if (nbst > kMaxB) nbst = kMaxB;
+            a.na = na; a.nbst = nbst;
+            break;
+        }
+    if (a.na == 0) return AGCN_ERR_UNSUPPORTED;
+    // Measured on B200 (tools/bench_stage.py, profiles/r1h_*): the halo-resident tile wins for the multi-tap convs whenever two
+    // activation stages fit; with a single stage (3xTF32 at BN = 128) or for 1x1 convs the per-tap kernel of conv_tc.cu is
+    // as fast or faster, so those shapes stay there.
+    if (taps == 1 || a.na < 2) return AGCN_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)a.na * a_slot + (size_t)a.nbst * b_slot + 1024 + kBarBytes;
+
+    CUtensorMap map_a, map_b, map_blo;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)v, (cuuint64_t)t_in, (cuuint64_t)nb};
+        cuuint64_t strides[3] = {(cuuint64_t)cin * 4, (cuuint64_t)v * cin * 4, (cuuint64_t)t_in * v * cin * 4};
+        cuuint32_t box[4] = {(cuuint32_t)kKChunk, (cuuint32_t)v, (cuuint32_t)(nt_max * es), 1};
+        cuuint32_t estr[4] = {1, 1, (cuuint32_t)es, 1};
+        CUresult r = enc(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc2: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    {
+        auto encode_w = [&](CUtensorMap* m, const float* ptr) -> CUresult {
+            cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)taps, (cuuint64_t)cout};
+            cuuint64_t strides[2] = {(cuuint64_t)cin * 4, (cuuint64_t)taps * cin * 4};
+            cuuint32_t box[3] = {(cuuint32_t)kKChunk, 1, (cuuint32_t)bn};
+            cuuint32_t estr[3] = {1, 1, 1};
+            return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        };
+        const long long nw = (long long)cout * taps * cin;
+        CUresult r = encode_w(&map_b, split ? w_split : w);
+        if (r != CUDA_SUCCESS) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc2: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+        map_blo = map_b;
+        if (split) {
+            r = encode_w(&map_blo, w_split + nw);
+            if (r != CUDA_SUCCESS) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc2: cuTensorMapEncodeTiled(B lo) failed with %d", (int)r);
+            split_weights_kernel<<<ceil_div(nw, 256), 256, 0, st>>>(w, w_split, nw);
+            int rc = check_launch("agcn_conv_fwd_tc2(split weights)");
+            if (rc) return rc;
+        }
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+        if (e != cudaSuccess) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc2: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const long long grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
+    if (split) conv_tc2_kernel<true><<<(unsigned)grid, kThreads2Split, smem, st>>>(map_a, map_b, map_blo, a);
+    else conv_tc2_kernel<false><<<(unsigned)grid, kThreads2, smem, st>>>(map_a, map_b, map_blo, a);
+    return check_launch("agcn_conv_fwd_tc2");
+}

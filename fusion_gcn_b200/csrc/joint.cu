@@ -74,40 +74,59 @@ __global__ void __launch_bounds__(kGramThreads, 2) joint_gram_kernel(GramArgs p)
     const int ntb = (t1 - t0 + p.tt - 1) / p.tt;
     const int nstage = ntb * npass;
 
+    // Per-timestep copy table (built once): element e of operand A / B -> (source offset relative to the timestep's first
+    // row and the pass's first channel, destination offset inside the stage).  Staging a timestep is then one table read,
+    // two adds and a 16-byte cp.async per element; no index arithmetic in the stage loop.
+    int2* tab_a = reinterpret_cast<int2*>(smem + 2 * stage_floats);
+    const int ne_a = p.vec ? rows_a * cq : rows_a * cwp;
+    const int ne_b = p.vec ? rows_b * cq : rows_b * cwp;
+    int2* tab_b = tab_a + ne_a;
+    {
+        const int per_row = p.vec ? cq : cwp, cstep = p.vec ? 4 : 1;
+        for (int e = tid; e < ne_a; e += kGramThreads) {
+            const int c = (e % per_row) * cstep, row = e / per_row, gg = row / V, u = row - gg * V;
+            tab_a[e] = make_int2(u * p.lda + p.offa + gg * p.sa + c, (row * ld + c) | (c << 20));
+        }
+        for (int e = tid; e < ne_b; e += kGramThreads) {
+            const int c = (e % per_row) * cstep, row = e / per_row, gg = row / V, u = row - gg * V;
+            tab_b[e] = make_int2(u * p.ldb + p.offb + gg * p.sb + c, (row * ld + c) | (c << 20));
+        }
+    }
+    __syncthreads();
+
     auto issue = [&](int s, float* dst) {
         const int tb = s / npass, ps = s - tb * npass;
         const int ts = t0 + tb * p.tt;
         const int ttn = (t1 - ts) < p.tt ? (t1 - ts) : p.tt;
         const int c0 = ps * kGramCW;
         const int cn = (p.width - c0) < cwp ? (p.width - c0) : cwp;      // valid channels in this pass
-        float* As = dst;
-        float* Bs = dst + p.tt * rows_a * ld;
-        if (p.vec) {
-            const int cqn = cn >> 2;
-            for (int idx = tid; idx < ttn * rows_a * cq; idx += kGramThreads) {
-                const int c4 = idx % cq; const int r = idx / cq; const int row = r % rows_a; const int tl = r / rows_a;
-                const int gg = row / V, u = row - gg * V;
-                float* d = As + (tl * rows_a + row) * ld + c4 * 4;
-                if (c4 < cqn) cp_async16(d, p.a + (((long long)n * p.t + ts + tl) * V + u) * p.lda + p.offa + gg * p.sa + c0 + c4 * 4);
-                else *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            for (int idx = tid; idx < ttn * rows_b * cq; idx += kGramThreads) {
-                const int c4 = idx % cq; const int r = idx / cq; const int row = r % rows_b; const int tl = r / rows_b;
-                const int gg = row / V, u = row - gg * V;
-                float* d = Bs + (tl * rows_b + row) * ld + c4 * 4;
-                if (c4 < cqn) cp_async16(d, p.b + (((long long)n * p.t + ts + tl) * V + u) * p.ldb + p.offb + gg * p.sb + c0 + c4 * 4);
-                else *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        } else {
-            for (int idx = tid; idx < ttn * rows_a * cwp; idx += kGramThreads) {
-                const int c = idx % cwp; const int r = idx / cwp; const int row = r % rows_a; const int tl = r / rows_a;
-                const int gg = row / V, u = row - gg * V;
-                As[(tl * rows_a + row) * ld + c] = (c < cn) ? __ldg(p.a + (((long long)n * p.t + ts + tl) * V + u) * p.lda + p.offa + gg * p.sa + c0 + c) : 0.f;
-            }
-            for (int idx = tid; idx < ttn * rows_b * cwp; idx += kGramThreads) {
-                const int c = idx % cwp; const int r = idx / cwp; const int row = r % rows_b; const int tl = r / rows_b;
-                const int gg = row / V, u = row - gg * V;
-                Bs[(tl * rows_b + row) * ld + c] = (c < cn) ? __ldg(p.b + (((long long)n * p.t + ts + tl) * V + u) * p.ldb + p.offb + gg * p.sb + c0 + c) : 0.f;
+        for (int tl = 0; tl < ttn; ++tl) {
+            const float* srca = p.a + ((long long)n * p.t + ts + tl) * V * p.lda + c0;
+            const float* srcb = p.b + ((long long)n * p.t + ts + tl) * V * p.ldb + c0;
+            float* As = dst + tl * rows_a * ld;
+            float* Bs = dst + p.tt * rows_a * ld + tl * rows_b * ld;
+            if (p.vec) {
+                for (int e = tid; e < ne_a; e += kGramThreads) {
+                    const int2 q = tab_a[e];
+                    float* d = As + (q.y & 0xFFFFF);
+                    if ((q.y >> 20) < cn) cp_async16(d, srca + q.x);
+                    else *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                for (int e = tid; e < ne_b; e += kGramThreads) {
+                    const int2 q = tab_b[e];
+                    float* d = Bs + (q.y & 0xFFFFF);
+                    if ((q.y >> 20) < cn) cp_async16(d, srcb + q.x);
+                    else *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            } else {
+                for (int e = tid; e < ne_a; e += kGramThreads) {
+                    const int2 q = tab_a[e];
+                    As[q.y & 0xFFFFF] = ((q.y >> 20) < cn) ? __ldg(srca + q.x) : 0.f;
+                }
+                for (int e = tid; e < ne_b; e += kGramThreads) {
+                    const int2 q = tab_b[e];
+                    Bs[q.y & 0xFFFFF] = ((q.y >> 20) < cn) ? __ldg(srcb + q.x) : 0.f;
+                }
             }
         }
         cp_async_commit();
@@ -123,22 +142,23 @@ __global__ void __launch_bounds__(kGramThreads, 2) joint_gram_kernel(GramArgs p)
             const int tb = s / npass;
             const int ts = t0 + tb * p.tt;
             const int ttn = (t1 - ts) < p.tt ? (t1 - ts) : p.tt;
-            for (int j = ks; j < ttn * cq; j += nks) {
-                const int tl = j / cq, c4 = j - tl * cq;
-                const float* ab = cur + tl * rows_a * ld + c4 * 4;
-                const float* bb = cur + tl * rows_b * ld + c4 * 4;
-                float4 av[5];
+            for (int tl = 0; tl < ttn; ++tl) {
+                const float* ab = cur + tl * rows_a * ld;
+                const float* bb = cur + tl * rows_b * ld;
+                for (int c4 = ks; c4 < cq; c4 += nks) {
+                    float4 av[5];
 #pragma unroll
-                for (int i = 0; i < 5; ++i) av[i] = *reinterpret_cast<const float4*>(ab + offu[i]);
+                    for (int i = 0; i < 5; ++i) av[i] = *reinterpret_cast<const float4*>(ab + offu[i] + c4 * 4);
 #pragma unroll
-                for (int jj = 0; jj < 5; ++jj) {
-                    const float4 bv = *reinterpret_cast<const float4*>(bb + offv[jj]);
+                    for (int jj = 0; jj < 5; ++jj) {
+                        const float4 bv = *reinterpret_cast<const float4*>(bb + offv[jj] + c4 * 4);
 #pragma unroll
-                    for (int i = 0; i < 5; ++i) {
-                        float x = acc[i][jj];
-                        x = fmaf(av[i].x, bv.x, x); x = fmaf(av[i].y, bv.y, x);
-                        x = fmaf(av[i].z, bv.z, x); x = fmaf(av[i].w, bv.w, x);
-                        acc[i][jj] = x;
+                        for (int i = 0; i < 5; ++i) {
+                            float x = acc[i][jj];
+                            x = fmaf(av[i].x, bv.x, x); x = fmaf(av[i].y, bv.y, x);
+                            x = fmaf(av[i].z, bv.z, x); x = fmaf(av[i].w, bv.w, x);
+                            acc[i][jj] = x;
+                        }
                     }
                 }
             }
@@ -369,7 +389,8 @@ extern "C" AGCN_API int agcn_joint_gram(const float* a, const float* b, float* o
     p.vec = (width % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && offa % 4 == 0 && offb % 4 == 0 && stridea % 4 == 0 && strideb % 4 == 0 &&
              aligned16(a) && aligned16(b)) ? 1 : 0;
     const int nblk = (v + 4) / 5, tiles = groups * nblk * nblk;
-    size_t smem = 2 * (size_t)tt * step_bytes;
+    const size_t tab_bytes = (size_t)(ga + groups) * v * (p.vec ? cwp / 4 : cwp) * sizeof(int2);   // per-timestep copy table
+    size_t smem = 2 * (size_t)tt * step_bytes + tab_bytes;
     const int ntw = (tiles + 31) / 32;
     const size_t red_bytes = (size_t)(kGramWarps / ntw) * tiles * 25 * sizeof(float);   // k-slice partials
     if (smem < red_bytes) smem = red_bytes;

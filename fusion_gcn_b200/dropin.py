@@ -1,0 +1,98 @@
+"""Drop-in installer / launcher: runs the UNMODIFIED reference (main.py, YAML configs, fusion wrappers) on top of the
+B200 unit.
+
+The reference discovers its model with ``import_model(cfg.model)`` -> ``models.<name>.<name>.Model``
+(torch_src/session/session.py:50, util/dynamic_import.py:29-38) and every multimodal wrapper builds the backbone as
+``agcn.Model(...)`` through the module attribute (torch_src/models/mmargcn/early_fusion_models.py:18,36,71,108,144,187,
+228,265; late_fusion_models.py:19,55; rgb_feature_models.py:22,43,89).  The reference tree is read-only, so the drop-in
+is a rebinding of those module attributes:
+
+    models.mmargcn.agcn.{TemporalConv, SpatialGraphConv, SpatialTemporalConv, Model}  -> fusion_gcn_b200.modules.*
+    models.agcn.agcn.{unit_tcn, unit_gcn, TCN_GCN_unit, Model}                        -> fusion_gcn_b200.modules_original.*
+
+Usage (on a box that has both the reference checkout and a B200):
+
+    python -m fusion_gcn_b200.dropin --reference /path/to/fusion-gcn [--precision fp32|tf32] -- -f config/<...>.yaml
+
+which installs the import shims the reference needs on a current software stack, rebinds the
+classes and then ``runpy``s ``torch_src/main.py`` with cwd = the reference root (its config code scans cwd for models and
+datasets, torch_src/config.py:21-41).  YAML files, main.py and the session code stay byte-identical.
+"""
+import importlib
+import os
+import runpy
+import sys
+from unittest.mock import MagicMock
+
+_ORIGINALS = {}          # (module name, attribute) -> reference object, for uninstall()
+
+_MMARGCN_NAMES = ("TemporalConv", "SpatialGraphConv", "SpatialTemporalConv", "Model")
+_ORIGINAL_NAMES = ("unit_tcn", "unit_gcn", "TCN_GCN_unit", "Model")
+
+
+def install_shims(reference_root: str, host_stubs: bool = True) -> None:
+    """Makes the reference importable on numpy >= 1.24 / a box without matplotlib, seaborn or ray."""
+    import numpy as np
+    for p in (os.path.join(reference_root, "torch_src"), reference_root):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    names = ["matplotlib", "matplotlib.pyplot"]
+    if host_stubs:
+        names += ["seaborn", "ray", "ray.tune", "ray.tune.schedulers"]
+    for name in names:
+        try:
+            importlib.import_module(name)
+        except Exception:                                   # absent (or broken) optional dependency: stub it
+            sys.modules.setdefault(name, MagicMock(name=name))
+    if not hasattr(np, "int"):
+        np.int = int                                        # util/graph.py:75,88
+    if not hasattr(np, "float"):
+        np.float = float                                    # util/graph.py:117,127
+    # np.bool is deliberately left alone (numpy >= 2 defines it; overriding it breaks numpy.ma / scipy)
+
+
+def install(reference_root: str, precision="fp32", host_stubs: bool = True) -> dict:
+    """Rebinds the reference's unit / backbone classes to the B200 implementations.  Returns the patched modules."""
+    from . import modules, modules_original
+    if not os.path.isfile(os.path.join(reference_root, "torch_src", "models", "mmargcn", "agcn.py")):
+        raise FileNotFoundError(f"{reference_root} does not look like a fusion-gcn checkout (torch_src/models/mmargcn/agcn.py missing)")
+    install_shims(reference_root, host_stubs)
+    modules.set_default_precision(precision)
+    ref_m = importlib.import_module("models.mmargcn.agcn")
+    ref_o = importlib.import_module("models.agcn.agcn")
+    for mod, names, impl in ((ref_m, _MMARGCN_NAMES, modules), (ref_o, _ORIGINAL_NAMES, modules_original)):
+        for name in names:
+            _ORIGINALS.setdefault((mod.__name__, name), getattr(mod, name))
+            setattr(mod, name, getattr(impl, name))
+    return {"models.mmargcn.agcn": ref_m, "models.agcn.agcn": ref_o}
+
+
+def uninstall() -> None:
+    """Restores the reference classes (used by the tests)."""
+    for (mod_name, name), obj in _ORIGINALS.items():
+        setattr(sys.modules[mod_name], name, obj)
+    _ORIGINALS.clear()
+
+
+def main(argv=None) -> None:
+    argv = list(sys.argv[1:] if argv is None else argv)
+    rest = []
+    if "--" in argv:
+        i = argv.index("--")
+        argv, rest = argv[:i], argv[i + 1:]
+    import argparse
+    ap = argparse.ArgumentParser(prog="python -m fusion_gcn_b200.dropin", description=__doc__.split("\n")[0])
+    ap.add_argument("--reference", default=os.environ.get("FUSION_GCN_REFERENCE", "/root/reference"))
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "fp32_ffma"])
+    args = ap.parse_args(argv)
+    root = os.path.abspath(args.reference)
+    install(root, args.precision)
+    from . import capi
+    capi.lib()                                               # fail before training starts if the extension is not built
+    os.chdir(root)
+    sys.argv = [os.path.join(root, "torch_src", "main.py")] + rest
+    runpy.run_path(sys.argv[0], run_name="__main__")
+
+
+if __name__ == "__main__":
+    main()

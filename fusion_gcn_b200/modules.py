@@ -27,6 +27,16 @@ _PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "fp32_ffma": PREC_FP32_FFMA
                PREC_FP32: PREC_FP32, PREC_TF32: PREC_TF32, PREC_FP32_FFMA: PREC_FP32_FFMA}
 
 
+_default_precision = PREC_FP32
+
+
+def set_default_precision(precision) -> None:
+    """Precision mode given to modules constructed from now on (used by the drop-in launcher, where the reference's own
+    session code builds the model)."""
+    global _default_precision
+    _default_precision = _PRECISIONS[precision]
+
+
 def set_precision(module: nn.Module, precision) -> nn.Module:
     """'fp32' (parity mode: 3xTF32 tensor cores + FFMA), 'tf32' (single-pass tensor cores) or 'fp32_ffma' (FFMA only)
     for every unit under ``module``."""
@@ -81,7 +91,7 @@ class TemporalConv(nn.Module):
         self.bn = nn.BatchNorm2d(out_channels)
         conv_init(self.conv)
         bn_init(self.bn, 1)
-        self._agcn_precision = PREC_FP32
+        self._agcn_precision = _default_precision
 
     def _params(self):
         return (self.conv.weight, self.conv.bias, self.bn.weight, self.bn.bias)
@@ -135,7 +145,7 @@ class SpatialGraphConv(nn.Module):
         bn_init(self.bn, 1e-6)
         for i in range(self.num_subsets):
             conv_branch_init(self.conv_d[i], self.num_subsets)
-        self._agcn_precision = PREC_FP32
+        self._agcn_precision = _default_precision
 
     # hooks for the original-variant subclass (parameter called PA, adjacency not a buffer)
     def _adj_fixed(self, x):
@@ -197,7 +207,7 @@ class SpatialTemporalConv(nn.Module):
         else:
             self.residual = self._tcn_cls(in_channels, out_channels, kernel_size=1, stride=stride)
             self._residual_kind = "conv"
-        self._agcn_precision = PREC_FP32
+        self._agcn_precision = _default_precision
 
     def forward_cl(self, x):
         g, t = self.gcn1, self.tcn1
@@ -253,7 +263,7 @@ class Model(nn.Module):
             nn.init.normal_(self.fc.weight, 0, math.sqrt(2. / num_classes))
             self.out_channels = num_classes
         bn_init(self.data_bn, 1)
-        self._agcn_precision = PREC_FP32
+        self._agcn_precision = _default_precision
 
     def _register_layers(self):
         for layer_idx, layer in enumerate(self.layers):
