@@ -35,7 +35,8 @@ constexpr int kThreads = 192;               // TMA warp, MMA warp, 4 epilogue wa
 constexpr int kThreadsSplit = 320;          // + 4 transform warps
 constexpr size_t kSmemBytes = (size_t)192 * 1024 + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
-constexpr int kWgSegment = 4;     // 3xTF32 weight gradient: promote every 4 row chunks
+constexpr int kWgTransformWarps = 6;                       // 3xTF32 weight gradient: operand-split warps
+constexpr int kWgThreadsSplit = (6 + kWgTransformWarps) * 32;
 
 struct TcArgs {
     float* y; const float* bias;
@@ -299,6 +300,9 @@ struct WgArgs {
     int flat, rows_box, rpad, tt, chunks_per_sample;
     long long chunks_total, chunks_per_split;
     int n_tile, n_tiles, m_tiles, stages;
+    int pair;          // 1: a tile is two consecutive taps stacked along M (cout <= 64): lanes 0..63 = tap 2j, lanes 64..127 = tap 2j+1
+    int tap_tiles;     // taps, or ceil(taps / 2) in pair mode
+    int seg_chunks;    // 3xTF32: row chunks per accumulator segment (promoted to fp32 registers in between)
 };
 
 __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
@@ -312,7 +316,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t l
 }
 
 template <bool SPLIT>
-__global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreads, 1)
+__global__ void __launch_bounds__(SPLIT ? kWgThreadsSplit : kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, WgArgs a) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -340,7 +344,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dy) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
-        for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); mbar_init(lo_bar(s), 4); }
+        for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); mbar_init(lo_bar(s), kWgTransformWarps); }
         for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -357,15 +361,26 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
     int tile = blockIdx.x;
     const int nt = tile % a.n_tiles; tile /= a.n_tiles;
     const int mt = tile % a.m_tiles;
-    const int tap = tile / a.m_tiles;
+    const int tap_tile = tile / a.m_tiles;
+    const int tap = a.pair ? 2 * tap_tile : tap_tile;                    // first (or only) tap of this tile
+    const bool tap_b = a.pair && (tap + 1 < a.taps);                     // the stacked second tap exists
     const int m0 = mt * 128, k0 = nt * a.n_tile;
     const int split = blockIdx.y;
     const long long c_begin = (long long)split * a.chunks_per_split;
     long long c_end = c_begin + a.chunks_per_split;
     if (c_end > a.chunks_total) c_end = a.chunks_total;
-    const int a_boxes = (a.cout - m0 + 31) / 32 < 4 ? (a.cout - m0 + 31) / 32 : 4;
+    // which of the 4 dy slots / nsub_b x slots receive a TMA box (bit j = slot j)
+    uint32_t loaded = 0;
+    if (a.pair) {
+        const int nb32 = (a.cout + 31) / 32;                             // <= 2
+        for (int i = 0; i < nb32; ++i) { loaded |= 1u << i; if (tap_b) loaded |= 1u << (2 + i); }
+    } else {
+        const int a_boxes = (a.cout - m0 + 31) / 32 < 4 ? (a.cout - m0 + 31) / 32 : 4;
+        loaded = (1u << a_boxes) - 1u;
+    }
     const int b_boxes = (a.cin - k0 + 31) / 32 < (int)nsub_b ? (a.cin - k0 + 31) / 32 : (int)nsub_b;
-    const uint32_t stage_tx = (uint32_t)(a_boxes + b_boxes) * (uint32_t)a.rows_box * 128u;
+    loaded |= ((1u << b_boxes) - 1u) << 4;
+    const uint32_t stage_tx = (uint32_t)__popc(loaded) * (uint32_t)a.rows_box * 128u;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -379,7 +394,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
                 mbar_wait(empty_bar(stage), phase ^ 1u);
                 mbar_expect_tx(full_bar(stage), stage_tx);
                 const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
-                for (int i = 0; i < a_boxes; ++i) tma_load_4d(sa + i * sub_bytes, &map_dy, full_bar(stage), m0 + 32 * i, a1, a2, n);
+                if (a.pair) {
+                    // slots 0,1: dy rows [a1, ..) for tap 2j; slots 2,3: the same channels V rows earlier for tap 2j+1
+                    //   sum_k dy[k - V][co] * x[k + (tap - pad) V][ci] = sum_k' dy[k'][co] * x[k' + (tap + 1 - pad) V][ci]
+                    for (int i = 0; i < 4; ++i)
+                        if ((loaded >> i) & 1u)
+                            tma_load_4d(sa + i * sub_bytes, &map_dy, full_bar(stage), 32 * (i & 1), i < 2 ? a1 : a1 - a.v, 0, n);
+                } else {
+                    for (int i = 0; i < 4; ++i)
+                        if ((loaded >> i) & 1u) tma_load_4d(sa + i * sub_bytes, &map_dy, full_bar(stage), m0 + 32 * i, a1, a2, n);
+                }
                 const uint32_t sb = sa + 4u * sub_bytes;
                 for (int j = 0; j < b_boxes; ++j) tma_load_4d(sb + j * sub_bytes, &map_x, full_bar(stage), k0 + 32 * j, b1, b2, n);
                 if (++stage == a.stages) { stage = 0; phase ^= 1u; }
@@ -396,6 +420,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
             uint32_t first = 1;
             long long done = 0;
             const long long nchunks = c_end - c_begin;
+            const int ksteps = (a.rows_box + 7) / 8;
             for (long long c = c_begin; c < c_end; ++c) {
                 mbar_wait(full_bar(stage), phase);
                 if (SPLIT) mbar_wait(lo_bar(stage), phase);
@@ -404,7 +429,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
                 const uint64_t da = make_smem_desc_mn(sa, sub_bytes), db = make_smem_desc_mn(sa + 4u * sub_bytes, sub_bytes);
                 const uint64_t dalo = make_smem_desc_mn(sa + raw_bytes, sub_bytes);
                 const uint64_t dblo = make_smem_desc_mn(sa + raw_bytes + 4u * sub_bytes, sub_bytes);
-                for (int kg = 0; kg < a.rpad / 8; ++kg) {
+                for (int kg = 0; kg < ksteps; ++kg) {
                     const uint64_t ko = (uint64_t)(kg * 64);
                     if (SPLIT) {
                         umma_tf32(d_tmem, dalo + ko, db + ko, idesc, first ? 0u : 1u);
@@ -418,7 +443,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
                 umma_commit(empty_bar(stage));
                 if (++stage == a.stages) { stage = 0; phase ^= 1u; }
                 ++done;
-                if (SPLIT && (done % kWgSegment) == 0 && done < nchunks) {
+                if (SPLIT && (done % a.seg_chunks) == 0 && done < nchunks) {
                     // promote this partial accumulator to the epilogue's fp32 registers, continue in the other TMEM buffer
                     umma_commit(tfull_bar(acc));
                     if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
@@ -432,10 +457,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
         }
     } else if (warp < 6) {
         const int q = warp & 3;
-        const int co = m0 + q * 32 + lane;
-        float* out = a.ws + (((long long)split * a.cout + co) * a.taps + tap) * a.cin + k0;
+        int co, otap;
+        if (a.pair) { co = (q & 1) * 32 + lane; otap = tap + (q >> 1); }
+        else { co = m0 + q * 32 + lane; otap = tap; }
+        const bool store = (co < a.cout) && (otap < a.taps);
+        float* out = a.ws + (((long long)split * a.cout + (store ? co : 0)) * a.taps + (store ? otap : 0)) * a.cin + k0;
         const long long nchunks = c_end - c_begin;
-        const int nseg = SPLIT ? (int)((nchunks + kWgSegment - 1) / kWgSegment) : 1;
+        const int nseg = SPLIT ? (int)((nchunks + a.seg_chunks - 1) / a.seg_chunks) : 1;
         int acc = 0; uint32_t acc_phase = 0;
         float sum[SPLIT ? 128 : 1];              // SPLIT: n_tile <= 128
         for (int sg = 0; sg < nseg; ++sg) {
@@ -452,7 +480,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
 #pragma unroll
                         for (int i = 0; i < 16; ++i) sum[SPLIT ? c + i : 0] = (sg == 0) ? vals[i] : sum[SPLIT ? c + i : 0] + vals[i];
                     }
-                    if (sg == nseg - 1 && co < a.cout) {
+                    if (sg == nseg - 1 && store) {
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
                             if (k0 + c + g * 4 < a.cin) {
@@ -471,12 +499,36 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
     } else if (SPLIT) {
-        const int tid128 = threadIdx.x - 6 * 32;
+        // operand split (kWgTransformWarps warps): hi = rna_tf32(x) in place, lo = x - hi into the stage's second half.
+        // Only the rows TMA wrote are touched (the pad rows stay zero in both halves).
+        const int tidx = threadIdx.x - 6 * 32;
+        constexpr uint32_t kStep = kWgTransformWarps * 32u * 16u;
+        const uint32_t box_bytes = (uint32_t)a.rows_box * 128u;
+        const int nslots = 4 + (int)nsub_b;
         int stage = 0; uint32_t phase = 0;
         for (long long c = c_begin; c < c_end; ++c) {
             mbar_wait(full_bar(stage), phase);
             const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
-            transform_split(sa, sa + raw_bytes, raw_bytes, tid128);
+            for (int j = 0; j < nslots; ++j) {
+                if (!((loaded >> j) & 1u)) continue;
+                const uint32_t s0 = sa + (uint32_t)j * sub_bytes;
+                for (uint32_t off = (uint32_t)tidx * 16u; off < box_bytes; off += 2u * kStep) {
+                    const uint32_t off2 = off + kStep;
+                    const bool two = off2 < box_bytes;
+                    const float4 v0 = lds128(s0 + off);
+                    float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (two) v1 = lds128(s0 + off2);
+                    const float4 h0 = make_float4(tf32_rna(v0.x), tf32_rna(v0.y), tf32_rna(v0.z), tf32_rna(v0.w));
+                    const float4 h1 = make_float4(tf32_rna(v1.x), tf32_rna(v1.y), tf32_rna(v1.z), tf32_rna(v1.w));
+                    sts128(s0 + off, h0);
+                    sts128(s0 + raw_bytes + off, make_float4(v0.x - h0.x, v0.y - h0.y, v0.z - h0.z, v0.w - h0.w));
+                    if (two) {
+                        sts128(s0 + off2, h1);
+                        sts128(s0 + raw_bytes + off2, make_float4(v1.x - h1.x, v1.y - h1.y, v1.z - h1.z, v1.w - h1.w));
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(lo_bar(stage));
             if (++stage == a.stages) { stage = 0; phase ^= 1u; }
@@ -509,15 +561,22 @@ static WgPlan plan_wgrad(int nb, int t_in, int t_out, int v, int cin, int cout, 
     a.n_tiles = (cin + a.n_tile - 1) / a.n_tile;
     a.m_tiles = (cout + 127) / 128;
     const int nsub = 4 + a.n_tile / 32;
-    int rmax = ((split ? 32 : 48) * 1024) / (nsub * 128);   // rows per stage: raw operands <= 48 KB (32 KB + 32 KB lo when split)
+    // Rows per stage.  3xTF32: 24 KB of raw operands (+ 24 KB of lo residuals) so that four stages are in flight -- with
+    // two 96 KB stages the TMA latency of every stage was exposed (ncu, profiles/r1i).  TF32: 48 KB, four stages.
+    int rmax = ((split ? 24 : 48) * 1024) / (nsub * 128);
     rmax = rmax / 8 * 8;
     if (rmax > 128) rmax = 128;
+    if (rmax < 8) return p;
     a.flat = (stride == 1 && t_in == t_out) ? 1 : 0;
+    // two taps per tile when the output channels fill only half of the M = 128 atom (flat layout only: the second tap is
+    // the same dy rows V positions earlier)
+    a.pair = (a.flat && taps > 1 && cout <= 64) ? 1 : 0;
+    a.tap_tiles = a.pair ? (taps + 1) / 2 : taps;
     if (a.flat) {
         a.rows_box = rmax;
         a.rpad = rmax;
         a.tt = 0;
-        a.chunks_per_sample = (t_out * v + a.rows_box - 1) / a.rows_box;
+        a.chunks_per_sample = (t_out * v + (a.pair ? v : 0) + a.rows_box - 1) / a.rows_box;
     } else {
         a.tt = rmax / v;
         if (a.tt < 1) { a.tt = 1; }
@@ -528,15 +587,16 @@ static WgPlan plan_wgrad(int nb, int t_in, int t_out, int v, int cin, int cout, 
         a.chunks_per_sample = (t_out + a.tt - 1) / a.tt;
     }
     a.chunks_total = (long long)nb * a.chunks_per_sample;
-    if (rmax < 8) return p;
+    a.seg_chunks = 256 / a.rows_box;
+    if (a.seg_chunks < 1) a.seg_chunks = 1;
     const size_t stage_bytes = (size_t)nsub * a.rpad * 128 * (split ? 2 : 1);
     int stages = (int)((192 * 1024) / stage_bytes);
     if (stages > kStages) stages = kStages;
     if (stages < 2) return p;
     a.stages = stages;
-    const long long tiles = (long long)taps * a.m_tiles * a.n_tiles;
-    long long splits = (2LL * kNumSMs + tiles - 1) / tiles;
-    if (splits > kNumSMs) splits = kNumSMs;
+    // one resident wave: (tiles x splits) CTAs <= 148 SMs (1 CTA / SM), every CTA streams an equal share of the row chunks
+    const long long tiles = (long long)a.tap_tiles * a.m_tiles * a.n_tiles;
+    long long splits = kNumSMs / tiles;
     if (splits > a.chunks_total) splits = a.chunks_total;
     if (splits < 1) splits = 1;
     a.chunks_per_split = (a.chunks_total + splits - 1) / splits;
@@ -676,9 +736,9 @@ int agcn_conv_wgrad_tc(const float* dy, const float* x, float* ws, int* splits_o
         if (e != cudaSuccess) return fail(AGCN_ERR_CUDA, "agcn_conv_wgrad_tc: %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    dim3 grid((unsigned)(taps * a.m_tiles * a.n_tiles), (unsigned)p.splits);
+    dim3 grid((unsigned)(a.tap_tiles * a.m_tiles * a.n_tiles), (unsigned)p.splits);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (split) wgrad_tc_kernel<true><<<grid, kThreadsSplit, p.smem, st>>>(map_dy, map_x, a);
+    if (split) wgrad_tc_kernel<true><<<grid, kWgThreadsSplit, p.smem, st>>>(map_dy, map_x, a);
     else wgrad_tc_kernel<false><<<grid, kThreads, p.smem, st>>>(map_dy, map_x, a);
     *splits_out = p.splits;
     return check_launch("agcn_conv_wgrad_tc");

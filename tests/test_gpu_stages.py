@@ -31,7 +31,7 @@ def both(fn_name, K, tensors, **kw):
 CONV_CASES = [  # nb, t_in, v, cin, cout, taps, stride
     (2, 12, 25, 3, 96, 1, 1), (2, 12, 25, 64, 64, 9, 1), (3, 13, 20, 16, 32, 9, 2), (2, 13, 20, 16, 32, 1, 2),
     (1, 7, 5, 515, 64, 1, 1), (2, 9, 22, 9, 16, 1, 1), (1, 1, 37, 256, 60, 1, 1), (2, 30, 25, 128, 256, 9, 2),
-    (1, 300, 25, 64, 64, 9, 1)]
+    (1, 300, 25, 64, 64, 9, 1), (2, 11, 20, 48, 48, 9, 1), (2, 9, 25, 32, 64, 3, 1)]
 
 
 @pytest.mark.parametrize("mode", ["ffma", "fp32"])
@@ -190,7 +190,8 @@ def _trunc_tf32(t):
 
 TC_CASES = [  # nb, t_in, v, cin, cout, taps, stride  (shapes the tcgen05 path takes; others fall back to FFMA)
     (2, 20, 25, 64, 64, 9, 1), (2, 21, 25, 64, 128, 9, 2), (2, 12, 25, 16, 96, 1, 1), (2, 14, 20, 64, 128, 9, 1),
-    (1, 10, 25, 768, 256, 1, 1), (2, 14, 22, 32, 32, 9, 1), (2, 20, 18, 128, 256, 1, 2)]
+    (1, 10, 25, 768, 256, 1, 1), (2, 14, 22, 32, 32, 9, 1), (2, 20, 18, 128, 256, 1, 2), (2, 11, 20, 48, 48, 9, 1),
+    (2, 9, 25, 32, 64, 3, 1)]
 
 
 @pytest.mark.parametrize("nb,t_in,v,cin,cout,taps,stride", TC_CASES)

@@ -173,7 +173,9 @@ def test_standalone_modules_reference_layout(pkg):
 def test_tf32_mode_unit_matches_truncated_tf32_math(pkg, name, monkeypatch):
     """TF32 mode (single-pass tcgen05 kind::tf32) is reported separately from the fp32 parity mode.  Its contract: the
     contractions see TF32-TRUNCATED operands with fp32 accumulation.  The same unit is run on the CPU with exactly that
-    arithmetic restated in torch (oracle.stages.Tf32Emulation) and must agree to 1e-4 on output, dx and every gradient.
+    arithmetic restated in torch (oracle.stages.Tf32Emulation) and must agree to 5e-4 on output, dx and every gradient
+    (an intermediate that differs by one fp32 ulp between the two summation orders can fall on the other side of a
+    TF32 truncation boundary, a 2^-10 relative flip of that operand, so the bound is a few truncation flips, not fp32).
     Against the fp64 reference the output stays within 2e-3; gradients of these tiny loudly-initialised fixtures amplify
     the truncation bias (measured 1e-2 .. 0.25 on dx, identical on GPU and in the emulation) and carry no bound."""
     from fusion_gcn_b200 import functional as FN, modules as M
@@ -195,8 +197,8 @@ def test_tf32_mode_unit_matches_truncated_tf32_math(pkg, name, monkeypatch):
     monkeypatch.setattr(FN, "K", S.Tf32Emulation())          # TEST-ONLY backend swap, CPU
     y_e, dx_e, grads_e = run("cpu")
     assert rel_err(y, g["f64.y"]) <= 2e-3
-    assert rel_err(y, y_e) <= 1e-4 and rel_err(dx, dx_e) <= 1e-4
-    worst = check_grads(grads, grads_e, 1e-4, name + "/tf32-vs-emulation")
+    assert rel_err(y, y_e) <= 5e-4 and rel_err(dx, dx_e) <= 5e-4
+    worst = check_grads(grads, grads_e, 5e-4, name + "/tf32-vs-emulation")
     print(f"tf32 {name}: y vs fp64 {rel_err(y, g['f64.y']):.2e}, dx vs fp64 {rel_err(dx, g['f64.dx']):.2e}, vs emulation worst {worst}")
 
 
