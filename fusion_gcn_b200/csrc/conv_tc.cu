@@ -25,6 +25,7 @@
 // place + lo tile -> fence.proxy.async -> mbarrier arrive); the weight hi/lo tensors are precomputed into the caller's
 // workspace and TMA-loaded.
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace agcn {
 namespace tc {
@@ -35,7 +36,9 @@ constexpr int kThreads = 192;               // TMA warp, MMA warp, 4 epilogue wa
 constexpr int kThreadsSplit = 320;          // + 4 transform warps
 constexpr size_t kSmemBytes = (size_t)192 * 1024 + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
-constexpr int kWgTransformWarps = 6;                       // 3xTF32 weight gradient: operand-split warps
+constexpr int kWgTransformWarps = 8;                       // 3xTF32 weight gradient: operand-split warps
+constexpr int kWgStages = 8;                               // barrier slots of the weight-gradient raw ring
+constexpr int kWgBarBytes = 512;
 constexpr int kWgThreadsSplit = (6 + kWgTransformWarps) * 32;
 
 struct TcArgs {
@@ -43,6 +46,7 @@ struct TcArgs {
     int nb, t_in, t_out, v, cin, cout, taps, stride, pad, transposed, accumulate;
     int tt, bn, n_tiles_n, kchunks, tiles_t, nparity;
     long long total_tiles;
+    int dbg;      // bring-up only (env AGCN_CONV_DEBUG): 1 skip operand split, 2 one MMA per stage, 4 skip global stores
 };
 
 // number of (tap) iterations and their A-box T coordinate for one tile
@@ -163,6 +167,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         const uint64_t dalo = make_smem_desc(sa + 2 * kABytes), dblo = make_smem_desc(sa + 3 * kABytes);
 #pragma unroll
                         for (int k = 0; k < kKChunk / 8; ++k) {
+                            if ((a.dbg & 2) && k) break;
                             const uint64_t ko = (uint64_t)(k * 2);
                             if (SPLIT) {
                                 umma_tf32(d_tmem, dalo + ko, db + ko, idesc, first ? 0u : 1u);
@@ -226,7 +231,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                             for (int i = 0; i < 16; ++i) sum[SPLIT ? c + i : 0] = (sg == 0) ? vals[i] : sum[SPLIT ? c + i : 0] + vals[i];
                         }
-                        if (sg == nseg - 1 && row_ok) {
+                        if (sg == nseg - 1 && row_ok && !(a.dbg & 4)) {
                             const int col = nt * a.bn + c;
 #pragma unroll
                             for (int g = 0; g < 4; ++g) {
@@ -269,7 +274,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 for (int kc = 0; kc < a.kchunks; ++kc) {
                     mbar_wait(full_bar(stage), phase);
                     const uint32_t sa = smem_base + stage * STAGE;
-                    transform_split(sa, sa + 2 * kABytes, (uint32_t)rows_box * 128u, tid128);
+                    if (!(a.dbg & 1)) transform_split(sa, sa + 2 * kABytes, (uint32_t)rows_box * 128u, tid128);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(lo_bar(stage));
                     if (++stage == NST) { stage = 0; phase ^= 1u; }
@@ -303,6 +308,7 @@ struct WgArgs {
     int pair;          // 1: a tile is two consecutive taps stacked along M (cout <= 64): lanes 0..63 = tap 2j, lanes 64..127 = tap 2j+1
     int tap_tiles;     // taps, or ceil(taps / 2) in pair mode
     int seg_chunks;    // 3xTF32: row chunks per accumulator segment (promoted to fp32 registers in between)
+    int dbg;           // bring-up only (env AGCN_WG_DEBUG): bit 0 skips the operand split, bit 1 skips the MMAs -> wrong results, timing probes
 };
 
 __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
@@ -322,22 +328,24 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sub_bytes = (uint32_t)a.rpad * 128u;
     const uint32_t nsub_b = (uint32_t)a.n_tile / 32u;
-    const uint32_t raw_bytes = (4u + nsub_b) * sub_bytes;
-    const uint32_t stage_bytes = raw_bytes * (SPLIT ? 2u : 1u);          // raw sub-boxes, then (SPLIT) their lo residuals
-    const uint32_t bar_base = smem_base + (uint32_t)a.stages * stage_bytes;
+    const uint32_t raw_bytes = (4u + nsub_b) * sub_bytes;                 // one stage of TMA payload (raw, becomes hi in place)
+    const uint32_t lo_ring = smem_base + (uint32_t)a.stages * raw_bytes;  // SPLIT: two slots of lo residuals
+    const uint32_t bar_base = lo_ring + (SPLIT ? 2u * raw_bytes : 0u);
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
-    auto lo_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
-    auto tfull_bar = [&](int s) { return bar_base + 8u * (3 * kStages + s); };
-    auto tempty_bar = [&](int s) { return bar_base + 8u * (3 * kStages + 2 + s); };
-    const uint32_t tmem_slot = bar_base + 8u * (3 * kStages + 4);
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kWgStages + s); };
+    auto lo_bar = [&](int s) { return bar_base + 8u * (2 * kWgStages + s); };
+    auto lo_empty = [&](int s) { return bar_base + 8u * (3 * kWgStages + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (3 * kWgStages + 2 + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (3 * kWgStages + 4 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (3 * kWgStages + 6);
+    constexpr int kCols = SPLIT ? 512 : 256;                              // SPLIT: 2 x 128 segment accumulators + 128 master sums
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     // clear the operand stages once: rows the TMA boxes never write must read as zero in the K reduction
     {
         uint8_t* base_ptr = smem_raw + (smem_base - smem_u32(smem_raw));
         uint4* p4 = reinterpret_cast<uint4*>(base_ptr);
-        const uint32_t n16 = (uint32_t)a.stages * stage_bytes / 16u;
+        const uint32_t n16 = ((uint32_t)a.stages + (SPLIT ? 2u : 0u)) * raw_bytes / 16u;
         for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) p4[i] = make_uint4(0, 0, 0, 0);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy zeros visible to TMA / UMMA
     }
@@ -345,11 +353,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dy) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
         for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); mbar_init(lo_bar(s), kWgTransformWarps); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(lo_empty(s), 1); mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(kTmemCols) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(kCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -393,7 +401,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
                 else { a1 = 0; a2 = cs * a.tt; b1 = 0; b2 = a.stride * a2 + tap - a.pad; }
                 mbar_wait(empty_bar(stage), phase ^ 1u);
                 mbar_expect_tx(full_bar(stage), stage_tx);
-                const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
+                const uint32_t sa = smem_base + (uint32_t)stage * raw_bytes;
                 if (a.pair) {
                     // slots 0,1: dy rows [a1, ..) for tap 2j; slots 2,3: the same channels V rows earlier for tap 2j+1
                     //   sum_k dy[k - V][co] * x[k + (tap - pad) V][ci] = sum_k' dy[k'][co] * x[k' + (tap + 1 - pad) V][ci]
@@ -419,17 +427,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
             uint32_t d_tmem = tmem_base;
             uint32_t first = 1;
             long long done = 0;
+            int sl = 0;
             const long long nchunks = c_end - c_begin;
             const int ksteps = (a.rows_box + 7) / 8;
             for (long long c = c_begin; c < c_end; ++c) {
                 mbar_wait(full_bar(stage), phase);
                 if (SPLIT) mbar_wait(lo_bar(stage), phase);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
+                const uint32_t sa = smem_base + (uint32_t)stage * raw_bytes;
+                const uint32_t slo = lo_ring + (uint32_t)sl * raw_bytes;
                 const uint64_t da = make_smem_desc_mn(sa, sub_bytes), db = make_smem_desc_mn(sa + 4u * sub_bytes, sub_bytes);
-                const uint64_t dalo = make_smem_desc_mn(sa + raw_bytes, sub_bytes);
-                const uint64_t dblo = make_smem_desc_mn(sa + raw_bytes + 4u * sub_bytes, sub_bytes);
-                for (int kg = 0; kg < ksteps; ++kg) {
+                const uint64_t dalo = make_smem_desc_mn(slo, sub_bytes);
+                const uint64_t dblo = make_smem_desc_mn(slo + 4u * sub_bytes, sub_bytes);
+                for (int kg = 0; kg < ((a.dbg & 2) ? 1 : ksteps); ++kg) {
                     const uint64_t ko = (uint64_t)(kg * 64);
                     if (SPLIT) {
                         umma_tf32(d_tmem, dalo + ko, db + ko, idesc, first ? 0u : 1u);
@@ -441,6 +451,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
                     first = 0;
                 }
                 umma_commit(empty_bar(stage));
+                if (SPLIT) { umma_commit(lo_empty(sl)); sl ^= 1; }
                 if (++stage == a.stages) { stage = 0; phase ^= 1u; }
                 ++done;
                 if (SPLIT && (done % a.seg_chunks) == 0 && done < nchunks) {
@@ -465,34 +476,29 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
         const long long nchunks = c_end - c_begin;
         const int nseg = SPLIT ? (int)((nchunks + a.seg_chunks - 1) / a.seg_chunks) : 1;
         int acc = 0; uint32_t acc_phase = 0;
-        float sum[SPLIT ? 128 : 1];              // SPLIT: n_tile <= 128
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const uint32_t master = tmem_base + 256u + lane_base;            // SPLIT: fp32 master sums (columns 256..383, n_tile <= 128)
         for (int sg = 0; sg < nseg; ++sg) {
             mbar_wait(tfull_bar(acc), acc_phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t taddr = tmem_base + (uint32_t)(acc * 128) + ((uint32_t)(q * 32) << 16);
+            const uint32_t taddr = tmem_base + (uint32_t)(acc * 128) + lane_base;
+            const bool last = sg == nseg - 1;
 #pragma unroll
             for (int cg = 0; cg < (SPLIT ? 8 : 16); ++cg) {
                 const int c = cg * 16;
                 if (c < a.n_tile) {
                     float vals[16];
-                    tmem_ld16(taddr + (uint32_t)c, vals);
-                    if (SPLIT) {
+                    if (SPLIT) tmem_promote16(taddr + (uint32_t)c, master + (uint32_t)c, sg == 0, !last, vals);
+                    else tmem_ld16(taddr + (uint32_t)c, vals);
+                    if (last && store) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) sum[SPLIT ? c + i : 0] = (sg == 0) ? vals[i] : sum[SPLIT ? c + i : 0] + vals[i];
-                    }
-                    if (sg == nseg - 1 && store) {
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            if (k0 + c + g * 4 < a.cin) {
-                                float4 o;
-                                if (SPLIT) o = make_float4(sum[SPLIT ? c + g * 4 : 0], sum[SPLIT ? c + g * 4 + 1 : 0], sum[SPLIT ? c + g * 4 + 2 : 0], sum[SPLIT ? c + g * 4 + 3 : 0]);
-                                else o = make_float4(vals[g * 4], vals[g * 4 + 1], vals[g * 4 + 2], vals[g * 4 + 3]);
-                                *reinterpret_cast<float4*>(out + c + g * 4) = o;
-                            }
-                        }
+                        for (int g = 0; g < 4; ++g)
+                            if (k0 + c + g * 4 < a.cin)
+                                *reinterpret_cast<float4*>(out + c + g * 4) = make_float4(vals[g * 4], vals[g * 4 + 1], vals[g * 4 + 2], vals[g * 4 + 3]);
                     }
                 }
             }
+            if (SPLIT && !last) tmem_st_wait();
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -502,42 +508,38 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
         // operand split (kWgTransformWarps warps): hi = rna_tf32(x) in place, lo = x - hi into the stage's second half.
         // Only the rows TMA wrote are touched (the pad rows stay zero in both halves).
         const int tidx = threadIdx.x - 6 * 32;
-        constexpr uint32_t kStep = kWgTransformWarps * 32u * 16u;
         const uint32_t box_bytes = (uint32_t)a.rows_box * 128u;
         const int nslots = 4 + (int)nsub_b;
         int stage = 0; uint32_t phase = 0;
+        int sl = 0; uint32_t pl = 0;
         for (long long c = c_begin; c < c_end; ++c) {
             mbar_wait(full_bar(stage), phase);
-            const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
-            for (int j = 0; j < nslots; ++j) {
-                if (!((loaded >> j) & 1u)) continue;
-                const uint32_t s0 = sa + (uint32_t)j * sub_bytes;
-                for (uint32_t off = (uint32_t)tidx * 16u; off < box_bytes; off += 2u * kStep) {
-                    const uint32_t off2 = off + kStep;
-                    const bool two = off2 < box_bytes;
-                    const float4 v0 = lds128(s0 + off);
-                    float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (two) v1 = lds128(s0 + off2);
-                    const float4 h0 = make_float4(tf32_rna(v0.x), tf32_rna(v0.y), tf32_rna(v0.z), tf32_rna(v0.w));
-                    const float4 h1 = make_float4(tf32_rna(v1.x), tf32_rna(v1.y), tf32_rna(v1.z), tf32_rna(v1.w));
-                    sts128(s0 + off, h0);
-                    sts128(s0 + raw_bytes + off, make_float4(v0.x - h0.x, v0.y - h0.y, v0.z - h0.z, v0.w - h0.w));
-                    if (two) {
-                        sts128(s0 + off2, h1);
-                        sts128(s0 + raw_bytes + off2, make_float4(v1.x - h1.x, v1.y - h1.y, v1.z - h1.z, v1.w - h1.w));
-                    }
+            mbar_wait(lo_empty(sl), pl ^ 1u);
+            const uint32_t sa = smem_base + (uint32_t)stage * raw_bytes;
+            const uint32_t slo = lo_ring + (uint32_t)sl * raw_bytes;
+            if (!(a.dbg & 1)) {
+                // Slots are `sub_bytes` apart and each holds box_bytes of payload.  When the payload fills the slot (flat layout)
+                // the loaded slots of each operand are contiguous, so they are split as two long runs.
+                if (box_bytes == sub_bytes && !a.pair) {
+                    transform_split4(sa, slo, (uint32_t)__popc(loaded & 15u) * sub_bytes, tidx, kWgTransformWarps * 32);
+                    transform_split4(sa + 4u * sub_bytes, slo + 4u * sub_bytes, (uint32_t)__popc(loaded >> 4) * sub_bytes, tidx, kWgTransformWarps * 32);
+                } else {
+                    for (int j = 0; j < nslots; ++j)
+                        if ((loaded >> j) & 1u)
+                            transform_split4(sa + (uint32_t)j * sub_bytes, slo + (uint32_t)j * sub_bytes, box_bytes, tidx, kWgTransformWarps * 32);
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(lo_bar(stage));
             if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+            sl ^= 1; if (sl == 0) pl ^= 1u;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kCols) : "memory");
     }
 }
 
@@ -589,9 +591,9 @@ static WgPlan plan_wgrad(int nb, int t_in, int t_out, int v, int cin, int cout, 
     a.chunks_total = (long long)nb * a.chunks_per_sample;
     a.seg_chunks = 256 / a.rows_box;
     if (a.seg_chunks < 1) a.seg_chunks = 1;
-    const size_t stage_bytes = (size_t)nsub * a.rpad * 128 * (split ? 2 : 1);
-    int stages = (int)((192 * 1024) / stage_bytes);
-    if (stages > kStages) stages = kStages;
+    const size_t raw_stage = (size_t)nsub * a.rpad * 128;
+    int stages = (int)((200 * 1024 - (split ? 2 * raw_stage : 0)) / raw_stage);     // 3xTF32: two extra slots hold the lo residuals
+    if (stages > kWgStages) stages = kWgStages;
     if (stages < 2) return p;
     a.stages = stages;
     // one resident wave: (tiles x splits) CTAs <= 148 SMs (1 CTA / SM), every CTA streams an equal share of the row chunks
@@ -602,7 +604,7 @@ static WgPlan plan_wgrad(int nb, int t_in, int t_out, int v, int cin, int cout, 
     a.chunks_per_split = (a.chunks_total + splits - 1) / splits;
     splits = (a.chunks_total + a.chunks_per_split - 1) / a.chunks_per_split;
     p.splits = (int)splits;
-    p.smem = (size_t)stages * stage_bytes + 1024 + 256;
+    p.smem = (size_t)(stages + (split ? 2 : 0)) * raw_stage + 1024 + kWgBarBytes;
     p.ok = true;
     return p;
 }
@@ -633,6 +635,8 @@ int agcn_conv_fwd_tc(const float* x, const float* w, const float* bias, float* y
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
     TcArgs a;
+    static const int dbg = getenv("AGCN_CONV_DEBUG") ? atoi(getenv("AGCN_CONV_DEBUG")) : 0;
+    a.dbg = dbg;
     a.y = y; a.bias = bias;
     a.nb = nb; a.t_in = t_in; a.t_out = t_out; a.v = v; a.cin = cin; a.cout = cout;
     a.taps = taps; a.stride = stride; a.pad = pad; a.transposed = transposed; a.accumulate = accumulate;
@@ -708,6 +712,8 @@ int agcn_conv_wgrad_tc(const float* dy, const float* x, float* ws, int* splits_o
     if (!enc) return fail(AGCN_ERR_CUDA, "agcn_conv_wgrad_tc: cuTensorMapEncodeTiled is not available from the driver");
     WgArgs& a = p.a;
     a.ws = ws;
+    static const int dbg = getenv("AGCN_WG_DEBUG") ? atoi(getenv("AGCN_WG_DEBUG")) : 0;
+    a.dbg = dbg;
     CUtensorMap map_dy, map_x;
     auto encode = [&](CUtensorMap* m, const float* ptr, int c, int t, int box1, int box2, int es2) -> CUresult {
         cuuint64_t dims[4]; cuuint64_t strides[3]; cuuint32_t box[4]; cuuint32_t estr[4] = {1, 1, 1, 1};
@@ -731,8 +737,8 @@ int agcn_conv_wgrad_tc(const float* dy, const float* x, float* ws, int* splits_o
     if (r != CUDA_SUCCESS) return fail(AGCN_ERR_CUDA, "agcn_conv_wgrad_tc: cuTensorMapEncodeTiled(x) failed with %d", (int)r);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
         if (e != cudaSuccess) return fail(AGCN_ERR_CUDA, "agcn_conv_wgrad_tc: %s", cudaGetErrorString(e));
         attr_set = true;
     }

@@ -12,14 +12,18 @@
 // re-loading a shifted box per tap this divides the L2->SMEM activation traffic (and, in 3xTF32 mode, the hi/lo
 // operand-split work) of the 9x1 temporal conv by ~3.5.
 //
-// Warp roles (7 warps, +4 in 3xTF32 mode), persistent over tiles, 1 CTA / SM:
-//   warp 0      activation producer: TMA boxes of one K chunk -> A ring (NA stages)
+// Warp roles (7 warps, +8 in 3xTF32 mode), persistent over tiles, 1 CTA / SM:
+//   warp 0      activation producer: TMA boxes of one K chunk -> A ring (NA stages of payload only)
 //   warp 1      MMA issuer: per (K chunk, tap): 4 x tcgen05.mma.kind::tf32 (M128, N=BN, K8), x3 in 3xTF32 mode
 //   warps 2..5  epilogue: tcgen05.ld -> (+bias, +old) -> st.global; in 3xTF32 mode also the fp32 promotion of segments
 //   warp 6      weight producer: one (tap, K chunk) BN x 32 box -> B ring (NB stages)
-//   warps 7..10 (3xTF32) split the A stage once per K chunk: hi = rna_tf32(x) in place, lo = x - hi into the stage's second
-//               half (the weights' hi / lo tensors are precomputed into the caller's workspace and TMA-loaded)
-// TMEM: 2 x 128 fp32 columns (epilogue of tile i overlaps the main loop of tile i+1; 3xTF32 segments ping-pong).
+//   warps 7..14 (3xTF32) split the A stage once per K chunk: hi = rna_tf32(x) in place, lo = x - hi into a 2-deep lo ring
+//               (the weights' hi / lo tensors are precomputed into the caller's workspace and TMA-loaded)
+// The achieved HBM bandwidth of these kernels is (payload bytes in flight per SM) / (~3 us loaded latency) (measured,
+// profiles/r1k): the A ring therefore holds only TMA payload and is as deep as shared memory allows; the lo residuals live
+// in their own two-slot ring between the split warps and the MMA issuer.
+// TMEM: 2 x 128 fp32 accumulator columns (epilogue of tile i overlaps the main loop of tile i+1; 3xTF32 segments
+// ping-pong) + 128 columns of fp32 master sums for the 3xTF32 segment promotion (tmem_promote16).
 #include "tc_common.cuh"
 #include <stdlib.h>
 
@@ -28,10 +32,12 @@ namespace tc2 {
 using namespace agcn::tc;
 
 constexpr int kMaxTaps = 9;
-constexpr int kMaxA = 4, kMaxB = 8;
+constexpr int kMaxA = 8, kMaxB = 8;
+constexpr int kSplitWarps = 8;
 constexpr int kThreads2 = 7 * 32;
-constexpr int kThreads2Split = 11 * 32;
+constexpr int kThreads2Split = (7 + kSplitWarps) * 32;
 constexpr uint32_t kBarBytes = 512;
+constexpr int kTmemCols2 = 512;
 constexpr uint32_t kSmemBudget = 222u * 1024u;
 
 struct Tc2Args {
@@ -39,11 +45,12 @@ struct Tc2Args {
     int nb, t_out, v, cin, cout, stride, transposed, accumulate;
     int tt, bn, n_tiles_n, kchunks, tiles_t, nparity;
     long long total_tiles;
-    int na, nbst;                 // ring depths
+    int dbg;                      // bring-up only (env AGCN_CONV_DEBUG): 1 skip operand split, 2 one MMA per tap, 4 skip global stores
+    int na, nbst, nlo;            // ring depths (nlo: 3xTF32 lo-residual ring, 1 or 2 slots)
     int nblk;                     // activation boxes per stage
     uint32_t blk_rows_bytes;      // bytes TMA writes per box
     uint32_t blk_bytes;           // box slot (1024-aligned, >= the rows the last tap's MMA touches)
-    uint32_t a_stage_bytes;       // nblk * blk_bytes  (3xTF32: the lo copy follows)
+    uint32_t a_stage_bytes;       // nblk * blk_bytes  (3xTF32: the lo residuals go to a separate two-slot ring)
     uint32_t b_stage_bytes;       // bn * 128          (3xTF32: the lo copy follows)
     int tmul;                     // box time coordinate = tmul * jt * tt + blk_t0[par][box]
     int ntap[2];
@@ -57,32 +64,33 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 const __grid_constant__ CUtensorMap map_blo, Tc2Args a) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t a_slot = a.a_stage_bytes * (SPLIT ? 2u : 1u);
+    const uint32_t a_slot = a.a_stage_bytes;
     const uint32_t b_slot = a.b_stage_bytes * (SPLIT ? 2u : 1u);
-    const uint32_t b_ring = smem_base + (uint32_t)a.na * a_slot;
+    const uint32_t lo_ring = smem_base + (uint32_t)a.na * a_slot;                       // SPLIT: two slots of a_stage_bytes
+    const uint32_t b_ring = lo_ring + (SPLIT ? (uint32_t)a.nlo * a_slot : 0u);
     const uint32_t bar_base = b_ring + (uint32_t)a.nbst * b_slot;
     auto a_full = [&](int s) { return bar_base + 8u * s; };
     auto a_empty = [&](int s) { return bar_base + 8u * (kMaxA + s); };
     auto a_lo = [&](int s) { return bar_base + 8u * (2 * kMaxA + s); };
     auto b_full = [&](int s) { return bar_base + 8u * (3 * kMaxA + s); };
     auto b_empty = [&](int s) { return bar_base + 8u * (3 * kMaxA + kMaxB + s); };
-    auto b_lo = [&](int s) { return bar_base + 8u * (3 * kMaxA + 2 * kMaxB + s); };
-    auto tfull_bar = [&](int s) { return bar_base + 8u * (3 * kMaxA + 3 * kMaxB + s); };
-    auto tempty_bar = [&](int s) { return bar_base + 8u * (3 * kMaxA + 3 * kMaxB + 2 + s); };
-    const uint32_t tmem_slot = bar_base + 8u * (3 * kMaxA + 3 * kMaxB + 4);
+    auto lo_empty = [&](int s) { return bar_base + 8u * (3 * kMaxA + 2 * kMaxB + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (3 * kMaxA + 2 * kMaxB + 2 + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (3 * kMaxA + 2 * kMaxB + 4 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (3 * kMaxA + 2 * kMaxB + 6);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
-        for (int s = 0; s < kMaxA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); mbar_init(a_lo(s), 4); }
-        for (int s = 0; s < kMaxB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); mbar_init(b_lo(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+        for (int s = 0; s < kMaxA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); mbar_init(a_lo(s), kSplitWarps); }
+        for (int s = 0; s < kMaxB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(lo_empty(s), 1); mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(kTmemCols) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(kTmemCols2) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -139,6 +147,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             int sa = 0; uint32_t pa = 0;
             int sb = 0; uint32_t pb = 0;
             int acc = 0; uint32_t acc_phase = 0;
+            int sl = 0;
             const uint32_t row_bytes_v = (uint32_t)a.v * 128u;
             for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
                 const int par = (int)((tile / a.n_tiles_n / a.tiles_t) % a.nparity);
@@ -153,15 +162,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     mbar_wait(a_full(sa), pa);
                     if (SPLIT) mbar_wait(a_lo(sa), pa);
                     const uint32_t abase = smem_base + (uint32_t)sa * a_slot;
+                    const uint32_t lobase = lo_ring + (uint32_t)sl * a_slot;
                     for (int i = 0; i < ntap; ++i) {
                         mbar_wait(b_full(sb), pb);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t aaddr = abase + (uint32_t)a.tap_blk[par][i] * a.blk_bytes + (uint32_t)a.tap_off[par][i] * row_bytes_v;
+                        const uint32_t aoff = (uint32_t)a.tap_blk[par][i] * a.blk_bytes + (uint32_t)a.tap_off[par][i] * row_bytes_v;
+                        const uint32_t aaddr = abase + aoff;
                         const uint32_t baddr = b_ring + (uint32_t)sb * b_slot;
                         const uint64_t da = make_smem_desc(aaddr), db = make_smem_desc(baddr);
-                        const uint64_t dalo = make_smem_desc(aaddr + a.a_stage_bytes), dblo = make_smem_desc(baddr + a.b_stage_bytes);
+                        const uint64_t dalo = make_smem_desc(lobase + aoff), dblo = make_smem_desc(baddr + a.b_stage_bytes);
 #pragma unroll
                         for (int k = 0; k < kKChunk / 8; ++k) {
+                            if ((a.dbg & 2) && k) break;
                             const uint64_t ko = (uint64_t)(k * 2);
                             if (SPLIT) {
                                 umma_tf32(d_tmem, dalo + ko, db + ko, idesc, first ? 0u : 1u);
@@ -186,6 +198,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         }
                     }
                     umma_commit(a_empty(sa));
+                    if (SPLIT) { umma_commit(lo_empty(sl)); if (++sl == a.nlo) sl = 0; }
                     if (++sa == a.na) { sa = 0; pa ^= 1u; }
                 }
                 umma_commit(tfull_bar(acc));
@@ -210,29 +223,26 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             float* yrow = a.y + (((long long)n * a.t_out + to) * a.v + vv) * a.cout + nt * a.bn;
             const int iters = a.ntap[par] * a.kchunks;
             const int nseg = SPLIT ? (iters + kSegment - 1) / kSegment : 1;
-            float sum[SPLIT ? 128 : 1];
+            const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+            const uint32_t master = tmem_base + 256u + lane_base;          // 3xTF32: fp32 master sums (columns 256..383)
             for (int sg = 0; sg < nseg; ++sg) {
                 mbar_wait(tfull_bar(acc), acc_phase);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t taddr = tmem_base + (uint32_t)(acc * 128) + ((uint32_t)(q * 32) << 16);
+                const uint32_t taddr = tmem_base + (uint32_t)(acc * 128) + lane_base;
+                const bool last = sg == nseg - 1;
 #pragma unroll
                 for (int cg = 0; cg < 8; ++cg) {
                     const int c = cg * 16;
                     if (c < a.bn) {
                         float vals[16];
-                        tmem_ld16(taddr + (uint32_t)c, vals);
-                        if (SPLIT) {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) sum[SPLIT ? c + i : 0] = (sg == 0) ? vals[i] : sum[SPLIT ? c + i : 0] + vals[i];
-                        }
-                        if (sg == nseg - 1 && row_ok) {
+                        if (SPLIT) tmem_promote16(taddr + (uint32_t)c, master + (uint32_t)c, sg == 0, !last, vals);
+                        else tmem_ld16(taddr + (uint32_t)c, vals);
+                        if (last && row_ok && !(a.dbg & 4)) {
                             const int col = nt * a.bn + c;
 #pragma unroll
                             for (int g = 0; g < 4; ++g) {
                                 if (col + g * 4 >= a.cout) break;
-                                float4 o;
-                                if (SPLIT) o = make_float4(sum[SPLIT ? c + g * 4 : 0], sum[SPLIT ? c + g * 4 + 1 : 0], sum[SPLIT ? c + g * 4 + 2 : 0], sum[SPLIT ? c + g * 4 + 3 : 0]);
-                                else o = make_float4(vals[g * 4], vals[g * 4 + 1], vals[g * 4 + 2], vals[g * 4 + 3]);
+                                float4 o = make_float4(vals[g * 4], vals[g * 4 + 1], vals[g * 4 + 2], vals[g * 4 + 3]);
                                 if (a.bias) {
                                     const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + col + g * 4));
                                     o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
@@ -247,6 +257,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         }
                     }
                 }
+                if (SPLIT && !last) tmem_st_wait();
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -254,43 +265,30 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             }
         }
     } else if (SPLIT) {
-        // ===================================================== operand split of the activation stage (128 threads)
-        const int tid128 = threadIdx.x - 7 * 32;
+        // ===================================================== operand split of the activation stage (kSplitWarps warps)
+        const int tids = threadIdx.x - 7 * 32;
         int sa = 0; uint32_t pa = 0;
+        int sl = 0; uint32_t pl = 0;
         for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
             for (int kc = 0; kc < a.kchunks; ++kc) {
                 mbar_wait(a_full(sa), pa);
+                mbar_wait(lo_empty(sl), pl ^ 1u);
                 const uint32_t src = smem_base + (uint32_t)sa * a_slot;
-                for (int b = 0; b < a.nblk; ++b) {
-                    const uint32_t s0 = src + (uint32_t)b * a.blk_bytes;
-                    // two 16-byte quads per thread per step: both loads are issued before the dependent converts
-                    for (uint32_t off = (uint32_t)tid128 * 16u; off < a.blk_rows_bytes; off += 256u * 16u) {
-                        const uint32_t off2 = off + 128u * 16u;
-                        const bool two = off2 < a.blk_rows_bytes;
-                        const float4 v0 = lds128(s0 + off);
-                        float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (two) v1 = lds128(s0 + off2);
-                        const float4 h0 = make_float4(tf32_rna(v0.x), tf32_rna(v0.y), tf32_rna(v0.z), tf32_rna(v0.w));
-                        const float4 h1 = make_float4(tf32_rna(v1.x), tf32_rna(v1.y), tf32_rna(v1.z), tf32_rna(v1.w));
-                        sts128(s0 + off, h0);
-                        sts128(s0 + a.a_stage_bytes + off, make_float4(v0.x - h0.x, v0.y - h0.y, v0.z - h0.z, v0.w - h0.w));
-                        if (two) {
-                            sts128(s0 + off2, h1);
-                            sts128(s0 + a.a_stage_bytes + off2, make_float4(v1.x - h1.x, v1.y - h1.y, v1.z - h1.z, v1.w - h1.w));
-                        }
-                    }
-                }
+                const uint32_t dst = lo_ring + (uint32_t)sl * a_slot;
+                for (int b = 0; b < ((a.dbg & 1) ? 0 : a.nblk); ++b)
+                    transform_split4(src + (uint32_t)b * a.blk_bytes, dst + (uint32_t)b * a.blk_bytes, a.blk_rows_bytes, tids, kSplitWarps * 32);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(a_lo(sa));
                 if (++sa == a.na) { sa = 0; pa ^= 1u; }
+                if (++sl == a.nlo) { sl = 0; pl ^= 1u; }
             }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols2) : "memory");
     }
 }
 
@@ -307,7 +305,9 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
     using namespace agcn::tc;
     using namespace agcn::tc2;
     static const bool disabled = getenv("AGCN_TC_V1") != nullptr;
-    if (disabled) return AGCN_ERR_UNSUPPORTED;
+    static const bool no_1x1 = getenv("AGCN_TC2_NO1X1") != nullptr;
+    static const int dbg = getenv("AGCN_CONV_DEBUG") ? atoi(getenv("AGCN_CONV_DEBUG")) : 0;
+    if (disabled || (no_1x1 && taps == 1)) return AGCN_ERR_UNSUPPORTED;
     if (cin % 4 || cout % 16 || v > 128 || stride > 2 || taps > kMaxTaps) return AGCN_ERR_UNSUPPORTED;
     if (transposed && stride > 1 && taps < stride) return AGCN_ERR_UNSUPPORTED;
     if (!aligned16(x) || !aligned16(w) || !aligned16(y) || (bias && !aligned16(bias))) return AGCN_ERR_UNSUPPORTED;
@@ -324,6 +324,7 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
     Tc2Args a;
     a.y = y; a.bias = bias;
     a.nb = nb; a.t_out = t_out; a.v = v; a.cin = cin; a.cout = cout; a.stride = stride; a.transposed = transposed; a.accumulate = accumulate;
+    a.dbg = dbg;
     a.tt = 128 / v;
     a.bn = bn;
     a.n_tiles_n = cout / bn;
@@ -380,23 +381,32 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
     a.blk_bytes = (need + 1023u) & ~1023u;
     a.a_stage_bytes = (uint32_t)a.nblk * a.blk_bytes;
     a.b_stage_bytes = (uint32_t)bn * 128u;
-    const uint32_t a_slot = a.a_stage_bytes * (split ? 2u : 1u), b_slot = a.b_stage_bytes * (split ? 2u : 1u);
+    const uint32_t a_slot = a.a_stage_bytes, b_slot = a.b_stage_bytes * (split ? 2u : 1u);
     const uint32_t budget = kSmemBudget - 1024u - kBarBytes;
-    a.na = 0; a.nbst = 0;
-    for (int min_b = 3; min_b >= 2 && a.na == 0; --min_b)
-        for (int na = kMaxA; na >= 1; --na) {
-            if ((uint64_t)na * a_slot + (uint64_t)min_b * b_slot > budget) continue;
-            int nbst = (int)((budget - (uint32_t)na * a_slot) / b_slot);
-            if (nbst > kMaxB) nbst = kMaxB;
-            a.na = na; a.nbst = nbst;
-            break;
+    // Ring depths.  Weights: 3 slots (2 when tight).  3xTF32 lo residuals: 2 slots, 1 when two would leave a single
+    // activation stage.  Everything else goes to the activation ring: payload bytes in flight set the achieved bandwidth.
+    a.na = 0; a.nbst = 0; a.nlo = split ? 2 : 0;
+    auto fit = [&](int nlo, int min_b) -> int {
+        const uint64_t fixed = (uint64_t)nlo * a_slot + (uint64_t)min_b * b_slot;
+        if (fixed + a_slot > budget) return 0;
+        int na = (int)((budget - fixed) / a_slot);
+        return na > kMaxA ? kMaxA : na;
+    };
+    int best_na = 0, best_lo = a.nlo, best_b = 3;
+    for (int nlo = a.nlo; nlo >= (split ? 1 : 0) && best_na < 2; --nlo)
+        for (int min_b = 3; min_b >= 2 && best_na < 2; --min_b) {
+            const int na = fit(nlo, min_b);
+            if (na > best_na) { best_na = na; best_lo = nlo; best_b = min_b; }
         }
-    if (a.na == 0) return AGCN_ERR_UNSUPPORTED;
-    // Measured on B200 (tools/bench_stage.py, profiles/r1h_*): the halo-resident tile wins for the multi-tap convs whenever two
-    // activation stages fit; with a single stage (3xTF32 at BN = 128) or for 1x1 convs the per-tap kernel of conv_tc.cu is
-    // as fast or faster, so those shapes stay there.
-    if (taps == 1 || a.na < 2) return AGCN_ERR_UNSUPPORTED;
-    const size_t smem = (size_t)a.na * a_slot + (size_t)a.nbst * b_slot + 1024 + kBarBytes;
+    if (best_na == 0) return AGCN_ERR_UNSUPPORTED;
+    a.na = best_na; a.nlo = best_lo;
+    {
+        int nbst = (int)((budget - (uint64_t)a.nlo * a_slot - (uint64_t)a.na * a_slot) / b_slot);
+        if (nbst > kMaxB) nbst = kMaxB;
+        if (nbst < best_b) nbst = best_b;
+        a.nbst = nbst;
+    }
+    const size_t smem = (size_t)(a.na + a.nlo) * a_slot + (size_t)a.nbst * b_slot + 1024 + kBarBytes;
 
     CUtensorMap map_a, map_b, map_blo;
     {

@@ -255,9 +255,13 @@ struct MixArgs {
     int nb, t, v, ldin, ldout, width, mode, accumulate, tt;
 };
 
+// CV = 1: scalar channels; CV = 4: one 16-byte channel quad per item; CV = 8: two quads W/2 channels apart per item
+// (the lanes of a warp then read contiguous quads -> conflict-free LDS.128, and each matrix row feeds 40 FMAs).
 template <int CV>
 __global__ void __launch_bounds__(256) joint_mix_kernel(MixArgs p) {
     extern __shared__ __align__(16) float smem[];
+    constexpr int NQ = CV == 8 ? 2 : 1;             // quads per item
+    constexpr int CE = CV == 1 ? 1 : 4;             // channels per quad
     const int V = p.v, W = p.width;
     const int nblk = (V + 4) / 5;
     const int mld = nblk * 8;                       // padded row of a staged matrix (5 of every 8 used)
@@ -292,7 +296,7 @@ __global__ void __launch_bounds__(256) joint_mix_kernel(MixArgs p) {
     {
         const float* src = p.in + ((long long)n * p.t + t0) * V * p.ldin;
         const int total = tn * V * p.ldin;
-        if (CV == 4) {
+        if (CV >= 4) {
             const float4* s4 = reinterpret_cast<const float4*>(src);
             float4* d4 = reinterpret_cast<float4*>(in_s);
             for (int idx = tid; idx < total / 4; idx += 256) d4[idx] = __ldg(s4 + idx);
@@ -303,19 +307,22 @@ __global__ void __launch_bounds__(256) joint_mix_kernel(MixArgs p) {
     __syncthreads();
 
     const int ogroups = (p.mode == AGCN_MIX_AGG_FWD) ? 3 : (p.mode == AGCN_MIX_AGG_BWD ? 1 : 6);
-    const int cq = W / CV;                          // channel vectors per group
+    const int cq = W / (CE * NQ);                   // items along the channel axis of one group
+    const int qstride = NQ == 2 ? W / 2 : 0;        // channel distance between the two quads of an item
     const int items = tn * ogroups * nblk * cq;
     for (int item = tid; item < items; item += 256) {
-        const int c = (item % cq) * CV;
+        const int c = (item % cq) * CE;
         int r = item / cq;
         const int jb = r % nblk; r /= nblk;
         const int og = r % ogroups;
         const int tl = r / ogroups;
-        float acc[5][CV];
+        float acc[NQ][5][CE];
 #pragma unroll
-        for (int j = 0; j < 5; ++j)
+        for (int q = 0; q < NQ; ++q)
 #pragma unroll
-            for (int e = 0; e < CV; ++e) acc[j][e] = 0.f;
+            for (int j = 0; j < 5; ++j)
+#pragma unroll
+                for (int e = 0; e < CE; ++e) acc[q][j][e] = 0.f;
         const int nterms = (p.mode == AGCN_MIX_AGG_BWD) ? 3 : 1;
         for (int term = 0; term < nterms; ++term) {
             int ig, slot;
@@ -324,22 +331,27 @@ __global__ void __launch_bounds__(256) joint_mix_kernel(MixArgs p) {
             else { ig = og ^ 1; slot = og; }
             const float* xin = in_s + (size_t)tl * V * p.ldin + ig * W + c;
             const float* m = Ms + (size_t)slot * V * mld + jb * 8;
+#pragma unroll 5
             for (int i = 0; i < V; ++i) {
-                float xv[CV];
-                if (CV == 4) {
-                    float4 q = *reinterpret_cast<const float4*>(xin + (size_t)i * p.ldin);
-                    xv[0] = q.x; xv[1] = q.y; xv[2] = q.z; xv[3] = q.w;
-                } else {
+                float xv[NQ][CE];
 #pragma unroll
-                    for (int e = 0; e < CV; ++e) xv[e] = xin[(size_t)i * p.ldin + e];
+                for (int q = 0; q < NQ; ++q) {
+                    if (CE == 4) {
+                        const float4 v4 = *reinterpret_cast<const float4*>(xin + (size_t)i * p.ldin + q * qstride);
+                        xv[q][0] = v4.x; xv[q][1 % CE] = v4.y; xv[q][2 % CE] = v4.z; xv[q][3 % CE] = v4.w;
+                    } else {
+                        xv[q][0] = xin[(size_t)i * p.ldin];
+                    }
                 }
                 const float4 m0 = *reinterpret_cast<const float4*>(m + (size_t)i * mld);
                 const float m4 = m[(size_t)i * mld + 4];
                 const float mv[5] = {m0.x, m0.y, m0.z, m0.w, m4};
 #pragma unroll
-                for (int j = 0; j < 5; ++j)
+                for (int q = 0; q < NQ; ++q)
 #pragma unroll
-                    for (int e = 0; e < CV; ++e) acc[j][e] = fmaf(xv[e], mv[j], acc[j][e]);
+                    for (int j = 0; j < 5; ++j)
+#pragma unroll
+                        for (int e = 0; e < CE; ++e) acc[q][j][e] = fmaf(xv[q][e], mv[j], acc[q][j][e]);
             }
         }
         const int t = t0 + tl;
@@ -348,16 +360,19 @@ __global__ void __launch_bounds__(256) joint_mix_kernel(MixArgs p) {
             const int jj = jb * 5 + j;
             if (jj >= V) continue;
             float* o = p.out + (((long long)n * p.t + t) * V + jj) * p.ldout + og * W + c;
-            if (CV == 4) {
-                float4 q = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
-                if (p.accumulate) {
-                    float4 old = *reinterpret_cast<const float4*>(o);
-                    q.x += old.x; q.y += old.y; q.z += old.z; q.w += old.w;
-                }
-                *reinterpret_cast<float4*>(o) = q;
-            } else {
 #pragma unroll
-                for (int e = 0; e < CV; ++e) o[e] = p.accumulate ? o[e] + acc[j][e] : acc[j][e];
+            for (int q = 0; q < NQ; ++q) {
+                if (CE == 4) {
+                    float4 v4 = make_float4(acc[q][j][0], acc[q][j][1 % CE], acc[q][j][2 % CE], acc[q][j][3 % CE]);
+                    float4* dst = reinterpret_cast<float4*>(o + q * qstride);
+                    if (p.accumulate) {
+                        const float4 old = *dst;
+                        v4.x += old.x; v4.y += old.y; v4.z += old.z; v4.w += old.w;
+                    }
+                    *dst = v4;
+                } else {
+                    o[0] = p.accumulate ? o[0] + acc[q][j][0] : acc[q][j][0];
+                }
             }
         }
     }
@@ -452,7 +467,11 @@ extern "C" AGCN_API int agcn_joint_mix(const float* in, const float* mats, float
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bool vec = (width % 4 == 0) && aligned16(in) && aligned16(out);
     cudaError_t e;
-    if (vec) {
+    if (vec && width % 8 == 0) {
+        e = cudaFuncSetAttribute(joint_mix_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return fail(AGCN_ERR_CUDA, "agcn_joint_mix: %s", cudaGetErrorString(e));
+        joint_mix_kernel<8><<<nb * tiles_t, 256, smem, s>>>(p);
+    } else if (vec) {
         e = cudaFuncSetAttribute(joint_mix_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return fail(AGCN_ERR_CUDA, "agcn_joint_mix: %s", cudaGetErrorString(e));
         joint_mix_kernel<4><<<nb * tiles_t, 256, smem, s>>>(p);

@@ -89,6 +89,61 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// raw (no wait) 16-column TMEM load / store; the caller batches them and issues one wait
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                   "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+                   "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+                   "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// 3xTF32 accumulator promotion inside TMEM.  The tensor core's fp32 accumulate truncates, so a long K reduction is cut into
+// short segments; each finished segment P (16 columns at `part`) is added in fp32 registers (round to nearest) to the master
+// sum S (16 columns at `master`) which also lives in TMEM:  first segment S = P, later S += P.  Returns the new S in v.
+__device__ __forceinline__ void tmem_promote16(uint32_t part, uint32_t master, bool first, bool write_back, float* v) {
+    uint32_t p[16], s[16];
+    tmem_ld16_nowait(part, p);
+    if (!first) tmem_ld16_nowait(master, s);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = first ? __uint_as_float(p[i]) : __uint_as_float(s[i]) + __uint_as_float(p[i]);
+    if (write_back) tmem_st16(master, v);
+}
+
+// Operand split of `bytes` bytes (multiple of 16) at src for the 3xTF32 path: hi = rna_tf32(x) overwrites src in place,
+// lo = x - hi (exact) goes to dst at the same offsets (any swizzle is preserved).  `nthreads` threads cooperate; every
+// thread keeps four 16-byte loads in flight before the dependent converts and stores.
+__device__ __forceinline__ void transform_split4(uint32_t src, uint32_t dst, uint32_t bytes, int tid, int nthreads) {
+    const uint32_t step = (uint32_t)nthreads * 16u;
+    for (uint32_t off = (uint32_t)tid * 16u; off < bytes; off += 4u * step) {
+        float4 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t o = off + (uint32_t)i * step;
+            v[i] = (o < bytes) ? lds128(src + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t o = off + (uint32_t)i * step;
+            if (o < bytes) {
+                const float4 hi = make_float4(tf32_rna(v[i].x), tf32_rna(v[i].y), tf32_rna(v[i].z), tf32_rna(v[i].w));
+                sts128(src + o, hi);
+                sts128(dst + o, make_float4(v[i].x - hi.x, v[i].y - hi.y, v[i].z - hi.z, v[i].w - hi.w));
+            }
+        }
+    }
+}
+
 // K-major, 128-byte swizzle shared-memory matrix descriptor (rows at 128 B pitch, 8-row atoms at 1024 B pitch)
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     uint64_t d = 0;
