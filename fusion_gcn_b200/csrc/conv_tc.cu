@@ -508,7 +508,6 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
         // operand split (kWgTransformWarps warps): hi = rna_tf32(x) in place, lo = x - hi into the stage's second half.
         // Only the rows TMA wrote are touched (the pad rows stay zero in both halves).
         const int tidx = threadIdx.x - 6 * 32;
-        const uint32_t box_bytes = (uint32_t)a.rows_box * 128u;
         const int nslots = 4 + (int)nsub_b;
         int stage = 0; uint32_t phase = 0;
         int sl = 0; uint32_t pl = 0;
@@ -520,13 +519,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
             if (!(a.dbg & 1)) {
                 // Slots are `sub_bytes` apart and each holds box_bytes of payload.  When the payload fills the slot (flat layout)
                 // the loaded slots of each operand are contiguous, so they are split as two long runs.
-                if (box_bytes == sub_bytes && !a.pair) {
-                    transform_split4(sa, slo, (uint32_t)__popc(loaded & 15u) * sub_bytes, tidx, kWgTransformWarps * 32);
+                // Slots are `sub_bytes` apart; rows a TMA box does not write are zero in the raw stage and split to (0, 0), so whole
+                // slots are processed: the loaded slots of each operand form one contiguous run whenever they are a prefix.
+                const uint32_t am = loaded & 15u, na_l = (uint32_t)__popc(am);
+                if (am == (1u << na_l) - 1u) {
+                    transform_split4(sa, slo, na_l * sub_bytes, tidx, kWgTransformWarps * 32);
                     transform_split4(sa + 4u * sub_bytes, slo + 4u * sub_bytes, (uint32_t)__popc(loaded >> 4) * sub_bytes, tidx, kWgTransformWarps * 32);
                 } else {
                     for (int j = 0; j < nslots; ++j)
                         if ((loaded >> j) & 1u)
-                            transform_split4(sa + (uint32_t)j * sub_bytes, slo + (uint32_t)j * sub_bytes, box_bytes, tidx, kWgTransformWarps * 32);
+                            transform_split4(sa + (uint32_t)j * sub_bytes, slo + (uint32_t)j * sub_bytes, sub_bytes, tidx, kWgTransformWarps * 32);
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

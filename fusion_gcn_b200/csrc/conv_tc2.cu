@@ -38,6 +38,8 @@ constexpr int kThreads2 = 7 * 32;
 constexpr int kThreads2Split = (7 + kSplitWarps) * 32;
 constexpr uint32_t kBarBytes = 512;
 constexpr int kTmemCols2 = 512;
+constexpr uint32_t kStagePitch = 144;                        // bytes per staged output row: 32 floats + 16 bytes (conflict-free 16-byte accesses)
+constexpr uint32_t kStageBytes = 4u * 32u * kStagePitch;     // four epilogue warps
 constexpr uint32_t kSmemBudget = 222u * 1024u;
 
 struct Tc2Args {
@@ -45,6 +47,8 @@ struct Tc2Args {
     int nb, t_out, v, cin, cout, stride, transposed, accumulate;
     int tt, bn, n_tiles_n, kchunks, tiles_t, nparity;
     long long total_tiles;
+    int seg_iters;                // 3xTF32: (tap, K chunk) iterations per accumulator segment
+    int acc_stride;               // TMEM columns between the two accumulator buffers (128, or 256 for tiles wider than 128)
     int dbg;                      // bring-up only (env AGCN_CONV_DEBUG): 1 skip operand split, 2 one MMA per tap, 4 skip global stores
     int na, nbst, nlo;            // ring depths (nlo: 3xTF32 lo-residual ring, 1 or 2 slots)
     int nblk;                     // activation boxes per stage
@@ -78,6 +82,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     auto tfull_bar = [&](int s) { return bar_base + 8u * (3 * kMaxA + 2 * kMaxB + 2 + s); };
     auto tempty_bar = [&](int s) { return bar_base + 8u * (3 * kMaxA + 2 * kMaxB + 4 + s); };
     const uint32_t tmem_slot = bar_base + 8u * (3 * kMaxA + 2 * kMaxB + 6);
+    const uint32_t stage_base = bar_base + kBarBytes + (uint32_t)((threadIdx.x >> 5) & 3) * (32u * kStagePitch);   // epilogue staging tile of this warp's lane quarter
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -156,7 +161,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 int it = 0;
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
+                uint32_t d_tmem = tmem_base + (uint32_t)(acc * a.acc_stride);
                 uint32_t first = 1;
                 for (int kc = 0; kc < a.kchunks; ++kc) {
                     mbar_wait(a_full(sa), pa);
@@ -187,13 +192,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         umma_commit(b_empty(sb));
                         if (++sb == a.nbst) { sb = 0; pb ^= 1u; }
                         ++it;
-                        if (SPLIT && (it % kSegment) == 0 && it < iters) {
+                        if (SPLIT && (it % a.seg_iters) == 0 && it < iters) {
                             // promote the partial accumulator to the epilogue's fp32 registers, continue in the other buffer
                             umma_commit(tfull_bar(acc));
                             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
                             mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
                             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                            d_tmem = tmem_base + (uint32_t)(acc * 128);
+                            d_tmem = tmem_base + (uint32_t)(acc * a.acc_stride);
                             first = 1;
                         }
                     }
@@ -220,40 +225,60 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const int j = jt * a.tt + tl;
             const int to = a.transposed ? a.stride * j + par : j;
             const bool row_ok = (tl < a.tt) && (to < a.t_out);
-            float* yrow = a.y + (((long long)n * a.t_out + to) * a.v + vv) * a.cout + nt * a.bn;
+            // element offset of this lane's output row (first column of the tile), -1 for rows outside the tensor
+            const long long my_off = row_ok ? (((long long)n * a.t_out + to) * a.v + vv) * a.cout + (long long)nt * a.bn : -1;
             const int iters = a.ntap[par] * a.kchunks;
-            const int nseg = SPLIT ? (iters + kSegment - 1) / kSegment : 1;
+            const int nseg = SPLIT ? (iters + a.seg_iters - 1) / a.seg_iters : 1;
             const uint32_t lane_base = (uint32_t)(q * 32) << 16;
             const uint32_t master = tmem_base + 256u + lane_base;          // 3xTF32: fp32 master sums (columns 256..383)
             for (int sg = 0; sg < nseg; ++sg) {
                 mbar_wait(tfull_bar(acc), acc_phase);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t taddr = tmem_base + (uint32_t)(acc * 128) + lane_base;
+                const uint32_t taddr = tmem_base + (uint32_t)(acc * a.acc_stride) + lane_base;
                 const bool last = sg == nseg - 1;
+                // 32 columns at a time: TMEM (lane = row, 32 consecutive columns per thread) -> per-warp staging tile in shared
+                // memory (144-byte row pitch) -> read back with 8 lanes per row, so that every st.global instruction writes four
+                // full 128-byte row segments.  Writing the TMEM fragment directly (one 16-byte piece of 32 different rows per
+                // instruction) held the 1x1 convolutions at a third of the HBM rate (measured, profiles/r1m).
 #pragma unroll
-                for (int cg = 0; cg < 8; ++cg) {
-                    const int c = cg * 16;
-                    if (c < a.bn) {
-                        float vals[16];
-                        if (SPLIT) tmem_promote16(taddr + (uint32_t)c, master + (uint32_t)c, sg == 0, !last, vals);
-                        else tmem_ld16(taddr + (uint32_t)c, vals);
-                        if (last && row_ok && !(a.dbg & 4)) {
-                            const int col = nt * a.bn + c;
+                for (int cc = 0; cc < 8; ++cc) {
+                    const int c0 = cc * 32;
+                    if (c0 < a.bn) {
+                        const bool wide = c0 + 16 < a.bn;                  // bn is a multiple of 16: the last chunk may be 16 wide
+                        float vals[32];
+                        if (SPLIT) {
+                            tmem_promote16(taddr + (uint32_t)c0, master + (uint32_t)c0, sg == 0, !last, vals);
+                            if (wide) tmem_promote16(taddr + (uint32_t)c0 + 16u, master + (uint32_t)c0 + 16u, sg == 0, !last, vals + 16);
+                        } else {
+                            tmem_ld16(taddr + (uint32_t)c0, vals);
+                            if (wide) tmem_ld16(taddr + (uint32_t)c0 + 16u, vals + 16);
+                        }
+                        if (last && !(a.dbg & 4)) {
+                            const uint32_t srow = stage_base + (uint32_t)lane * kStagePitch;
 #pragma unroll
-                            for (int g = 0; g < 4; ++g) {
-                                if (col + g * 4 >= a.cout) break;
-                                float4 o = make_float4(vals[g * 4], vals[g * 4 + 1], vals[g * 4 + 2], vals[g * 4 + 3]);
-                                if (a.bias) {
-                                    const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + col + g * 4));
-                                    o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                            for (int g = 0; g < 8; ++g)
+                                if (g < 4 || wide) sts128(srow + (uint32_t)g * 16u, make_float4(vals[g * 4], vals[g * 4 + 1], vals[g * 4 + 2], vals[g * 4 + 3]));
+                            __syncwarp();
+                            const int cq = lane & 7;                       // 16-byte column piece handled by this lane
+                            const bool col_ok = cq < 4 || wide;
+                            float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (a.bias && col_ok) bq = __ldg(reinterpret_cast<const float4*>(a.bias + nt * a.bn + c0 + cq * 4));
+#pragma unroll
+                            for (int rr = 0; rr < 8; ++rr) {
+                                const int src_lane = rr * 4 + (lane >> 3);
+                                const long long off = __shfl_sync(0xffffffffu, my_off, src_lane);
+                                if (off >= 0 && col_ok) {
+                                    float4 o = lds128(stage_base + (uint32_t)src_lane * kStagePitch + (uint32_t)cq * 16u);
+                                    o.x += bq.x; o.y += bq.y; o.z += bq.z; o.w += bq.w;
+                                    float4* p = reinterpret_cast<float4*>(a.y + off + c0 + cq * 4);
+                                    if (a.accumulate) {
+                                        const float4 old = *p;
+                                        o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                                    }
+                                    *p = o;
                                 }
-                                float4* p = reinterpret_cast<float4*>(yrow + c + g * 4);
-                                if (a.accumulate) {
-                                    const float4 old = *p;
-                                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-                                }
-                                *p = o;
                             }
+                            __syncwarp();
                         }
                     }
                 }
@@ -312,12 +337,16 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
     if (transposed && stride > 1 && taps < stride) return AGCN_ERR_UNSUPPORTED;
     if (!aligned16(x) || !aligned16(w) || !aligned16(y) || (bias && !aligned16(bias))) return AGCN_ERR_UNSUPPORTED;
     if (split && (w_split == nullptr || !aligned16(w_split) || ((long long)cout * taps * cin) % 4)) return AGCN_ERR_UNSUPPORTED;
-    int bn;
-    if (cout % 128 == 0) bn = 128;
-    else if (cout % 96 == 0) bn = 96;
-    else if (cout % 64 == 0) bn = 64;
-    else if (cout <= 128) bn = cout;
-    else return AGCN_ERR_UNSUPPORTED;
+    // Output-channel tile.  A 3xTF32 tile whose K reduction needs more than one accumulator segment keeps fp32 master sums
+    // in TMEM columns 256..383, so it is at most 128 wide; single-segment tiles (1x1 convs with cin <= 256) and the TF32
+    // mode use up to 256 columns per accumulator buffer, which avoids re-loading (and re-splitting) the activations per tile.
+    const int kiters = taps * ((cin + kKChunk - 1) / kKChunk);
+    const bool one_segment = !split || kiters <= 8;
+    const int bn_cap = one_segment ? 256 : 128;
+    int bn = 0;
+    for (int cand = bn_cap; cand >= 16; cand -= 16)
+        if (cout % cand == 0) { bn = cand; break; }
+    if (bn == 0 || (bn < 64 && cout > 128)) return AGCN_ERR_UNSUPPORTED;
     EncodeTiledFn enc = encode_fn();
     if (!enc) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc2: cuTensorMapEncodeTiled is not available from the driver");
 
@@ -325,6 +354,8 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
     a.y = y; a.bias = bias;
     a.nb = nb; a.t_out = t_out; a.v = v; a.cin = cin; a.cout = cout; a.stride = stride; a.transposed = transposed; a.accumulate = accumulate;
     a.dbg = dbg;
+    a.seg_iters = (split && kiters <= 8) ? 8 : kSegment;
+    a.acc_stride = bn > 128 ? 256 : 128;
     a.tt = 128 / v;
     a.bn = bn;
     a.n_tiles_n = cout / bn;
@@ -382,7 +413,7 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
     a.a_stage_bytes = (uint32_t)a.nblk * a.blk_bytes;
     a.b_stage_bytes = (uint32_t)bn * 128u;
     const uint32_t a_slot = a.a_stage_bytes, b_slot = a.b_stage_bytes * (split ? 2u : 1u);
-    const uint32_t budget = kSmemBudget - 1024u - kBarBytes;
+    const uint32_t budget = kSmemBudget - 1024u - kBarBytes - kStageBytes;
     // Ring depths.  Weights: 3 slots (2 when tight).  3xTF32 lo residuals: 2 slots, 1 when two would leave a single
     // activation stage.  Everything else goes to the activation ring: payload bytes in flight set the achieved bandwidth.
     a.na = 0; a.nbst = 0; a.nlo = split ? 2 : 0;
@@ -406,7 +437,7 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
         if (nbst < best_b) nbst = best_b;
         a.nbst = nbst;
     }
-    const size_t smem = (size_t)(a.na + a.nlo) * a_slot + (size_t)a.nbst * b_slot + 1024 + kBarBytes;
+    const size_t smem = (size_t)(a.na + a.nlo) * a_slot + (size_t)a.nbst * b_slot + 1024 + kBarBytes + kStageBytes;
 
     CUtensorMap map_a, map_b, map_blo;
     {

@@ -2,6 +2,7 @@
 // mixing over the joint axis with A_k + B_k + C_k resident in shared memory.
 // Reference arithmetic: torch_src/models/mmargcn/agcn.py:98-110 (matmul, softmax(-2), matmul) and its backward.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace agcn {
 
@@ -382,15 +383,27 @@ __global__ void __launch_bounds__(256) joint_mix_kernel(MixArgs p) {
 
 using namespace agcn;
 
+// implemented in gram_tc.cu; AGCN_ERR_UNSUPPORTED when the shape is outside the tensor-core path
+int agcn_joint_gram_tc(const float* a, const float* b, float* out,
+                       int nb, int t, int v, int lda, int ldb, int groups,
+                       int offa, int stridea, int offb, int strideb, int width, int nchunk, int split, void* stream);
+
 extern "C" AGCN_API int agcn_joint_gram(const float* a, const float* b, float* out,
                                int nb, int t, int v, int lda, int ldb, int groups,
-                               int offa, int stridea, int offb, int strideb, int width, int nchunk, void* stream) {
+                               int offa, int stridea, int offb, int strideb, int width, int nchunk, int precision, void* stream) {
     AGCN_REQUIRE(a && b && out, AGCN_ERR_NULL, "agcn_joint_gram: null pointer");
     AGCN_REQUIRE(nb > 0 && t > 0 && v > 0 && groups > 0 && width > 0 && nchunk > 0 && nchunk <= t,
                  AGCN_ERR_BAD_SHAPE, "agcn_joint_gram: bad shape nb=%d t=%d v=%d groups=%d width=%d nchunk=%d", nb, t, v, groups, width, nchunk);
     AGCN_REQUIRE(v <= kMaxV && groups <= 3, AGCN_ERR_UNSUPPORTED, "agcn_joint_gram: V=%d > %d or groups=%d > 3", v, kMaxV, groups);
     AGCN_REQUIRE(offa >= 0 && offb >= 0 && offa + (groups - 1) * stridea + width <= lda && offb + (groups - 1) * strideb + width <= ldb,
                  AGCN_ERR_BAD_SHAPE, "agcn_joint_gram: channel window outside the row");
+    AGCN_REQUIRE(precision == AGCN_PREC_FP32 || precision == AGCN_PREC_TF32 || precision == AGCN_PREC_FP32_FFMA, AGCN_ERR_UNSUPPORTED,
+                 "agcn_joint_gram: unknown precision %d", precision);
+    if (precision != AGCN_PREC_FP32_FFMA) {
+        const int rc = agcn_joint_gram_tc(a, b, out, nb, t, v, lda, ldb, groups, offa, stridea, offb, strideb, width, nchunk,
+                                          precision == AGCN_PREC_FP32, stream);
+        if (rc != AGCN_ERR_UNSUPPORTED) return rc;
+    }
     GramArgs p{a, b, out, nb, t, v, lda, ldb, groups, offa, stridea, offb, strideb, width, nchunk, 1, 0};
     const int cwp = ((width < kGramCW ? width : kGramCW) + 3) & ~3;
     const int ld = cwp + 4;
@@ -467,7 +480,8 @@ extern "C" AGCN_API int agcn_joint_mix(const float* in, const float* mats, float
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bool vec = (width % 4 == 0) && aligned16(in) && aligned16(out);
     cudaError_t e;
-    if (vec && width % 8 == 0) {
+    static const bool mix8 = getenv("AGCN_MIX8") != nullptr;      // 2-quad items: measured slower on B200 (114 registers), kept for experiments
+    if (vec && width % 8 == 0 && mix8) {
         e = cudaFuncSetAttribute(joint_mix_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return fail(AGCN_ERR_CUDA, "agcn_joint_mix: %s", cudaGetErrorString(e));
         joint_mix_kernel<8><<<nb * tiles_t, 256, smem, s>>>(p);

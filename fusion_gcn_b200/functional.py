@@ -76,8 +76,8 @@ def gcn_forward(x, adj_a, adj_b, wa, ba, wb, bb, wd, bd, bn_w, bn_b, down_w, dow
     bdc = bd[0] + bd[1] + bd[2]
 
     e = K.conv_fwd(x, wab, bab, precision=prec)                                        # theta / phi embeddings
-    nchunk = K.pick_nchunk(nb, t)
-    s_part = K.joint_gram(e, e, groups=3, offa=0, stridea=2 * ci, offb=ci, strideb=2 * ci, width=ci, nchunk=nchunk)
+    nchunk = K.pick_nchunk(nb, t, v, ci)
+    s_part = K.joint_gram(e, e, groups=3, offa=0, stridea=2 * ci, offb=ci, strideb=2 * ci, width=ci, nchunk=nchunk, precision=prec)
     scale = 1.0 / float(ci * t)
     p, g = K.attention_fwd(s_part, adj_a.contiguous(), adj_b.contiguous(), scale)
     z = K.joint_mix(x, g, width=cin, mode=K.MIX_AGG_FWD)                               # [nb,t,v,3*cin]
@@ -124,7 +124,8 @@ def gcn_backward(d_o, ctx, bn_w, dbn_w, down_w, spec: UnitSpec, dx=None, need_dx
     d_wdc, _ = K.conv_wgrad(dy, z, want_bias=False, precision=prec)
     d_bdc = _zero_bias(x, cout)
     dz = K.conv_fwd(dy, _t(ctx["wdc"]), precision=prec)                                # [nb,t,v,3*cin]
-    dg_part = K.joint_gram(x, dz, groups=3, offa=0, stridea=0, offb=0, strideb=cin, width=cin, nchunk=ctx["nchunk"])
+    dg_part = K.joint_gram(x, dz, groups=3, offa=0, stridea=0, offb=0, strideb=cin, width=cin, nchunk=K.pick_nchunk(nb, t, v, cin),
+                           precision=prec)
     ds, d_adj_b = K.attention_bwd(dg_part, p, ctx["scale"])
     if need_dx:
         dx = K.joint_mix(dz, g, width=cin, mode=K.MIX_AGG_BWD, out=dx, accumulate=have)

@@ -57,7 +57,8 @@ def start_timing(names):
 
 
 def stop_timing():
-    """-> {(name, nb, t_in, t_out, v, cin, cout, taps): (total_ms, launches)}; synchronises the device."""
+    """-> {(name, signature): (total_ms, launches, algorithmic_flops, algorithmic_bytes)}; synchronises the device.
+    ``signature`` is the tuple of shape arguments of the call; flops / bytes are per launch."""
     global _timing
     if _timing is None:
         return {}
@@ -65,21 +66,23 @@ def stop_timing():
     _timing = None
     torch.cuda.synchronize()
     out = {}
-    for key, e0, e1 in records:
-        tot, cnt = out.get(key, (0.0, 0))
-        out[key] = (tot + e0.elapsed_time(e1), cnt + 1)
+    for key, work, e0, e1 in records:
+        tot, cnt = out.get(key, (0.0, 0, 0.0, 0.0))[:2]
+        out[key] = (tot + e0.elapsed_time(e1), cnt + 1, work[0], work[1])
     return out
 
 
-def _call(name, *args):
+def _call(name, *args, sig=None, work=(0.0, 0.0)):
+    """``sig``: shape signature of the call, ``work``: (algorithmic FLOPs, algorithmic bytes) of one launch -- used only while
+    bench.py is timing (CUDA events on the launching stream around the C-ABI call)."""
     capi.launch_count += 1
     fn = getattr(capi.lib(), name)
-    if _timing is not None and name in _timing[0]:
+    if _timing is not None and (name in _timing[0] or "*" in _timing[0]):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         rc = fn(*args)
         e1.record()
-        _timing[1].append(((name,) + tuple(args[4:11]), e0, e1))
+        _timing[1].append(((name, sig), work, e0, e1))
     else:
         rc = fn(*args)
     capi.check(rc, name)
@@ -104,8 +107,11 @@ def conv_fwd(x, w, bias=None, *, t_out=None, stride=1, pad=0, transposed=False, 
     _check(x, w, bias, out)
     ws_bytes = capi.lib().agcn_conv_fwd_workspace_bytes(cin, cout, taps, precision)
     ws = torch.empty((ws_bytes + 3) // 4, device=x.device, dtype=torch.float32) if ws_bytes else None
+    rows = nb * t_out * v
     _call("agcn_conv_fwd", _ptr(x), _ptr(w), _ptr(bias), _ptr(out), nb, t_in, t_out, v, cin, cout, taps, stride, pad,
-          int(transposed), int(accumulate), precision, _ptr(ws), ws_bytes, _stream())
+          int(transposed), int(accumulate), precision, _ptr(ws), ws_bytes, _stream(),
+          sig=(nb, t_in, t_out, v, cin, cout, taps, stride, int(transposed), int(accumulate)),
+          work=(2.0 * rows * cin * cout * taps, 4.0 * (x.numel() + rows * cout * (2 if accumulate else 1))))
     return out
 
 
@@ -122,24 +128,31 @@ def conv_wgrad(dy, x, *, taps=1, stride=1, pad=0, want_bias=True, precision=PREC
     dw = torch.empty((cout, taps, cin), device=x.device, dtype=torch.float32)
     db = torch.empty((cout,), device=x.device, dtype=torch.float32) if want_bias else None
     _call("agcn_conv_wgrad", _ptr(dy), _ptr(x), _ptr(dw), _ptr(db), nb, t_in, t_out, v, cin, cout, taps, stride, pad,
-          _ptr(ws), ws_bytes, precision, _stream())
+          _ptr(ws), ws_bytes, precision, _stream(), sig=(nb, t_in, t_out, v, cin, cout, taps, stride),
+          work=(2.0 * nb * t_out * v * cin * cout * taps, 4.0 * (x.numel() + dy.numel())))
     return dw, db
 
 
 # ----------------------------------------------------------------------------- V x V attention
-def pick_nchunk(nb: int, t: int) -> int:
-    """Chunks of the t axis so that nb*nchunk CTAs cover the 148 SMs about four times."""
+def pick_nchunk(nb: int, t: int, v: int = 0, width: int = 0) -> int:
+    """Chunks of the t axis of the joint-gram reduction (one CTA per (sample, chunk)).  Shapes the tensor-core kernel takes
+    (3*v <= 80, width 16 or a multiple of 32) want ONE resident wave of long-running CTAs (<= 148); the FFMA kernel wants
+    about four waves of short ones."""
+    if v and 3 * v <= 80 and (width == 16 or (width > 0 and width % 32 == 0)):
+        return max(1, min(NUM_SMS // max(nb, 1), max(1, t // 8)))
     n = max(1, min((4 * NUM_SMS + nb - 1) // nb, max(1, t // 4)))
     return min(n, t)
 
 
-def joint_gram(a, b, *, groups, offa, stridea, offb, strideb, width, nchunk):
+def joint_gram(a, b, *, groups, offa, stridea, offb, strideb, width, nchunk, precision=PREC_FP32):
     nb, t, v, lda = a.shape
     ldb = b.shape[3]
     _check(a, b)
     out = torch.empty((nb, nchunk, groups, v, v), device=a.device, dtype=torch.float32)
+    same = a.data_ptr() == b.data_ptr()
     _call("agcn_joint_gram", _ptr(a), _ptr(b), _ptr(out), nb, t, v, lda, ldb, groups, offa, stridea, offb, strideb, width,
-          nchunk, _stream())
+          nchunk, precision, _stream(), sig=(nb, t, v, lda, ldb, groups, width, nchunk),
+          work=(2.0 * nb * t * groups * v * v * width, 4.0 * (a.numel() + (0 if same else b.numel()))))
     return out
 
 
@@ -149,7 +162,7 @@ def attention_fwd(s_part, adj_a, adj_b, scale: float) -> Tuple[torch.Tensor, tor
     p = torch.empty((nb, groups, v, v), device=s_part.device, dtype=torch.float32)
     g = torch.empty_like(p)
     _call("agcn_attention_fwd", _ptr(s_part), _ptr(adj_a), _ptr(adj_b), _ptr(p), _ptr(g), nb, nchunk, groups, v, float(scale),
-          _stream())
+          _stream(), sig=(nb, nchunk, groups, v), work=(0.0, 4.0 * (s_part.numel() + 2 * p.numel())))
     return p, g
 
 
@@ -160,7 +173,7 @@ def attention_bwd(dg_part, p, scale: float) -> Tuple[torch.Tensor, torch.Tensor]
     ds = torch.empty_like(p)
     dadj_b = torch.empty((groups, v, v), device=p.device, dtype=torch.float32)
     _call("agcn_attention_bwd", _ptr(dg_part), _ptr(p), _ptr(dg_sum), _ptr(ds), _ptr(dadj_b), nb, nchunk, groups, v,
-          float(scale), _stream())
+          float(scale), _stream(), sig=(nb, nchunk, groups, v), work=(0.0, 4.0 * (dg_part.numel() + 3 * p.numel())))
     return ds, dadj_b
 
 
@@ -172,7 +185,10 @@ def joint_mix(inp, mats, *, width, mode, out=None, accumulate=False):
             raise RuntimeError("joint_mix: accumulate needs an output tensor")
         out = torch.empty((nb, t, v, ldout), device=inp.device, dtype=torch.float32)
     _check(inp, mats, out)
-    _call("agcn_joint_mix", _ptr(inp), _ptr(mats), _ptr(out), nb, t, v, ldin, ldout, width, mode, int(accumulate), _stream())
+    terms = {MIX_AGG_FWD: 3, MIX_AGG_BWD: 3, MIX_SCORE_BWD: 6}[mode]
+    _call("agcn_joint_mix", _ptr(inp), _ptr(mats), _ptr(out), nb, t, v, ldin, ldout, width, mode, int(accumulate), _stream(),
+          sig=(nb, t, v, ldin, ldout, width, mode, int(accumulate)),
+          work=(2.0 * nb * t * terms * v * v * width, 4.0 * (inp.numel() + out.numel() * (2 if accumulate else 1))))
     return out
 
 
@@ -201,7 +217,8 @@ def bn_stats(x, gamma, beta, running_mean, running_var, nbt, momentum, eps, trai
         raise RuntimeError("num_batches_tracked must be int64")
     _call("agcn_bn_stats", x.data_ptr(), outer, inner, ostride, c, _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var),
           _ptr(nbt), float(momentum), float(eps), int(training), scale[0].data_ptr(), scale[1].data_ptr(),
-          scale[2].data_ptr(), scale[3].data_ptr(), _ptr(ws), nbytes, _stream())
+          scale[2].data_ptr(), scale[3].data_ptr(), _ptr(ws), nbytes, _stream(),
+          sig=(outer, inner, c, int(training)), work=(0.0, 4.0 * outer * inner * c if training else 0.0))
     return scale[0], scale[1], scale[2], scale[3]
 
 
@@ -212,7 +229,8 @@ def bn_apply(y, scale, shift, *, res_mode=RES_NONE, res=None, scale2=None, shift
     _check_strided(y, res, out)
     _check(scale, shift, scale2, shift2)
     _call("agcn_bn_apply", y.data_ptr(), _ptr(scale), _ptr(shift), res_mode, _ptr(res), _ptr(scale2), _ptr(shift2), int(relu),
-          out.data_ptr(), outer, inner, ostride, c, _stream())
+          out.data_ptr(), outer, inner, ostride, c, _stream(), sig=(outer, inner, c, res_mode, int(relu)),
+          work=(0.0, 4.0 * outer * inner * c * (2 if res_mode == RES_NONE else 3)))
     return out
 
 
@@ -229,7 +247,11 @@ def bn_bwd(dout, mask_out, y, save_mean, save_invstd, gamma, *, want_dy=True, dy
     ws, nbytes = _bn_ws(c, y.device)
     _call("agcn_bn_bwd", dout.data_ptr(), _ptr(mask_out), y.data_ptr(), _ptr(save_mean), _ptr(save_invstd), _ptr(gamma),
           _ptr(dy), dgb[0].data_ptr(), dgb[1].data_ptr(), _ptr(dres), int(dres_accumulate), outer, inner, ostride, c,
-          _ptr(ws), nbytes, _stream())
+          _ptr(ws), nbytes, _stream(),
+          sig=(outer, inner, c, int(mask_out is not None), int(dy is not None), int(dres is not None), int(dres_accumulate)),
+          # two passes over (dout, y[, mask]); the second writes dy [and dres, read first when accumulating]
+          work=(0.0, 4.0 * outer * inner * c * (2 * (2 + int(mask_out is not None)) + int(dy is not None)
+                                               + int(dres is not None) * (1 + int(dres_accumulate)))))
     return dy, dgb[0], dgb[1]
 
 
@@ -239,7 +261,7 @@ def pool_fwd(x, groups: int):
     rows = x.numel() // c // groups
     _check(x)
     out = torch.empty((groups, c), device=x.device, dtype=torch.float32)
-    _call("agcn_pool_fwd", _ptr(x), _ptr(out), groups, rows, c, _stream())
+    _call("agcn_pool_fwd", _ptr(x), _ptr(out), groups, rows, c, _stream(), sig=(groups, rows, c), work=(0.0, 4.0 * x.numel()))
     return out
 
 
@@ -248,5 +270,5 @@ def pool_bwd(dout, shape):
     dx = torch.empty(shape, device=dout.device, dtype=torch.float32)
     rows = dx.numel() // c // groups
     _check(dout)
-    _call("agcn_pool_bwd", _ptr(dout), _ptr(dx), groups, rows, c, _stream())
+    _call("agcn_pool_bwd", _ptr(dout), _ptr(dx), groups, rows, c, _stream(), sig=(groups, rows, c), work=(0.0, 4.0 * dx.numel()))
     return dx

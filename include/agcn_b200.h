@@ -97,10 +97,13 @@ int agcn_conv_wgrad(const float* dy, const float* x, float* dw, float* dbias,
  * a: [nb][t][v][lda], b: [nb][t][v][ldb].  The t axis is split into nchunk contiguous chunks so that a
  * grid of nb*nchunk CTAs fills the GPU; the consumer sums the chunks in a fixed order.
  * Used for the score theta^T phi (agcn.py:104-106, a = b = [theta|phi] embedding) and for
- * dG = X^T dZ (gradient of agcn.py:110).  V <= 32.                                                     */
+ * dG = X^T dZ (gradient of agcn.py:110).  V <= 32.
+ * precision: AGCN_PREC_FP32 / AGCN_PREC_TF32 run the contraction on the tensor cores (3xTF32 / single-pass TF32) when
+ * groups == 3, 3*V <= 80 and width is 16 (theta|phi sharing a 32-channel row) or a multiple of 32; every other shape and
+ * AGCN_PREC_FP32_FFMA use the FFMA kernel.                                                                */
 int agcn_joint_gram(const float* a, const float* b, float* out,
                     int nb, int t, int v, int lda, int ldb, int groups,
-                    int offa, int stridea, int offb, int strideb, int width, int nchunk, void* stream);
+                    int offa, int stridea, int offb, int strideb, int width, int nchunk, int precision, void* stream);
 
 /* p[nb][k][:, v] = softmax_u(scale * sum_chunk s_part[nb][chunk][k][u][v]);  g = p + adj_a[k] + adj_b[k]
  * (agcn.py:98-100,106-108; softmax over dim -2, i.e. columns sum to one).                               */

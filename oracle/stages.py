@@ -67,12 +67,12 @@ def conv_wgrad(dy, x, *, taps=1, stride=1, pad=0, want_bias=True, precision=PREC
     return dw, db
 
 
-def pick_nchunk(nb, t):
+def pick_nchunk(nb, t, v=0, width=0):
     n = max(1, min((4 * NUM_SMS + nb - 1) // nb, max(1, t // 4)))
     return min(n, t)
 
 
-def joint_gram(a, b, *, groups, offa, stridea, offb, strideb, width, nchunk):
+def joint_gram(a, b, *, groups, offa, stridea, offb, strideb, width, nchunk, precision=0):
     nb, t, v, _ = a.shape
     t_per = (t + nchunk - 1) // nchunk
     out = a.new_zeros(nb, nchunk, groups, v, v)
@@ -225,13 +225,20 @@ class Tf32Emulation:
     @staticmethod
     def _fwd_on_tc(x, w, transposed, stride):
         cout, taps, cin = w.shape
-        ok = cin % 4 == 0 and cout % 16 == 0 and (cout <= 128 or cout % 64 == 0 or cout % 96 == 0)
+        ok = cin % 4 == 0 and cout % 16 == 0 and (cout <= 128 or any(cout % c == 0 for c in range(64, 257, 16)))
         return ok and not (transposed and stride > 1 and taps < stride)
 
     def conv_fwd(self, x, w, bias=None, *, stride=1, transposed=False, precision=PREC_FP32, **kw):
         if precision == PREC_TF32 and self._fwd_on_tc(x, w, transposed, stride):
             x, w = _trunc_tf32(x), _trunc_tf32(w)
         return conv_fwd(x, w, bias, stride=stride, transposed=transposed, **kw)
+
+    def joint_gram(self, a, b, *, precision=PREC_FP32, **kw):
+        v, width, same_row = a.shape[2], kw["width"], a is b and kw["stridea"] == 32 and kw["strideb"] == 32 and kw["offb"] == kw["offa"] + 16
+        on_tc = kw["groups"] == 3 and 3 * v <= 80 and ((width == 16 and same_row) or width % 32 == 0)
+        if precision == PREC_TF32 and on_tc:
+            a, b = _trunc_tf32(a), _trunc_tf32(b)
+        return joint_gram(a, b, **kw)
 
     def conv_wgrad(self, dy, x, *, precision=PREC_FP32, **kw):
         _, db = conv_wgrad(dy, x, **kw)

@@ -73,6 +73,31 @@ def test_joint_gram_score_and_dg(K, nb, t, v, ci, nchunk):
     assert rel_err(dg, dg_ref) <= 2e-6
 
 
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "ffma"])
+@pytest.mark.parametrize("nb,t,v,ci,nchunk", [(2, 12, 25, 16, 3), (3, 9, 20, 32, 2), (2, 7, 22, 64, 7), (1, 30, 25, 16, 1), (2, 5, 18, 32, 5)])
+def test_joint_gram_tensor_core_shapes(K, nb, t, v, ci, nchunk, mode):
+    """Shapes the tcgen05 gram kernel takes (score with theta|phi sharing a 32-channel row, 32/64-wide groups, dG with
+    C = 4*ci channels): fp32 mode = 3xTF32 (1e-5), TF32 mode against TF32-truncated operands (1e-5) and raw operands
+    (3e-3), FFMA mode = the SIMT kernel (2e-6)."""
+    prec = {"fp32": K.PREC_FP32, "tf32": K.PREC_TF32, "ffma": K.PREC_FP32_FFMA}[mode]
+    tol = {"fp32": 1e-5, "tf32": 3e-3, "ffma": 2e-6}[mode]
+    e = rnd(nb, t, v, 6 * ci)
+    kw = dict(groups=3, offa=0, stridea=2 * ci, offb=ci, strideb=2 * ci, width=ci, nchunk=nchunk)
+    ec = e.cuda()            # one tensor for both operands, as in the unit (the shared theta|phi row needs a == b)
+    s = K.joint_gram(ec, ec, precision=prec, **kw)
+    assert rel_err(s, S.joint_gram(e.double(), e.double(), **kw)) <= tol
+    if mode == "tf32":
+        et = _trunc_tf32(e)
+        assert rel_err(s, S.joint_gram(et.double(), et.double(), **kw)) <= 1e-5
+    c = 4 * ci
+    x, dz = rnd(nb, t, v, c, seed=5), rnd(nb, t, v, 3 * c, seed=6)
+    kw = dict(groups=3, offa=0, stridea=0, offb=0, strideb=c, width=c, nchunk=nchunk)
+    dg = K.joint_gram(x.cuda(), dz.cuda(), precision=prec, **kw)
+    assert rel_err(dg, S.joint_gram(x.double(), dz.double(), **kw)) <= tol
+    if mode == "tf32":
+        assert rel_err(dg, S.joint_gram(_trunc_tf32(x).double(), _trunc_tf32(dz).double(), **kw)) <= 1e-5
+
+
 def test_joint_gram_wide_channels(K):
     x, dz = rnd(2, 6, 25, 256), rnd(2, 6, 25, 768, seed=1)
     kw = dict(groups=3, offa=0, stridea=0, offb=0, strideb=256, width=256, nchunk=2)

@@ -52,14 +52,14 @@ def main():
         act = rows * c * 4
         if want(f"gram_score_{tag}"):
             e = torch.randn(NB, t, V, 6 * ci, device=dev)
-            nchunk = K.pick_nchunk(NB, t)
-            ms = timeit(lambda: K.joint_gram(e, e, groups=3, offa=0, stridea=2 * ci, offb=ci, strideb=2 * ci, width=ci, nchunk=nchunk), once)
+            nchunk = K.pick_nchunk(NB, t, V, ci)
+            ms = timeit(lambda: K.joint_gram(e, e, groups=3, offa=0, stridea=2 * ci, offb=ci, strideb=2 * ci, width=ci, nchunk=nchunk, precision=prec), once)
             report(f"gram_score_{tag}", ms, e.numel() * 4, 3 * 2.0 * rows * V * ci)
             del e
         if want(f"gram_dg_{tag}"):
             dz = torch.randn(NB, t, V, 3 * c, device=dev)
-            nchunk = K.pick_nchunk(NB, t)
-            ms = timeit(lambda: K.joint_gram(x, dz, groups=3, offa=0, stridea=0, offb=0, strideb=c, width=c, nchunk=nchunk), once)
+            nchunk = K.pick_nchunk(NB, t, V, c)
+            ms = timeit(lambda: K.joint_gram(x, dz, groups=3, offa=0, stridea=0, offb=0, strideb=c, width=c, nchunk=nchunk, precision=prec), once)
             report(f"gram_dg_{tag}", ms, act * 4, 3 * 2.0 * rows * V * c)
             del dz
         if want(f"mix_fwd_{tag}") or want(f"mix_bwd_{tag}"):
