@@ -311,15 +311,6 @@ struct WgArgs {
     int dbg;           // bring-up only (env AGCN_WG_DEBUG): bit 0 skips the operand split, bit 1 skips the MMAs -> wrong results, timing probes
 };
 
-__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;   // leading byte offset: between 32-channel (MN) atoms
-    d |= (uint64_t)(512 >> 4) << 32;                     // stride byte offset: between 4-row (K) groups of the 32B-atom swizzle
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)1 << 61;                              // SWIZZLE_128B_BASE32B: the only layout for MN-major tf32 operands
-    return d;
-}
 
 template <bool SPLIT>
 __global__ void __launch_bounds__(SPLIT ? kWgThreadsSplit : kThreads, 1)

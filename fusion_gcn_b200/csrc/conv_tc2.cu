@@ -263,19 +263,27 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                             const bool col_ok = cq < 4 || wide;
                             float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (a.bias && col_ok) bq = __ldg(reinterpret_cast<const float4*>(a.bias + nt * a.bn + c0 + cq * 4));
+                            // four row offsets (and, when accumulating, four old values) are fetched before the first dependent
+                            // add / store, so the global-load latency is paid twice per chunk, not once per row
 #pragma unroll
-                            for (int rr = 0; rr < 8; ++rr) {
-                                const int src_lane = rr * 4 + (lane >> 3);
-                                const long long off = __shfl_sync(0xffffffffu, my_off, src_lane);
-                                if (off >= 0 && col_ok) {
-                                    float4 o = lds128(stage_base + (uint32_t)src_lane * kStagePitch + (uint32_t)cq * 16u);
-                                    o.x += bq.x; o.y += bq.y; o.z += bq.z; o.w += bq.w;
-                                    float4* p = reinterpret_cast<float4*>(a.y + off + c0 + cq * 4);
-                                    if (a.accumulate) {
-                                        const float4 old = *p;
-                                        o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                            for (int half = 0; half < 2; ++half) {
+                                long long offs[4];
+                                float4 oldv[4];
+#pragma unroll
+                                for (int r4 = 0; r4 < 4; ++r4) {
+                                    offs[r4] = __shfl_sync(0xffffffffu, my_off, (half * 4 + r4) * 4 + (lane >> 3));
+                                    oldv[r4] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                    if (a.accumulate && offs[r4] >= 0 && col_ok)
+                                        oldv[r4] = *reinterpret_cast<const float4*>(a.y + offs[r4] + c0 + cq * 4);
+                                }
+#pragma unroll
+                                for (int r4 = 0; r4 < 4; ++r4) {
+                                    const int src_lane = (half * 4 + r4) * 4 + (lane >> 3);
+                                    if (offs[r4] >= 0 && col_ok) {
+                                        float4 o = lds128(stage_base + (uint32_t)src_lane * kStagePitch + (uint32_t)cq * 16u);
+                                        o.x += bq.x + oldv[r4].x; o.y += bq.y + oldv[r4].y; o.z += bq.z + oldv[r4].z; o.w += bq.w + oldv[r4].w;
+                                        *reinterpret_cast<float4*>(a.y + offs[r4] + c0 + cq * 4) = o;
                                     }
-                                    *p = o;
                                 }
                             }
                             __syncwarp();

@@ -356,6 +356,27 @@ __global__ void __launch_bounds__(256) joint_mix_kernel(MixArgs p) {
             }
         }
         const int t = t0 + tl;
+        // when accumulating, all old values are loaded before the first add / store (one exposed load latency per item)
+        float oldv[NQ][5][CE];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const int jj = jb * 5 + j;
+            const float* o = p.out + (((long long)n * p.t + t) * V + (jj < V ? jj : 0)) * p.ldout + og * W + c;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                if (p.accumulate && jj < V) {
+                    if (CE == 4) {
+                        const float4 v4 = *reinterpret_cast<const float4*>(o + q * qstride);
+                        oldv[q][j][0] = v4.x; oldv[q][j][1 % CE] = v4.y; oldv[q][j][2 % CE] = v4.z; oldv[q][j][3 % CE] = v4.w;
+                    } else {
+                        oldv[q][j][0] = o[0];
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < CE; ++e) oldv[q][j][e] = 0.f;
+                }
+            }
+        }
 #pragma unroll
         for (int j = 0; j < 5; ++j) {
             const int jj = jb * 5 + j;
@@ -364,15 +385,11 @@ __global__ void __launch_bounds__(256) joint_mix_kernel(MixArgs p) {
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
                 if (CE == 4) {
-                    float4 v4 = make_float4(acc[q][j][0], acc[q][j][1 % CE], acc[q][j][2 % CE], acc[q][j][3 % CE]);
-                    float4* dst = reinterpret_cast<float4*>(o + q * qstride);
-                    if (p.accumulate) {
-                        const float4 old = *dst;
-                        v4.x += old.x; v4.y += old.y; v4.z += old.z; v4.w += old.w;
-                    }
-                    *dst = v4;
+                    *reinterpret_cast<float4*>(o + q * qstride) =
+                        make_float4(acc[q][j][0] + oldv[q][j][0], acc[q][j][1 % CE] + oldv[q][j][1 % CE],
+                                    acc[q][j][2 % CE] + oldv[q][j][2 % CE], acc[q][j][3 % CE] + oldv[q][j][3 % CE]);
                 } else {
-                    o[0] = p.accumulate ? o[0] + acc[q][j][0] : acc[q][j][0];
+                    o[0] = acc[q][j][0] + oldv[q][j][0];
                 }
             }
         }

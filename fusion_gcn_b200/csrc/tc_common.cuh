@@ -160,6 +160,18 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 }
 
 
+// MN-major (channels contiguous) operand, 128B swizzle with 32-byte atoms: 32 fp32 along M/N per 128-byte row, rows along K in
+// groups of 4 (512 bytes); `lbo_bytes` is the distance between successive 32-wide M/N atoms
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;   // leading byte offset: between 32-channel (MN) atoms
+    d |= (uint64_t)(512 >> 4) << 32;                     // stride byte offset: between 4-row (K) groups of the 32B-atom swizzle
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;                              // SWIZZLE_128B_BASE32B: the only layout for MN-major tf32 operands
+    return d;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
