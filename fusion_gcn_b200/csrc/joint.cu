@@ -472,8 +472,16 @@ extern "C" AGCN_API int agcn_attention_bwd(const float* dg_part, const float* p,
     return check_launch("agcn_attention_bwd(dadj_b)");
 }
 
+// implemented in mix_tc.cu; AGCN_ERR_UNSUPPORTED when the shape / mode is outside the tensor-core path
+size_t agcn_joint_mix_tc_workspace_bytes(int nb);
+int agcn_joint_mix_tc(const float* in, const float* mats, float* out, float* gp,
+                      int nb, int t, int v, int ldin, int ldout, int width, int mode, int accumulate, int split, void* stream);
+
+extern "C" AGCN_API size_t agcn_joint_mix_workspace_bytes(int nb) { return nb > 0 ? agcn_joint_mix_tc_workspace_bytes(nb) : 0; }
+
 extern "C" AGCN_API int agcn_joint_mix(const float* in, const float* mats, float* out,
-                              int nb, int t, int v, int ldin, int ldout, int width, int mode, int accumulate, void* stream) {
+                              int nb, int t, int v, int ldin, int ldout, int width, int mode, int accumulate,
+                              int precision, void* workspace, size_t workspace_bytes, void* stream) {
     AGCN_REQUIRE(in && mats && out, AGCN_ERR_NULL, "agcn_joint_mix: null pointer");
     AGCN_REQUIRE(nb > 0 && t > 0 && v > 0 && width > 0, AGCN_ERR_BAD_SHAPE, "agcn_joint_mix: bad shape");
     AGCN_REQUIRE(v <= kMaxV, AGCN_ERR_UNSUPPORTED, "agcn_joint_mix: V=%d > %d", v, kMaxV);
@@ -484,6 +492,13 @@ extern "C" AGCN_API int agcn_joint_mix(const float* in, const float* mats, float
     else return fail(AGCN_ERR_UNSUPPORTED, "agcn_joint_mix: unknown mode %d", mode);
     AGCN_REQUIRE(ldin == need_in && ldout == need_out, AGCN_ERR_BAD_SHAPE,
                  "agcn_joint_mix: mode %d expects ldin=%d ldout=%d, got %d %d", mode, need_in, need_out, ldin, ldout);
+    AGCN_REQUIRE(precision == AGCN_PREC_FP32 || precision == AGCN_PREC_TF32 || precision == AGCN_PREC_FP32_FFMA, AGCN_ERR_UNSUPPORTED,
+                 "agcn_joint_mix: unknown precision %d", precision);
+    if (precision != AGCN_PREC_FP32_FFMA && workspace != nullptr && workspace_bytes >= agcn_joint_mix_tc_workspace_bytes(nb)) {
+        const int rc = agcn_joint_mix_tc(in, mats, out, static_cast<float*>(workspace), nb, t, v, ldin, ldout, width, mode, accumulate,
+                                         precision == AGCN_PREC_FP32, stream);
+        if (rc != AGCN_ERR_UNSUPPORTED) return rc;
+    }
     const int nblk = (v + 4) / 5, mld = nblk * 8;
     const int nslots = mode == AGCN_MIX_SCORE_BWD ? 6 : 3;
     // choose tt so that the staged rows stay below ~64 KB and there are enough work items per CTA

@@ -1,0 +1,363 @@
+// Per-sample mixing over the joint axis on the tensor cores (tcgen05 / TMA), sm_100a only.
+//
+//   AGG_FWD : out[n][t][v][k*W + c]  = sum_u         in[n][t][u][c]       * G[n][k][u][v]       (agcn.py:110, X . G_k)
+//   AGG_BWD : out[n][t][u][c]      (+)= sum_k sum_v  in[n][t][v][k*W + c] * G[n][k][u][v]       (its input gradient)
+//
+// GEMM view (per timestep): the contraction index is the JOINT, the channels are the M dimension:
+//   D[(t, cb, c)][col] = sum_joint A[(t, cb, c)][joint] * B[col][joint],   cb = 32-channel block, c = channel in block
+// so an M = 128 tile is four (timestep, channel-block) pairs.  Activations are channels-contiguous, i.e. M-contiguous
+// ("MN-major", 128B swizzle with 32-byte atoms, the same operand form as the weight-gradient kernel): one TMA box of
+// 32 channels x 32 joint rows per pair (rows >= V are out of bounds of the tensor map and arrive as zeros), LBO = one box.
+// B is the per-sample matrix, padded to 32 x 32 per subset by pad_mats_kernel and TMA-loaded once per sample:
+//   AGG_FWD: B[N = (k, v)][K = u] = G[k][u][v]  (N contiguous: Gp [k][u][v32]),  N = 96, K = 32  (4 UMMA K steps)
+//   AGG_BWD: B[N = u][K = (k, v)] = G[k][u][v]  (N contiguous: GpT[k][v][u32]),  N = 32, K = 3 x 32 (12 UMMA K steps)
+// The K reduction is at most 96 long, so the 3xTF32 mode needs no accumulator promotion.
+// The epilogue thread of TMEM lane (pair, c) owns one channel of one timestep: for every accumulator column (an output
+// joint) the 32 lanes of a warp write 32 consecutive channels, a full 128-byte line.
+// Warp roles: 0 activation producer (TMA), 1 MMA issuer, 2..5 epilogue, 6 matrix producer, 7..14 operand split (3xTF32).
+// Persistent: CTA c walks a contiguous range of tiles (tiles of one sample are consecutive, so B changes at most a few times).
+#include "tc_common.cuh"
+#include <stdlib.h>
+
+namespace agcn {
+namespace mtc {
+using namespace agcn::tc;
+
+constexpr int kMaxA = 8;
+constexpr int kSplitWarps = 8;
+constexpr int kThreadsM = 7 * 32;
+constexpr int kThreadsMSplit = (7 + kSplitWarps) * 32;
+constexpr uint32_t kBarBytes = 512;
+constexpr uint32_t kBoxBytes = 4096;      // 32 rows x 128 bytes
+constexpr uint32_t kMatBytes = 3u * kBoxBytes;
+
+struct MArgs {
+    float* out;
+    int nb, t, v, width, bwd, accumulate;
+    int ncb;                 // 32-channel blocks per timestep
+    int tiles_per_sample;    // ceil(t * ncb / 4)
+    long long total_tiles;
+    int kb;                  // K blocks per tile: 1 (fwd) or 3 (bwd)
+    int ncols;               // accumulator columns: 96 (fwd) or 32 (bwd)
+    int na, nlo;
+    uint32_t a_tile;         // kb * 4 * kBoxBytes
+    int ldout;
+};
+
+// mats [nb][3][v][v] -> gp [nb][3][32][32] (zero padded): fwd keeps [k][u][v], bwd stores the transpose [k][v][u]
+__global__ void pad_mats_kernel(const float* mats, float* gp, int nb, int v, int transpose) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nb * 3 * 1024) return;
+    const int c = idx & 31, r = (idx >> 5) & 31, nk = idx >> 10;
+    float val = 0.f;
+    if (r < v && c < v) val = transpose ? mats[((long long)nk * v + c) * v + r] : mats[((long long)nk * v + r) * v + c];
+    gp[idx] = val;
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(SPLIT ? kThreadsMSplit : kThreadsM, 1)
+mix_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, MArgs p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t lo_ring = smem_base + (uint32_t)p.na * p.a_tile;                       // SPLIT: nlo slots of a_tile
+    const uint32_t b_ring = lo_ring + (SPLIT ? (uint32_t)p.nlo * p.a_tile : 0u);          // 2 slots of kMatBytes (+ 2 lo slots when SPLIT)
+    const uint32_t b_lo = b_ring + 2u * kMatBytes;
+    const uint32_t bar_base = b_lo + (SPLIT ? 2u * kMatBytes : 0u);
+    auto a_full = [&](int s) { return bar_base + 8u * s; };
+    auto a_empty = [&](int s) { return bar_base + 8u * (kMaxA + s); };
+    auto a_lo = [&](int s) { return bar_base + 8u * (2 * kMaxA + s); };
+    auto lo_empty = [&](int s) { return bar_base + 8u * (3 * kMaxA + s); };
+    auto b_full = [&](int s) { return bar_base + 8u * (3 * kMaxA + 2 + s); };
+    auto b_empty = [&](int s) { return bar_base + 8u * (3 * kMaxA + 4 + s); };
+    auto b_lo_bar = [&](int s) { return bar_base + 8u * (3 * kMaxA + 6 + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (3 * kMaxA + 8 + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (3 * kMaxA + 10 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (3 * kMaxA + 12);
+    constexpr int kCols = 256;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+        for (int s = 0; s < kMaxA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); mbar_init(a_lo(s), kSplitWarps); }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(lo_empty(s), 1); mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); mbar_init(b_lo_bar(s), kSplitWarps);
+            mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(kCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    // contiguous tile range of this CTA
+    const long long per = (p.total_tiles + gridDim.x - 1) / gridDim.x;
+    const long long tile_begin = (long long)blockIdx.x * per;
+    long long tile_end = tile_begin + per;
+    if (tile_end > p.total_tiles) tile_end = p.total_tiles;
+    const uint32_t a_tx = p.a_tile;
+
+    if (warp == 0) {
+        // ===================================================== activation producer
+        if (lane == 0) {
+            int sa = 0; uint32_t pa = 0;
+            for (long long tile = tile_begin; tile < tile_end; ++tile) {
+                const int n = (int)(tile / p.tiles_per_sample);
+                const int ts = (int)(tile - (long long)n * p.tiles_per_sample);
+                mbar_wait(a_empty(sa), pa ^ 1u);
+                mbar_expect_tx(a_full(sa), a_tx);
+                const uint32_t dst = smem_base + (uint32_t)sa * p.a_tile;
+                for (int k = 0; k < p.kb; ++k)
+                    for (int j = 0; j < 4; ++j) {
+                        const int pair = ts * 4 + j;
+                        const int tt = pair / p.ncb, cb = pair - tt * p.ncb;        // tt >= t for the pairs past the end: zero-filled box
+                        tma_load_4d(dst + (uint32_t)(k * 4 + j) * kBoxBytes, &map_a, a_full(sa), k * p.width + cb * 32, 0, tt, n);
+                    }
+                if (++sa == p.na) { sa = 0; pa ^= 1u; }
+            }
+        }
+    } else if (warp == 6) {
+        // ===================================================== matrix producer: one padded (3 x 32 x 32) block per sample
+        if (lane == 0) {
+            int m = -1;
+            int cur = -1;
+            for (long long tile = tile_begin; tile < tile_end; ++tile) {
+                const int n = (int)(tile / p.tiles_per_sample);
+                if (n == cur) continue;
+                cur = n;
+                ++m;
+                const int sb = m & 1;
+                mbar_wait(b_empty(sb), ((uint32_t)(m >> 1) & 1u) ^ 1u);
+                mbar_expect_tx(b_full(sb), kMatBytes);
+                tma_load_4d(b_ring + (uint32_t)sb * kMatBytes, &map_b, b_full(sb), 0, 0, 0, n);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                                   ((uint32_t)(p.ncols >> 3) << 17) | ((128u >> 4) << 24);
+            int sa = 0; uint32_t pa = 0;
+            int m = -1, sb = 0;                   // m: index of the current sample in this CTA's sequence; its matrix sits in slot m & 1
+            int acc = 0; uint32_t acc_phase = 0;
+            int sl = 0;
+            int cur = -1;
+            for (long long tile = tile_begin; tile < tile_end; ++tile) {
+                const int n = (int)(tile / p.tiles_per_sample);
+                if (n != cur) {
+                    if (m >= 0) umma_commit(b_empty(sb));             // every MMA that reads the previous matrix has been issued
+                    cur = n;
+                    ++m;
+                    sb = m & 1;
+                    mbar_wait(b_full(sb), (uint32_t)(m >> 1) & 1u);
+                    if (SPLIT) mbar_wait(b_lo_bar(sb), (uint32_t)(m >> 1) & 1u);
+                }
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                mbar_wait(a_full(sa), pa);
+                if (SPLIT) mbar_wait(a_lo(sa), pa);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
+                const uint32_t abase = smem_base + (uint32_t)sa * p.a_tile;
+                const uint32_t alo = lo_ring + (uint32_t)sl * p.a_tile;
+                const uint32_t bbase = b_ring + (uint32_t)sb * kMatBytes;
+                const uint32_t blo = b_lo + (uint32_t)sb * kMatBytes;
+                uint32_t first = 1;
+                for (int k = 0; k < p.kb; ++k) {
+                    // fwd: B atoms = the three subsets (LBO = one box), K rows inside each box;  bwd: one atom, K block k = box k
+                    const uint32_t bo = p.bwd ? (uint32_t)k * kBoxBytes : 0u;
+                    const uint64_t da = make_smem_desc_mn(abase + (uint32_t)k * 4u * kBoxBytes, kBoxBytes);
+                    const uint64_t dal = make_smem_desc_mn(alo + (uint32_t)k * 4u * kBoxBytes, kBoxBytes);
+                    const uint64_t db = make_smem_desc_mn(bbase + bo, kBoxBytes);
+                    const uint64_t dbl = make_smem_desc_mn(blo + bo, kBoxBytes);
+#pragma unroll
+                    for (int kg = 0; kg < 4; ++kg) {
+                        const uint64_t ko = (uint64_t)(kg * 64);          // 8 rows = 1024 bytes, in 16-byte units
+                        if (SPLIT) {
+                            umma_tf32(d_tmem, dal + ko, db + ko, idesc, first ? 0u : 1u);
+                            umma_tf32(d_tmem, da + ko, dbl + ko, idesc, 1u);
+                            umma_tf32(d_tmem, da + ko, db + ko, idesc, 1u);
+                        } else {
+                            umma_tf32(d_tmem, da + ko, db + ko, idesc, first ? 0u : 1u);
+                        }
+                        first = 0;
+                    }
+                }
+                umma_commit(a_empty(sa));
+                if (SPLIT) { umma_commit(lo_empty(sl)); if (++sl == p.nlo) sl = 0; }
+                umma_commit(tfull_bar(acc));
+                if (++sa == p.na) { sa = 0; pa ^= 1u; }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else if (warp < 6) {
+        // ===================================================== epilogue: warp quarter q = pair q of the tile, lane = channel
+        const int q = warp & 3;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (long long tile = tile_begin; tile < tile_end; ++tile) {
+            const int n = (int)(tile / p.tiles_per_sample);
+            const int ts = (int)(tile - (long long)n * p.tiles_per_sample);
+            const int pair = ts * 4 + q;
+            const int tt = pair / p.ncb, cb = pair - tt * p.ncb;
+            const bool ok = tt < p.t;
+            float* obase = p.out + ((long long)n * p.t + (ok ? tt : 0)) * p.v * p.ldout + cb * 32 + lane;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + (uint32_t)(acc * 128) + ((uint32_t)(q * 32) << 16);
+            if (!p.bwd) {
+                // column j = k*32 + v -> out[.., v, k*W + cb*32 + c]
+#pragma unroll
+                for (int cg = 0; cg < 6; ++cg) {
+                    float vals[16];
+                    tmem_ld16(taddr + (uint32_t)(cg * 16), vals);
+                    const int k = cg >> 1, v0 = (cg & 1) * 16;
+                    if (ok) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (v0 + i < p.v) obase[(long long)(v0 + i) * p.ldout + k * p.width] = vals[i];
+                    }
+                }
+            } else {
+                // column j = u -> out[.., u, cb*32 + c]
+#pragma unroll
+                for (int cg = 0; cg < 2; ++cg) {
+                    float vals[16];
+                    tmem_ld16(taddr + (uint32_t)(cg * 16), vals);
+                    if (ok) {
+                        float oldv[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            oldv[i] = (p.accumulate && cg * 16 + i < p.v) ? obase[(long long)(cg * 16 + i) * p.ldout] : 0.f;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (cg * 16 + i < p.v) obase[(long long)(cg * 16 + i) * p.ldout] = vals[i] + oldv[i];
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    } else if (SPLIT && warp >= 7) {
+        // ===================================================== operand split: activations per tile, matrices per sample
+        const int tids = threadIdx.x - 7 * 32;
+        int sa = 0; uint32_t pa = 0;
+        int sl = 0; uint32_t pl = 0;
+        int m = -1;
+        int cur = -1;
+        for (long long tile = tile_begin; tile < tile_end; ++tile) {
+            const int n = (int)(tile / p.tiles_per_sample);
+            if (n != cur) {
+                cur = n;
+                ++m;
+                const int sb = m & 1;
+                mbar_wait(b_full(sb), (uint32_t)(m >> 1) & 1u);
+                // the lo slot of this matrix slot is free once the matrix slot itself was released (b_empty), which the matrix
+                // producer already waited for before refilling it
+                transform_split4(b_ring + (uint32_t)sb * kMatBytes, b_lo + (uint32_t)sb * kMatBytes, kMatBytes, tids, kSplitWarps * 32);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(b_lo_bar(sb));
+            }
+            mbar_wait(a_full(sa), pa);
+            mbar_wait(lo_empty(sl), pl ^ 1u);
+            transform_split4(smem_base + (uint32_t)sa * p.a_tile, lo_ring + (uint32_t)sl * p.a_tile, p.a_tile, tids, kSplitWarps * 32);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_lo(sa));
+            if (++sa == p.na) { sa = 0; pa ^= 1u; }
+            if (++sl == p.nlo) { sl = 0; pl ^= 1u; }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kCols) : "memory");
+    }
+}
+
+}  // namespace mtc
+}  // namespace agcn
+
+using namespace agcn;
+
+size_t agcn_joint_mix_tc_workspace_bytes(int nb) { return (size_t)nb * 3 * 1024 * sizeof(float); }
+
+// Returns AGCN_ERR_UNSUPPORTED for shapes / modes outside this path (the caller then runs the FFMA kernel).
+// gp: nb*3*1024 floats of scratch for the padded matrices.
+int agcn_joint_mix_tc(const float* in, const float* mats, float* out, float* gp,
+                      int nb, int t, int v, int ldin, int ldout, int width, int mode, int accumulate, int split, void* stream) {
+    using namespace agcn::tc;
+    using namespace agcn::mtc;
+    static const bool disabled = getenv("AGCN_MIX_SIMT") != nullptr;
+    if (disabled) return AGCN_ERR_UNSUPPORTED;
+    if (mode != AGCN_MIX_AGG_FWD && mode != AGCN_MIX_AGG_BWD) return AGCN_ERR_UNSUPPORTED;
+    if (v > 32 || width % 32 || !aligned16(in) || !aligned16(out) || gp == nullptr || !aligned16(gp)) return AGCN_ERR_UNSUPPORTED;
+    if (mode == AGCN_MIX_AGG_FWD && accumulate) return AGCN_ERR_UNSUPPORTED;
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return fail(AGCN_ERR_CUDA, "agcn_joint_mix_tc: cuTensorMapEncodeTiled is not available from the driver");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MArgs p;
+    p.out = out; p.nb = nb; p.t = t; p.v = v; p.width = width; p.bwd = mode == AGCN_MIX_AGG_BWD ? 1 : 0; p.accumulate = accumulate;
+    p.ncb = width / 32;
+    p.tiles_per_sample = (t * p.ncb + 3) / 4;
+    p.total_tiles = (long long)nb * p.tiles_per_sample;
+    p.kb = p.bwd ? 3 : 1;
+    p.ncols = p.bwd ? 32 : 96;
+    p.a_tile = (uint32_t)p.kb * 4u * kBoxBytes;
+    p.ldout = ldout;
+    const uint32_t fixed = 2u * kMatBytes * (split ? 2u : 1u) + kBarBytes + 1024u;
+    const uint32_t budget = 220u * 1024u - fixed;
+    p.nlo = split ? 2 : 0;
+    int na = (int)((budget - (uint32_t)p.nlo * p.a_tile) / p.a_tile);
+    if (split && na < 2) { p.nlo = 1; na = (int)((budget - p.a_tile) / p.a_tile); }
+    if (na > kMaxA) na = kMaxA;
+    if (na < 1) return AGCN_ERR_UNSUPPORTED;
+    p.na = na;
+    const size_t smem = (size_t)(p.na + p.nlo) * p.a_tile + fixed;
+
+    pad_mats_kernel<<<ceil_div((long long)nb * 3 * 1024, 256), 256, 0, st>>>(mats, gp, nb, v, p.bwd);
+    int rc = check_launch("agcn_joint_mix_tc(pad)");
+    if (rc) return rc;
+
+    CUtensorMap map_a, map_b;
+    {
+        // activations: dims (c, v, t, n); box 32 channels x 32 joint rows (rows >= v are out of bounds -> zeros) x 1 x 1
+        cuuint64_t dims[4] = {(cuuint64_t)ldin, (cuuint64_t)v, (cuuint64_t)t, (cuuint64_t)nb};
+        cuuint64_t strides[3] = {(cuuint64_t)ldin * 4, (cuuint64_t)v * ldin * 4, (cuuint64_t)t * v * ldin * 4};
+        cuuint32_t box[4] = {32u, 32u, 1u, 1u};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(in), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(AGCN_ERR_CUDA, "agcn_joint_mix_tc: cuTensorMapEncodeTiled(in) failed with %d", (int)r);
+    }
+    {
+        // padded matrices: dims (32, 32, 3, n); one box = the three 32 x 32 blocks of a sample
+        cuuint64_t dims[4] = {32u, 32u, 3u, (cuuint64_t)nb};
+        cuuint64_t strides[3] = {128u, 4096u, 12288u};
+        cuuint32_t box[4] = {32u, 32u, 3u, 1u};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, gp, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(AGCN_ERR_CUDA, "agcn_joint_mix_tc: cuTensorMapEncodeTiled(mats) failed with %d", (int)r);
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(mix_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(mix_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        if (e != cudaSuccess) return fail(AGCN_ERR_CUDA, "agcn_joint_mix_tc: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const long long grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
+    if (split) mix_tc_kernel<true><<<(unsigned)grid, kThreadsMSplit, smem, st>>>(map_a, map_b, p);
+    else mix_tc_kernel<false><<<(unsigned)grid, kThreadsM, smem, st>>>(map_a, map_b, p);
+    return check_launch("agcn_joint_mix_tc");
+}

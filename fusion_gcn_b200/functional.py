@@ -80,7 +80,7 @@ def gcn_forward(x, adj_a, adj_b, wa, ba, wb, bb, wd, bd, bn_w, bn_b, down_w, dow
     s_part = K.joint_gram(e, e, groups=3, offa=0, stridea=2 * ci, offb=ci, strideb=2 * ci, width=ci, nchunk=nchunk, precision=prec)
     scale = 1.0 / float(ci * t)
     p, g = K.attention_fwd(s_part, adj_a.contiguous(), adj_b.contiguous(), scale)
-    z = K.joint_mix(x, g, width=cin, mode=K.MIX_AGG_FWD)                               # [nb,t,v,3*cin]
+    z = K.joint_mix(x, g, width=cin, mode=K.MIX_AGG_FWD, precision=prec)                               # [nb,t,v,3*cin]
     y = K.conv_fwd(z, wdc, bdc, precision=prec)
     sc, sh, mean, invstd = _bn_forward(y, bn_w, bn_b, spec.bn_gcn, spec.training)
     if spec.has_down:
@@ -128,7 +128,7 @@ def gcn_backward(d_o, ctx, bn_w, dbn_w, down_w, spec: UnitSpec, dx=None, need_dx
                            precision=prec)
     ds, d_adj_b = K.attention_bwd(dg_part, p, ctx["scale"])
     if need_dx:
-        dx = K.joint_mix(dz, g, width=cin, mode=K.MIX_AGG_BWD, out=dx, accumulate=have)
+        dx = K.joint_mix(dz, g, width=cin, mode=K.MIX_AGG_BWD, out=dx, accumulate=have, precision=prec)
         have = True
     de = K.joint_mix(e, ds, width=ci, mode=K.MIX_SCORE_BWD)
     d_wab, d_bab = K.conv_wgrad(de, x, precision=prec)

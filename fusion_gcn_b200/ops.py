@@ -177,7 +177,7 @@ def attention_bwd(dg_part, p, scale: float) -> Tuple[torch.Tensor, torch.Tensor]
     return ds, dadj_b
 
 
-def joint_mix(inp, mats, *, width, mode, out=None, accumulate=False):
+def joint_mix(inp, mats, *, width, mode, out=None, accumulate=False, precision=PREC_FP32):
     nb, t, v, ldin = inp.shape
     ldout = {MIX_AGG_FWD: 3 * width, MIX_AGG_BWD: width, MIX_SCORE_BWD: 6 * width}[mode]
     if out is None:
@@ -186,7 +186,10 @@ def joint_mix(inp, mats, *, width, mode, out=None, accumulate=False):
         out = torch.empty((nb, t, v, ldout), device=inp.device, dtype=torch.float32)
     _check(inp, mats, out)
     terms = {MIX_AGG_FWD: 3, MIX_AGG_BWD: 3, MIX_SCORE_BWD: 6}[mode]
-    _call("agcn_joint_mix", _ptr(inp), _ptr(mats), _ptr(out), nb, t, v, ldin, ldout, width, mode, int(accumulate), _stream(),
+    ws_bytes = capi.lib().agcn_joint_mix_workspace_bytes(nb) if (mode != MIX_SCORE_BWD and precision != PREC_FP32_FFMA) else 0
+    ws = torch.empty((ws_bytes + 3) // 4, device=inp.device, dtype=torch.float32) if ws_bytes else None
+    _call("agcn_joint_mix", _ptr(inp), _ptr(mats), _ptr(out), nb, t, v, ldin, ldout, width, mode, int(accumulate), precision,
+          _ptr(ws), ws_bytes, _stream(),
           sig=(nb, t, v, ldin, ldout, width, mode, int(accumulate)),
           work=(2.0 * nb * t * terms * v * v * width, 4.0 * (inp.numel() + out.numel() * (2 if accumulate else 1))))
     return out

@@ -116,9 +116,14 @@ int agcn_attention_bwd(const float* dg_part, const float* p, float* dg_sum, floa
                        int nb, int nchunk, int groups, int v, float scale, void* stream);
 
 /* Per-sample mixing over the joint axis, see agcn_mix_mode.  in: [nb][t][v][ldin], out: [nb][t][v][ldout],
- * mats: [nb][3][v][v], width = channels per group.  V <= 32.                                            */
+ * mats: [nb][3][v][v], width = channels per group.  V <= 32.
+ * precision: AGCN_PREC_FP32 / AGCN_PREC_TF32 run AGCN_MIX_AGG_FWD / AGCN_MIX_AGG_BWD on the tensor cores (3xTF32 / single-pass
+ * TF32) when width is a multiple of 32 and the workspace holds agcn_joint_mix_workspace_bytes(nb) bytes (zero-padded copies
+ * of the matrices); every other case and AGCN_PREC_FP32_FFMA use the FFMA kernel (workspace may then be NULL).              */
+size_t agcn_joint_mix_workspace_bytes(int nb);
 int agcn_joint_mix(const float* in, const float* mats, float* out,
-                   int nb, int t, int v, int ldin, int ldout, int width, int mode, int accumulate, void* stream);
+                   int nb, int t, int v, int ldin, int ldout, int width, int mode, int accumulate,
+                   int precision, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- BatchNorm (training-mode batch statistics; nn.BatchNorm2d/1d at agcn.py:44,78,83,150) ----------
  * The tensor is addressed as x[outer][inner][c] with element offset outer*outer_stride + inner*c_total...

@@ -100,7 +100,7 @@ def attention_bwd(dg_part, p, scale):
     return ds.contiguous(), dg.sum(dim=0).contiguous()
 
 
-def joint_mix(inp, mats, *, width, mode, out=None, accumulate=False):
+def joint_mix(inp, mats, *, width, mode, out=None, accumulate=False, precision=0):
     nb, t, v, _ = inp.shape
     w = width
     if mode == MIX_AGG_FWD:
@@ -239,6 +239,11 @@ class Tf32Emulation:
         if precision == PREC_TF32 and on_tc:
             a, b = _trunc_tf32(a), _trunc_tf32(b)
         return joint_gram(a, b, **kw)
+
+    def joint_mix(self, inp, mats, *, width, mode, precision=PREC_FP32, **kw):
+        if precision == PREC_TF32 and mode in (MIX_AGG_FWD, MIX_AGG_BWD) and width % 32 == 0:
+            inp, mats = _trunc_tf32(inp), _trunc_tf32(mats)
+        return joint_mix(inp, mats, width=width, mode=mode, **kw)
 
     def conv_wgrad(self, dy, x, *, precision=PREC_FP32, **kw):
         _, db = conv_wgrad(dy, x, **kw)

@@ -122,21 +122,39 @@ def test_attention_fwd_bwd(K, nb, v, nchunk):
     assert rel_err(ds_ref.unsqueeze(1).expand_as(spd.grad), spd.grad) <= 1e-6      # p was rounded to fp32 for the kernel
 
 
-@pytest.mark.parametrize("nb,t,v,w", [(2, 9, 25, 64), (2, 5, 20, 3), (1, 4, 22, 256), (3, 7, 5, 8), (2, 3, 18, 9), (1, 11, 25, 16)])
-def test_joint_mix_modes(K, nb, t, v, w):
+@pytest.mark.parametrize("mode", ["ffma", "fp32"])
+@pytest.mark.parametrize("nb,t,v,w", [(2, 9, 25, 64), (2, 5, 20, 3), (1, 4, 22, 256), (3, 7, 5, 8), (2, 3, 18, 9), (1, 11, 25, 16),
+                                      (3, 13, 25, 32), (2, 301, 25, 64), (5, 6, 20, 128), (2, 7, 32, 96)])
+def test_joint_mix_modes(K, nb, t, v, w, mode):
+    """mode 'ffma' = the FFMA kernel; 'fp32' = AGCN_PREC_FP32, which runs AGG_FWD / AGG_BWD as 3xTF32 tcgen05 MMAs when the
+    width is a multiple of 32 (1e-5) and on the FFMA kernel otherwise."""
+    prec, tol = (K.PREC_FP32_FFMA, 2e-6) if mode == "ffma" else (K.PREC_FP32, 1e-5)
     mats = rnd(nb, 3, v, v, seed=1)
     x = rnd(nb, t, v, w)
-    z, z_ref = both("joint_mix", K, (x, mats), width=w, mode=S.MIX_AGG_FWD)
-    assert rel_err(z, z_ref) <= 2e-6
+    z, z_ref = both("joint_mix", K, (x, mats), width=w, mode=S.MIX_AGG_FWD, precision=prec)
+    assert rel_err(z, z_ref) <= tol
     dz = rnd(nb, t, v, 3 * w, seed=2)
-    dx, dx_ref = both("joint_mix", K, (dz, mats), width=w, mode=S.MIX_AGG_BWD)
-    assert rel_err(dx, dx_ref) <= 2e-6
+    dx, dx_ref = both("joint_mix", K, (dz, mats), width=w, mode=S.MIX_AGG_BWD, precision=prec)
+    assert rel_err(dx, dx_ref) <= tol
     base = rnd(nb, t, v, w, seed=3)
-    acc = K.joint_mix(dz.cuda(), mats.cuda(), width=w, mode=K.MIX_AGG_BWD, out=base.cuda().clone(), accumulate=True)
-    assert rel_err(acc, dx_ref + base.double()) <= 2e-6
+    acc = K.joint_mix(dz.cuda(), mats.cuda(), width=w, mode=K.MIX_AGG_BWD, out=base.cuda().clone(), accumulate=True, precision=prec)
+    assert rel_err(acc, dx_ref + base.double()) <= tol
     e = rnd(nb, t, v, 6 * w, seed=4)
-    de, de_ref = both("joint_mix", K, (e, mats), width=w, mode=S.MIX_SCORE_BWD)
+    de, de_ref = both("joint_mix", K, (e, mats), width=w, mode=S.MIX_SCORE_BWD, precision=prec)
     assert rel_err(de, de_ref) <= 2e-6
+
+
+@pytest.mark.parametrize("nb,t,v,w", [(2, 9, 25, 64), (3, 13, 20, 32), (1, 40, 22, 128)])
+def test_joint_mix_tf32_mode(K, nb, t, v, w):
+    """AGCN_PREC_TF32: the tensor-core mix sees TF32-truncated operands (1e-5 against that, 3e-3 against the raw operands)."""
+    mats = rnd(nb, 3, v, v, seed=1)
+    x = rnd(nb, t, v, w)
+    z = K.joint_mix(x.cuda(), mats.cuda(), width=w, mode=K.MIX_AGG_FWD, precision=K.PREC_TF32)
+    assert rel_err(z, S.joint_mix(_trunc_tf32(x).double(), _trunc_tf32(mats).double(), width=w, mode=S.MIX_AGG_FWD)) <= 1e-5
+    assert rel_err(z, S.joint_mix(x.double(), mats.double(), width=w, mode=S.MIX_AGG_FWD)) <= 3e-3
+    dz = rnd(nb, t, v, 3 * w, seed=2)
+    dx = K.joint_mix(dz.cuda(), mats.cuda(), width=w, mode=K.MIX_AGG_BWD, precision=K.PREC_TF32)
+    assert rel_err(dx, S.joint_mix(_trunc_tf32(dz).double(), _trunc_tf32(mats).double(), width=w, mode=S.MIX_AGG_BWD)) <= 1e-5
 
 
 @pytest.mark.parametrize("rows,c", [(1000, 64), (777, 3), (4099, 256), (300, 515), (50, 12), (9000, 128), (64, 8)])

@@ -65,12 +65,12 @@ def main():
         if want(f"mix_fwd_{tag}") or want(f"mix_bwd_{tag}"):
             g = torch.randn(NB, 3, V, V, device=dev)
             if want(f"mix_fwd_{tag}"):
-                ms = timeit(lambda: K.joint_mix(x, g, width=c, mode=K.MIX_AGG_FWD), once)
+                ms = timeit(lambda: K.joint_mix(x, g, width=c, mode=K.MIX_AGG_FWD, precision=prec), once)
                 report(f"mix_fwd_{tag}", ms, act * 4, 3 * 2.0 * rows * V * c)
             if want(f"mix_bwd_{tag}"):
                 dz = torch.randn(NB, t, V, 3 * c, device=dev)
                 dx = torch.randn(NB, t, V, c, device=dev)
-                ms = timeit(lambda: K.joint_mix(dz, g, width=c, mode=K.MIX_AGG_BWD, out=dx, accumulate=True), once)
+                ms = timeit(lambda: K.joint_mix(dz, g, width=c, mode=K.MIX_AGG_BWD, out=dx, accumulate=True, precision=prec), once)
                 report(f"mix_bwd_{tag}", ms, act * 5, 3 * 2.0 * rows * V * c)
                 del dz, dx
         if want(f"mix_score_bwd_{tag}"):

@@ -1,0 +1,11 @@
+#!/bin/bash
+tag=${1:-mc}
+mkdir -p gpurun_out
+timeout 1200 python tools/tc_debug.py k32 k64 multi_tile taps9 n256 n96_k16 v20_acc v22 stride2 res_stride2 dgrad_s1 dgrad_s2 wide_k big big256 > gpurun_out/${tag}_tc_debug.log 2>&1; cat gpurun_out/${tag}_tc_debug.log
+if grep -q "TIMEOUT\|FAILED" gpurun_out/${tag}_tc_debug.log; then echo "tc_debug found hangs/failures: stopping"; exit 0; fi
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 > gpurun_out/${tag}_pytest.log; tail -3 gpurun_out/${tag}_pytest.log
+timeout 600 python tools/bench_stage.py conv > gpurun_out/${tag}_stage_fp32.log 2>&1; cat gpurun_out/${tag}_stage_fp32.log
+AGCN_NO_MCAST=1 timeout 600 python tools/bench_stage.py conv_proj_c64 conv_tconv > gpurun_out/${tag}_stage_fp32_nomc.log 2>&1; cat gpurun_out/${tag}_stage_fp32_nomc.log
+timeout 600 python tools/bench_stage.py conv --tf32 > gpurun_out/${tag}_stage_tf32.log 2>&1; cat gpurun_out/${tag}_stage_tf32.log
+python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_bench_fp32.json 2>gpurun_out/${tag}_bench_fp32.err; python tools/show_bench.py gpurun_out/${tag}_bench_fp32.json
+python bench.py --steps 5 --warmup 3 --no-cpu-baseline --precision tf32 > gpurun_out/${tag}_bench_tf32.json 2>gpurun_out/${tag}_bench_tf32.err; python tools/show_bench.py gpurun_out/${tag}_bench_tf32.json
