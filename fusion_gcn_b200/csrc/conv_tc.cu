@@ -308,6 +308,8 @@ struct WgArgs {
     int pair;          // 1: a tile is two consecutive taps stacked along M (cout <= 64): lanes 0..63 = tap 2j, lanes 64..127 = tap 2j+1
     int tap_tiles;     // taps, or ceil(taps / 2) in pair mode
     int seg_chunks;    // 3xTF32: row chunks per accumulator segment (promoted to fp32 registers in between)
+    int blocked;       // 1: tensor maps carry the 32-channel block as its own dimension: ONE TMA box per operand and stage
+    int nblk_a;        // blocked: dy channel blocks per box (<= 4; pair mode: 2, loaded twice)
     int dbg;           // bring-up only (env AGCN_WG_DEBUG): bit 0 skips the operand split, bit 1 skips the MMAs -> wrong results, timing probes
 };
 
@@ -368,16 +370,23 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
     const long long c_begin = (long long)split * a.chunks_per_split;
     long long c_end = c_begin + a.chunks_per_split;
     if (c_end > a.chunks_total) c_end = a.chunks_total;
-    // which of the 4 dy slots / nsub_b x slots receive a TMA box (bit j = slot j)
+    // which of the 4 dy slots / nsub_b x slots receive TMA data (bit j = slot j)
     uint32_t loaded = 0;
-    if (a.pair) {
+    int b_boxes;
+    if (a.blocked) {
+        // one box per operand (pair mode: two dy boxes); blocks past the tensor's channel extent arrive as zeros
+        loaded = (1u << a.nblk_a) - 1u;
+        if (a.pair && tap_b) loaded |= loaded << 2;
+        b_boxes = (int)nsub_b;
+    } else if (a.pair) {
         const int nb32 = (a.cout + 31) / 32;                             // <= 2
         for (int i = 0; i < nb32; ++i) { loaded |= 1u << i; if (tap_b) loaded |= 1u << (2 + i); }
+        b_boxes = (a.cin - k0 + 31) / 32 < (int)nsub_b ? (a.cin - k0 + 31) / 32 : (int)nsub_b;
     } else {
         const int a_boxes = (a.cout - m0 + 31) / 32 < 4 ? (a.cout - m0 + 31) / 32 : 4;
         loaded = (1u << a_boxes) - 1u;
+        b_boxes = (a.cin - k0 + 31) / 32 < (int)nsub_b ? (a.cin - k0 + 31) / 32 : (int)nsub_b;
     }
-    const int b_boxes = (a.cin - k0 + 31) / 32 < (int)nsub_b ? (a.cin - k0 + 31) / 32 : (int)nsub_b;
     loaded |= ((1u << b_boxes) - 1u) << 4;
     const uint32_t stage_tx = (uint32_t)__popc(loaded) * (uint32_t)a.rows_box * 128u;
 
@@ -393,6 +402,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
                 mbar_wait(empty_bar(stage), phase ^ 1u);
                 mbar_expect_tx(full_bar(stage), stage_tx);
                 const uint32_t sa = smem_base + (uint32_t)stage * raw_bytes;
+                if (a.blocked) {
+                    // dims (32 channels, flat row, channel block, sample): the box lands as [block][row][128 B], exactly the slot layout
+                    tma_load_4d(sa, &map_dy, full_bar(stage), 0, a1, a.pair ? 0 : m0 / 32, n);
+                    if (a.pair && tap_b) tma_load_4d(sa + 2u * sub_bytes, &map_dy, full_bar(stage), 0, a1 - a.v, 0, n);
+                    tma_load_4d(sa + 4u * sub_bytes, &map_x, full_bar(stage), 0, b1, k0 / 32, n);
+                    if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+                    continue;
+                }
                 if (a.pair) {
                     // slots 0,1: dy rows [a1, ..) for tap 2j; slots 2,3: the same channels V rows earlier for tap 2j+1
                     //   sum_k dy[k - V][co] * x[k + (tap - pad) V][ci] = sum_k' dy[k'][co] * x[k' + (tap + 1 - pad) V][ci]
@@ -556,9 +573,11 @@ static WgPlan plan_wgrad(int nb, int t_in, int t_out, int v, int cin, int cout, 
     a.n_tiles = (cin + a.n_tile - 1) / a.n_tile;
     a.m_tiles = (cout + 127) / 128;
     const int nsub = 4 + a.n_tile / 32;
-    // Rows per stage.  3xTF32: 24 KB of raw operands (+ 24 KB of lo residuals) so that four stages are in flight -- with
-    // two 96 KB stages the TMA latency of every stage was exposed (ncu, profiles/r1i).  TF32: 48 KB, four stages.
-    int rmax = ((split ? 24 : 48) * 1024) / (nsub * 128);
+    // Rows per stage.  Every stage costs ~1000-1400 cycles of fixed work (TMA issue, barrier hops, operand split, MMA issue;
+    // probes in profiles/r1v, r1w), so stages are as tall as shared memory allows: TF32 four stages of 48 KB; 3xTF32 three raw
+    // stages + two lo slots in 200 KB (40 KB each).
+    static const int split_kb = getenv("AGCN_WG_SPLIT_KB") ? atoi(getenv("AGCN_WG_SPLIT_KB")) : 40;
+    int rmax = ((split ? split_kb : 48) * 1024) / (nsub * 128);
     rmax = rmax / 8 * 8;
     if (rmax > 128) rmax = 128;
     if (rmax < 8) return p;
@@ -708,9 +727,19 @@ int agcn_conv_wgrad_tc(const float* dy, const float* x, float* ws, int* splits_o
     static const int dbg = getenv("AGCN_WG_DEBUG") ? atoi(getenv("AGCN_WG_DEBUG")) : 0;
     a.dbg = dbg;
     CUtensorMap map_dy, map_x;
+    static const bool no_blocked = getenv("AGCN_WG_NOBLOCK") != nullptr;
+    a.blocked = (!no_blocked && a.flat && cin % 32 == 0 && cout % 32 == 0) ? 1 : 0;
+    a.nblk_a = a.pair ? cout / 32 : ((cout + 31) / 32 < 4 ? (cout + 31) / 32 : 4);
     auto encode = [&](CUtensorMap* m, const float* ptr, int c, int t, int box1, int box2, int es2) -> CUresult {
         cuuint64_t dims[4]; cuuint64_t strides[3]; cuuint32_t box[4]; cuuint32_t estr[4] = {1, 1, 1, 1};
-        if (a.flat) {
+        if (a.blocked) {
+            // (32 channels, flat row, channel block, sample): the channel block is a dimension of its own (stride 128 B, smaller
+            // than the row stride), so ONE box covers all 32-channel blocks of the tile -- the per-box issue cost of the TMA
+            // producer thread (~180 cycles, profiles/r1v) was the floor of this kernel
+            dims[0] = 32; dims[1] = (cuuint64_t)t * v; dims[2] = (cuuint64_t)c / 32; dims[3] = nb;
+            strides[0] = (cuuint64_t)c * 4; strides[1] = 128; strides[2] = (cuuint64_t)t * v * c * 4;
+            box[0] = 32; box[1] = box1; box[2] = (cuuint32_t)box2; box[3] = 1;
+        } else if (a.flat) {
             dims[0] = c; dims[1] = (cuuint64_t)t * v; dims[2] = 1; dims[3] = nb;
             strides[0] = (cuuint64_t)c * 4; strides[1] = (cuuint64_t)t * v * c * 4; strides[2] = (cuuint64_t)t * v * c * 4;
             box[0] = 32; box[1] = box1; box[2] = 1; box[3] = 1;
@@ -724,10 +753,14 @@ int agcn_conv_wgrad_tc(const float* dy, const float* x, float* ws, int* splits_o
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     };
-    CUresult r = encode(&map_dy, dy, cout, t_out, a.rows_box, a.tt, 1);
-    if (r != CUDA_SUCCESS) return fail(AGCN_ERR_CUDA, "agcn_conv_wgrad_tc: cuTensorMapEncodeTiled(dy) failed with %d", (int)r);
-    r = encode(&map_x, x, cin, t_in, a.rows_box, a.tt * stride, stride);
-    if (r != CUDA_SUCCESS) return fail(AGCN_ERR_CUDA, "agcn_conv_wgrad_tc: cuTensorMapEncodeTiled(x) failed with %d", (int)r);
+    CUresult r = encode(&map_dy, dy, cout, t_out, a.rows_box, a.blocked ? a.nblk_a : a.tt, 1);
+    if (r == CUDA_SUCCESS) r = encode(&map_x, x, cin, t_in, a.rows_box, a.blocked ? a.n_tile / 32 : a.tt * stride, stride);
+    if (r != CUDA_SUCCESS && a.blocked) {          // driver refused the blocked maps: fall back to one box per 32-channel block
+        a.blocked = 0;
+        r = encode(&map_dy, dy, cout, t_out, a.rows_box, a.tt, 1);
+        if (r == CUDA_SUCCESS) r = encode(&map_x, x, cin, t_in, a.rows_box, a.tt * stride, stride);
+    }
+    if (r != CUDA_SUCCESS) return fail(AGCN_ERR_CUDA, "agcn_conv_wgrad_tc: cuTensorMapEncodeTiled failed with %d", (int)r);
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);

@@ -10,10 +10,11 @@ constexpr int kKChunk = 32;       // fp32 elements per 128-byte swizzle row
 constexpr int kTmemCols = 256;
 constexpr int kSegment = 4;       // 3xTF32: promote the TMEM accumulator to fp32 registers every 4 (tap, k-chunk) steps (K = 128)
 
+// round-to-nearest (ties away) to the 10-bit TF32 mantissa, i.e. what cvt.rna.tf32.f32 returns -- done with two full-rate
+// integer instructions (add half an ulp, clear the low 13 bits) because the conversion pipe runs at a quarter of that rate and
+// was a measurable share of the operand-split warps' time (profiles/r1y)
 __device__ __forceinline__ float tf32_rna(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
     float4 v;
