@@ -167,6 +167,35 @@ def run_ours(args):
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
+    # ---- the same step replayed as ONE CUDA graph (fusion_gcn_b200/graphed.py): device-resident and end to end
+    ms_graph = ms_graph_e2e = 0.0
+    graph_info = None
+    if world == 1 and not args.no_graph:
+        try:
+            from fusion_gcn_b200.graphed import GraphedStep
+            gs = GraphedStep(model, loss_fn, x_dev, y_dev, warmup=1)
+            for _ in range(args.warmup):
+                gs()
+            barrier()
+            h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            h0.record()
+            for _ in range(args.steps):
+                gs()
+            h1.record()
+            barrier()
+            ms_graph = h0.elapsed_time(h1)
+            h0.record()
+            for _ in range(args.steps):
+                graph_loss = gs(x_host, y_host).item()
+            h1.record()
+            barrier()
+            ms_graph_e2e = h0.elapsed_time(h1)
+            graph_info = {"launches_per_replay": gs.launches_per_replay, "last_loss": round(graph_loss, 5)}
+            del gs
+        except Exception as exc:                     # noqa: BLE001 -- reported in the JSON line, the eager numbers stand
+            graph_info = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        model.zero_grad(set_to_none=True)
+        torch.cuda.empty_cache()
     # ---- the separately reported TF32 mode (single-pass tensor cores, own tolerance), device-resident, same step
     ms_tf32 = 0.0
     if args.precision == "fp32" and not args.no_tf32:
@@ -196,7 +225,7 @@ def run_ours(args):
     value = n_global * args.steps / (ms / 1e3)
     e2e_value = n_global * args.steps / (ms_e2e / 1e3)
     # dominant kernel: the C-ABI launch signature with the largest summed device time (CUDA events around every call)
-    roof, top = None, []
+    roof, top, families = None, [], {}
     if timings:
         traffic_db = {}
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
@@ -215,6 +244,13 @@ def run_ours(args):
 
         ranked = sorted(timings.items(), key=lambda kv: -kv[1][0])
         top = [describe(k, v) for k, v in ranked[:6]]
+        for (name, _sig), (tot_ms, cnt, _f, _b) in ranked:        # share of the step per C-ABI entry point (all signatures)
+            fam = families.setdefault(name, [0.0, 0])
+            fam[0] += tot_ms
+            fam[1] += cnt
+        if args.dump_kernels:
+            with open(args.dump_kernels, "w") as fh:
+                json.dump([describe(k, v) for k, v in ranked], fh, indent=0)
         d = top[0]
         hbm_bound = d["frac_hbm"] >= d["frac_tensor"]
         roof = {"bound": "hbm" if hbm_bound else "tensor", "achieved": d["gbs"] if hbm_bound else d["tflops"],
@@ -241,10 +277,17 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": roof,
         "top_kernels": top,
+        "entry_point_shares": {k: {"share_of_step": round(v[0] / ms, 4), "launches_per_step": round(v[1] / args.steps, 1)}
+                               for k, v in sorted(families.items(), key=lambda kv: -kv[1][0])},
         "tf32_mode": None if ms_tf32 <= 0 else {
             "value": round(n_global * args.steps / (ms_tf32 / 1e3), 2), "unit": "sequences/s", "ms_per_step": round(ms_tf32 / args.steps, 3),
             "note": "AGCN_PREC_TF32 (single-pass tcgen05 kind::tf32, operands truncated to TF32), reported separately from the fp32 parity "
                     "mode; tolerance: logits within 3e-2 of the fp64 oracle (tests/test_gpu_unit.py::test_tf32_mode_model_logits)"},
+        "graph_mode": None if graph_info is None else dict(graph_info, **({} if ms_graph <= 0 else {
+            "value": round(n_global * args.steps / (ms_graph / 1e3), 2), "e2e_value": round(n_global * args.steps / (ms_graph_e2e / 1e3), 2),
+            "unit": "sequences/s", "ms_per_step": round(ms_graph / args.steps, 3),
+            "note": "same fp32 step (zero-grad + fwd + CE + bwd) captured once and replayed as one CUDA graph; e2e_value copies the "
+                    "batch from pinned host memory into the graph's static input and reads the loss back every step"})),
         "model_roofline": {"hbm_seq_s": round(pk["hbm_gbs"] * 1e3 / mbytes, 1), "achieved_frac_of_hbm_ceiling": round(value / world / (pk["hbm_gbs"] * 1e3 / mbytes), 4),
                            "algorithmic_gflop_per_seq": gflop, "algorithmic_mb_per_seq": mbytes,
                            "achieved_tflops": round(value * gflop / 1e3, 2), "achieved_gbs": round(value / world * mbytes / 1e3, 1)},
@@ -254,6 +297,103 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_infer(args):
+    """BASELINE config 5: forward only, eval mode, torch.no_grad(), large batch, replicas without communication."""
+    import torch.distributed as dist
+    from fusion_gcn_b200 import capi, ops
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch N>1 with torch.distributed.run")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    m, t, v, c, ncls, _ = WORKLOADS[args.workload]
+    n_local, micro = args.batch, min(args.batch, args.micro_batch)
+    model = build_model(args.workload, args.precision, dev).eval()
+    gen = torch.Generator().manual_seed(1234 + rank)
+    x_host = torch.randn(n_local, m, t, v, c, generator=gen).pin_memory()
+    x_dev = x_host.to(dev)
+
+    def step(x):
+        with torch.no_grad():
+            return torch.cat([model(x[i:i + micro]) for i in range(0, n_local, micro)])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(x_dev)
+    ops.start_timing(("*",))
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    l0 = capi.lib().agcn_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(x_dev)
+    e1.record()
+    barrier()
+    launches = capi.lib().agcn_launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    timings = ops.stop_timing()
+    ms = e0.elapsed_time(e1)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        pred = step(x_host.to(dev, non_blocking=True)).argmax(1).cpu()
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    t_all = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    ms, ms_e2e = float(t_all[0]), float(t_all[1])
+    pk = peaks()
+    n_global = n_local * world
+    value = n_global * args.steps / (ms / 1e3)
+    gflop, mbytes = WORK[args.workload][0] / 3.0, WORK[args.workload][1] / 3.0      # forward = a third of fwd+bwd (SURVEY Appendix B)
+    fam = {}
+    for (name, _sig), (tot_ms, cnt, _f, _b) in timings.items():
+        e = fam.setdefault(name, [0.0, 0]); e[0] += tot_ms; e[1] += cnt
+    (kname, ksig), (ktot, kcnt, kflops, kbytes) = max(timings.items(), key=lambda kv: kv[1][0])
+    avg_s = ktot / kcnt / 1e3
+    tensor_peak = pk["bf16_tflops_sustained"] or pk["bf16_tflops"]
+    f_h, f_t = kbytes / avg_s / 1e9 / pk["hbm_gbs"], kflops / avg_s / 1e12 / tensor_peak
+    hbm_bound = f_h >= f_t
+    line = {
+        "metric": "AGCN forward sequences/sec (inference sweep, BASELINE config 5)", "value": round(value, 2), "unit": "sequences/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "tf32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: AGCN 10 units, forward only, eval mode, no_grad, N={n_local}/GPU (micro-batches of {micro}), "
+                               f"M={m}, T={t}, V={v}, C={c}, {ncls} classes, random init", "precision_mode": args.precision,
+                   "l2_policy": "activations per step (GBs) exceed the 126 MB L2; no explicit flush",
+                   "parallelism": "replicas only, no communication" if world > 1 else "single GPU"},
+        "e2e": {"value": round(n_global * args.steps / (ms_e2e / 1e3), 2), "unit": "sequences/s", "h2d_bytes_per_step": x_host.numel() * 4,
+                "d2h_bytes_per_step": n_local * 8, "ms_per_step": round(ms_e2e / args.steps, 3), "last_pred0": int(pred[0])},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {"bound": "hbm" if hbm_bound else "tensor", "achieved": round(kbytes / avg_s / 1e9 if hbm_bound else kflops / avg_s / 1e12, 2),
+                     "peak": pk["hbm_gbs"] if hbm_bound else tensor_peak, "unit": "GB/s" if hbm_bound else "TFLOP/s",
+                     "frac": round(f_h if hbm_bound else f_t, 4), "traffic": None, "kernel": f"{kname}{list(ksig)}",
+                     "avg_launch_ms": round(avg_s * 1e3, 4), "share_of_step": round(ktot / ms, 4), "peak_source": pk["source"]},
+        "entry_point_shares": {k: {"share_of_step": round(v_[0] / ms, 4), "launches_per_step": round(v_[1] / args.steps, 1)}
+                               for k, v_ in sorted(fam.items(), key=lambda kv: -kv[1][0])},
+        "model_roofline": {"hbm_seq_s": round(pk["hbm_gbs"] * 1e3 / mbytes, 1), "achieved_frac_of_hbm_ceiling": round(value / world / (pk["hbm_gbs"] * 1e3 / mbytes), 4),
+                           "algorithmic_gflop_per_seq": round(gflop, 2), "algorithmic_mb_per_seq": round(mbytes, 1)},
+    }
+    print(json.dumps(line), flush=True)
 
 
 def cpu_reference(workload, steps, warmup, n=None):
@@ -311,15 +451,23 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="ntu", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=64, help="sequences per GPU")
+    ap.add_argument("--batch", type=int, default=None, help="sequences per GPU (default 64; 256 for --mode infer)")
+    ap.add_argument("--mode", default="train", choices=["train", "infer"], help="train: fwd+CE+bwd (the BASELINE metric); infer: forward only, eval mode")
+    ap.add_argument("--micro-batch", type=int, default=512, help="--mode infer: sequences per forward call")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-kernels", default=None, help="write the per-signature timing table (all C-ABI launches) to this JSON file")
+    ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay timing")
     ap.add_argument("--no-tf32", action="store_true", help="skip the extra TF32-mode timing that the fp32 run reports beside the headline")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
+    if args.batch is None:
+        args.batch = 256 if args.mode == "infer" else 64
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "infer":
+        run_infer(args)
     else:
         run_ours(args)
 

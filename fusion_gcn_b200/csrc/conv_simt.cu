@@ -4,6 +4,7 @@
 // Channels-last activations, rows = (nb, t, v).  Reference arithmetic: nn.Conv2d at
 // torch_src/models/mmargcn/agcn.py:41-42,71-73,77 and its autograd backward.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace agcn {
 
@@ -388,6 +389,84 @@ __global__ void __launch_bounds__(256) wgrad_skinny_kernel(const float* __restri
     }
 }
 
+// Vectorised variant for cout % 4 == 0: a thread owns FOUR consecutive output channels of one row lane, so every dy access is a
+// 16-byte load, and four rows are fetched before the dependent FMAs (the scalar one-load-per-iteration loop above left the
+// first unit's weight gradients at ~0.8 TB/s, profiles/r2a).  CMAX = register bound on cin (4 or 16).
+// part: [gridDim.x][cout][cin], bpart: [gridDim.x][cout] (may be null).  Shared: xs[128][cin] | red[lanes][cout][CMAX + 1].
+template <int CMAX>
+__global__ void __launch_bounds__(256) wgrad_skinny4_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                            float* __restrict__ part, float* __restrict__ bpart,
+                                                            long long rows, int cin, int cout) {
+    extern __shared__ __align__(16) float sm[];
+    float* xs = sm;                                  // [128][cin]
+    float* red = xs + kSkinnyRows * 16;              // [lanes][cout][CMAX + 1]
+    const int tid = threadIdx.x;
+    const int cq = cout >> 2;
+    const int lanes = 256 / cq;
+    const int q = tid % cq, rl = tid / cq;
+    const bool on = rl < lanes;
+    float acc[4][CMAX], bsum[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        bsum[c] = 0.f;
+#pragma unroll
+        for (int i = 0; i < CMAX; ++i) acc[c][i] = 0.f;
+    }
+    const long long per = ((rows + gridDim.x - 1) / gridDim.x + kSkinnyRows - 1) / kSkinnyRows * kSkinnyRows;
+    const long long rb = (long long)blockIdx.x * per;
+    long long re = rb + per; if (re > rows) re = rows;
+    for (long long r0 = rb; r0 < re; r0 += kSkinnyRows) {
+        const int rn = (re - r0) < kSkinnyRows ? (int)(re - r0) : kSkinnyRows;
+        __syncthreads();
+        for (int i = tid; i < rn * cin; i += 256) xs[i] = __ldg(x + r0 * cin + i);
+        __syncthreads();
+        if (on) {
+            const float4* src = reinterpret_cast<const float4*>(dy + r0 * cout) + q;
+            for (int r = rl; r < rn; r += 4 * lanes) {
+                float4 d[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int rr = r + j * lanes;
+                    d[j] = rr < rn ? __ldg(src + (long long)rr * cq) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int rr = r + j * lanes;
+                    if (rr < rn) {
+                        bsum[0] += d[j].x; bsum[1] += d[j].y; bsum[2] += d[j].z; bsum[3] += d[j].w;
+#pragma unroll
+                        for (int i = 0; i < CMAX; ++i)
+                            if (i < cin) {
+                                const float xv = xs[rr * cin + i];
+                                acc[0][i] = fmaf(d[j].x, xv, acc[0][i]); acc[1][i] = fmaf(d[j].y, xv, acc[1][i]);
+                                acc[2][i] = fmaf(d[j].z, xv, acc[2][i]); acc[3][i] = fmaf(d[j].w, xv, acc[3][i]);
+                            }
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    constexpr int LD = CMAX + 1;
+    if (on) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float* dst = red + ((long long)rl * cout + q * 4 + c) * LD;
+#pragma unroll
+            for (int i = 0; i < CMAX; ++i) dst[i] = acc[c][i];
+            dst[CMAX] = bsum[c];
+        }
+    }
+    __syncthreads();
+    for (int o = tid; o < cout * LD; o += 256) {
+        const int c = o / LD, i = o - c * LD;
+        float s = 0.f;
+        for (int l = 0; l < lanes; ++l) s += red[((long long)l * cout + c) * LD + i];
+        if (i < cin) part[((long long)blockIdx.x * cout + c) * cin + i] = s;
+        else if (i == CMAX && bpart != nullptr) bpart[(long long)blockIdx.x * cout + c] = s;
+    }
+}
+
 // column sums of dy for the bias gradient when the weight gradient runs on tensor cores: part[P][cout]
 __global__ void __launch_bounds__(256) bias_partial_kernel(const float* dy, long long rows, int cout, float* part) {
     __shared__ float sm[8][33];
@@ -560,7 +639,18 @@ extern "C" AGCN_API int agcn_conv_wgrad(const float* dy, const float* x, float* 
             float* bpart = dbias ? part + P * wsize : nullptr;
             const size_t smem = ((size_t)kSkinnyRows * 16 + (size_t)lanes * cpad * 17) * sizeof(float);
             cudaStream_t s = static_cast<cudaStream_t>(stream);
-            wgrad_skinny_kernel<<<(unsigned)P, 256, smem, s>>>(dy, x, part, bpart, rows, cin, cout, cpad);
+            static const bool scalar_only = getenv("AGCN_SKINNY_SCALAR") != nullptr;
+            const int cmax = cin <= 4 ? 4 : 16;
+            const size_t smem4 = ((size_t)kSkinnyRows * 16 + (size_t)(256 / (cout / 4 > 0 ? cout / 4 : 1)) * cout * (cmax + 1)) * sizeof(float);
+            if (!scalar_only && cout % 4 == 0 && cout >= 16 && aligned16(dy) && smem4 <= 100 * 1024) {
+                cudaError_t e = cmax == 4 ? cudaFuncSetAttribute(wgrad_skinny4_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)
+                                          : cudaFuncSetAttribute(wgrad_skinny4_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+                if (e != cudaSuccess) return fail(AGCN_ERR_CUDA, "agcn_conv_wgrad: %s", cudaGetErrorString(e));
+                if (cmax == 4) wgrad_skinny4_kernel<4><<<(unsigned)P, 256, smem4, s>>>(dy, x, part, bpart, rows, cin, cout);
+                else wgrad_skinny4_kernel<16><<<(unsigned)P, 256, smem4, s>>>(dy, x, part, bpart, rows, cin, cout);
+            } else {
+                wgrad_skinny_kernel<<<(unsigned)P, 256, smem, s>>>(dy, x, part, bpart, rows, cin, cout, cpad);
+            }
             int rc = check_launch("agcn_conv_wgrad(skinny)");
             if (rc) return rc;
             const long long total = wsize + (dbias ? cout : 0);

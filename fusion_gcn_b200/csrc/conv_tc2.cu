@@ -60,6 +60,7 @@ struct Tc2Args {
     int ntap[2];
     signed char tap_id[2][kMaxTaps], tap_blk[2][kMaxTaps], tap_off[2][kMaxTaps];
     int blk_t0[2][2];
+    int par_val[2];
 };
 
 template <bool SPLIT>
@@ -223,7 +224,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const int n = (int)(r / a.nparity);
             const int tl = row_local / a.v, vv = row_local - tl * a.v;
             const int j = jt * a.tt + tl;
-            const int to = a.transposed ? a.stride * j + par : j;
+            const int to = a.transposed ? a.stride * j + a.par_val[par] : j;
             const bool row_ok = (tl < a.tt) && (to < a.t_out);
             // element offset of this lane's output row (first column of the tile), -1 for rows outside the tensor
             const long long my_off = row_ok ? (((long long)n * a.t_out + to) * a.v + vv) * a.cout + (long long)nt * a.bn : -1;
@@ -339,10 +340,11 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
     using namespace agcn::tc2;
     static const bool disabled = getenv("AGCN_TC_V1") != nullptr;
     static const bool no_1x1 = getenv("AGCN_TC2_NO1X1") != nullptr;
+    static const bool no_skip_parity = getenv("AGCN_TC2_NO_SKIP_PARITY") != nullptr;
     static const int dbg = getenv("AGCN_CONV_DEBUG") ? atoi(getenv("AGCN_CONV_DEBUG")) : 0;
     if (disabled || (no_1x1 && taps == 1)) return AGCN_ERR_UNSUPPORTED;
     if (cin % 4 || cout % 16 || v > 128 || stride > 2 || taps > kMaxTaps) return AGCN_ERR_UNSUPPORTED;
-    if (transposed && stride > 1 && taps < stride) return AGCN_ERR_UNSUPPORTED;
+    if (transposed && stride > 1 && taps < stride && no_skip_parity) return AGCN_ERR_UNSUPPORTED;
     if (!aligned16(x) || !aligned16(w) || !aligned16(y) || (bias && !aligned16(bias))) return AGCN_ERR_UNSUPPORTED;
     if (split && (w_split == nullptr || !aligned16(w_split) || ((long long)cout * taps * cin) % 4)) return AGCN_ERR_UNSUPPORTED;
     // Output-channel tile.  A 3xTF32 tile whose K reduction needs more than one accumulator segment keeps fp32 master sums
@@ -378,7 +380,8 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
     a.tmul = transposed ? 1 : stride;
     int nt_max = 0;                                  // timesteps per box
     a.nblk = 1;
-    for (int p = 0; p < 2; ++p) { a.ntap[p] = 0; a.blk_t0[p][0] = a.blk_t0[p][1] = 0; }
+    for (int p = 0; p < 2; ++p) { a.ntap[p] = 0; a.blk_t0[p][0] = a.blk_t0[p][1] = 0; a.par_val[p] = p; }
+    bool skipped_parity = false;
     if (!transposed) {
         a.nblk = (stride == 2 && taps > 1) ? 2 : 1;
         for (int tap = 0; tap < taps; ++tap) {
@@ -393,24 +396,36 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
         a.blk_t0[0][1] = 1 - pad;
         if (stride != 1 && stride != 2 && taps > 1) return AGCN_ERR_UNSUPPORTED;
     } else {
-        for (int par = 0; par < a.nparity; ++par) {
+        int ncls = 0;
+        for (int pv = 0; pv < stride; ++pv) {
             int qmin = 1 << 30, qmax = -(1 << 30);
             for (int tap = 0; tap < taps; ++tap) {
-                const int num = par + pad - tap;
+                const int num = pv + pad - tap;
                 if (num % stride) continue;
                 const int q = num / stride;
                 if (q < qmin) qmin = q;
                 if (q > qmax) qmax = q;
             }
-            if (qmin > qmax) return AGCN_ERR_UNSUPPORTED;          // a parity class without taps
+            if (qmin > qmax) {                                     // no tap reaches this parity (strided 1x1 residual conv): its
+                skipped_parity = true;                             // output rows receive no contribution
+                continue;
+            }
+            const int par = ncls++;
+            a.par_val[par] = pv;
             for (int tap = 0; tap < taps; ++tap) {
-                const int num = par + pad - tap;
+                const int num = pv + pad - tap;
                 if (num % stride) continue;
                 const int i = a.ntap[par]++;
                 a.tap_id[par][i] = (signed char)tap; a.tap_blk[par][i] = 0; a.tap_off[par][i] = (signed char)(num / stride - qmin);
             }
             a.blk_t0[par][0] = qmin;
             if (a.tt + qmax - qmin > nt_max) nt_max = a.tt + qmax - qmin;
+        }
+        if (ncls == 0) return AGCN_ERR_UNSUPPORTED;
+        if (ncls != a.nparity) {
+            if (no_skip_parity) return AGCN_ERR_UNSUPPORTED;
+            a.nparity = ncls;
+            a.total_tiles = (long long)nb * a.nparity * a.tiles_t * a.n_tiles_n;
         }
     }
     if (nt_max * es > 256) return AGCN_ERR_UNSUPPORTED;
@@ -487,6 +502,11 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
         if (e != cudaSuccess) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc2: %s", cudaGetErrorString(e));
         attr_set = true;
+    }
+    if (skipped_parity && !accumulate) {
+        // the kernel only visits the parity classes that have taps; the other output timesteps are exact zeros
+        cudaError_t e = cudaMemsetAsync(y, 0, (size_t)nb * t_out * v * cout * sizeof(float), st);
+        if (e != cudaSuccess) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc2: cudaMemsetAsync: %s", cudaGetErrorString(e));
     }
     const long long grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
     if (split) conv_tc2_kernel<true><<<(unsigned)grid, kThreads2Split, smem, st>>>(map_a, map_b, map_blo, a);

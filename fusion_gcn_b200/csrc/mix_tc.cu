@@ -3,6 +3,10 @@
 //   AGG_FWD : out[n][t][v][k*W + c]  = sum_u         in[n][t][u][c]       * G[n][k][u][v]       (agcn.py:110, X . G_k)
 //   AGG_BWD : out[n][t][u][c]      (+)= sum_k sum_v  in[n][t][v][k*W + c] * G[n][k][u][v]       (its input gradient)
 //
+//   SCORE_BWD: in = e = [theta_0 phi_0 theta_1 phi_1 theta_2 phi_2] (6 groups of W channels), M = dS:
+//             out[n][t][u][theta_k c] = sum_v M[n][k][u][v] * in[n][t][v][phi_k c]                 (d theta, agcn.py:104-106 backward)
+//             out[n][t][v][phi_k c]   = sum_u M[n][k][u][v] * in[n][t][u][theta_k c]               (d phi)
+//
 // GEMM view (per timestep): the contraction index is the JOINT, the channels are the M dimension:
 //   D[(t, cb, c)][col] = sum_joint A[(t, cb, c)][joint] * B[col][joint],   cb = 32-channel block, c = channel in block
 // so an M = 128 tile is four (timestep, channel-block) pairs.  Activations are channels-contiguous, i.e. M-contiguous
@@ -11,6 +15,10 @@
 // B is the per-sample matrix, padded to 32 x 32 per subset by pad_mats_kernel and TMA-loaded once per sample:
 //   AGG_FWD: B[N = (k, v)][K = u] = G[k][u][v]  (N contiguous: Gp [k][u][v32]),  N = 96, K = 32  (4 UMMA K steps)
 //   AGG_BWD: B[N = u][K = (k, v)] = G[k][u][v]  (N contiguous: GpT[k][v][u32]),  N = 32, K = 3 x 32 (12 UMMA K steps)
+//   SCORE_BWD: a tile is one 32-channel block over four consecutive timesteps (so all 128 rows share the subset k);
+//            B[N = 64][K = 32] = [dS_k^T | dS_k] (two 32-column atoms): every channel row gets both mixes, and the epilogue
+//            lane keeps the 32 columns that belong to it (a theta channel produces d phi and vice versa) and writes them
+//            to the partner channel (+-W).  The tensor core does twice the needed MACs, which is free here (HBM bound).
 // The K reduction is at most 96 long, so the 3xTF32 mode needs no accumulator promotion.
 // The epilogue thread of TMEM lane (pair, c) owns one channel of one timestep: for every accumulator column (an output
 // joint) the 32 lanes of a warp write 32 consecutive channels, a full 128-byte line.
@@ -29,7 +37,7 @@ constexpr int kThreadsM = 7 * 32;
 constexpr int kThreadsMSplit = (7 + kSplitWarps) * 32;
 constexpr uint32_t kBarBytes = 512;
 constexpr uint32_t kBoxBytes = 4096;      // 32 rows x 128 bytes
-constexpr uint32_t kMatBytes = 3u * kBoxBytes;
+constexpr uint32_t kMatBytes = 3u * kBoxBytes;     // AGG modes; SCORE_BWD holds 6 boxes per sample (MArgs::mat_bytes)
 
 struct MArgs {
     float* out;
@@ -42,7 +50,26 @@ struct MArgs {
     int na, nlo;
     uint32_t a_tile;         // kb * 4 * kBoxBytes
     int ldout;
+    int score;               // SCORE_BWD
+    int tgroups;             // SCORE_BWD: ceil(t / 4) timestep groups per channel block
+    uint32_t mat_bytes;      // padded matrices of one sample: 3 boxes (AGG) or 6 boxes (SCORE_BWD)
 };
+
+// which (timestep, 32-channel block) the j-th quarter of tile `ts` of a sample covers
+__device__ __forceinline__ void tile_pair(const MArgs& p, int ts, int j, int& tt, int& cb) {
+    if (p.score) { const int tg = ts / p.ncb; cb = ts - tg * p.ncb; tt = tg * 4 + j; }
+    else { const int pair = ts * 4 + j; tt = pair / p.ncb; cb = pair - tt * p.ncb; }
+}
+
+// SCORE_BWD: mats [nb][3][v][v] -> gp [nb][3][2][32][32]: box 0 = transpose ([v][u]), box 1 = as is ([u][v])
+__global__ void pad_mats_score_kernel(const float* mats, float* gp, int nb, int v) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nb * 6 * 1024) return;
+    const int c = idx & 31, r = (idx >> 5) & 31, box = (idx >> 10) & 1, nk = idx >> 11;
+    float val = 0.f;
+    if (r < v && c < v) val = box == 0 ? mats[((long long)nk * v + c) * v + r] : mats[((long long)nk * v + r) * v + c];
+    gp[idx] = val;
+}
 
 // mats [nb][3][v][v] -> gp [nb][3][32][32] (zero padded): fwd keeps [k][u][v], bwd stores the transpose [k][v][u]
 __global__ void pad_mats_kernel(const float* mats, float* gp, int nb, int v, int transpose) {
@@ -60,9 +87,9 @@ mix_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t lo_ring = smem_base + (uint32_t)p.na * p.a_tile;                       // SPLIT: nlo slots of a_tile
-    const uint32_t b_ring = lo_ring + (SPLIT ? (uint32_t)p.nlo * p.a_tile : 0u);          // 2 slots of kMatBytes (+ 2 lo slots when SPLIT)
-    const uint32_t b_lo = b_ring + 2u * kMatBytes;
-    const uint32_t bar_base = b_lo + (SPLIT ? 2u * kMatBytes : 0u);
+    const uint32_t b_ring = lo_ring + (SPLIT ? (uint32_t)p.nlo * p.a_tile : 0u);          // 2 slots of mat_bytes (+ 2 lo slots when SPLIT)
+    const uint32_t b_lo = b_ring + 2u * p.mat_bytes;
+    const uint32_t bar_base = b_lo + (SPLIT ? 2u * p.mat_bytes : 0u);
     auto a_full = [&](int s) { return bar_base + 8u * s; };
     auto a_empty = [&](int s) { return bar_base + 8u * (kMaxA + s); };
     auto a_lo = [&](int s) { return bar_base + 8u * (2 * kMaxA + s); };
@@ -115,8 +142,8 @@ mix_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 const uint32_t dst = smem_base + (uint32_t)sa * p.a_tile;
                 for (int k = 0; k < p.kb; ++k)
                     for (int j = 0; j < 4; ++j) {
-                        const int pair = ts * 4 + j;
-                        const int tt = pair / p.ncb, cb = pair - tt * p.ncb;        // tt >= t for the pairs past the end: zero-filled box
+                        int tt, cb;                                                 // tt >= t for the pairs past the end: zero-filled box
+                        tile_pair(p, ts, j, tt, cb);
                         tma_load_4d(dst + (uint32_t)(k * 4 + j) * kBoxBytes, &map_a, a_full(sa), k * p.width + cb * 32, 0, tt, n);
                     }
                 if (++sa == p.na) { sa = 0; pa ^= 1u; }
@@ -134,8 +161,8 @@ mix_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 ++m;
                 const int sb = m & 1;
                 mbar_wait(b_empty(sb), ((uint32_t)(m >> 1) & 1u) ^ 1u);
-                mbar_expect_tx(b_full(sb), kMatBytes);
-                tma_load_4d(b_ring + (uint32_t)sb * kMatBytes, &map_b, b_full(sb), 0, 0, 0, n);
+                mbar_expect_tx(b_full(sb), p.mat_bytes);
+                tma_load_4d(b_ring + (uint32_t)sb * p.mat_bytes, &map_b, b_full(sb), 0, 0, 0, n);
             }
         }
     } else if (warp == 1) {
@@ -165,12 +192,18 @@ mix_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
                 const uint32_t abase = smem_base + (uint32_t)sa * p.a_tile;
                 const uint32_t alo = lo_ring + (uint32_t)sl * p.a_tile;
-                const uint32_t bbase = b_ring + (uint32_t)sb * kMatBytes;
-                const uint32_t blo = b_lo + (uint32_t)sb * kMatBytes;
+                const uint32_t bbase = b_ring + (uint32_t)sb * p.mat_bytes;
+                const uint32_t blo = b_lo + (uint32_t)sb * p.mat_bytes;
                 uint32_t first = 1;
+                uint32_t score_off = 0;           // SCORE_BWD: the [dS_k^T | dS_k] box pair of this tile's subset
+                if (p.score) {
+                    const int ts = (int)(tile - (long long)n * p.tiles_per_sample);
+                    const int cb = ts % p.ncb;
+                    score_off = (uint32_t)((cb * 32) / (2 * p.width)) * 2u * kBoxBytes;
+                }
                 for (int k = 0; k < p.kb; ++k) {
                     // fwd: B atoms = the three subsets (LBO = one box), K rows inside each box;  bwd: one atom, K block k = box k
-                    const uint32_t bo = p.bwd ? (uint32_t)k * kBoxBytes : 0u;
+                    const uint32_t bo = p.score ? score_off : (p.bwd ? (uint32_t)k * kBoxBytes : 0u);
                     const uint64_t da = make_smem_desc_mn(abase + (uint32_t)k * 4u * kBoxBytes, kBoxBytes);
                     const uint64_t dal = make_smem_desc_mn(alo + (uint32_t)k * 4u * kBoxBytes, kBoxBytes);
                     const uint64_t db = make_smem_desc_mn(bbase + bo, kBoxBytes);
@@ -202,14 +235,32 @@ mix_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         for (long long tile = tile_begin; tile < tile_end; ++tile) {
             const int n = (int)(tile / p.tiles_per_sample);
             const int ts = (int)(tile - (long long)n * p.tiles_per_sample);
-            const int pair = ts * 4 + q;
-            const int tt = pair / p.ncb, cb = pair - tt * p.ncb;
+            int tt, cb;
+            tile_pair(p, ts, q, tt, cb);
             const bool ok = tt < p.t;
             float* obase = p.out + ((long long)n * p.t + (ok ? tt : 0)) * p.v * p.ldout + cb * 32 + lane;
             mbar_wait(tfull_bar(acc), acc_phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem_base + (uint32_t)(acc * 128) + ((uint32_t)(q * 32) << 16);
-            if (!p.bwd) {
+            if (p.score) {
+                // this lane's input channel is a phi channel (is_phi) -> it owns d theta = columns 0..31 (dS^T mix), written to the
+                // partner theta channel (ch - W); a theta channel owns d phi = columns 32..63, written to ch + W
+                const int ch = cb * 32 + lane;
+                const bool is_phi = ((ch / p.width) & 1) != 0;
+                float* ob = obase + (is_phi ? -p.width : p.width);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t ra[16], rb[16];
+                    tmem_ld16_nowait(taddr + (uint32_t)(h * 16), ra);
+                    tmem_ld16_nowait(taddr + 32u + (uint32_t)(h * 16), rb);
+                    tmem_ld_wait();
+                    if (ok) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (h * 16 + i < p.v) ob[(long long)(h * 16 + i) * p.ldout] = __uint_as_float(is_phi ? ra[i] : rb[i]);
+                    }
+                }
+            } else if (!p.bwd) {
                 // column j = k*32 + v -> out[.., v, k*W + cb*32 + c]
 #pragma unroll
                 for (int cg = 0; cg < 6; ++cg) {
@@ -260,7 +311,7 @@ mix_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 mbar_wait(b_full(sb), (uint32_t)(m >> 1) & 1u);
                 // the lo slot of this matrix slot is free once the matrix slot itself was released (b_empty), which the matrix
                 // producer already waited for before refilling it
-                transform_split4(b_ring + (uint32_t)sb * kMatBytes, b_lo + (uint32_t)sb * kMatBytes, kMatBytes, tids, kSplitWarps * 32);
+                transform_split4(b_ring + (uint32_t)sb * p.mat_bytes, b_lo + (uint32_t)sb * p.mat_bytes, p.mat_bytes, tids, kSplitWarps * 32);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(b_lo_bar(sb));
@@ -287,7 +338,7 @@ mix_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
 
 using namespace agcn;
 
-size_t agcn_joint_mix_tc_workspace_bytes(int nb) { return (size_t)nb * 3 * 1024 * sizeof(float); }
+size_t agcn_joint_mix_tc_workspace_bytes(int nb) { return (size_t)nb * 6 * 1024 * sizeof(float); }   // SCORE_BWD pads 6 boxes per sample
 
 // Returns AGCN_ERR_UNSUPPORTED for shapes / modes outside this path (the caller then runs the FFMA kernel).
 // gp: nb*3*1024 floats of scratch for the padded matrices.
@@ -297,22 +348,27 @@ int agcn_joint_mix_tc(const float* in, const float* mats, float* out, float* gp,
     using namespace agcn::mtc;
     static const bool disabled = getenv("AGCN_MIX_SIMT") != nullptr;
     if (disabled) return AGCN_ERR_UNSUPPORTED;
-    if (mode != AGCN_MIX_AGG_FWD && mode != AGCN_MIX_AGG_BWD) return AGCN_ERR_UNSUPPORTED;
-    if (v > 32 || width % 32 || !aligned16(in) || !aligned16(out) || gp == nullptr || !aligned16(gp)) return AGCN_ERR_UNSUPPORTED;
-    if (mode == AGCN_MIX_AGG_FWD && accumulate) return AGCN_ERR_UNSUPPORTED;
+    static const bool score_simt = getenv("AGCN_MIX_SCORE_SIMT") != nullptr;
+    const bool score = mode == AGCN_MIX_SCORE_BWD;
+    if (mode != AGCN_MIX_AGG_FWD && mode != AGCN_MIX_AGG_BWD && !(score && !score_simt)) return AGCN_ERR_UNSUPPORTED;
+    if (v > 32 || width % (score ? 16 : 32) || !aligned16(in) || !aligned16(out) || gp == nullptr || !aligned16(gp)) return AGCN_ERR_UNSUPPORTED;
+    if (mode != AGCN_MIX_AGG_BWD && accumulate) return AGCN_ERR_UNSUPPORTED;
     EncodeTiledFn enc = encode_fn();
     if (!enc) return fail(AGCN_ERR_CUDA, "agcn_joint_mix_tc: cuTensorMapEncodeTiled is not available from the driver");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     MArgs p;
     p.out = out; p.nb = nb; p.t = t; p.v = v; p.width = width; p.bwd = mode == AGCN_MIX_AGG_BWD ? 1 : 0; p.accumulate = accumulate;
-    p.ncb = width / 32;
-    p.tiles_per_sample = (t * p.ncb + 3) / 4;
+    p.score = score ? 1 : 0;
+    p.ncb = (score ? 6 * width : width) / 32;
+    p.tgroups = (t + 3) / 4;
+    p.tiles_per_sample = score ? p.ncb * p.tgroups : (t * p.ncb + 3) / 4;
     p.total_tiles = (long long)nb * p.tiles_per_sample;
     p.kb = p.bwd ? 3 : 1;
-    p.ncols = p.bwd ? 32 : 96;
+    p.ncols = score ? 64 : (p.bwd ? 32 : 96);
     p.a_tile = (uint32_t)p.kb * 4u * kBoxBytes;
     p.ldout = ldout;
-    const uint32_t fixed = 2u * kMatBytes * (split ? 2u : 1u) + kBarBytes + 1024u;
+    p.mat_bytes = score ? 2u * kMatBytes : kMatBytes;
+    const uint32_t fixed = 2u * p.mat_bytes * (split ? 2u : 1u) + kBarBytes + 1024u;
     const uint32_t budget = 220u * 1024u - fixed;
     p.nlo = split ? 2 : 0;
     int na = (int)((budget - (uint32_t)p.nlo * p.a_tile) / p.a_tile);
@@ -322,7 +378,8 @@ int agcn_joint_mix_tc(const float* in, const float* mats, float* out, float* gp,
     p.na = na;
     const size_t smem = (size_t)(p.na + p.nlo) * p.a_tile + fixed;
 
-    pad_mats_kernel<<<ceil_div((long long)nb * 3 * 1024, 256), 256, 0, st>>>(mats, gp, nb, v, p.bwd);
+    if (score) pad_mats_score_kernel<<<ceil_div((long long)nb * 6 * 1024, 256), 256, 0, st>>>(mats, gp, nb, v);
+    else pad_mats_kernel<<<ceil_div((long long)nb * 3 * 1024, 256), 256, 0, st>>>(mats, gp, nb, v, p.bwd);
     int rc = check_launch("agcn_joint_mix_tc(pad)");
     if (rc) return rc;
 
@@ -340,9 +397,10 @@ int agcn_joint_mix_tc(const float* in, const float* mats, float* out, float* gp,
     }
     {
         // padded matrices: dims (32, 32, 3, n); one box = the three 32 x 32 blocks of a sample
-        cuuint64_t dims[4] = {32u, 32u, 3u, (cuuint64_t)nb};
-        cuuint64_t strides[3] = {128u, 4096u, 12288u};
-        cuuint32_t box[4] = {32u, 32u, 3u, 1u};
+        const cuuint32_t nbox = score ? 6u : 3u;
+        cuuint64_t dims[4] = {32u, 32u, nbox, (cuuint64_t)nb};
+        cuuint64_t strides[3] = {128u, 4096u, 4096u * nbox};
+        cuuint32_t box[4] = {32u, 32u, nbox, 1u};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = enc(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, gp, dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,

@@ -130,7 +130,7 @@ def gcn_backward(d_o, ctx, bn_w, dbn_w, down_w, spec: UnitSpec, dx=None, need_dx
     if need_dx:
         dx = K.joint_mix(dz, g, width=cin, mode=K.MIX_AGG_BWD, out=dx, accumulate=have, precision=prec)
         have = True
-    de = K.joint_mix(e, ds, width=ci, mode=K.MIX_SCORE_BWD)
+    de = K.joint_mix(e, ds, width=ci, mode=K.MIX_SCORE_BWD, precision=prec)
     d_wab, d_bab = K.conv_wgrad(de, x, precision=prec)
     if need_dx:
         dx = K.conv_fwd(de, _t(ctx["wab"]), out=dx, accumulate=have, precision=prec)

@@ -1,0 +1,55 @@
+"""Whole training step (forward + loss + backward of the 10-unit model) replayed as ONE CUDA graph.
+
+The reference launches every ATen kernel of a step from Python (torch_src/session/procedures/step.py:39-43).  The C ABI
+of this package never allocates, never synchronises and takes the stream from the caller, so a step is capturable: the
+~630 launches of the NTU model become one ``cudaGraphLaunch`` and the host leaves the critical path (the eager step is
+launch-bound below ~8 sequences per GPU, profiles/r1q).  Inputs, logits, loss and the parameter gradients live at fixed
+addresses in the graph's memory pool; ``__call__`` copies a new batch into the static input and replays.
+"""
+from typing import Callable, Optional
+
+import torch
+
+from . import capi
+
+
+class GraphedStep:
+    """``step = GraphedStep(model, loss_fn, x_example, y_example)``; ``loss = step(x, y)`` runs zero-grad + forward + loss +
+    backward and leaves the gradients in ``p.grad`` (static tensors, overwritten by every replay).  ``after_backward`` (for
+    instance a gradient all-reduce) is captured into the same graph when given."""
+
+    def __init__(self, model: torch.nn.Module, loss_fn: Callable, x_example: torch.Tensor, y_example: torch.Tensor,
+                 warmup: int = 3, after_backward: Optional[Callable[[], None]] = None):
+        if not x_example.is_cuda:
+            raise RuntimeError("GraphedStep needs CUDA tensors (there is no CPU path)")
+        self.model, self.loss_fn = model, loss_fn
+        self.x = x_example.detach().clone()
+        self.y = y_example.detach().clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):          # warm-up off the default stream: lazy initialisation (function attributes,
+            for _ in range(max(1, warmup)):    # driver entry points, allocator) must not happen during capture
+                model.zero_grad(set_to_none=True)
+                loss_fn(model(self.x), self.y).backward()
+                if after_backward is not None:
+                    after_backward()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        model.zero_grad(set_to_none=True)      # gradients are (re)allocated inside the capture, from the graph's pool
+        self.graph = torch.cuda.CUDAGraph()
+        before = capi.lib().agcn_launch_count()
+        with torch.cuda.graph(self.graph):
+            self.logits = model(self.x)
+            self.loss = loss_fn(self.logits, self.y)
+            self.loss.backward()
+            if after_backward is not None:
+                after_backward()
+        self.launches_per_replay = int(capi.lib().agcn_launch_count() - before)   # kernels of libagcn_b200.so in the graph
+
+    def __call__(self, x: Optional[torch.Tensor] = None, y: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if x is not None:
+            self.x.copy_(x, non_blocking=True)
+        if y is not None:
+            self.y.copy_(y, non_blocking=True)
+        self.graph.replay()
+        return self.loss

@@ -186,7 +186,7 @@ def joint_mix(inp, mats, *, width, mode, out=None, accumulate=False, precision=P
         out = torch.empty((nb, t, v, ldout), device=inp.device, dtype=torch.float32)
     _check(inp, mats, out)
     terms = {MIX_AGG_FWD: 3, MIX_AGG_BWD: 3, MIX_SCORE_BWD: 6}[mode]
-    ws_bytes = capi.lib().agcn_joint_mix_workspace_bytes(nb) if (mode != MIX_SCORE_BWD and precision != PREC_FP32_FFMA) else 0
+    ws_bytes = capi.lib().agcn_joint_mix_workspace_bytes(nb) if precision != PREC_FP32_FFMA else 0
     ws = torch.empty((ws_bytes + 3) // 4, device=inp.device, dtype=torch.float32) if ws_bytes else None
     _call("agcn_joint_mix", _ptr(inp), _ptr(mats), _ptr(out), nb, t, v, ldin, ldout, width, mode, int(accumulate), precision,
           _ptr(ws), ws_bytes, _stream(),

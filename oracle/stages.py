@@ -226,7 +226,7 @@ class Tf32Emulation:
     def _fwd_on_tc(x, w, transposed, stride):
         cout, taps, cin = w.shape
         ok = cin % 4 == 0 and cout % 16 == 0 and (cout <= 128 or any(cout % c == 0 for c in range(64, 257, 16)))
-        return ok and not (transposed and stride > 1 and taps < stride)
+        return ok          # (a strided 1x1 input gradient has empty parity classes; the tensor-core kernel skips them)
 
     def conv_fwd(self, x, w, bias=None, *, stride=1, transposed=False, precision=PREC_FP32, **kw):
         if precision == PREC_TF32 and self._fwd_on_tc(x, w, transposed, stride):
@@ -241,7 +241,7 @@ class Tf32Emulation:
         return joint_gram(a, b, **kw)
 
     def joint_mix(self, inp, mats, *, width, mode, precision=PREC_FP32, **kw):
-        if precision == PREC_TF32 and mode in (MIX_AGG_FWD, MIX_AGG_BWD) and width % 32 == 0:
+        if precision == PREC_TF32 and width % (16 if mode == MIX_SCORE_BWD else 32) == 0:
             inp, mats = _trunc_tf32(inp), _trunc_tf32(mats)
         return joint_mix(inp, mats, width=width, mode=mode, **kw)
 

@@ -221,3 +221,35 @@ def test_tf32_mode_model_logits(pkg):
     y.sum().backward()
     assert rel_err(y, y_ref) <= 3e-2
     assert all(torch.isfinite(q.grad).all() for q in model.parameters())
+
+
+def test_graphed_step_matches_eager(pkg):
+    """the whole step captured in one CUDA graph gives the same loss, gradients and BN running statistics as
+    the eager launches (same kernels, same order), and a replay on a new batch follows the new data."""
+    import copy
+    from fusion_gcn_b200 import graph as G, modules as M
+    from fusion_gcn_b200.graphed import GraphedStep
+    torch.manual_seed(3)
+    graph = G.SkeletonGraph(G.UTD_EDGES, center_joint=G.UTD_CENTER)
+    model = M.Model((1, 40, 20, 3), 11, graph, start_feature_size=16).cuda().train()
+    twin = copy.deepcopy(model)
+    loss_fn = torch.nn.CrossEntropyLoss()
+    xs = [torch.randn(3, 1, 40, 20, 3, device="cuda") for _ in range(2)]
+    ys = [torch.randint(11, (3,), device="cuda") for _ in range(2)]
+    warm = 2
+    step = GraphedStep(model, loss_fn, xs[0], ys[0], warmup=warm)
+    assert step.launches_per_replay > 100
+    for _ in range(warm):                       # the twin sees the same number of warm-up steps (running statistics)
+        twin.zero_grad(set_to_none=True)
+        loss_fn(twin(xs[0]), ys[0]).backward()
+    for x, y in zip(xs, ys):
+        loss = step(x, y)
+        twin.zero_grad(set_to_none=True)
+        ref = loss_fn(twin(x), y)
+        ref.backward()
+        torch.cuda.synchronize()
+        assert rel_err(loss, ref) <= 1e-6
+        for (k, p), q in zip(model.named_parameters(), twin.parameters()):
+            assert p.grad is not None and rel_err(p.grad, q.grad) <= 1e-6, k
+    for (k, a), b in zip(model.state_dict().items(), twin.state_dict().values()):
+        assert rel_err(a, b) <= 1e-6, k

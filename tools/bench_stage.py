@@ -76,7 +76,7 @@ def main():
         if want(f"mix_score_bwd_{tag}"):
             e = torch.randn(NB, t, V, 6 * ci, device=dev)
             ds = torch.randn(NB, 3, V, V, device=dev)
-            ms = timeit(lambda: K.joint_mix(e, ds, width=ci, mode=K.MIX_SCORE_BWD), once)
+            ms = timeit(lambda: K.joint_mix(e, ds, width=ci, mode=K.MIX_SCORE_BWD, precision=prec), once)
             report(f"mix_score_bwd_{tag}", ms, e.numel() * 8, 6 * 2.0 * rows * V * ci)
             del e, ds
         for nm, cin, cout, taps in (("emb", c, 6 * ci, 1), ("proj", 3 * c, c, 1), ("dproj", c, 3 * c, 1), ("tconv", c, c, 9)):
@@ -105,6 +105,24 @@ def main():
             report(f"bn_bwd_{tag}", ms, act * 6, 0)
         del x
         torch.cuda.empty_cache()
+    if want("first_unit"):
+        t = 300
+        rows = NB * t * V
+        for cin, cout in ((3, 96), (9, 64), (3, 64)):
+            xs = torch.randn(NB, t, V, cin, device=dev)
+            dy = torch.randn(NB, t, V, cout, device=dev)
+            w = torch.randn(cout, 1, cin, device=dev)
+            ms = timeit(lambda: K.conv_wgrad(dy, xs, want_bias=True, precision=prec), once)
+            report(f"first_unit_wgrad_{cin}_{cout}", ms, rows * (cin + cout) * 4, 2.0 * rows * cin * cout)
+            ms = timeit(lambda: K.conv_fwd(xs, w, None, precision=prec), once)
+            report(f"first_unit_conv_{cin}_{cout}", ms, rows * (cin + cout) * 4, 2.0 * rows * cin * cout)
+    if want("res_dgrad"):
+        for cin, cout, t_out in ((256, 128, 150), (128, 64, 300)):      # input gradient of the strided 1x1 residual conv
+            t_in = t_out // 2
+            dy = torch.randn(NB, t_in, V, cin, device=dev)
+            w = torch.randn(cout, 1, cin, device=dev) * 0.05
+            ms = timeit(lambda: K.conv_fwd(dy, w, None, t_out=t_out, stride=2, pad=0, transposed=True, precision=prec), once)
+            report(f"res_dgrad_{cin}_{cout}", ms, NB * V * (t_in * cin + t_out * cout) * 4, 2.0 * NB * t_in * V * cin * cout)
     if want("skinny"):
         t = 300
         rows = NB * t * V
