@@ -26,6 +26,8 @@ SIGNATURES = {
     "agcn_launch_count": (_c_ll, []),
     "agcn_conv_fwd_workspace_bytes": (_c_size_t, [_c_int] * 4),
     "agcn_conv_fwd": (_c_int, [_c_void_p] * 4 + [_c_int] * 12 + [_c_void_p, _c_size_t, _c_void_p]),
+    "agcn_conv_fwd_stats_bytes": (_c_size_t, [_c_int]),
+    "agcn_conv_fwd_stats": (_c_int, [_c_void_p] * 4 + [_c_int] * 10 + [_c_void_p, _c_size_t, _c_void_p, _c_size_t, ctypes.POINTER(_c_int), _c_void_p]),
     "agcn_conv_wgrad_workspace_bytes": (_c_size_t, [_c_int] * 7),
     "agcn_conv_wgrad": (_c_int, [_c_void_p] * 4 + [_c_int] * 9 + [_c_void_p, _c_size_t, _c_int, _c_void_p]),
     "agcn_joint_gram": (_c_int, [_c_void_p] * 3 + [_c_int] * 13 + [_c_void_p]),
@@ -36,6 +38,7 @@ SIGNATURES = {
     "agcn_bn_workspace_bytes": (_c_size_t, [_c_int]),
     "agcn_bn_stats": (_c_int, [_c_void_p, _c_int, _c_int, _c_ll, _c_int] + [_c_void_p] * 5 + [_c_float, _c_float, _c_int]
                       + [_c_void_p] * 4 + [_c_void_p, _c_size_t, _c_void_p]),
+    "agcn_bn_finalize": (_c_int, [_c_void_p, _c_int, _c_ll, _c_int] + [_c_void_p] * 5 + [_c_float, _c_float] + [_c_void_p] * 5),
     "agcn_bn_apply": (_c_int, [_c_void_p] * 3 + [_c_int] + [_c_void_p] * 3 + [_c_int, _c_void_p, _c_int, _c_int, _c_ll, _c_int, _c_void_p]),
     "agcn_bn_bwd": (_c_int, [_c_void_p] * 10 + [_c_int, _c_int, _c_int, _c_ll, _c_int, _c_void_p, _c_size_t, _c_void_p]),
     "agcn_pool_fwd": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),

@@ -374,6 +374,19 @@ extern "C" AGCN_API int agcn_bn_stats(const float* x, int outer, int inner, long
     return check_launch("agcn_bn_stats(finalize)");
 }
 
+extern "C" AGCN_API int agcn_bn_finalize(const float* part, int nparts, long long rows, int channels,
+                                const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                long long* num_batches_tracked, float momentum, float eps,
+                                float* scale, float* shift, float* save_mean, float* save_invstd, void* stream) {
+    AGCN_REQUIRE(part && scale && shift, AGCN_ERR_NULL, "agcn_bn_finalize: null pointer");
+    AGCN_REQUIRE(nparts > 0 && rows > 0 && channels > 0, AGCN_ERR_BAD_SHAPE, "agcn_bn_finalize: bad shape nparts=%d rows=%lld channels=%d",
+                 nparts, rows, channels);
+    bn_finalize_kernel<<<ceil_div(channels, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        part, nparts, channels, (double)rows, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, 1,
+        scale, shift, save_mean, save_invstd);
+    return check_launch("agcn_bn_finalize");
+}
+
 extern "C" AGCN_API int agcn_bn_apply(const float* y, const float* scale, const float* shift,
                              int res_mode, const float* res, const float* scale2, const float* shift2,
                              int relu, float* out, int outer, int inner, long long outer_stride, int channels, void* stream) {

@@ -510,7 +510,8 @@ int agcn_conv_fwd_tc(const float* x, const float* w, const float* bias, float* y
                      int taps, int stride, int pad, int transposed, int accumulate, int split, float* w_lo, void* stream);
 int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* y,
                       int nb, int t_in, int t_out, int v, int cin, int cout,
-                      int taps, int stride, int pad, int transposed, int accumulate, int split, float* w_split, void* stream);
+                      int taps, int stride, int pad, int transposed, int accumulate, int split, float* w_split, void* stream,
+                      float* stat_part, int* stat_nparts);
 size_t agcn_conv_wgrad_tc_workspace_floats(int nb, int t_in, int t_out, int v, int cin, int cout, int taps, int stride, int pad, int split);
 int agcn_conv_wgrad_tc(const float* dy, const float* x, float* ws, int* splits_out,
                        int nb, int t_in, int t_out, int v, int cin, int cout, int taps, int stride, int pad, int split, void* stream);
@@ -522,10 +523,11 @@ extern "C" AGCN_API size_t agcn_conv_fwd_workspace_bytes(int cin, int cout, int 
     return (size_t)2 * cout * taps * cin * sizeof(float);   // TF32 hi | lo split of the weights for the 3xTF32 path
 }
 
-extern "C" AGCN_API int agcn_conv_fwd(const float* x, const float* w, const float* bias, float* y,
-                             int nb, int t_in, int t_out, int v, int cin, int cout,
-                             int taps, int stride, int pad, int transposed, int accumulate,
-                             int precision, void* workspace, size_t workspace_bytes, void* stream) {
+static int conv_fwd_impl(const float* x, const float* w, const float* bias, float* y,
+                         int nb, int t_in, int t_out, int v, int cin, int cout,
+                         int taps, int stride, int pad, int transposed, int accumulate,
+                         int precision, void* workspace, size_t workspace_bytes, void* stream,
+                         float* stat_part, int* stat_nparts) {
     AGCN_REQUIRE(x && w && y, AGCN_ERR_NULL, "agcn_conv_fwd: null pointer");
     AGCN_REQUIRE(nb > 0 && t_in > 0 && t_out > 0 && v > 0 && cin > 0 && cout > 0 && taps > 0 && stride > 0 && pad >= 0,
                  AGCN_ERR_BAD_SHAPE, "agcn_conv_fwd: bad shape nb=%d t_in=%d t_out=%d v=%d cin=%d cout=%d taps=%d stride=%d pad=%d",
@@ -535,8 +537,13 @@ extern "C" AGCN_API int agcn_conv_fwd(const float* x, const float* w, const floa
         const int split = precision == AGCN_PREC_FP32;
         const bool ws_ok = !split || (workspace != nullptr && workspace_bytes >= agcn_conv_fwd_workspace_bytes(cin, cout, taps, precision));
         if (ws_ok) {
+            if (stat_part != nullptr) {       // try the epilogue with fused column sums first; shapes it does not take run without
+                int rc3 = agcn_conv_fwd_tc2(x, w, bias, y, nb, t_in, t_out, v, cin, cout, taps, stride, pad, transposed, accumulate, split,
+                                            static_cast<float*>(workspace), stream, stat_part, stat_nparts);
+                if (rc3 != AGCN_ERR_UNSUPPORTED) return rc3;
+            }
             int rc2 = agcn_conv_fwd_tc2(x, w, bias, y, nb, t_in, t_out, v, cin, cout, taps, stride, pad, transposed, accumulate, split,
-                                        static_cast<float*>(workspace), stream);
+                                        static_cast<float*>(workspace), stream, nullptr, nullptr);
             if (rc2 != AGCN_ERR_UNSUPPORTED) return rc2;
             int rc = agcn_conv_fwd_tc(x, w, bias, y, nb, t_in, t_out, v, cin, cout, taps, stride, pad, transposed,
                                       accumulate, split, static_cast<float*>(workspace), stream);
@@ -564,6 +571,32 @@ extern "C" AGCN_API int agcn_conv_fwd(const float* x, const float* w, const floa
     if (vec) conv_fwd_kernel<true><<<grid, 256, 0, s>>>(a);
     else conv_fwd_kernel<false><<<grid, 256, 0, s>>>(a);
     return check_launch("agcn_conv_fwd");
+}
+
+extern "C" AGCN_API int agcn_conv_fwd(const float* x, const float* w, const float* bias, float* y,
+                             int nb, int t_in, int t_out, int v, int cin, int cout,
+                             int taps, int stride, int pad, int transposed, int accumulate,
+                             int precision, void* workspace, size_t workspace_bytes, void* stream) {
+    return conv_fwd_impl(x, w, bias, y, nb, t_in, t_out, v, cin, cout, taps, stride, pad, transposed, accumulate, precision,
+                         workspace, workspace_bytes, stream, nullptr, nullptr);
+}
+
+extern "C" AGCN_API size_t agcn_conv_fwd_stats_bytes(int cout) {
+    return cout > 0 ? (size_t)4 * kNumSMs * 2 * cout * sizeof(float) : 0;
+}
+
+extern "C" AGCN_API int agcn_conv_fwd_stats(const float* x, const float* w, const float* bias, float* y,
+                                   int nb, int t_in, int t_out, int v, int cin, int cout,
+                                   int taps, int stride, int pad,
+                                   int precision, void* workspace, size_t workspace_bytes,
+                                   float* stat_part, size_t stat_part_bytes, int* stat_nparts, void* stream) {
+    AGCN_REQUIRE(stat_part && stat_nparts, AGCN_ERR_NULL, "agcn_conv_fwd_stats: null pointer");
+    AGCN_REQUIRE(cout > 0 && stat_part_bytes >= agcn_conv_fwd_stats_bytes(cout), AGCN_ERR_WORKSPACE, "agcn_conv_fwd_stats: partial buffer too small");
+    AGCN_REQUIRE(aligned16(stat_part), AGCN_ERR_MISALIGNED, "agcn_conv_fwd_stats: partial buffer not 16-byte aligned");
+    *stat_nparts = 0;
+    static const bool off = getenv("AGCN_NO_FUSED_STATS") != nullptr;
+    return conv_fwd_impl(x, w, bias, y, nb, t_in, t_out, v, cin, cout, taps, stride, pad, 0, 0, precision,
+                         workspace, workspace_bytes, stream, off ? nullptr : stat_part, off ? nullptr : stat_nparts);
 }
 
 extern "C" AGCN_API size_t agcn_conv_wgrad_workspace_bytes(int nb, int t_in, int t_out, int v, int cin, int cout, int taps) {

@@ -41,9 +41,12 @@ constexpr int kTmemCols2 = 512;
 constexpr uint32_t kStagePitch = 144;                        // bytes per staged output row: 32 floats + 16 bytes (conflict-free 16-byte accesses)
 constexpr uint32_t kStageBytes = 4u * 32u * kStagePitch;     // four epilogue warps
 constexpr uint32_t kSmemBudget = 222u * 1024u;
+constexpr int kStatCols = 256;                               // fused BatchNorm statistics: widest output the per-warp column sums cover
+constexpr uint32_t kStatBytes = 4u * 2u * kStatCols * 4u;    // four epilogue warps x (sum | sum of squares) x kStatCols floats
 
 struct Tc2Args {
     float* y; const float* bias;
+    float* stat_part;             // != NULL: per-warp column sums of the written output, [gridDim.x * 4][2][cout] (BatchNorm statistics)
     int nb, t_out, v, cin, cout, stride, transposed, accumulate;
     int tt, bn, n_tiles_n, kchunks, tiles_t, nparity;
     long long total_tiles;
@@ -104,6 +107,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    // fused BatchNorm statistics: per epilogue warp, sum and sum of squares of every output column it has written
+    float* stat_sm = reinterpret_cast<float*>(smem_raw + (bar_base + kBarBytes + kStageBytes - smem_u32(smem_raw))) + ((threadIdx.x >> 5) & 3) * (2 * kStatCols);
 
     const uint32_t a_tx = (uint32_t)a.nblk * a.blk_rows_bytes;
     const uint32_t b_tx = (uint32_t)a.bn * 128u * (SPLIT ? 2u : 1u);
@@ -216,6 +222,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const int q = warp & 3;
         const int row_local = q * 32 + lane;
         int acc = 0; uint32_t acc_phase = 0;
+        if (a.stat_part != nullptr) {
+            for (int i = lane; i < 2 * kStatCols; i += 32) stat_sm[i] = 0.f;
+            __syncwarp();
+        }
         for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
             long long r = tile;
             const int nt = (int)(r % a.n_tiles_n); r /= a.n_tiles_n;
@@ -264,6 +274,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                             const bool col_ok = cq < 4 || wide;
                             float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (a.bias && col_ok) bq = __ldg(reinterpret_cast<const float4*>(a.bias + nt * a.bn + c0 + cq * 4));
+                            float4 ssum = make_float4(0.f, 0.f, 0.f, 0.f), ssq = ssum;      // column sums over this lane's 8 rows
                             // four row offsets (and, when accumulating, four old values) are fetched before the first dependent
                             // add / store, so the global-load latency is paid twice per chunk, not once per row
 #pragma unroll
@@ -284,7 +295,28 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                                         float4 o = lds128(stage_base + (uint32_t)src_lane * kStagePitch + (uint32_t)cq * 16u);
                                         o.x += bq.x + oldv[r4].x; o.y += bq.y + oldv[r4].y; o.z += bq.z + oldv[r4].z; o.w += bq.w + oldv[r4].w;
                                         *reinterpret_cast<float4*>(a.y + offs[r4] + c0 + cq * 4) = o;
+                                        ssum.x += o.x; ssum.y += o.y; ssum.z += o.z; ssum.w += o.w;
+                                        ssq.x = fmaf(o.x, o.x, ssq.x); ssq.y = fmaf(o.y, o.y, ssq.y); ssq.z = fmaf(o.z, o.z, ssq.z); ssq.w = fmaf(o.w, o.w, ssq.w);
                                     }
+                                }
+                            }
+                            if (a.stat_part != nullptr) {
+                                // lanes l, l+8, l+16, l+24 hold the same four columns (different rows): fixed-order butterfly, then
+                                // lanes 0..7 add the warp's 32-row sums into the warp's shared-memory accumulators
+#pragma unroll
+                                for (int d = 8; d <= 16; d <<= 1) {
+                                    ssum.x += __shfl_xor_sync(0xffffffffu, ssum.x, d); ssum.y += __shfl_xor_sync(0xffffffffu, ssum.y, d);
+                                    ssum.z += __shfl_xor_sync(0xffffffffu, ssum.z, d); ssum.w += __shfl_xor_sync(0xffffffffu, ssum.w, d);
+                                    ssq.x += __shfl_xor_sync(0xffffffffu, ssq.x, d); ssq.y += __shfl_xor_sync(0xffffffffu, ssq.y, d);
+                                    ssq.z += __shfl_xor_sync(0xffffffffu, ssq.z, d); ssq.w += __shfl_xor_sync(0xffffffffu, ssq.w, d);
+                                }
+                                if (lane < 8 && col_ok) {
+                                    float4* s0 = reinterpret_cast<float4*>(stat_sm + nt * a.bn + c0 + lane * 4);
+                                    float4* s1 = reinterpret_cast<float4*>(stat_sm + kStatCols + nt * a.bn + c0 + lane * 4);
+                                    float4 u0 = *s0, u1 = *s1;
+                                    u0.x += ssum.x; u0.y += ssum.y; u0.z += ssum.z; u0.w += ssum.w;
+                                    u1.x += ssq.x; u1.y += ssq.y; u1.z += ssq.z; u1.w += ssq.w;
+                                    *s0 = u0; *s1 = u1;
                                 }
                             }
                             __syncwarp();
@@ -297,6 +329,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 if (lane == 0) mbar_arrive(tempty_bar(acc));
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
+        }
+        if (a.stat_part != nullptr) {
+            __syncwarp();
+            float* dst = a.stat_part + ((long long)blockIdx.x * 4 + q) * 2 * a.cout;
+            for (int i = lane; i < a.cout; i += 32) { dst[i] = stat_sm[i]; dst[a.cout + i] = stat_sm[kStatCols + i]; }
         }
     } else if (SPLIT) {
         // ===================================================== operand split of the activation stage (kSplitWarps warps)
@@ -333,9 +370,11 @@ using namespace agcn;
 
 // Returns AGCN_ERR_UNSUPPORTED for shapes outside this path (the caller then tries the older kernels).
 // split != 0: 3xTF32 (fp32 parity mode).
+// stat_part != NULL (forward gather, no accumulate, cout <= 256): the epilogue also leaves [*stat_nparts][2][cout] column sums.
 int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* y,
                       int nb, int t_in, int t_out, int v, int cin, int cout,
-                      int taps, int stride, int pad, int transposed, int accumulate, int split, float* w_split, void* stream) {
+                      int taps, int stride, int pad, int transposed, int accumulate, int split, float* w_split, void* stream,
+                      float* stat_part, int* stat_nparts) {
     using namespace agcn::tc;
     using namespace agcn::tc2;
     static const bool disabled = getenv("AGCN_TC_V1") != nullptr;
@@ -347,6 +386,7 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
     if (transposed && stride > 1 && taps < stride && no_skip_parity) return AGCN_ERR_UNSUPPORTED;
     if (!aligned16(x) || !aligned16(w) || !aligned16(y) || (bias && !aligned16(bias))) return AGCN_ERR_UNSUPPORTED;
     if (split && (w_split == nullptr || !aligned16(w_split) || ((long long)cout * taps * cin) % 4)) return AGCN_ERR_UNSUPPORTED;
+    if (stat_part != nullptr && (transposed || accumulate || cout > kStatCols || stat_nparts == nullptr)) return AGCN_ERR_UNSUPPORTED;
     // Output-channel tile.  A 3xTF32 tile whose K reduction needs more than one accumulator segment keeps fp32 master sums
     // in TMEM columns 256..383, so it is at most 128 wide; single-segment tiles (1x1 convs with cin <= 256) and the TF32
     // mode use up to 256 columns per accumulator buffer, which avoids re-loading (and re-splitting) the activations per tile.
@@ -361,7 +401,7 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
     if (!enc) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc2: cuTensorMapEncodeTiled is not available from the driver");
 
     Tc2Args a;
-    a.y = y; a.bias = bias;
+    a.y = y; a.bias = bias; a.stat_part = stat_part;
     a.nb = nb; a.t_out = t_out; a.v = v; a.cin = cin; a.cout = cout; a.stride = stride; a.transposed = transposed; a.accumulate = accumulate;
     a.dbg = dbg;
     a.seg_iters = (split && kiters <= 8) ? 8 : kSegment;
@@ -436,7 +476,8 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
     a.a_stage_bytes = (uint32_t)a.nblk * a.blk_bytes;
     a.b_stage_bytes = (uint32_t)bn * 128u;
     const uint32_t a_slot = a.a_stage_bytes, b_slot = a.b_stage_bytes * (split ? 2u : 1u);
-    const uint32_t budget = kSmemBudget - 1024u - kBarBytes - kStageBytes;
+    const uint32_t stat_bytes = stat_part != nullptr ? kStatBytes : 0u;
+    const uint32_t budget = kSmemBudget - 1024u - kBarBytes - kStageBytes - stat_bytes;
     // Ring depths.  Weights: 3 slots (2 when tight).  3xTF32 lo residuals: 2 slots, 1 when two would leave a single
     // activation stage.  Everything else goes to the activation ring: payload bytes in flight set the achieved bandwidth.
     a.na = 0; a.nbst = 0; a.nlo = split ? 2 : 0;
@@ -460,7 +501,7 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
         if (nbst < best_b) nbst = best_b;
         a.nbst = nbst;
     }
-    const size_t smem = (size_t)(a.na + a.nlo) * a_slot + (size_t)a.nbst * b_slot + 1024 + kBarBytes + kStageBytes;
+    const size_t smem = (size_t)(a.na + a.nlo) * a_slot + (size_t)a.nbst * b_slot + 1024 + kBarBytes + kStageBytes + stat_bytes;
 
     CUtensorMap map_a, map_b, map_blo;
     {
@@ -511,5 +552,6 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
     const long long grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
     if (split) conv_tc2_kernel<true><<<(unsigned)grid, kThreads2Split, smem, st>>>(map_a, map_b, map_blo, a);
     else conv_tc2_kernel<false><<<(unsigned)grid, kThreads2, smem, st>>>(map_a, map_b, map_blo, a);
+    if (stat_nparts != nullptr) *stat_nparts = stat_part != nullptr ? (int)grid * 4 : 0;
     return check_launch("agcn_conv_fwd_tc2");
 }

@@ -52,6 +52,21 @@ def _bn_forward(y, gamma, beta, buf: BnBuffers, training: bool):
                       BN_MOMENTUM, BN_EPS, training)
 
 
+def _conv_bn(x, w, bias, gamma, beta, buf: BnBuffers, training: bool, prec: int, **kw):
+    """Conv2d -> BatchNorm2d pair (agcn.py:41-51,73-83): y = conv(x) and the BN scale / shift / saved statistics of y.
+    In training mode the column sums come out of the convolution's epilogue (conv_fwd_stats) when the kernel covers the
+    shape, which saves the separate statistics pass over y."""
+    if training:
+        y, part = K.conv_fwd_stats(x, w, bias, precision=prec, **kw)
+        if part is not None:
+            rows = y.numel() // y.shape[-1]
+            return y, K.bn_finalize(part, rows, gamma, beta, buf.running_mean, buf.running_var, buf.num_batches_tracked,
+                                    BN_MOMENTUM, BN_EPS)
+    else:
+        y = K.conv_fwd(x, w, bias, precision=prec, **kw)
+    return y, _bn_forward(y, gamma, beta, buf, training)
+
+
 def _zero_bias(like, n):
     """Gradient of a conv bias that feeds a training-mode BatchNorm: BN subtracts the batch mean, so the loss does not
     depend on the bias and its gradient is identically zero (the reference's autograd produces ~1e-9 rounding
@@ -81,11 +96,9 @@ def gcn_forward(x, adj_a, adj_b, wa, ba, wb, bb, wd, bd, bn_w, bn_b, down_w, dow
     scale = 1.0 / float(ci * t)
     p, g = K.attention_fwd(s_part, adj_a.contiguous(), adj_b.contiguous(), scale)
     z = K.joint_mix(x, g, width=cin, mode=K.MIX_AGG_FWD, precision=prec)                               # [nb,t,v,3*cin]
-    y = K.conv_fwd(z, wdc, bdc, precision=prec)
-    sc, sh, mean, invstd = _bn_forward(y, bn_w, bn_b, spec.bn_gcn, spec.training)
+    y, (sc, sh, mean, invstd) = _conv_bn(z, wdc, bdc, bn_w, bn_b, spec.bn_gcn, spec.training, prec)
     if spec.has_down:
-        yd = K.conv_fwd(x, down_w.reshape(cout, 1, cin), down_b, precision=prec)
-        sc2, sh2, mean2, invstd2 = _bn_forward(yd, dbn_w, dbn_b, spec.bn_down, spec.training)
+        yd, (sc2, sh2, mean2, invstd2) = _conv_bn(x, down_w.reshape(cout, 1, cin), down_b, dbn_w, dbn_b, spec.bn_down, spec.training, prec)
         o = K.bn_apply(y, sc, sh, res_mode=K.RES_AFFINE, res=yd, scale2=sc2, shift2=sh2, relu=True)
     else:
         yd = mean2 = invstd2 = None
@@ -160,15 +173,13 @@ def tcn_forward(o, x_res, wt, bt, bn_w, bn_b, wr, br, rbn_w, rbn_b, spec: UnitSp
     t_out = (t + 2 * pad - ksz) // s + 1
     prec = spec.precision
     wtp = _pack_taps(wt)
-    u = K.conv_fwd(o, wtp, bt, t_out=t_out, stride=s, pad=pad, precision=prec)
-    sc, sh, mean, invstd = _bn_forward(u, bn_w, bn_b, spec.bn_tcn, spec.training)
+    u, (sc, sh, mean, invstd) = _conv_bn(o, wtp, bt, bn_w, bn_b, spec.bn_tcn, spec.training, prec, t_out=t_out, stride=s, pad=pad)
     ur = mean2 = invstd2 = wrp = None
     if spec.residual == "identity":
         out = K.bn_apply(u, sc, sh, res_mode=K.RES_TENSOR, res=x_res, relu=spec.relu_out)
     elif spec.residual == "conv":
         wrp = _pack_taps(wr)
-        ur = K.conv_fwd(x_res, wrp, br, t_out=t_out, stride=s, pad=0, precision=prec)
-        sc2, sh2, mean2, invstd2 = _bn_forward(ur, rbn_w, rbn_b, spec.bn_res, spec.training)
+        ur, (sc2, sh2, mean2, invstd2) = _conv_bn(x_res, wrp, br, rbn_w, rbn_b, spec.bn_res, spec.training, prec, t_out=t_out, stride=s, pad=0)
         out = K.bn_apply(u, sc, sh, res_mode=K.RES_AFFINE, res=ur, scale2=sc2, shift2=sh2, relu=spec.relu_out)
     else:
         out = K.bn_apply(u, sc, sh, relu=spec.relu_out)

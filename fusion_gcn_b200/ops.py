@@ -72,7 +72,7 @@ def stop_timing():
     return out
 
 
-def _call(name, *args, sig=None, work=(0.0, 0.0)):
+def _call(name, *args, sig=None, work=(0.0, 0.0), alias=None):
     """``sig``: shape signature of the call, ``work``: (algorithmic FLOPs, algorithmic bytes) of one launch -- used only while
     bench.py is timing (CUDA events on the launching stream around the C-ABI call)."""
     capi.launch_count += 1
@@ -82,7 +82,7 @@ def _call(name, *args, sig=None, work=(0.0, 0.0)):
         e0.record()
         rc = fn(*args)
         e1.record()
-        _timing[1].append(((name, sig), work, e0, e1))
+        _timing[1].append(((alias or name, sig), work, e0, e1))
     else:
         rc = fn(*args)
     capi.check(rc, name)
@@ -113,6 +113,48 @@ def conv_fwd(x, w, bias=None, *, t_out=None, stride=1, pad=0, transposed=False, 
           sig=(nb, t_in, t_out, v, cin, cout, taps, stride, int(transposed), int(accumulate)),
           work=(2.0 * rows * cin * cout * taps, 4.0 * (x.numel() + rows * cout * (2 if accumulate else 1))))
     return out
+
+
+def conv_fwd_stats(x, w, bias=None, *, t_out=None, stride=1, pad=0, precision=PREC_FP32):
+    """conv_fwd whose epilogue also accumulates the column sums of y for the training-mode BatchNorm that follows
+    (agcn_conv_fwd_stats).  -> (y, part) with part [nparts, 2, cout] (sum | sum of squares), or (y, None) when the fused
+    epilogue does not cover the shape (run bn_stats on y then)."""
+    import ctypes
+    nb, t_in, v, cin = x.shape
+    cout, taps, cin_w = w.shape
+    if cin_w != cin:
+        raise RuntimeError(f"conv_fwd_stats: weight expects {cin_w} input channels, tensor has {cin}")
+    if t_out is None:
+        t_out = t_in
+    out = torch.empty((nb, t_out, v, cout), device=x.device, dtype=torch.float32)
+    _check(x, w, bias, out)
+    L = capi.lib()
+    ws_bytes = L.agcn_conv_fwd_workspace_bytes(cin, cout, taps, precision)
+    ws = torch.empty((ws_bytes + 3) // 4, device=x.device, dtype=torch.float32) if ws_bytes else None
+    part_bytes = L.agcn_conv_fwd_stats_bytes(cout)
+    part = torch.empty(part_bytes // 4, device=x.device, dtype=torch.float32)
+    nparts = ctypes.c_int(0)
+    rows = nb * t_out * v
+    _call("agcn_conv_fwd_stats", _ptr(x), _ptr(w), _ptr(bias), _ptr(out), nb, t_in, t_out, v, cin, cout, taps, stride, pad,
+          precision, _ptr(ws), ws_bytes, _ptr(part), part_bytes, ctypes.byref(nparts), _stream(),
+          sig=(nb, t_in, t_out, v, cin, cout, taps, stride, 0, 0),
+          work=(2.0 * rows * cin * cout * taps, 4.0 * (x.numel() + rows * cout)), alias="agcn_conv_fwd")
+    if nparts.value == 0:
+        return out, None
+    return out, part[:nparts.value * 2 * cout].view(nparts.value, 2, cout)
+
+
+def bn_finalize(part, rows, gamma, beta, running_mean, running_var, nbt, momentum, eps):
+    """Training-mode BatchNorm parameters from column sums (conv_fwd_stats): -> scale, shift, save_mean, save_invstd."""
+    nparts, _, c = part.shape
+    scale = torch.empty((4, c), device=part.device, dtype=torch.float32)
+    _check(part, gamma, beta, running_mean, running_var)
+    if nbt is not None and nbt.dtype != torch.int64:
+        raise RuntimeError("num_batches_tracked must be int64")
+    _call("agcn_bn_finalize", _ptr(part), nparts, int(rows), c, _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var),
+          _ptr(nbt), float(momentum), float(eps), scale[0].data_ptr(), scale[1].data_ptr(), scale[2].data_ptr(), scale[3].data_ptr(),
+          _stream(), sig=(nparts, c), work=(0.0, 0.0))
+    return scale[0], scale[1], scale[2], scale[3]
 
 
 def conv_wgrad(dy, x, *, taps=1, stride=1, pad=0, want_bias=True, precision=PREC_FP32):

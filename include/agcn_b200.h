@@ -83,6 +83,19 @@ int agcn_conv_fwd(const float* x, const float* w, const float* bias, float* y,
                   int taps, int stride, int pad, int transposed, int accumulate,
                   int precision, void* workspace, size_t workspace_bytes, void* stream);
 
+/* agcn_conv_fwd (forward gather, no accumulate) whose epilogue also leaves the per-channel sums the training-mode
+ * BatchNorm that follows needs (nn.Conv2d -> nn.BatchNorm2d pairs at agcn.py:41-51,73-83): stat_part receives
+ * [*stat_nparts][2][cout] floats (sum | sum of squares of y over a fixed row partition, deterministic), to be
+ * combined by agcn_bn_finalize.  *stat_nparts == 0 on return means the fused epilogue does not cover this shape:
+ * y is complete, run agcn_bn_stats on it.  stat_part: agcn_conv_fwd_stats_bytes(cout) bytes, 16-byte aligned.
+ * stat_nparts is a HOST pointer.                                                                          */
+size_t agcn_conv_fwd_stats_bytes(int cout);
+int agcn_conv_fwd_stats(const float* x, const float* w, const float* bias, float* y,
+                        int nb, int t_in, int t_out, int v, int cin, int cout,
+                        int taps, int stride, int pad,
+                        int precision, void* workspace, size_t workspace_bytes,
+                        float* stat_part, size_t stat_part_bytes, int* stat_nparts, void* stream);
+
 /* Weight / bias gradient of the forward-gather contraction above:
  *   dw[co][tap][ci] = sum_rows dy[nb][to][v][co] * x[nb][stride*to+tap-pad][v][ci];   dbias[co] = sum_rows dy
  * Deterministic (two-phase split reduction, no atomics).  dbias may be NULL.                            */
@@ -117,9 +130,10 @@ int agcn_attention_bwd(const float* dg_part, const float* p, float* dg_sum, floa
 
 /* Per-sample mixing over the joint axis, see agcn_mix_mode.  in: [nb][t][v][ldin], out: [nb][t][v][ldout],
  * mats: [nb][3][v][v], width = channels per group.  V <= 32.
- * precision: AGCN_PREC_FP32 / AGCN_PREC_TF32 run AGCN_MIX_AGG_FWD / AGCN_MIX_AGG_BWD on the tensor cores (3xTF32 / single-pass
- * TF32) when width is a multiple of 32 and the workspace holds agcn_joint_mix_workspace_bytes(nb) bytes (zero-padded copies
- * of the matrices); every other case and AGCN_PREC_FP32_FFMA use the FFMA kernel (workspace may then be NULL).              */
+ * precision: AGCN_PREC_FP32 / AGCN_PREC_TF32 run the mix on the tensor cores (3xTF32 / single-pass TF32) when width is a
+ * multiple of 32 (AGCN_MIX_AGG_FWD / AGCN_MIX_AGG_BWD) or of 16 (AGCN_MIX_SCORE_BWD) and the workspace holds
+ * agcn_joint_mix_workspace_bytes(nb) bytes (zero-padded copies of the matrices); every other case and
+ * AGCN_PREC_FP32_FFMA use the FFMA kernel (workspace may then be NULL).                                                     */
 size_t agcn_joint_mix_workspace_bytes(int nb);
 int agcn_joint_mix(const float* in, const float* mats, float* out,
                    int nb, int t, int v, int ldin, int ldout, int width, int mode, int accumulate,
@@ -140,6 +154,13 @@ int agcn_bn_stats(const float* x, int outer, int inner, long long outer_stride, 
                   long long* num_batches_tracked, float momentum, float eps, int training,
                   float* scale, float* shift, float* save_mean, float* save_invstd,
                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* The finalize half of agcn_bn_stats (training mode) on column sums produced by agcn_conv_fwd_stats:
+ * part[nparts][2][channels] (sum | sum of squares), rows = number of rows they cover.                     */
+int agcn_bn_finalize(const float* part, int nparts, long long rows, int channels,
+                     const float* gamma, const float* beta, float* running_mean, float* running_var,
+                     long long* num_batches_tracked, float momentum, float eps,
+                     float* scale, float* shift, float* save_mean, float* save_invstd, void* stream);
 
 /* out = act(scale*y + shift + R),  R = 0 | res | scale2*res + shift2;  act = ReLU when relu!=0.
  * (agcn.py:113-115 and :135-136).  Same addressing as agcn_bn_stats for y / res / out.                   */

@@ -100,6 +100,30 @@ def attention_bwd(dg_part, p, scale):
     return ds.contiguous(), dg.sum(dim=0).contiguous()
 
 
+def conv_fwd_stats(x, w, bias=None, *, t_out=None, stride=1, pad=0, precision=0):
+    """conv_fwd plus the column sums a following training-mode BatchNorm needs: part [1, 2, cout] = (sum, sum of squares)."""
+    y = conv_fwd(x, w, bias, t_out=t_out, stride=stride, pad=pad)
+    flat = y.reshape(-1, y.shape[-1]).double()
+    return y, torch.stack([flat.sum(0), (flat * flat).sum(0)]).unsqueeze(0)
+
+
+def bn_finalize(part, rows, gamma, beta, running_mean, running_var, nbt, momentum, eps):
+    s = part.double().sum(0)
+    mean = s[0] / rows
+    var = (s[1] / rows - mean * mean).clamp_min(0)
+    if running_mean is not None:
+        unbiased = var * rows / (rows - 1) if rows > 1 else var
+        running_mean.mul_(1 - momentum).add_((momentum * mean).to(running_mean.dtype))
+        running_var.mul_(1 - momentum).add_((momentum * unbiased).to(running_var.dtype))
+    if nbt is not None:
+        nbt += 1
+    invstd = 1.0 / torch.sqrt(var + eps)
+    g = gamma.double() if gamma is not None else torch.ones_like(mean)
+    b = beta.double() if beta is not None else torch.zeros_like(mean)
+    dt = gamma.dtype if gamma is not None else torch.float32
+    return (g * invstd).to(dt), (b - mean * g * invstd).to(dt), mean.to(dt), invstd.to(dt)
+
+
 def joint_mix(inp, mats, *, width, mode, out=None, accumulate=False, precision=0):
     nb, t, v, _ = inp.shape
     w = width
@@ -232,6 +256,11 @@ class Tf32Emulation:
         if precision == PREC_TF32 and self._fwd_on_tc(x, w, transposed, stride):
             x, w = _trunc_tf32(x), _trunc_tf32(w)
         return conv_fwd(x, w, bias, stride=stride, transposed=transposed, **kw)
+
+    def conv_fwd_stats(self, x, w, bias=None, *, stride=1, precision=PREC_FP32, **kw):
+        if precision == PREC_TF32 and self._fwd_on_tc(x, w, False, stride):
+            x, w = _trunc_tf32(x), _trunc_tf32(w)
+        return conv_fwd_stats(x, w, bias, stride=stride, **kw)
 
     def joint_gram(self, a, b, *, precision=PREC_FP32, **kw):
         v, width, same_row = a.shape[2], kw["width"], a is b and kw["stridea"] == 32 and kw["strideb"] == 32 and kw["offb"] == kw["offa"] + 16

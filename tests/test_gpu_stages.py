@@ -61,6 +61,38 @@ def test_conv_fwd_dgrad_wgrad(K, nb, t_in, v, cin, cout, taps, stride, mode):
     assert rel_err(dw, dw_ref) <= 2.5 * tol and rel_err(db, db_ref) <= 5e-6
 
 
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+@pytest.mark.parametrize("nb,t_in,v,cin,cout,taps,stride", [
+    (3, 40, 25, 64, 64, 9, 1), (2, 31, 25, 192, 64, 1, 1), (4, 30, 20, 64, 128, 9, 2), (2, 24, 22, 384, 128, 1, 1),
+    (2, 16, 25, 128, 256, 1, 2), (1, 12, 25, 256, 256, 9, 1), (2, 12, 25, 3, 64, 1, 1), (3, 700, 25, 64, 64, 1, 1)])
+def test_conv_fwd_fused_bn_statistics(K, nb, t_in, v, cin, cout, taps, stride, mode):
+    """agcn_conv_fwd_stats + agcn_bn_finalize against conv_fwd followed by bn_stats on its output (same y bit for bit; scale /
+    shift / mean / invstd and the running statistics to 1e-5), including more tiles than CTAs and a shape the fused epilogue
+    does not cover (cin = 3: part is None and the caller falls back)."""
+    prec = K.PREC_FP32 if mode == "fp32" else K.PREC_TF32
+    pad = (taps - 1) // 2
+    t_out = (t_in + 2 * pad - taps) // stride + 1
+    x, w, b = rnd(nb, t_in, v, cin).cuda(), (rnd(cout, taps, cin, seed=1) * 0.1).cuda(), rnd(cout, seed=2).cuda()
+    gamma, beta = (rnd(cout, seed=3) * 0.3 + 1).cuda(), (rnd(cout, seed=4) * 0.1).cuda()
+    y_ref = K.conv_fwd(x, w, b, t_out=t_out, stride=stride, pad=pad, precision=prec)
+    y, part = K.conv_fwd_stats(x, w, b, t_out=t_out, stride=stride, pad=pad, precision=prec)
+    assert torch.equal(y, y_ref)
+    if cin % 4:
+        assert part is None
+        return
+    assert part is not None and part.shape[1:] == (2, cout)
+    rm, rv, nbt = torch.zeros(cout).cuda(), torch.ones(cout).cuda(), torch.zeros((), dtype=torch.long).cuda()
+    rm2, rv2, nbt2 = rm.clone(), rv.clone(), nbt.clone()
+    got = K.bn_finalize(part, nb * t_out * v, gamma, beta, rm, rv, nbt, 0.1, 1e-5)
+    ref = S.bn_stats(y_ref.double().cpu(), gamma.double().cpu(), beta.double().cpu(), rm2.double().cpu(), rv2.double().cpu(), None, 0.1, 1e-5, True)
+    for a, r in zip(got, ref):
+        assert rel_err(a, r) <= 1e-5
+    want = K.bn_stats(y_ref, gamma, beta, rm2, rv2, nbt2, 0.1, 1e-5, True)
+    for a, r in zip(got, want):
+        assert rel_err(a, r) <= 1e-5
+    assert rel_err(rm, rm2) <= 1e-5 and rel_err(rv, rv2) <= 1e-5 and int(nbt) == 1 == int(nbt2)
+
+
 @pytest.mark.parametrize("nb,t,v,ci,nchunk", [(2, 12, 25, 16, 3), (3, 7, 20, 4, 7), (1, 30, 22, 64, 4), (2, 5, 5, 2, 1), (2, 9, 18, 3, 2)])
 def test_joint_gram_score_and_dg(K, nb, t, v, ci, nchunk):
     e = rnd(nb, t, v, 6 * ci)

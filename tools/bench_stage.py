@@ -87,6 +87,13 @@ def main():
                 ms = timeit(lambda: K.conv_fwd(xi, w, b, pad=(taps - 1) // 2, precision=prec), once)
                 report(f"conv_{nm}_{tag}", ms, rows * (cin + cout) * 4, 2.0 * rows * cin * cout * taps)
                 del xi
+            if want(f"convstats_{nm}_{tag}") and nm in ("proj", "tconv"):
+                xi = torch.randn(NB, t, V, cin, device=dev)
+                w = torch.randn(cout, taps, cin, device=dev) * 0.05
+                b = torch.randn(cout, device=dev)
+                ms = timeit(lambda: K.conv_fwd_stats(xi, w, b, pad=(taps - 1) // 2, precision=prec), once)
+                report(f"convstats_{nm}_{tag}", ms, rows * (cin + cout) * 4, 2.0 * rows * cin * cout * taps)
+                del xi
             if want(f"wgrad_{nm}_{tag}"):
                 xi = torch.randn(NB, t, V, cin, device=dev)
                 dy = torch.randn(NB, t, V, cout, device=dev)
