@@ -67,8 +67,14 @@ __global__ void __launch_bounds__(256) colsum_strip_kernel(const float* x, const
 }
 
 // Vectorised variant for channels % 4 == 0 and 256 % (channels/4) == 0 (64, 128, 256, ...; outer == 1 or not).
+// mask_bits (MODE 1, contiguous rows only): the ReLU mask as one bit per element, bit (e & 31) of word e >> 5 for the linear element
+// index e = row * channels + c, written by bn_apply_kernel -- read instead of the fp32 mask tensor (1/32 of the bytes).
+__device__ __forceinline__ unsigned mask_nibble(const unsigned* bits, long long off) {
+    return (__ldg(bits + (off >> 5)) >> (unsigned)(off & 31)) & 0xFu;
+}
+
 template <int MODE>
-__global__ void __launch_bounds__(256) colsum_vec_kernel(const float* x, const float* dout, const float* mask,
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const float* x, const float* dout, const float* mask, const unsigned* mask_bits,
                                                          const float* mean, const float* invstd,
                                                          RowMap m, long long rows, float* part) {
     extern __shared__ __align__(16) float smv[];   // [2][lanes_r][channels]
@@ -93,7 +99,13 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const float* x, const f
             s1.x = fmaf(v.x, v.x, s1.x); s1.y = fmaf(v.y, v.y, s1.y); s1.z = fmaf(v.z, v.z, s1.z); s1.w = fmaf(v.w, v.w, s1.w);
         } else {
             float4 g = __ldg(reinterpret_cast<const float4*>(dout + off));
-            if (mask != nullptr) {
+            if (mask_bits != nullptr) {
+                const unsigned nib = mask_nibble(mask_bits, off);
+                if (!(nib & 1u)) g.x = 0.f;
+                if (!(nib & 2u)) g.y = 0.f;
+                if (!(nib & 4u)) g.z = 0.f;
+                if (!(nib & 8u)) g.w = 0.f;
+            } else if (mask != nullptr) {
                 float4 k = __ldg(reinterpret_cast<const float4*>(mask + off));
                 if (!(k.x > 0.f)) g.x = 0.f;
                 if (!(k.y > 0.f)) g.y = 0.f;
@@ -174,11 +186,16 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* part, int
 template <bool VEC>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const float* y, const float* scale, const float* shift, int res_mode,
                                                        const float* res, const float* scale2, const float* shift2, int relu,
-                                                       float* out, RowMap m, long long rows) {
+                                                       float* out, unsigned* mask_bits, RowMap m, long long rows) {
     constexpr int W = VEC ? 4 : 1;
     const int cq = m.channels / W;
     const long long total = rows * cq;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    // the trip count is uniform per warp (mask words are assembled with full-warp shuffles); lanes past the end idle
+    for (long long idx0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); idx0 < total; idx0 += (long long)gridDim.x * blockDim.x) {
+        const long long idx = idx0 + (threadIdx.x & 31);
+        const bool live = idx < total;
+        unsigned nib = 0u;
+        if (live) {
         const long long r = idx / cq;
         const int c = (int)(idx - r * cq) * W;
         const long long off = m.row_offset(r) + c;
@@ -196,12 +213,22 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* y, const flo
             }
             if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
             *reinterpret_cast<float4*>(out + off) = o;
+            nib = (o.x > 0.f ? 1u : 0u) | (o.y > 0.f ? 2u : 0u) | (o.z > 0.f ? 4u : 0u) | (o.w > 0.f ? 8u : 0u);
         } else {
             float o = fmaf(__ldg(y + off), scale[c], shift[c]);
             if (res_mode == AGCN_RES_TENSOR) o += __ldg(res + off);
             else if (res_mode == AGCN_RES_AFFINE) o += fmaf(__ldg(res + off), scale2[c], shift2[c]);
             if (relu) o = fmaxf(o, 0.f);
             out[off] = o;
+        }
+        }
+        if (VEC && mask_bits != nullptr) {
+            // eight consecutive lanes hold the 32 bits of one word (element offset = 4 * idx for contiguous rows)
+            unsigned wbits = nib << (4u * (threadIdx.x & 7));
+            wbits |= __shfl_xor_sync(0xffffffffu, wbits, 1);
+            wbits |= __shfl_xor_sync(0xffffffffu, wbits, 2);
+            wbits |= __shfl_xor_sync(0xffffffffu, wbits, 4);
+            if (live && (threadIdx.x & 7) == 0) mask_bits[idx >> 3] = wbits;
         }
     }
 }
@@ -223,8 +250,8 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* part,
 }
 
 template <bool VEC>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* dout, const float* mask, const float* y, const float* coef,
-                                                           float* dy, float* dres, int dres_acc, RowMap m, long long rows) {
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* dout, const float* mask, const unsigned* mask_bits, const float* y,
+                                                           const float* coef, float* dy, float* dres, int dres_acc, RowMap m, long long rows) {
     constexpr int W = VEC ? 4 : 1;
     const int C = m.channels;
     const int cq = C / W;
@@ -237,7 +264,10 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* dout, co
         if constexpr (VEC) {
             const float4 a = __ldg(reinterpret_cast<const float4*>(dout + off));
             g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w;
-            if (mask) {
+            if (mask_bits) {
+                const unsigned nib = mask_nibble(mask_bits, off);
+                mk[0] = (float)(nib & 1u); mk[1] = (float)((nib >> 1) & 1u); mk[2] = (float)((nib >> 2) & 1u); mk[3] = (float)((nib >> 3) & 1u);
+            } else if (mask) {
                 const float4 k = __ldg(reinterpret_cast<const float4*>(mask + off));
                 mk[0] = k.x; mk[1] = k.y; mk[2] = k.z; mk[3] = k.w;
             }
@@ -308,15 +338,21 @@ static bool vec_ok(const RowMap& m, std::initializer_list<const void*> ptrs) {
     return true;
 }
 
+static bool colsum_vec_shape(const RowMap& m) {
+    const int cq = m.channels / 4;
+    return m.channels % 4 == 0 && cq <= 256 && (256 % cq) == 0 && m.channels <= 1024;
+}
+
 template <int MODE>
 static int launch_colsum(const float* x, const float* dout, const float* mask, const float* mean, const float* invstd,
-                         const RowMap& m, long long rows, float* part, int P, cudaStream_t s) {
+                         const RowMap& m, long long rows, float* part, int P, cudaStream_t s, const unsigned* mask_bits = nullptr) {
     const int cq = m.channels / 4;
-    const bool vec = vec_ok(m, {x, dout, mask, mean, invstd}) && cq <= 256 && (256 % cq) == 0 && m.channels <= 1024;
+    const bool vec = vec_ok(m, {x, dout, mask, mean, invstd}) && colsum_vec_shape(m);
+    if (mask_bits != nullptr && !vec) return fail(AGCN_ERR_UNSUPPORTED, "bn column sums: a bit mask needs the vectorised layout");
     if (vec) {
         const int lanes_r = 256 / cq;
         size_t smem = (size_t)2 * lanes_r * m.channels * sizeof(float);
-        colsum_vec_kernel<MODE><<<P, 256, smem, s>>>(x, dout, mask, mean, invstd, m, rows, part);
+        colsum_vec_kernel<MODE><<<P, 256, smem, s>>>(x, dout, mask, mask_bits, mean, invstd, m, rows, part);
     } else {
         dim3 grid((unsigned)P, (unsigned)ceil_div(m.channels, 32));
         colsum_strip_kernel<MODE><<<grid, 256, 0, s>>>(x, dout, mask, mean, invstd, m, rows, part);
@@ -387,9 +423,18 @@ extern "C" AGCN_API int agcn_bn_finalize(const float* part, int nparts, long lon
     return check_launch("agcn_bn_finalize");
 }
 
-extern "C" AGCN_API int agcn_bn_apply(const float* y, const float* scale, const float* shift,
-                             int res_mode, const float* res, const float* scale2, const float* shift2,
-                             int relu, float* out, int outer, int inner, long long outer_stride, int channels, void* stream) {
+extern "C" AGCN_API size_t agcn_bn_mask_words(int outer, int inner, int channels) {
+    // one bit per element of a CONTIGUOUS [rows][channels] tensor; only layouts both the writer (agcn_bn_apply_mask) and the
+    // reader (agcn_bn_bwd_bits) vectorise are supported -- 0 otherwise (use the fp32 tensor as the mask then)
+    if (outer != 1 || inner <= 0 || channels <= 0) return 0;
+    RowMap m{1, inner, 0, channels};
+    if (!colsum_vec_shape(m)) return 0;
+    return (size_t)(((long long)inner * channels + 31) / 32);
+}
+
+static int bn_apply_impl(const float* y, const float* scale, const float* shift,
+                         int res_mode, const float* res, const float* scale2, const float* shift2,
+                         int relu, float* out, unsigned* mask_bits, int outer, int inner, long long outer_stride, int channels, void* stream) {
     int rc = check_map("agcn_bn_apply", outer, inner, outer_stride, channels);
     if (rc) return rc;
     AGCN_REQUIRE(y && scale && shift && out, AGCN_ERR_NULL, "agcn_bn_apply: null pointer");
@@ -399,18 +444,35 @@ extern "C" AGCN_API int agcn_bn_apply(const float* y, const float* scale, const 
     RowMap m{outer, inner, outer_stride, channels};
     const long long rows = (long long)outer * inner;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (vec_ok(m, {y, scale, shift, res, scale2, shift2, out}))
-        bn_apply_kernel<true><<<elementwise_blocks(rows * (channels / 4)), 256, 0, s>>>(y, scale, shift, res_mode, res, scale2, shift2, relu, out, m, rows);
+    const bool vec = vec_ok(m, {y, scale, shift, res, scale2, shift2, out});
+    if (mask_bits != nullptr)
+        AGCN_REQUIRE(vec && agcn_bn_mask_words(outer, inner, channels) > 0, AGCN_ERR_UNSUPPORTED,
+                     "agcn_bn_apply_mask: layout not supported (agcn_bn_mask_words returned 0)");
+    if (vec)
+        bn_apply_kernel<true><<<elementwise_blocks(rows * (channels / 4)), 256, 0, s>>>(y, scale, shift, res_mode, res, scale2, shift2, relu, out, mask_bits, m, rows);
     else
-        bn_apply_kernel<false><<<elementwise_blocks(rows * channels), 256, 0, s>>>(y, scale, shift, res_mode, res, scale2, shift2, relu, out, m, rows);
+        bn_apply_kernel<false><<<elementwise_blocks(rows * channels), 256, 0, s>>>(y, scale, shift, res_mode, res, scale2, shift2, relu, out, nullptr, m, rows);
     return check_launch("agcn_bn_apply");
 }
 
-extern "C" AGCN_API int agcn_bn_bwd(const float* dout, const float* mask_out, const float* y,
-                           const float* save_mean, const float* save_invstd, const float* gamma,
-                           float* dy, float* dgamma, float* dbeta, float* dres, int dres_accumulate,
-                           int outer, int inner, long long outer_stride, int channels,
-                           void* workspace, size_t workspace_bytes, void* stream) {
+extern "C" AGCN_API int agcn_bn_apply(const float* y, const float* scale, const float* shift,
+                             int res_mode, const float* res, const float* scale2, const float* shift2,
+                             int relu, float* out, int outer, int inner, long long outer_stride, int channels, void* stream) {
+    return bn_apply_impl(y, scale, shift, res_mode, res, scale2, shift2, relu, out, nullptr, outer, inner, outer_stride, channels, stream);
+}
+
+extern "C" AGCN_API int agcn_bn_apply_mask(const float* y, const float* scale, const float* shift,
+                                  int res_mode, const float* res, const float* scale2, const float* shift2,
+                                  int relu, float* out, unsigned* mask_bits, int inner, int channels, void* stream) {
+    AGCN_REQUIRE(mask_bits, AGCN_ERR_NULL, "agcn_bn_apply_mask: null mask pointer");
+    return bn_apply_impl(y, scale, shift, res_mode, res, scale2, shift2, relu, out, mask_bits, 1, inner, 0, channels, stream);
+}
+
+static int bn_bwd_impl(const float* dout, const float* mask_out, const unsigned* mask_bits, const float* y,
+                       const float* save_mean, const float* save_invstd, const float* gamma,
+                       float* dy, float* dgamma, float* dbeta, float* dres, int dres_accumulate,
+                       int outer, int inner, long long outer_stride, int channels,
+                       void* workspace, size_t workspace_bytes, void* stream) {
     int rc = check_map("agcn_bn_bwd", outer, inner, outer_stride, channels);
     if (rc) return rc;
     AGCN_REQUIRE(dout && y && save_mean && save_invstd && workspace, AGCN_ERR_NULL, "agcn_bn_bwd: null pointer");
@@ -421,17 +483,38 @@ extern "C" AGCN_API int agcn_bn_bwd(const float* dout, const float* mask_out, co
     float* part = static_cast<float*>(workspace);
     float* coef = part + (size_t)kMaxPartials * 2 * channels;
     const int P = num_partials(rows);
-    rc = launch_colsum<1>(y, dout, mask_out, save_mean, save_invstd, m, rows, part, P, s);
+    if (mask_bits != nullptr)
+        AGCN_REQUIRE(agcn_bn_mask_words(outer, inner, channels) > 0 && vec_ok(m, {dout, y, dy, dres, workspace}), AGCN_ERR_UNSUPPORTED,
+                     "agcn_bn_bwd_bits: layout not supported (agcn_bn_mask_words returned 0)");
+    rc = launch_colsum<1>(y, dout, mask_out, save_mean, save_invstd, m, rows, part, P, s, mask_bits);
     if (rc) return rc;
     bn_bwd_finalize_kernel<<<ceil_div(channels, 32), 256, 0, s>>>(part, P, channels, (double)rows, gamma, save_mean, save_invstd, dgamma, dbeta, coef);
     rc = check_launch("agcn_bn_bwd(finalize)");
     if (rc) return rc;
     if (dy == nullptr && dres == nullptr) return AGCN_OK;
     if (vec_ok(m, {dout, mask_out, y, dy, dres, coef}))
-        bn_bwd_apply_kernel<true><<<elementwise_blocks(rows * (channels / 4)), 256, 0, s>>>(dout, mask_out, y, coef, dy, dres, dres_accumulate, m, rows);
+        bn_bwd_apply_kernel<true><<<elementwise_blocks(rows * (channels / 4)), 256, 0, s>>>(dout, mask_out, mask_bits, y, coef, dy, dres, dres_accumulate, m, rows);
     else
-        bn_bwd_apply_kernel<false><<<elementwise_blocks(rows * channels), 256, 0, s>>>(dout, mask_out, y, coef, dy, dres, dres_accumulate, m, rows);
+        bn_bwd_apply_kernel<false><<<elementwise_blocks(rows * channels), 256, 0, s>>>(dout, mask_out, nullptr, y, coef, dy, dres, dres_accumulate, m, rows);
     return check_launch("agcn_bn_bwd(apply)");
+}
+
+extern "C" AGCN_API int agcn_bn_bwd(const float* dout, const float* mask_out, const float* y,
+                           const float* save_mean, const float* save_invstd, const float* gamma,
+                           float* dy, float* dgamma, float* dbeta, float* dres, int dres_accumulate,
+                           int outer, int inner, long long outer_stride, int channels,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+    return bn_bwd_impl(dout, mask_out, nullptr, y, save_mean, save_invstd, gamma, dy, dgamma, dbeta, dres, dres_accumulate,
+                       outer, inner, outer_stride, channels, workspace, workspace_bytes, stream);
+}
+
+extern "C" AGCN_API int agcn_bn_bwd_bits(const float* dout, const unsigned* mask_bits, const float* y,
+                                const float* save_mean, const float* save_invstd, const float* gamma,
+                                float* dy, float* dgamma, float* dbeta, float* dres, int dres_accumulate,
+                                int inner, int channels, void* workspace, size_t workspace_bytes, void* stream) {
+    AGCN_REQUIRE(mask_bits, AGCN_ERR_NULL, "agcn_bn_bwd_bits: null mask pointer");
+    return bn_bwd_impl(dout, nullptr, mask_bits, y, save_mean, save_invstd, gamma, dy, dgamma, dbeta, dres, dres_accumulate,
+                       1, inner, 0, channels, workspace, workspace_bytes, stream);
 }
 
 extern "C" AGCN_API int agcn_pool_fwd(const float* x, float* out, int groups, int rows_per_group, int channels, void* stream) {

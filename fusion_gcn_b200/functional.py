@@ -67,6 +67,13 @@ def _conv_bn(x, w, bias, gamma, beta, buf: BnBuffers, training: bool, prec: int,
     return y, _bn_forward(y, gamma, beta, buf, training)
 
 
+def _apply(want_mask, *args, **kw):
+    """bn_apply -> (out, ReLU bit mask | None); the mask is only produced when the backward will need it."""
+    if want_mask:
+        return K.bn_apply(*args, want_mask=True, **kw)
+    return K.bn_apply(*args, **kw), None
+
+
 def _zero_bias(like, n):
     """Gradient of a conv bias that feeds a training-mode BatchNorm: BN subtracts the batch mean, so the loss does not
     depend on the bias and its gradient is identically zero (the reference's autograd produces ~1e-9 rounding
@@ -90,6 +97,7 @@ def gcn_forward(x, adj_a, adj_b, wa, ba, wb, bb, wd, bd, bn_w, bn_b, down_w, dow
     wdc = torch.cat([w.reshape(cout, 1, cin) for w in wd], dim=2).contiguous()
     bdc = bd[0] + bd[1] + bd[2]
 
+    want_mask = ctx is not None and spec.training        # the backward reads the ReLU mask as one bit per element
     e = K.conv_fwd(x, wab, bab, precision=prec)                                        # theta / phi embeddings
     nchunk = K.pick_nchunk(nb, t, v, ci)
     s_part = K.joint_gram(e, e, groups=3, offa=0, stridea=2 * ci, offb=ci, strideb=2 * ci, width=ci, nchunk=nchunk, precision=prec)
@@ -99,14 +107,14 @@ def gcn_forward(x, adj_a, adj_b, wa, ba, wb, bb, wd, bd, bn_w, bn_b, down_w, dow
     y, (sc, sh, mean, invstd) = _conv_bn(z, wdc, bdc, bn_w, bn_b, spec.bn_gcn, spec.training, prec)
     if spec.has_down:
         yd, (sc2, sh2, mean2, invstd2) = _conv_bn(x, down_w.reshape(cout, 1, cin), down_b, dbn_w, dbn_b, spec.bn_down, spec.training, prec)
-        o = K.bn_apply(y, sc, sh, res_mode=K.RES_AFFINE, res=yd, scale2=sc2, shift2=sh2, relu=True)
+        o, o_bits = _apply(want_mask, y, sc, sh, res_mode=K.RES_AFFINE, res=yd, scale2=sc2, shift2=sh2, relu=True)
     else:
         yd = mean2 = invstd2 = None
-        o = K.bn_apply(y, sc, sh, res_mode=K.RES_TENSOR, res=x, relu=True)
+        o, o_bits = _apply(want_mask, y, sc, sh, res_mode=K.RES_TENSOR, res=x, relu=True)
     if spec.attention_out is not None:
         spec.attention_out[:] = [p[:, k] for k in range(3)]
     if ctx is not None:
-        ctx.update(x=x, e=e, p=p, g=g, z=z, y=y, yd=yd, o=o.detach(), mean=mean, invstd=invstd, mean2=mean2, invstd2=invstd2,
+        ctx.update(x=x, e=e, p=p, g=g, z=z, y=y, yd=yd, o=o.detach(), o_bits=o_bits, mean=mean, invstd=invstd, mean2=mean2, invstd2=invstd2,
                    wab=wab, wdc=wdc, nchunk=nchunk, scale=scale, ci=ci)
     return o
 
@@ -119,8 +127,8 @@ def gcn_backward(d_o, ctx, bn_w, dbn_w, down_w, spec: UnitSpec, dx=None, need_dx
     cout, ci, prec = spec.cout, ctx["ci"], spec.precision
     have = dx is not None
     if spec.has_down:
-        dy, dgam, dbet = K.bn_bwd(d_o, o, y, ctx["mean"], ctx["invstd"], bn_w)
-        dyd, dgam2, dbet2 = K.bn_bwd(d_o, o, ctx["yd"], ctx["mean2"], ctx["invstd2"], dbn_w)
+        dy, dgam, dbet = K.bn_bwd(d_o, o, y, ctx["mean"], ctx["invstd"], bn_w, mask_bits=ctx["o_bits"])
+        dyd, dgam2, dbet2 = K.bn_bwd(d_o, o, ctx["yd"], ctx["mean2"], ctx["invstd2"], dbn_w, mask_bits=ctx["o_bits"])
         wdown = down_w.reshape(cout, 1, cin)
         d_down_w, _ = K.conv_wgrad(dyd, x, want_bias=False, precision=prec)
         d_down_b = _zero_bias(x, cout)
@@ -131,7 +139,7 @@ def gcn_backward(d_o, ctx, bn_w, dbn_w, down_w, spec: UnitSpec, dx=None, need_dx
         if need_dx and dx is None:
             dx = torch.empty_like(x)
         dy, dgam, dbet = K.bn_bwd(d_o, o, y, ctx["mean"], ctx["invstd"], bn_w,
-                                  dres=dx if need_dx else None, dres_accumulate=have)
+                                  dres=dx if need_dx else None, dres_accumulate=have, mask_bits=ctx["o_bits"])
         have = have or need_dx
         dgam2 = dbet2 = d_down_w = d_down_b = None
     d_wdc, _ = K.conv_wgrad(dy, z, want_bias=False, precision=prec)
@@ -175,16 +183,17 @@ def tcn_forward(o, x_res, wt, bt, bn_w, bn_b, wr, br, rbn_w, rbn_b, spec: UnitSp
     wtp = _pack_taps(wt)
     u, (sc, sh, mean, invstd) = _conv_bn(o, wtp, bt, bn_w, bn_b, spec.bn_tcn, spec.training, prec, t_out=t_out, stride=s, pad=pad)
     ur = mean2 = invstd2 = wrp = None
+    want_mask = ctx is not None and spec.training and spec.relu_out
     if spec.residual == "identity":
-        out = K.bn_apply(u, sc, sh, res_mode=K.RES_TENSOR, res=x_res, relu=spec.relu_out)
+        out, out_bits = _apply(want_mask, u, sc, sh, res_mode=K.RES_TENSOR, res=x_res, relu=spec.relu_out)
     elif spec.residual == "conv":
         wrp = _pack_taps(wr)
         ur, (sc2, sh2, mean2, invstd2) = _conv_bn(x_res, wrp, br, rbn_w, rbn_b, spec.bn_res, spec.training, prec, t_out=t_out, stride=s, pad=0)
-        out = K.bn_apply(u, sc, sh, res_mode=K.RES_AFFINE, res=ur, scale2=sc2, shift2=sh2, relu=spec.relu_out)
+        out, out_bits = _apply(want_mask, u, sc, sh, res_mode=K.RES_AFFINE, res=ur, scale2=sc2, shift2=sh2, relu=spec.relu_out)
     else:
-        out = K.bn_apply(u, sc, sh, relu=spec.relu_out)
+        out, out_bits = _apply(want_mask, u, sc, sh, relu=spec.relu_out)
     if ctx is not None:
-        ctx.update(t_o=o.detach(), t_x=x_res, u=u, ur=ur, out=out.detach(), t_mean=mean, t_invstd=invstd, t_mean2=mean2, t_invstd2=invstd2,
+        ctx.update(t_o=o.detach(), t_x=x_res, u=u, ur=ur, out=out.detach(), out_bits=out_bits, t_mean=mean, t_invstd=invstd, t_mean2=mean2, t_invstd2=invstd2,
                    wtp=wtp, wrp=wrp, pad=pad)
     return out
 
@@ -195,21 +204,22 @@ def tcn_backward(d_out, ctx, bn_w, rbn_w, spec: UnitSpec, need_dres=True, need_d
     s, pad, prec = spec.stride, ctx["pad"], spec.precision
     ksz = spec.kernel_size
     mask = out if spec.relu_out else None
+    bits = ctx["out_bits"] if spec.relu_out else None
     d_xres = None
     d_wr = d_br = dgam2 = dbet2 = None
     if spec.residual == "identity":
         d_xres = torch.empty_like(x_res) if need_dres else None
-        du, dgam, dbet = K.bn_bwd(d_out, mask, u, ctx["t_mean"], ctx["t_invstd"], bn_w, dres=d_xres, dres_accumulate=False)
+        du, dgam, dbet = K.bn_bwd(d_out, mask, u, ctx["t_mean"], ctx["t_invstd"], bn_w, dres=d_xres, dres_accumulate=False, mask_bits=bits)
     elif spec.residual == "conv":
-        du, dgam, dbet = K.bn_bwd(d_out, mask, u, ctx["t_mean"], ctx["t_invstd"], bn_w)
-        dur, dgam2, dbet2 = K.bn_bwd(d_out, mask, ctx["ur"], ctx["t_mean2"], ctx["t_invstd2"], rbn_w)
+        du, dgam, dbet = K.bn_bwd(d_out, mask, u, ctx["t_mean"], ctx["t_invstd"], bn_w, mask_bits=bits)
+        dur, dgam2, dbet2 = K.bn_bwd(d_out, mask, ctx["ur"], ctx["t_mean2"], ctx["t_invstd2"], rbn_w, mask_bits=bits)
         d_wrp, _ = K.conv_wgrad(dur, x_res, taps=1, stride=s, pad=0, want_bias=False, precision=prec)
         d_br = _zero_bias(d_out, d_wrp.shape[0])
         d_wr = d_wrp.permute(0, 2, 1).unsqueeze(-1)
         if need_dres:
             d_xres = K.conv_fwd(dur, _t(ctx["wrp"]), t_out=x_res.shape[1], stride=s, pad=0, transposed=True, precision=prec)
     else:
-        du, dgam, dbet = K.bn_bwd(d_out, mask, u, ctx["t_mean"], ctx["t_invstd"], bn_w)
+        du, dgam, dbet = K.bn_bwd(d_out, mask, u, ctx["t_mean"], ctx["t_invstd"], bn_w, mask_bits=bits)
     d_wtp, _ = K.conv_wgrad(du, o, taps=ksz, stride=s, pad=pad, want_bias=False, precision=prec)
     d_bt = _zero_bias(d_out, d_wtp.shape[0])
     d_o = None

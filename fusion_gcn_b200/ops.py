@@ -267,22 +267,34 @@ def bn_stats(x, gamma, beta, running_mean, running_var, nbt, momentum, eps, trai
     return scale[0], scale[1], scale[2], scale[3]
 
 
-def bn_apply(y, scale, shift, *, res_mode=RES_NONE, res=None, scale2=None, shift2=None, relu=False, rowmap=None, out=None):
+def bn_apply(y, scale, shift, *, res_mode=RES_NONE, res=None, scale2=None, shift2=None, relu=False, rowmap=None, out=None,
+             want_mask=False):
+    """out = act(scale*y + shift + R).  ``want_mask``: also return the ReLU mask (out > 0) as one bit per element (int32 words,
+    agcn_bn_apply_mask) for bn_bwd(mask_bits=...), or None when the layout is not supported: -> (out, bits | None)."""
     outer, inner, ostride, c = _rowmap(y, rowmap)
     if out is None:
         out = torch.empty_like(y)
     _check_strided(y, res, out)
     _check(scale, shift, scale2, shift2)
+    if want_mask:
+        words = capi.lib().agcn_bn_mask_words(outer, inner, c) if (y.is_contiguous() and out.is_contiguous() and (res is None or res.is_contiguous())) else 0
+        if words:
+            bits = torch.empty(words, device=y.device, dtype=torch.int32)
+            _call("agcn_bn_apply_mask", y.data_ptr(), _ptr(scale), _ptr(shift), res_mode, _ptr(res), _ptr(scale2), _ptr(shift2), int(relu),
+                  out.data_ptr(), bits.data_ptr(), inner, c, _stream(), sig=(outer, inner, c, res_mode, int(relu)),
+                  work=(0.0, 4.0 * outer * inner * c * (2 if res_mode == RES_NONE else 3)), alias="agcn_bn_apply")
+            return out, bits
     _call("agcn_bn_apply", y.data_ptr(), _ptr(scale), _ptr(shift), res_mode, _ptr(res), _ptr(scale2), _ptr(shift2), int(relu),
           out.data_ptr(), outer, inner, ostride, c, _stream(), sig=(outer, inner, c, res_mode, int(relu)),
           work=(0.0, 4.0 * outer * inner * c * (2 if res_mode == RES_NONE else 3)))
-    return out
+    return (out, None) if want_mask else out
 
 
 def bn_bwd(dout, mask_out, y, save_mean, save_invstd, gamma, *, want_dy=True, dy=None, dres=None, dres_accumulate=False,
-           rowmap=None):
+           rowmap=None, mask_bits=None):
     """-> dy | None, dgamma, dbeta; optionally writes / accumulates the masked gradient into ``dres``.
-    ``dy`` may be a preallocated tensor addressed with the same rowmap as ``y``."""
+    ``dy`` may be a preallocated tensor addressed with the same rowmap as ``y``.  ``mask_bits`` (from bn_apply(want_mask=True))
+    replaces the fp32 tensor ``mask_out`` as the ReLU mask."""
     outer, inner, ostride, c = _rowmap(y, rowmap)
     if want_dy and dy is None:
         dy = torch.empty_like(y)
@@ -290,6 +302,16 @@ def bn_bwd(dout, mask_out, y, save_mean, save_invstd, gamma, *, want_dy=True, dy
     _check(save_mean, save_invstd, gamma)
     dgb = torch.empty((2, c), device=y.device, dtype=torch.float32)
     ws, nbytes = _bn_ws(c, y.device)
+    if mask_bits is not None:
+        if mask_bits.dtype != torch.int32 or not mask_bits.is_cuda:
+            raise RuntimeError("bn_bwd: mask_bits must be the int32 CUDA tensor returned by bn_apply(want_mask=True)")
+        _check(dout, y, dy, dres)
+        _call("agcn_bn_bwd_bits", dout.data_ptr(), mask_bits.data_ptr(), y.data_ptr(), _ptr(save_mean), _ptr(save_invstd), _ptr(gamma),
+              _ptr(dy), dgb[0].data_ptr(), dgb[1].data_ptr(), _ptr(dres), int(dres_accumulate), inner, c, _ptr(ws), nbytes, _stream(),
+              sig=(outer, inner, c, 2, int(dy is not None), int(dres is not None), int(dres_accumulate)),
+              work=(0.0, 4.0 * outer * inner * c * (2 * 2 + 2.0 / 32 + int(dy is not None) + int(dres is not None) * (1 + int(dres_accumulate)))),
+              alias="agcn_bn_bwd")
+        return dy, dgb[0], dgb[1]
     _call("agcn_bn_bwd", dout.data_ptr(), _ptr(mask_out), y.data_ptr(), _ptr(save_mean), _ptr(save_invstd), _ptr(gamma),
           _ptr(dy), dgb[0].data_ptr(), dgb[1].data_ptr(), _ptr(dres), int(dres_accumulate), outer, inner, ostride, c,
           _ptr(ws), nbytes, _stream(),

@@ -168,6 +168,20 @@ int agcn_bn_apply(const float* y, const float* scale, const float* shift,
                   int res_mode, const float* res, const float* scale2, const float* shift2,
                   int relu, float* out, int outer, int inner, long long outer_stride, int channels, void* stream);
 
+/* ReLU mask as ONE BIT per element (bit e & 31 of word e >> 5, e = row * channels + c) for contiguous [inner][channels]
+ * tensors: agcn_bn_apply_mask = agcn_bn_apply that also writes the bits of (out > 0); agcn_bn_bwd_bits = agcn_bn_bwd reading
+ * them instead of the fp32 tensor mask_out (the two backward passes then read 1/32 of the mask bytes).
+ * agcn_bn_mask_words returns the number of 32-bit words, or 0 when the layout is not supported (outer != 1, channels
+ * not a multiple of 4, channels/4 not a divisor of 256) -- use the tensor mask then.                                  */
+size_t agcn_bn_mask_words(int outer, int inner, int channels);
+int agcn_bn_apply_mask(const float* y, const float* scale, const float* shift,
+                       int res_mode, const float* res, const float* scale2, const float* shift2,
+                       int relu, float* out, unsigned* mask_bits, int inner, int channels, void* stream);
+int agcn_bn_bwd_bits(const float* dout, const unsigned* mask_bits, const float* y,
+                     const float* save_mean, const float* save_invstd, const float* gamma,
+                     float* dy, float* dgamma, float* dbeta, float* dres, int dres_accumulate,
+                     int inner, int channels, void* workspace, size_t workspace_bytes, void* stream);
+
 /* BatchNorm backward through an optional ReLU mask:
  *   g = dout * [mask_out > 0]  (g = dout when mask_out == NULL)
  *   dbeta = sum g;  dgamma = sum g*xhat;  dy = gamma*invstd*(g - dbeta/m - xhat*dgamma/m),  xhat = (y-mean)*invstd

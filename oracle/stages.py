@@ -178,7 +178,13 @@ def bn_stats(x, gamma, beta, running_mean, running_var, nbt, momentum, eps, trai
     return scale, b - mean * scale, mean, invstd
 
 
-def bn_apply(y, scale, shift, *, res_mode=RES_NONE, res=None, scale2=None, shift2=None, relu=False, rowmap=None, out=None):
+def bn_apply(y, scale, shift, *, res_mode=RES_NONE, res=None, scale2=None, shift2=None, relu=False, rowmap=None, out=None,
+             want_mask=False):
+    r = _bn_apply(y, scale, shift, res_mode=res_mode, res=res, scale2=scale2, shift2=shift2, relu=relu, rowmap=rowmap, out=out)
+    return (r, (r > 0)) if want_mask else r            # the "bit mask" of the CUDA path is a bool tensor here
+
+
+def _bn_apply(y, scale, shift, *, res_mode=RES_NONE, res=None, scale2=None, shift2=None, relu=False, rowmap=None, out=None):
     if out is None:
         out = torch.empty_like(y)
     yv = _rows_view(y, rowmap)
@@ -194,9 +200,11 @@ def bn_apply(y, scale, shift, *, res_mode=RES_NONE, res=None, scale2=None, shift
 
 
 def bn_bwd(dout, mask_out, y, save_mean, save_invstd, gamma, *, want_dy=True, dy=None, dres=None, dres_accumulate=False,
-           rowmap=None):
+           rowmap=None, mask_bits=None):
     g = _rows_view(dout, rowmap)
-    if mask_out is not None:
+    if mask_bits is not None:
+        g = g * mask_bits.reshape(g.shape).to(g.dtype)
+    elif mask_out is not None:
         g = g * (_rows_view(mask_out, rowmap) > 0).to(g.dtype)
     yv = _rows_view(y, rowmap)
     c = yv.shape[-1]

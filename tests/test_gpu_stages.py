@@ -246,6 +246,34 @@ def test_bn_rowmap_data_bn_addressing(K):
         assert rel_err(out[2], flat.mean(0)) <= 5e-6
 
 
+@pytest.mark.parametrize("rows,c", [(1000, 64), (4099, 256), (777, 128), (9001, 16), (50, 12), (333, 515), (37, 32)])
+def test_relu_bit_mask_matches_tensor_mask(K, rows, c):
+    """agcn_bn_apply_mask / agcn_bn_bwd_bits: the ReLU mask as one bit per element gives bit-identical results to the fp32
+    tensor mask (rows * c not a multiple of 32 included); unsupported layouts return no bit mask."""
+    y, res = (rnd(rows, c) * 2).cuda(), rnd(rows, c, seed=1).cuda()
+    sc, sh = (rnd(c, seed=2) * 0.3 + 1).cuda(), (rnd(c, seed=3) * 0.1).cuda()
+    out_ref = K.bn_apply(y, sc, sh, res_mode=K.RES_TENSOR, res=res, relu=True)
+    out, bits = K.bn_apply(y, sc, sh, res_mode=K.RES_TENSOR, res=res, relu=True, want_mask=True)
+    assert torch.equal(out, out_ref)
+    if c % 4 or 256 % (c // 4):
+        assert bits is None
+        return
+    assert bits is not None and bits.numel() == (rows * c + 31) // 32
+    flat = (out_ref > 0).flatten().cpu()
+    pad = torch.zeros(bits.numel() * 32, dtype=torch.bool)
+    pad[:flat.numel()] = flat
+    want = (pad.view(-1, 32).long() << torch.arange(32)).sum(1)
+    assert torch.equal(bits.cpu().long() & 0xFFFFFFFF, want)
+    dout, mean, invstd, gamma = rnd(rows, c, seed=4).cuda(), (rnd(c, seed=5) * 0.1).cuda(), (rnd(c, seed=6).abs() + 0.5).cuda(), (rnd(c, seed=7) + 1).cuda()
+    for acc in (False, True):
+        dres_a, dres_b = rnd(rows, c, seed=8).cuda(), rnd(rows, c, seed=8).cuda()
+        a = K.bn_bwd(dout, out_ref, y, mean, invstd, gamma, dres=dres_a, dres_accumulate=acc)
+        b = K.bn_bwd(dout, None, y, mean, invstd, gamma, dres=dres_b, dres_accumulate=acc, mask_bits=bits)
+        for u, v in zip(a, b):
+            assert torch.equal(u, v)
+        assert torch.equal(dres_a, dres_b)
+
+
 @pytest.mark.parametrize("groups,rows,c", [(4, 100, 256), (3, 37, 60), (2, 1, 8)])
 def test_pool(K, groups, rows, c):
     x = rnd(groups * rows, c).view(groups, rows, c)

@@ -110,6 +110,11 @@ def main():
             report(f"bn_apply_res_{tag}", ms, act * 3, 0)
             ms = timeit(lambda: K.bn_bwd(x, x, x, mean, invstd, gamma), once)
             report(f"bn_bwd_{tag}", ms, act * 6, 0)
+            _, bits = K.bn_apply(x, sc, sh, res_mode=K.RES_TENSOR, res=x, relu=True, want_mask=True)
+            ms = timeit(lambda: K.bn_apply(x, sc, sh, res_mode=K.RES_TENSOR, res=x, relu=True, want_mask=True), once)
+            report(f"bn_apply_res_mask_{tag}", ms, act * 3, 0)
+            ms = timeit(lambda: K.bn_bwd(x, None, x, mean, invstd, gamma, mask_bits=bits), once)
+            report(f"bn_bwd_bits_{tag}", ms, act * 4, 0)
         del x
         torch.cuda.empty_cache()
     if want("first_unit"):
