@@ -262,31 +262,59 @@ mix_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 }
             } else if (!p.bwd) {
                 // column j = k*32 + v -> out[.., v, k*W + cb*32 + c]
+                // two 16-column loads (one subset's 32 joint columns) per TMEM round trip; batching all six cost registers the
+                // 480-thread 3xTF32 variant does not have (spills, 0.30 -> 0.45 ms, profiles/r2c)
 #pragma unroll
-                for (int cg = 0; cg < 6; ++cg) {
-                    float vals[16];
-                    tmem_ld16(taddr + (uint32_t)(cg * 16), vals);
-                    const int k = cg >> 1, v0 = (cg & 1) * 16;
+                for (int k = 0; k < 3; ++k) {
+                    uint32_t r0[16], r1[16];
+                    tmem_ld16_nowait(taddr + (uint32_t)(k * 32), r0);
+                    tmem_ld16_nowait(taddr + (uint32_t)(k * 32 + 16), r1);
+                    tmem_ld_wait();
                     if (ok) {
 #pragma unroll
                         for (int i = 0; i < 16; ++i)
-                            if (v0 + i < p.v) obase[(long long)(v0 + i) * p.ldout + k * p.width] = vals[i];
+                            if (i < p.v) obase[(long long)i * p.ldout + k * p.width] = __uint_as_float(r0[i]);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (16 + i < p.v) obase[(long long)(16 + i) * p.ldout + k * p.width] = __uint_as_float(r1[i]);
                     }
                 }
             } else {
                 // column j = u -> out[.., u, cb*32 + c]
+                if constexpr (!SPLIT) {
+                    // both TMEM loads and all the old values (accumulate) are in flight before the first dependent add / store
+                    // (TF32: 0.305 -> 0.237 ms; the 480-thread 3xTF32 variant has no registers for it and keeps the 16-column loop)
+                    uint32_t rv[2][16];
+                    tmem_ld16_nowait(taddr, rv[0]);
+                    tmem_ld16_nowait(taddr + 16u, rv[1]);
+                    float oldv[2][16];
 #pragma unroll
-                for (int cg = 0; cg < 2; ++cg) {
-                    float vals[16];
-                    tmem_ld16(taddr + (uint32_t)(cg * 16), vals);
+                    for (int cg = 0; cg < 2; ++cg)
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            oldv[cg][i] = (ok && p.accumulate && cg * 16 + i < p.v) ? obase[(long long)(cg * 16 + i) * p.ldout] : 0.f;
+                    tmem_ld_wait();
                     if (ok) {
-                        float oldv[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            oldv[i] = (p.accumulate && cg * 16 + i < p.v) ? obase[(long long)(cg * 16 + i) * p.ldout] : 0.f;
+                        for (int cg = 0; cg < 2; ++cg)
 #pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            if (cg * 16 + i < p.v) obase[(long long)(cg * 16 + i) * p.ldout] = vals[i] + oldv[i];
+                            for (int i = 0; i < 16; ++i)
+                                if (cg * 16 + i < p.v) obase[(long long)(cg * 16 + i) * p.ldout] = __uint_as_float(rv[cg][i]) + oldv[cg][i];
+                    }
+                } else {
+#pragma unroll
+                    for (int cg = 0; cg < 2; ++cg) {
+                        float vals[16];
+                        tmem_ld16(taddr + (uint32_t)(cg * 16), vals);
+                        if (ok) {
+                            float oldv[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                oldv[i] = (p.accumulate && cg * 16 + i < p.v) ? obase[(long long)(cg * 16 + i) * p.ldout] : 0.f;
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (cg * 16 + i < p.v) obase[(long long)(cg * 16 + i) * p.ldout] = vals[i] + oldv[i];
+                        }
                     }
                 }
             }
