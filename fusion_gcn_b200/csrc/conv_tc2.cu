@@ -41,6 +41,7 @@ constexpr int kTmemCols2 = 512;
 constexpr uint32_t kStagePitch = 144;                        // bytes per staged output row: 32 floats + 16 bytes (conflict-free 16-byte accesses)
 constexpr uint32_t kStageBytes = 4u * 32u * kStagePitch;     // four epilogue warps
 constexpr uint32_t kSmemBudget = 222u * 1024u;
+constexpr uint32_t kTmaStageBytes = 2u * 128u * 128u;         // TMA-store epilogue: two chunk buffers of 128 rows x 32 floats
 constexpr int kStatCols = 256;                               // fused BatchNorm statistics: widest output the per-warp column sums cover
 constexpr uint32_t kStatBytes = 4u * 2u * kStatCols * 4u;    // four epilogue warps x (sum | sum of squares) x kStatCols floats
 
@@ -64,12 +65,14 @@ struct Tc2Args {
     signed char tap_id[2][kMaxTaps], tap_blk[2][kMaxTaps], tap_off[2][kMaxTaps];
     int blk_t0[2][2];
     int par_val[2];
+    int tma_store;                // 1: epilogue stages 32-column chunks in shared memory and writes them with TMA (bulk tensor stores / reduce-adds)
 };
 
 template <bool SPLIT>
 __global__ void __launch_bounds__(SPLIT ? kThreads2Split : kThreads2, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                const __grid_constant__ CUtensorMap map_blo, Tc2Args a) {
+                const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_y0,
+                const __grid_constant__ CUtensorMap map_y1, Tc2Args a) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_slot = a.a_stage_bytes;
@@ -93,6 +96,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+        if (a.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_y0) : "memory");
         for (int s = 0; s < kMaxA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); mbar_init(a_lo(s), kSplitWarps); }
         for (int s = 0; s < kMaxB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(lo_empty(s), 1); mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
@@ -109,7 +113,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
     // fused BatchNorm statistics: per epilogue warp, sum and sum of squares of every output column it has written
-    float* stat_sm = reinterpret_cast<float*>(smem_raw + (bar_base + kBarBytes + kStageBytes - smem_u32(smem_raw))) + ((threadIdx.x >> 5) & 3) * (2 * kStatCols);
+    const uint32_t tbuf_base = bar_base + 1024u;                   // TMA-store epilogue: two 128-row x 128-byte chunk buffers (1024-aligned)
+    const uint32_t epi_end = a.tma_store ? tbuf_base + kTmaStageBytes : bar_base + kBarBytes + kStageBytes;
+    float* stat_sm = reinterpret_cast<float*>(smem_raw + (epi_end - smem_u32(smem_raw))) + ((threadIdx.x >> 5) & 3) * (2 * kStatCols);
 
     const uint32_t a_tx = (uint32_t)a.nblk * a.blk_rows_bytes;
     const uint32_t b_tx = (uint32_t)a.bn * 128u * (SPLIT ? 2u : 1u);
@@ -226,6 +232,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             for (int i = lane; i < 2 * kStatCols; i += 32) stat_sm[i] = 0.f;
             __syncwarp();
         }
+        uint32_t ck = 0;                                   // chunks stored so far by this CTA (TMA-store epilogue: buffer = ck & 1)
+        const bool issuer = (warp == 2 && lane == 0);      // the thread that issues and tracks the bulk stores
         for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
             long long r = tile;
             const int nt = (int)(r % a.n_tiles_n); r /= a.n_tiles_n;
@@ -264,7 +272,72 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                             tmem_ld16(taddr + (uint32_t)c0, vals);
                             if (wide) tmem_ld16(taddr + (uint32_t)c0 + 16u, vals + 16);
                         }
-                        if (last && !(a.dbg & 4)) {
+                        if (last && a.tma_store) {
+                            // ---- TMA-store epilogue.  The 128 epilogue threads write their rows of the 32-column chunk (+ bias) into a
+                            // 128B-swizzled shared-memory tile, one elected thread hands it to the TMA unit as ONE bulk tensor store (or
+                            // reduce-add when accumulating) of the [tt][v][32] box -- rows outside the tensor are clipped by the hardware,
+                            // and the warps are free to fetch the next chunk while the copy engine drains the tile to HBM.
+                            const uint32_t buf = tbuf_base + (ck & 1u) * (128u * 128u);
+                            if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");     // the store that last read `buf` is done
+                            asm volatile("bar.sync 1, 128;" ::: "memory");
+                            {
+                                const uint32_t srow = buf + (uint32_t)row_local * 128u;
+                                const uint32_t sw = (uint32_t)(row_local & 7);
+#pragma unroll
+                                for (int g = 0; g < 8; ++g) {
+                                    float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
+                                    if (a.bias) bq = __ldg(reinterpret_cast<const float4*>(a.bias + nt * a.bn + c0 + g * 4));
+                                    sts128(srow + (((uint32_t)g ^ sw) << 4),
+                                           make_float4(vals[g * 4] + bq.x, vals[g * 4 + 1] + bq.y, vals[g * 4 + 2] + bq.z, vals[g * 4 + 3] + bq.w));
+                                }
+                            }
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                            asm volatile("bar.sync 1, 128;" ::: "memory");
+                            if (issuer && !(a.dbg & 4)) {
+                                const CUtensorMap* my = (a.transposed && a.par_val[par] == 1) ? &map_y1 : &map_y0;
+                                const int cc0 = nt * a.bn + c0, ct = jt * a.tt;
+                                if (a.accumulate)
+                                    asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                                                 ::"l"(my), "r"(buf), "r"(cc0), "r"(0), "r"(ct), "r"(n) : "memory");
+                                else
+                                    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                                                 ::"l"(my), "r"(buf), "r"(cc0), "r"(0), "r"(ct), "r"(n) : "memory");
+                                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                            } else if (issuer) {
+                                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                            }
+                            ++ck;
+                            if (a.stat_part != nullptr) {
+                                // column sums from the staged tile: lane -> 16-byte column piece (lane & 7), rows (lane >> 3) + 4 i of this warp
+                                const int cq = lane & 7;
+                                float4 ssum = make_float4(0.f, 0.f, 0.f, 0.f), ssq = ssum;
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const int r = q * 32 + i * 4 + (lane >> 3);
+                                    const int rtl = r / a.v;
+                                    if (rtl < a.tt && jt * a.tt + rtl < a.t_out) {
+                                        const float4 o = lds128(buf + (uint32_t)r * 128u + (((uint32_t)cq ^ (uint32_t)(r & 7)) << 4));
+                                        ssum.x += o.x; ssum.y += o.y; ssum.z += o.z; ssum.w += o.w;
+                                        ssq.x = fmaf(o.x, o.x, ssq.x); ssq.y = fmaf(o.y, o.y, ssq.y); ssq.z = fmaf(o.z, o.z, ssq.z); ssq.w = fmaf(o.w, o.w, ssq.w);
+                                    }
+                                }
+#pragma unroll
+                                for (int d = 8; d <= 16; d <<= 1) {
+                                    ssum.x += __shfl_xor_sync(0xffffffffu, ssum.x, d); ssum.y += __shfl_xor_sync(0xffffffffu, ssum.y, d);
+                                    ssum.z += __shfl_xor_sync(0xffffffffu, ssum.z, d); ssum.w += __shfl_xor_sync(0xffffffffu, ssum.w, d);
+                                    ssq.x += __shfl_xor_sync(0xffffffffu, ssq.x, d); ssq.y += __shfl_xor_sync(0xffffffffu, ssq.y, d);
+                                    ssq.z += __shfl_xor_sync(0xffffffffu, ssq.z, d); ssq.w += __shfl_xor_sync(0xffffffffu, ssq.w, d);
+                                }
+                                if (lane < 8) {
+                                    float4* s0 = reinterpret_cast<float4*>(stat_sm + nt * a.bn + c0 + lane * 4);
+                                    float4* s1 = reinterpret_cast<float4*>(stat_sm + kStatCols + nt * a.bn + c0 + lane * 4);
+                                    float4 u0 = *s0, u1 = *s1;
+                                    u0.x += ssum.x; u0.y += ssum.y; u0.z += ssum.z; u0.w += ssum.w;
+                                    u1.x += ssq.x; u1.y += ssq.y; u1.z += ssq.z; u1.w += ssq.w;
+                                    *s0 = u0; *s1 = u1;
+                                }
+                            }
+                        } else if (last && !(a.dbg & 4)) {
                             const uint32_t srow = stage_base + (uint32_t)lane * kStagePitch;
 #pragma unroll
                             for (int g = 0; g < 8; ++g)
@@ -330,6 +403,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         }
+        if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // shared memory must outlive the bulk stores reading it
         if (a.stat_part != nullptr) {
             __syncwarp();
             float* dst = a.stat_part + ((long long)blockIdx.x * 4 + q) * 2 * a.cout;
@@ -477,7 +551,12 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
     a.b_stage_bytes = (uint32_t)bn * 128u;
     const uint32_t a_slot = a.a_stage_bytes, b_slot = a.b_stage_bytes * (split ? 2u : 1u);
     const uint32_t stat_bytes = stat_part != nullptr ? kStatBytes : 0u;
-    const uint32_t budget = kSmemBudget - 1024u - kBarBytes - kStageBytes - stat_bytes;
+    // TMA-store epilogue for the 1x1 convolutions (their time is the output stream: skipping the stores halves it, profiles/r2b);
+    // the 9-tap kernels are bound elsewhere and keep their shared memory for the operand rings
+    static const bool no_tma_store = getenv("AGCN_TC2_NO_TMA_STORE") != nullptr;
+    a.tma_store = (!no_tma_store && taps == 1 && bn % 32 == 0 && aligned16(y)) ? 1 : 0;
+    const uint32_t epi_bytes = a.tma_store ? 1024u + kTmaStageBytes : kBarBytes + kStageBytes;
+    const uint32_t budget = kSmemBudget - 1024u - epi_bytes - stat_bytes;
     // Ring depths.  Weights: 3 slots (2 when tight).  3xTF32 lo residuals: 2 slots, 1 when two would leave a single
     // activation stage.  Everything else goes to the activation ring: payload bytes in flight set the achieved bandwidth.
     a.na = 0; a.nbst = 0; a.nlo = split ? 2 : 0;
@@ -501,7 +580,7 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
         if (nbst < best_b) nbst = best_b;
         a.nbst = nbst;
     }
-    const size_t smem = (size_t)(a.na + a.nlo) * a_slot + (size_t)a.nbst * b_slot + 1024 + kBarBytes + kStageBytes + stat_bytes;
+    const size_t smem = (size_t)(a.na + a.nlo) * a_slot + (size_t)a.nbst * b_slot + 1024 + epi_bytes + stat_bytes;
 
     CUtensorMap map_a, map_b, map_blo;
     {
@@ -537,6 +616,24 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
             if (rc) return rc;
         }
     }
+    CUtensorMap map_y0 = map_a, map_y1 = map_a;
+    if (a.tma_store) {
+        // output tile box: 32 channels x V joints x tt timesteps of one sample.  Transposed stride-s gather: one map per output-time
+        // parity (base shifted by `parity` timesteps, time stride s) so that a tile's rows are dense in the map's coordinates.
+        const int tstep = transposed ? stride : 1;
+        for (int cls = 0; cls < a.nparity; ++cls) {
+            const int pv = transposed ? a.par_val[cls] : 0;
+            const long long nt_cls = transposed ? (t_out - pv + stride - 1) / stride : t_out;
+            cuuint64_t dims[4] = {(cuuint64_t)cout, (cuuint64_t)v, (cuuint64_t)nt_cls, (cuuint64_t)nb};
+            cuuint64_t strides[3] = {(cuuint64_t)cout * 4, (cuuint64_t)tstep * v * cout * 4, (cuuint64_t)t_out * v * cout * 4};
+            cuuint32_t box[4] = {32u, (cuuint32_t)v, (cuuint32_t)a.tt, 1u};
+            cuuint32_t estr[4] = {1, 1, 1, 1};
+            CUresult r = enc(pv == 1 ? &map_y1 : &map_y0, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, y + (long long)pv * v * cout, dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc2: cuTensorMapEncodeTiled(Y) failed with %d", (int)r);
+        }
+    }
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
@@ -550,8 +647,8 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
         if (e != cudaSuccess) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc2: cudaMemsetAsync: %s", cudaGetErrorString(e));
     }
     const long long grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
-    if (split) conv_tc2_kernel<true><<<(unsigned)grid, kThreads2Split, smem, st>>>(map_a, map_b, map_blo, a);
-    else conv_tc2_kernel<false><<<(unsigned)grid, kThreads2, smem, st>>>(map_a, map_b, map_blo, a);
+    if (split) conv_tc2_kernel<true><<<(unsigned)grid, kThreads2Split, smem, st>>>(map_a, map_b, map_blo, map_y0, map_y1, a);
+    else conv_tc2_kernel<false><<<(unsigned)grid, kThreads2, smem, st>>>(map_a, map_b, map_blo, map_y0, map_y1, a);
     if (stat_nparts != nullptr) *stat_nparts = stat_part != nullptr ? (int)grid * 4 : 0;
     return check_launch("agcn_conv_fwd_tc2");
 }
