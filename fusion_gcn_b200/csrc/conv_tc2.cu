@@ -554,7 +554,8 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
     // TMA-store epilogue for the 1x1 convolutions (their time is the output stream: skipping the stores halves it, profiles/r2b);
     // the 9-tap kernels are bound elsewhere and keep their shared memory for the operand rings
     static const bool no_tma_store = getenv("AGCN_TC2_NO_TMA_STORE") != nullptr;
-    a.tma_store = (!no_tma_store && taps == 1 && bn % 32 == 0 && aligned16(y)) ? 1 : 0;
+    static const bool tma_store_all = getenv("AGCN_TC2_TMA_STORE_ALL") != nullptr;      // experiment: also the 9-tap kernels
+    a.tma_store = (!no_tma_store && (taps == 1 || tma_store_all) && bn % 32 == 0 && aligned16(y)) ? 1 : 0;
     const uint32_t epi_bytes = a.tma_store ? 1024u + kTmaStageBytes : kBarBytes + kStageBytes;
     const uint32_t budget = kSmemBudget - 1024u - epi_bytes - stat_bytes;
     // Ring depths.  Weights: 3 slots (2 when tight).  3xTF32 lo residuals: 2 slots, 1 when two would leave a single

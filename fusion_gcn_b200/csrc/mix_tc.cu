@@ -50,6 +50,7 @@ struct MArgs {
     int na, nlo;
     uint32_t a_tile;         // kb * 4 * kBoxBytes
     int ldout;
+    int tma_out;             // 1: outputs leave through per-warp shared-memory tiles and TMA bulk stores / reduce-adds
     int score;               // SCORE_BWD
     int tgroups;             // SCORE_BWD: ceil(t / 4) timestep groups per channel block
     uint32_t mat_bytes;      // padded matrices of one sample: 3 boxes (AGG) or 6 boxes (SCORE_BWD)
@@ -81,10 +82,13 @@ __global__ void pad_mats_kernel(const float* mats, float* gp, int nb, int v, int
     gp[idx] = val;
 }
 
-template <bool SPLIT>
+// MODE: 0 AGG_FWD, 1 AGG_BWD, 2 SCORE_BWD -- a template parameter so that each variant carries only its own epilogue
+template <bool SPLIT, int MODE>
 __global__ void __launch_bounds__(SPLIT ? kThreadsMSplit : kThreadsM, 1)
-mix_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, MArgs p) {
+mix_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+              const __grid_constant__ CUtensorMap map_o, MArgs p) {
     extern __shared__ uint8_t smem_raw[];
+    constexpr bool kScore = MODE == 2, kBwd = MODE == 1;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t lo_ring = smem_base + (uint32_t)p.na * p.a_tile;                       // SPLIT: nlo slots of a_tile
     const uint32_t b_ring = lo_ring + (SPLIT ? (uint32_t)p.nlo * p.a_tile : 0u);          // 2 slots of mat_bytes (+ 2 lo slots when SPLIT)
@@ -196,14 +200,14 @@ mix_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 const uint32_t blo = b_lo + (uint32_t)sb * p.mat_bytes;
                 uint32_t first = 1;
                 uint32_t score_off = 0;           // SCORE_BWD: the [dS_k^T | dS_k] box pair of this tile's subset
-                if (p.score) {
+                if (kScore) {
                     const int ts = (int)(tile - (long long)n * p.tiles_per_sample);
                     const int cb = ts % p.ncb;
                     score_off = (uint32_t)((cb * 32) / (2 * p.width)) * 2u * kBoxBytes;
                 }
                 for (int k = 0; k < p.kb; ++k) {
                     // fwd: B atoms = the three subsets (LBO = one box), K rows inside each box;  bwd: one atom, K block k = box k
-                    const uint32_t bo = p.score ? score_off : (p.bwd ? (uint32_t)k * kBoxBytes : 0u);
+                    const uint32_t bo = kScore ? score_off : (kBwd ? (uint32_t)k * kBoxBytes : 0u);
                     const uint64_t da = make_smem_desc_mn(abase + (uint32_t)k * 4u * kBoxBytes, kBoxBytes);
                     const uint64_t dal = make_smem_desc_mn(alo + (uint32_t)k * 4u * kBoxBytes, kBoxBytes);
                     const uint64_t db = make_smem_desc_mn(bbase + bo, kBoxBytes);
@@ -242,7 +246,68 @@ mix_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             mbar_wait(tfull_bar(acc), acc_phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem_base + (uint32_t)(acc * 128) + ((uint32_t)(q * 32) << 16);
-            if (p.score) {
+            if (p.tma_out) {
+                // ---- TMA-store epilogue: the warp transposes its 32 channels x V joints block(s) through a private shared-memory
+                // tile ([joint][channel], 128-byte rows) and lane 0 hands each [V][32] box to the copy engine (reduce-add when
+                // accumulating): no per-thread global stores, no read-modify-write loads, rows past V never leave the SM.
+                constexpr int nbox = (kScore || kBwd) ? 1 : 3;
+                const uint32_t sbuf = bar_base + kBarBytes + (uint32_t)q * (uint32_t)nbox * kBoxBytes;
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the previous tile's stores have read the tile
+                __syncwarp();
+                int chan0 = cb * 32;
+                uint32_t col = (uint32_t)lane;
+                bool is_phi = false;
+                if (kScore) {
+                    is_phi = (((cb * 32 + lane) / p.width) & 1) != 0;
+                    if (p.width == 16) col = (uint32_t)(lane ^ 16);                      // theta | phi share the block: swap halves
+                    else chan0 += ((((cb * 32) / p.width) & 1) != 0) ? -p.width : p.width;   // whole block is theta (-> +W) or phi (-> -W)
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    if (k < nbox) {
+                        uint32_t r0[16], r1[16];
+                        if constexpr (kScore) {
+                            // phi channels own columns 0..31 (dS^T mix = d theta), theta channels columns 32..63 (d phi)
+                            uint32_t a0[16], a1[16];
+                            tmem_ld16_nowait(taddr, a0);
+                            tmem_ld16_nowait(taddr + 16u, a1);
+                            tmem_ld16_nowait(taddr + 32u, r0);
+                            tmem_ld16_nowait(taddr + 48u, r1);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) { if (is_phi) { r0[i] = a0[i]; r1[i] = a1[i]; } }
+                        } else {
+                            tmem_ld16_nowait(taddr + (uint32_t)(k * 32), r0);
+                            tmem_ld16_nowait(taddr + (uint32_t)(k * 32 + 16), r1);
+                            tmem_ld_wait();
+                        }
+                        const uint32_t base = sbuf + (uint32_t)k * kBoxBytes + col * 4u;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (i < p.v) asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + (uint32_t)i * 128u), "r"(r0[i]) : "memory");
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (16 + i < p.v) asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + (uint32_t)(16 + i) * 128u), "r"(r1[i]) : "memory");
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    if (ok) {
+                        for (int k = 0; k < nbox; ++k) {
+                            const int c0 = chan0 + k * p.width;
+                            const uint32_t src = sbuf + (uint32_t)k * kBoxBytes;
+                            if (p.accumulate)
+                                asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                                             ::"l"(&map_o), "r"(src), "r"(c0), "r"(0), "r"(tt), "r"(n) : "memory");
+                            else
+                                asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                                             ::"l"(&map_o), "r"(src), "r"(c0), "r"(0), "r"(tt), "r"(n) : "memory");
+                        }
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            } else if constexpr (kScore) {
                 // this lane's input channel is a phi channel (is_phi) -> it owns d theta = columns 0..31 (dS^T mix), written to the
                 // partner theta channel (ch - W); a theta channel owns d phi = columns 32..63, written to ch + W
                 const int ch = cb * 32 + lane;
@@ -260,7 +325,7 @@ mix_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                             if (h * 16 + i < p.v) ob[(long long)(h * 16 + i) * p.ldout] = __uint_as_float(is_phi ? ra[i] : rb[i]);
                     }
                 }
-            } else if (!p.bwd) {
+            } else if constexpr (!kBwd) {
                 // column j = k*32 + v -> out[.., v, k*W + cb*32 + c]
                 // two 16-column loads (one subset's 32 joint columns) per TMEM round trip; batching all six cost registers the
                 // 480-thread 3xTF32 variant does not have (spills, 0.30 -> 0.45 ms, profiles/r2c)
@@ -323,6 +388,7 @@ mix_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             if (lane == 0) mbar_arrive(tempty_bar(acc));
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
+        if (p.tma_out && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     } else if (SPLIT && warp >= 7) {
         // ===================================================== operand split: activations per tile, matrices per sample
         const int tids = threadIdx.x - 7 * 32;
@@ -396,7 +462,10 @@ int agcn_joint_mix_tc(const float* in, const float* mats, float* out, float* gp,
     p.a_tile = (uint32_t)p.kb * 4u * kBoxBytes;
     p.ldout = ldout;
     p.mat_bytes = score ? 2u * kMatBytes : kMatBytes;
-    const uint32_t fixed = 2u * p.mat_bytes * (split ? 2u : 1u) + kBarBytes + 1024u;
+    static const bool no_tma_out = getenv("AGCN_MIX_NO_TMA_STORE") != nullptr;
+    p.tma_out = (!no_tma_out && ldout % 4 == 0 && (!score || width == 16 || width % 32 == 0)) ? 1 : 0;
+    const uint32_t out_stage = p.tma_out ? 4u * ((score || p.bwd) ? 1u : 3u) * kBoxBytes : 0u;
+    const uint32_t fixed = 2u * p.mat_bytes * (split ? 2u : 1u) + kBarBytes + out_stage + 1024u;
     const uint32_t budget = 220u * 1024u - fixed;
     p.nlo = split ? 2 : 0;
     int na = (int)((budget - (uint32_t)p.nlo * p.a_tile) / p.a_tile);
@@ -435,15 +504,27 @@ int agcn_joint_mix_tc(const float* in, const float* mats, float* out, float* gp,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(AGCN_ERR_CUDA, "agcn_joint_mix_tc: cuTensorMapEncodeTiled(mats) failed with %d", (int)r);
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(mix_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(mix_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-        if (e != cudaSuccess) return fail(AGCN_ERR_CUDA, "agcn_joint_mix_tc: %s", cudaGetErrorString(e));
-        attr_set = true;
+    CUtensorMap map_o = map_a;
+    if (p.tma_out) {
+        // output: dims (c, v, t, n); one box = 32 channels x V joints of one timestep (dense 128-byte rows in shared memory)
+        cuuint64_t dims[4] = {(cuuint64_t)ldout, (cuuint64_t)v, (cuuint64_t)t, (cuuint64_t)nb};
+        cuuint64_t strides[3] = {(cuuint64_t)ldout * 4, (cuuint64_t)v * ldout * 4, (cuuint64_t)t * v * ldout * 4};
+        cuuint32_t box[4] = {32u, (cuuint32_t)v, 1u, 1u};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&map_o, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(AGCN_ERR_CUDA, "agcn_joint_mix_tc: cuTensorMapEncodeTiled(out) failed with %d", (int)r);
     }
-    const long long grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
-    if (split) mix_tc_kernel<true><<<(unsigned)grid, kThreadsMSplit, smem, st>>>(map_a, map_b, p);
-    else mix_tc_kernel<false><<<(unsigned)grid, kThreadsM, smem, st>>>(map_a, map_b, p);
+    auto launch = [&](auto kern, int threads) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        if (e != cudaSuccess) return e;
+        kern<<<(unsigned)(p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs), threads, smem, st>>>(map_a, map_b, map_o, p);
+        return cudaSuccess;
+    };
+    cudaError_t e;
+    if (split) e = score ? launch(mix_tc_kernel<true, 2>, kThreadsMSplit) : p.bwd ? launch(mix_tc_kernel<true, 1>, kThreadsMSplit) : launch(mix_tc_kernel<true, 0>, kThreadsMSplit);
+    else e = score ? launch(mix_tc_kernel<false, 2>, kThreadsM) : p.bwd ? launch(mix_tc_kernel<false, 1>, kThreadsM) : launch(mix_tc_kernel<false, 0>, kThreadsM);
+    if (e != cudaSuccess) return fail(AGCN_ERR_CUDA, "agcn_joint_mix_tc: %s", cudaGetErrorString(e));
     return check_launch("agcn_joint_mix_tc");
 }
