@@ -65,6 +65,8 @@ struct Tc2Args {
     signed char tap_id[2][kMaxTaps], tap_blk[2][kMaxTaps], tap_off[2][kMaxTaps];
     int blk_t0[2][2];
     int par_val[2];
+    int dual;                     // 3xTF32, bn <= 64, multi-segment: the hi*hi products and the two cross terms accumulate in SEPARATE TMEM columns
+                                  // (main at +0, cross at +bn); only the main chain carries full-magnitude truncation error, so segments are 3x longer
     int tma_store;                // 1: epilogue stages 32-column chunks in shared memory and writes them with TMA (bulk tensor stores / reduce-adds)
 };
 
@@ -160,13 +162,21 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         }
     } else if (warp == 1) {
         // ===================================================== MMA issuer
-        if (lane == 0) {
+        // All 32 lanes run the (warp-uniform) control flow and the mbarrier waits; ONE elected lane issues tcgen05.mma / commit.
+        // Under `if (lane == 0)` ptxas cannot prove the descriptor / TMEM operands warp-uniform and wraps every UTCHMMA in an
+        // ELECT + 5 x R2UR.BROADCAST + branch waterfall (~100 cycles per instruction, which bounded every tile narrower than 256
+        // columns, profiles/r2f); in uniform control flow the operands live in uniform registers.
+        {
+            const bool leader = elect_one_sync() != 0;
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.bn >> 3) << 17) | ((128u >> 4) << 24);
             int sa = 0; uint32_t pa = 0;
             int sb = 0; uint32_t pb = 0;
             int acc = 0; uint32_t acc_phase = 0;
             int sl = 0;
             const uint32_t row_bytes_v = (uint32_t)a.v * 128u;
+            const uint32_t cross_off = a.dual ? (uint32_t)a.bn : 0u;      // TMEM column offset of the cross-term accumulator
+            const uint32_t main_first = a.dual ? 1u : 0u;                 // dual: the hi*hi chain starts its own accumulator each segment
             for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
                 const int par = (int)((tile / a.n_tiles_n / a.tiles_t) % a.nparity);
                 const int ntap = a.ntap[par];
@@ -174,7 +184,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 int it = 0;
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                uint32_t d_tmem = tmem_base + (uint32_t)(acc * a.acc_stride);
+                uint32_t d_tmem = tmem_u + (uint32_t)(acc * a.acc_stride);
                 uint32_t first = 1;
                 for (int kc = 0; kc < a.kchunks; ++kc) {
                     mbar_wait(a_full(sa), pa);
@@ -189,37 +199,46 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         const uint32_t baddr = b_ring + (uint32_t)sb * b_slot;
                         const uint64_t da = make_smem_desc(aaddr), db = make_smem_desc(baddr);
                         const uint64_t dalo = make_smem_desc(lobase + aoff), dblo = make_smem_desc(baddr + a.b_stage_bytes);
+                        if (leader) {
 #pragma unroll
                         for (int k = 0; k < kKChunk / 8; ++k) {
                             if ((a.dbg & 2) && k) break;
                             const uint64_t ko = (uint64_t)(k * 2);
+                            const uint32_t fresh = (k == 0) ? first : 0u;       // first MMA of an accumulator segment overwrites
                             if (SPLIT) {
-                                umma_tf32(d_tmem, dalo + ko, db + ko, idesc, first ? 0u : 1u);
-                                umma_tf32(d_tmem, da + ko, dblo + ko, idesc, 1u);
-                                umma_tf32(d_tmem, da + ko, db + ko, idesc, 1u);
+                                // cross terms into d_tmem + cross_off (0 = same accumulator as the hi*hi chain); branch-free on purpose:
+                                // this single-thread issue loop is latency-critical (a data-dependent branch here cost 15 %, profiles/r2f)
+                                umma_tf32(d_tmem + cross_off, dalo + ko, db + ko, idesc, fresh ^ 1u);
+                                umma_tf32(d_tmem + cross_off, da + ko, dblo + ko, idesc, 1u);
+                                umma_tf32(d_tmem, da + ko, db + ko, idesc, (fresh & main_first) ^ 1u);
                             } else {
-                                umma_tf32(d_tmem, da + ko, db + ko, idesc, first ? 0u : 1u);
+                                umma_tf32(d_tmem, da + ko, db + ko, idesc, fresh ^ 1u);
                             }
-                            first = 0;
                         }
                         umma_commit(b_empty(sb));
+                        }
+                        __syncwarp();
+                        first = 0;
                         if (++sb == a.nbst) { sb = 0; pb ^= 1u; }
                         ++it;
                         if (SPLIT && (it % a.seg_iters) == 0 && it < iters) {
                             // promote the partial accumulator to the epilogue's fp32 registers, continue in the other buffer
-                            umma_commit(tfull_bar(acc));
+                            if (leader) umma_commit(tfull_bar(acc));
+                            __syncwarp();
                             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
                             mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
                             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                            d_tmem = tmem_base + (uint32_t)(acc * a.acc_stride);
+                            d_tmem = tmem_u + (uint32_t)(acc * a.acc_stride);
                             first = 1;
                         }
                     }
-                    umma_commit(a_empty(sa));
-                    if (SPLIT) { umma_commit(lo_empty(sl)); if (++sl == a.nlo) sl = 0; }
+                    if (leader) { umma_commit(a_empty(sa)); if (SPLIT) umma_commit(lo_empty(sl)); }
+                    __syncwarp();
+                    if (SPLIT) { if (++sl == a.nlo) sl = 0; }
                     if (++sa == a.na) { sa = 0; pa ^= 1u; }
                 }
-                umma_commit(tfull_bar(acc));
+                if (leader) umma_commit(tfull_bar(acc));
+                __syncwarp();
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         }
@@ -265,7 +284,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     if (c0 < a.bn) {
                         const bool wide = c0 + 16 < a.bn;                  // bn is a multiple of 16: the last chunk may be 16 wide
                         float vals[32];
-                        if (SPLIT) {
+                        if (SPLIT && a.dual) {
+                            tmem_promote16_dual(taddr + (uint32_t)c0, taddr + (uint32_t)(a.bn + c0), master + (uint32_t)c0, sg == 0, !last, vals);
+                            if (wide) tmem_promote16_dual(taddr + (uint32_t)c0 + 16u, taddr + (uint32_t)(a.bn + c0) + 16u, master + (uint32_t)c0 + 16u, sg == 0, !last, vals + 16);
+                        } else if (SPLIT) {
                             tmem_promote16(taddr + (uint32_t)c0, master + (uint32_t)c0, sg == 0, !last, vals);
                             if (wide) tmem_promote16(taddr + (uint32_t)c0 + 16u, master + (uint32_t)c0 + 16u, sg == 0, !last, vals + 16);
                         } else {
@@ -478,7 +500,9 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
     a.y = y; a.bias = bias; a.stat_part = stat_part;
     a.nb = nb; a.t_out = t_out; a.v = v; a.cin = cin; a.cout = cout; a.stride = stride; a.transposed = transposed; a.accumulate = accumulate;
     a.dbg = dbg;
-    a.seg_iters = (split && kiters <= 8) ? 8 : kSegment;
+    static const bool no_dual = getenv("AGCN_TC2_NO_DUAL") != nullptr;
+    a.dual = (split && kiters > 8 && bn <= 64 && !no_dual) ? 1 : 0;
+    a.seg_iters = (split && kiters <= 8) ? 8 : (a.dual ? 3 * kSegment : kSegment);
     a.acc_stride = bn > 128 ? 256 : 128;
     a.tt = 128 / v;
     a.bn = bn;

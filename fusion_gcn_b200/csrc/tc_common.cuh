@@ -81,6 +81,12 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// 1 in exactly one (elected) lane of a fully converged warp
+__device__ __forceinline__ uint32_t elect_one_sync() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -123,6 +129,26 @@ __device__ __forceinline__ void tmem_promote16(uint32_t part, uint32_t master, b
     tmem_ld_wait();
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = first ? __uint_as_float(p[i]) : __uint_as_float(s[i]) + __uint_as_float(p[i]);
+    if (write_back) tmem_st16(master, v);
+}
+
+// Same with the segment's products split over two accumulators: `part` holds the hi*hi chain, `cross` the lo*hi + hi*lo terms.
+__device__ __forceinline__ void tmem_promote16_dual(uint32_t part, uint32_t cross, uint32_t master, bool first, bool write_back, float* v) {
+    {   // two round trips keep at most 32 loaded registers alive (the 480-thread kernels have no room for 48)
+        uint32_t p[16], c[16];
+        tmem_ld16_nowait(part, p);
+        tmem_ld16_nowait(cross, c);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(p[i]) + __uint_as_float(c[i]);
+    }
+    if (!first) {
+        uint32_t s[16];
+        tmem_ld16_nowait(master, s);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += __uint_as_float(s[i]);
+    }
     if (write_back) tmem_st16(master, v);
 }
 
