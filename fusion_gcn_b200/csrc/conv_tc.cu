@@ -426,18 +426,22 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        // all 32 lanes run the warp-uniform control flow and the mbarrier waits, ONE elected lane issues the MMAs / commits, so
+        // that ptxas keeps the descriptors in uniform registers (no per-instruction R2UR waterfall; see conv_tc2.cu)
+        {
+            const bool leader = elect_one_sync() != 0;
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
             // tf32 x tf32 -> f32, A and B MN-major, M = 128, N = n_tile
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                                    ((uint32_t)(a.n_tile >> 3) << 17) | ((128u >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            uint32_t d_tmem = tmem_base;
+            uint32_t d_tmem = tmem_u;
             uint32_t first = 1;
             long long done = 0;
             int sl = 0;
             const long long nchunks = c_end - c_begin;
-            const int ksteps = (a.rows_box + 7) / 8;
+            const int ksteps = (a.dbg & 2) ? 1 : (a.rows_box + 7) / 8;
             for (long long c = c_begin; c < c_end; ++c) {
                 mbar_wait(full_bar(stage), phase);
                 if (SPLIT) mbar_wait(lo_bar(stage), phase);
@@ -447,32 +451,39 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
                 const uint64_t da = make_smem_desc_mn(sa, sub_bytes), db = make_smem_desc_mn(sa + 4u * sub_bytes, sub_bytes);
                 const uint64_t dalo = make_smem_desc_mn(slo, sub_bytes);
                 const uint64_t dblo = make_smem_desc_mn(slo + 4u * sub_bytes, sub_bytes);
-                for (int kg = 0; kg < ((a.dbg & 2) ? 1 : ksteps); ++kg) {
-                    const uint64_t ko = (uint64_t)(kg * 64);
-                    if (SPLIT) {
-                        umma_tf32(d_tmem, dalo + ko, db + ko, idesc, first ? 0u : 1u);
-                        umma_tf32(d_tmem, da + ko, dblo + ko, idesc, 1u);
-                        umma_tf32(d_tmem, da + ko, db + ko, idesc, 1u);
-                    } else {
-                        umma_tf32(d_tmem, da + ko, db + ko, idesc, first ? 0u : 1u);
+                if (leader) {
+                    for (int kg = 0; kg < ksteps; ++kg) {
+                        const uint64_t ko = (uint64_t)(kg * 64);
+                        const uint32_t fresh = (kg == 0) ? first : 0u;
+                        if (SPLIT) {
+                            umma_tf32(d_tmem, dalo + ko, db + ko, idesc, fresh ^ 1u);
+                            umma_tf32(d_tmem, da + ko, dblo + ko, idesc, 1u);
+                            umma_tf32(d_tmem, da + ko, db + ko, idesc, 1u);
+                        } else {
+                            umma_tf32(d_tmem, da + ko, db + ko, idesc, fresh ^ 1u);
+                        }
                     }
-                    first = 0;
+                    umma_commit(empty_bar(stage));
+                    if (SPLIT) umma_commit(lo_empty(sl));
                 }
-                umma_commit(empty_bar(stage));
-                if (SPLIT) { umma_commit(lo_empty(sl)); sl ^= 1; }
+                __syncwarp();
+                first = 0;
+                if (SPLIT) sl ^= 1;
                 if (++stage == a.stages) { stage = 0; phase ^= 1u; }
                 ++done;
                 if (SPLIT && (done % a.seg_chunks) == 0 && done < nchunks) {
                     // promote this partial accumulator to the epilogue's fp32 registers, continue in the other TMEM buffer
-                    umma_commit(tfull_bar(acc));
+                    if (leader) umma_commit(tfull_bar(acc));
+                    __syncwarp();
                     if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
                     mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    d_tmem = tmem_base + (uint32_t)(acc * 128);
+                    d_tmem = tmem_u + (uint32_t)(acc * 128);
                     first = 1;
                 }
             }
-            umma_commit(tfull_bar(acc));
+            if (leader) umma_commit(tfull_bar(acc));
+            __syncwarp();
         }
     } else if (warp < 6) {
         const int q = warp & 3;

@@ -103,12 +103,15 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             (void)stage_tx;
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        // warp-uniform control flow, one elected lane issues (uniform-register MMA operands, see conv_tc2.cu)
+        {
+            const bool leader = elect_one_sync() != 0;
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(80 >> 3) << 17) | ((128u >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             int sl = 0;
-            uint32_t d_tmem = tmem_base;
+            uint32_t d_tmem = tmem_u;
             uint32_t first = 1;
             const int ksteps = p.kw / 8;
             const uint32_t b_off = p.shared_tile ? 64u : (uint32_t)p.kpg * p.a_tile;      // B tile relative to the stage base
@@ -120,35 +123,42 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
                 const uint32_t slo = lo_ring + (uint32_t)sl * p.stage_bytes;
-                for (int k = 0; k < nk; ++k) {
-                    const uint32_t ao = (uint32_t)k * p.a_tile, bo = b_off + (uint32_t)k * (p.shared_tile ? p.a_tile : p.b_tile);
-                    const uint64_t da = make_smem_desc(sa + ao), db = make_smem_desc(sa + bo);
-                    const uint64_t dalo = make_smem_desc(slo + ao), dblo = make_smem_desc(slo + bo);
-                    for (int ks = 0; ks < ksteps; ++ks) {
-                        const uint64_t ko = (uint64_t)(ks * 2);
-                        if (SPLIT) {
-                            umma_tf32(d_tmem, dalo + ko, db + ko, idesc, first ? 0u : 1u);
-                            umma_tf32(d_tmem, da + ko, dblo + ko, idesc, 1u);
-                            umma_tf32(d_tmem, da + ko, db + ko, idesc, 1u);
-                        } else {
-                            umma_tf32(d_tmem, da + ko, db + ko, idesc, first ? 0u : 1u);
+                if (leader) {
+                    for (int k = 0; k < nk; ++k) {
+                        const uint32_t ao = (uint32_t)k * p.a_tile, bo = b_off + (uint32_t)k * (p.shared_tile ? p.a_tile : p.b_tile);
+                        const uint64_t da = make_smem_desc(sa + ao), db = make_smem_desc(sa + bo);
+                        const uint64_t dalo = make_smem_desc(slo + ao), dblo = make_smem_desc(slo + bo);
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            const uint64_t ko = (uint64_t)(ks * 2);
+                            const uint32_t fresh = (k == 0 && ks == 0) ? first : 0u;
+                            if (SPLIT) {
+                                umma_tf32(d_tmem, dalo + ko, db + ko, idesc, fresh ^ 1u);
+                                umma_tf32(d_tmem, da + ko, dblo + ko, idesc, 1u);
+                                umma_tf32(d_tmem, da + ko, db + ko, idesc, 1u);
+                            } else {
+                                umma_tf32(d_tmem, da + ko, db + ko, idesc, fresh ^ 1u);
+                            }
                         }
-                        first = 0;
                     }
+                    umma_commit(empty_bar(stage));
+                    if (SPLIT) umma_commit(lo_empty(sl));
                 }
-                umma_commit(empty_bar(stage));
-                if (SPLIT) { umma_commit(lo_empty(sl)); sl ^= 1; }
+                __syncwarp();
+                first = 0;
+                if (SPLIT) sl ^= 1;
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 if (SPLIT && ((s + 1) % kSegStages) == 0 && s + 1 < nstage) {
-                    umma_commit(tfull_bar(acc));
+                    if (leader) umma_commit(tfull_bar(acc));
+                    __syncwarp();
                     if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
                     mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    d_tmem = tmem_base + (uint32_t)(acc * 128);
+                    d_tmem = tmem_u + (uint32_t)(acc * 128);
                     first = 1;
                 }
             }
-            umma_commit(tfull_bar(acc));
+            if (leader) umma_commit(tfull_bar(acc));
+            __syncwarp();
         }
     } else if (warp < 6) {
         // epilogue: lane quarter q holds accumulator rows r = q*32 + lane = u*GA + ga; columns j = v*groups + g

@@ -171,7 +171,10 @@ mix_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         }
     } else if (warp == 1) {
         // ===================================================== MMA issuer
-        if (lane == 0) {
+        // warp-uniform control flow, one elected lane issues (uniform-register MMA operands, see conv_tc2.cu)
+        {
+            const bool leader = elect_one_sync() != 0;
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                                    ((uint32_t)(p.ncols >> 3) << 17) | ((128u >> 4) << 24);
             int sa = 0; uint32_t pa = 0;
@@ -182,7 +185,8 @@ mix_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             for (long long tile = tile_begin; tile < tile_end; ++tile) {
                 const int n = (int)(tile / p.tiles_per_sample);
                 if (n != cur) {
-                    if (m >= 0) umma_commit(b_empty(sb));             // every MMA that reads the previous matrix has been issued
+                    if (m >= 0 && leader) umma_commit(b_empty(sb));   // every MMA that reads the previous matrix has been issued
+                    __syncwarp();
                     cur = n;
                     ++m;
                     sb = m & 1;
@@ -193,41 +197,44 @@ mix_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 mbar_wait(a_full(sa), pa);
                 if (SPLIT) mbar_wait(a_lo(sa), pa);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
+                const uint32_t d_tmem = tmem_u + (uint32_t)(acc * 128);
                 const uint32_t abase = smem_base + (uint32_t)sa * p.a_tile;
                 const uint32_t alo = lo_ring + (uint32_t)sl * p.a_tile;
                 const uint32_t bbase = b_ring + (uint32_t)sb * p.mat_bytes;
                 const uint32_t blo = b_lo + (uint32_t)sb * p.mat_bytes;
-                uint32_t first = 1;
                 uint32_t score_off = 0;           // SCORE_BWD: the [dS_k^T | dS_k] box pair of this tile's subset
                 if (kScore) {
                     const int ts = (int)(tile - (long long)n * p.tiles_per_sample);
                     const int cb = ts % p.ncb;
                     score_off = (uint32_t)((cb * 32) / (2 * p.width)) * 2u * kBoxBytes;
                 }
-                for (int k = 0; k < p.kb; ++k) {
-                    // fwd: B atoms = the three subsets (LBO = one box), K rows inside each box;  bwd: one atom, K block k = box k
-                    const uint32_t bo = kScore ? score_off : (kBwd ? (uint32_t)k * kBoxBytes : 0u);
-                    const uint64_t da = make_smem_desc_mn(abase + (uint32_t)k * 4u * kBoxBytes, kBoxBytes);
-                    const uint64_t dal = make_smem_desc_mn(alo + (uint32_t)k * 4u * kBoxBytes, kBoxBytes);
-                    const uint64_t db = make_smem_desc_mn(bbase + bo, kBoxBytes);
-                    const uint64_t dbl = make_smem_desc_mn(blo + bo, kBoxBytes);
+                if (leader) {
+                    for (int k = 0; k < p.kb; ++k) {
+                        // fwd: B atoms = the three subsets (LBO = one box), K rows inside each box;  bwd: one atom, K block k = box k
+                        const uint32_t bo = kScore ? score_off : (kBwd ? (uint32_t)k * kBoxBytes : 0u);
+                        const uint64_t da = make_smem_desc_mn(abase + (uint32_t)k * 4u * kBoxBytes, kBoxBytes);
+                        const uint64_t dal = make_smem_desc_mn(alo + (uint32_t)k * 4u * kBoxBytes, kBoxBytes);
+                        const uint64_t db = make_smem_desc_mn(bbase + bo, kBoxBytes);
+                        const uint64_t dbl = make_smem_desc_mn(blo + bo, kBoxBytes);
 #pragma unroll
-                    for (int kg = 0; kg < 4; ++kg) {
-                        const uint64_t ko = (uint64_t)(kg * 64);          // 8 rows = 1024 bytes, in 16-byte units
-                        if (SPLIT) {
-                            umma_tf32(d_tmem, dal + ko, db + ko, idesc, first ? 0u : 1u);
-                            umma_tf32(d_tmem, da + ko, dbl + ko, idesc, 1u);
-                            umma_tf32(d_tmem, da + ko, db + ko, idesc, 1u);
-                        } else {
-                            umma_tf32(d_tmem, da + ko, db + ko, idesc, first ? 0u : 1u);
+                        for (int kg = 0; kg < 4; ++kg) {
+                            const uint64_t ko = (uint64_t)(kg * 64);          // 8 rows = 1024 bytes, in 16-byte units
+                            const uint32_t acc_flag = (k == 0 && kg == 0) ? 0u : 1u;
+                            if (SPLIT) {
+                                umma_tf32(d_tmem, dal + ko, db + ko, idesc, acc_flag);
+                                umma_tf32(d_tmem, da + ko, dbl + ko, idesc, 1u);
+                                umma_tf32(d_tmem, da + ko, db + ko, idesc, 1u);
+                            } else {
+                                umma_tf32(d_tmem, da + ko, db + ko, idesc, acc_flag);
+                            }
                         }
-                        first = 0;
                     }
+                    umma_commit(a_empty(sa));
+                    if (SPLIT) umma_commit(lo_empty(sl));
+                    umma_commit(tfull_bar(acc));
                 }
-                umma_commit(a_empty(sa));
-                if (SPLIT) { umma_commit(lo_empty(sl)); if (++sl == p.nlo) sl = 0; }
-                umma_commit(tfull_bar(acc));
+                __syncwarp();
+                if (SPLIT) { if (++sl == p.nlo) sl = 0; }
                 if (++sa == p.na) { sa = 0; pa ^= 1u; }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
