@@ -391,7 +391,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
     const uint32_t stage_tx = (uint32_t)__popc(loaded) * (uint32_t)a.rows_box * 128u;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {   // warp-uniform loop, elected lane issues the TMA loads (uniform-register operands)
+            const bool leader = elect_one_sync() != 0;
             int stage = 0; uint32_t phase = 0;
             for (long long c = c_begin; c < c_end; ++c) {
                 const int n = (int)(c / a.chunks_per_sample);
@@ -400,28 +401,30 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
                 if (a.flat) { a1 = cs * a.rows_box; a2 = 0; b1 = a1 + (tap - a.pad) * a.v; b2 = 0; }
                 else { a1 = 0; a2 = cs * a.tt; b1 = 0; b2 = a.stride * a2 + tap - a.pad; }
                 mbar_wait(empty_bar(stage), phase ^ 1u);
-                mbar_expect_tx(full_bar(stage), stage_tx);
                 const uint32_t sa = smem_base + (uint32_t)stage * raw_bytes;
-                if (a.blocked) {
-                    // dims (32 channels, flat row, channel block, sample): the box lands as [block][row][128 B], exactly the slot layout
-                    tma_load_4d(sa, &map_dy, full_bar(stage), 0, a1, a.pair ? 0 : m0 / 32, n);
-                    if (a.pair && tap_b) tma_load_4d(sa + 2u * sub_bytes, &map_dy, full_bar(stage), 0, a1 - a.v, 0, n);
-                    tma_load_4d(sa + 4u * sub_bytes, &map_x, full_bar(stage), 0, b1, k0 / 32, n);
-                    if (++stage == a.stages) { stage = 0; phase ^= 1u; }
-                    continue;
+                if (leader) {
+                    mbar_expect_tx(full_bar(stage), stage_tx);
+                    if (a.blocked) {
+                        // dims (32 channels, flat row, channel block, sample): the box lands as [block][row][128 B], exactly the slot layout
+                        tma_load_4d(sa, &map_dy, full_bar(stage), 0, a1, a.pair ? 0 : m0 / 32, n);
+                        if (a.pair && tap_b) tma_load_4d(sa + 2u * sub_bytes, &map_dy, full_bar(stage), 0, a1 - a.v, 0, n);
+                        tma_load_4d(sa + 4u * sub_bytes, &map_x, full_bar(stage), 0, b1, k0 / 32, n);
+                    } else {
+                        if (a.pair) {
+                            // slots 0,1: dy rows [a1, ..) for tap 2j; slots 2,3: the same channels V rows earlier for tap 2j+1
+                            //   sum_k dy[k - V][co] * x[k + (tap - pad) V][ci] = sum_k' dy[k'][co] * x[k' + (tap + 1 - pad) V][ci]
+                            for (int i = 0; i < 4; ++i)
+                                if ((loaded >> i) & 1u)
+                                    tma_load_4d(sa + i * sub_bytes, &map_dy, full_bar(stage), 32 * (i & 1), i < 2 ? a1 : a1 - a.v, 0, n);
+                        } else {
+                            for (int i = 0; i < 4; ++i)
+                                if ((loaded >> i) & 1u) tma_load_4d(sa + i * sub_bytes, &map_dy, full_bar(stage), m0 + 32 * i, a1, a2, n);
+                        }
+                        const uint32_t sb = sa + 4u * sub_bytes;
+                        for (int j = 0; j < b_boxes; ++j) tma_load_4d(sb + j * sub_bytes, &map_x, full_bar(stage), k0 + 32 * j, b1, b2, n);
+                    }
                 }
-                if (a.pair) {
-                    // slots 0,1: dy rows [a1, ..) for tap 2j; slots 2,3: the same channels V rows earlier for tap 2j+1
-                    //   sum_k dy[k - V][co] * x[k + (tap - pad) V][ci] = sum_k' dy[k'][co] * x[k' + (tap + 1 - pad) V][ci]
-                    for (int i = 0; i < 4; ++i)
-                        if ((loaded >> i) & 1u)
-                            tma_load_4d(sa + i * sub_bytes, &map_dy, full_bar(stage), 32 * (i & 1), i < 2 ? a1 : a1 - a.v, 0, n);
-                } else {
-                    for (int i = 0; i < 4; ++i)
-                        if ((loaded >> i) & 1u) tma_load_4d(sa + i * sub_bytes, &map_dy, full_bar(stage), m0 + 32 * i, a1, a2, n);
-                }
-                const uint32_t sb = sa + 4u * sub_bytes;
-                for (int j = 0; j < b_boxes; ++j) tma_load_4d(sb + j * sub_bytes, &map_x, full_bar(stage), k0 + 32 * j, b1, b2, n);
+                __syncwarp();
                 if (++stage == a.stages) { stage = 0; phase ^= 1u; }
             }
         }

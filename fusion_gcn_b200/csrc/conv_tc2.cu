@@ -123,8 +123,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const uint32_t b_tx = (uint32_t)a.bn * 128u * (SPLIT ? 2u : 1u);
 
     if (warp == 0) {
-        // ===================================================== activation producer
-        if (lane == 0) {
+        // ===================================================== activation producer (warp-uniform loop, elected lane issues: the TMA
+        // operands then stay in uniform registers, like the MMA operands)
+        {
+            const bool leader = elect_one_sync() != 0;
             int sa = 0; uint32_t pa = 0;
             for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
                 long long r = tile / a.n_tiles_n;
@@ -134,17 +136,21 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 const int tb = a.tmul * jt * a.tt;
                 for (int kc = 0; kc < a.kchunks; ++kc) {
                     mbar_wait(a_empty(sa), pa ^ 1u);
-                    mbar_expect_tx(a_full(sa), a_tx);
                     const uint32_t dst = smem_base + (uint32_t)sa * a_slot;
-                    for (int b = 0; b < a.nblk; ++b)
-                        tma_load_4d(dst + (uint32_t)b * a.blk_bytes, &map_a, a_full(sa), kc * kKChunk, 0, tb + a.blk_t0[par][b], n);
+                    if (leader) {
+                        mbar_expect_tx(a_full(sa), a_tx);
+                        for (int b = 0; b < a.nblk; ++b)
+                            tma_load_4d(dst + (uint32_t)b * a.blk_bytes, &map_a, a_full(sa), kc * kKChunk, 0, tb + a.blk_t0[par][b], n);
+                    }
+                    __syncwarp();
                     if (++sa == a.na) { sa = 0; pa ^= 1u; }
                 }
             }
         }
     } else if (warp == 6) {
-        // ===================================================== weight producer
-        if (lane == 0) {
+        // ===================================================== weight producer (same pattern)
+        {
+            const bool leader = elect_one_sync() != 0;
             int sb = 0; uint32_t pb = 0;
             for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
                 const int nt = (int)(tile % a.n_tiles_n);
@@ -152,9 +158,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 for (int kc = 0; kc < a.kchunks; ++kc) {
                     for (int i = 0; i < a.ntap[par]; ++i) {
                         mbar_wait(b_empty(sb), pb ^ 1u);
-                        mbar_expect_tx(b_full(sb), b_tx);
-                        tma_load_3d(b_ring + (uint32_t)sb * b_slot, &map_b, b_full(sb), kc * kKChunk, a.tap_id[par][i], nt * a.bn);
-                        if (SPLIT) tma_load_3d(b_ring + (uint32_t)sb * b_slot + a.b_stage_bytes, &map_blo, b_full(sb), kc * kKChunk, a.tap_id[par][i], nt * a.bn);
+                        if (leader) {
+                            mbar_expect_tx(b_full(sb), b_tx);
+                            tma_load_3d(b_ring + (uint32_t)sb * b_slot, &map_b, b_full(sb), kc * kKChunk, a.tap_id[par][i], nt * a.bn);
+                            if (SPLIT) tma_load_3d(b_ring + (uint32_t)sb * b_slot + a.b_stage_bytes, &map_blo, b_full(sb), kc * kKChunk, a.tap_id[par][i], nt * a.bn);
+                        }
+                        __syncwarp();
                         if (++sb == a.nbst) { sb = 0; pb ^= 1u; }
                     }
                 }

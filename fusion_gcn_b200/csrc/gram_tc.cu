@@ -83,21 +83,25 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t stage_tx = (uint32_t)p.kpg * (p.a_rows_bytes + (p.shared_tile ? 0u : p.b_rows_bytes));
 
     if (warp == 0) {
-        if (lane == 0) {
+        {   // warp-uniform loop, elected lane issues the TMA loads (uniform-register operands)
+            const bool leader = elect_one_sync() != 0;
             int stage = 0; uint32_t phase = 0;
             for (int s = 0; s < nstage; ++s) {
                 const int tt = t0 + s / p.nkg, kg = s % p.nkg;
                 mbar_wait(empty_bar(stage), phase ^ 1u);
                 // the last K-chunk group of a timestep may hold fewer chunks
                 const int nk = (p.nkc - kg * p.kpg) < p.kpg ? (p.nkc - kg * p.kpg) : p.kpg;
-                mbar_expect_tx(full_bar(stage), (uint32_t)nk * (p.a_rows_bytes + (p.shared_tile ? 0u : p.b_rows_bytes)));
                 const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
-                for (int k = 0; k < nk; ++k) {
-                    const int c0 = (kg * p.kpg + k) * 32;
-                    tma_load_5d(sa + (uint32_t)k * p.a_tile, &map_a, full_bar(stage), p.offa + c0, 0, 0, tt, n);
-                    if (!p.shared_tile)
-                        tma_load_5d(sa + (uint32_t)p.kpg * p.a_tile + (uint32_t)k * p.b_tile, &map_b, full_bar(stage), p.offb + c0, 0, 0, tt, n);
+                if (leader) {
+                    mbar_expect_tx(full_bar(stage), (uint32_t)nk * (p.a_rows_bytes + (p.shared_tile ? 0u : p.b_rows_bytes)));
+                    for (int k = 0; k < nk; ++k) {
+                        const int c0 = (kg * p.kpg + k) * 32;
+                        tma_load_5d(sa + (uint32_t)k * p.a_tile, &map_a, full_bar(stage), p.offa + c0, 0, 0, tt, n);
+                        if (!p.shared_tile)
+                            tma_load_5d(sa + (uint32_t)p.kpg * p.a_tile + (uint32_t)k * p.b_tile, &map_b, full_bar(stage), p.offb + c0, 0, 0, tt, n);
+                    }
                 }
+                __syncwarp();
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
             (void)stage_tx;

@@ -135,21 +135,25 @@ mix_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     const uint32_t a_tx = p.a_tile;
 
     if (warp == 0) {
-        // ===================================================== activation producer
-        if (lane == 0) {
+        // ===================================================== activation producer (warp-uniform loop, elected lane issues)
+        {
+            const bool leader = elect_one_sync() != 0;
             int sa = 0; uint32_t pa = 0;
             for (long long tile = tile_begin; tile < tile_end; ++tile) {
                 const int n = (int)(tile / p.tiles_per_sample);
                 const int ts = (int)(tile - (long long)n * p.tiles_per_sample);
                 mbar_wait(a_empty(sa), pa ^ 1u);
-                mbar_expect_tx(a_full(sa), a_tx);
                 const uint32_t dst = smem_base + (uint32_t)sa * p.a_tile;
-                for (int k = 0; k < p.kb; ++k)
-                    for (int j = 0; j < 4; ++j) {
-                        int tt, cb;                                                 // tt >= t for the pairs past the end: zero-filled box
-                        tile_pair(p, ts, j, tt, cb);
-                        tma_load_4d(dst + (uint32_t)(k * 4 + j) * kBoxBytes, &map_a, a_full(sa), k * p.width + cb * 32, 0, tt, n);
-                    }
+                if (leader) {
+                    mbar_expect_tx(a_full(sa), a_tx);
+                    for (int k = 0; k < p.kb; ++k)
+                        for (int j = 0; j < 4; ++j) {
+                            int tt, cb;                                             // tt >= t for the pairs past the end: zero-filled box
+                            tile_pair(p, ts, j, tt, cb);
+                            tma_load_4d(dst + (uint32_t)(k * 4 + j) * kBoxBytes, &map_a, a_full(sa), k * p.width + cb * 32, 0, tt, n);
+                        }
+                }
+                __syncwarp();
                 if (++sa == p.na) { sa = 0; pa ^= 1u; }
             }
         }
