@@ -32,7 +32,7 @@ namespace tc2 {
 using namespace agcn::tc;
 
 constexpr int kMaxTaps = 9;
-constexpr int kMaxA = 8, kMaxB = 8;
+constexpr int kMaxA = 8, kMaxB = 8, kMaxLo = 4;
 constexpr int kSplitWarps = 8;
 constexpr int kThreads2 = 7 * 32;
 constexpr int kThreads2Split = (7 + kSplitWarps) * 32;
@@ -88,9 +88,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     auto b_full = [&](int s) { return bar_base + 8u * (3 * kMaxA + s); };
     auto b_empty = [&](int s) { return bar_base + 8u * (3 * kMaxA + kMaxB + s); };
     auto lo_empty = [&](int s) { return bar_base + 8u * (3 * kMaxA + 2 * kMaxB + s); };
-    auto tfull_bar = [&](int s) { return bar_base + 8u * (3 * kMaxA + 2 * kMaxB + 2 + s); };
-    auto tempty_bar = [&](int s) { return bar_base + 8u * (3 * kMaxA + 2 * kMaxB + 4 + s); };
-    const uint32_t tmem_slot = bar_base + 8u * (3 * kMaxA + 2 * kMaxB + 6);
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (3 * kMaxA + 2 * kMaxB + kMaxLo + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (3 * kMaxA + 2 * kMaxB + kMaxLo + 2 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (3 * kMaxA + 2 * kMaxB + kMaxLo + 4);
     const uint32_t stage_base = bar_base + kBarBytes + (uint32_t)((threadIdx.x >> 5) & 3) * (32u * kStagePitch);   // epilogue staging tile of this warp's lane quarter
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -101,7 +101,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         if (a.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_y0) : "memory");
         for (int s = 0; s < kMaxA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); mbar_init(a_lo(s), kSplitWarps); }
         for (int s = 0; s < kMaxB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(lo_empty(s), 1); mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+        for (int s = 0; s < kMaxLo; ++s) mbar_init(lo_empty(s), 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -593,7 +594,11 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
     const uint32_t budget = kSmemBudget - 1024u - epi_bytes - stat_bytes;
     // Ring depths.  Weights: 3 slots (2 when tight).  3xTF32 lo residuals: 2 slots, 1 when two would leave a single
     // activation stage.  Everything else goes to the activation ring: payload bytes in flight set the achieved bandwidth.
-    a.na = 0; a.nbst = 0; a.nlo = split ? 2 : 0;
+    static const int nlo_env = getenv("AGCN_TC2_NLO") ? atoi(getenv("AGCN_TC2_NLO")) : 0;
+    // lo-residual ring: 2 slots (3 or 4 measured no faster for the 1x1 kernels and slower where they shorten the payload ring, profiles/r2g)
+    int nlo_want = split ? 2 : 0;
+    if (split && nlo_env >= 1 && nlo_env <= kMaxLo) nlo_want = nlo_env;
+    a.na = 0; a.nbst = 0; a.nlo = nlo_want;
     auto fit = [&](int nlo, int min_b) -> int {
         const uint64_t fixed = (uint64_t)nlo * a_slot + (uint64_t)min_b * b_slot;
         if (fixed + a_slot > budget) return 0;
