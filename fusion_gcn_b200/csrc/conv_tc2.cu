@@ -53,7 +53,7 @@ struct Tc2Args {
     long long total_tiles;
     int seg_iters;                // 3xTF32: (tap, K chunk) iterations per accumulator segment
     int acc_stride;               // TMEM columns between the two accumulator buffers (128, or 256 for tiles wider than 128)
-    int dbg;                      // bring-up only (env AGCN_CONV_DEBUG): 1 skip operand split, 2 one MMA per tap, 4 skip global stores
+    int dbg;                      // bring-up only (env AGCN_CONV_DEBUG): 1 skip operand split, 2 one MMA per tap, 4 skip global stores, 8 no split warps / handshake
     int na, nbst, nlo;            // ring depths (nlo: 3xTF32 lo-residual ring, 1 or 2 slots)
     int nblk;                     // activation boxes per stage
     uint32_t blk_rows_bytes;      // bytes TMA writes per box
@@ -67,6 +67,7 @@ struct Tc2Args {
     int par_val[2];
     int dual;                     // 3xTF32, bn <= 64, multi-segment: the hi*hi products and the two cross terms accumulate in SEPARATE TMEM columns
                                   // (main at +0, cross at +bn); only the main chain carries full-magnitude truncation error, so segments are 3x longer
+    int w_resident;               // 1: 1x1 conv whose whole weight tile (all K chunks, hi [+ lo]) fits the weight ring: loaded ONCE per CTA, kept for every tile
     int tma_store;                // 1: epilogue stages 32-column chunks in shared memory and writes them with TMA (bulk tensor stores / reduce-adds)
 };
 
@@ -154,6 +155,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const bool leader = elect_one_sync() != 0;
             int sb = 0; uint32_t pb = 0;
             for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+                if (a.w_resident && tile != blockIdx.x) break;            // resident weights: one load per CTA
                 const int nt = (int)(tile % a.n_tiles_n);
                 const int par = (int)((tile / a.n_tiles_n / a.tiles_t) % a.nparity);
                 for (int kc = 0; kc < a.kchunks; ++kc) {
@@ -191,6 +193,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 const int par = (int)((tile / a.n_tiles_n / a.tiles_t) % a.nparity);
                 const int ntap = a.ntap[par];
                 const int iters = ntap * a.kchunks;
+                const bool wait_b = !(a.w_resident && tile != blockIdx.x);
                 int it = 0;
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -198,11 +201,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 uint32_t first = 1;
                 for (int kc = 0; kc < a.kchunks; ++kc) {
                     mbar_wait(a_full(sa), pa);
-                    if (SPLIT) mbar_wait(a_lo(sa), pa);
+                    if (SPLIT && !(a.dbg & 8)) mbar_wait(a_lo(sa), pa);
                     const uint32_t abase = smem_base + (uint32_t)sa * a_slot;
                     const uint32_t lobase = lo_ring + (uint32_t)sl * a_slot;
                     for (int i = 0; i < ntap; ++i) {
-                        mbar_wait(b_full(sb), pb);
+                        if (wait_b) mbar_wait(b_full(sb), pb);                     // resident weights arrive once
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint32_t aoff = (uint32_t)a.tap_blk[par][i] * a.blk_bytes + (uint32_t)a.tap_off[par][i] * row_bytes_v;
                         const uint32_t aaddr = abase + aoff;
@@ -225,7 +228,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                                 umma_tf32(d_tmem, da + ko, db + ko, idesc, fresh ^ 1u);
                             }
                         }
-                        umma_commit(b_empty(sb));
+                        if (!a.w_resident) umma_commit(b_empty(sb));
                         }
                         __syncwarp();
                         first = 0;
@@ -447,6 +450,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         int sa = 0; uint32_t pa = 0;
         int sl = 0; uint32_t pl = 0;
         for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+            if (a.dbg & 8) break;                       // timing probe: no split warps at all (results wrong)
             for (int kc = 0; kc < a.kchunks; ++kc) {
                 mbar_wait(a_full(sa), pa);
                 mbar_wait(lo_empty(sl), pl ^ 1u);
@@ -618,6 +622,21 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
         if (nbst > kMaxB) nbst = kMaxB;
         if (nbst < best_b) nbst = best_b;
         a.nbst = nbst;
+    }
+    // Resident weights: a 1x1 conv with a single output-channel tile re-reads the SAME weight boxes for every 125-row tile (for
+    // 64 -> 192 channels in 3xTF32 that is 98 KB of weights per 32 KB of activations through the SM's ingress).  When all K chunks
+    // fit the weight ring next to at least three activation stages they are loaded once per CTA and never released.
+    static const bool no_resident = getenv("AGCN_TC2_NO_RESIDENT_W") != nullptr;
+    a.w_resident = 0;
+    if (!no_resident && taps == 1 && a.n_tiles_n == 1 && a.nparity == 1 && a.kchunks <= kMaxB) {
+        const uint64_t wbytes = (uint64_t)a.kchunks * b_slot;
+        const uint64_t fixed_lo = (uint64_t)a.nlo * a_slot;
+        if (wbytes + fixed_lo + 3ull * a_slot <= budget) {
+            a.w_resident = 1;
+            a.nbst = a.kchunks;
+            int na = (int)((budget - wbytes - fixed_lo) / a_slot);
+            a.na = na > kMaxA ? kMaxA : na;
+        }
     }
     const size_t smem = (size_t)(a.na + a.nlo) * a_slot + (size_t)a.nbst * b_slot + 1024 + epi_bytes + stat_bytes;
 

@@ -1,0 +1,3 @@
+#!/bin/bash
+mkdir -p gpurun_out
+( for d in 0 1 8 9 15; do echo "== AGCN_CONV_DEBUG=$d fp32"; AGCN_CONV_DEBUG=$d timeout 200 python tools/bench_stage.py conv_emb_c64 conv_proj_c64 conv_dproj_c64 conv_tconv_c64 conv_tconv_c128; done ) > gpurun_out/p3_probe.log 2>&1; cat gpurun_out/p3_probe.log
