@@ -155,8 +155,9 @@ __device__ __forceinline__ void tmem_promote16_dual(uint32_t part, uint32_t cros
 // Operand split of `bytes` bytes (multiple of 16) at src for the 3xTF32 path: hi = rna_tf32(x) overwrites src in place,
 // lo = x - hi (exact) goes to dst at the same offsets (any swizzle is preserved).  `nthreads` threads cooperate; every
 // thread keeps four 16-byte loads in flight before the dependent converts and stores.
-// (Tried and dropped, profiles/r2a: leaving src untouched and writing only lo = x - trunc(x), relying on the tensor core's own
-// truncation for hi -- one store fewer per load, but only 1-3 % faster per kernel and it failed parity at unit level.)
+// (Tried twice and dropped: leaving src untouched -- the tensor core truncates the raw operand itself -- and writing only
+// lo = x - trunc(x).  Without rounding lo the error is one-sided (2^-20) and stage tolerances fail (profiles/r2a); with
+// lo = rna_tf32(x - trunc(x)) parity holds but no kernel gets faster, several get 5-15 % slower (profiles/r2i).)
 __device__ __forceinline__ void transform_split4(uint32_t src, uint32_t dst, uint32_t bytes, int tid, int nthreads) {
     const uint32_t step = (uint32_t)nthreads * 16u;
     for (uint32_t off = (uint32_t)tid * 16u; off < bytes; off += 4u * step) {
