@@ -488,6 +488,38 @@ __global__ void __launch_bounds__(256) bias_partial_kernel(const float* dy, long
     }
 }
 
+// the same column sums with 16-byte loads: thread = (row lane, channel quad), four rows in flight (cout % 4 == 0, cout / 4 <= 256)
+__global__ void __launch_bounds__(256) bias_partial_vec_kernel(const float* __restrict__ dy, long long rows, int cout, float* __restrict__ part) {
+    extern __shared__ __align__(16) float bsm[];      // [lanes_r][cout]
+    const int cq = cout >> 2;
+    const int lanes_r = 256 / cq;
+    const int q = threadIdx.x % cq, rl = threadIdx.x / cq;
+    const long long per = (rows + gridDim.x - 1) / gridDim.x;
+    const long long r0 = (long long)blockIdx.x * per;
+    long long r1 = r0 + per; if (r1 > rows) r1 = rows;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rl < lanes_r) {
+        const float4* src = reinterpret_cast<const float4*>(dy) + q;
+        for (long long r = r0 + rl; r < r1; r += 4LL * lanes_r) {
+            float4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const long long rr = r + (long long)j * lanes_r;
+                v[j] = rr < r1 ? __ldg(src + rr * cq) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { s.x += v[j].x; s.y += v[j].y; s.z += v[j].z; s.w += v[j].w; }
+        }
+        *reinterpret_cast<float4*>(bsm + (size_t)rl * cout + q * 4) = s;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < cout; c += 256) {
+        float acc = 0.f;
+        for (int l = 0; l < lanes_r; ++l) acc += bsm[(size_t)l * cout + c];
+        part[(long long)blockIdx.x * cout + c] = acc;
+    }
+}
+
 constexpr int kBiasPartials = 2 * kNumSMs;
 
 static int wgrad_splits(long long rows, int cin, int cout, int taps) {
@@ -646,8 +678,13 @@ extern "C" AGCN_API int agcn_conv_wgrad(const float* dy, const float* x, float* 
                 const long long rows = (long long)nb * t_out * v;
                 int P = (int)((rows + 255) / 256);
                 if (P > kBiasPartials) P = kBiasPartials;
-                dim3 grid((unsigned)P, (unsigned)ceil_div(cout, 32));
-                bias_partial_kernel<<<grid, 256, 0, s>>>(dy, rows, cout, part);
+                if (cout % 4 == 0 && cout / 4 <= 256 && aligned16(dy)) {
+                    const size_t bsmem = (size_t)(256 / (cout / 4)) * cout * sizeof(float);
+                    bias_partial_vec_kernel<<<P, 256, bsmem, s>>>(dy, rows, cout, part);
+                } else {
+                    dim3 grid((unsigned)P, (unsigned)ceil_div(cout, 32));
+                    bias_partial_kernel<<<grid, 256, 0, s>>>(dy, rows, cout, part);
+                }
                 rc = check_launch("agcn_conv_wgrad(bias partial)");
                 if (rc) return rc;
                 wgrad_reduce_kernel<<<ceil_div(cout, 256), 256, 0, s>>>(nullptr, part, nullptr, dbias, 0, cout, P);

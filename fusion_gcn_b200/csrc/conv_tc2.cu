@@ -182,6 +182,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const bool leader = elect_one_sync() != 0;
             const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.bn >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc_wide = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * a.bn) >> 3) << 17) | ((128u >> 4) << 24);
             int sa = 0; uint32_t pa = 0;
             int sb = 0; uint32_t pb = 0;
             int acc = 0; uint32_t acc_phase = 0;
@@ -213,6 +214,19 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         const uint64_t da = make_smem_desc(aaddr), db = make_smem_desc(baddr);
                         const uint64_t dalo = make_smem_desc(lobase + aoff), dblo = make_smem_desc(baddr + a.b_stage_bytes);
                         if (leader) {
+                        if (SPLIT && a.dual) {
+                            // narrow tiles: ONE MMA of width 2*bn against [W_hi ; W_lo] (adjacent in the weight slot) yields x_hi.W_hi in
+                            // the main columns and x_hi.W_lo in the cross columns; a second one adds x_lo.W_hi to the cross columns.
+                            // Two instructions and two reads of the activation tile per K step instead of three.
+#pragma unroll
+                            for (int k = 0; k < kKChunk / 8; ++k) {
+                                if ((a.dbg & 2) && k) break;
+                                const uint64_t ko = (uint64_t)(k * 2);
+                                const uint32_t fresh = (k == 0) ? first : 0u;
+                                umma_tf32(d_tmem, da + ko, db + ko, idesc_wide, fresh ^ 1u);
+                                umma_tf32(d_tmem + cross_off, dalo + ko, db + ko, idesc, 1u);
+                            }
+                        } else {
 #pragma unroll
                         for (int k = 0; k < kKChunk / 8; ++k) {
                             if ((a.dbg & 2) && k) break;
@@ -227,6 +241,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                             } else {
                                 umma_tf32(d_tmem, da + ko, db + ko, idesc, fresh ^ 1u);
                             }
+                        }
                         }
                         if (!a.w_resident) umma_commit(b_empty(sb));
                         }
