@@ -45,11 +45,15 @@ def make_graph(kind):
 
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    fallback = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
     if os.path.isfile(path):
-        d = json.load(open(path))
-        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained"),
-                "source": "measured"}
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+        try:
+            d = json.load(open(path))
+            return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"]),
+                    "bf16_tflops_sustained": d.get("bf16_tflops_sustained"), "source": "measured"}
+        except (KeyError, TypeError, ValueError):          # unexpected layout: say so and use the recipe's fallback numbers
+            fallback["source"] = "fallback (MEASURED_PEAKS.json present but not in the expected layout)"
+    return fallback
 
 
 class ClockSampler:
