@@ -530,9 +530,11 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
     a.nb = nb; a.t_out = t_out; a.v = v; a.cin = cin; a.cout = cout; a.stride = stride; a.transposed = transposed; a.accumulate = accumulate;
     a.dbg = dbg;
     static const bool no_dual = getenv("AGCN_TC2_NO_DUAL") != nullptr;
-    a.dual = (split && kiters > 8 && bn <= 64 && !no_dual) ? 1 : 0;
+    // main | cross accumulator pairs: multi-segment tiles up to 64 wide (2*bn <= 128 next to the master sums), single-segment
+    // tiles (1x1 convs with cin <= 256: no master sums) up to 128 wide (2*bn <= 256 = one of the two accumulator buffers)
+    a.dual = (split && !no_dual && ((kiters > 8 && bn <= 64) || (kiters <= 8 && bn <= 128))) ? 1 : 0;
     a.seg_iters = (split && kiters <= 8) ? 8 : (a.dual ? 3 * kSegment : kSegment);
-    a.acc_stride = bn > 128 ? 256 : 128;
+    a.acc_stride = (bn > 128 || (a.dual && 2 * bn > 128)) ? 256 : 128;
     a.tt = 128 / v;
     a.bn = bn;
     a.n_tiles_n = cout / bn;
