@@ -14,15 +14,23 @@
 //
 // Warp roles (7 warps, +8 in 3xTF32 mode), persistent over tiles, 1 CTA / SM:
 //   warp 0      activation producer: TMA boxes of one K chunk -> A ring (NA stages of payload only)
-//   warp 1      MMA issuer: per (K chunk, tap): 4 x tcgen05.mma.kind::tf32 (M128, N=BN, K8), x3 in 3xTF32 mode
-//   warps 2..5  epilogue: tcgen05.ld -> (+bias, +old) -> st.global; in 3xTF32 mode also the fp32 promotion of segments
-//   warp 6      weight producer: one (tap, K chunk) BN x 32 box -> B ring (NB stages)
+//   warp 1      MMA issuer: per (K chunk, tap): 4 x tcgen05.mma.kind::tf32 (M128, N=BN, K8); 3xTF32 mode: x3 (lo*hi, hi*lo, hi*hi),
+//               or x2 for tiles narrow enough to hold a [main | cross] accumulator pair: one 2*BN-wide MMA against [W_hi ; W_lo]
+//               and one against W_hi with the lo activations
+//   warps 2..5  epilogue: tcgen05.ld -> (+bias) -> 1x1 convs: swizzled shared-memory chunk -> TMA bulk store / reduce-add;
+//               9-tap convs: per-warp staging -> full-line st.global (+old when accumulating); optional BatchNorm column sums;
+//               in 3xTF32 mode also the fp32 promotion of accumulator segments
+//   warp 6      weight producer: one (tap, K chunk) BN x 32 box -> B ring (NB stages); small 1x1 weights stay resident
 //   warps 7..14 (3xTF32) split the A stage once per K chunk: hi = rna_tf32(x) in place, lo = x - hi into a 2-deep lo ring
 //               (the weights' hi / lo tensors are precomputed into the caller's workspace and TMA-loaded)
+// Warps 0, 1 and 6 run their loops on all 32 lanes (warp-uniform control flow, mbarrier waits included) and let ONE elected lane
+// issue the TMA / MMA / commit instructions: ptxas then keeps the descriptors, coordinates and TMEM addresses in uniform
+// registers.  Under `if (lane == 0)` every UTCHMMA / UTMALDG is wrapped in an ELECT + R2UR.BROADCAST + branch waterfall that
+// costs ~100 cycles per instruction and bounded every tile narrower than 256 columns (profiles/r2f, r2y).
 // The achieved HBM bandwidth of these kernels is (payload bytes in flight per SM) / (~3 us loaded latency) (measured,
 // profiles/r1k): the A ring therefore holds only TMA payload and is as deep as shared memory allows; the lo residuals live
 // in their own two-slot ring between the split warps and the MMA issuer.
-// TMEM: 2 x 128 fp32 accumulator columns (epilogue of tile i overlaps the main loop of tile i+1; 3xTF32 segments
+// TMEM: 2 accumulator buffers of 128 (or 256) fp32 columns (epilogue of tile i overlaps the main loop of tile i+1; 3xTF32 segments
 // ping-pong) + 128 columns of fp32 master sums for the 3xTF32 segment promotion (tmem_promote16).
 #include "tc_common.cuh"
 #include <stdlib.h>
