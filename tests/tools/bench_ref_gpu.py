@@ -1,7 +1,7 @@
 """Same-hardware baseline: the oracle port of the reference (eager PyTorch: cuDNN conv, cuBLAS bmm, ATen softmax / BN)
 on one B200, NTU shape, fwd+CE+bwd, train mode.  Reported beside the product numbers, never used by the product.
 
-  python tools/bench_ref_gpu.py [--batch 64] [--steps 5] [--tf32]     (run on the GPU box)
+  python tests/tools/bench_ref_gpu.py [--batch 64] [--steps 5] [--tf32]     (run on the GPU box)
 """
 import argparse
 import json
@@ -10,7 +10,7 @@ import sys
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 

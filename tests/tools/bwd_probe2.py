@@ -2,7 +2,7 @@
 one, in ONE process, and print the first calls whose outputs differ."""
 import os, sys
 import torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from fusion_gcn_b200 import graph as G, modules as M, functional as FN, ops
 from oracle import agcn_oracle as O

@@ -1,7 +1,7 @@
-"""Smoke-model gradient errors per tensor (debug aid): python tools/smoke_probe.py [start] [seed]"""
+"""Smoke-model gradient errors per tensor (debug aid): python tests/tools/smoke_probe.py [start] [seed]"""
 import os, sys
 import torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from fusion_gcn_b200 import graph as G, modules as M
 from oracle import agcn_oracle as O

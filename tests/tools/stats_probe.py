@@ -1,7 +1,7 @@
 """Debug aid: for every Conv->BN pair of the smoke model, compare the fused-epilogue statistics with bn_stats on the same y."""
 import os, sys
 import torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from fusion_gcn_b200 import graph as G, modules as M, functional as FN, ops as K
 from oracle import agcn_oracle as O

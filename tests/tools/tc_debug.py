@@ -1,4 +1,4 @@
-"""Bring-up harness for the tcgen05 implicit-GEMM path (run on the GPU box):  python tools/tc_debug.py [case ...]
+"""Bring-up harness for the tcgen05 implicit-GEMM path (run on the GPU box):  python tests/tools/tc_debug.py [case ...]
 Each case runs in its own subprocess under a timeout so that a deadlocked kernel cannot take the whole call down.
 Compares agcn_conv_fwd(precision=TF32) with fp64 contractions of (a) the raw fp32 inputs, (b) inputs truncated to
 TF32, (c) inputs rounded to TF32, and prints where the largest errors sit."""
@@ -6,7 +6,7 @@ import subprocess
 import sys
 import os
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 CASES = {  # name: nb, t_in, v, cin, cout, taps, stride, transposed, bias, accumulate

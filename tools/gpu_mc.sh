@@ -1,7 +1,7 @@
 #!/bin/bash
 tag=${1:-mc}
 mkdir -p gpurun_out
-timeout 1200 python tools/tc_debug.py k32 k64 multi_tile taps9 n256 n96_k16 v20_acc v22 stride2 res_stride2 dgrad_s1 dgrad_s2 wide_k big big256 > gpurun_out/${tag}_tc_debug.log 2>&1; cat gpurun_out/${tag}_tc_debug.log
+timeout 1200 python tests/tools/tc_debug.py k32 k64 multi_tile taps9 n256 n96_k16 v20_acc v22 stride2 res_stride2 dgrad_s1 dgrad_s2 wide_k big big256 > gpurun_out/${tag}_tc_debug.log 2>&1; cat gpurun_out/${tag}_tc_debug.log
 if grep -q "TIMEOUT\|FAILED" gpurun_out/${tag}_tc_debug.log; then echo "tc_debug found hangs/failures: stopping"; exit 0; fi
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 > gpurun_out/${tag}_pytest.log; tail -3 gpurun_out/${tag}_pytest.log
 timeout 600 python tools/bench_stage.py conv > gpurun_out/${tag}_stage_fp32.log 2>&1; cat gpurun_out/${tag}_stage_fp32.log

@@ -1,7 +1,7 @@
 #!/bin/bash
 tag=${1:-wgb}
 mkdir -p gpurun_out
-timeout 900 python tools/tc_debug.py wg_1x1 wg_1x1_odd wg_taps9 wg_c256 wg_k768 wg_m384 wg_stride2 wg_res_stride2 wg_fc wg_big wg_big256 > gpurun_out/${tag}_tc_debug.log 2>&1; cat gpurun_out/${tag}_tc_debug.log
+timeout 900 python tests/tools/tc_debug.py wg_1x1 wg_1x1_odd wg_taps9 wg_c256 wg_k768 wg_m384 wg_stride2 wg_res_stride2 wg_fc wg_big wg_big256 > gpurun_out/${tag}_tc_debug.log 2>&1; cat gpurun_out/${tag}_tc_debug.log
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 > gpurun_out/${tag}_pytest.log; tail -3 gpurun_out/${tag}_pytest.log
 timeout 600 python tools/bench_stage.py wgrad > gpurun_out/${tag}_stage_fp32.log 2>&1; cat gpurun_out/${tag}_stage_fp32.log
 timeout 600 python tools/bench_stage.py wgrad --tf32 > gpurun_out/${tag}_stage_tf32.log 2>&1; cat gpurun_out/${tag}_stage_tf32.log
