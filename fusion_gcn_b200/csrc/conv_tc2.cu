@@ -314,7 +314,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 // memory (144-byte row pitch) -> read back with 8 lanes per row, so that every st.global instruction writes four
                 // full 128-byte row segments.  Writing the TMEM fragment directly (one 16-byte piece of 32 different rows per
                 // instruction) held the 1x1 convolutions at a third of the HBM rate (measured, profiles/r1m).
-#pragma unroll
+                // NOT unrolled: eight copies of this body (three accumulator flavours, two store paths, statistics) made the 3xTF32
+                // kernel 229 KB of SASS (14 300 instructions; 3 950 rolled) for no measurable gain (profiles/r2l)
+#pragma unroll 1
                 for (int cc = 0; cc < 8; ++cc) {
                     const int c0 = cc * 32;
                     if (c0 < a.bn) {
