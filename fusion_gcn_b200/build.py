@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libagcn_b200.so")
-SOURCES = ["common.cu", "conv_simt.cu", "conv_tc.cu", "conv_tc2.cu", "joint.cu", "gram_tc.cu", "mix_tc.cu", "bn.cu"]
+SOURCES = ["common.cu", "conv_simt.cu", "wgrad_tc.cu", "conv_tc2.cu", "joint.cu", "gram_tc.cu", "mix_tc.cu", "bn.cu"]
 FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC",
          "-Xcompiler", "-fvisibility=hidden"]
 
@@ -19,11 +19,12 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not _stale():
+def build(force=False, verbose=False, probes=False):
+    """``probes=True`` compiles the A/B switches and limiter probes in (-DAGCN_PROBES); the default library has none."""
+    if not force and not probes and not _stale():
         return OUT
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcuda"]
+    cmd = [nvcc] + FLAGS + (["-DAGCN_PROBES"] if probes else []) + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcuda"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
@@ -34,4 +35,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, probes="--probes" in sys.argv))

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include "../../include/agcn_b200.h"
 
 #define AGCN_API __attribute__((visibility("default")))
@@ -28,6 +29,14 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 constexpr int kNumSMs = 148;   // B200
+
+// A/B switches and limiter probes exist only in builds made with -DAGCN_PROBES
+// (python -m fusion_gcn_b200.build --probes); the default library never reads the environment.
+#ifdef AGCN_PROBES
+inline const char* probe_env(const char* name) { return getenv(name); }
+#else
+inline const char* probe_env(const char*) { return nullptr; }
+#endif
 
 }  // namespace agcn
 

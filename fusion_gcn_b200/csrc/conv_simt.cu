@@ -536,10 +536,7 @@ static int wgrad_splits(long long rows, int cin, int cout, int taps) {
 
 using namespace agcn;
 
-// implemented in conv_tc.cu; return AGCN_ERR_UNSUPPORTED when the shape is outside the tensor-core path
-int agcn_conv_fwd_tc(const float* x, const float* w, const float* bias, float* y,
-                     int nb, int t_in, int t_out, int v, int cin, int cout,
-                     int taps, int stride, int pad, int transposed, int accumulate, int split, float* w_lo, void* stream);
+// implemented in conv_tc2.cu / wgrad_tc.cu; return AGCN_ERR_UNSUPPORTED when the shape is outside the tensor-core path
 int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* y,
                       int nb, int t_in, int t_out, int v, int cin, int cout,
                       int taps, int stride, int pad, int transposed, int accumulate, int split, float* w_split, void* stream,
@@ -576,10 +573,7 @@ static int conv_fwd_impl(const float* x, const float* w, const float* bias, floa
             }
             int rc2 = agcn_conv_fwd_tc2(x, w, bias, y, nb, t_in, t_out, v, cin, cout, taps, stride, pad, transposed, accumulate, split,
                                         static_cast<float*>(workspace), stream, nullptr, nullptr);
-            if (rc2 != AGCN_ERR_UNSUPPORTED) return rc2;
-            int rc = agcn_conv_fwd_tc(x, w, bias, y, nb, t_in, t_out, v, cin, cout, taps, stride, pad, transposed,
-                                      accumulate, split, static_cast<float*>(workspace), stream);
-            if (rc != AGCN_ERR_UNSUPPORTED) return rc;   // unsupported shapes fall through to the FFMA kernel
+            if (rc2 != AGCN_ERR_UNSUPPORTED) return rc2;   // unsupported shapes fall through to the FFMA kernel
         }
     }
     if (taps == 1 && stride == 1 && pad == 0 && t_in == t_out && cout < 16 && cin % 4 == 0 && cin <= 1024 && aligned16(x) && aligned16(w)) {
@@ -626,7 +620,7 @@ extern "C" AGCN_API int agcn_conv_fwd_stats(const float* x, const float* w, cons
     AGCN_REQUIRE(cout > 0 && stat_part_bytes >= agcn_conv_fwd_stats_bytes(cout), AGCN_ERR_WORKSPACE, "agcn_conv_fwd_stats: partial buffer too small");
     AGCN_REQUIRE(aligned16(stat_part), AGCN_ERR_MISALIGNED, "agcn_conv_fwd_stats: partial buffer not 16-byte aligned");
     *stat_nparts = 0;
-    static const bool off = getenv("AGCN_NO_FUSED_STATS") != nullptr;
+    static const bool off = probe_env("AGCN_NO_FUSED_STATS") != nullptr;
     return conv_fwd_impl(x, w, bias, y, nb, t_in, t_out, v, cin, cout, taps, stride, pad, 0, 0, precision,
                          workspace, workspace_bytes, stream, off ? nullptr : stat_part, off ? nullptr : stat_nparts);
 }
@@ -709,7 +703,7 @@ extern "C" AGCN_API int agcn_conv_wgrad(const float* dy, const float* x, float* 
             float* bpart = dbias ? part + P * wsize : nullptr;
             const size_t smem = ((size_t)kSkinnyRows * 16 + (size_t)lanes * cpad * 17) * sizeof(float);
             cudaStream_t s = static_cast<cudaStream_t>(stream);
-            static const bool scalar_only = getenv("AGCN_SKINNY_SCALAR") != nullptr;
+            static const bool scalar_only = probe_env("AGCN_SKINNY_SCALAR") != nullptr;
             const int cmax = cin <= 4 ? 4 : 16;
             const size_t smem4 = ((size_t)kSkinnyRows * 16 + (size_t)(256 / (cout / 4 > 0 ? cout / 4 : 1)) * cout * (cmax + 1)) * sizeof(float);
             if (!scalar_only && cout % 4 == 0 && cout >= 16 && aligned16(dy) && smem4 <= 100 * 1024) {

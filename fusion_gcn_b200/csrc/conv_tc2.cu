@@ -512,10 +512,10 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
                       float* stat_part, int* stat_nparts) {
     using namespace agcn::tc;
     using namespace agcn::tc2;
-    static const bool disabled = getenv("AGCN_TC_V1") != nullptr;
-    static const bool no_1x1 = getenv("AGCN_TC2_NO1X1") != nullptr;
-    static const bool no_skip_parity = getenv("AGCN_TC2_NO_SKIP_PARITY") != nullptr;
-    static const int dbg = getenv("AGCN_CONV_DEBUG") ? atoi(getenv("AGCN_CONV_DEBUG")) : 0;
+    static const bool disabled = probe_env("AGCN_TC_V1") != nullptr;
+    static const bool no_1x1 = probe_env("AGCN_TC2_NO1X1") != nullptr;
+    static const bool no_skip_parity = probe_env("AGCN_TC2_NO_SKIP_PARITY") != nullptr;
+    static const int dbg = probe_env("AGCN_CONV_DEBUG") ? atoi(probe_env("AGCN_CONV_DEBUG")) : 0;
     if (disabled || (no_1x1 && taps == 1)) return AGCN_ERR_UNSUPPORTED;
     if (cin % 4 || cout % 16 || v > 128 || stride > 2 || taps > kMaxTaps) return AGCN_ERR_UNSUPPORTED;
     if (transposed && stride > 1 && taps < stride && no_skip_parity) return AGCN_ERR_UNSUPPORTED;
@@ -539,7 +539,7 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
     a.y = y; a.bias = bias; a.stat_part = stat_part;
     a.nb = nb; a.t_out = t_out; a.v = v; a.cin = cin; a.cout = cout; a.stride = stride; a.transposed = transposed; a.accumulate = accumulate;
     a.dbg = dbg;
-    static const bool no_dual = getenv("AGCN_TC2_NO_DUAL") != nullptr;
+    static const bool no_dual = probe_env("AGCN_TC2_NO_DUAL") != nullptr;
     // main | cross accumulator pairs: multi-segment tiles up to 64 wide (2*bn <= 128 next to the master sums), single-segment
     // tiles (1x1 convs with cin <= 256: no master sums) up to 128 wide (2*bn <= 256 = one of the two accumulator buffers)
     a.dual = (split && !no_dual && ((kiters > 8 && bn <= 64) || (kiters <= 8 && bn <= 128))) ? 1 : 0;
@@ -618,14 +618,14 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
     const uint32_t stat_bytes = stat_part != nullptr ? kStatBytes : 0u;
     // TMA-store epilogue for the 1x1 convolutions (their time is the output stream: skipping the stores halves it, profiles/r2b);
     // the 9-tap kernels are bound elsewhere and keep their shared memory for the operand rings
-    static const bool no_tma_store = getenv("AGCN_TC2_NO_TMA_STORE") != nullptr;
-    static const bool tma_store_all = getenv("AGCN_TC2_TMA_STORE_ALL") != nullptr;      // experiment: also the 9-tap kernels
+    static const bool no_tma_store = probe_env("AGCN_TC2_NO_TMA_STORE") != nullptr;
+    static const bool tma_store_all = probe_env("AGCN_TC2_TMA_STORE_ALL") != nullptr;      // experiment: also the 9-tap kernels
     a.tma_store = (!no_tma_store && (taps == 1 || tma_store_all) && bn % 32 == 0 && aligned16(y)) ? 1 : 0;
     const uint32_t epi_bytes = a.tma_store ? 1024u + kTmaStageBytes : kBarBytes + kStageBytes;
     const uint32_t budget = kSmemBudget - 1024u - epi_bytes - stat_bytes;
     // Ring depths.  Weights: 3 slots (2 when tight).  3xTF32 lo residuals: 2 slots, 1 when two would leave a single
     // activation stage.  Everything else goes to the activation ring: payload bytes in flight set the achieved bandwidth.
-    static const int nlo_env = getenv("AGCN_TC2_NLO") ? atoi(getenv("AGCN_TC2_NLO")) : 0;
+    static const int nlo_env = probe_env("AGCN_TC2_NLO") ? atoi(probe_env("AGCN_TC2_NLO")) : 0;
     // lo-residual ring: 2 slots (3 or 4 measured no faster for the 1x1 kernels and slower where they shorten the payload ring, profiles/r2g)
     int nlo_want = split ? 2 : 0;
     if (split && nlo_env >= 1 && nlo_env <= kMaxLo) nlo_want = nlo_env;
@@ -653,7 +653,7 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
     // Resident weights: a 1x1 conv with a single output-channel tile re-reads the SAME weight boxes for every 125-row tile (for
     // 64 -> 192 channels in 3xTF32 that is 98 KB of weights per 32 KB of activations through the SM's ingress).  When all K chunks
     // fit the weight ring next to at least three activation stages they are loaded once per CTA and never released.
-    static const bool no_resident = getenv("AGCN_TC2_NO_RESIDENT_W") != nullptr;
+    static const bool no_resident = probe_env("AGCN_TC2_NO_RESIDENT_W") != nullptr;
     a.w_resident = 0;
     if (!no_resident && taps == 1 && a.n_tiles_n == 1 && a.nparity == 1 && a.kchunks <= kMaxB) {
         const uint64_t wbytes = (uint64_t)a.kchunks * b_slot;
@@ -719,12 +719,10 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
             if (r != CUDA_SUCCESS) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc2: cuTensorMapEncodeTiled(Y) failed with %d", (int)r);
         }
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    {   // per call: the attribute is per device / context, a process-wide flag would skip the second GPU
         cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
         if (e != cudaSuccess) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc2: %s", cudaGetErrorString(e));
-        attr_set = true;
     }
     if (skipped_parity && !accumulate) {
         // the kernel only visits the parity classes that have taps; the other output timesteps are exact zeros

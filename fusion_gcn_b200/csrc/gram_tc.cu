@@ -244,7 +244,7 @@ int agcn_joint_gram_tc(const float* a, const float* b, float* out,
                        int offa, int stridea, int offb, int strideb, int width, int nchunk, int split, void* stream) {
     using namespace agcn::tc;
     using namespace agcn::gtc;
-    static const bool disabled = getenv("AGCN_GRAM_SIMT") != nullptr;
+    static const bool disabled = probe_env("AGCN_GRAM_SIMT") != nullptr;
     if (disabled) return AGCN_ERR_UNSUPPORTED;
     const int ga = stridea == 0 ? 1 : groups;
     if (groups != 3 || v * groups > 80 || v * ga > 128) return AGCN_ERR_UNSUPPORTED;
@@ -295,12 +295,10 @@ int agcn_joint_gram_tc(const float* a, const float* b, float* out,
     if (r != CUDA_SUCCESS) return fail(AGCN_ERR_CUDA, "agcn_joint_gram_tc: cuTensorMapEncodeTiled(a) failed with %d", (int)r);
     r = encode(&map_b, b, ldb, groups, strideb);
     if (r != CUDA_SUCCESS) return fail(AGCN_ERR_CUDA, "agcn_joint_gram_tc: cuTensorMapEncodeTiled(b) failed with %d", (int)r);
-    static bool attr_set = false;
-    if (!attr_set) {
+    {   // per call: the attribute is per device / context, a process-wide flag would skip the second GPU
         cudaError_t e = cudaFuncSetAttribute(gram_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gram_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
         if (e != cudaSuccess) return fail(AGCN_ERR_CUDA, "agcn_joint_gram_tc: %s", cudaGetErrorString(e));
-        attr_set = true;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (split) gram_tc_kernel<true><<<nb * nchunk, kThreadsGSplit, smem, st>>>(map_a, map_b, p);

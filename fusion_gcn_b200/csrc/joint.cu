@@ -512,7 +512,7 @@ extern "C" AGCN_API int agcn_joint_mix(const float* in, const float* mats, float
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bool vec = (width % 4 == 0) && aligned16(in) && aligned16(out);
     cudaError_t e;
-    static const bool mix8 = getenv("AGCN_MIX8") != nullptr;      // 2-quad items: measured slower on B200 (114 registers), kept for experiments
+    static const bool mix8 = probe_env("AGCN_MIX8") != nullptr;      // 2-quad items: measured slower on B200 (114 registers), kept for experiments
     if (vec && width % 8 == 0 && mix8) {
         e = cudaFuncSetAttribute(joint_mix_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return fail(AGCN_ERR_CUDA, "agcn_joint_mix: %s", cudaGetErrorString(e));

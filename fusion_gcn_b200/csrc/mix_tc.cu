@@ -451,9 +451,9 @@ int agcn_joint_mix_tc(const float* in, const float* mats, float* out, float* gp,
                       int nb, int t, int v, int ldin, int ldout, int width, int mode, int accumulate, int split, void* stream) {
     using namespace agcn::tc;
     using namespace agcn::mtc;
-    static const bool disabled = getenv("AGCN_MIX_SIMT") != nullptr;
+    static const bool disabled = probe_env("AGCN_MIX_SIMT") != nullptr;
     if (disabled) return AGCN_ERR_UNSUPPORTED;
-    static const bool score_simt = getenv("AGCN_MIX_SCORE_SIMT") != nullptr;
+    static const bool score_simt = probe_env("AGCN_MIX_SCORE_SIMT") != nullptr;
     const bool score = mode == AGCN_MIX_SCORE_BWD;
     if (mode != AGCN_MIX_AGG_FWD && mode != AGCN_MIX_AGG_BWD && !(score && !score_simt)) return AGCN_ERR_UNSUPPORTED;
     if (v > 32 || width % (score ? 16 : 32) || !aligned16(in) || !aligned16(out) || gp == nullptr || !aligned16(gp)) return AGCN_ERR_UNSUPPORTED;
@@ -473,7 +473,7 @@ int agcn_joint_mix_tc(const float* in, const float* mats, float* out, float* gp,
     p.a_tile = (uint32_t)p.kb * 4u * kBoxBytes;
     p.ldout = ldout;
     p.mat_bytes = score ? 2u * kMatBytes : kMatBytes;
-    static const bool no_tma_out = getenv("AGCN_MIX_NO_TMA_STORE") != nullptr;
+    static const bool no_tma_out = probe_env("AGCN_MIX_NO_TMA_STORE") != nullptr;
     p.tma_out = (!no_tma_out && ldout % 4 == 0 && (!score || width == 16 || width % 32 == 0)) ? 1 : 0;
     const uint32_t out_stage = p.tma_out ? 4u * ((score || p.bwd) ? 1u : 3u) * kBoxBytes : 0u;
     const uint32_t fixed = 2u * p.mat_bytes * (split ? 2u : 1u) + kBarBytes + out_stage + 1024u;

@@ -1,304 +1,26 @@
-// tcgen05 / TMA tensor-core path of the implicit GEMM (AGCN_PREC_TF32), sm_100a only.
+// tcgen05 / TMA tensor-core weight gradient of the implicit GEMM, sm_100a only (the forward / input-gradient contraction
+// lives in conv_tc2.cu).
 //
-//   y[nb][to][v][co] (+)= bias[co] + sum_tap sum_ci x[nb][ti(to,tap)][v][ci] * w[co][tap][ci]
-//
-// Tiling: one CTA tile = `tt` consecutive output timesteps x all V joints (tt*V <= 128 rows, the UMMA M=128 atom)
-// x BN output channels.  The temporal taps are not materialised: for tap `tap` the A operand is the same TMA box
-// shifted along the T coordinate of a 4-D tensor map (cin, V, T, nb); out-of-range timesteps are zero-filled by
-// TMA, which is exactly the conv's zero padding.  Stride-2 convs use the tensor map's elementStrides; the
-// transposed (input-gradient) gather of a stride-s conv is split into s parity classes of output timesteps, each
-// of which is a plain shifted box again.
-//
-// Pipeline (192 threads, 1 CTA / SM, persistent over tiles):
-//   warp 0      TMA producer: A box (<=128 rows x 32 fp32, 128B swizzle) + B box (BN x 32) per (tap, k-chunk) stage
-//   warp 1      MMA issuer: 4 x tcgen05.mma.kind::tf32 (M128, N=BN, K8) per stage, fp32 accumulators in TMEM,
-//               tcgen05.commit releases the smem stage / publishes the accumulator
-//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 16 columns) -> +bias (+old) -> coalesced-per-row st.global
-// TMEM: 2 x 128 columns, so the epilogue of tile i overlaps the main loop of tile i+1.
+//   dw[co][tap][ci] = sum_rows dy[nb][to][v][co] * x[nb][stride*to+tap-pad][v][ci]
 //
 // Precision.  tcgen05.mma kind::tf32 reads fp32 words from shared memory and uses their upper 19 bits (measured on
 // B200: results match an fp64 contraction of TF32-TRUNCATED operands to 1e-6).  SPLIT = false is that single pass
 // (AGCN_PREC_TF32).  SPLIT = true is the fp32-parity mode (AGCN_PREC_FP32, "3xTF32"): with hi = rna_tf32(x) (round to
 // nearest, so the split is unbiased) and lo = x - hi (exact in fp32), it issues
 //   lo_a*hi_b + hi_a*lo_b + hi_a*hi_b  =  a*b - lo_a*lo_b  (relative error ~2^-22 per product)
-// The activation hi/lo tiles are produced in shared memory by four transform warps (ld.shared -> cvt.rna -> st.shared in
-// place + lo tile -> fence.proxy.async -> mbarrier arrive); the weight hi/lo tensors are precomputed into the caller's
-// workspace and TMA-loaded.
 #include "tc_common.cuh"
 #include <stdlib.h>
 
 namespace agcn {
 namespace tc {
 
-constexpr int kStages = 6;                  // barrier slots; SPLIT kernels use 3 stages of twice the size
-constexpr int kABytes = 16 * 1024;
 constexpr int kThreads = 192;               // TMA warp, MMA warp, 4 epilogue warps
-constexpr int kThreadsSplit = 320;          // + 4 transform warps
-constexpr size_t kSmemBytes = (size_t)192 * 1024 + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
 constexpr int kWgTransformWarps = 8;                       // 3xTF32 weight gradient: operand-split warps
 constexpr int kWgStages = 8;                               // barrier slots of the weight-gradient raw ring
 constexpr int kWgBarBytes = 512;
 constexpr int kWgThreadsSplit = (6 + kWgTransformWarps) * 32;
 
-struct TcArgs {
-    float* y; const float* bias;
-    int nb, t_in, t_out, v, cin, cout, taps, stride, pad, transposed, accumulate;
-    int tt, bn, n_tiles_n, kchunks, tiles_t, nparity;
-    long long total_tiles;
-    int dbg;      // bring-up only (env AGCN_CONV_DEBUG): 1 skip operand split, 2 one MMA per stage, 4 skip global stores
-};
-
-// number of (tap) iterations and their A-box T coordinate for one tile
-struct TapIter {
-    int tap, tcoord;
-};
-__device__ __forceinline__ bool tap_valid(const TcArgs& a, int par, int tap, int jt, int& tcoord) {
-    if (!a.transposed) {
-        tcoord = a.stride * (jt * a.tt) + tap - a.pad;
-        return true;
-    }
-    int num = par + a.pad - tap;
-    if (num % a.stride) return false;      // C++ remainder of a negative multiple of stride is 0 as well
-    tcoord = jt * a.tt + num / a.stride;
-    return true;
-}
-
-// (tap, k-chunk) iterations of one tile
-__device__ __forceinline__ int tile_iters(const TcArgs& a, int par) {
-    int taps = a.taps;
-    if (a.transposed && a.stride > 1) {
-        taps = 0;
-        for (int tap = 0; tap < a.taps; ++tap) taps += ((par + a.pad - tap) % a.stride == 0) ? 1 : 0;
-    }
-    return taps * a.kchunks;
-}
-
-template <bool SPLIT>
-__global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreads, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const __grid_constant__ CUtensorMap map_blo, TcArgs a) {
-    constexpr int NST = SPLIT ? 3 : 6;
-    constexpr uint32_t STAGE = SPLIT ? 64u * 1024u : 32u * 1024u;     // A raw | B raw | (A lo | B lo)
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar_base = smem_base + NST * STAGE;
-    // barriers: full[6], empty[6], lo[6], tmem_full[2], tmem_empty[2]; then the TMEM base address word
-    auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
-    auto lo_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
-    auto tfull_bar = [&](int s) { return bar_base + 8u * (3 * kStages + s); };
-    auto tempty_bar = [&](int s) { return bar_base + 8u * (3 * kStages + 2 + s); };
-    const uint32_t tmem_slot = bar_base + 8u * (3 * kStages + 4);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
-        for (int s = 0; s < NST; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); mbar_init(lo_bar(s), 4); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(kTmemCols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    uint32_t tmem_base;
-    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-
-    const int rows_box = a.v * a.tt;
-    const uint32_t stage_tx = (uint32_t)(rows_box * 128 + a.bn * 128 * (SPLIT ? 2 : 1));
-
-    if (warp == 0) {
-        // ===================================================== TMA producer
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-                long long r = tile;
-                const int nt = (int)(r % a.n_tiles_n); r /= a.n_tiles_n;
-                const int jt = (int)(r % a.tiles_t); r /= a.tiles_t;
-                const int par = (int)(r % a.nparity);
-                const int n = (int)(r / a.nparity);
-                for (int tap = 0; tap < a.taps; ++tap) {
-                    int tcoord;
-                    if (!tap_valid(a, par, tap, jt, tcoord)) continue;
-                    for (int kc = 0; kc < a.kchunks; ++kc) {
-                        mbar_wait(empty_bar(stage), phase ^ 1u);
-                        mbar_expect_tx(full_bar(stage), stage_tx);
-                        const uint32_t sa = smem_base + stage * STAGE;
-                        tma_load_4d(sa, &map_a, full_bar(stage), kc * kKChunk, 0, tcoord, n);
-                        tma_load_3d(sa + kABytes, &map_b, full_bar(stage), kc * kKChunk, tap, nt * a.bn);        // W (or W hi)
-                        if (SPLIT) tma_load_3d(sa + 3 * kABytes, &map_blo, full_bar(stage), kc * kKChunk, tap, nt * a.bn);
-                        if (++stage == NST) { stage = 0; phase ^= 1u; }
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ===================================================== MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.bn >> 3) << 17) | ((128u >> 4) << 24);
-            int stage = 0; uint32_t phase = 0;
-            int acc = 0; uint32_t acc_phase = 0;
-            for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-                long long r = tile;
-                r /= a.n_tiles_n;
-                const int jt = (int)(r % a.tiles_t); r /= a.tiles_t;
-                const int par = (int)(r % a.nparity);
-                const int iters = tile_iters(a, par);
-                int it = 0;
-                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
-                uint32_t first = 1;
-                for (int tap = 0; tap < a.taps; ++tap) {
-                    int tcoord;
-                    if (!tap_valid(a, par, tap, jt, tcoord)) continue;
-                    for (int kc = 0; kc < a.kchunks; ++kc) {
-                        mbar_wait(full_bar(stage), phase);
-                        if (SPLIT) mbar_wait(lo_bar(stage), phase);
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t sa = smem_base + stage * STAGE;
-                        const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + kABytes);
-                        const uint64_t dalo = make_smem_desc(sa + 2 * kABytes), dblo = make_smem_desc(sa + 3 * kABytes);
-#pragma unroll
-                        for (int k = 0; k < kKChunk / 8; ++k) {
-                            if ((a.dbg & 2) && k) break;
-                            const uint64_t ko = (uint64_t)(k * 2);
-                            if (SPLIT) {
-                                umma_tf32(d_tmem, dalo + ko, db + ko, idesc, first ? 0u : 1u);
-                                umma_tf32(d_tmem, da + ko, dblo + ko, idesc, 1u);
-                                umma_tf32(d_tmem, da + ko, db + ko, idesc, 1u);
-                            } else {
-                                umma_tf32(d_tmem, da + ko, db + ko, idesc, first ? 0u : 1u);
-                            }
-                            first = 0;
-                        }
-                        umma_commit(empty_bar(stage));          // smem stage reusable once these MMAs retire
-                        if (++stage == NST) { stage = 0; phase ^= 1u; }
-                        ++it;
-                        if (SPLIT && (it % kSegment) == 0 && it < iters) {
-                            // promote: hand this partial accumulator to the epilogue (it adds segments in fp32 registers,
-                            // round-to-nearest) and continue in the other TMEM buffer.  Keeps the chain of truncating
-                            // tensor-core accumulations short (<= kSegment*4*3 MMAs).
-                            umma_commit(tfull_bar(acc));
-                            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-                            mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                            d_tmem = tmem_base + (uint32_t)(acc * 128);
-                            first = 1;
-                        }
-                    }
-                }
-                umma_commit(tfull_bar(acc));                     // accumulator complete
-                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-            }
-        }
-    } else if (warp < 6) {
-        // ===================================================== epilogue warps (TMEM lane quarter = warp % 4)
-        const int q = warp & 3;
-        const int row_local = q * 32 + lane;
-        int acc = 0; uint32_t acc_phase = 0;
-        for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-            long long r = tile;
-            const int nt = (int)(r % a.n_tiles_n); r /= a.n_tiles_n;
-            const int jt = (int)(r % a.tiles_t); r /= a.tiles_t;
-            const int par = (int)(r % a.nparity);
-            const int n = (int)(r / a.nparity);
-            const int tl = row_local / a.v, vv = row_local - tl * a.v;
-            const int j = jt * a.tt + tl;
-            const int to = a.transposed ? a.stride * j + par : j;
-            const bool row_ok = (tl < a.tt) && (to < a.t_out);
-            float* yrow = a.y + (((long long)n * a.t_out + to) * a.v + vv) * a.cout + nt * a.bn;
-            const int iters = tile_iters(a, par);
-            const int nseg = SPLIT ? (iters + kSegment - 1) / kSegment : 1;
-            float sum[SPLIT ? 128 : 1];              // SPLIT: fp32 running sum of the promoted segments (bn <= 128)
-            for (int sg = 0; sg < nseg; ++sg) {
-                mbar_wait(tfull_bar(acc), acc_phase);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t taddr = tmem_base + (uint32_t)(acc * 128) + ((uint32_t)(q * 32) << 16);
-#pragma unroll
-                for (int cg = 0; cg < 8; ++cg) {
-                    const int c = cg * 16;
-                    if (c < a.bn) {
-                        float vals[16];
-                        tmem_ld16(taddr + (uint32_t)c, vals);
-                        if (SPLIT) {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) sum[SPLIT ? c + i : 0] = (sg == 0) ? vals[i] : sum[SPLIT ? c + i : 0] + vals[i];
-                        }
-                        if (sg == nseg - 1 && row_ok && !(a.dbg & 4)) {
-                            const int col = nt * a.bn + c;
-#pragma unroll
-                            for (int g = 0; g < 4; ++g) {
-                                if (col + g * 4 >= a.cout) break;
-                                float4 o;
-                                if (SPLIT) o = make_float4(sum[SPLIT ? c + g * 4 : 0], sum[SPLIT ? c + g * 4 + 1 : 0], sum[SPLIT ? c + g * 4 + 2 : 0], sum[SPLIT ? c + g * 4 + 3 : 0]);
-                                else o = make_float4(vals[g * 4], vals[g * 4 + 1], vals[g * 4 + 2], vals[g * 4 + 3]);
-                                if (a.bias) {
-                                    const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + col + g * 4));
-                                    o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                                }
-                                float4* p = reinterpret_cast<float4*>(yrow + c + g * 4);
-                                if (a.accumulate) {
-                                    const float4 old = *p;
-                                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-                                }
-                                *p = o;
-                            }
-                        }
-                    }
-                }
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tempty_bar(acc));
-                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-            }
-        }
-    } else if (SPLIT) {
-        // ===================================================== transform warps: A -> (hi in place, lo tile)
-        const int tid128 = threadIdx.x - 6 * 32;
-        int stage = 0; uint32_t phase = 0;
-        for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-            long long r = tile;
-            r /= a.n_tiles_n;
-            const int jt = (int)(r % a.tiles_t); r /= a.tiles_t;
-            const int par = (int)(r % a.nparity);
-            for (int tap = 0; tap < a.taps; ++tap) {
-                int tcoord;
-                if (!tap_valid(a, par, tap, jt, tcoord)) continue;
-                for (int kc = 0; kc < a.kchunks; ++kc) {
-                    mbar_wait(full_bar(stage), phase);
-                    const uint32_t sa = smem_base + stage * STAGE;
-                    if (!(a.dbg & 1)) transform_split(sa, sa + 2 * kABytes, (uint32_t)rows_box * 128u, tid128);
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(lo_bar(stage));
-                    if (++stage == NST) { stage = 0; phase ^= 1u; }
-                }
-            }
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
-    }
-}
-
-// ---------------------------------------------------------------- host side
-// ================================================================================================ weight gradient
-//   dw[co][tap][ci] = sum_rows dy[row][co] * x[gather(row, tap)][ci]
-// UMMA view: D[M = co (128)][N = ci (<=256)] += A[M x K] * B[N x K]^T with K = rows.  Both operands are MN-major in
-// shared memory: a TMA box of 32 channels x R rows lands as R rows of 128 bytes (128B swizzle), which is exactly the
-// canonical MN-major "128B swizzle, 32-byte atom" layout that tf32 MN-major operands require (32 fp32 along MN,
-// 4 rows along K per 512-byte atom; TMA swizzle CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).  One MMA (K = 8) consumes two
-// 4-row groups (SBO = 512 B) of every 32-channel sub-box; sub-boxes are LBO = rpad*128 bytes apart.
-// Split-K over row chunks across CTAs; partial tiles go to the workspace and are summed by wgrad_reduce_kernel
-// (deterministic).  Rows [rows_box, rpad) of every sub-box are zero (shared memory is cleared once, TMA never writes them).
 struct WgArgs {
     float* ws;
     int nb, t_in, t_out, v, cin, cout, taps, stride, pad;
@@ -590,7 +312,7 @@ static WgPlan plan_wgrad(int nb, int t_in, int t_out, int v, int cin, int cout, 
     // Rows per stage.  Every stage costs ~1000-1400 cycles of fixed work (TMA issue, barrier hops, operand split, MMA issue;
     // probes in profiles/r1v, r1w), so stages are as tall as shared memory allows: TF32 four stages of 48 KB; 3xTF32 three raw
     // stages + two lo slots in 200 KB (40 KB each).
-    static const int split_kb = getenv("AGCN_WG_SPLIT_KB") ? atoi(getenv("AGCN_WG_SPLIT_KB")) : 40;
+    static const int split_kb = probe_env("AGCN_WG_SPLIT_KB") ? atoi(probe_env("AGCN_WG_SPLIT_KB")) : 40;
     int rmax = ((split ? split_kb : 48) * 1024) / (nsub * 128);
     rmax = rmax / 8 * 8;
     if (rmax > 128) rmax = 128;
@@ -640,87 +362,6 @@ static WgPlan plan_wgrad(int nb, int t_in, int t_out, int v, int cin, int cout, 
 
 using namespace agcn;
 
-// returns AGCN_ERR_UNSUPPORTED (without touching the error string's meaning) when the shape is outside this path.
-// split != 0: 3xTF32 (fp32 parity); w_split must then point to 2*cout*taps*cin floats of scratch (hi | lo).
-int agcn_conv_fwd_tc(const float* x, const float* w, const float* bias, float* y,
-                     int nb, int t_in, int t_out, int v, int cin, int cout,
-                     int taps, int stride, int pad, int transposed, int accumulate, int split, float* w_split, void* stream) {
-    using namespace agcn::tc;
-    if (cin % 4 || cout % 16 || v > 128 || stride > 4) return AGCN_ERR_UNSUPPORTED;
-    if (transposed && stride > 1 && taps < stride) return AGCN_ERR_UNSUPPORTED;       // some parity classes would have no taps
-    if (!aligned16(x) || !aligned16(w) || !aligned16(y) || (bias && !aligned16(bias))) return AGCN_ERR_UNSUPPORTED;
-    if (split && (w_split == nullptr || !aligned16(w_split) || ((long long)cout * taps * cin) % 4)) return AGCN_ERR_UNSUPPORTED;
-    int bn;
-    if (cout % 128 == 0) bn = 128;
-    else if (cout % 96 == 0) bn = 96;
-    else if (cout % 64 == 0) bn = 64;
-    else if (cout <= 128) bn = cout;
-    else return AGCN_ERR_UNSUPPORTED;
-    EncodeTiledFn enc = encode_fn();
-    if (!enc) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc: cuTensorMapEncodeTiled is not available from the driver");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-
-    TcArgs a;
-    static const int dbg = getenv("AGCN_CONV_DEBUG") ? atoi(getenv("AGCN_CONV_DEBUG")) : 0;
-    a.dbg = dbg;
-    a.y = y; a.bias = bias;
-    a.nb = nb; a.t_in = t_in; a.t_out = t_out; a.v = v; a.cin = cin; a.cout = cout;
-    a.taps = taps; a.stride = stride; a.pad = pad; a.transposed = transposed; a.accumulate = accumulate;
-    a.tt = 128 / v;
-    const int es = transposed ? 1 : stride;          // element stride of the A box along T
-    while (a.tt * es > 256) --a.tt;
-    a.bn = bn;
-    a.n_tiles_n = cout / bn;
-    a.kchunks = (cin + kKChunk - 1) / kKChunk;
-    a.nparity = transposed ? stride : 1;
-    const int t_per_class = transposed ? (t_out + stride - 1) / stride : t_out;
-    a.tiles_t = (t_per_class + a.tt - 1) / a.tt;
-    a.total_tiles = (long long)nb * a.nparity * a.tiles_t * a.n_tiles_n;
-
-    CUtensorMap map_a, map_b, map_blo;
-    {
-        cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)v, (cuuint64_t)t_in, (cuuint64_t)nb};
-        cuuint64_t strides[3] = {(cuuint64_t)cin * 4, (cuuint64_t)v * cin * 4, (cuuint64_t)t_in * v * cin * 4};
-        cuuint32_t box[4] = {(cuuint32_t)kKChunk, (cuuint32_t)v, (cuuint32_t)(a.tt * es), 1};
-        cuuint32_t estr[4] = {1, 1, (cuuint32_t)es, 1};
-        CUresult r = enc(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
-    }
-    auto encode_w = [&](CUtensorMap* m, const float* ptr) -> CUresult {
-        cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)taps, (cuuint64_t)cout};
-        cuuint64_t strides[2] = {(cuuint64_t)cin * 4, (cuuint64_t)taps * cin * 4};
-        cuuint32_t box[3] = {(cuuint32_t)kKChunk, 1, (cuuint32_t)bn};
-        cuuint32_t estr[3] = {1, 1, 1};
-        return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    };
-    const long long nw = (long long)cout * taps * cin;
-    CUresult r = encode_w(&map_b, split ? w_split : w);
-    if (r != CUDA_SUCCESS) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
-    map_blo = map_b;
-    if (split) {
-        r = encode_w(&map_blo, w_split + nw);
-        if (r != CUDA_SUCCESS) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc: cuTensorMapEncodeTiled(B lo) failed with %d", (int)r);
-        split_weights_kernel<<<ceil_div(nw, 256), 256, 0, st>>>(w, w_split, nw);
-        int rc = check_launch("agcn_conv_fwd_tc(split weights)");
-        if (rc) return rc;
-    }
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-        if (e != cudaSuccess) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc: %s", cudaGetErrorString(e));
-        attr_set = true;
-    }
-    long long grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
-    if (split) conv_tc_kernel<true><<<(unsigned)grid, kThreadsSplit, kSmemBytes, st>>>(map_a, map_b, map_blo, a);
-    else conv_tc_kernel<false><<<(unsigned)grid, kThreads, kSmemBytes, st>>>(map_a, map_b, map_blo, a);
-    return check_launch("agcn_conv_fwd_tc");
-}
-
 // ---- weight gradient on tensor cores; returns AGCN_ERR_UNSUPPORTED for shapes outside the path
 size_t agcn_conv_wgrad_tc_workspace_floats(int nb, int t_in, int t_out, int v, int cin, int cout, int taps, int stride, int pad, int split) {
     agcn::tc::WgPlan p = agcn::tc::plan_wgrad(nb, t_in, t_out, v, cin, cout, taps, stride, pad, split != 0);
@@ -738,10 +379,10 @@ int agcn_conv_wgrad_tc(const float* dy, const float* x, float* ws, int* splits_o
     if (!enc) return fail(AGCN_ERR_CUDA, "agcn_conv_wgrad_tc: cuTensorMapEncodeTiled is not available from the driver");
     WgArgs& a = p.a;
     a.ws = ws;
-    static const int dbg = getenv("AGCN_WG_DEBUG") ? atoi(getenv("AGCN_WG_DEBUG")) : 0;
+    static const int dbg = probe_env("AGCN_WG_DEBUG") ? atoi(probe_env("AGCN_WG_DEBUG")) : 0;
     a.dbg = dbg;
     CUtensorMap map_dy, map_x;
-    static const bool no_blocked = getenv("AGCN_WG_NOBLOCK") != nullptr;
+    static const bool no_blocked = probe_env("AGCN_WG_NOBLOCK") != nullptr;
     a.blocked = (!no_blocked && a.flat && cin % 32 == 0 && cout % 32 == 0) ? 1 : 0;
     a.nblk_a = a.pair ? cout / 32 : ((cout + 31) / 32 < 4 ? (cout + 31) / 32 : 4);
     auto encode = [&](CUtensorMap* m, const float* ptr, int c, int t, int box1, int box2, int es2) -> CUresult {
@@ -775,12 +416,10 @@ int agcn_conv_wgrad_tc(const float* dy, const float* x, float* ws, int* splits_o
         if (r == CUDA_SUCCESS) r = encode(&map_x, x, cin, t_in, a.rows_box, a.tt * stride, stride);
     }
     if (r != CUDA_SUCCESS) return fail(AGCN_ERR_CUDA, "agcn_conv_wgrad_tc: cuTensorMapEncodeTiled failed with %d", (int)r);
-    static bool attr_set = false;
-    if (!attr_set) {
+    {   // per call: the attribute is per device / context, a process-wide flag would skip the second GPU
         cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
         if (e != cudaSuccess) return fail(AGCN_ERR_CUDA, "agcn_conv_wgrad_tc: %s", cudaGetErrorString(e));
-        attr_set = true;
     }
     dim3 grid((unsigned)(a.tap_tiles * a.m_tiles * a.n_tiles), (unsigned)p.splits);
     cudaStream_t st = static_cast<cudaStream_t>(stream);

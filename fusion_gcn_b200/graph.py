@@ -76,6 +76,6 @@ def imu_fusion_graph(graph, num_imu_joints, mode="append_center", interconnect=F
             new += [(nv + i, kwargs["right_wrist_joint"]), (nv + i, kwargs["right_hip_joint"])]
     else:
         raise ValueError("Unsupported imu_enhanced_mode: " + str(mode))
-    if interconnect:
+    if interconnect or kwargs.get("interconnect_imu_joints", False):       # the reference's keyword (fusion.py:84)
         new += [(nv + i, nv + j) for i in range(num_imu_joints) for j in range(i + 1, num_imu_joints)]
     return SkeletonGraph(np.vstack((np.asarray(graph.edges), np.asarray(new, dtype=np.int64))), center_joint=graph.center_joint)

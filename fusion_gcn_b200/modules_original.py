@@ -53,11 +53,13 @@ class Model(M.Model):
 
     def __init__(self, data_shape, num_classes, graph, **kwargs):
         shape = data_shape["skeleton"] if isinstance(data_shape, dict) else data_shape
-        adj = kwargs.pop("adjacency_matrix", None)
-        kwargs.pop("mode", None)
+        adj = kwargs.get("adjacency_matrix", None)
         if adj is None:
             adj = adjacency_from_graph(graph)
-        super().__init__(shape, num_classes, graph, adjacency_matrix=np.asarray(adj), **kwargs)
+        # the reference reads nothing else from **kwargs (agcn.py:137-146): unknown model_args from a YAML (``mode`` ...) are
+        # ignored there, so they are ignored here too; the size options of the mmargcn variant are accepted as an extension
+        known = {k: v for k, v in kwargs.items() if k in ("num_layers", "start_feature_size", "without_fc", "dropout")}
+        super().__init__(shape, num_classes, graph, adjacency_matrix=np.asarray(adj), **known)
 
     def _register_layers(self):
         for layer_idx, layer in enumerate(self.layers):

@@ -5,6 +5,7 @@ Every function takes/returns fp32 CUDA tensors in the channels-last activation l
 device memory and the stream.  ``oracle/stages.py`` restates each function in plain torch for
 the tests; nothing here falls back to it.
 """
+import threading
 from typing import Optional, Tuple
 
 import torch
@@ -20,15 +21,32 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
+_tl = threading.local()          # device of the tensors of the call being assembled (forward and backward run on different host threads)
+
+
+def _same_device(t):
+    dev = getattr(_tl, "dev", None)
+    if dev is None:
+        _tl.dev = t.device
+    elif t.device != dev:
+        _tl.dev = None
+        raise RuntimeError(f"fusion_gcn_b200: tensors of one call live on different devices ({dev} and {t.device})")
+
+
 def _check(*tensors):
     for t in tensors:
         if t is None:
             continue
+        if t.is_cuda:
+            _same_device(t)
         if not t.is_cuda:
+            _tl.dev = None
             raise RuntimeError("fusion_gcn_b200 kernels need CUDA tensors (there is no CPU path)")
         if t.dtype != torch.float32:
+            _tl.dev = None
             raise RuntimeError(f"fp32 tensor expected, got {t.dtype}")
         if not t.is_contiguous():
+            _tl.dev = None
             raise RuntimeError("contiguous tensor expected")
 
 
@@ -37,14 +55,20 @@ def _check_strided(*tensors):
     for t in tensors:
         if t is None:
             continue
+        if t.is_cuda:
+            _same_device(t)
         if not t.is_cuda:
+            _tl.dev = None
             raise RuntimeError("fusion_gcn_b200 kernels need CUDA tensors (there is no CPU path)")
         if t.dtype != torch.float32:
+            _tl.dev = None
             raise RuntimeError(f"fp32 tensor expected, got {t.dtype}")
 
 
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    """Current stream of the device the call's tensors live on (not of the current device: the two differ when a caller
+    drives cuda:1 tensors while cuda:0 is current)."""
+    return torch.cuda.current_stream(getattr(_tl, "dev", None)).cuda_stream
 
 
 _timing = None            # (set of entry-point names, list of (key, start_event, end_event)) while bench.py is timing
@@ -77,6 +101,14 @@ def _call(name, *args, sig=None, work=(0.0, 0.0), alias=None):
     bench.py is timing (CUDA events on the launching stream around the C-ABI call)."""
     capi.launch_count += 1
     fn = getattr(capi.lib(), name)
+    dev = getattr(_tl, "dev", None)
+    if dev is not None and dev.index is not None and dev.index != torch.cuda.current_device():
+        # the C ABI launches on the CURRENT device and never changes it: make the tensors' device current for the call
+        _tl.dev = None
+        capi.launch_count -= 1
+        with torch.cuda.device(dev):
+            return _call(name, *args, sig=sig, work=work, alias=alias)
+    _tl.dev = None                 # the next call collects its own device
     if _timing is not None and (name in _timing[0] or "*" in _timing[0]):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
