@@ -332,7 +332,7 @@ def run_ours(args):
                            "achieved_tflops": round(value * gflop / 1e3, 2), "achieved_gbs": round(value / world * mbytes / 1e3, 1)},
     }
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_reference(args.workload, steps=3, warmup=1)
+        line["cpu_baseline"] = cpu_reference(args.workload, steps=5, warmup=1)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -435,33 +435,65 @@ def run_infer(args):
     print(json.dumps(line), flush=True)
 
 
+def _reference_graph(ref, gk):
+    """The reference's own util.graph.Graph for the workload (datasets/*/constants.py edge lists, fusion.py:65-89)."""
+    const = {"ntu": ref["ntu"], "utd": ref["utd"], "mmact_imu": ref["mmact"]}[gk]
+    g = ref["Graph"](const.skeleton_edges, center_joint=const.center_joint)
+    if gk == "mmact_imu":
+        g = ref["fusion"].get_skeleton_imu_fusion_graph(g, "append_center", 4)
+    return g
+
+
 def cpu_reference(workload, steps, warmup, n=None):
-    """The reference's CPU path on the host cores: oracle/agcn_oracle.py (a port that calls the same ATen ops as
-    torch_src/models/mmargcn/agcn.py; the Python reference itself cannot travel to the GPU box), all host threads,
-    bounded sample of the same workload (N=4 sequences per step at NTU/MMAct shape, N=16 at UTD shape)."""
-    from oracle import agcn_oracle as O
+    """The reference's CPU path on the host cores, all host threads, bounded sample of the same workload (N=16 sequences per
+    step).  kind "reference": the UNMODIFIED torch_src/models/mmargcn/agcn.py::Model, imported from the byte copy that
+    baseline/install_ref.py places under baseline/_ref (or /root/reference in the build container), with the reference's own
+    Graph / partition strategy, nn.CrossEntropyLoss and loss.backward() as in torch_src/session/procedures/step.py:39-46.
+    kind "port": oracle/agcn_oracle.py (same ATen ops), only when no reference copy is present."""
+    from oracle import agcn_oracle as O, ref_loader
     from fusion_gcn_b200 import graph as G
     m, t, v, c, ncls, gk = WORKLOADS[workload]
-    n = n or (16 if t * v * m <= 4000 else 4)
+    n = n or 16
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    adj = G.adjacency_from_graph(make_graph(gk))
-    p = O.as_leaves(O.init_state(adj, (m, t, v, c), ncls, seed=1))
     gen = torch.Generator().manual_seed(1234)
     x = torch.randn(n, m, t, v, c, generator=gen)
     y = torch.randint(ncls, (n,), generator=gen)
-    leaves = [a for a in p.values() if a.requires_grad]
+    kind = "port"
+    if ref_loader.available():
+        try:
+            ref = ref_loader.load()
+            torch.manual_seed(1)
+            model = ref["agcn"].Model((m, t, v, c), ncls, _reference_graph(ref, gk)).train()
+            loss_fn = torch.nn.CrossEntropyLoss()
+
+            def one_step():
+                model.zero_grad(set_to_none=True)
+                loss = loss_fn(model(x), y)
+                loss.backward()
+                return loss
+            kind = "reference"
+        except Exception as exc:            # noqa: BLE001 -- fall back to the port and say so
+            sys.stderr.write(f"bench.py: reference import failed ({type(exc).__name__}: {exc}); timing the oracle port instead\n")
+    if kind == "port":
+        adj = G.adjacency_from_graph(make_graph(gk))
+        p = O.as_leaves(O.init_state(adj, (m, t, v, c), ncls, seed=1))
+        leaves = [a for a in p.values() if a.requires_grad]
+
+        def one_step():
+            for a in leaves:
+                a.grad = None
+            loss = torch.nn.functional.cross_entropy(O.model_forward(x, p, c, True), y)
+            loss.backward()
+            return loss
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        for a in leaves:
-            a.grad = None
-        loss = torch.nn.functional.cross_entropy(O.model_forward(x, p, c, True), y)
-        loss.backward()
+        one_step()
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     total = sum(times)
-    return {"value": round(n * len(times) / total, 3), "unit": "sequences/s", "cores": torch.get_num_threads(), "kind": "port",
+    return {"value": round(n * len(times) / total, 3), "unit": "sequences/s", "cores": torch.get_num_threads(), "kind": kind,
             "sample": f"{len(times)} steps of N={n} sequences at the {workload} shape (same model, fwd+CE+bwd, fp32, train mode)",
             "ms_per_step": round(total / len(times) * 1e3, 1)}
 
@@ -471,13 +503,13 @@ def run_reference(args):
     if rank != 0:
         return
     m, t, v, c, ncls, _ = WORKLOADS[args.workload]
-    steps = max(1, min(args.steps, 5))
+    steps = max(5, min(args.steps, 8))
     base = cpu_reference(args.workload, steps=steps, warmup=max(1, min(args.warmup, 2)))
     line = {"impl": "reference", "metric": "AGCN fwd+bwd sequences/sec", "value": base["value"], "unit": "sequences/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": base["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: AGCN 10 units, M={m}, T={t}, V={v}, C={c}, {ncls} classes, train mode, fwd+CE+bwd; "
-                                   "reference CPU path (oracle port) on the host cores, bounded sample"},
+                                   f"reference CPU path ({base['kind']}) on the host cores, bounded sample: {base['sample']}"},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)

@@ -84,8 +84,18 @@ def temporal_conv(x, p: Dict[str, torch.Tensor], prefix: str, stride: int, train
     return _bn(y, p, prefix + ".bn", training)
 
 
+def _relu(pre, mask, collect, key):
+    """relu(pre).  ``collect`` (a dict) receives the pre-activation; ``mask`` (a bool tensor) REPLACES the sign test:
+    relu(z) = z * [z > 0], and a parity test may fix the bracket to the mask the implementation under test used, so that
+    gradients are compared on the same linear piece of the network (elements whose pre-activation is a rounding error
+    away from zero otherwise flip the bracket and move whole gradient tensors by O(1e-2) -- in the fp32 reference too)."""
+    if collect is not None:
+        collect[key] = pre
+    return torch.relu(pre) if mask is None else pre * mask.to(pre.dtype)
+
+
 def spatial_graph_conv(x, p, prefix: str, training: bool, adj_a: Optional[torch.Tensor] = None,
-                       b_name: str = "adj_b") -> Tuple[torch.Tensor, List[torch.Tensor]]:
+                       b_name: str = "adj_b", mask=None, collect=None) -> Tuple[torch.Tensor, List[torch.Tensor]]:
     n, c, t, v = x.shape
     a = p[prefix + ".adj_a"] if adj_a is None else adj_a
     fixed_plus_learned = a + p[prefix + "." + b_name]
@@ -110,19 +120,21 @@ def spatial_graph_conv(x, p, prefix: str, training: bool, adj_a: Optional[torch.
         d = _bn(d, p, prefix + ".down.1", training)
     else:
         d = x
-    return torch.relu(y + d), attn
+    return _relu(y + d, mask, collect, "pre_o"), attn
 
 
 def st_unit(x, p, prefix: str, stride: int, residual: str, training: bool,
-            adj_a=None, b_name="adj_b"):
-    """residual in {'none', 'identity', 'conv'}."""
-    o, attn = spatial_graph_conv(x, p, prefix + ".gcn1", training, adj_a, b_name)
+            adj_a=None, b_name="adj_b", masks=None, collect=None):
+    """residual in {'none', 'identity', 'conv'}.  ``masks`` = (mask of the gcn ReLU, mask of the output ReLU) and
+    ``collect`` as in :func:`_relu`."""
+    o, attn = spatial_graph_conv(x, p, prefix + ".gcn1", training, adj_a, b_name,
+                                 mask=None if masks is None else masks[0], collect=collect)
     u = temporal_conv(o, p, prefix + ".tcn1", stride, training)
     if residual == "identity":
         u = u + x
     elif residual == "conv":
         u = u + temporal_conv(x, p, prefix + ".residual", stride, training)
-    return torch.relu(u), attn
+    return _relu(u, None if masks is None else masks[1], collect, "pre_out"), attn
 
 
 # --------------------------------------------------------------------------- model
@@ -136,9 +148,12 @@ def layer_plan(num_channels: int, start: int = 64, num_layers: int = 10):
 
 
 def model_forward(x, p, num_channels: int, training: bool, start: int = 64, num_layers: int = 10,
-                  variant: str = "mmargcn", adj_a=None, return_attention: bool = False):
+                  variant: str = "mmargcn", adj_a=None, return_attention: bool = False, dropout_masks=None):
     """x: (N, M, T, V, C).  variant 'mmargcn' -> layers l0.., param adj_b, buffer adj_a;
-    variant 'original' -> layers l1.., param PA, adjacency passed as ``adj_a``."""
+    variant 'original' -> layers l1.., param PA, adjacency passed as ``adj_a``.
+    ``dropout_masks``: the (already 1/(1-p)-scaled) masks of the nn.Dropout modules the reference inserts after every
+    unit but the last when dropout > 0 (agcn.py:166-169), each (N*M, C, T', V); the state-dict keys then follow the
+    reference's renumbering (unit i is l{2i}, the dropouts take the odd names)."""
     n, m, t, v, c = x.shape
     h = x.permute(0, 1, 3, 4, 2).reshape(n, m * v * c, t)
     h = _bn(h, p, "data_bn", training)
@@ -146,8 +161,11 @@ def model_forward(x, p, num_channels: int, training: bool, start: int = 64, num_
     first = 0 if variant == "mmargcn" else 1
     b_name = "adj_b" if variant == "mmargcn" else "PA"
     attention = []
+    step = 1 if dropout_masks is None else 2
     for i, (_, _, stride, residual) in enumerate(layer_plan(num_channels, start, num_layers)):
-        h, attn = st_unit(h, p, f"l{i + first}", stride, residual, training, adj_a, b_name)
+        h, attn = st_unit(h, p, f"l{step * i + first}", stride, residual, training, adj_a, b_name)
+        if dropout_masks is not None and i < len(dropout_masks):
+            h = h * dropout_masks[i].to(h.dtype)
         attention.append(attn)
     feat = h.reshape(n, m, h.shape[1], -1).mean(3).mean(1)
     if "fc.weight" in p:

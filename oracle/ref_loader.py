@@ -1,6 +1,7 @@
 """TEST INFRASTRUCTURE ONLY -- loader for the *real* reference modules.
 
-Only usable where /root/reference exists (the build container).  It is used by
+Usable where /root/reference exists (the build container) or where ``baseline/_ref`` holds the byte copy made by
+``baseline/install_ref.py`` (the GPU box).  It is used by
 ``oracle/make_golden.py`` to generate the committed fixtures under
 ``tests/golden/`` and by the ``not gpu`` tests that pin ``oracle/agcn_oracle.py``
 against the reference itself.  Nothing on the GPU box may import the reference
@@ -14,7 +15,20 @@ import os
 import sys
 from unittest.mock import MagicMock
 
-REFERENCE_ROOT = os.environ.get("FUSION_GCN_REFERENCE", "/root/reference")
+_TRAVELLING_COPY = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+
+
+def _pick_root():
+    """/root/reference in the build container; on the GPU box the byte copy made by baseline/install_ref.py
+    (git-ignored, shipped with the snapshot)."""
+    env = os.environ.get("FUSION_GCN_REFERENCE")
+    for cand in ([env] if env else []) + ["/root/reference", _TRAVELLING_COPY]:
+        if os.path.isfile(os.path.join(cand, "torch_src", "models", "mmargcn", "agcn.py")):
+            return cand
+    return env or "/root/reference"
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def available() -> bool:

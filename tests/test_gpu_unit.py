@@ -107,7 +107,7 @@ def test_model_vs_cpu_oracle_seeded(pkg, shape, edges, start, n, precision, slac
     ref64 = {k: a.grad for k, a in p.items() if a.requires_grad}
     ref32 = {k: a.grad for k, a in p32.items() if a.requires_grad}
     noise = max(rel_err(ref32[k], ref64[k]) for k in ref64 if not ZERO_GRAD.search(k))
-    check_grads({k: q.grad for k, q in model.named_parameters()}, ref64, max(TOL, slack * noise), str(shape))
+    check_grads({k: q.grad for k, q in model.named_parameters()}, ref64, max(TOL, min(slack * noise, 1e-2)), str(shape))   # capped
 
 
 def test_properties_at_ntu_batch_shape(pkg):

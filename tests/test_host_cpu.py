@@ -160,3 +160,24 @@ def test_bench_reference_arm_line_schema():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and "sample" in line["cpu_baseline"]
     assert line["e2e"] == {"value": line["value"], "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"]
+
+
+@pytest.mark.parametrize("cin,cout,stride,residual,v", [(8, 8, 1, True, 25), (8, 16, 2, True, 22), (3, 8, 1, False, 20)])
+def test_unit_parity_harness_on_cpu(torch_stage_backend, cin, cout, stride, residual, v):
+    """The BASELINE-shape parity harness (tests/unit_parity.py: plain fp64 forward, ReLU brackets equal except at ties,
+    gradients on the same linear piece at 1e-4) run on CPU over the torch stage backend, so the harness itself is checked
+    without a GPU."""
+    import unit_parity as UP
+    from fusion_gcn_b200 import graph as G, modules as M
+    unit = UP.baseline_unit(M, G, cin, cout, stride, residual, v, seed=3)
+    x, w = UP.unit_inputs(3, cin, cout, 21, v, stride, seed=4)
+    err = UP.run_unit_parity(unit, x, w, "cpu")
+    assert err["y"] <= 1e-5 and err["dx"] <= 1e-5
+
+
+def test_model_level_cases_of_the_gpu_suite_on_cpu(torch_stage_backend):
+    """The original-variant and dropout model cases of tests/test_gpu_baseline_shapes.py (strict load of reference-keyed
+    states, mask capture and replay in the oracle) over the torch stage backend."""
+    import test_gpu_baseline_shapes as T
+    T.run_original_variant("cpu")
+    T.run_dropout_model("cpu")

@@ -101,20 +101,24 @@ def main():
                 report(f"wgrad_{nm}_{tag}", ms, rows * (cin + cout) * 4, 2.0 * rows * cin * cout * taps)
                 del xi, dy
         if want(f"bn_{tag}"):
+            # every operand is its own buffer: aliased operands (res = x, dout = y = mask) are served from L2 / one DRAM
+            # stream and overstate the achieved bandwidth
             gamma, beta = torch.ones(c, device=dev), torch.zeros(c, device=dev)
             rm, rv = torch.zeros(c, device=dev), torch.ones(c, device=dev)
+            res, dout, msk = (torch.randn_like(x) for _ in range(3))
             ms = timeit(lambda: K.bn_stats(x, gamma, beta, rm, rv, None, 0.1, 1e-5, True), once)
             report(f"bn_stats_{tag}", ms, act, 0)
             sc, sh, mean, invstd = K.bn_stats(x, gamma, beta, rm, rv, None, 0.1, 1e-5, True)
-            ms = timeit(lambda: K.bn_apply(x, sc, sh, res_mode=K.RES_TENSOR, res=x, relu=True), once)
+            ms = timeit(lambda: K.bn_apply(x, sc, sh, res_mode=K.RES_TENSOR, res=res, relu=True), once)
             report(f"bn_apply_res_{tag}", ms, act * 3, 0)
-            ms = timeit(lambda: K.bn_bwd(x, x, x, mean, invstd, gamma), once)
-            report(f"bn_bwd_{tag}", ms, act * 6, 0)
-            _, bits = K.bn_apply(x, sc, sh, res_mode=K.RES_TENSOR, res=x, relu=True, want_mask=True)
-            ms = timeit(lambda: K.bn_apply(x, sc, sh, res_mode=K.RES_TENSOR, res=x, relu=True, want_mask=True), once)
+            ms = timeit(lambda: K.bn_bwd(dout, msk, x, mean, invstd, gamma), once)
+            report(f"bn_bwd_{tag}", ms, act * 7, 0)              # two passes over (dout, mask, y) + dy
+            _, bits = K.bn_apply(x, sc, sh, res_mode=K.RES_TENSOR, res=res, relu=True, want_mask=True)
+            ms = timeit(lambda: K.bn_apply(x, sc, sh, res_mode=K.RES_TENSOR, res=res, relu=True, want_mask=True), once)
             report(f"bn_apply_res_mask_{tag}", ms, act * 3, 0)
-            ms = timeit(lambda: K.bn_bwd(x, None, x, mean, invstd, gamma, mask_bits=bits), once)
-            report(f"bn_bwd_bits_{tag}", ms, act * 4, 0)
+            ms = timeit(lambda: K.bn_bwd(dout, None, x, mean, invstd, gamma, mask_bits=bits), once)
+            report(f"bn_bwd_bits_{tag}", ms, act * 5, 0)         # two passes over (dout, y) + dy (+ 1/32 for the bits)
+            del res, dout, msk
         del x
         torch.cuda.empty_cache()
     if want("first_unit"):
