@@ -148,12 +148,14 @@ def layer_plan(num_channels: int, start: int = 64, num_layers: int = 10):
 
 
 def model_forward(x, p, num_channels: int, training: bool, start: int = 64, num_layers: int = 10,
-                  variant: str = "mmargcn", adj_a=None, return_attention: bool = False, dropout_masks=None):
+                  variant: str = "mmargcn", adj_a=None, return_attention: bool = False, dropout_masks=None,
+                  masks=None, collect=None):
     """x: (N, M, T, V, C).  variant 'mmargcn' -> layers l0.., param adj_b, buffer adj_a;
     variant 'original' -> layers l1.., param PA, adjacency passed as ``adj_a``.
     ``dropout_masks``: the (already 1/(1-p)-scaled) masks of the nn.Dropout modules the reference inserts after every
     unit but the last when dropout > 0 (agcn.py:166-169), each (N*M, C, T', V); the state-dict keys then follow the
-    reference's renumbering (unit i is l{2i}, the dropouts take the odd names)."""
+    reference's renumbering (unit i is l{2i}, the dropouts take the odd names).
+    ``masks`` / ``collect``: per-unit ReLU brackets / pre-activations as in :func:`st_unit` (lists with one entry per unit)."""
     n, m, t, v, c = x.shape
     h = x.permute(0, 1, 3, 4, 2).reshape(n, m * v * c, t)
     h = _bn(h, p, "data_bn", training)
@@ -163,7 +165,12 @@ def model_forward(x, p, num_channels: int, training: bool, start: int = 64, num_
     attention = []
     step = 1 if dropout_masks is None else 2
     for i, (_, _, stride, residual) in enumerate(layer_plan(num_channels, start, num_layers)):
-        h, attn = st_unit(h, p, f"l{step * i + first}", stride, residual, training, adj_a, b_name)
+        pre = None
+        if collect is not None:
+            pre = {}
+            collect.append(pre)
+        h, attn = st_unit(h, p, f"l{step * i + first}", stride, residual, training, adj_a, b_name,
+                          masks=None if masks is None else masks[i], collect=pre)
         if dropout_masks is not None and i < len(dropout_masks):
             h = h * dropout_masks[i].to(h.dtype)
         attention.append(attn)

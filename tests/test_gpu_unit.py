@@ -11,6 +11,8 @@ from oracle import agcn_oracle as O
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
+from fusion_gcn_b200.modules import _PRECISIONS  # noqa: E402
+PARITY_MODES = [m for m in ("fp32", "bf16x3") if m in _PRECISIONS]      # every mode that claims the 1e-4 contract
 
 
 @pytest.fixture(scope="module")
@@ -65,15 +67,8 @@ def test_model_vs_reference_golden(pkg, name):
         assert rel_err(model(x), g["f64.y_eval"]) <= TOL
 
 
-@pytest.mark.parametrize("precision,slack", [("fp32_ffma", 8.0), ("fp32", 32.0)])
-@pytest.mark.parametrize("shape,edges,start,n", [
-    ((1, 100, 20, 3), "utd", 64, 4),          # config C1 shape (UTD-MHAD skeleton)
-    ((2, 60, 25, 3), "ntu", 64, 2),           # NTU graph, two bodies, full channel widths
-    ((2, 33, 22, 3), "mmact_imu", 32, 2),     # config C3 graph: COCO-18 + 4 IMU joints, odd T through two stride-2 layers
-    ((1, 20, 20, 9), "utd", 16, 3),           # channel fusion C = 9
-])
-def test_model_vs_cpu_oracle_seeded(pkg, shape, edges, start, n, precision, slack):
-    from fusion_gcn_b200 import graph as G, modules as M
+def seeded_model_case(M, G, shape, edges, start, n, precision, device):
+    import unit_parity as UP
     if edges == "utd":
         graph = G.SkeletonGraph(G.UTD_EDGES, center_joint=G.UTD_CENTER)
     elif edges == "ntu":
@@ -86,28 +81,28 @@ def test_model_vs_cpu_oracle_seeded(pkg, shape, edges, start, n, precision, slac
     gen = torch.Generator().manual_seed(5)
     x = torch.randn(n, m, t, v, c, generator=gen)
     w = torch.randn(n, 27, generator=gen)
-    p = O.as_leaves(state, torch.float64)
-    y_ref = O.model_forward(x.double(), p, c, True, start=start)
-    (y_ref * w.double()).sum().backward()
-    p32 = O.as_leaves(state, torch.float32)              # the reference arithmetic in fp32: its own noise floor
-    (O.model_forward(x, p32, c, True, start=start) * w).sum().backward()
     model = M.Model(shape, 27, graph, start_feature_size=start)
     model.load_state_dict(state, strict=True)
     M.set_precision(model, precision)
-    model.cuda().train()
-    y = model(x.cuda())
-    (y * w.cuda()).sum().backward()
-    assert rel_err(y, y_ref) <= TOL
-    # These full-width, tiny-batch seeded models are ill-conditioned: the reference arithmetic evaluated in fp32 is itself
-    # 1e-3..3e-2 away from fp64 on some gradients (probed for many seeds, loud and default init), and the amplification is
-    # chaotic per tensor.  The 1e-4 contract is therefore checked on the well-conditioned golden fixtures above; here the
-    # bound is max(1e-4, slack x the fp32 reference's WORST per-tensor error against fp64) -- a conditioning-aware sanity
-    # check that still catches any formula / indexing bug (those give O(1) errors).  slack 8 for the IEEE-fp32 FFMA kernels,
-    # 32 for the default fp32 parity mode (3xTF32 tensor cores carry ~5x the per-op rounding error of FFMA).
-    ref64 = {k: a.grad for k, a in p.items() if a.requires_grad}
-    ref32 = {k: a.grad for k, a in p32.items() if a.requires_grad}
-    noise = max(rel_err(ref32[k], ref64[k]) for k in ref64 if not ZERO_GRAD.search(k))
-    check_grads({k: q.grad for k, q in model.named_parameters()}, ref64, max(TOL, min(slack * noise, 1e-2)), str(shape))   # capped
+    return UP.run_model_parity(model, state, x, w, device, c, start)
+
+
+@pytest.mark.parametrize("precision", ["fp32_ffma"] + PARITY_MODES)
+@pytest.mark.parametrize("shape,edges,start,n", [
+    ((1, 100, 20, 3), "utd", 64, 4),          # config C1 shape (UTD-MHAD skeleton)
+    ((2, 60, 25, 3), "ntu", 64, 2),           # NTU graph, two bodies, full channel widths
+    ((2, 33, 22, 3), "mmact_imu", 32, 2),     # config C3 graph: COCO-18 + 4 IMU joints, odd T through two stride-2 layers
+    ((1, 20, 20, 9), "utd", 16, 3),           # channel fusion C = 9
+])
+def test_model_vs_cpu_oracle_seeded(pkg, shape, edges, start, n, precision):
+    """Full-width seeded models at the north-star tolerance, 1e-4 on logits and EVERY gradient, no noise-scaled slack.
+    Round 1 bounded these by a multiple of the fp32 reference's own error (up to 1e-2..1, i.e. nothing): that error is the
+    ReLU-tie phenomenon, not conditioning -- a pre-activation within rounding of zero flips its bracket in ANY fp32
+    implementation and moves whole gradient tensors by O(1e-2).  tests/unit_parity.py::run_model_parity pins it down:
+    brackets must equal the fp64 ones except within 1e-5 of zero, and gradients are compared on the same linear piece."""
+    from fusion_gcn_b200 import graph as G, modules as M
+    err = seeded_model_case(M, G, shape, edges, start, n, precision, "cuda")
+    print(f"[{precision}] {shape}: logits {err['y']:.2e}, worst grad {err['worst_grad']}, ReLU ties {err['relu_ties']}")
 
 
 def test_properties_at_ntu_batch_shape(pkg):

@@ -181,3 +181,11 @@ def test_model_level_cases_of_the_gpu_suite_on_cpu(torch_stage_backend):
     import test_gpu_baseline_shapes as T
     T.run_original_variant("cpu")
     T.run_dropout_model("cpu")
+
+
+def test_model_parity_harness_on_cpu(torch_stage_backend):
+    """tests/unit_parity.py::run_model_parity (the model-level 1e-4 contract of the GPU suite) over the torch stage backend."""
+    import test_gpu_unit as T
+    from fusion_gcn_b200 import graph as G, modules as M
+    err = T.seeded_model_case(M, G, (1, 20, 20, 9), "utd", 16, 3, "fp32", "cpu")
+    assert err["y"] <= 1e-5

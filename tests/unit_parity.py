@@ -129,3 +129,73 @@ def unit_inputs(nb, cin, cout, t, v, stride, seed):
     x = torch.randn(nb, cin, t, v, generator=g)
     w = torch.randn(nb, cout, (t - 1) // stride + 1, v, generator=g)
     return x, w
+
+
+def run_model_parity(model, state, x, w, device, num_channels, start, tol=TOL, tie=TIE, variant="mmargcn", adj_a=None):
+    """Whole Model (ours) against the fp64 oracle with the same three-step contract as run_unit_parity: logits against the plain
+    oracle, every unit's two ReLU brackets equal to the fp64 ones except at ties, all parameter gradients against the oracle
+    evaluated on our brackets -- 1e-4, no noise-scaled slack.  ``model`` must be freshly loaded from ``state``."""
+    from torch import nn
+    units = [m for m in model.layers if not isinstance(m, nn.Dropout)]
+    seen = []
+
+    def wrap(unit):
+        inner = unit.forward_cl
+
+        def recording(h):
+            out = inner(h)
+            seen.append((unit, h.detach(), out.detach()))
+            return out
+        unit.forward_cl = recording
+    for u in units:
+        wrap(u)
+    model.to(device).train()
+    xd, wd = x.to(device), w.to(device)
+    y = model(xd)
+    (y * wd).sum().backward()
+    after = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    masks = []
+    with torch.no_grad():
+        for unit, h_in, out in seen:
+            o = unit.gcn1.forward_cl(h_in)                               # (N', T, V, C) -> reference layout (N', C, T, V)
+            masks.append(((o > 0).permute(0, 3, 1, 2), (out > 0).permute(0, 3, 1, 2)))
+    a64 = None if adj_a is None else torch.as_tensor(adj_a, dtype=torch.float64, device=device)
+
+    def leaves():
+        return O.as_leaves({k: v.to(device) for k, v in state.items()}, torch.float64)
+    p_true, pre = leaves(), []
+    with torch.no_grad():
+        y64 = O.model_forward(xd.double(), p_true, num_channels, True, start=start, variant=variant, adj_a=a64, collect=pre)
+    err = {"y": rel_err(y, y64)}
+    assert err["y"] <= tol, f"logit error {err['y']:.3e}"
+    flips = 0
+    for i, ((mo, mout), pr) in enumerate(zip(masks, pre)):
+        for ours, key in ((mo, "pre_o"), (mout, "pre_out")):
+            z = pr[key]
+            diff = ours != (z > 0)
+            flips += int(diff.sum())
+            if diff.any():
+                worst = float(z[diff].abs().max() / z.abs().max())
+                assert worst <= tie, f"unit {i} {key}: ReLU bracket differs where the fp64 pre-activation is {worst:.2e} (relative) from zero"
+    err["relu_ties"] = flips
+    p64 = leaves()
+    y64m = O.model_forward(xd.double(), p64, num_channels, True, start=start, variant=variant, adj_a=a64, masks=masks)
+    (y64m * wd.double()).sum().backward()
+    ref = {k: v.grad for k, v in p64.items() if v.requires_grad}
+    scale = max(float(v.abs().max()) for v in ref.values())
+    worst = ("", 0.0)
+    for name, prm in model.named_parameters():
+        r = ref[name]
+        if ZERO_GRAD.search(name):
+            e = float(prm.grad.abs().max()) / scale
+        else:
+            e = float((prm.grad.double() - r).abs().max()) / max(float(r.abs().max()), 1e-7 * scale)
+        assert e <= tol, f"gradient {name} error {e:.3e}"
+        if e > worst[1]:
+            worst = (name, e)
+    err["worst_grad"] = worst
+    for k, v in p_true.items():
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            e = float((after[k].double() - v).abs().max()) / max(float(v.abs().max()), 1e-3)
+            assert e <= tol, f"{k} error {e:.3e}"
+    return err

@@ -1,0 +1,16 @@
+#!/bin/bash
+# One GPU-box job: tools/gpu_job.sh <tag> [steps...]   steps: pytest | pytestnew | peaks | bench | stage | stagetf32
+tag=$1; shift
+mkdir -p gpurun_out
+for step in "$@"; do
+  case $step in
+    pytest)    python -m pytest tests -m gpu -q -rf -p no:cacheprovider > gpurun_out/${tag}_pytest.log 2>&1; tail -5 gpurun_out/${tag}_pytest.log ;;
+    pytestnew) python -m pytest tests/test_gpu_baseline_shapes.py -m gpu -q -rf -s -p no:cacheprovider > gpurun_out/${tag}_pytest_new.log 2>&1; tail -5 gpurun_out/${tag}_pytest_new.log ;;
+    peaks)     python tools/measure_peaks.py > gpurun_out/${tag}_peaks.json 2> gpurun_out/${tag}_peaks.err; cat gpurun_out/${tag}_peaks.json ;;
+    bench)     python bench.py --steps 10 --warmup 3 --dump-kernels gpurun_out/${tag}_kernels.json > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; tail -c 600 gpurun_out/${tag}_bench.json; tail -3 gpurun_out/${tag}_bench.err ;;
+    stage)     python tools/bench_stage.py > gpurun_out/${tag}_stage_fp32.log 2>&1; tail -3 gpurun_out/${tag}_stage_fp32.log ;;
+    stagetf32) python tools/bench_stage.py --tf32 > gpurun_out/${tag}_stage_tf32.log 2>&1 ;;
+    smoke)     python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.log 2>&1; tail -2 gpurun_out/${tag}_smoke.log ;;
+    *) echo "unknown step $step" ;;
+  esac
+done
