@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libagcn_b200.so")
 PREC_FP32 = 0          # fp32 parity: 3xTF32 tensor cores where possible, FFMA otherwise
 PREC_TF32 = 1          # single-pass TF32 tensor cores
 PREC_FP32_FFMA = 2     # force FFMA
+PREC_BF16X3 = 3        # fp32 parity on bf16 triple products (h.h + h.m + m.h, tcgen05 kind::f16)
 MIX_AGG_FWD, MIX_AGG_BWD, MIX_SCORE_BWD = 0, 1, 2
 RES_NONE, RES_TENSOR, RES_AFFINE = 0, 1, 2
 

@@ -545,11 +545,13 @@ size_t agcn_conv_wgrad_tc_workspace_floats(int nb, int t_in, int t_out, int v, i
 int agcn_conv_wgrad_tc(const float* dy, const float* x, float* ws, int* splits_out,
                        int nb, int t_in, int t_out, int v, int cin, int cout, int taps, int stride, int pad, int split, void* stream);
 
-static bool known_precision(int p) { return p == AGCN_PREC_FP32 || p == AGCN_PREC_TF32 || p == AGCN_PREC_FP32_FFMA; }
+static bool known_precision(int p) { return p >= AGCN_PREC_FP32 && p <= AGCN_PREC_BF16X3; }
 
 extern "C" AGCN_API size_t agcn_conv_fwd_workspace_bytes(int cin, int cout, int taps, int precision) {
-    if (precision != AGCN_PREC_FP32 || cin <= 0 || cout <= 0 || taps <= 0) return 0;
-    return (size_t)2 * cout * taps * cin * sizeof(float);   // TF32 hi | lo split of the weights for the 3xTF32 path
+    if ((precision != AGCN_PREC_FP32 && precision != AGCN_PREC_BF16X3) || cin <= 0 || cout <= 0 || taps <= 0) return 0;
+    // TF32 hi | lo split of the weights for the 3xTF32 path; the BF16x3 path needs half of it (bf16 h | m) and falls back to 3xTF32
+    // for channel counts that are not a multiple of 16
+    return (size_t)2 * cout * taps * cin * sizeof(float);
 }
 
 static int conv_fwd_impl(const float* x, const float* w, const float* bias, float* y,
@@ -562,8 +564,9 @@ static int conv_fwd_impl(const float* x, const float* w, const float* bias, floa
                  AGCN_ERR_BAD_SHAPE, "agcn_conv_fwd: bad shape nb=%d t_in=%d t_out=%d v=%d cin=%d cout=%d taps=%d stride=%d pad=%d",
                  nb, t_in, t_out, v, cin, cout, taps, stride, pad);
     AGCN_REQUIRE(known_precision(precision), AGCN_ERR_UNSUPPORTED, "agcn_conv_fwd: unknown precision %d", precision);
-    if (precision == AGCN_PREC_TF32 || precision == AGCN_PREC_FP32) {
-        const int split = precision == AGCN_PREC_FP32;
+    if (precision == AGCN_PREC_TF32 || precision == AGCN_PREC_FP32 || precision == AGCN_PREC_BF16X3) {
+        const int first_split = precision == AGCN_PREC_FP32 ? 1 : (precision == AGCN_PREC_BF16X3 ? 2 : 0);
+        for (int split = first_split; split >= (first_split == 2 ? 1 : first_split); --split) {      // BF16x3 falls back to 3xTF32
         const bool ws_ok = !split || (workspace != nullptr && workspace_bytes >= agcn_conv_fwd_workspace_bytes(cin, cout, taps, precision));
         if (ws_ok) {
             if (stat_part != nullptr) {       // try the epilogue with fused column sums first; shapes it does not take run without
@@ -574,6 +577,7 @@ static int conv_fwd_impl(const float* x, const float* w, const float* bias, floa
             int rc2 = agcn_conv_fwd_tc2(x, w, bias, y, nb, t_in, t_out, v, cin, cout, taps, stride, pad, transposed, accumulate, split,
                                         static_cast<float*>(workspace), stream, nullptr, nullptr);
             if (rc2 != AGCN_ERR_UNSUPPORTED) return rc2;   // unsupported shapes fall through to the FFMA kernel
+        }
         }
     }
     if (taps == 1 && stride == 1 && pad == 0 && t_in == t_out && cout < 16 && cin % 4 == 0 && cin <= 1024 && aligned16(x) && aligned16(w)) {
@@ -654,7 +658,7 @@ extern "C" AGCN_API int agcn_conv_wgrad(const float* dy, const float* x, float* 
     AGCN_REQUIRE(workspace_bytes >= need, AGCN_ERR_WORKSPACE, "agcn_conv_wgrad: workspace %zu < %zu", workspace_bytes, need);
     AGCN_REQUIRE(aligned16(workspace), AGCN_ERR_MISALIGNED, "agcn_conv_wgrad: workspace not 16-byte aligned");
     AGCN_REQUIRE(known_precision(precision), AGCN_ERR_UNSUPPORTED, "agcn_conv_wgrad: unknown precision %d", precision);
-    const int tc_split = precision == AGCN_PREC_FP32;
+    const int tc_split = precision == AGCN_PREC_FP32 || precision == AGCN_PREC_BF16X3;
     const size_t tc_floats = precision == AGCN_PREC_FP32_FFMA ? 0 :
         agcn_conv_wgrad_tc_workspace_floats(nb, t_in, t_out, v, cin, cout, taps, stride, pad, tc_split);
     if (tc_floats > 0 && (tc_floats + (size_t)kBiasPartials * cout) * sizeof(float) <= workspace_bytes) {

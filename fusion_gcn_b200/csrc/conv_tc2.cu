@@ -30,6 +30,12 @@
 // The achieved HBM bandwidth of these kernels is (payload bytes in flight per SM) / (~3 us loaded latency) (measured,
 // profiles/r1k): the A ring therefore holds only TMA payload and is as deep as shared memory allows; the lo residuals live
 // in their own two-slot ring between the split warps and the MMA issuer.
+// MODE 2 (AGCN_PREC_BF16X3, the second fp32-parity mode): x = h + m + O(2^-17 x) with h = bf16(x), m = bf16(x - h); the product is
+// h_a h_b + h_a m_b + m_a h_b on tcgen05 kind::f16 (BF16 operands, fp32 accumulate): three MMAs at TWICE the TF32 rate on operands of
+// HALF the bytes, i.e. half the tensor time and half the shared-memory operand traffic of 3xTF32, at ~1e-5 instead of ~2e-7 unit-level
+// error (both inside the 1e-4 contract).  A K chunk is then 64 channels = two 32-channel fp32 TMA boxes per box slot; the converter
+// warps (one thread per activation row) rewrite them IN PLACE as one 128-byte bf16 row of h (over the first box) and of m (over the
+// second), same 128B swizzle, so no extra ring exists.  Weights: bf16 h | m tensors precomputed into the caller's workspace.
 // TMEM: 2 accumulator buffers of 128 (or 256) fp32 columns (epilogue of tile i overlaps the main loop of tile i+1; 3xTF32 segments
 // ping-pong) + 128 columns of fp32 master sums for the 3xTF32 segment promotion (tmem_promote16).
 #include "tc_common.cuh"
@@ -79,15 +85,66 @@ struct Tc2Args {
     int tma_store;                // 1: epilogue stages 32-column chunks in shared memory and writes them with TMA (bulk tensor stores / reduce-adds)
 };
 
-template <bool SPLIT>
-__global__ void __launch_bounds__(SPLIT ? kThreads2Split : kThreads2, 1)
+// round-to-nearest (ties away) bf16 pieces of eight fp32 values: h = bf16(x), m = bf16(x - h), packed in channel order
+__device__ __forceinline__ void bf16_split8(const float4& a, const float4& b, uint4& h, uint4& m) {
+    const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t hb[8], mb[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        hb[i] = (__float_as_uint(x[i]) + 0x8000u) & 0xFFFF0000u;
+        mb[i] = __float_as_uint(x[i] - __uint_as_float(hb[i])) + 0x8000u;          // exact difference; only the upper half is kept below
+    }
+    h = make_uint4(__byte_perm(hb[0], hb[1], 0x7632), __byte_perm(hb[2], hb[3], 0x7632), __byte_perm(hb[4], hb[5], 0x7632), __byte_perm(hb[6], hb[7], 0x7632));
+    m = make_uint4(__byte_perm(mb[0], mb[1], 0x7632), __byte_perm(mb[2], mb[3], 0x7632), __byte_perm(mb[4], mb[5], 0x7632), __byte_perm(mb[6], mb[7], 0x7632));
+}
+__device__ __forceinline__ void sts128u(uint32_t addr, const uint4& v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// One activation row of a 64-channel K chunk, in place: p0 / p1 = the row in the first / second 32-channel fp32 box (128 bytes each,
+// 16-byte chunk j stored at j ^ sw), rewritten as 64 bf16 of h at p0 and 64 bf16 of m at p1 (chunk q = channels 8q..8q+7 at q ^ sw).
+// Every fp32 chunk is read before the bf16 chunk that overwrites its bytes is stored.
+__device__ __forceinline__ void bf16_split_row(uint32_t p0, uint32_t p1, uint32_t sw, bool has1) {
+    float4 f[8];
+    uint4 hq[4], mq[4], h2[4], m2[4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = lds128(p0 + (((uint32_t)j ^ sw) << 4));
+#pragma unroll
+    for (int q = 0; q < 4; ++q) bf16_split8(f[2 * q], f[2 * q + 1], hq[q], mq[q]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = has1 ? lds128(p1 + (((uint32_t)j ^ sw) << 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) bf16_split8(f[2 * q], f[2 * q + 1], h2[q], m2[q]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        sts128u(p0 + (((uint32_t)q ^ sw) << 4), hq[q]);
+        sts128u(p0 + (((uint32_t)(q + 4) ^ sw) << 4), h2[q]);
+        sts128u(p1 + (((uint32_t)q ^ sw) << 4), mq[q]);
+        sts128u(p1 + (((uint32_t)(q + 4) ^ sw) << 4), m2[q]);
+    }
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// MODE: 0 single-pass TF32, 1 3xTF32 (fp32 parity), 2 BF16x3 (fp32 parity, bf16 triple products)
+template <int MODE>
+__global__ void __launch_bounds__(MODE != 0 ? kThreads2Split : kThreads2, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_y0,
                 const __grid_constant__ CUtensorMap map_y1, Tc2Args a) {
+    constexpr bool SPLIT = MODE == 1;      // 3xTF32: hi in place, lo into its own ring
+    constexpr bool BF = MODE == 2;         // BF16x3: h | m in place over the two fp32 boxes of a 64-channel chunk
+    constexpr bool CONV = MODE != 0;       // converter warps, [hi ; lo] weight slots, segment promotion
+    constexpr int kChunkCh = BF ? 64 : kKChunk;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_slot = a.a_stage_bytes;
-    const uint32_t b_slot = a.b_stage_bytes * (SPLIT ? 2u : 1u);
+    const uint32_t b_slot = a.b_stage_bytes * (CONV ? 2u : 1u);
     const uint32_t lo_ring = smem_base + (uint32_t)a.na * a_slot;                       // SPLIT: two slots of a_stage_bytes
     const uint32_t b_ring = lo_ring + (SPLIT ? (uint32_t)a.nlo * a_slot : 0u);
     const uint32_t bar_base = b_ring + (uint32_t)a.nbst * b_slot;
@@ -130,7 +187,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     float* stat_sm = reinterpret_cast<float*>(smem_raw + (epi_end - smem_u32(smem_raw))) + ((threadIdx.x >> 5) & 3) * (2 * kStatCols);
 
     const uint32_t a_tx = (uint32_t)a.nblk * a.blk_rows_bytes;
-    const uint32_t b_tx = (uint32_t)a.bn * 128u * (SPLIT ? 2u : 1u);
+    const uint32_t b_tx = (uint32_t)a.bn * 128u * (CONV ? 2u : 1u);
 
     if (warp == 0) {
         // ===================================================== activation producer (warp-uniform loop, elected lane issues: the TMA
@@ -148,9 +205,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     mbar_wait(a_empty(sa), pa ^ 1u);
                     const uint32_t dst = smem_base + (uint32_t)sa * a_slot;
                     if (leader) {
-                        mbar_expect_tx(a_full(sa), a_tx);
-                        for (int b = 0; b < a.nblk; ++b)
-                            tma_load_4d(dst + (uint32_t)b * a.blk_bytes, &map_a, a_full(sa), kc * kKChunk, 0, tb + a.blk_t0[par][b], n);
+                        if (BF) {
+                            // 64-channel chunk = two 32-channel fp32 boxes per slot (the second only when it holds real channels)
+                            const int nh = (a.cin - kc * 64 > 32) ? 2 : 1;
+                            mbar_expect_tx(a_full(sa), a_tx * (uint32_t)nh);
+                            for (int b = 0; b < a.nblk; ++b)
+                                for (int h = 0; h < nh; ++h)
+                                    tma_load_4d(dst + (uint32_t)(b * 2 + h) * a.blk_bytes, &map_a, a_full(sa), kc * 64 + h * 32, 0, tb + a.blk_t0[par][b], n);
+                        } else {
+                            mbar_expect_tx(a_full(sa), a_tx);
+                            for (int b = 0; b < a.nblk; ++b)
+                                tma_load_4d(dst + (uint32_t)b * a.blk_bytes, &map_a, a_full(sa), kc * kKChunk, 0, tb + a.blk_t0[par][b], n);
+                        }
                     }
                     __syncwarp();
                     if (++sa == a.na) { sa = 0; pa ^= 1u; }
@@ -171,8 +237,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         mbar_wait(b_empty(sb), pb ^ 1u);
                         if (leader) {
                             mbar_expect_tx(b_full(sb), b_tx);
-                            tma_load_3d(b_ring + (uint32_t)sb * b_slot, &map_b, b_full(sb), kc * kKChunk, a.tap_id[par][i], nt * a.bn);
-                            if (SPLIT) tma_load_3d(b_ring + (uint32_t)sb * b_slot + a.b_stage_bytes, &map_blo, b_full(sb), kc * kKChunk, a.tap_id[par][i], nt * a.bn);
+                            tma_load_3d(b_ring + (uint32_t)sb * b_slot, &map_b, b_full(sb), kc * kChunkCh, a.tap_id[par][i], nt * a.bn);
+                            if (CONV) tma_load_3d(b_ring + (uint32_t)sb * b_slot + a.b_stage_bytes, &map_blo, b_full(sb), kc * kChunkCh, a.tap_id[par][i], nt * a.bn);
                         }
                         __syncwarp();
                         if (++sb == a.nbst) { sb = 0; pb ^= 1u; }
@@ -189,8 +255,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         {
             const bool leader = elect_one_sync() != 0;
             const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.bn >> 3) << 17) | ((128u >> 4) << 24);
-            const uint32_t idesc_wide = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * a.bn) >> 3) << 17) | ((128u >> 4) << 24);
+            constexpr uint32_t kFmt = BF ? 1u : 2u;          // operand format: 1 = BF16 (kind::f16), 2 = TF32
+            const uint32_t idesc = (1u << 4) | (kFmt << 7) | (kFmt << 10) | ((uint32_t)(a.bn >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc_wide = (1u << 4) | (kFmt << 7) | (kFmt << 10) | ((uint32_t)((2 * a.bn) >> 3) << 17) | ((128u >> 4) << 24);
             int sa = 0; uint32_t pa = 0;
             int sb = 0; uint32_t pb = 0;
             int acc = 0; uint32_t acc_phase = 0;
@@ -210,19 +277,38 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 uint32_t first = 1;
                 for (int kc = 0; kc < a.kchunks; ++kc) {
                     mbar_wait(a_full(sa), pa);
-                    if (SPLIT && !(a.dbg & 8)) mbar_wait(a_lo(sa), pa);
+                    if (CONV && !(a.dbg & 8)) mbar_wait(a_lo(sa), pa);
+                    const int ksteps = BF ? ((a.cin - kc * 64 >= 64) ? 4 : (a.cin - kc * 64) / 16) : 4;      // BF16x3: UMMA K = 16 channels
                     const uint32_t abase = smem_base + (uint32_t)sa * a_slot;
                     const uint32_t lobase = lo_ring + (uint32_t)sl * a_slot;
                     for (int i = 0; i < ntap; ++i) {
                         if (wait_b) mbar_wait(b_full(sb), pb);                     // resident weights arrive once
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t aoff = (uint32_t)a.tap_blk[par][i] * a.blk_bytes + (uint32_t)a.tap_off[par][i] * row_bytes_v;
+                        const uint32_t aoff = (uint32_t)a.tap_blk[par][i] * a.blk_bytes * (BF ? 2u : 1u) + (uint32_t)a.tap_off[par][i] * row_bytes_v;
                         const uint32_t aaddr = abase + aoff;
                         const uint32_t baddr = b_ring + (uint32_t)sb * b_slot;
                         const uint64_t da = make_smem_desc(aaddr), db = make_smem_desc(baddr);
-                        const uint64_t dalo = make_smem_desc(lobase + aoff), dblo = make_smem_desc(baddr + a.b_stage_bytes);
+                        // second operand piece: 3xTF32 lo residuals (own ring) / BF16x3 m piece (the box after the h piece)
+                        const uint64_t dalo = make_smem_desc(BF ? aaddr + a.blk_bytes : lobase + aoff), dblo = make_smem_desc(baddr + a.b_stage_bytes);
                         if (leader) {
-                        if (SPLIT && a.dual) {
+                        if (BF) {
+                            // h.Wh (+ h.Wm) + m.Wh on kind::f16; dual: one 2*bn-wide MMA against [W_h ; W_m] yields main | cross columns
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                if (k < ksteps) {
+                                    const uint64_t ko = (uint64_t)(k * 2);           // 16 bf16 = 32 bytes per K step
+                                    const uint32_t fresh = (k == 0) ? first : 0u;
+                                    if (a.dual) {
+                                        umma_bf16(d_tmem, da + ko, db + ko, idesc_wide, fresh ^ 1u);
+                                        umma_bf16(d_tmem + cross_off, dalo + ko, db + ko, idesc, 1u);
+                                    } else {
+                                        umma_bf16(d_tmem, dalo + ko, db + ko, idesc, fresh ^ 1u);
+                                        umma_bf16(d_tmem, da + ko, dblo + ko, idesc, 1u);
+                                        umma_bf16(d_tmem, da + ko, db + ko, idesc, 1u);
+                                    }
+                                }
+                            }
+                        } else if (SPLIT && a.dual) {
                             // narrow tiles: ONE MMA of width 2*bn against [W_hi ; W_lo] (adjacent in the weight slot) yields x_hi.W_hi in
                             // the main columns and x_hi.W_lo in the cross columns; a second one adds x_lo.W_hi to the cross columns.
                             // Two instructions and two reads of the activation tile per K step instead of three.
@@ -257,7 +343,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         first = 0;
                         if (++sb == a.nbst) { sb = 0; pb ^= 1u; }
                         ++it;
-                        if (SPLIT && (it % a.seg_iters) == 0 && it < iters) {
+                        if (CONV && (it % a.seg_iters) == 0 && it < iters) {
                             // promote the partial accumulator to the epilogue's fp32 registers, continue in the other buffer
                             if (leader) umma_commit(tfull_bar(acc));
                             __syncwarp();
@@ -302,7 +388,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             // element offset of this lane's output row (first column of the tile), -1 for rows outside the tensor
             const long long my_off = row_ok ? (((long long)n * a.t_out + to) * a.v + vv) * a.cout + (long long)nt * a.bn : -1;
             const int iters = a.ntap[par] * a.kchunks;
-            const int nseg = SPLIT ? (iters + a.seg_iters - 1) / a.seg_iters : 1;
+            const int nseg = CONV ? (iters + a.seg_iters - 1) / a.seg_iters : 1;
             const uint32_t lane_base = (uint32_t)(q * 32) << 16;
             const uint32_t master = tmem_base + 256u + lane_base;          // 3xTF32: fp32 master sums (columns 256..383)
             for (int sg = 0; sg < nseg; ++sg) {
@@ -322,10 +408,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     if (c0 < a.bn) {
                         const bool wide = c0 + 16 < a.bn;                  // bn is a multiple of 16: the last chunk may be 16 wide
                         float vals[32];
-                        if (SPLIT && a.dual) {
+                        if (CONV && a.dual) {
                             tmem_promote16_dual(taddr + (uint32_t)c0, taddr + (uint32_t)(a.bn + c0), master + (uint32_t)c0, sg == 0, !last, vals);
                             if (wide) tmem_promote16_dual(taddr + (uint32_t)c0 + 16u, taddr + (uint32_t)(a.bn + c0) + 16u, master + (uint32_t)c0 + 16u, sg == 0, !last, vals + 16);
-                        } else if (SPLIT) {
+                        } else if (CONV) {
                             tmem_promote16(taddr + (uint32_t)c0, master + (uint32_t)c0, sg == 0, !last, vals);
                             if (wide) tmem_promote16(taddr + (uint32_t)c0 + 16u, master + (uint32_t)c0 + 16u, sg == 0, !last, vals + 16);
                         } else {
@@ -456,7 +542,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         }
                     }
                 }
-                if (SPLIT && !last) tmem_st_wait();
+                if (CONV && !last) tmem_st_wait();
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -468,6 +554,28 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             __syncwarp();
             float* dst = a.stat_part + ((long long)blockIdx.x * 4 + q) * 2 * a.cout;
             for (int i = lane; i < a.cout; i += 32) { dst[i] = stat_sm[i]; dst[a.cout + i] = stat_sm[kStatCols + i]; }
+        }
+    } else if (BF) {
+        // ===================================================== BF16x3 converter: one thread per activation row, in place
+        const int tids = threadIdx.x - 7 * 32;
+        const int rows = (int)(a.blk_rows_bytes >> 7);
+        int sa = 0; uint32_t pa = 0;
+        for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+            for (int kc = 0; kc < a.kchunks; ++kc) {
+                mbar_wait(a_full(sa), pa);
+                const uint32_t src = smem_base + (uint32_t)sa * a_slot;
+                const bool has1 = a.cin - kc * 64 > 32;
+                for (int idx = tids; idx < a.nblk * rows; idx += kSplitWarps * 32) {
+                    const int b = idx >= rows ? 1 : 0;
+                    const int r = idx - b * rows;
+                    const uint32_t p0 = src + (uint32_t)(b * 2) * a.blk_bytes + (uint32_t)r * 128u;
+                    bf16_split_row(p0, p0 + a.blk_bytes, (uint32_t)(r & 7), has1);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_lo(sa));
+                if (++sa == a.na) { sa = 0; pa ^= 1u; }
+            }
         }
     } else if (SPLIT) {
         // ===================================================== operand split of the activation stage (kSplitWarps warps)
@@ -503,8 +611,19 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
 using namespace agcn;
 
-// Returns AGCN_ERR_UNSUPPORTED for shapes outside this path (the caller then tries the older kernels).
-// split != 0: 3xTF32 (fp32 parity mode).
+// bf16 h | m pieces of the weights for the BF16x3 mode: w_split[0 .. n) = bf16(w), w_split[n .. 2n) = bf16(w - h) (16-bit elements)
+static __global__ void split_weights_bf16_kernel(const float* w, uint16_t* w_split, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float v = w[i];
+        const uint32_t hb = (__float_as_uint(v) + 0x8000u) & 0xFFFF0000u;
+        w_split[i] = (uint16_t)(hb >> 16);
+        w_split[n + i] = (uint16_t)((__float_as_uint(v - __uint_as_float(hb)) + 0x8000u) >> 16);
+    }
+}
+
+// Returns AGCN_ERR_UNSUPPORTED for shapes outside this path (the caller then tries the next kernel).
+// split: 0 single-pass TF32, 1 3xTF32 (fp32 parity mode), 2 BF16x3 (fp32 parity mode on bf16 triple products).
 // stat_part != NULL (forward gather, no accumulate, cout <= 256): the epilogue also leaves [*stat_nparts][2][cout] column sums.
 int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* y,
                       int nb, int t_in, int t_out, int v, int cin, int cout,
@@ -521,12 +640,16 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
     if (transposed && stride > 1 && taps < stride && no_skip_parity) return AGCN_ERR_UNSUPPORTED;
     if (!aligned16(x) || !aligned16(w) || !aligned16(y) || (bias && !aligned16(bias))) return AGCN_ERR_UNSUPPORTED;
     if (split && (w_split == nullptr || !aligned16(w_split) || ((long long)cout * taps * cin) % 4)) return AGCN_ERR_UNSUPPORTED;
+    const bool bf = split == 2;
+    if (bf && (cin % 16 || ((long long)cout * taps * cin) % 8)) return AGCN_ERR_UNSUPPORTED;      // UMMA K = 16 bf16; m tensor 16-byte aligned
+    const int chunk_ch = bf ? 64 : kKChunk;
     if (stat_part != nullptr && (transposed || accumulate || cout > kStatCols || stat_nparts == nullptr)) return AGCN_ERR_UNSUPPORTED;
     // Output-channel tile.  A 3xTF32 tile whose K reduction needs more than one accumulator segment keeps fp32 master sums
     // in TMEM columns 256..383, so it is at most 128 wide; single-segment tiles (1x1 convs with cin <= 256) and the TF32
     // mode use up to 256 columns per accumulator buffer, which avoids re-loading (and re-splitting) the activations per tile.
-    const int kiters = taps * ((cin + kKChunk - 1) / kKChunk);
-    const bool one_segment = !split || kiters <= 8;
+    const int kiters = taps * ((cin + chunk_ch - 1) / chunk_ch);
+    const int seg_cap = bf ? 12 : 8;                      // (tap, K chunk) iterations one accumulator segment may hold without promotion
+    const bool one_segment = !split || kiters <= seg_cap;
     const int bn_cap = one_segment ? 256 : 128;
     int bn = 0;
     for (int cand = bn_cap; cand >= 16; cand -= 16)
@@ -542,13 +665,13 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
     static const bool no_dual = probe_env("AGCN_TC2_NO_DUAL") != nullptr;
     // main | cross accumulator pairs: multi-segment tiles up to 64 wide (2*bn <= 128 next to the master sums), single-segment
     // tiles (1x1 convs with cin <= 256: no master sums) up to 128 wide (2*bn <= 256 = one of the two accumulator buffers)
-    a.dual = (split && !no_dual && ((kiters > 8 && bn <= 64) || (kiters <= 8 && bn <= 128))) ? 1 : 0;
-    a.seg_iters = (split && kiters <= 8) ? 8 : (a.dual ? 3 * kSegment : kSegment);
+    a.dual = (split && !no_dual && ((kiters > seg_cap && bn <= 64) || (kiters <= seg_cap && bn <= 128))) ? 1 : 0;
+    a.seg_iters = (split && kiters <= seg_cap) ? seg_cap : (a.dual ? 3 * kSegment : (bf ? 6 : kSegment));
     a.acc_stride = (bn > 128 || (a.dual && 2 * bn > 128)) ? 256 : 128;
     a.tt = 128 / v;
     a.bn = bn;
     a.n_tiles_n = cout / bn;
-    a.kchunks = (cin + kKChunk - 1) / kKChunk;
+    a.kchunks = (cin + chunk_ch - 1) / chunk_ch;
     a.nparity = transposed ? stride : 1;
     const int t_per_class = transposed ? (t_out + stride - 1) / stride : t_out;
     a.tiles_t = (t_per_class + a.tt - 1) / a.tt;
@@ -612,7 +735,7 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
     uint32_t need = ((uint32_t)(nt_max - a.tt) * v + 128u) * 128u;       // rows the last tap's M=128 operand touches
     if (need < a.blk_rows_bytes) need = a.blk_rows_bytes;
     a.blk_bytes = (need + 1023u) & ~1023u;
-    a.a_stage_bytes = (uint32_t)a.nblk * a.blk_bytes;
+    a.a_stage_bytes = (uint32_t)a.nblk * a.blk_bytes * (bf ? 2u : 1u);      // BF16x3: two 32-channel fp32 boxes per slot -> h | m in place
     a.b_stage_bytes = (uint32_t)bn * 128u;
     const uint32_t a_slot = a.a_stage_bytes, b_slot = a.b_stage_bytes * (split ? 2u : 1u);
     const uint32_t stat_bytes = stat_part != nullptr ? kStatBytes : 0u;
@@ -627,8 +750,8 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
     // activation stage.  Everything else goes to the activation ring: payload bytes in flight set the achieved bandwidth.
     static const int nlo_env = probe_env("AGCN_TC2_NLO") ? atoi(probe_env("AGCN_TC2_NLO")) : 0;
     // lo-residual ring: 2 slots (3 or 4 measured no faster for the 1x1 kernels and slower where they shorten the payload ring, profiles/r2g)
-    int nlo_want = split ? 2 : 0;
-    if (split && nlo_env >= 1 && nlo_env <= kMaxLo) nlo_want = nlo_env;
+    int nlo_want = split == 1 ? 2 : 0;
+    if (split == 1 && nlo_env >= 1 && nlo_env <= kMaxLo) nlo_want = nlo_env;
     a.na = 0; a.nbst = 0; a.nlo = nlo_want;
     auto fit = [&](int nlo, int min_b) -> int {
         const uint64_t fixed = (uint64_t)nlo * a_slot + (uint64_t)min_b * b_slot;
@@ -637,7 +760,7 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
         return na > kMaxA ? kMaxA : na;
     };
     int best_na = 0, best_lo = a.nlo, best_b = 3;
-    for (int nlo = a.nlo; nlo >= (split ? 1 : 0) && best_na < 2; --nlo)
+    for (int nlo = a.nlo; nlo >= (split == 1 ? 1 : 0) && best_na < 2; --nlo)
         for (int min_b = 3; min_b >= 2 && best_na < 2; --min_b) {
             const int na = fit(nlo, min_b);
             if (na > best_na) { best_na = na; best_lo = nlo; best_b = min_b; }
@@ -680,23 +803,26 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     {
-        auto encode_w = [&](CUtensorMap* m, const float* ptr) -> CUresult {
+        // weight boxes: bn rows x one 128-byte K chunk (32 fp32 or 64 bf16 channels; channels past cin are zero-filled)
+        const size_t esz = bf ? 2 : 4;
+        auto encode_w = [&](CUtensorMap* m, const void* ptr) -> CUresult {
             cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)taps, (cuuint64_t)cout};
-            cuuint64_t strides[2] = {(cuuint64_t)cin * 4, (cuuint64_t)taps * cin * 4};
-            cuuint32_t box[3] = {(cuuint32_t)kKChunk, 1, (cuuint32_t)bn};
+            cuuint64_t strides[2] = {(cuuint64_t)cin * esz, (cuuint64_t)taps * cin * esz};
+            cuuint32_t box[3] = {(cuuint32_t)chunk_ch, 1, (cuuint32_t)bn};
             cuuint32_t estr[3] = {1, 1, 1};
-            return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
+            return enc(m, bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         };
         const long long nw = (long long)cout * taps * cin;
-        CUresult r = encode_w(&map_b, split ? w_split : w);
+        CUresult r = encode_w(&map_b, split ? static_cast<const void*>(w_split) : static_cast<const void*>(w));
         if (r != CUDA_SUCCESS) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc2: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
         map_blo = map_b;
         if (split) {
-            r = encode_w(&map_blo, w_split + nw);
+            r = encode_w(&map_blo, bf ? static_cast<const void*>(reinterpret_cast<uint16_t*>(w_split) + nw) : static_cast<const void*>(w_split + nw));
             if (r != CUDA_SUCCESS) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc2: cuTensorMapEncodeTiled(B lo) failed with %d", (int)r);
-            split_weights_kernel<<<ceil_div(nw, 256), 256, 0, st>>>(w, w_split, nw);
+            if (bf) split_weights_bf16_kernel<<<ceil_div(nw, 256), 256, 0, st>>>(w, reinterpret_cast<uint16_t*>(w_split), nw);
+            else split_weights_kernel<<<ceil_div(nw, 256), 256, 0, st>>>(w, w_split, nw);
             int rc = check_launch("agcn_conv_fwd_tc2(split weights)");
             if (rc) return rc;
         }
@@ -720,8 +846,9 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
         }
     }
     {   // per call: the attribute is per device / context, a process-wide flag would skip the second GPU
-        cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
         if (e != cudaSuccess) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc2: %s", cudaGetErrorString(e));
     }
     if (skipped_parity && !accumulate) {
@@ -730,8 +857,9 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
         if (e != cudaSuccess) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc2: cudaMemsetAsync: %s", cudaGetErrorString(e));
     }
     const long long grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
-    if (split) conv_tc2_kernel<true><<<(unsigned)grid, kThreads2Split, smem, st>>>(map_a, map_b, map_blo, map_y0, map_y1, a);
-    else conv_tc2_kernel<false><<<(unsigned)grid, kThreads2, smem, st>>>(map_a, map_b, map_blo, map_y0, map_y1, a);
+    if (split == 2) conv_tc2_kernel<2><<<(unsigned)grid, kThreads2Split, smem, st>>>(map_a, map_b, map_blo, map_y0, map_y1, a);
+    else if (split) conv_tc2_kernel<1><<<(unsigned)grid, kThreads2Split, smem, st>>>(map_a, map_b, map_blo, map_y0, map_y1, a);
+    else conv_tc2_kernel<0><<<(unsigned)grid, kThreads2, smem, st>>>(map_a, map_b, map_blo, map_y0, map_y1, a);
     if (stat_nparts != nullptr) *stat_nparts = stat_part != nullptr ? (int)grid * 4 : 0;
     return check_launch("agcn_conv_fwd_tc2");
 }

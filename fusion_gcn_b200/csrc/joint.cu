@@ -414,11 +414,11 @@ extern "C" AGCN_API int agcn_joint_gram(const float* a, const float* b, float* o
     AGCN_REQUIRE(v <= kMaxV && groups <= 3, AGCN_ERR_UNSUPPORTED, "agcn_joint_gram: V=%d > %d or groups=%d > 3", v, kMaxV, groups);
     AGCN_REQUIRE(offa >= 0 && offb >= 0 && offa + (groups - 1) * stridea + width <= lda && offb + (groups - 1) * strideb + width <= ldb,
                  AGCN_ERR_BAD_SHAPE, "agcn_joint_gram: channel window outside the row");
-    AGCN_REQUIRE(precision == AGCN_PREC_FP32 || precision == AGCN_PREC_TF32 || precision == AGCN_PREC_FP32_FFMA, AGCN_ERR_UNSUPPORTED,
+    AGCN_REQUIRE(precision >= AGCN_PREC_FP32 && precision <= AGCN_PREC_BF16X3, AGCN_ERR_UNSUPPORTED,
                  "agcn_joint_gram: unknown precision %d", precision);
     if (precision != AGCN_PREC_FP32_FFMA) {
         const int rc = agcn_joint_gram_tc(a, b, out, nb, t, v, lda, ldb, groups, offa, stridea, offb, strideb, width, nchunk,
-                                          precision == AGCN_PREC_FP32, stream);
+                                          precision == AGCN_PREC_FP32 || precision == AGCN_PREC_BF16X3 /* the V x V stages run 3xTF32 in both parity modes */, stream);
         if (rc != AGCN_ERR_UNSUPPORTED) return rc;
     }
     GramArgs p{a, b, out, nb, t, v, lda, ldb, groups, offa, stridea, offb, strideb, width, nchunk, 1, 0};
@@ -492,11 +492,11 @@ extern "C" AGCN_API int agcn_joint_mix(const float* in, const float* mats, float
     else return fail(AGCN_ERR_UNSUPPORTED, "agcn_joint_mix: unknown mode %d", mode);
     AGCN_REQUIRE(ldin == need_in && ldout == need_out, AGCN_ERR_BAD_SHAPE,
                  "agcn_joint_mix: mode %d expects ldin=%d ldout=%d, got %d %d", mode, need_in, need_out, ldin, ldout);
-    AGCN_REQUIRE(precision == AGCN_PREC_FP32 || precision == AGCN_PREC_TF32 || precision == AGCN_PREC_FP32_FFMA, AGCN_ERR_UNSUPPORTED,
+    AGCN_REQUIRE(precision >= AGCN_PREC_FP32 && precision <= AGCN_PREC_BF16X3, AGCN_ERR_UNSUPPORTED,
                  "agcn_joint_mix: unknown precision %d", precision);
     if (precision != AGCN_PREC_FP32_FFMA && workspace != nullptr && workspace_bytes >= agcn_joint_mix_tc_workspace_bytes(nb)) {
         const int rc = agcn_joint_mix_tc(in, mats, out, static_cast<float*>(workspace), nb, t, v, ldin, ldout, width, mode, accumulate,
-                                         precision == AGCN_PREC_FP32, stream);
+                                         precision == AGCN_PREC_FP32 || precision == AGCN_PREC_BF16X3 /* the V x V stages run 3xTF32 in both parity modes */, stream);
         if (rc != AGCN_ERR_UNSUPPORTED) return rc;
     }
     const int nblk = (v + 4) / 5, mld = nblk * 8;

@@ -20,11 +20,11 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import functional as FN
-from .capi import PREC_FP32, PREC_FP32_FFMA, PREC_TF32
+from .capi import PREC_BF16X3, PREC_FP32, PREC_FP32_FFMA, PREC_TF32
 from .graph import adjacency_from_graph
 
-_PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "fp32_ffma": PREC_FP32_FFMA,
-               PREC_FP32: PREC_FP32, PREC_TF32: PREC_TF32, PREC_FP32_FFMA: PREC_FP32_FFMA}
+_PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "fp32_ffma": PREC_FP32_FFMA, "bf16x3": PREC_BF16X3,
+               PREC_FP32: PREC_FP32, PREC_TF32: PREC_TF32, PREC_FP32_FFMA: PREC_FP32_FFMA, PREC_BF16X3: PREC_BF16X3}
 
 
 _default_precision = PREC_FP32

@@ -11,7 +11,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import capi
-from .capi import (MIX_AGG_BWD, MIX_AGG_FWD, MIX_SCORE_BWD, PREC_FP32, PREC_FP32_FFMA, PREC_TF32, RES_AFFINE,  # noqa: F401
+from .capi import (MIX_AGG_BWD, MIX_AGG_FWD, MIX_SCORE_BWD, PREC_BF16X3, PREC_FP32, PREC_FP32_FFMA, PREC_TF32, RES_AFFINE,  # noqa: F401
                    RES_NONE, RES_TENSOR)
 
 NUM_SMS = 148

@@ -46,7 +46,10 @@ typedef enum {
 typedef enum {
     AGCN_PREC_FP32 = 0,       /* fp32 parity mode: 3xTF32 error-compensated tcgen05 MMAs where the shape allows, FFMA otherwise */
     AGCN_PREC_TF32 = 1,       /* single-pass tcgen05 kind::tf32 (operands truncated to TF32); own tolerance             */
-    AGCN_PREC_FP32_FFMA = 2   /* force the FFMA kernels (reference path for tests)                                       */
+    AGCN_PREC_FP32_FFMA = 2,  /* force the FFMA kernels (reference path for tests)                                       */
+    AGCN_PREC_BF16X3 = 3      /* second fp32 parity mode: x = h + m (two bf16 pieces), products h.h + h.m + m.h on tcgen05
+                                 kind::f16 -- half the tensor time and operand bytes of 3xTF32, ~1e-5 unit-level error (inside
+                                 the 1e-4 contract); stages without a BF16x3 kernel run their 3xTF32 kernel                */
 } agcn_precision;
 
 /* joint-mix modes (agcn_joint_mix) */

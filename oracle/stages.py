@@ -12,7 +12,7 @@ Maths: SURVEY.md Appendix A; reference lines torch_src/models/mmargcn/agcn.py:37
 """
 import torch
 
-PREC_FP32, PREC_TF32, PREC_FP32_FFMA = 0, 1, 2
+PREC_FP32, PREC_TF32, PREC_FP32_FFMA, PREC_BF16X3 = 0, 1, 2, 3
 MIX_AGG_FWD, MIX_AGG_BWD, MIX_SCORE_BWD = 0, 1, 2
 RES_NONE, RES_TENSOR, RES_AFFINE = 0, 1, 2
 NUM_SMS = 148

@@ -31,15 +31,19 @@ def both(fn_name, K, tensors, **kw):
 CONV_CASES = [  # nb, t_in, v, cin, cout, taps, stride
     (2, 12, 25, 3, 96, 1, 1), (2, 12, 25, 64, 64, 9, 1), (3, 13, 20, 16, 32, 9, 2), (2, 13, 20, 16, 32, 1, 2),
     (1, 7, 5, 515, 64, 1, 1), (2, 9, 22, 9, 16, 1, 1), (1, 1, 37, 256, 60, 1, 1), (2, 30, 25, 128, 256, 9, 2),
-    (1, 300, 25, 64, 64, 9, 1), (2, 11, 20, 48, 48, 9, 1), (2, 9, 25, 32, 64, 3, 1)]
+    (1, 300, 25, 64, 64, 9, 1), (2, 11, 20, 48, 48, 9, 1), (2, 9, 25, 32, 64, 3, 1),
+    # BASELINE layer widths of the theta/phi, conv_d and temporal convolutions (half K chunks, multi-segment, 256-wide tiles)
+    (2, 12, 25, 96, 64, 1, 1), (2, 20, 25, 256, 256, 9, 1), (2, 20, 25, 128, 128, 9, 1), (2, 10, 25, 768, 256, 1, 1),
+    (2, 10, 25, 256, 768, 1, 1), (2, 10, 22, 384, 128, 1, 1), (2, 21, 25, 256, 256, 9, 2)]
 
 
-@pytest.mark.parametrize("mode", ["ffma", "fp32"])
+@pytest.mark.parametrize("mode", ["ffma", "fp32", "bf16x3"])
 @pytest.mark.parametrize("nb,t_in,v,cin,cout,taps,stride", CONV_CASES)
 def test_conv_fwd_dgrad_wgrad(K, nb, t_in, v, cin, cout, taps, stride, mode):
     """mode 'ffma' = AGCN_PREC_FP32_FFMA (pure FFMA kernels); mode 'fp32' = AGCN_PREC_FP32, the parity mode, which runs
     3xTF32 error-compensated tcgen05 MMAs on the shapes the tensor-core path takes (and FFMA on the rest)."""
-    prec, tol = (K.PREC_FP32_FFMA, 2e-6) if mode == "ffma" else (K.PREC_FP32, 1e-5)
+    prec, tol = {"ffma": (K.PREC_FP32_FFMA, 2e-6), "fp32": (K.PREC_FP32, 1e-5), "bf16x3": (K.PREC_BF16X3, 4e-5)}[mode]
+    # bf16x3: x = h + m to 2^-17 (two bf16 pieces), products h.h + h.m + m.h: per-stage error ~1e-5, unit-level 1e-5..3e-5
     pad = (taps - 1) // 2
     t_out = (t_in + 2 * pad - taps) // stride + 1
     x, w, b = rnd(nb, t_in, v, cin), rnd(cout, taps, cin, seed=1) * 0.1, rnd(cout, seed=2)
@@ -61,7 +65,7 @@ def test_conv_fwd_dgrad_wgrad(K, nb, t_in, v, cin, cout, taps, stride, mode):
     assert rel_err(dw, dw_ref) <= 2.5 * tol and rel_err(db, db_ref) <= 5e-6
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "bf16x3"])
 @pytest.mark.parametrize("nb,t_in,v,cin,cout,taps,stride", [
     (3, 40, 25, 64, 64, 9, 1), (2, 31, 25, 192, 64, 1, 1), (4, 30, 20, 64, 128, 9, 2), (2, 24, 22, 384, 128, 1, 1),
     (2, 16, 25, 128, 256, 1, 2), (1, 12, 25, 256, 256, 9, 1), (2, 12, 25, 3, 64, 1, 1), (3, 700, 25, 64, 64, 1, 1)])
@@ -69,7 +73,7 @@ def test_conv_fwd_fused_bn_statistics(K, nb, t_in, v, cin, cout, taps, stride, m
     """agcn_conv_fwd_stats + agcn_bn_finalize against conv_fwd followed by bn_stats on its output (same y bit for bit; scale /
     shift / mean / invstd and the running statistics to 1e-5), including more tiles than CTAs and a shape the fused epilogue
     does not cover (cin = 3: part is None and the caller falls back)."""
-    prec = K.PREC_FP32 if mode == "fp32" else K.PREC_TF32
+    prec = {"fp32": K.PREC_FP32, "tf32": K.PREC_TF32, "bf16x3": K.PREC_BF16X3}[mode]
     pad = (taps - 1) // 2
     t_out = (t_in + 2 * pad - taps) // stride + 1
     x, w, b = rnd(nb, t_in, v, cin).cuda(), (rnd(cout, taps, cin, seed=1) * 0.1).cuda(), rnd(cout, seed=2).cuda()

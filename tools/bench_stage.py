@@ -42,7 +42,7 @@ def report(name, ms, nbytes, flops):
 def main():
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     once = "--once" in sys.argv
-    prec = K.PREC_TF32 if "--tf32" in sys.argv else K.PREC_FP32
+    prec = K.PREC_TF32 if "--tf32" in sys.argv else K.PREC_BF16X3 if "--bf16x3" in sys.argv else K.PREC_FP32
     want = lambda n: not args or any(a in n for a in args)   # noqa: E731
     dev = "cuda"
     for tag, (c, t) in SHAPES.items():

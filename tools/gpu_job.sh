@@ -9,6 +9,9 @@ for step in "$@"; do
     peaks)     python tools/measure_peaks.py > gpurun_out/${tag}_peaks.json 2> gpurun_out/${tag}_peaks.err; cat gpurun_out/${tag}_peaks.json ;;
     bench)     python bench.py --steps 10 --warmup 3 --dump-kernels gpurun_out/${tag}_kernels.json > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; tail -c 600 gpurun_out/${tag}_bench.json; tail -3 gpurun_out/${tag}_bench.err ;;
     stage)     python tools/bench_stage.py > gpurun_out/${tag}_stage_fp32.log 2>&1; tail -3 gpurun_out/${tag}_stage_fp32.log ;;
+    stagebf)   python tools/bench_stage.py conv wgrad --bf16x3 > gpurun_out/${tag}_stage_bf16x3.log 2>&1; cat gpurun_out/${tag}_stage_bf16x3.log ;;
+    stageconv) python tools/bench_stage.py conv wgrad > gpurun_out/${tag}_stage_fp32.log 2>&1; cat gpurun_out/${tag}_stage_fp32.log ;;
+    convtest)  timeout 600 python -m pytest tests/test_gpu_stages.py -m gpu -q -rf -x -k "conv" -p no:cacheprovider > gpurun_out/${tag}_convtest.log 2>&1; tail -15 gpurun_out/${tag}_convtest.log ;;
     stagetf32) python tools/bench_stage.py --tf32 > gpurun_out/${tag}_stage_tf32.log 2>&1 ;;
     smoke)     python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.log 2>&1; tail -2 gpurun_out/${tag}_smoke.log ;;
     *) echo "unknown step $step" ;;
