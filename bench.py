@@ -204,7 +204,7 @@ def run_ours(args):
         torch.cuda.empty_cache()
     # ---- the separately reported TF32 mode (single-pass tensor cores, own tolerance), device-resident, same step
     ms_tf32 = ms_tf32_graph = 0.0
-    if args.precision == "fp32" and not args.no_tf32:
+    if args.precision in ("fp32", "bf16x3") and not args.no_tf32:
         from fusion_gcn_b200 import modules as M
         M.set_precision(model, "tf32")
         for _ in range(args.warmup):
@@ -297,7 +297,7 @@ def run_ours(args):
     line = {
         "metric": "AGCN fwd+bwd sequences/sec", "value": round(value, 2), "unit": "sequences/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_head / args.steps, 3), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "tf32", "data": "synthetic",
+        "vs_baseline": None, "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: AGCN 10 units, N={n_local}/GPU (global {n_global}), M={m}, T={t}, V={v}, C={c}, "
                                f"{ncls} classes, train mode, fwd+CE+bwd, random init", "precision_mode": args.precision,
                    "l2_policy": "activations per step (GBs) exceed the 126 MB L2; no explicit flush",
@@ -525,7 +525,8 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="sequences per GPU (default 64; 256 for --mode infer)")
     ap.add_argument("--mode", default="train", choices=["train", "infer"], help="train: fwd+CE+bwd (the BASELINE metric); infer: forward only, eval mode")
     ap.add_argument("--micro-batch", type=int, default=512, help="--mode infer: sequences per forward call")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16x3", "tf32"],
+                    help="fp32 = 3xTF32 parity mode, bf16x3 = bf16 triple-product parity mode (both meet 1e-4), tf32 = single pass (own tolerance)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dump-kernels", default=None, help="write the per-signature timing table (all C-ABI launches) to this JSON file")
     ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay timing")

@@ -636,7 +636,7 @@ extern "C" AGCN_API size_t agcn_conv_wgrad_workspace_bytes(int nb, int t_in, int
     const int pad = (taps - 1) / 2;
     size_t tc = 0;
     for (int stride = 1; stride <= 2; ++stride)
-        for (int split = 0; split <= 1; ++split) {
+        for (int split = 0; split <= 2; ++split) {
             size_t f = agcn_conv_wgrad_tc_workspace_floats(nb, t_in, t_out, v, cin, cout, taps, stride, pad, split);
             if (f > tc) tc = f;
         }
@@ -658,9 +658,13 @@ extern "C" AGCN_API int agcn_conv_wgrad(const float* dy, const float* x, float* 
     AGCN_REQUIRE(workspace_bytes >= need, AGCN_ERR_WORKSPACE, "agcn_conv_wgrad: workspace %zu < %zu", workspace_bytes, need);
     AGCN_REQUIRE(aligned16(workspace), AGCN_ERR_MISALIGNED, "agcn_conv_wgrad: workspace not 16-byte aligned");
     AGCN_REQUIRE(known_precision(precision), AGCN_ERR_UNSUPPORTED, "agcn_conv_wgrad: unknown precision %d", precision);
-    const int tc_split = precision == AGCN_PREC_FP32 || precision == AGCN_PREC_BF16X3;
-    const size_t tc_floats = precision == AGCN_PREC_FP32_FFMA ? 0 :
+    int tc_split = precision == AGCN_PREC_FP32 ? 1 : (precision == AGCN_PREC_BF16X3 ? 2 : 0);
+    size_t tc_floats = precision == AGCN_PREC_FP32_FFMA ? 0 :
         agcn_conv_wgrad_tc_workspace_floats(nb, t_in, t_out, v, cin, cout, taps, stride, pad, tc_split);
+    if (tc_floats == 0 && tc_split == 2) {          // shape outside the BF16x3 plan: the 3xTF32 kernel is the other parity path
+        tc_split = 1;
+        tc_floats = agcn_conv_wgrad_tc_workspace_floats(nb, t_in, t_out, v, cin, cout, taps, stride, pad, tc_split);
+    }
     if (tc_floats > 0 && (tc_floats + (size_t)kBiasPartials * cout) * sizeof(float) <= workspace_bytes) {
         float* ws = static_cast<float*>(workspace);
         int tc_splits = 0;

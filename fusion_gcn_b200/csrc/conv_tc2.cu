@@ -85,52 +85,6 @@ struct Tc2Args {
     int tma_store;                // 1: epilogue stages 32-column chunks in shared memory and writes them with TMA (bulk tensor stores / reduce-adds)
 };
 
-// round-to-nearest (ties away) bf16 pieces of eight fp32 values: h = bf16(x), m = bf16(x - h), packed in channel order
-__device__ __forceinline__ void bf16_split8(const float4& a, const float4& b, uint4& h, uint4& m) {
-    const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    uint32_t hb[8], mb[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        hb[i] = (__float_as_uint(x[i]) + 0x8000u) & 0xFFFF0000u;
-        mb[i] = __float_as_uint(x[i] - __uint_as_float(hb[i])) + 0x8000u;          // exact difference; only the upper half is kept below
-    }
-    h = make_uint4(__byte_perm(hb[0], hb[1], 0x7632), __byte_perm(hb[2], hb[3], 0x7632), __byte_perm(hb[4], hb[5], 0x7632), __byte_perm(hb[6], hb[7], 0x7632));
-    m = make_uint4(__byte_perm(mb[0], mb[1], 0x7632), __byte_perm(mb[2], mb[3], 0x7632), __byte_perm(mb[4], mb[5], 0x7632), __byte_perm(mb[6], mb[7], 0x7632));
-}
-__device__ __forceinline__ void sts128u(uint32_t addr, const uint4& v) {
-    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-// One activation row of a 64-channel K chunk, in place: p0 / p1 = the row in the first / second 32-channel fp32 box (128 bytes each,
-// 16-byte chunk j stored at j ^ sw), rewritten as 64 bf16 of h at p0 and 64 bf16 of m at p1 (chunk q = channels 8q..8q+7 at q ^ sw).
-// Every fp32 chunk is read before the bf16 chunk that overwrites its bytes is stored.
-__device__ __forceinline__ void bf16_split_row(uint32_t p0, uint32_t p1, uint32_t sw, bool has1) {
-    float4 f[8];
-    uint4 hq[4], mq[4], h2[4], m2[4];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = lds128(p0 + (((uint32_t)j ^ sw) << 4));
-#pragma unroll
-    for (int q = 0; q < 4; ++q) bf16_split8(f[2 * q], f[2 * q + 1], hq[q], mq[q]);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = has1 ? lds128(p1 + (((uint32_t)j ^ sw) << 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) bf16_split8(f[2 * q], f[2 * q + 1], h2[q], m2[q]);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        sts128u(p0 + (((uint32_t)q ^ sw) << 4), hq[q]);
-        sts128u(p0 + (((uint32_t)(q + 4) ^ sw) << 4), h2[q]);
-        sts128u(p1 + (((uint32_t)q ^ sw) << 4), mq[q]);
-        sts128u(p1 + (((uint32_t)(q + 4) ^ sw) << 4), m2[q]);
-    }
-}
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-
 // MODE: 0 single-pass TF32, 1 3xTF32 (fp32 parity), 2 BF16x3 (fp32 parity, bf16 triple products)
 template <int MODE>
 __global__ void __launch_bounds__(MODE != 0 ? kThreads2Split : kThreads2, 1)

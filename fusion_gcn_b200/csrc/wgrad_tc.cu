@@ -36,14 +36,20 @@ struct WgArgs {
 };
 
 
-template <bool SPLIT>
-__global__ void __launch_bounds__(SPLIT ? kWgThreadsSplit : kThreads, 1)
+// MODE: 0 single-pass TF32, 1 3xTF32, 2 BF16x3.  BF16x3: the TMA boxes are plain-128B-swizzled fp32 blocks of 32 channels; the
+// converter warps (one thread per K row) rewrite every PAIR of slots in place as 64 bf16 channels of h (first slot) and of m
+// (second slot) -- MN-major 16-bit operands, 64 channels per 128-byte row, 8-row swizzle groups -- and the issuer runs
+// h.h + h.m + m.h on kind::f16 with K = 16 rows per MMA.  No lo ring: four 48 KB stages like the TF32 mode.
+template <int MODE>
+__global__ void __launch_bounds__(MODE != 0 ? kWgThreadsSplit : kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, WgArgs a) {
+    constexpr bool SPLIT = MODE == 1, BF = MODE == 2, CONV = MODE != 0;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sub_bytes = (uint32_t)a.rpad * 128u;
     const uint32_t nsub_b = (uint32_t)a.n_tile / 32u;
-    const uint32_t raw_bytes = (4u + nsub_b) * sub_bytes;                 // one stage of TMA payload (raw, becomes hi in place)
+    const uint32_t nsub_slots = BF ? ((nsub_b + 1u) & ~1u) : nsub_b;      // BF16x3: x slots come in (h, m) pairs
+    const uint32_t raw_bytes = (4u + nsub_slots) * sub_bytes;             // one stage of TMA payload (raw, becomes hi / h|m in place)
     const uint32_t lo_ring = smem_base + (uint32_t)a.stages * raw_bytes;  // SPLIT: two slots of lo residuals
     const uint32_t bar_base = lo_ring + (SPLIT ? 2u * raw_bytes : 0u);
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -53,7 +59,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
     auto tfull_bar = [&](int s) { return bar_base + 8u * (3 * kWgStages + 2 + s); };
     auto tempty_bar = [&](int s) { return bar_base + 8u * (3 * kWgStages + 4 + s); };
     const uint32_t tmem_slot = bar_base + 8u * (3 * kWgStages + 6);
-    constexpr int kCols = SPLIT ? 512 : 256;                              // SPLIT: 2 x 128 segment accumulators + 128 master sums
+    constexpr int kCols = CONV ? 512 : 256;                               // parity modes: 2 x 128 segment accumulators + 128 master sums
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     // clear the operand stages once: rows the TMA boxes never write must read as zero in the K reduction
@@ -157,7 +163,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
             const bool leader = elect_one_sync() != 0;
             const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
             // tf32 x tf32 -> f32, A and B MN-major, M = 128, N = n_tile
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+            constexpr uint32_t kFmt = BF ? 1u : 2u;                        // operand format: BF16 (kind::f16) or TF32
+            const uint32_t idesc = (1u << 4) | (kFmt << 7) | (kFmt << 10) | (1u << 15) | (1u << 16) |
                                    ((uint32_t)(a.n_tile >> 3) << 17) | ((128u >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
@@ -166,17 +173,29 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
             long long done = 0;
             int sl = 0;
             const long long nchunks = c_end - c_begin;
-            const int ksteps = (a.dbg & 2) ? 1 : (a.rows_box + 7) / 8;
+            const int ksteps = (a.dbg & 2) ? 1 : (BF ? (a.rows_box + 15) / 16 : (a.rows_box + 7) / 8);
             for (long long c = c_begin; c < c_end; ++c) {
                 mbar_wait(full_bar(stage), phase);
-                if (SPLIT) mbar_wait(lo_bar(stage), phase);
+                if (CONV) mbar_wait(lo_bar(stage), phase);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t sa = smem_base + (uint32_t)stage * raw_bytes;
                 const uint32_t slo = lo_ring + (uint32_t)sl * raw_bytes;
                 const uint64_t da = make_smem_desc_mn(sa, sub_bytes), db = make_smem_desc_mn(sa + 4u * sub_bytes, sub_bytes);
                 const uint64_t dalo = make_smem_desc_mn(slo, sub_bytes);
                 const uint64_t dblo = make_smem_desc_mn(slo + 4u * sub_bytes, sub_bytes);
-                if (leader) {
+                if (leader && BF) {
+                    // h pieces in the even slots, m pieces in the odd slots; 64-channel blocks are two slots apart
+                    const uint64_t dah = make_smem_desc_mn16(sa, 2u * sub_bytes), dam = make_smem_desc_mn16(sa + sub_bytes, 2u * sub_bytes);
+                    const uint64_t dbh = make_smem_desc_mn16(sa + 4u * sub_bytes, 2u * sub_bytes), dbm = make_smem_desc_mn16(sa + 5u * sub_bytes, 2u * sub_bytes);
+                    for (int kg = 0; kg < ksteps; ++kg) {
+                        const uint64_t ko = (uint64_t)(kg * 128);          // 16 rows = 2048 bytes, in 16-byte units
+                        const uint32_t fresh = (kg == 0) ? first : 0u;
+                        umma_bf16(d_tmem, dam + ko, dbh + ko, idesc, fresh ^ 1u);
+                        umma_bf16(d_tmem, dah + ko, dbm + ko, idesc, 1u);
+                        umma_bf16(d_tmem, dah + ko, dbh + ko, idesc, 1u);
+                    }
+                    umma_commit(empty_bar(stage));
+                } else if (leader) {
                     for (int kg = 0; kg < ksteps; ++kg) {
                         const uint64_t ko = (uint64_t)(kg * 64);
                         const uint32_t fresh = (kg == 0) ? first : 0u;
@@ -196,7 +215,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
                 if (SPLIT) sl ^= 1;
                 if (++stage == a.stages) { stage = 0; phase ^= 1u; }
                 ++done;
-                if (SPLIT && (done % a.seg_chunks) == 0 && done < nchunks) {
+                if (CONV && (done % a.seg_chunks) == 0 && done < nchunks) {
                     // promote this partial accumulator to the epilogue's fp32 registers, continue in the other TMEM buffer
                     if (leader) umma_commit(tfull_bar(acc));
                     __syncwarp();
@@ -218,7 +237,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
         const bool store = (co < a.cout) && (otap < a.taps);
         float* out = a.ws + (((long long)split * a.cout + (store ? co : 0)) * a.taps + (store ? otap : 0)) * a.cin + k0;
         const long long nchunks = c_end - c_begin;
-        const int nseg = SPLIT ? (int)((nchunks + a.seg_chunks - 1) / a.seg_chunks) : 1;
+        const int nseg = CONV ? (int)((nchunks + a.seg_chunks - 1) / a.seg_chunks) : 1;
         int acc = 0; uint32_t acc_phase = 0;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const uint32_t master = tmem_base + 256u + lane_base;            // SPLIT: fp32 master sums (columns 256..383, n_tile <= 128)
@@ -228,11 +247,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
             const uint32_t taddr = tmem_base + (uint32_t)(acc * 128) + lane_base;
             const bool last = sg == nseg - 1;
 #pragma unroll
-            for (int cg = 0; cg < (SPLIT ? 8 : 16); ++cg) {
+            for (int cg = 0; cg < (CONV ? 8 : 16); ++cg) {
                 const int c = cg * 16;
                 if (c < a.n_tile) {
                     float vals[16];
-                    if (SPLIT) tmem_promote16(taddr + (uint32_t)c, master + (uint32_t)c, sg == 0, !last, vals);
+                    if (CONV) tmem_promote16(taddr + (uint32_t)c, master + (uint32_t)c, sg == 0, !last, vals);
                     else tmem_ld16(taddr + (uint32_t)c, vals);
                     if (last && store) {
 #pragma unroll
@@ -242,11 +261,33 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
                     }
                 }
             }
-            if (SPLIT && !last) tmem_st_wait();
+            if (CONV && !last) tmem_st_wait();
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    } else if (BF) {
+        // BF16x3 converter (kWgTransformWarps warps): slot pair (2j, 2j+1) of 32-channel fp32 blocks -> 64 bf16 channels of h | m in
+        // place, one thread per (pair, K row).  Only rows TMA wrote are touched (the pad rows stay zero); a pair whose first slot is
+        // never loaded stays zero, a pair with only its first slot loaded gets zero upper channels.
+        const int tidx = threadIdx.x - 6 * 32;
+        const int npairs = (4 + (int)nsub_b + 1) / 2;
+        int stage = 0; uint32_t phase = 0;
+        for (long long c = c_begin; c < c_end; ++c) {
+            mbar_wait(full_bar(stage), phase);
+            const uint32_t sa = smem_base + (uint32_t)stage * raw_bytes;
+            for (int idx = tidx; idx < npairs * a.rows_box; idx += kWgTransformWarps * 32) {
+                const int pr = idx / a.rows_box, r = idx - pr * a.rows_box;
+                if ((loaded >> (2 * pr)) & 1u) {
+                    const uint32_t p0 = sa + (uint32_t)(2 * pr) * sub_bytes + (uint32_t)r * 128u;
+                    bf16_split_row(p0, p0 + sub_bytes, (uint32_t)(r & 7), ((loaded >> (2 * pr + 1)) & 1u) != 0);
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(lo_bar(stage));
+            if (++stage == a.stages) { stage = 0; phase ^= 1u; }
         }
     } else if (SPLIT) {
         // operand split (kWgTransformWarps warps): hi = rna_tf32(x) in place, lo = x - hi into the stage's second half.
@@ -296,7 +337,8 @@ struct WgPlan {
     size_t smem;
 };
 
-static WgPlan plan_wgrad(int nb, int t_in, int t_out, int v, int cin, int cout, int taps, int stride, int pad, bool split) {
+// split: 0 TF32, 1 3xTF32, 2 BF16x3
+static WgPlan plan_wgrad(int nb, int t_in, int t_out, int v, int cin, int cout, int taps, int stride, int pad, int split) {
     WgPlan p;
     p.ok = false;
     if (cin % 4 || cout % 4 || v > 128 || stride > 4) return p;
@@ -308,13 +350,14 @@ static WgPlan plan_wgrad(int nb, int t_in, int t_out, int v, int cin, int cout, 
     if (a.n_tile > n_cap) a.n_tile = n_cap;
     a.n_tiles = (cin + a.n_tile - 1) / a.n_tile;
     a.m_tiles = (cout + 127) / 128;
-    const int nsub = 4 + a.n_tile / 32;
+    const bool bf = split == 2;
+    const int nsub = 4 + (bf ? (a.n_tile / 32 + 1) / 2 * 2 : a.n_tile / 32);     // BF16x3: x slots come in (h, m) pairs
     // Rows per stage.  Every stage costs ~1000-1400 cycles of fixed work (TMA issue, barrier hops, operand split, MMA issue;
     // probes in profiles/r1v, r1w), so stages are as tall as shared memory allows: TF32 four stages of 48 KB; 3xTF32 three raw
     // stages + two lo slots in 200 KB (40 KB each).
     static const int split_kb = probe_env("AGCN_WG_SPLIT_KB") ? atoi(probe_env("AGCN_WG_SPLIT_KB")) : 40;
-    int rmax = ((split ? split_kb : 48) * 1024) / (nsub * 128);
-    rmax = rmax / 8 * 8;
+    int rmax = ((split == 1 ? split_kb : 48) * 1024) / (nsub * 128);
+    rmax = bf ? rmax / 16 * 16 : rmax / 8 * 8;                                     // BF16x3: UMMA K = 16 rows
     if (rmax > 128) rmax = 128;
     if (rmax < 8) return p;
     a.flat = (stride == 1 && t_in == t_out) ? 1 : 0;
@@ -332,15 +375,15 @@ static WgPlan plan_wgrad(int nb, int t_in, int t_out, int v, int cin, int cout, 
         if (a.tt < 1) { a.tt = 1; }
         while (a.tt * stride > 256) --a.tt;
         a.rows_box = a.tt * v;
-        a.rpad = (a.rows_box + 7) / 8 * 8;
-        if ((size_t)nsub * a.rpad * 128 * (split ? 2 : 1) > 96 * 1024) return p;
+        a.rpad = bf ? (a.rows_box + 15) / 16 * 16 : (a.rows_box + 7) / 8 * 8;
+        if ((size_t)nsub * a.rpad * 128 * (split == 1 ? 2 : 1) > 96 * 1024) return p;
         a.chunks_per_sample = (t_out + a.tt - 1) / a.tt;
     }
     a.chunks_total = (long long)nb * a.chunks_per_sample;
-    a.seg_chunks = 256 / a.rows_box;
+    a.seg_chunks = (bf ? 512 : 256) / a.rows_box;      // rows per accumulator segment: <= 32 K steps x 3 chained MMAs
     if (a.seg_chunks < 1) a.seg_chunks = 1;
     const size_t raw_stage = (size_t)nsub * a.rpad * 128;
-    int stages = (int)((200 * 1024 - (split ? 2 * raw_stage : 0)) / raw_stage);     // 3xTF32: two extra slots hold the lo residuals
+    int stages = (int)((200 * 1024 - (split == 1 ? 2 * raw_stage : 0)) / raw_stage);     // 3xTF32: two extra slots hold the lo residuals
     if (stages > kWgStages) stages = kWgStages;
     if (stages < 2) return p;
     a.stages = stages;
@@ -352,7 +395,7 @@ static WgPlan plan_wgrad(int nb, int t_in, int t_out, int v, int cin, int cout, 
     a.chunks_per_split = (a.chunks_total + splits - 1) / splits;
     splits = (a.chunks_total + a.chunks_per_split - 1) / a.chunks_per_split;
     p.splits = (int)splits;
-    p.smem = (size_t)(stages + (split ? 2 : 0)) * raw_stage + 1024 + kWgBarBytes;
+    p.smem = (size_t)(stages + (split == 1 ? 2 : 0)) * raw_stage + 1024 + kWgBarBytes;
     p.ok = true;
     return p;
 }
@@ -364,7 +407,7 @@ using namespace agcn;
 
 // ---- weight gradient on tensor cores; returns AGCN_ERR_UNSUPPORTED for shapes outside the path
 size_t agcn_conv_wgrad_tc_workspace_floats(int nb, int t_in, int t_out, int v, int cin, int cout, int taps, int stride, int pad, int split) {
-    agcn::tc::WgPlan p = agcn::tc::plan_wgrad(nb, t_in, t_out, v, cin, cout, taps, stride, pad, split != 0);
+    agcn::tc::WgPlan p = agcn::tc::plan_wgrad(nb, t_in, t_out, v, cin, cout, taps, stride, pad, split);
     if (!p.ok) return 0;
     return (size_t)p.splits * cout * taps * cin;
 }
@@ -373,7 +416,7 @@ int agcn_conv_wgrad_tc(const float* dy, const float* x, float* ws, int* splits_o
                        int nb, int t_in, int t_out, int v, int cin, int cout, int taps, int stride, int pad, int split, void* stream) {
     using namespace agcn::tc;
     if (!aligned16(dy) || !aligned16(x) || !aligned16(ws)) return AGCN_ERR_UNSUPPORTED;
-    WgPlan p = plan_wgrad(nb, t_in, t_out, v, cin, cout, taps, stride, pad, split != 0);
+    WgPlan p = plan_wgrad(nb, t_in, t_out, v, cin, cout, taps, stride, pad, split);
     if (!p.ok) return AGCN_ERR_UNSUPPORTED;
     EncodeTiledFn enc = encode_fn();
     if (!enc) return fail(AGCN_ERR_CUDA, "agcn_conv_wgrad_tc: cuTensorMapEncodeTiled is not available from the driver");
@@ -404,8 +447,10 @@ int agcn_conv_wgrad_tc(const float* dy, const float* x, float* ws, int* splits_o
             box[0] = 32; box[1] = v; box[2] = box2; box[3] = 1;
             estr[2] = es2;
         }
+        // TF32 operands are read by the MMA as they land (32-byte-atom swizzle, the only MN-major tf32 layout); the BF16x3
+        // converter reads plain 128B-swizzled rows
         return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, split == 2 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     };
     CUresult r = encode(&map_dy, dy, cout, t_out, a.rows_box, a.blocked ? a.nblk_a : a.tt, 1);
@@ -417,14 +462,16 @@ int agcn_conv_wgrad_tc(const float* dy, const float* x, float* ws, int* splits_o
     }
     if (r != CUDA_SUCCESS) return fail(AGCN_ERR_CUDA, "agcn_conv_wgrad_tc: cuTensorMapEncodeTiled failed with %d", (int)r);
     {   // per call: the attribute is per device / context, a process-wide flag would skip the second GPU
-        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
         if (e != cudaSuccess) return fail(AGCN_ERR_CUDA, "agcn_conv_wgrad_tc: %s", cudaGetErrorString(e));
     }
     dim3 grid((unsigned)(a.tap_tiles * a.m_tiles * a.n_tiles), (unsigned)p.splits);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (split) wgrad_tc_kernel<true><<<grid, kWgThreadsSplit, p.smem, st>>>(map_dy, map_x, a);
-    else wgrad_tc_kernel<false><<<grid, kThreads, p.smem, st>>>(map_dy, map_x, a);
+    if (split == 2) wgrad_tc_kernel<2><<<grid, kWgThreadsSplit, p.smem, st>>>(map_dy, map_x, a);
+    else if (split) wgrad_tc_kernel<1><<<grid, kWgThreadsSplit, p.smem, st>>>(map_dy, map_x, a);
+    else wgrad_tc_kernel<0><<<grid, kThreads, p.smem, st>>>(map_dy, map_x, a);
     *splits_out = p.splits;
     return check_launch("agcn_conv_wgrad_tc");
 }

@@ -8,6 +8,7 @@ for step in "$@"; do
     pytestnew) python -m pytest tests/test_gpu_baseline_shapes.py -m gpu -q -rf -s -p no:cacheprovider > gpurun_out/${tag}_pytest_new.log 2>&1; tail -5 gpurun_out/${tag}_pytest_new.log ;;
     peaks)     python tools/measure_peaks.py > gpurun_out/${tag}_peaks.json 2> gpurun_out/${tag}_peaks.err; cat gpurun_out/${tag}_peaks.json ;;
     bench)     python bench.py --steps 10 --warmup 3 --dump-kernels gpurun_out/${tag}_kernels.json > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; tail -c 600 gpurun_out/${tag}_bench.json; tail -3 gpurun_out/${tag}_bench.err ;;
+    benchbf)   python bench.py --steps 10 --warmup 3 --precision bf16x3 --no-cpu-baseline --dump-kernels gpurun_out/${tag}_kernels_bf16x3.json > gpurun_out/${tag}_bench_bf16x3.json 2> gpurun_out/${tag}_bench_bf16x3.err; tail -c 400 gpurun_out/${tag}_bench_bf16x3.json; tail -3 gpurun_out/${tag}_bench_bf16x3.err ;;
     stage)     python tools/bench_stage.py > gpurun_out/${tag}_stage_fp32.log 2>&1; tail -3 gpurun_out/${tag}_stage_fp32.log ;;
     stagebf)   python tools/bench_stage.py conv wgrad --bf16x3 > gpurun_out/${tag}_stage_bf16x3.log 2>&1; cat gpurun_out/${tag}_stage_bf16x3.log ;;
     stageconv) python tools/bench_stage.py conv wgrad > gpurun_out/${tag}_stage_fp32.log 2>&1; cat gpurun_out/${tag}_stage_fp32.log ;;
