@@ -519,11 +519,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 mbar_wait(a_full(sa), pa);
                 const uint32_t src = smem_base + (uint32_t)sa * a_slot;
                 const bool has1 = a.cin - kc * 64 > 32;
-                for (int idx = tids; idx < a.nblk * rows; idx += kSplitWarps * 32) {
-                    const int b = idx >= rows ? 1 : 0;
-                    const int r = idx - b * rows;
+                // lanes l and l + 16 of a warp share a row (one 32-channel box each): 16 rows per warp, 128 rows per pass
+                const int hf = lane >> 4;
+                const int total = a.nblk * rows;
+                for (int base = 0; base < total; base += kSplitWarps * 16) {
+                    const int idx = base + (tids >> 5) * 16 + (lane & 15);
+                    const bool active = idx < total;
+                    const int b = (active && idx >= rows) ? 1 : 0;
+                    const int r = active ? idx - b * rows : 0;
                     const uint32_t p0 = src + (uint32_t)(b * 2) * a.blk_bytes + (uint32_t)r * 128u;
-                    bf16_split_row(p0, p0 + a.blk_bytes, (uint32_t)(r & 7), has1);
+                    bf16_split_row_pair(p0, p0 + a.blk_bytes, (uint32_t)(r & 7), hf, has1, active);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
@@ -609,6 +614,22 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
     for (int cand = bn_cap; cand >= 16; cand -= 16)
         if (cout % cand == 0) { bn = cand; break; }
     if (bn == 0 || (bn < 64 && cout > 128)) return AGCN_ERR_UNSUPPORTED;
+    if (split && taps == 1 && bn > 128) {
+        // Ring depth.  The [hi ; lo] weight slot of a tile wider than 128 columns is 48..64 KB: next to the epilogue buffers only ONE
+        // activation stage then fits and load -> convert -> MMA serialise (measured: 768 -> 256 at 0.48 ms against 0.22 ms in the
+        // TF32 mode).  Unless the whole weight tile can stay resident, take the widest tile that leaves two weight slots and three
+        // activation stages (five with the 3xTF32 lo ring); the activation tile is then re-read (from L2) once per extra tile.
+        const uint64_t a_st = (uint64_t)(bf ? 2 : 1) * 16384u;
+        const int kch = (cin + chunk_ch - 1) / chunk_ch;
+        auto fits = [&](int cand) {
+            const uint64_t b = (uint64_t)cand * 256u;
+            const bool resident = cout == cand && kch <= kMaxB && (uint64_t)kch * b + (split == 1 ? 5u : 3u) * a_st <= 176u * 1024u;
+            return resident || 2u * b + (split == 1 ? 5u : 3u) * a_st <= 176u * 1024u;
+        };
+        if (!fits(bn))
+            for (int cand = 128; cand >= 64; cand -= 16)
+                if (cout % cand == 0 && fits(cand)) { bn = cand; break; }
+    }
     EncodeTiledFn enc = encode_fn();
     if (!enc) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc2: cuTensorMapEncodeTiled is not available from the driver");
 

@@ -131,10 +131,13 @@ def unit_inputs(nb, cin, cout, t, v, stride, seed):
     return x, w
 
 
-def run_model_parity(model, state, x, w, device, num_channels, start, tol=TOL, tie=TIE, variant="mmargcn", adj_a=None):
+def run_model_parity(model, state, x, w, device, num_channels, start, tol=TOL, tie=TOL, variant="mmargcn", adj_a=None):
     """Whole Model (ours) against the fp64 oracle with the same three-step contract as run_unit_parity: logits against the plain
     oracle, every unit's two ReLU brackets equal to the fp64 ones except at ties, all parameter gradients against the oracle
-    evaluated on our brackets -- 1e-4, no noise-scaled slack.  ``model`` must be freshly loaded from ``state``."""
+    evaluated on our brackets -- 1e-4, no noise-scaled slack.  ``model`` must be freshly loaded from ``state``.
+    The tie window equals the forward tolerance here: through ten units the permitted forward error (1e-4 of the layer
+    maximum) is exactly what may move a pre-activation across zero, so a bracket difference inside that window is explained by
+    the forward contract and one outside it is a wrong mask."""
     from torch import nn
     units = [m for m in model.layers if not isinstance(m, nn.Dropout)]
     seen = []
