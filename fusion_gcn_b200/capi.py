@@ -47,6 +47,11 @@ SIGNATURES = {
     "agcn_bn_bwd": (_c_int, [_c_void_p] * 10 + [_c_int, _c_int, _c_int, _c_ll, _c_int, _c_void_p, _c_size_t, _c_void_p]),
     "agcn_pool_fwd": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
     "agcn_pool_bwd": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
+    "agcn_optim_chunk": (_c_int, []),
+    "agcn_optim_sgd": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_float, _c_void_p, _c_float, _c_float, _c_float, _c_int, _c_int,
+                                _c_void_p, _c_void_p, _c_void_p]),
+    "agcn_optim_adam": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_float, _c_void_p, _c_float, _c_float, _c_float, _c_float, _c_int,
+                                 _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
 }
 
 _lock = threading.Lock()

@@ -1,0 +1,113 @@
+// Multi-tensor optimizer steps: ONE launch updates every parameter tensor of a group.
+//
+// The reference builds torch.optim.{SGD, Adam, AdamW} over model.parameters() (torch_src/session_helper.py:48-82) and steps them
+// after every batch (torch_src/session/procedures/step.py:48-49), under GradScaler when --mixed_precision is set (:67-71).  The
+// AGCN model has 274 parameter tensors, most of them a few hundred floats: per-tensor kernels leave hundreds of launches of a few
+// microseconds behind the 60 ms step.  Here the tensors stay where PyTorch put them (state-dict / checkpoint layout untouched); a
+// device table of (param, grad, state1, state2, numel) rows and a list of (tensor, chunk) work items let one grid walk all of them.
+// GradScaler: torch hands optimizers that declare _step_supports_amp_scaling the device scalars `grad_scale` and `found_inf`; the
+// unscale (g / scale) and the skip-on-overflow are done here, so no host synchronisation is needed and the step is graph-capturable.
+// Arithmetic follows torch/optim/sgd.py (_single_tensor_sgd) and torch/optim/adam.py (_single_tensor_adam, capturable form).
+#include "common.cuh"
+
+namespace agcn {
+
+constexpr int kOptChunk = 4096;          // elements per work item
+constexpr int kOptThreads = 256;
+
+struct OptRow { float* p; const float* g; float* s1; float* s2; long long n; };
+
+struct SgdHyper { float lr, momentum, dampening, weight_decay; int nesterov, first; };
+struct AdamHyper { float lr, beta1, beta2, eps, weight_decay; int decoupled; };
+
+template <typename F>
+__device__ __forceinline__ void for_chunk(const OptRow& t, long long base, F f) {
+    const long long end = (base + kOptChunk < t.n) ? base + kOptChunk : t.n;
+    for (long long i = base + threadIdx.x; i < end; i += kOptThreads) f(i);
+}
+
+__global__ void __launch_bounds__(kOptThreads)
+sgd_kernel(const OptRow* __restrict__ table, const int2* __restrict__ items, SgdHyper h, const float* __restrict__ lr_dev,
+           const float* __restrict__ grad_scale, const float* __restrict__ found_inf) {
+    if (found_inf != nullptr && *found_inf != 0.f) return;          // GradScaler: skip the whole step on overflow
+    const int2 it = items[blockIdx.x];
+    const OptRow t = table[it.x];
+    const float lr = lr_dev != nullptr ? *lr_dev : h.lr;
+    const float inv_scale = grad_scale != nullptr ? 1.f / *grad_scale : 1.f;
+    for_chunk(t, (long long)it.y * kOptChunk, [&](long long i) {
+        const float p = t.p[i];
+        float g = t.g[i] * inv_scale;
+        if (h.weight_decay != 0.f) g = fmaf(h.weight_decay, p, g);
+        if (h.momentum != 0.f) {
+            float buf = h.first ? g : fmaf(h.momentum, t.s1[i], (1.f - h.dampening) * g);
+            t.s1[i] = buf;
+            g = h.nesterov ? fmaf(h.momentum, buf, g) : buf;
+        }
+        t.p[i] = fmaf(-lr, g, p);
+    });
+}
+
+__global__ void __launch_bounds__(kOptThreads)
+adam_kernel(const OptRow* __restrict__ table, const int2* __restrict__ items, AdamHyper h, const float* __restrict__ lr_dev,
+            const float* __restrict__ step_dev, const float* __restrict__ grad_scale, const float* __restrict__ found_inf) {
+    if (found_inf != nullptr && *found_inf != 0.f) return;
+    const int2 it = items[blockIdx.x];
+    const OptRow t = table[it.x];
+    const float lr = lr_dev != nullptr ? *lr_dev : h.lr;
+    const float inv_scale = grad_scale != nullptr ? 1.f / *grad_scale : 1.f;
+    const float step = *step_dev + 1.f;                              // steps completed so far + this one
+    const float bc1 = 1.f - powf(h.beta1, step);
+    const float bc2_sqrt = sqrtf(1.f - powf(h.beta2, step));
+    const float step_size = lr / bc1;
+    for_chunk(t, (long long)it.y * kOptChunk, [&](long long i) {
+        float p = t.p[i];
+        float g = t.g[i] * inv_scale;
+        if (h.decoupled) p *= 1.f - lr * h.weight_decay;            // AdamW
+        else if (h.weight_decay != 0.f) g = fmaf(h.weight_decay, p, g);
+        const float m = fmaf(h.beta1, t.s1[i], (1.f - h.beta1) * g);        // exp_avg.lerp_(grad, 1 - beta1)
+        const float v = fmaf(h.beta2, t.s2[i], (1.f - h.beta2) * g * g);
+        t.s1[i] = m;
+        t.s2[i] = v;
+        const float denom = sqrtf(v) / bc2_sqrt + h.eps;
+        t.p[i] = p - step_size * (m / denom);
+    });
+}
+
+static int check_table(const void* table, const int* items, int nitems, const char* what) {
+    AGCN_REQUIRE(table && items, AGCN_ERR_NULL, "%s: null table / work list", what);
+    AGCN_REQUIRE(nitems > 0, AGCN_ERR_BAD_SHAPE, "%s: empty work list", what);
+    AGCN_REQUIRE((reinterpret_cast<uintptr_t>(table) & 7u) == 0 && (reinterpret_cast<uintptr_t>(items) & 7u) == 0, AGCN_ERR_MISALIGNED,
+                 "%s: table / work list not 8-byte aligned", what);
+    return AGCN_OK;
+}
+
+}  // namespace agcn
+
+using namespace agcn;
+
+extern "C" AGCN_API int agcn_optim_chunk(void) { return kOptChunk; }
+
+extern "C" AGCN_API int agcn_optim_sgd(const void* table, const int* items, int nitems, float lr, const float* lr_dev,
+                                       float momentum, float dampening, float weight_decay, int nesterov, int first_step,
+                                       const float* grad_scale, const float* found_inf, void* stream) {
+    int rc = check_table(table, items, nitems, "agcn_optim_sgd");
+    if (rc) return rc;
+    AGCN_REQUIRE(!nesterov || (momentum > 0.f && dampening == 0.f), AGCN_ERR_UNSUPPORTED,
+                 "agcn_optim_sgd: Nesterov momentum requires a momentum and zero dampening");       // torch/optim/sgd.py raises the same
+    SgdHyper h{lr, momentum, dampening, weight_decay, nesterov, first_step};
+    sgd_kernel<<<nitems, kOptThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const OptRow*>(table), reinterpret_cast<const int2*>(items),
+                                                                              h, lr_dev, grad_scale, found_inf);
+    return check_launch("agcn_optim_sgd");
+}
+
+extern "C" AGCN_API int agcn_optim_adam(const void* table, const int* items, int nitems, float lr, const float* lr_dev,
+                                        float beta1, float beta2, float eps, float weight_decay, int decoupled,
+                                        const float* step_dev, const float* grad_scale, const float* found_inf, void* stream) {
+    int rc = check_table(table, items, nitems, "agcn_optim_adam");
+    if (rc) return rc;
+    AGCN_REQUIRE(step_dev != nullptr, AGCN_ERR_NULL, "agcn_optim_adam: null step counter");
+    AdamHyper h{lr, beta1, beta2, eps, weight_decay, decoupled};
+    adam_kernel<<<nitems, kOptThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const OptRow*>(table), reinterpret_cast<const int2*>(items),
+                                                                               h, lr_dev, step_dev, grad_scale, found_inf);
+    return check_launch("agcn_optim_adam");
+}

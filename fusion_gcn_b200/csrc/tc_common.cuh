@@ -195,27 +195,26 @@ __device__ __forceinline__ void bf16_split8(const float4& a, const float4& b, ui
 __device__ __forceinline__ void sts128u(uint32_t addr, const uint4& v) {
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-// One activation row of a 64-channel K chunk, in place, by a PAIR of lanes (l, l + 16) of one warp: p0 / p1 = the row in the
-// first / second 32-channel fp32 box (128 bytes each, 16-byte chunk j stored at j ^ sw), rewritten as 64 bf16 of h at p0 and 64
-// bf16 of m at p1 (chunk q = channels 8q..8q+7 at q ^ sw).  Lane half `hf` converts box hf.  Both lanes read their 128 bytes,
-// the warp synchronises, then both write -- so every fp32 chunk is read before the bf16 chunk that overwrites its bytes is
-// stored.  Must be called by all 32 lanes (inactive rows pass active = false).
-__device__ __forceinline__ void bf16_split_row_pair(uint32_t p0, uint32_t p1, uint32_t sw, int hf, bool has1, bool active) {
+// One activation row of a 64-channel K chunk, in place: p0 / p1 = the row in the first / second 32-channel fp32 box (128 bytes each,
+// 16-byte chunk j stored at j ^ sw), rewritten as 64 bf16 of h at p0 and 64 bf16 of m at p1 (chunk q = channels 8q..8q+7 at q ^ sw).
+// Every fp32 chunk is read before the bf16 chunk that overwrites its bytes is stored.
+__device__ __forceinline__ void bf16_split_row(uint32_t p0, uint32_t p1, uint32_t sw, bool has1) {
     float4 f[8];
-    uint4 hq[4], mq[4];
-    const uint32_t src = hf ? p1 : p0;
-    const bool rd = active && (hf == 0 || has1);
+    uint4 hq[4], mq[4], h2[4], m2[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = rd ? lds128(src + (((uint32_t)j ^ sw) << 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < 8; ++j) f[j] = lds128(p0 + (((uint32_t)j ^ sw) << 4));
 #pragma unroll
     for (int q = 0; q < 4; ++q) bf16_split8(f[2 * q], f[2 * q + 1], hq[q], mq[q]);
-    __syncwarp();
-    if (active) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            sts128u(p0 + (((uint32_t)(q + 4 * hf) ^ sw) << 4), hq[q]);
-            sts128u(p1 + (((uint32_t)(q + 4 * hf) ^ sw) << 4), mq[q]);
-        }
+    for (int j = 0; j < 8; ++j) f[j] = has1 ? lds128(p1 + (((uint32_t)j ^ sw) << 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) bf16_split8(f[2 * q], f[2 * q + 1], h2[q], m2[q]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        sts128u(p0 + (((uint32_t)q ^ sw) << 4), hq[q]);
+        sts128u(p0 + (((uint32_t)(q + 4) ^ sw) << 4), h2[q]);
+        sts128u(p1 + (((uint32_t)q ^ sw) << 4), mq[q]);
+        sts128u(p1 + (((uint32_t)(q + 4) ^ sw) << 4), m2[q]);
     }
 }
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {

@@ -277,15 +277,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
         for (long long c = c_begin; c < c_end; ++c) {
             mbar_wait(full_bar(stage), phase);
             const uint32_t sa = smem_base + (uint32_t)stage * raw_bytes;
-            // lanes l and l + 16 of a warp share a (pair, row): 16 tasks per warp, 128 per pass
-            const int hf = lane >> 4;
-            const int total = npairs * a.rows_box;
-            for (int base = 0; base < total; base += kWgTransformWarps * 16) {
-                const int idx = base + (tidx >> 5) * 16 + (lane & 15);
-                const int pr = idx < total ? idx / a.rows_box : 0, r = idx < total ? idx - pr * a.rows_box : 0;
-                const bool active = idx < total && ((loaded >> (2 * pr)) & 1u);
-                const uint32_t p0 = sa + (uint32_t)(2 * pr) * sub_bytes + (uint32_t)r * 128u;
-                bf16_split_row_pair(p0, p0 + sub_bytes, (uint32_t)(r & 7), hf, ((loaded >> (2 * pr + 1)) & 1u) != 0, active);
+            for (int idx = tidx; idx < npairs * a.rows_box; idx += kWgTransformWarps * 32) {
+                const int pr = idx / a.rows_box, r = idx - pr * a.rows_box;
+                if ((loaded >> (2 * pr)) & 1u) {
+                    const uint32_t p0 = sa + (uint32_t)(2 * pr) * sub_bytes + (uint32_t)r * 128u;
+                    bf16_split_row(p0, p0 + sub_bytes, (uint32_t)(r & 7), ((loaded >> (2 * pr + 1)) & 1u) != 0);
+                }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();

@@ -200,6 +200,26 @@ int agcn_bn_bwd(const float* dout, const float* mask_out, const float* y,
 int agcn_pool_fwd(const float* x, float* out, int groups, int rows_per_group, int channels, void* stream);
 int agcn_pool_bwd(const float* dout, float* dx, int groups, int rows_per_group, int channels, void* stream);
 
+/* ---- multi-tensor optimizer steps (torch_src/session_helper.py:48-82 builds torch.optim.{SGD, Adam, AdamW};
+ * torch_src/session/procedures/step.py:48-49,67-71 steps them, under GradScaler with --mixed_precision) ------------
+ * ONE launch updates every parameter tensor of a group.  `table`: device array of rows
+ *     { float* param; const float* grad; float* state1; float* state2; long long numel; }      (40 bytes each)
+ * `items`: device array of (row index, chunk index) int pairs, one per agcn_optim_chunk() elements of every tensor.
+ * lr_dev (may be NULL) overrides `lr` with a device scalar, so a captured CUDA graph follows a learning-rate schedule.
+ * grad_scale / found_inf (may be NULL) are GradScaler's device scalars: gradients are divided by *grad_scale and the
+ * whole step is skipped when *found_inf != 0 -- no host synchronisation.
+ * SGD  (torch/optim/sgd.py): g += wd*p; buf = first_step ? g : momentum*buf + (1-dampening)*g (state1);
+ *                            g = nesterov ? g + momentum*buf : buf; p -= lr*g.
+ * Adam (torch/optim/adam.py): state1 = exp_avg, state2 = exp_avg_sq, *step_dev = steps completed before this one (the caller
+ *                            increments it afterwards); decoupled != 0 is AdamW (p *= 1 - lr*wd instead of g += wd*p). */
+int agcn_optim_chunk(void);
+int agcn_optim_sgd(const void* table, const int* items, int nitems, float lr, const float* lr_dev,
+                   float momentum, float dampening, float weight_decay, int nesterov, int first_step,
+                   const float* grad_scale, const float* found_inf, void* stream);
+int agcn_optim_adam(const void* table, const int* items, int nitems, float lr, const float* lr_dev,
+                    float beta1, float beta2, float eps, float weight_decay, int decoupled,
+                    const float* step_dev, const float* grad_scale, const float* found_inf, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,134 @@
+"""-m gpu: the fused multi-tensor optimizers (fusion_gcn_b200/optim.py, agcn_optim_sgd / agcn_optim_adam) against torch.optim
+on the same parameters and gradients over several steps, with the YAML hyper-parameters the reference ships
+(config/**: SGD momentum 0.9 + nesterov + weight_decay 1e-4; ADAM weight_decay 0.01), under a learning-rate scheduler, through
+GradScaler (torch_src/session/procedures/step.py:55-78) including a skipped overflow step, and across a state_dict round trip
+with the torch classes (torch_src/progress.py:203-276 checkpoints the optimizer)."""
+import copy
+
+import pytest
+import torch
+
+from helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def O():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from fusion_gcn_b200 import capi, optim
+    capi.lib()
+    return optim
+
+
+def make_params(seed=0):
+    g = torch.Generator().manual_seed(seed)
+    shapes = [(64, 3, 1, 1), (64,), (3, 25, 25), (256, 256, 9, 1), (60, 256), (1,), (128, 64, 1, 1), (5000,)]
+    return [torch.nn.Parameter(torch.randn(*s, generator=g).cuda()) for s in shapes]
+
+
+def grads_for(params, step, seed=100):
+    g = torch.Generator().manual_seed(seed + step)
+    return [torch.randn(*p.shape, generator=g).cuda() * 0.1 for p in params]
+
+
+CASES = [
+    ("SGD", dict(lr=0.1, momentum=0.9, nesterov=True, weight_decay=1e-4)),
+    ("SGD", dict(lr=0.05, momentum=0.8, dampening=0.1)),
+    ("SGD", dict(lr=0.05)),
+    ("ADAM", dict(lr=1e-3, weight_decay=0.01)),
+    ("ADAM", dict(lr=3e-3, betas=(0.8, 0.95), eps=1e-6)),
+    ("ADAMW", dict(lr=1e-3, weight_decay=0.05)),
+]
+TORCH = {"SGD": torch.optim.SGD, "ADAM": torch.optim.Adam, "ADAMW": torch.optim.AdamW}
+
+
+@pytest.mark.parametrize("name,kw", CASES)
+def test_matches_torch_optim_with_scheduler(O, name, kw):
+    from fusion_gcn_b200 import capi
+    p_ref, p_ours = make_params(), make_params()
+    ref = TORCH[name](p_ref, **kw)
+    ours = O.FUSED_OPTIMIZERS[name](p_ours, **kw)
+    s_ref = torch.optim.lr_scheduler.MultiStepLR(ref, milestones=[2, 4], gamma=0.5)
+    s_ours = torch.optim.lr_scheduler.MultiStepLR(ours, milestones=[2, 4], gamma=0.5)
+    before = capi.lib().agcn_launch_count()
+    for step in range(6):
+        for a, b, g in zip(p_ref, p_ours, grads_for(p_ref, step)):
+            a.grad, b.grad = g.clone(), g.clone()
+        ref.step(); ours.step()
+        s_ref.step(); s_ours.step()
+    assert capi.lib().agcn_launch_count() - before == 6          # ONE launch per step for all eight tensors
+    for a, b in zip(p_ref, p_ours):
+        assert rel_err(b, a) <= 2e-6
+    sd_ref, sd_ours = ref.state_dict(), ours.state_dict()
+    assert sd_ref["param_groups"][0]["lr"] == sd_ours["param_groups"][0]["lr"]
+    for k, st in sd_ref["state"].items():
+        for key, val in st.items():
+            assert rel_err(sd_ours["state"][k][key], val) <= 2e-6, (k, key)
+
+
+@pytest.mark.parametrize("name,kw", [CASES[0], CASES[3]])
+def test_state_dict_round_trip_with_torch(O, name, kw):
+    """A checkpoint written by torch.optim loads into the fused class (and back) and training continues identically."""
+    p_ref, p_ours = make_params(1), make_params(1)
+    ref = TORCH[name](p_ref, **kw)
+    for step in range(2):
+        for a, g in zip(p_ref, grads_for(p_ref, step)):
+            a.grad = g
+        ref.step()
+    for a, b in zip(p_ref, p_ours):
+        b.data.copy_(a.data)
+    ours = O.FUSED_OPTIMIZERS[name](p_ours, **kw)
+    ours.load_state_dict(copy.deepcopy(ref.state_dict()))
+    for step in range(2, 5):
+        for a, b, g in zip(p_ref, p_ours, grads_for(p_ref, step)):
+            a.grad, b.grad = g.clone(), g.clone()
+        ref.step(); ours.step()
+    for a, b in zip(p_ref, p_ours):
+        assert rel_err(b, a) <= 2e-6
+    back = TORCH[name](make_params(1), **kw)
+    back.load_state_dict(copy.deepcopy(ours.state_dict()))          # and the fused state is a valid torch.optim state
+
+
+@pytest.mark.parametrize("name,kw", [CASES[0], CASES[3]])
+def test_gradscaler_unscale_and_overflow_skip(O, name, kw):
+    """GradScaler.step: scaled gradients are unscaled inside the kernel; a step whose gradients contain inf is skipped on the
+    device (parameters, momentum and the Adam step counter untouched) and the scale backs off -- same as torch.optim."""
+    p_ref, p_ours = make_params(2), make_params(2)
+    ref, ours = TORCH[name](p_ref, **kw), O.FUSED_OPTIMIZERS[name](p_ours, **kw)
+    sc_ref = torch.amp.GradScaler("cuda", init_scale=256.0, growth_interval=1000)
+    sc_ours = torch.amp.GradScaler("cuda", init_scale=256.0, growth_interval=1000)
+    for step in range(5):
+        gs = grads_for(p_ref, step)
+        if step == 2:
+            gs[3][0, 0, 0, 0] = float("inf")
+        for a, b, g in zip(p_ref, p_ours, gs):
+            a.grad, b.grad = g * sc_ref.get_scale(), g * sc_ours.get_scale()
+        sc_ref.step(ref); sc_ref.update()
+        sc_ours.step(ours); sc_ours.update()
+        assert sc_ref.get_scale() == sc_ours.get_scale()
+    assert sc_ours.get_scale() == 128.0
+    for a, b in zip(p_ref, p_ours):
+        assert torch.isfinite(b).all() and rel_err(b, a) <= 2e-6
+
+
+def test_training_steps_on_the_model_match_torch_sgd(O):
+    """Three optimisation steps of a small AGCN model with FusedSGD against torch.optim.SGD on an identical copy."""
+    from fusion_gcn_b200 import graph as G, modules as M
+    torch.manual_seed(0)
+    graph = G.SkeletonGraph(G.UTD_EDGES, center_joint=G.UTD_CENTER)
+    m1 = M.Model((1, 16, 20, 3), 27, graph, start_feature_size=16).cuda().train()
+    m2 = copy.deepcopy(m1)
+    kw = dict(lr=0.05, momentum=0.9, nesterov=True, weight_decay=1e-4)
+    o1, o2 = torch.optim.SGD(m1.parameters(), **kw), O.FusedSGD(m2.parameters(), **kw)
+    x = torch.randn(4, 1, 16, 20, 3, device="cuda")
+    y = torch.randint(0, 27, (4,), device="cuda")
+    lf = torch.nn.CrossEntropyLoss()
+    for _ in range(3):
+        for m, o in ((m1, o1), (m2, o2)):
+            o.zero_grad(set_to_none=True)
+            lf(m(x), y).backward()
+            o.step()
+    for (k, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert rel_err(b, a) <= 1e-5, k

@@ -62,7 +62,8 @@ def test_conv_fwd_dgrad_wgrad(K, nb, t_in, v, cin, cout, taps, stride, mode):
     assert rel_err(dx_ref, xg.grad) <= 1e-12            # the stage oracle itself is consistent with autograd
     assert rel_err(dx, xg.grad) <= tol
     (dw, db), (dw_ref, db_ref) = both("conv_wgrad", K, (dy, x), taps=taps, stride=stride, pad=pad, precision=prec)
-    assert rel_err(dw, dw_ref) <= 2.5 * tol and rel_err(db, db_ref) <= 5e-6
+    # both parity modes compute weight gradients with bf16 triple products (a leaf of the backward pass: the error does not propagate)
+    assert rel_err(dw, dw_ref) <= (5e-6 if mode == "ffma" else 4e-5) and rel_err(db, db_ref) <= 5e-6
 
 
 @pytest.mark.parametrize("mode", ["fp32", "tf32", "bf16x3"])

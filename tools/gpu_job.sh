@@ -15,6 +15,16 @@ for step in "$@"; do
     convtest)  timeout 600 python -m pytest tests/test_gpu_stages.py -m gpu -q -rf -x -k "conv" -p no:cacheprovider > gpurun_out/${tag}_convtest.log 2>&1; tail -15 gpurun_out/${tag}_convtest.log ;;
     stagetf32) python tools/bench_stage.py --tf32 > gpurun_out/${tag}_stage_tf32.log 2>&1 ;;
     smoke)     python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.log 2>&1; tail -2 gpurun_out/${tag}_smoke.log ;;
+    ncu)       # NCU_CASES="case[:flag] ..." NCU_KERNEL=regex : one --set full capture per case, raw page as CSV
+               for spec in $NCU_CASES; do
+                 c=${spec%%:*}; f=""; [ "$spec" != "$c" ] && f="--${spec#*:}"
+                 out=gpurun_out/${tag}_ncu_${c}${f#--}
+                 timeout 300 ncu --set full --clock-control none --import-source on -k regex:${NCU_KERNEL:-tc} -c 1 -f -o $out python tools/bench_stage.py $c --once $f > ${out}.log 2>&1
+                 ncu -i ${out}.ncu-rep --page raw --csv > ${out}_raw.csv 2>/dev/null; rm -f ${out}.ncu-rep
+                 tail -2 ${out}.log
+               done ;;
+    optim)     python -m pytest tests/test_gpu_optim.py -m gpu -q -rf -x -p no:cacheprovider > gpurun_out/${tag}_optim.log 2>&1; tail -8 gpurun_out/${tag}_optim.log ;;
+    pytests)   python -m pytest tests -m gpu -q -rf -s -p no:cacheprovider > gpurun_out/${tag}_pytest_s.log 2>&1; grep -E "^\[|passed|failed" gpurun_out/${tag}_pytest_s.log | tail -60 ;;
     *) echo "unknown step $step" ;;
   esac
 done
