@@ -19,6 +19,7 @@ MIX_AGG_FWD, MIX_AGG_BWD, MIX_SCORE_BWD = 0, 1, 2
 RES_NONE, RES_TENSOR, RES_AFFINE = 0, 1, 2
 
 _c_int, _c_ll, _c_float, _c_void_p, _c_size_t = ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
+_c_double = ctypes.c_double
 
 # name -> (restype, argtypes); mirrors include/agcn_b200.h one to one
 SIGNATURES = {
@@ -48,9 +49,9 @@ SIGNATURES = {
     "agcn_pool_fwd": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
     "agcn_pool_bwd": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
     "agcn_optim_chunk": (_c_int, []),
-    "agcn_optim_sgd": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_float, _c_void_p, _c_float, _c_float, _c_float, _c_int, _c_int,
+    "agcn_optim_sgd": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_double, _c_void_p, _c_double, _c_double, _c_double, _c_int, _c_int,
                                 _c_void_p, _c_void_p, _c_void_p]),
-    "agcn_optim_adam": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_float, _c_void_p, _c_float, _c_float, _c_float, _c_float, _c_int,
+    "agcn_optim_adam": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_double, _c_void_p, _c_double, _c_double, _c_double, _c_double, _c_int,
                                  _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
 }
 

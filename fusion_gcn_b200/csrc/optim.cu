@@ -17,8 +17,10 @@ constexpr int kOptThreads = 256;
 
 struct OptRow { float* p; const float* g; float* s1; float* s2; long long n; };
 
-struct SgdHyper { float lr, momentum, dampening, weight_decay; int nesterov, first; };
-struct AdamHyper { float lr, beta1, beta2, eps, weight_decay; int decoupled; };
+// hyper-parameters arrive as doubles (Python floats) and are rounded to fp32 only where torch rounds them: 1 - beta and the bias
+// corrections are formed in double first (1.f - 0.999f is 1.3e-5 away from float(1 - 0.999))
+struct SgdHyper { double lr, momentum, dampening, weight_decay; int nesterov, first; };
+struct AdamHyper { double lr, beta1, beta2, eps, weight_decay; int decoupled; };
 
 template <typename F>
 __device__ __forceinline__ void for_chunk(const OptRow& t, long long base, F f) {
@@ -32,16 +34,17 @@ sgd_kernel(const OptRow* __restrict__ table, const int2* __restrict__ items, Sgd
     if (found_inf != nullptr && *found_inf != 0.f) return;          // GradScaler: skip the whole step on overflow
     const int2 it = items[blockIdx.x];
     const OptRow t = table[it.x];
-    const float lr = lr_dev != nullptr ? *lr_dev : h.lr;
+    const float lr = lr_dev != nullptr ? *lr_dev : (float)h.lr;
     const float inv_scale = grad_scale != nullptr ? 1.f / *grad_scale : 1.f;
+    const float wd = (float)h.weight_decay, mom = (float)h.momentum, damp1 = (float)(1.0 - h.dampening);
     for_chunk(t, (long long)it.y * kOptChunk, [&](long long i) {
         const float p = t.p[i];
         float g = t.g[i] * inv_scale;
-        if (h.weight_decay != 0.f) g = fmaf(h.weight_decay, p, g);
-        if (h.momentum != 0.f) {
-            float buf = h.first ? g : fmaf(h.momentum, t.s1[i], (1.f - h.dampening) * g);
+        if (wd != 0.f) g = fmaf(wd, p, g);
+        if (mom != 0.f) {
+            float buf = h.first ? g : fmaf(mom, t.s1[i], damp1 * g);
             t.s1[i] = buf;
-            g = h.nesterov ? fmaf(h.momentum, buf, g) : buf;
+            g = h.nesterov ? fmaf(mom, buf, g) : buf;
         }
         t.p[i] = fmaf(-lr, g, p);
     });
@@ -53,24 +56,27 @@ adam_kernel(const OptRow* __restrict__ table, const int2* __restrict__ items, Ad
     if (found_inf != nullptr && *found_inf != 0.f) return;
     const int2 it = items[blockIdx.x];
     const OptRow t = table[it.x];
-    const float lr = lr_dev != nullptr ? *lr_dev : h.lr;
+    const double lr_d = lr_dev != nullptr ? (double)*lr_dev : h.lr;
     const float inv_scale = grad_scale != nullptr ? 1.f / *grad_scale : 1.f;
-    const float step = *step_dev + 1.f;                              // steps completed so far + this one
-    const float bc1 = 1.f - powf(h.beta1, step);
-    const float bc2_sqrt = sqrtf(1.f - powf(h.beta2, step));
-    const float step_size = lr / bc1;
+    const double step = (double)*step_dev + 1.0;                     // steps completed so far + this one
+    const float step_size = (float)(lr_d / (1.0 - pow(h.beta1, step)));
+    const float bc2_sqrt = (float)sqrt(1.0 - pow(h.beta2, step));
+    const float b1 = (float)h.beta1, b2 = (float)h.beta2, omb1 = (float)(1.0 - h.beta1), omb2 = (float)(1.0 - h.beta2);
+    const float wd = (float)h.weight_decay, eps = (float)h.eps, decay = (float)(1.0 - lr_d * h.weight_decay);
     for_chunk(t, (long long)it.y * kOptChunk, [&](long long i) {
         float p = t.p[i];
         float g = t.g[i] * inv_scale;
-        if (h.decoupled) p *= 1.f - lr * h.weight_decay;            // AdamW
-        else if (h.weight_decay != 0.f) g = fmaf(h.weight_decay, p, g);
-        const float m = fmaf(h.beta1, t.s1[i], (1.f - h.beta1) * g);        // exp_avg.lerp_(grad, 1 - beta1)
-        const float v = fmaf(h.beta2, t.s2[i], (1.f - h.beta2) * g * g);
+        if (h.decoupled) p *= decay;                                 // AdamW
+        else if (wd != 0.f) g = fmaf(wd, p, g);
+        const float m0 = t.s1[i];
+        const float m = fmaf(omb1, g - m0, m0);                      // exp_avg.lerp_(grad, 1 - beta1)
+        const float v = fmaf(omb2 * g, g, b2 * t.s2[i]);             // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
         t.s1[i] = m;
         t.s2[i] = v;
-        const float denom = sqrtf(v) / bc2_sqrt + h.eps;
-        t.p[i] = p - step_size * (m / denom);
+        const float denom = sqrtf(v) / bc2_sqrt + eps;
+        t.p[i] = fmaf(-step_size, m / denom, p);
     });
+    (void)b1;
 }
 
 static int check_table(const void* table, const int* items, int nitems, const char* what) {
@@ -87,12 +93,12 @@ using namespace agcn;
 
 extern "C" AGCN_API int agcn_optim_chunk(void) { return kOptChunk; }
 
-extern "C" AGCN_API int agcn_optim_sgd(const void* table, const int* items, int nitems, float lr, const float* lr_dev,
-                                       float momentum, float dampening, float weight_decay, int nesterov, int first_step,
+extern "C" AGCN_API int agcn_optim_sgd(const void* table, const int* items, int nitems, double lr, const float* lr_dev,
+                                       double momentum, double dampening, double weight_decay, int nesterov, int first_step,
                                        const float* grad_scale, const float* found_inf, void* stream) {
     int rc = check_table(table, items, nitems, "agcn_optim_sgd");
     if (rc) return rc;
-    AGCN_REQUIRE(!nesterov || (momentum > 0.f && dampening == 0.f), AGCN_ERR_UNSUPPORTED,
+    AGCN_REQUIRE(!nesterov || (momentum > 0.0 && dampening == 0.0), AGCN_ERR_UNSUPPORTED,
                  "agcn_optim_sgd: Nesterov momentum requires a momentum and zero dampening");       // torch/optim/sgd.py raises the same
     SgdHyper h{lr, momentum, dampening, weight_decay, nesterov, first_step};
     sgd_kernel<<<nitems, kOptThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const OptRow*>(table), reinterpret_cast<const int2*>(items),
@@ -100,8 +106,8 @@ extern "C" AGCN_API int agcn_optim_sgd(const void* table, const int* items, int 
     return check_launch("agcn_optim_sgd");
 }
 
-extern "C" AGCN_API int agcn_optim_adam(const void* table, const int* items, int nitems, float lr, const float* lr_dev,
-                                        float beta1, float beta2, float eps, float weight_decay, int decoupled,
+extern "C" AGCN_API int agcn_optim_adam(const void* table, const int* items, int nitems, double lr, const float* lr_dev,
+                                        double beta1, double beta2, double eps, double weight_decay, int decoupled,
                                         const float* step_dev, const float* grad_scale, const float* found_inf, void* stream) {
     int rc = check_table(table, items, nitems, "agcn_optim_adam");
     if (rc) return rc;

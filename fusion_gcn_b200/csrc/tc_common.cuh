@@ -217,6 +217,21 @@ __device__ __forceinline__ void bf16_split_row(uint32_t p0, uint32_t p1, uint32_
         sts128u(p1 + (((uint32_t)(q + 4) ^ sw) << 4), m2[q]);
     }
 }
+// One 128-byte activation row (32 fp32 channels, 16-byte chunk j stored at j ^ sw) rewritten IN PLACE as [h of the 32 channels |
+// m of the 32 channels] in bf16 (chunk q of h at q ^ sw, chunk q of m at (4 + q) ^ sw): the K-interleaved BF16x3 operand row.
+__device__ __forceinline__ void bf16_interleave_row(uint32_t p, uint32_t sw) {
+    float4 f[8];
+    uint4 hq[4], mq[4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = lds128(p + (((uint32_t)j ^ sw) << 4));
+#pragma unroll
+    for (int q = 0; q < 4; ++q) bf16_split8(f[2 * q], f[2 * q + 1], hq[q], mq[q]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        sts128u(p + (((uint32_t)q ^ sw) << 4), hq[q]);
+        sts128u(p + (((uint32_t)(q + 4) ^ sw) << 4), mq[q]);
+    }
+}
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t"

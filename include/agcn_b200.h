@@ -207,17 +207,18 @@ int agcn_pool_bwd(const float* dout, float* dx, int groups, int rows_per_group, 
  * `items`: device array of (row index, chunk index) int pairs, one per agcn_optim_chunk() elements of every tensor.
  * lr_dev (may be NULL) overrides `lr` with a device scalar, so a captured CUDA graph follows a learning-rate schedule.
  * grad_scale / found_inf (may be NULL) are GradScaler's device scalars: gradients are divided by *grad_scale and the
- * whole step is skipped when *found_inf != 0 -- no host synchronisation.
+ * whole step is skipped when *found_inf != 0 -- no host synchronisation.  Hyper-parameters are doubles (Python floats): 1 - beta
+ * and the Adam bias corrections are formed in double before they are rounded to fp32, as torch.optim does on the host.
  * SGD  (torch/optim/sgd.py): g += wd*p; buf = first_step ? g : momentum*buf + (1-dampening)*g (state1);
  *                            g = nesterov ? g + momentum*buf : buf; p -= lr*g.
  * Adam (torch/optim/adam.py): state1 = exp_avg, state2 = exp_avg_sq, *step_dev = steps completed before this one (the caller
  *                            increments it afterwards); decoupled != 0 is AdamW (p *= 1 - lr*wd instead of g += wd*p). */
 int agcn_optim_chunk(void);
-int agcn_optim_sgd(const void* table, const int* items, int nitems, float lr, const float* lr_dev,
-                   float momentum, float dampening, float weight_decay, int nesterov, int first_step,
+int agcn_optim_sgd(const void* table, const int* items, int nitems, double lr, const float* lr_dev,
+                   double momentum, double dampening, double weight_decay, int nesterov, int first_step,
                    const float* grad_scale, const float* found_inf, void* stream);
-int agcn_optim_adam(const void* table, const int* items, int nitems, float lr, const float* lr_dev,
-                    float beta1, float beta2, float eps, float weight_decay, int decoupled,
+int agcn_optim_adam(const void* table, const int* items, int nitems, double lr, const float* lr_dev,
+                    double beta1, double beta2, double eps, double weight_decay, int decoupled,
                     const float* step_dev, const float* grad_scale, const float* found_inf, void* stream);
 
 #ifdef __cplusplus

@@ -99,6 +99,8 @@ def test_gradscaler_unscale_and_overflow_skip(O, name, kw):
     ref, ours = TORCH[name](p_ref, **kw), O.FUSED_OPTIMIZERS[name](p_ours, **kw)
     sc_ref = torch.amp.GradScaler("cuda", init_scale=256.0, growth_interval=1000)
     sc_ours = torch.amp.GradScaler("cuda", init_scale=256.0, growth_interval=1000)
+    for sc in (sc_ref, sc_ours):
+        sc.scale(torch.zeros(1, device="cuda"))                    # lazily creates the device scale tensor, as a real loss would
     for step in range(5):
         gs = grads_for(p_ref, step)
         if step == 2:
@@ -131,4 +133,4 @@ def test_training_steps_on_the_model_match_torch_sgd(O):
             lf(m(x), y).backward()
             o.step()
     for (k, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):
-        assert rel_err(b, a) <= 1e-5, k
+        assert torch.allclose(b, a, rtol=1e-5, atol=1e-7), k        # (zero-gradient biases move by rounding noise only: absolute bound)
