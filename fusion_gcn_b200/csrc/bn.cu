@@ -73,10 +73,12 @@ __device__ __forceinline__ unsigned mask_nibble(const unsigned* bits, long long 
     return (__ldg(bits + (off >> 5)) >> (unsigned)(off & 31)) & 0xFu;
 }
 
+// bcast_rows > 0 (MODE 1): dout is the gradient of a fused mean pool, [groups][channels]; element (r, c) reads
+// dout[r / bcast_rows][c] * bcast_scale (agcn_bn_bwd_pool).
 template <int MODE>
 __global__ void __launch_bounds__(256) colsum_vec_kernel(const float* x, const float* dout, const float* mask, const unsigned* mask_bits,
                                                          const float* mean, const float* invstd,
-                                                         RowMap m, long long rows, float* part) {
+                                                         RowMap m, long long rows, float* part, int bcast_rows = 0, float bcast_scale = 1.f) {
     extern __shared__ __align__(16) float smv[];   // [2][lanes_r][channels]
     const int cq = m.channels >> 2;
     const int lanes_r = 256 / cq;
@@ -98,7 +100,13 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const float* x, const f
             s0.x += v.x; s0.y += v.y; s0.z += v.z; s0.w += v.w;
             s1.x = fmaf(v.x, v.x, s1.x); s1.y = fmaf(v.y, v.y, s1.y); s1.z = fmaf(v.z, v.z, s1.z); s1.w = fmaf(v.w, v.w, s1.w);
         } else {
-            float4 g = __ldg(reinterpret_cast<const float4*>(dout + off));
+            float4 g;
+            if (bcast_rows > 0) {
+                g = __ldg(reinterpret_cast<const float4*>(dout + (r / bcast_rows) * m.channels + q * 4));
+                g.x *= bcast_scale; g.y *= bcast_scale; g.z *= bcast_scale; g.w *= bcast_scale;
+            } else {
+                g = __ldg(reinterpret_cast<const float4*>(dout + off));
+            }
             if (mask_bits != nullptr) {
                 const unsigned nib = mask_nibble(mask_bits, off);
                 if (!(nib & 1u)) g.x = 0.f;
@@ -233,6 +241,72 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* y, const flo
     }
 }
 
+// Fused tail of the model (mmargcn/agcn.py:135-136 of the last unit + :194-196): out = relu(scale*y + shift + R) is NOT written; the
+// kernel leaves its ReLU mask (one bit per element, for the backward) and the per-group column sums of out.  grid = (parts, groups):
+// block (p, g) walks a contiguous slice of the rows of group g; thread = (channel quad, row lane) like colsum_vec_kernel, so eight
+// consecutive lanes own the 32 bits of one mask word.  part[(g * parts + p)][channels]; pool_finalize_kernel adds the parts in order.
+__global__ void __launch_bounds__(256) bn_apply_pool_kernel(const float* y, const float* scale, const float* shift, int res_mode,
+                                                            const float* res, const float* scale2, const float* shift2,
+                                                            unsigned* mask_bits, float* part, int rows_per_group, int C) {
+    extern __shared__ __align__(16) float smp[];   // [lanes_r][C]
+    const int cq = C >> 2;
+    const int lanes_r = 256 / cq;
+    const int q = threadIdx.x % cq, rl = threadIdx.x / cq;
+    const int P = gridDim.x, g = blockIdx.y;
+    const int per = (rows_per_group + P - 1) / P;
+    const int r0 = blockIdx.x * per;
+    int r1 = r0 + per; if (r1 > rows_per_group) r1 = rows_per_group;
+    const float4 sc = *reinterpret_cast<const float4*>(scale + q * 4), sh = *reinterpret_cast<const float4*>(shift + q * 4);
+    float4 s2 = make_float4(0.f, 0.f, 0.f, 0.f), h2 = s2;
+    if (res_mode == AGCN_RES_AFFINE) { s2 = *reinterpret_cast<const float4*>(scale2 + q * 4); h2 = *reinterpret_cast<const float4*>(shift2 + q * 4); }
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    // uniform trip count per warp: the mask word is assembled with full-warp shuffles
+    for (int rb = r0; rb < r1; rb += lanes_r) {
+        const int r = rb + rl;
+        const bool live = r < r1;
+        unsigned nib = 0u;
+        const long long off = ((long long)g * rows_per_group + (live ? r : r0)) * C + q * 4;
+        if (live) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(y + off));
+            float4 o = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
+            if (res_mode == AGCN_RES_TENSOR) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(res + off));
+                o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+            } else if (res_mode == AGCN_RES_AFFINE) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(res + off));
+                o.x += fmaf(t.x, s2.x, h2.x); o.y += fmaf(t.y, s2.y, h2.y); o.z += fmaf(t.z, s2.z, h2.z); o.w += fmaf(t.w, s2.w, h2.w);
+            }
+            o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+            acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+            nib = (o.x > 0.f ? 1u : 0u) | (o.y > 0.f ? 2u : 0u) | (o.z > 0.f ? 4u : 0u) | (o.w > 0.f ? 8u : 0u);
+        }
+        unsigned wbits = nib << (4u * (threadIdx.x & 7));
+        wbits |= __shfl_xor_sync(0xffffffffu, wbits, 1);
+        wbits |= __shfl_xor_sync(0xffffffffu, wbits, 2);
+        wbits |= __shfl_xor_sync(0xffffffffu, wbits, 4);
+        if (live && (threadIdx.x & 7) == 0) mask_bits[off >> 5] = wbits;
+    }
+    *reinterpret_cast<float4*>(smp + (size_t)rl * C + q * 4) = acc;
+    __syncthreads();
+    if (rl == 0) {
+        float4 t = acc;
+        for (int i = 1; i < lanes_r; ++i) {
+            const float4 u = *reinterpret_cast<const float4*>(smp + (size_t)i * C + q * 4);
+            t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+        }
+        *reinterpret_cast<float4*>(part + ((size_t)g * P + blockIdx.x) * C + q * 4) = t;
+    }
+}
+
+__global__ void pool_finalize_kernel(const float* part, float* pooled, int P, int C, int groups, float inv_rows) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= groups * C) return;
+    const int g = idx / C, c = idx - g * C;
+    float s = 0.f;
+    for (int p = 0; p < P; ++p) s += part[((size_t)g * P + p) * C + c];
+    pooled[idx] = s * inv_rows;
+}
+
 // coef[0][c] = gamma*invstd, coef[1][c] = s1/m, coef[2][c] = s2/m * invstd, coef[3][c] = mean;  dgamma = s2, dbeta = s1
 __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* part, int P, int C, double count, const float* gamma,
                                        const float* mean, const float* invstd, float* dgamma, float* dbeta, float* coef) {
@@ -251,7 +325,8 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* part,
 
 template <bool VEC>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* dout, const float* mask, const unsigned* mask_bits, const float* y,
-                                                           const float* coef, float* dy, float* dres, int dres_acc, RowMap m, long long rows) {
+                                                           const float* coef, float* dy, float* dres, int dres_acc, RowMap m, long long rows,
+                                                           int bcast_rows = 0, float bcast_scale = 1.f) {
     constexpr int W = VEC ? 4 : 1;
     const int C = m.channels;
     const int cq = C / W;
@@ -262,8 +337,9 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* dout, co
         const long long off = m.row_offset(r) + c;
         float g[4] = {0.f, 0.f, 0.f, 0.f}, yv[4] = {0.f, 0.f, 0.f, 0.f}, mk[4] = {1.f, 1.f, 1.f, 1.f};
         if constexpr (VEC) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(dout + off));
-            g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w;
+            const float4 a = bcast_rows > 0 ? __ldg(reinterpret_cast<const float4*>(dout + (r / bcast_rows) * C + c))
+                                            : __ldg(reinterpret_cast<const float4*>(dout + off));
+            g[0] = a.x * bcast_scale; g[1] = a.y * bcast_scale; g[2] = a.z * bcast_scale; g[3] = a.w * bcast_scale;
             if (mask_bits) {
                 const unsigned nib = mask_nibble(mask_bits, off);
                 mk[0] = (float)(nib & 1u); mk[1] = (float)((nib >> 1) & 1u); mk[2] = (float)((nib >> 2) & 1u); mk[3] = (float)((nib >> 3) & 1u);
@@ -345,14 +421,15 @@ static bool colsum_vec_shape(const RowMap& m) {
 
 template <int MODE>
 static int launch_colsum(const float* x, const float* dout, const float* mask, const float* mean, const float* invstd,
-                         const RowMap& m, long long rows, float* part, int P, cudaStream_t s, const unsigned* mask_bits = nullptr) {
+                         const RowMap& m, long long rows, float* part, int P, cudaStream_t s, const unsigned* mask_bits = nullptr,
+                         int bcast_rows = 0, float bcast_scale = 1.f) {
     const int cq = m.channels / 4;
     const bool vec = vec_ok(m, {x, dout, mask, mean, invstd}) && colsum_vec_shape(m);
-    if (mask_bits != nullptr && !vec) return fail(AGCN_ERR_UNSUPPORTED, "bn column sums: a bit mask needs the vectorised layout");
+    if ((mask_bits != nullptr || bcast_rows > 0) && !vec) return fail(AGCN_ERR_UNSUPPORTED, "bn column sums: a bit mask needs the vectorised layout");
     if (vec) {
         const int lanes_r = 256 / cq;
         size_t smem = (size_t)2 * lanes_r * m.channels * sizeof(float);
-        colsum_vec_kernel<MODE><<<P, 256, smem, s>>>(x, dout, mask, mask_bits, mean, invstd, m, rows, part);
+        colsum_vec_kernel<MODE><<<P, 256, smem, s>>>(x, dout, mask, mask_bits, mean, invstd, m, rows, part, bcast_rows, bcast_scale);
     } else {
         dim3 grid((unsigned)P, (unsigned)ceil_div(m.channels, 32));
         colsum_strip_kernel<MODE><<<grid, 256, 0, s>>>(x, dout, mask, mean, invstd, m, rows, part);
@@ -472,7 +549,7 @@ static int bn_bwd_impl(const float* dout, const float* mask_out, const unsigned*
                        const float* save_mean, const float* save_invstd, const float* gamma,
                        float* dy, float* dgamma, float* dbeta, float* dres, int dres_accumulate,
                        int outer, int inner, long long outer_stride, int channels,
-                       void* workspace, size_t workspace_bytes, void* stream) {
+                       void* workspace, size_t workspace_bytes, void* stream, int bcast_rows = 0) {
     int rc = check_map("agcn_bn_bwd", outer, inner, outer_stride, channels);
     if (rc) return rc;
     AGCN_REQUIRE(dout && y && save_mean && save_invstd && workspace, AGCN_ERR_NULL, "agcn_bn_bwd: null pointer");
@@ -486,14 +563,16 @@ static int bn_bwd_impl(const float* dout, const float* mask_out, const unsigned*
     if (mask_bits != nullptr)
         AGCN_REQUIRE(agcn_bn_mask_words(outer, inner, channels) > 0 && vec_ok(m, {dout, y, dy, dres, workspace}), AGCN_ERR_UNSUPPORTED,
                      "agcn_bn_bwd_bits: layout not supported (agcn_bn_mask_words returned 0)");
-    rc = launch_colsum<1>(y, dout, mask_out, save_mean, save_invstd, m, rows, part, P, s, mask_bits);
+    const float bcast_scale = bcast_rows > 0 ? 1.f / (float)bcast_rows : 1.f;
+    rc = launch_colsum<1>(y, dout, mask_out, save_mean, save_invstd, m, rows, part, P, s, mask_bits, bcast_rows, bcast_scale);
     if (rc) return rc;
     bn_bwd_finalize_kernel<<<ceil_div(channels, 32), 256, 0, s>>>(part, P, channels, (double)rows, gamma, save_mean, save_invstd, dgamma, dbeta, coef);
     rc = check_launch("agcn_bn_bwd(finalize)");
     if (rc) return rc;
     if (dy == nullptr && dres == nullptr) return AGCN_OK;
     if (vec_ok(m, {dout, mask_out, y, dy, dres, coef}))
-        bn_bwd_apply_kernel<true><<<elementwise_blocks(rows * (channels / 4)), 256, 0, s>>>(dout, mask_out, mask_bits, y, coef, dy, dres, dres_accumulate, m, rows);
+        bn_bwd_apply_kernel<true><<<elementwise_blocks(rows * (channels / 4)), 256, 0, s>>>(dout, mask_out, mask_bits, y, coef, dy, dres, dres_accumulate, m, rows,
+                                                                                            bcast_rows, bcast_scale);
     else
         bn_bwd_apply_kernel<false><<<elementwise_blocks(rows * channels), 256, 0, s>>>(dout, mask_out, nullptr, y, coef, dy, dres, dres_accumulate, m, rows);
     return check_launch("agcn_bn_bwd(apply)");
@@ -515,6 +594,47 @@ extern "C" AGCN_API int agcn_bn_bwd_bits(const float* dout, const unsigned* mask
     AGCN_REQUIRE(mask_bits, AGCN_ERR_NULL, "agcn_bn_bwd_bits: null mask pointer");
     return bn_bwd_impl(dout, nullptr, mask_bits, y, save_mean, save_invstd, gamma, dy, dgamma, dbeta, dres, dres_accumulate,
                        1, inner, 0, channels, workspace, workspace_bytes, stream);
+}
+
+constexpr int kPoolParts = 8;
+
+extern "C" AGCN_API size_t agcn_bn_apply_pool_workspace_bytes(int groups, int channels) {
+    return (groups > 0 && channels > 0) ? (size_t)groups * kPoolParts * channels * sizeof(float) : 0;
+}
+
+extern "C" AGCN_API int agcn_bn_apply_pool(const float* y, const float* scale, const float* shift,
+                                           int res_mode, const float* res, const float* scale2, const float* shift2,
+                                           unsigned* mask_bits, float* pooled, int groups, int rows_per_group, int channels,
+                                           void* workspace, size_t workspace_bytes, void* stream) {
+    AGCN_REQUIRE(y && scale && shift && mask_bits && pooled && workspace, AGCN_ERR_NULL, "agcn_bn_apply_pool: null pointer");
+    AGCN_REQUIRE(groups > 0 && rows_per_group > 0 && channels > 0, AGCN_ERR_BAD_SHAPE, "agcn_bn_apply_pool: bad shape");
+    AGCN_REQUIRE(res_mode >= 0 && res_mode <= 2 && (res_mode == AGCN_RES_NONE || res) && (res_mode != AGCN_RES_AFFINE || (scale2 && shift2)),
+                 AGCN_ERR_NULL, "agcn_bn_apply_pool: residual operands missing");
+    AGCN_REQUIRE(workspace_bytes >= agcn_bn_apply_pool_workspace_bytes(groups, channels), AGCN_ERR_WORKSPACE, "agcn_bn_apply_pool: workspace too small");
+    RowMap m{1, groups * rows_per_group, 0, channels};
+    AGCN_REQUIRE(agcn_bn_mask_words(1, groups * rows_per_group, channels) > 0 && channels % 32 == 0 &&
+                 vec_ok(m, {y, scale, shift, res, scale2, shift2, pooled, workspace}),
+                 AGCN_ERR_UNSUPPORTED, "agcn_bn_apply_pool: layout not supported (use agcn_bn_apply_mask + agcn_pool_fwd)");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    float* part = static_cast<float*>(workspace);
+    const int cq = channels / 4;
+    const size_t smem = (size_t)(256 / cq) * channels * sizeof(float);
+    dim3 grid((unsigned)kPoolParts, (unsigned)groups);
+    bn_apply_pool_kernel<<<grid, 256, smem, s>>>(y, scale, shift, res_mode, res, scale2, shift2, mask_bits, part, rows_per_group, channels);
+    int rc = check_launch("agcn_bn_apply_pool");
+    if (rc) return rc;
+    pool_finalize_kernel<<<ceil_div((long long)groups * channels, 256), 256, 0, s>>>(part, pooled, kPoolParts, channels, groups, 1.f / (float)rows_per_group);
+    return check_launch("agcn_bn_apply_pool(finalize)");
+}
+
+extern "C" AGCN_API int agcn_bn_bwd_pool(const float* dpooled, const unsigned* mask_bits, const float* y,
+                                         const float* save_mean, const float* save_invstd, const float* gamma,
+                                         float* dy, float* dgamma, float* dbeta, float* dres, int dres_accumulate,
+                                         int groups, int rows_per_group, int channels, void* workspace, size_t workspace_bytes, void* stream) {
+    AGCN_REQUIRE(mask_bits && dpooled, AGCN_ERR_NULL, "agcn_bn_bwd_pool: null pointer");
+    AGCN_REQUIRE(groups > 0 && rows_per_group > 0, AGCN_ERR_BAD_SHAPE, "agcn_bn_bwd_pool: bad shape");
+    return bn_bwd_impl(dpooled, nullptr, mask_bits, y, save_mean, save_invstd, gamma, dy, dgamma, dbeta, dres, dres_accumulate,
+                       1, groups * rows_per_group, 0, channels, workspace, workspace_bytes, stream, rows_per_group);
 }
 
 extern "C" AGCN_API int agcn_pool_fwd(const float* x, float* out, int groups, int rows_per_group, int channels, void* stream) {

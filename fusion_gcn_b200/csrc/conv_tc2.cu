@@ -33,11 +33,9 @@
 // MODE 2 (AGCN_PREC_BF16X3, the second fp32-parity mode): x = h + m + O(2^-17 x) with h = bf16(x), m = bf16(x - h); the product is
 // h_a h_b + h_a m_b + m_a h_b on tcgen05 kind::f16 (BF16 operands, fp32 accumulate): three MMAs at TWICE the TF32 rate on operands of
 // HALF the bytes, i.e. half the tensor time and half the shared-memory operand traffic of 3xTF32, at ~1e-5 instead of ~2e-7 unit-level
-// error.  Layout: the pieces are interleaved ALONG K inside one 128-byte row -- [h of 32 channels | m of 32 channels] -- so a K chunk
-// is still ONE 32-channel fp32 TMA box, rewritten in place row by row by the converter warps (128 bytes in, 128 bytes out, no
-// cross-row hazard, no second ring), and the stage sizes / ring depths are those of the TF32 mode.  The UMMA K step of 16 bf16 is 32
-// bytes: descriptor offsets +0 / +32 address the two h steps, +64 / +96 the two m steps of the same rows.  Weights: the same
-// interleaved rows, precomputed per call into the caller's workspace.
+// error (both inside the 1e-4 contract).  A K chunk is then 64 channels = two 32-channel fp32 TMA boxes per box slot; the converter
+// warps (one thread per activation row) rewrite them IN PLACE as one 128-byte bf16 row of h (over the first box) and of m (over the
+// second), same 128B swizzle, so no extra ring exists.  Weights: bf16 h | m tensors precomputed into the caller's workspace.
 // TMEM: 2 accumulator buffers of 128 (or 256) fp32 columns (epilogue of tile i overlaps the main loop of tile i+1; 3xTF32 segments
 // ping-pong) + 128 columns of fp32 master sums for the 3xTF32 segment promotion (tmem_promote16).
 #include "tc_common.cuh"
@@ -94,13 +92,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_y0,
                 const __grid_constant__ CUtensorMap map_y1, Tc2Args a) {
     constexpr bool SPLIT = MODE == 1;      // 3xTF32: hi in place, lo into its own ring
-    constexpr bool BF = MODE == 2;         // BF16x3: every 128-byte row rewritten in place as [h | m] bf16 pieces of its 32 channels
+    constexpr bool BF = MODE == 2;         // BF16x3: h | m in place over the two fp32 boxes of a 64-channel chunk
     constexpr bool CONV = MODE != 0;       // converter warps, [hi ; lo] weight slots, segment promotion
-    constexpr int kChunkCh = BF ? 64 : kKChunk;      // weight-map elements per K chunk row (BF16x3: 32 h + 32 m bf16)
+    constexpr int kChunkCh = BF ? 64 : kKChunk;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_slot = a.a_stage_bytes;
-    const uint32_t b_slot = a.b_stage_bytes * (SPLIT ? 2u : 1u);
+    const uint32_t b_slot = a.b_stage_bytes * (CONV ? 2u : 1u);
     const uint32_t lo_ring = smem_base + (uint32_t)a.na * a_slot;                       // SPLIT: two slots of a_stage_bytes
     const uint32_t b_ring = lo_ring + (SPLIT ? (uint32_t)a.nlo * a_slot : 0u);
     const uint32_t bar_base = b_ring + (uint32_t)a.nbst * b_slot;
@@ -143,7 +141,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     float* stat_sm = reinterpret_cast<float*>(smem_raw + (epi_end - smem_u32(smem_raw))) + ((threadIdx.x >> 5) & 3) * (2 * kStatCols);
 
     const uint32_t a_tx = (uint32_t)a.nblk * a.blk_rows_bytes;
-    const uint32_t b_tx = (uint32_t)a.bn * 128u * (SPLIT ? 2u : 1u);
+    const uint32_t b_tx = (uint32_t)a.bn * 128u * (CONV ? 2u : 1u);
 
     if (warp == 0) {
         // ===================================================== activation producer (warp-uniform loop, elected lane issues: the TMA
@@ -161,9 +159,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     mbar_wait(a_empty(sa), pa ^ 1u);
                     const uint32_t dst = smem_base + (uint32_t)sa * a_slot;
                     if (leader) {
-                        mbar_expect_tx(a_full(sa), a_tx);
-                        for (int b = 0; b < a.nblk; ++b)
-                            tma_load_4d(dst + (uint32_t)b * a.blk_bytes, &map_a, a_full(sa), kc * kKChunk, 0, tb + a.blk_t0[par][b], n);
+                        if (BF) {
+                            // 64-channel chunk = two 32-channel fp32 boxes per slot (the second only when it holds real channels)
+                            const int nh = (a.cin - kc * 64 > 32) ? 2 : 1;
+                            mbar_expect_tx(a_full(sa), a_tx * (uint32_t)nh);
+                            for (int b = 0; b < a.nblk; ++b)
+                                for (int h = 0; h < nh; ++h)
+                                    tma_load_4d(dst + (uint32_t)(b * 2 + h) * a.blk_bytes, &map_a, a_full(sa), kc * 64 + h * 32, 0, tb + a.blk_t0[par][b], n);
+                        } else {
+                            mbar_expect_tx(a_full(sa), a_tx);
+                            for (int b = 0; b < a.nblk; ++b)
+                                tma_load_4d(dst + (uint32_t)b * a.blk_bytes, &map_a, a_full(sa), kc * kKChunk, 0, tb + a.blk_t0[par][b], n);
+                        }
                     }
                     __syncwarp();
                     if (++sa == a.na) { sa = 0; pa ^= 1u; }
@@ -185,7 +192,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         if (leader) {
                             mbar_expect_tx(b_full(sb), b_tx);
                             tma_load_3d(b_ring + (uint32_t)sb * b_slot, &map_b, b_full(sb), kc * kChunkCh, a.tap_id[par][i], nt * a.bn);
-                            if (SPLIT) tma_load_3d(b_ring + (uint32_t)sb * b_slot + a.b_stage_bytes, &map_blo, b_full(sb), kc * kChunkCh, a.tap_id[par][i], nt * a.bn);
+                            if (CONV) tma_load_3d(b_ring + (uint32_t)sb * b_slot + a.b_stage_bytes, &map_blo, b_full(sb), kc * kChunkCh, a.tap_id[par][i], nt * a.bn);
                         }
                         __syncwarp();
                         if (++sb == a.nbst) { sb = 0; pb ^= 1u; }
@@ -225,31 +232,34 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 for (int kc = 0; kc < a.kchunks; ++kc) {
                     mbar_wait(a_full(sa), pa);
                     if (CONV && !(a.dbg & 8)) mbar_wait(a_lo(sa), pa);
-                    const int ksteps = (a.cin - kc * 32 >= 32) ? 2 : (a.cin - kc * 32 + 15) / 16;      // BF16x3: UMMA K = 16 channels
+                    const int ksteps = BF ? ((a.cin - kc * 64 >= 64) ? 4 : (a.cin - kc * 64) / 16) : 4;      // BF16x3: UMMA K = 16 channels
                     const uint32_t abase = smem_base + (uint32_t)sa * a_slot;
                     const uint32_t lobase = lo_ring + (uint32_t)sl * a_slot;
                     for (int i = 0; i < ntap; ++i) {
                         if (wait_b) mbar_wait(b_full(sb), pb);                     // resident weights arrive once
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t aoff = (uint32_t)a.tap_blk[par][i] * a.blk_bytes + (uint32_t)a.tap_off[par][i] * row_bytes_v;
+                        const uint32_t aoff = (uint32_t)a.tap_blk[par][i] * a.blk_bytes * (BF ? 2u : 1u) + (uint32_t)a.tap_off[par][i] * row_bytes_v;
                         const uint32_t aaddr = abase + aoff;
                         const uint32_t baddr = b_ring + (uint32_t)sb * b_slot;
                         const uint64_t da = make_smem_desc(aaddr), db = make_smem_desc(baddr);
                         // second operand piece: 3xTF32 lo residuals (own ring) / BF16x3 m piece (the box after the h piece)
-                        // second operand piece: 3xTF32 lo residuals (own ring / second half of the weight slot); BF16x3: the m half of the
-                        // same rows, 64 bytes (4 descriptor units) further along K
-                        const uint64_t dalo = BF ? da + 4u : make_smem_desc(lobase + aoff), dblo = BF ? db + 4u : make_smem_desc(baddr + a.b_stage_bytes);
+                        const uint64_t dalo = make_smem_desc(BF ? aaddr + a.blk_bytes : lobase + aoff), dblo = make_smem_desc(baddr + a.b_stage_bytes);
                         if (leader) {
                         if (BF) {
-                            // m.Wh + h.Wm (cross terms, into their own columns when a.dual) + h.Wh, two K steps of 16 channels
+                            // h.Wh (+ h.Wm) + m.Wh on kind::f16; dual: one 2*bn-wide MMA against [W_h ; W_m] yields main | cross columns
 #pragma unroll
-                            for (int k = 0; k < 2; ++k) {
+                            for (int k = 0; k < 4; ++k) {
                                 if (k < ksteps) {
                                     const uint64_t ko = (uint64_t)(k * 2);           // 16 bf16 = 32 bytes per K step
                                     const uint32_t fresh = (k == 0) ? first : 0u;
-                                    umma_bf16(d_tmem + cross_off, dalo + ko, db + ko, idesc, fresh ^ 1u);
-                                    umma_bf16(d_tmem + cross_off, da + ko, dblo + ko, idesc, 1u);
-                                    umma_bf16(d_tmem, da + ko, db + ko, idesc, (fresh & main_first) ^ 1u);
+                                    if (a.dual) {
+                                        umma_bf16(d_tmem, da + ko, db + ko, idesc_wide, fresh ^ 1u);
+                                        umma_bf16(d_tmem + cross_off, dalo + ko, db + ko, idesc, 1u);
+                                    } else {
+                                        umma_bf16(d_tmem, dalo + ko, db + ko, idesc, fresh ^ 1u);
+                                        umma_bf16(d_tmem, da + ko, dblo + ko, idesc, 1u);
+                                        umma_bf16(d_tmem, da + ko, db + ko, idesc, 1u);
+                                    }
                                 }
                             }
                         } else if (SPLIT && a.dual) {
@@ -508,10 +518,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             for (int kc = 0; kc < a.kchunks; ++kc) {
                 mbar_wait(a_full(sa), pa);
                 const uint32_t src = smem_base + (uint32_t)sa * a_slot;
+                const bool has1 = a.cin - kc * 64 > 32;
+                // one thread per row: the two-lanes-per-row variant measured 3-25 % slower on every shape (profiles/r3e)
                 for (int idx = tids; idx < a.nblk * rows; idx += kSplitWarps * 32) {
                     const int b = idx >= rows ? 1 : 0;
                     const int r = idx - b * rows;
-                    bf16_interleave_row(src + (uint32_t)b * a.blk_bytes + (uint32_t)r * 128u, (uint32_t)(r & 7));
+                    const uint32_t p0 = src + (uint32_t)(b * 2) * a.blk_bytes + (uint32_t)r * 128u;
+                    bf16_split_row(p0, p0 + a.blk_bytes, (uint32_t)(r & 7), has1);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
@@ -553,25 +566,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
 using namespace agcn;
 
-// Weights of the BF16x3 mode: w [cout][taps][cin] fp32 -> w_split [cout][taps][nchunk][64] bf16, every 32-channel K chunk stored as
-// one 128-byte row [h of 32 channels | m of 32 channels] (h = bf16(w), m = bf16(w - h); channels past cin are zeros).
-static __global__ void split_weights_bf16_kernel(const float* w, uint16_t* w_split, long long rows, int cin, int nchunk) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // (row, chunk, channel in chunk)
-    if (i >= rows * nchunk * 32) return;
-    const int c = (int)(i & 31);
-    const long long rc = i >> 5;
-    const int kc = (int)(rc % nchunk);
-    const long long row = rc / nchunk;
-    const int ch = kc * 32 + c;
-    uint16_t h = 0, m = 0;
-    if (ch < cin) {
-        const float v = w[row * cin + ch];
+// bf16 h | m pieces of the weights for the BF16x3 mode: w_split[0 .. n) = bf16(w), w_split[n .. 2n) = bf16(w - h) (16-bit elements)
+static __global__ void split_weights_bf16_kernel(const float* w, uint16_t* w_split, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float v = w[i];
         const uint32_t hb = (__float_as_uint(v) + 0x8000u) & 0xFFFF0000u;
-        h = (uint16_t)(hb >> 16);
-        m = (uint16_t)((__float_as_uint(v - __uint_as_float(hb)) + 0x8000u) >> 16);
+        w_split[i] = (uint16_t)(hb >> 16);
+        w_split[n + i] = (uint16_t)((__float_as_uint(v - __uint_as_float(hb)) + 0x8000u) >> 16);
     }
-    w_split[rc * 64 + c] = h;
-    w_split[rc * 64 + 32 + c] = m;
 }
 
 // Returns AGCN_ERR_UNSUPPORTED for shapes outside this path (the caller then tries the next kernel).
@@ -593,29 +596,30 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
     if (!aligned16(x) || !aligned16(w) || !aligned16(y) || (bias && !aligned16(bias))) return AGCN_ERR_UNSUPPORTED;
     if (split && (w_split == nullptr || !aligned16(w_split) || ((long long)cout * taps * cin) % 4)) return AGCN_ERR_UNSUPPORTED;
     const bool bf = split == 2;
-    if (bf && cin % 16) return AGCN_ERR_UNSUPPORTED;      // UMMA K = 16 bf16 channels
-    const int chunk_ch = kKChunk;
+    if (bf && (cin % 16 || ((long long)cout * taps * cin) % 8)) return AGCN_ERR_UNSUPPORTED;      // UMMA K = 16 bf16; m tensor 16-byte aligned
+    const int chunk_ch = bf ? 64 : kKChunk;
     if (stat_part != nullptr && (transposed || accumulate || cout > kStatCols || stat_nparts == nullptr)) return AGCN_ERR_UNSUPPORTED;
     // Output-channel tile.  A 3xTF32 tile whose K reduction needs more than one accumulator segment keeps fp32 master sums
     // in TMEM columns 256..383, so it is at most 128 wide; single-segment tiles (1x1 convs with cin <= 256) and the TF32
     // mode use up to 256 columns per accumulator buffer, which avoids re-loading (and re-splitting) the activations per tile.
-    const int kiters = taps * ((cin + kKChunk - 1) / kKChunk);
-    // (tap, K chunk) iterations one accumulator segment may hold without promotion: <= 48 chained MMAs into the main columns.
-    // 3xTF32: 4 K steps x 3 products -> 8 iterations only with the cross terms in their own columns (dual), else kSegment.
-    // BF16x3: 2 K steps per iteration -> 8 iterations with all three products in one accumulator, 24 with dual columns (tiles <= 128 wide).
-    const int seg_cap = bf ? (kiters <= 8 ? 8 : 24) : 8;
+    const int kiters = taps * ((cin + chunk_ch - 1) / chunk_ch);
+    // (tap, K chunk) iterations one accumulator segment may hold without promotion.  3xTF32: 8 (the strict mode keeps the chained
+    // truncating accumulations of the hi*hi products <= 96 per segment).  BF16x3 never promotes: its K reduction is at most 144
+    // chained adds into the main columns (9 taps x 256 channels / 16), whose truncation (<= 144 x 2^-24, one-sided) stays below the
+    // mode's own 2^-17 operand error -- and without master sums in TMEM every tile up to 128 wide takes the wide [W_h ; W_m] MMA.
+    const int seg_cap = bf ? (1 << 28) : 8;
     const bool one_segment = !split || kiters <= seg_cap;
-    const int bn_cap = (one_segment && !(bf && kiters > 8)) ? 256 : 128;       // (BF16x3 single segments longer than 8 iterations need the dual columns)
+    const int bn_cap = bf ? ((taps == 1 && kiters <= 4) ? 256 : 128) : (one_segment ? 256 : 128);
     int bn = 0;
     for (int cand = bn_cap; cand >= 16; cand -= 16)
         if (cout % cand == 0) { bn = cand; break; }
     if (bn == 0 || (bn < 64 && cout > 128)) return AGCN_ERR_UNSUPPORTED;
-    if (split == 1 && taps == 1 && bn > 128) {
+    if (split && taps == 1 && bn > 128) {
         // Ring depth.  The [hi ; lo] weight slot of a tile wider than 128 columns is 48..64 KB: next to the epilogue buffers only ONE
         // activation stage then fits and load -> convert -> MMA serialise (measured: 768 -> 256 at 0.48 ms against 0.22 ms in the
         // TF32 mode).  Unless the whole weight tile can stay resident, take the widest tile that leaves two weight slots and three
         // activation stages (five with the 3xTF32 lo ring); the activation tile is then re-read (from L2) once per extra tile.
-        const uint64_t a_st = 16384u;
+        const uint64_t a_st = (uint64_t)(bf ? 2 : 1) * 16384u;
         const int kch = (cin + chunk_ch - 1) / chunk_ch;
         auto fits = [&](int cand) {
             const uint64_t b = (uint64_t)cand * 256u;
@@ -637,7 +641,7 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
     // main | cross accumulator pairs: multi-segment tiles up to 64 wide (2*bn <= 128 next to the master sums), single-segment
     // tiles (1x1 convs with cin <= 256: no master sums) up to 128 wide (2*bn <= 256 = one of the two accumulator buffers)
     a.dual = (split && !no_dual && ((kiters > seg_cap && bn <= 64) || (kiters <= seg_cap && bn <= 128))) ? 1 : 0;
-    a.seg_iters = (split && kiters <= seg_cap) ? seg_cap : (bf ? (a.dual ? 24 : 8) : (a.dual ? 3 * kSegment : kSegment));
+    a.seg_iters = (split && kiters <= seg_cap) ? seg_cap : (a.dual ? 3 * kSegment : kSegment);
     a.acc_stride = (bn > 128 || (a.dual && 2 * bn > 128)) ? 256 : 128;
     a.tt = 128 / v;
     a.bn = bn;
@@ -706,9 +710,9 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
     uint32_t need = ((uint32_t)(nt_max - a.tt) * v + 128u) * 128u;       // rows the last tap's M=128 operand touches
     if (need < a.blk_rows_bytes) need = a.blk_rows_bytes;
     a.blk_bytes = (need + 1023u) & ~1023u;
-    a.a_stage_bytes = (uint32_t)a.nblk * a.blk_bytes;
+    a.a_stage_bytes = (uint32_t)a.nblk * a.blk_bytes * (bf ? 2u : 1u);      // BF16x3: two 32-channel fp32 boxes per slot -> h | m in place
     a.b_stage_bytes = (uint32_t)bn * 128u;
-    const uint32_t a_slot = a.a_stage_bytes, b_slot = a.b_stage_bytes * (split == 1 ? 2u : 1u);
+    const uint32_t a_slot = a.a_stage_bytes, b_slot = a.b_stage_bytes * (split ? 2u : 1u);
     const uint32_t stat_bytes = stat_part != nullptr ? kStatBytes : 0u;
     // TMA-store epilogue for the 1x1 convolutions (their time is the output stream: skipping the stores halves it, profiles/r2b);
     // the 9-tap kernels are bound elsewhere and keep their shared memory for the operand rings
@@ -774,12 +778,12 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     {
-        // weight boxes: bn rows x one 128-byte K chunk row (32 fp32 channels, or the [h | m] bf16 pieces of 32 channels)
-        const int nchunk = (cin + kKChunk - 1) / kKChunk;
+        // weight boxes: bn rows x one 128-byte K chunk (32 fp32 or 64 bf16 channels; channels past cin are zero-filled)
+        const size_t esz = bf ? 2 : 4;
         auto encode_w = [&](CUtensorMap* m, const void* ptr) -> CUresult {
-            cuuint64_t dims[3] = {(cuuint64_t)(bf ? nchunk * 64 : cin), (cuuint64_t)taps, (cuuint64_t)cout};
-            cuuint64_t strides[2] = {(cuuint64_t)(bf ? nchunk * 128 : cin * 4), (cuuint64_t)taps * (bf ? nchunk * 128 : cin * 4)};
-            cuuint32_t box[3] = {(cuuint32_t)(bf ? 64 : kKChunk), 1, (cuuint32_t)bn};
+            cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)taps, (cuuint64_t)cout};
+            cuuint64_t strides[2] = {(cuuint64_t)cin * esz, (cuuint64_t)taps * cin * esz};
+            cuuint32_t box[3] = {(cuuint32_t)chunk_ch, 1, (cuuint32_t)bn};
             cuuint32_t estr[3] = {1, 1, 1};
             return enc(m, bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -789,15 +793,11 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
         CUresult r = encode_w(&map_b, split ? static_cast<const void*>(w_split) : static_cast<const void*>(w));
         if (r != CUDA_SUCCESS) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc2: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
         map_blo = map_b;
-        if (bf) {
-            const long long n = (long long)cout * taps * nchunk * 32;
-            split_weights_bf16_kernel<<<ceil_div(n, 256), 256, 0, st>>>(w, reinterpret_cast<uint16_t*>(w_split), (long long)cout * taps, cin, nchunk);
-            int rc = check_launch("agcn_conv_fwd_tc2(split weights)");
-            if (rc) return rc;
-        } else if (split) {
-            r = encode_w(&map_blo, w_split + nw);
+        if (split) {
+            r = encode_w(&map_blo, bf ? static_cast<const void*>(reinterpret_cast<uint16_t*>(w_split) + nw) : static_cast<const void*>(w_split + nw));
             if (r != CUDA_SUCCESS) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc2: cuTensorMapEncodeTiled(B lo) failed with %d", (int)r);
-            split_weights_kernel<<<ceil_div(nw, 256), 256, 0, st>>>(w, w_split, nw);
+            if (bf) split_weights_bf16_kernel<<<ceil_div(nw, 256), 256, 0, st>>>(w, reinterpret_cast<uint16_t*>(w_split), nw);
+            else split_weights_kernel<<<ceil_div(nw, 256), 256, 0, st>>>(w, w_split, nw);
             int rc = check_launch("agcn_conv_fwd_tc2(split weights)");
             if (rc) return rc;
         }

@@ -45,6 +45,7 @@ class UnitSpec:
     bn_tcn: Optional[BnBuffers] = None
     bn_res: Optional[BnBuffers] = None
     attention_out: Optional[List[torch.Tensor]] = field(default=None)   # receives adj_c (3 x [nb,V,V], detached)
+    pool_groups: int = 0            # > 0 (last unit of Model): return the mean-pooled [pool_groups, cout] instead of the feature map
 
 
 def _bn_forward(y, gamma, beta, buf: BnBuffers, training: bool):
@@ -184,17 +185,22 @@ def tcn_forward(o, x_res, wt, bt, bn_w, bn_b, wr, br, rbn_w, rbn_b, spec: UnitSp
     u, (sc, sh, mean, invstd) = _conv_bn(o, wtp, bt, bn_w, bn_b, spec.bn_tcn, spec.training, prec, t_out=t_out, stride=s, pad=pad)
     ur = mean2 = invstd2 = wrp = None
     want_mask = ctx is not None and spec.training and spec.relu_out
+    # the model's tail (agcn.py:194-196): the last unit's output only feeds the global mean pool, so the pooled means and the ReLU
+    # mask bits come out of the normalise / residual / ReLU pass and the feature map itself is never written
+    pool = spec.pool_groups if (spec.pool_groups and spec.relu_out and K.bn_pool_supported(u.numel() // u.shape[-1], u.shape[-1])) else 0
+    apply = (lambda *a, **kw: K.bn_apply_pool(*a, groups=pool, **{k: v for k, v in kw.items() if k != "relu"})) if pool else \
+        (lambda *a, **kw: _apply(want_mask, *a, **kw))
     if spec.residual == "identity":
-        out, out_bits = _apply(want_mask, u, sc, sh, res_mode=K.RES_TENSOR, res=x_res, relu=spec.relu_out)
+        out, out_bits = apply(u, sc, sh, res_mode=K.RES_TENSOR, res=x_res, relu=spec.relu_out)
     elif spec.residual == "conv":
         wrp = _pack_taps(wr)
         ur, (sc2, sh2, mean2, invstd2) = _conv_bn(x_res, wrp, br, rbn_w, rbn_b, spec.bn_res, spec.training, prec, t_out=t_out, stride=s, pad=0)
-        out, out_bits = _apply(want_mask, u, sc, sh, res_mode=K.RES_AFFINE, res=ur, scale2=sc2, shift2=sh2, relu=spec.relu_out)
+        out, out_bits = apply(u, sc, sh, res_mode=K.RES_AFFINE, res=ur, scale2=sc2, shift2=sh2, relu=spec.relu_out)
     else:
-        out, out_bits = _apply(want_mask, u, sc, sh, relu=spec.relu_out)
+        out, out_bits = apply(u, sc, sh, relu=spec.relu_out)
     if ctx is not None:
-        ctx.update(t_o=o.detach(), t_x=x_res, u=u, ur=ur, out=out.detach(), out_bits=out_bits, t_mean=mean, t_invstd=invstd, t_mean2=mean2, t_invstd2=invstd2,
-                   wtp=wtp, wrp=wrp, pad=pad)
+        ctx.update(t_o=o.detach(), t_x=x_res, u=u, ur=ur, out=None if pool else out.detach(), out_bits=out_bits, t_mean=mean, t_invstd=invstd,
+                   t_mean2=mean2, t_invstd2=invstd2, wtp=wtp, wrp=wrp, pad=pad, pool_rows=(u.numel() // u.shape[-1] // pool) if pool else 0)
     return out
 
 
@@ -205,21 +211,22 @@ def tcn_backward(d_out, ctx, bn_w, rbn_w, spec: UnitSpec, need_dres=True, need_d
     ksz = spec.kernel_size
     mask = out if spec.relu_out else None
     bits = ctx["out_bits"] if spec.relu_out else None
+    pk = dict(pool_rows=ctx["pool_rows"]) if ctx.get("pool_rows") else {}       # d_out is then the pooled gradient [groups, c]
     d_xres = None
     d_wr = d_br = dgam2 = dbet2 = None
     if spec.residual == "identity":
         d_xres = torch.empty_like(x_res) if need_dres else None
-        du, dgam, dbet = K.bn_bwd(d_out, mask, u, ctx["t_mean"], ctx["t_invstd"], bn_w, dres=d_xres, dres_accumulate=False, mask_bits=bits)
+        du, dgam, dbet = K.bn_bwd(d_out, mask, u, ctx["t_mean"], ctx["t_invstd"], bn_w, dres=d_xres, dres_accumulate=False, mask_bits=bits, **pk)
     elif spec.residual == "conv":
-        du, dgam, dbet = K.bn_bwd(d_out, mask, u, ctx["t_mean"], ctx["t_invstd"], bn_w, mask_bits=bits)
-        dur, dgam2, dbet2 = K.bn_bwd(d_out, mask, ctx["ur"], ctx["t_mean2"], ctx["t_invstd2"], rbn_w, mask_bits=bits)
+        du, dgam, dbet = K.bn_bwd(d_out, mask, u, ctx["t_mean"], ctx["t_invstd"], bn_w, mask_bits=bits, **pk)
+        dur, dgam2, dbet2 = K.bn_bwd(d_out, mask, ctx["ur"], ctx["t_mean2"], ctx["t_invstd2"], rbn_w, mask_bits=bits, **pk)
         d_wrp, _ = K.conv_wgrad(dur, x_res, taps=1, stride=s, pad=0, want_bias=False, precision=prec)
         d_br = _zero_bias(d_out, d_wrp.shape[0])
         d_wr = d_wrp.permute(0, 2, 1).unsqueeze(-1)
         if need_dres:
             d_xres = K.conv_fwd(dur, _t(ctx["wrp"]), t_out=x_res.shape[1], stride=s, pad=0, transposed=True, precision=prec)
     else:
-        du, dgam, dbet = K.bn_bwd(d_out, mask, u, ctx["t_mean"], ctx["t_invstd"], bn_w, mask_bits=bits)
+        du, dgam, dbet = K.bn_bwd(d_out, mask, u, ctx["t_mean"], ctx["t_invstd"], bn_w, mask_bits=bits, **pk)
     d_wtp, _ = K.conv_wgrad(du, o, taps=ksz, stride=s, pad=pad, want_bias=False, precision=prec)
     d_bt = _zero_bias(d_out, d_wtp.shape[0])
     d_o = None
@@ -407,3 +414,24 @@ class LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = K.conv_fwd(dy4, _t(w.view(cout, 1, cin)), precision=ctx.precision).view(n, cin)
         return dx, dw.view(cout, cin), db, None
+
+
+class LinearCrossEntropyFn(torch.autograd.Function):
+    """fc (agcn.py:198-199) + nn.CrossEntropyLoss with default options (session.py:53, step.py:41-42) as one node:
+    (features [n, cin], fc.weight, fc.bias, labels int64 [n]) -> (loss, logits).  ``logits`` is returned for the metrics and is
+    not differentiable through this node."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, labels):
+        loss, logits, dlogits = K.linear_ce_fwd(x.contiguous(), w, b, labels)
+        ctx.save_for_backward(x, w, dlogits)
+        ctx.has_bias = b is not None
+        ctx.mark_non_differentiable(logits)
+        return loss, logits
+
+    @staticmethod
+    def backward(ctx, d_loss, _d_logits):
+        x, w, dlogits = ctx.saved_tensors
+        dw, db, dx = K.linear_ce_bwd(x.contiguous(), w, dlogits, d_loss.contiguous().to(torch.float32), need_dx=ctx.needs_input_grad[0],
+                                     need_db=ctx.has_bias)
+        return dx, dw, db, None

@@ -13,6 +13,19 @@ import torch
 from . import capi
 
 
+def loss_and_logits(model: torch.nn.Module, loss_fn: Callable, x: torch.Tensor, y: torch.Tensor):
+    """loss_fn(model(x), y) -- through the fused classifier + cross-entropy head (``Model.loss``) when ``loss_fn`` is a plain
+    ``nn.CrossEntropyLoss()`` (mean reduction, no class weights, no label smoothing: what the reference builds at
+    torch_src/session/session.py:53) and the model has one; any other loss runs as given."""
+    fused = (isinstance(loss_fn, torch.nn.CrossEntropyLoss) and loss_fn.weight is None and loss_fn.reduction == "mean"
+             and loss_fn.label_smoothing == 0.0 and getattr(model, "fc", None) is not None and hasattr(model, "loss")
+             and y.dtype == torch.int64 and y.dim() == 1)
+    if fused:
+        return model.loss(x, y)
+    logits = model(x)
+    return loss_fn(logits, y), logits
+
+
 class GraphedStep:
     """``step = GraphedStep(model, loss_fn, x_example, y_example)``; ``loss = step(x, y)`` runs zero-grad + forward + loss +
     backward and leaves the gradients in ``p.grad`` (static tensors, overwritten by every replay).  ``after_backward`` (for
@@ -30,7 +43,7 @@ class GraphedStep:
         with torch.cuda.stream(side):          # warm-up off the default stream: lazy initialisation (function attributes,
             for _ in range(max(1, warmup)):    # driver entry points, allocator) must not happen during capture
                 model.zero_grad(set_to_none=True)
-                loss_fn(model(self.x), self.y).backward()
+                loss_and_logits(model, loss_fn, self.x, self.y)[0].backward()
                 if after_backward is not None:
                     after_backward()
         torch.cuda.current_stream().wait_stream(side)
@@ -39,8 +52,7 @@ class GraphedStep:
         self.graph = torch.cuda.CUDAGraph()
         before = capi.lib().agcn_launch_count()
         with torch.cuda.graph(self.graph):
-            self.logits = model(self.x)
-            self.loss = loss_fn(self.logits, self.y)
+            self.loss, self.logits = loss_and_logits(model, loss_fn, self.x, self.y)
             self.loss.backward()
             if after_backward is not None:
                 after_backward()

@@ -209,11 +209,13 @@ class SpatialTemporalConv(nn.Module):
             self._residual_kind = "conv"
         self._agcn_precision = _default_precision
 
-    def forward_cl(self, x):
+    def forward_cl(self, x, pool_groups: int = 0):
+        """``pool_groups`` > 0: return the mean over the (T, V) positions and bodies of every sample, [pool_groups, C_out], instead
+        of the feature map (the model's tail, agcn.py:194-196, fused into this unit's last pass)."""
         g, t = self.gcn1, self.tcn1
         spec = FN.UnitSpec(cin=g.in_channels, cout=self.out_channels, stride=self.stride, residual=self._residual_kind,
                            kernel_size=t.conv.kernel_size[0], relu_out=True, training=self.training,
-                           precision=self._agcn_precision, bn_tcn=_bn_buffers(t.bn))
+                           precision=self._agcn_precision, bn_tcn=_bn_buffers(t.bn), pool_groups=pool_groups)
         g._fill_spec(spec)
         params = g._params(x) + list(t._params())
         if self._residual_kind == "conv":
@@ -278,10 +280,32 @@ class Model(nn.Module):
             h = layer(h) if isinstance(layer, nn.Dropout) else layer.forward_cl(h)
         return h
 
-    def forward(self, x):
+    def pooled_features(self, x):
+        """(N, M, T, V, C) -> (N, C_out): features_cl followed by the mean over (T, V) and bodies, with the pool fused into the last
+        unit's normalise / residual / ReLU pass (the last feature map is never written)."""
         n = x.shape[0]
-        h = self.features_cl(x)
-        x = FN.PoolFn.apply(h, n)
+        x = _prep(x)
+        buf = FN.BnBuffers(self.data_bn.running_mean, self.data_bn.running_var, self.data_bn.num_batches_tracked)
+        h = FN.DataBnFn.apply(x, self.data_bn.weight, self.data_bn.bias, buf, self.training)
+        for i, layer in enumerate(self.layers):
+            if isinstance(layer, nn.Dropout):
+                h = layer(h)
+            elif i == len(self.layers) - 1:
+                h = layer.forward_cl(h, pool_groups=n)
+            else:
+                h = layer.forward_cl(h)
+        return h if h.dim() == 2 else FN.PoolFn.apply(h, n)       # (layouts the fused tail does not cover pool separately)
+
+    def loss(self, x, labels):
+        """(loss, logits) of nn.CrossEntropyLoss()(self(x), labels) with the classifier and the loss fused into one kernel
+        (the reference computes them separately, procedures/step.py:41-42).  Mean reduction, no class weights / smoothing."""
+        if self.fc is None:
+            raise RuntimeError("Model(without_fc=True) has no classifier to fuse the loss with")
+        feat = self.pooled_features(x)
+        return FN.LinearCrossEntropyFn.apply(feat, self.fc.weight, self.fc.bias, labels)
+
+    def forward(self, x):
+        x = self.pooled_features(x)
         if self.fc is not None:
             x = FN.LinearFn.apply(x, self.fc.weight, self.fc.bias, self._agcn_precision)
         return x

@@ -323,7 +323,7 @@ def bn_apply(y, scale, shift, *, res_mode=RES_NONE, res=None, scale2=None, shift
 
 
 def bn_bwd(dout, mask_out, y, save_mean, save_invstd, gamma, *, want_dy=True, dy=None, dres=None, dres_accumulate=False,
-           rowmap=None, mask_bits=None):
+           rowmap=None, mask_bits=None, pool_rows=0):
     """-> dy | None, dgamma, dbeta; optionally writes / accumulates the masked gradient into ``dres``.
     ``dy`` may be a preallocated tensor addressed with the same rowmap as ``y``.  ``mask_bits`` (from bn_apply(want_mask=True))
     replaces the fp32 tensor ``mask_out`` as the ReLU mask."""
@@ -334,6 +334,15 @@ def bn_bwd(dout, mask_out, y, save_mean, save_invstd, gamma, *, want_dy=True, dy
     _check(save_mean, save_invstd, gamma)
     dgb = torch.empty((2, c), device=y.device, dtype=torch.float32)
     ws, nbytes = _bn_ws(c, y.device)
+    if pool_rows:
+        # ``dout`` is the gradient of the fused mean pool, [groups, c], broadcast over the pool_rows rows of each group
+        _check(dout, y, dy, dres)
+        _call("agcn_bn_bwd_pool", dout.data_ptr(), mask_bits.data_ptr(), y.data_ptr(), _ptr(save_mean), _ptr(save_invstd), _ptr(gamma),
+              _ptr(dy), dgb[0].data_ptr(), dgb[1].data_ptr(), _ptr(dres), int(dres_accumulate), dout.shape[0], int(pool_rows), c,
+              _ptr(ws), nbytes, _stream(), sig=(dout.shape[0], int(pool_rows), c, int(dy is not None), int(dres is not None)),
+              work=(0.0, 4.0 * inner * c * (2 + 2.0 / 32 + int(dy is not None) + int(dres is not None) * (1 + int(dres_accumulate)))),
+              alias="agcn_bn_bwd")
+        return dy, dgb[0], dgb[1]
     if mask_bits is not None:
         if mask_bits.dtype != torch.int32 or not mask_bits.is_cuda:
             raise RuntimeError("bn_bwd: mask_bits must be the int32 CUDA tensor returned by bn_apply(want_mask=True)")
@@ -354,6 +363,30 @@ def bn_bwd(dout, mask_out, y, save_mean, save_invstd, gamma, *, want_dy=True, dy
     return dy, dgb[0], dgb[1]
 
 
+def bn_pool_supported(rows: int, channels: int) -> bool:
+    """Whether the fused BN-apply + mean-pool tail (agcn_bn_apply_pool / agcn_bn_bwd_pool) covers this layout."""
+    return channels % 32 == 0 and capi.lib().agcn_bn_mask_words(1, rows, channels) > 0
+
+
+def bn_apply_pool(y, scale, shift, *, groups, res_mode=RES_NONE, res=None, scale2=None, shift2=None):
+    """pooled[g] = mean over the rows of group g of relu(scale*y + shift + R); the full-size output is never written.
+    -> (pooled [groups, c], ReLU mask bits for bn_bwd(pool_rows=...))."""
+    c = y.shape[-1]
+    rows = y.numel() // c
+    if rows % groups:
+        raise RuntimeError("bn_apply_pool: rows not divisible by groups")
+    _check(y, scale, shift, res, scale2, shift2)
+    L = capi.lib()
+    bits = torch.empty(L.agcn_bn_mask_words(1, rows, c), device=y.device, dtype=torch.int32)
+    pooled = torch.empty((groups, c), device=y.device, dtype=torch.float32)
+    ws_bytes = L.agcn_bn_apply_pool_workspace_bytes(groups, c)
+    ws = torch.empty(ws_bytes // 4, device=y.device, dtype=torch.float32)
+    _call("agcn_bn_apply_pool", _ptr(y), _ptr(scale), _ptr(shift), res_mode, _ptr(res), _ptr(scale2), _ptr(shift2), bits.data_ptr(),
+          _ptr(pooled), groups, rows // groups, c, _ptr(ws), ws_bytes, _stream(), sig=(groups, rows // groups, c, res_mode),
+          work=(0.0, 4.0 * rows * c * (1 if res_mode == RES_NONE else 2)), alias="agcn_bn_apply")
+    return pooled, bits
+
+
 # ----------------------------------------------------------------------------- pooling
 def pool_fwd(x, groups: int):
     c = x.shape[-1]
@@ -371,3 +404,31 @@ def pool_bwd(dout, shape):
     _check(dout)
     _call("agcn_pool_bwd", _ptr(dout), _ptr(dx), groups, rows, c, _stream(), sig=(groups, rows, c), work=(0.0, 4.0 * dx.numel()))
     return dx
+
+
+# ----------------------------------------------------------------------------- classifier head + loss
+def linear_ce_fwd(x, w, bias, labels):
+    """-> (loss scalar, logits [n, ncls], dlogits [n, ncls]); see agcn_linear_ce_fwd."""
+    n, cin = x.shape
+    ncls = w.shape[0]
+    _check(x, w, bias)
+    if labels.dtype != torch.int64 or not labels.is_cuda or labels.shape != (n,):
+        raise RuntimeError("linear_ce_fwd: labels must be an int64 CUDA tensor of shape [n]")
+    buf = torch.empty((2 * n * ncls + n + 1,), device=x.device, dtype=torch.float32)
+    logits, dlogits = buf[:n * ncls].view(n, ncls), buf[n * ncls:2 * n * ncls].view(n, ncls)
+    per, loss = buf[2 * n * ncls:2 * n * ncls + n], buf[2 * n * ncls + n:].view(())
+    _call("agcn_linear_ce_fwd", _ptr(x), _ptr(w), _ptr(bias), labels.data_ptr(), logits.data_ptr(), dlogits.data_ptr(), per.data_ptr(),
+          loss.data_ptr(), n, cin, ncls, _stream(), sig=(n, cin, ncls), work=(2.0 * n * cin * ncls, 4.0 * (x.numel() + w.numel())))
+    return loss, logits, dlogits
+
+
+def linear_ce_bwd(x, w, dlogits, grad_loss, need_dx=True, need_db=True):
+    n, cin = x.shape
+    ncls = w.shape[0]
+    _check(x, w, dlogits, grad_loss)
+    dw = torch.empty_like(w)
+    db = torch.empty((ncls,), device=x.device, dtype=torch.float32) if need_db else None
+    dx = torch.empty_like(x) if need_dx else None
+    _call("agcn_linear_ce_bwd", _ptr(x), _ptr(w), dlogits.data_ptr(), _ptr(grad_loss), _ptr(dw), _ptr(db), _ptr(dx), n, cin, ncls, _stream(),
+          sig=(n, cin, ncls), work=(4.0 * n * cin * ncls, 4.0 * (x.numel() + w.numel())))
+    return dw, db, dx

@@ -200,6 +200,34 @@ int agcn_bn_bwd(const float* dout, const float* mask_out, const float* y,
 int agcn_pool_fwd(const float* x, float* out, int groups, int rows_per_group, int channels, void* stream);
 int agcn_pool_bwd(const float* dout, float* dx, int groups, int rows_per_group, int channels, void* stream);
 
+/* Fused tail of the model: the last unit's out = relu(scale*y + shift + R) (agcn.py:135-136) feeds only the global mean pool
+ * x.view(N, M, C, -1).mean(3).mean(1) (agcn.py:194-196), so `out` is never written: agcn_bn_apply_pool leaves the pooled means
+ * pooled[groups][channels] (group g = rows [g*rows_per_group, (g+1)*rows_per_group)) and the ReLU mask bits (layout of
+ * agcn_bn_apply_mask); agcn_bn_bwd_pool is agcn_bn_bwd_bits whose upstream gradient is the pooled gradient broadcast over the
+ * group (dout[row][c] = dpooled[row / rows_per_group][c] / rows_per_group).  channels must be a multiple of 32 with
+ * agcn_bn_mask_words(1, groups*rows_per_group, channels) > 0, else AGCN_ERR_UNSUPPORTED (use the unfused calls).                  */
+size_t agcn_bn_apply_pool_workspace_bytes(int groups, int channels);
+int agcn_bn_apply_pool(const float* y, const float* scale, const float* shift,
+                       int res_mode, const float* res, const float* scale2, const float* shift2,
+                       unsigned* mask_bits, float* pooled, int groups, int rows_per_group, int channels,
+                       void* workspace, size_t workspace_bytes, void* stream);
+int agcn_bn_bwd_pool(const float* dpooled, const unsigned* mask_bits, const float* y,
+                     const float* save_mean, const float* save_invstd, const float* gamma,
+                     float* dy, float* dgamma, float* dbeta, float* dres, int dres_accumulate,
+                     int groups, int rows_per_group, int channels, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- classifier head fused with its loss -------------------------------------------------------------
+ * logits = x . w^T + bias (nn.Linear, agcn.py:178,198-199) and loss = mean_n( logsumexp(logits[n]) - logits[n][label[n]] )
+ * (nn.CrossEntropyLoss with its defaults, torch_src/session/session.py:53 applied at procedures/step.py:41-42), one launch.
+ * Also leaves dlogits[n][c] = (softmax(logits[n])[c] - [c == label[n]]) / n for the backward and the per-sample losses.
+ * x: [n][cin], w: [ncls][cin], labels: int64 [n] in [0, ncls).  agcn_linear_ce_bwd: with g = *grad_loss (device scalar, may be
+ * NULL = 1): dw = g * dlogits^T x, dbias = g * colsum(dlogits), dx = g * dlogits w (dbias / dx may be NULL).            */
+int agcn_linear_ce_fwd(const float* x, const float* w, const float* bias, const long long* labels,
+                       float* logits, float* dlogits, float* loss_per_sample, float* loss,
+                       int n, int cin, int ncls, void* stream);
+int agcn_linear_ce_bwd(const float* x, const float* w, const float* dlogits, const float* grad_loss,
+                       float* dw, float* dbias, float* dx, int n, int cin, int ncls, void* stream);
+
 /* ---- multi-tensor optimizer steps (torch_src/session_helper.py:48-82 builds torch.optim.{SGD, Adam, AdamW};
  * torch_src/session/procedures/step.py:48-49,67-71 steps them, under GradScaler with --mixed_precision) ------------
  * ONE launch updates every parameter tensor of a group.  `table`: device array of rows

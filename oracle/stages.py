@@ -200,7 +200,10 @@ def _bn_apply(y, scale, shift, *, res_mode=RES_NONE, res=None, scale2=None, shif
 
 
 def bn_bwd(dout, mask_out, y, save_mean, save_invstd, gamma, *, want_dy=True, dy=None, dres=None, dres_accumulate=False,
-           rowmap=None, mask_bits=None):
+           rowmap=None, mask_bits=None, pool_rows=0):
+    if pool_rows:          # dout is the pooled gradient [groups, c]: broadcast over the rows of each group, divided by their number
+        groups, c = dout.shape
+        dout = (dout / pool_rows).reshape(groups, 1, c).expand(groups, pool_rows, c).reshape(y.shape).contiguous()
     g = _rows_view(dout, rowmap)
     if mask_bits is not None:
         g = g * mask_bits.reshape(g.shape).to(g.dtype)
@@ -227,6 +230,17 @@ def bn_bwd(dout, mask_out, y, save_mean, save_invstd, gamma, *, want_dy=True, dy
     return dy, dgamma, dbeta
 
 
+def bn_pool_supported(rows, channels):
+    return channels % 32 == 0
+
+
+def bn_apply_pool(y, scale, shift, *, groups, res_mode=RES_NONE, res=None, scale2=None, shift2=None):
+    """Fused tail: (mean over each group's rows of relu(scale*y + shift + R), ReLU mask)."""
+    out = _bn_apply(y, scale, shift, res_mode=res_mode, res=res, scale2=scale2, shift2=shift2, relu=True)
+    c = out.shape[-1]
+    return out.reshape(groups, -1, c).mean(dim=1), (out > 0)
+
+
 def pool_fwd(x, groups):
     c = x.shape[-1]
     return x.reshape(groups, -1, c).mean(dim=1)
@@ -239,6 +253,20 @@ def pool_bwd(dout, shape):
         rows *= s
     rows = rows // c // groups
     return (dout / rows).reshape(groups, 1, c).expand(groups, rows, c).reshape(shape).contiguous()
+
+
+def linear_ce_fwd(x, w, bias, labels):
+    logits = x @ w.t() + (bias if bias is not None else 0)
+    p = torch.softmax(logits, dim=1)
+    n = x.shape[0]
+    onehot = torch.nn.functional.one_hot(labels, w.shape[0]).to(x.dtype)
+    loss = (torch.logsumexp(logits, dim=1) - (logits * onehot).sum(1)).mean()
+    return loss, logits, (p - onehot) / n
+
+
+def linear_ce_bwd(x, w, dlogits, grad_loss, need_dx=True, need_db=True):
+    d = dlogits * grad_loss
+    return d.t() @ x, (d.sum(0) if need_db else None), (d @ w if need_dx else None)
 
 
 # --------------------------------------------------------------------------- TF32-mode emulation (tests only)

@@ -330,3 +330,41 @@ def test_tf32_tensor_core_path(K, nb, t_in, v, cin, cout, taps, stride):
     dw_ref, db_ref = S.conv_wgrad(_trunc_tf32(dy).double(), _trunc_tf32(x).double(), taps=taps, stride=stride, pad=pad)
     assert rel_err(dw, dw_ref) <= 2e-5
     assert rel_err(db, S.conv_wgrad(dy.double(), x.double(), taps=taps, stride=stride, pad=pad)[1]) <= 5e-6
+
+
+@pytest.mark.parametrize("groups,rpg,c,res_mode", [(4, 75, 256, 1), (3, 50, 64, 2), (2, 33, 128, 0), (64, 3750, 256, 1)])
+def test_bn_apply_pool_tail_and_its_backward(K, groups, rpg, c, res_mode):
+    """agcn_bn_apply_pool / agcn_bn_bwd_pool (the model's fused tail) against bn_apply + pool_fwd and pool_bwd + bn_bwd."""
+    rows = groups * rpg
+    assert K.bn_pool_supported(rows, c)
+    y, res = rnd(rows, c).cuda(), rnd(rows, c, seed=1).cuda()
+    sc, sh = (rnd(c, seed=2) * 0.3 + 1).cuda(), (rnd(c, seed=3) * 0.2).cuda()
+    sc2, sh2 = (rnd(c, seed=4) * 0.3 + 1).cuda(), (rnd(c, seed=5) * 0.2).cuda()
+    kw = dict(res_mode=res_mode, res=res if res_mode else None, scale2=sc2 if res_mode == 2 else None, shift2=sh2 if res_mode == 2 else None)
+    pooled, bits = K.bn_apply_pool(y, sc, sh, groups=groups, **kw)
+    out, bits_ref = K.bn_apply(y, sc, sh, relu=True, want_mask=True, **kw)
+    assert torch.equal(bits, bits_ref)
+    assert rel_err(pooled, out.double().reshape(groups, rpg, c).mean(1)) <= 2e-6
+    d_pooled = rnd(groups, c, seed=6).cuda()
+    mean, invstd, gamma = (rnd(c, seed=7) * 0.1).cuda(), (rnd(c, seed=8).abs() + 0.5).cuda(), (rnd(c, seed=9) * 0.3 + 1).cuda()
+    d_full = K.pool_bwd(d_pooled, (rows, c))
+    dres_a, dres_b = torch.empty_like(y), torch.empty_like(y)
+    got = K.bn_bwd(d_pooled, None, y, mean, invstd, gamma, dres=dres_a, mask_bits=bits, pool_rows=rpg)
+    want = K.bn_bwd(d_full, None, y, mean, invstd, gamma, dres=dres_b, mask_bits=bits)
+    for a, b in zip(got, want):
+        assert rel_err(a, b) <= 2e-6
+    assert rel_err(dres_a, dres_b) <= 1e-6
+
+
+@pytest.mark.parametrize("n,cin,ncls", [(64, 256, 60), (3, 64, 27), (16, 1024, 35), (1, 32, 5)])
+def test_linear_cross_entropy_head(K, n, cin, ncls):
+    x, w, b = rnd(n, cin), rnd(ncls, cin, seed=1) * 0.2, rnd(ncls, seed=2)
+    labels = torch.randint(0, ncls, (n,), generator=torch.Generator().manual_seed(3))
+    loss, logits, dlogits = K.linear_ce_fwd(x.cuda(), w.cuda(), b.cuda(), labels.cuda())
+    xr, wr, br = x.double().requires_grad_(True), w.double().requires_grad_(True), b.double().requires_grad_(True)
+    lr = torch.nn.functional.linear(xr, wr, br)
+    loss_ref = torch.nn.functional.cross_entropy(lr, labels)
+    (loss_ref * 1.7).backward()
+    assert rel_err(logits, lr) <= 2e-6 and abs(float(loss) - float(loss_ref)) <= 2e-6 * max(1.0, abs(float(loss_ref)))
+    dw, db, dx = K.linear_ce_bwd(x.cuda(), w.cuda(), dlogits, torch.tensor(1.7).cuda())
+    assert rel_err(dw, wr.grad) <= 5e-6 and rel_err(db, br.grad) <= 5e-6 and rel_err(dx, xr.grad) <= 5e-6

@@ -191,3 +191,32 @@ def test_model_parity_harness_on_cpu(torch_stage_backend):
     from fusion_gcn_b200 import graph as G, modules as M
     err = T.seeded_model_case(M, G, (1, 20, 20, 9), "utd", 16, 3, "fp32", "cpu")
     assert err["y"] <= 1e-5
+
+
+def test_fused_head_and_pooled_tail_match_the_separate_ops(torch_stage_backend):
+    """Model.loss (fc + cross-entropy as one node) and the pooled tail of the last unit against nn.CrossEntropyLoss()(model(x), y)
+    built from the separate pool / linear ops: same loss, logits and gradients (host composition, torch stage backend)."""
+    import copy
+    from fusion_gcn_b200 import functional as FN, graph as G, modules as M
+    from fusion_gcn_b200.graphed import loss_and_logits
+    torch.manual_seed(3)
+    model = M.Model((2, 12, 25, 3), 11, G.SkeletonGraph(G.NTU_EDGES, center_joint=G.NTU_CENTER), start_feature_size=8).double().train()
+    ref = copy.deepcopy(model)
+    x = torch.randn(3, 2, 12, 25, 3, dtype=torch.float64)
+    y = torch.tensor([1, 7, 10])
+    import fusion_gcn_b200.modules as MM
+    orig = MM._prep
+    MM._prep = lambda t: t.contiguous()                  # keep fp64 through the stage backend
+    try:
+        loss, logits = loss_and_logits(model, torch.nn.CrossEntropyLoss(), x, y)
+        loss.backward()
+        h = ref.features_cl(x)                                                    # unfused: feature map -> PoolFn -> LinearFn -> torch CE
+        feat = FN.PoolFn.apply(h, 3)
+        logits_ref = FN.LinearFn.apply(feat, ref.fc.weight, ref.fc.bias, 0)
+        loss_ref = torch.nn.functional.cross_entropy(logits_ref, y)
+        loss_ref.backward()
+    finally:
+        MM._prep = orig
+    assert abs(float(loss) - float(loss_ref)) <= 1e-12 and torch.allclose(logits, logits_ref, atol=1e-12)
+    for (k, a), (_, b) in zip(model.named_parameters(), ref.named_parameters()):
+        assert torch.allclose(a.grad, b.grad, rtol=1e-9, atol=1e-12), k
