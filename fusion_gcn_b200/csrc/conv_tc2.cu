@@ -617,14 +617,15 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
     if (split && taps == 1 && bn > 128) {
         // Ring depth.  The [hi ; lo] weight slot of a tile wider than 128 columns is 48..64 KB: next to the epilogue buffers only ONE
         // activation stage then fits and load -> convert -> MMA serialise (measured: 768 -> 256 at 0.48 ms against 0.22 ms in the
-        // TF32 mode).  Unless the whole weight tile can stay resident, take the widest tile that leaves two weight slots and three
-        // activation stages (five with the 3xTF32 lo ring); the activation tile is then re-read (from L2) once per extra tile.
+        // TF32 mode).  Unless the whole weight tile can stay resident, take the widest tile that leaves two weight slots and two
+        // activation stages (plus the 3xTF32 lo ring); the activation tile is then re-read (from L2) and re-converted once per extra
+        // tile, which is why tiles that already get two stages keep their width (128 -> 192 at 192 columns beats 2 x 96, r3h).
         const uint64_t a_st = (uint64_t)(bf ? 2 : 1) * 16384u;
         const int kch = (cin + chunk_ch - 1) / chunk_ch;
         auto fits = [&](int cand) {
             const uint64_t b = (uint64_t)cand * 256u;
             const bool resident = cout == cand && kch <= kMaxB && (uint64_t)kch * b + (split == 1 ? 5u : 3u) * a_st <= 176u * 1024u;
-            return resident || 2u * b + (split == 1 ? 5u : 3u) * a_st <= 176u * 1024u;
+            return resident || 2u * b + (split == 1 ? 4u : 2u) * a_st <= 176u * 1024u;
         };
         if (!fits(bn))
             for (int cand = 128; cand >= 64; cand -= 16)

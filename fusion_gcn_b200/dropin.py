@@ -51,8 +51,11 @@ def install_shims(reference_root: str, host_stubs: bool = True) -> None:
     # np.bool is deliberately left alone (numpy >= 2 defines it; overriding it breaks numpy.ma / scipy)
 
 
-def install(reference_root: str, precision="fp32", host_stubs: bool = True) -> dict:
-    """Rebinds the reference's unit / backbone classes to the B200 implementations.  Returns the patched modules."""
+def install(reference_root: str, precision="fp32", host_stubs: bool = True, fused_optimizers: bool = False, prefetch: bool = False) -> dict:
+    """Rebinds the reference's unit / backbone classes to the B200 implementations.  Returns the patched modules.
+    ``fused_optimizers``: the YAML optimizer names SGD / ADAM / ADAMW (torch_src/session_helper.py:48-53) build the multi-tensor
+    classes of fusion_gcn_b200.optim.  ``prefetch``: the sessions' ``DataLoader`` (session/training.py:18-25, evaluation.py:20-24,
+    debugging.py:15-21) becomes fusion_gcn_b200.pipeline.PrefetchLoader (same batches, pinned staging + asynchronous H2D)."""
     from . import modules, modules_original
     if not os.path.isfile(os.path.join(reference_root, "torch_src", "models", "mmargcn", "agcn.py")):
         raise FileNotFoundError(f"{reference_root} does not look like a fusion-gcn checkout (torch_src/models/mmargcn/agcn.py missing)")
@@ -64,7 +67,26 @@ def install(reference_root: str, precision="fp32", host_stubs: bool = True) -> d
         for name in names:
             _ORIGINALS.setdefault((mod.__name__, name), getattr(mod, name))
             setattr(mod, name, getattr(impl, name))
-    return {"models.mmargcn.agcn": ref_m, "models.agcn.agcn": ref_o}
+    patched = {"models.mmargcn.agcn": ref_m, "models.agcn.agcn": ref_o}
+    if fused_optimizers:
+        from .optim import FUSED_OPTIMIZERS
+        helper = importlib.import_module("session_helper")
+        _ORIGINALS.setdefault((helper.__name__, "available_optimizers"), helper.available_optimizers)
+        helper.available_optimizers = dict(helper.available_optimizers, **FUSED_OPTIMIZERS)
+        patched["session_helper"] = helper
+    if prefetch:
+        import torch
+        from .pipeline import PrefetchLoader
+        device = "cuda" if torch.cuda.is_available() else "cpu"
+
+        def loader(dataset, batch_size=1, shuffle=False, drop_last=False, **kw):
+            return PrefetchLoader(dataset, batch_size, shuffle=shuffle, drop_last=drop_last, device=device)
+        for name in ("session.training", "session.evaluation", "session.debugging"):
+            mod = importlib.import_module(name)
+            _ORIGINALS.setdefault((mod.__name__, "DataLoader"), mod.DataLoader)
+            mod.DataLoader = loader
+            patched[name] = mod
+    return patched
 
 
 def uninstall() -> None:
@@ -72,6 +94,20 @@ def uninstall() -> None:
     for (mod_name, name), obj in _ORIGINALS.items():
         setattr(sys.modules[mod_name], name, obj)
     _ORIGINALS.clear()
+
+
+def _trace_losses(path: str) -> None:
+    """Appends every training-step loss (procedures/step.py:39-43) to ``path`` as text, one value per line."""
+    step = importlib.import_module("session.procedures.step")
+    inner = step.DefaultStep.forward
+
+    def forward(self, model, loss_function, features, label, loss_quotient=1):
+        y_pred, loss = inner(self, model, loss_function, features, label, loss_quotient)
+        if model.training:
+            with open(path, "a") as fh:
+                fh.write(repr(float(loss.detach())) + "\n")
+        return y_pred, loss
+    step.DefaultStep.forward = forward
 
 
 def main(argv=None) -> None:
@@ -83,12 +119,28 @@ def main(argv=None) -> None:
     import argparse
     ap = argparse.ArgumentParser(prog="python -m fusion_gcn_b200.dropin", description=__doc__.split("\n")[0])
     ap.add_argument("--reference", default=os.environ.get("FUSION_GCN_REFERENCE", "/root/reference"))
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "fp32_ffma"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16x3", "tf32", "fp32_ffma"])
+    ap.add_argument("--no-dropin", action="store_true", help="run the UNMODIFIED reference under the same import shims (A/B baseline)")
+    ap.add_argument("--reference-fp32", action="store_true", help="with --no-dropin: disable cuDNN / cuBLAS TF32 so the reference is an fp32 oracle (SURVEY D9)")
+    ap.add_argument("--no-fused-optimizers", action="store_true", help="keep torch.optim instead of fusion_gcn_b200.optim")
+    ap.add_argument("--no-prefetch", action="store_true", help="keep torch's DataLoader instead of fusion_gcn_b200.pipeline.PrefetchLoader")
+    ap.add_argument("--trace-loss", default=None, metavar="FILE", help="append every training-step loss to FILE")
     args = ap.parse_args(argv)
     root = os.path.abspath(args.reference)
-    install(root, args.precision)
-    from . import capi
-    capi.lib()                                               # fail before training starts if the extension is not built
+    if args.no_dropin:
+        if not os.path.isfile(os.path.join(root, "torch_src", "main.py")):
+            raise FileNotFoundError(f"{root} does not look like a fusion-gcn checkout")
+        install_shims(root)
+        if args.reference_fp32:
+            import torch
+            torch.backends.cudnn.allow_tf32 = False
+            torch.backends.cuda.matmul.allow_tf32 = False
+    else:
+        install(root, args.precision, fused_optimizers=not args.no_fused_optimizers, prefetch=not args.no_prefetch)
+        from . import capi
+        capi.lib()                                           # fail before training starts if the extension is not built
+    if args.trace_loss:
+        _trace_losses(args.trace_loss)
     os.chdir(root)
     sys.argv = [os.path.join(root, "torch_src", "main.py")] + rest
     runpy.run_path(sys.argv[0], run_name="__main__")

@@ -248,7 +248,14 @@ def test_graphed_step_matches_eager(pkg):
         ref.backward()
         torch.cuda.synchronize()
         assert rel_err(loss, ref) <= 1e-6
+        # (the graphed step takes the fused fc + cross-entropy head, the twin torch's: same maths, fp32 rounding apart; the
+        # mathematically-zero bias gradients of SURVEY D8 are compared on an absolute scale)
+        scale = max(float(q.grad.abs().max()) for q in twin.parameters())
         for (k, p), q in zip(model.named_parameters(), twin.parameters()):
-            assert p.grad is not None and rel_err(p.grad, q.grad) <= 1e-6, k
+            assert p.grad is not None, k
+            if ZERO_GRAD.search(k):
+                assert float((p.grad - q.grad).abs().max()) <= 1e-6 * scale, k
+            else:
+                assert rel_err(p.grad, q.grad) <= 2e-5, k
     for (k, a), b in zip(model.state_dict().items(), twin.state_dict().values()):
-        assert rel_err(a, b) <= 1e-6, k
+        assert stat_err(a, b) <= 1e-6, k
