@@ -46,15 +46,15 @@ batch_size: 9
 epochs: 2
 {optimizer_block}
 """)
-    cmd = [sys.executable, "-m", "fusion_gcn_b200.dropin", "--reference", ref_loader.REFERENCE_ROOT, "--trace-loss", trace] + extra + \\
+    cmd = [sys.executable, "-m", "fusion_gcn_b200.dropin", "--reference", ref_loader.REFERENCE_ROOT, "--trace-loss", trace] + extra + \
           ["--", "-f", cfg, "--disable_logging", "--disable_checkpointing"]
     res = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stderr[-3000:]
     return [float(v) for v in open(trace).read().split()]
 
 
-SGD = "base_lr: 0.01\\noptimizer: SGD\\noptimizer_args:\\n  momentum: 0.9\\n  nesterov: true\\n  weight_decay: 0.0001\\nlr_scheduler: multistep\\nlr_scheduler_args:\\n  milestones: [1]"
-ADAM = "base_lr: 0.001\\noptimizer: ADAM\\noptimizer_args:\\n  weight_decay: 0.01"
+SGD = "base_lr: 0.01\noptimizer: SGD\noptimizer_args:\n  momentum: 0.9\n  nesterov: true\n  weight_decay: 0.0001\nlr_scheduler: multistep\nlr_scheduler_args:\n  milestones: [1]"
+ADAM = "base_lr: 0.001\noptimizer: ADAM\noptimizer_args:\n  weight_decay: 0.01"
 
 
 @pytest.mark.parametrize("model,opt", [("agcn", SGD), ("mmargcn", ADAM)])
@@ -66,11 +66,11 @@ def test_training_curve_matches_the_reference_on_the_same_gpu(tmp_path, model, o
     tmp = str(tmp_path)
     _write_dataset(os.path.join(tmp, "data"))
     if model == "mmargcn":
-        opt = opt + "\\nmode: skeleton"
+        opt = opt + "\nmode: skeleton"
     ref = _run(tmp, "ref", model, opt, ["--no-dropin", "--reference-fp32"])
     ours = _run(tmp, "ours", model, opt, [])
     assert len(ref) == len(ours) == 12 and all(np.isfinite(ours))                       # 2 epochs x 6 batches of 9 (drop_last)
-    print(f"{model}: reference {['%.4f' % v for v in ref]}\\n{model}: ours      {['%.4f' % v for v in ours]}")
+    print(f"{model}: reference {['%.4f' % v for v in ref]}\n{model}: ours      {['%.4f' % v for v in ours]}")
     assert abs(ours[0] - ref[0]) <= 1e-4 * abs(ref[0])                                  # same init, same first batch
     for i, (a, b) in enumerate(zip(ours, ref)):
         assert abs(a - b) <= (2e-3 if i < 3 else 5e-2) * max(1.0, abs(b)), (i, a, b)

@@ -25,6 +25,7 @@ for step in "$@"; do
                done ;;
     optim)     python -m pytest tests/test_gpu_optim.py -m gpu -q -rf -x -p no:cacheprovider > gpurun_out/${tag}_optim.log 2>&1; tail -8 gpurun_out/${tag}_optim.log ;;
     pytests)   python -m pytest tests -m gpu -q -rf -s -p no:cacheprovider > gpurun_out/${tag}_pytest_s.log 2>&1; grep -E "^\[|passed|failed" gpurun_out/${tag}_pytest_s.log | tail -60 ;;
+    launcher)  python -m pytest tests/test_gpu_launcher.py -m gpu -q -rf -s -x -p no:cacheprovider > gpurun_out/${tag}_launcher.log 2>&1; tail -12 gpurun_out/${tag}_launcher.log ;;
     *) echo "unknown step $step" ;;
   esac
 done
