@@ -46,11 +46,20 @@ def make_graph(kind):
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     fallback = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+    tf32 = {}
+    tpath = os.path.join(ROOT, "profiles", "tf32_peak.json")            # tools/measure_peaks.py on a B200 of this pool (cuBLAS TF32 8192^3)
+    if os.path.isfile(tpath):
+        try:
+            t = json.load(open(tpath))
+            tf32 = {"tf32_tflops": float(t["tf32_tflops"]), "tf32_tflops_sustained": float(t["tf32_tflops_sustained"])}
+        except (KeyError, TypeError, ValueError):
+            tf32 = {}
+    fallback.update(tf32)
     if os.path.isfile(path):
         try:
             d = json.load(open(path))
-            return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"]),
-                    "bf16_tflops_sustained": d.get("bf16_tflops_sustained"), "source": "measured"}
+            return dict({"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"]),
+                         "bf16_tflops_sustained": d.get("bf16_tflops_sustained"), "source": "measured"}, **tf32)
         except (KeyError, TypeError, ValueError):          # unexpected layout: say so and use the recipe's fallback numbers
             fallback["source"] = "fallback (MEASURED_PEAKS.json present but not in the expected layout)"
     return fallback
@@ -119,7 +128,12 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     m, t, v, c, ncls, _ = WORKLOADS[args.workload]
-    n_local = args.batch                      # weak scaling: fixed per-GPU batch
+    if args.scaling == "strong":
+        if args.batch % world:
+            raise SystemExit(f"--scaling strong: global batch {args.batch} is not divisible by {world} GPUs")
+        n_local = args.batch // world         # strong scaling: the GLOBAL batch is fixed (BASELINE configs[1]: N=64 sharded 32/16/8 per GPU)
+    else:
+        n_local = args.batch                  # weak scaling: fixed per-GPU batch
     model = build_model(args.workload, args.precision, dev)
     reducer = GradientAllReducer(model.parameters()) if world > 1 else None
     gen = torch.Generator().manual_seed(1234 + rank)
@@ -236,11 +250,34 @@ def run_ours(args):
                 ms_tf32_graph = 0.0
             model.zero_grad(set_to_none=True)
         M.set_precision(model, args.precision)
-    t_all = torch.tensor([ms, ms_e2e, ms_tf32, ms_graph, ms_graph_e2e, -graph_ok, ms_tf32_graph, -float(ms_tf32_graph > 0)], device=dev, dtype=torch.float64)
+    # ---- N > 1: the same GLOBAL batch sharded over the GPUs (strong scaling, BASELINE configs[1]), one CUDA graph per step
+    ms_strong = 0.0
+    n_strong = args.batch // world if args.batch % world == 0 else 0
+    if world > 1 and args.scaling == "weak" and not args.no_strong and not args.no_graph and graph_ok and n_strong > 0:
+        try:
+            xs, ys = x_dev[:n_strong].contiguous(), y_dev[:n_strong].contiguous()
+            gs = GraphedStep(model, loss_fn, xs, ys, warmup=2, after_backward=reducer)
+            for _ in range(args.warmup):
+                gs()
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(args.steps):
+                gs()
+            s1.record()
+            barrier()
+            ms_strong = s0.elapsed_time(s1)
+            del gs
+        except Exception:                                # noqa: BLE001 -- the weak-scaling numbers stand
+            ms_strong = 0.0
+        model.zero_grad(set_to_none=True)
+    t_all = torch.tensor([ms, ms_e2e, ms_tf32, ms_graph, ms_graph_e2e, -graph_ok, ms_tf32_graph, -float(ms_tf32_graph > 0),
+                          ms_strong, -float(ms_strong > 0)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
     ms, ms_e2e, ms_tf32, ms_graph, ms_graph_e2e = (float(t_all[i]) for i in range(5))
     ms_tf32_graph = float(t_all[6]) if float(t_all[7]) <= -1.0 else 0.0
+    ms_strong = float(t_all[8]) if float(t_all[9]) <= -1.0 else 0.0
     graph_ok = float(t_all[5]) <= -1.0 and ms_graph > 0          # every rank captured and replayed
     if rank != 0:
         if world > 1:
@@ -282,6 +319,25 @@ def run_ours(args):
         if args.dump_kernels:
             with open(args.dump_kernels, "w") as fh:
                 json.dump([describe(k, v) for k, v in ranked], fh, indent=0)
+        # dominant kernel FAMILY (C-ABI entry point x temporal taps): all its launches summed, algorithmic work / device time
+        fam_work = {}
+        for (name, sig), (tot_ms, cnt, flops, nbytes) in ranked:
+            label = name
+            if name in ("agcn_conv_fwd", "agcn_conv_wgrad"):
+                label = f"{name}[taps={sig[6]}]"
+            f = fam_work.setdefault(label, [0.0, 0, 0.0, 0.0])
+            f[0] += tot_ms; f[1] += cnt; f[2] += flops * cnt; f[3] += nbytes * cnt
+        fl, (f_ms, f_cnt, f_flops, f_bytes) = max(fam_work.items(), key=lambda kv: kv[1][0])
+        fam_tf, fam_gbs = f_flops / (f_ms / 1e3) / 1e12, f_bytes / (f_ms / 1e3) / 1e9
+        family_roof = {"family": fl, "share_of_step": round(f_ms / ms, 4), "launches_per_step": round(f_cnt / args.steps, 1),
+                       "tflops": round(fam_tf, 2), "gbs": round(fam_gbs, 1), "frac_tensor_bf16": round(fam_tf / tensor_peak, 4),
+                       "frac_hbm": round(fam_gbs / pk["hbm_gbs"], 4)}
+        if pk.get("tf32_tflops_sustained"):
+            # issued-FLOP view: fp32 mode = 3 TF32 products per algorithmic MAC, bf16x3 = 3 BF16 products, tf32 = 1 TF32 product
+            issue = {"fp32": (3.0, pk["tf32_tflops_sustained"], "3 x TF32"), "bf16x3": (3.0, tensor_peak, "3 x BF16"),
+                     "tf32": (1.0, pk["tf32_tflops_sustained"], "1 x TF32")}[args.precision]
+            family_roof["frac_tensor_mode"] = round(fam_tf * issue[0] / issue[1], 4)
+            family_roof["mode_peak"] = f"{issue[2]} products per MAC against the measured {'TF32' if 'TF32' in issue[2] else 'BF16'} sustained peak {issue[1]} TFLOP/s"
         d = top[0]
         hbm_bound = d["frac_hbm"] >= d["frac_tensor"]
         roof = {"bound": "hbm" if hbm_bound else "tensor", "achieved": d["gbs"] if hbm_bound else d["tflops"],
@@ -292,13 +348,14 @@ def run_ours(args):
                 "avg_launch_ms": d["avg_launch_ms"], "launches_timed": d["launches_timed"], "share_of_step": d["share_of_step"],
                 "frac_tensor": d["frac_tensor"], "frac_hbm": d["frac_hbm"],
                 "peak_source": pk["source"] + (" copy bandwidth" if hbm_bound else " bf16 sustained (kernel timed inside a long step)"),
+                "top_family": family_roof,
                 "note": "achieved = algorithmic work of one launch (DESIGN.md section 4) / mean CUDA-event time of that launch signature inside the "
                         "timed region; bound = the roof the kernel sits closer to. fp32 parity mode issues 3 TF32 MMAs per product (3xTF32), so its "
                         "tensor ceiling for algorithmic FLOPs is a third of the TF32 rate (itself half of the bf16 peak used as denominator)."}
     gflop, mbytes = WORK[args.workload]
     line = {
         "metric": "AGCN fwd+bwd sequences/sec", "value": round(value, 2), "unit": "sequences/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": round(ms_head / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": round(ms_head / args.steps, 3), "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: AGCN 10 units, N={n_local}/GPU (global {n_global}), M={m}, T={t}, V={v}, C={c}, "
                                f"{ncls} classes, train mode, fwd+CE+bwd, random init", "precision_mode": args.precision,
@@ -329,6 +386,11 @@ def run_ours(args):
             "unit": "sequences/s", "ms_per_step": round(ms_graph / args.steps, 3),
             "note": "same step (zero-grad + fwd + CE + bwd [+ gradient all-reduce]) captured once and replayed as one CUDA graph; e2e_value "
                     "copies the batch from pinned host memory into the graph's static input and reads the loss back every step"})),
+        "strong_scaling": None if ms_strong <= 0 else {
+            "value": round(n_strong * world * args.steps / (ms_strong / 1e3), 2), "unit": "sequences/s", "global_batch": n_strong * world,
+            "per_gpu_batch": n_strong, "ms_per_step": round(ms_strong / args.steps, 3),
+            "note": "BASELINE configs[1]: the N=64 batch sharded over the GPUs (32/16/8 sequences per GPU at 2/4/8), one CUDA graph per step "
+                    "with the bucketed all-reduce overlapped with backward; compare with the 1-GPU headline for strong-scaling efficiency"},
         "model_roofline": {"hbm_seq_s": round(pk["hbm_gbs"] * 1e3 / mbytes, 1), "achieved_frac_of_hbm_ceiling": round(value / world / (pk["hbm_gbs"] * 1e3 / mbytes), 4),
                            "algorithmic_gflop_per_seq": gflop, "algorithmic_mb_per_seq": mbytes,
                            "achieved_tflops": round(value * gflop / 1e3, 2), "achieved_gbs": round(value / world * mbytes / 1e3, 1)},
@@ -530,6 +592,9 @@ def main():
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16x3", "tf32"],
                     help="fp32 = 3xTF32 parity mode, bf16x3 = bf16 triple-product parity mode (both meet 1e-4), tf32 = single pass (own tolerance)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch sequences per GPU (default); strong: --batch sequences in total, sharded over the GPUs")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1, weak scaling: skip the extra strong-scaling timing (global batch = --batch)")
     ap.add_argument("--dump-kernels", default=None, help="write the per-signature timing table (all C-ABI launches) to this JSON file")
     ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay timing")
     ap.add_argument("--no-tf32", action="store_true", help="skip the extra TF32-mode timing that the fp32 run reports beside the headline")

@@ -79,6 +79,19 @@ adam_kernel(const OptRow* __restrict__ table, const int2* __restrict__ items, Ad
     (void)b1;
 }
 
+// flat[off ...] <-> tensor copies for the gradient buckets of the data-parallel all-reduce: rows { flat slice, tensor, -, -, numel }
+// (OptRow with p = flat slice, g = tensor).  to_flat: flat = tensor;  else: tensor = flat * scale (the 1 / world averaging).
+__global__ void __launch_bounds__(kOptThreads)
+bucket_copy_kernel(const OptRow* __restrict__ table, const int2* __restrict__ items, int to_flat, float scale) {
+    const int2 it = items[blockIdx.x];
+    const OptRow t = table[it.x];
+    float* tensor = const_cast<float*>(t.g);
+    for_chunk(t, (long long)it.y * kOptChunk, [&](long long i) {
+        if (to_flat) t.p[i] = tensor[i];
+        else tensor[i] = t.p[i] * scale;
+    });
+}
+
 static int check_table(const void* table, const int* items, int nitems, const char* what) {
     AGCN_REQUIRE(table && items, AGCN_ERR_NULL, "%s: null table / work list", what);
     AGCN_REQUIRE(nitems > 0, AGCN_ERR_BAD_SHAPE, "%s: empty work list", what);
@@ -116,4 +129,12 @@ extern "C" AGCN_API int agcn_optim_adam(const void* table, const int* items, int
     adam_kernel<<<nitems, kOptThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const OptRow*>(table), reinterpret_cast<const int2*>(items),
                                                                                h, lr_dev, step_dev, grad_scale, found_inf);
     return check_launch("agcn_optim_adam");
+}
+
+extern "C" AGCN_API int agcn_bucket_copy(const void* table, const int* items, int nitems, int to_flat, float scale, void* stream) {
+    int rc = check_table(table, items, nitems, "agcn_bucket_copy");
+    if (rc) return rc;
+    bucket_copy_kernel<<<nitems, kOptThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const OptRow*>(table), reinterpret_cast<const int2*>(items),
+                                                                                 to_flat, scale);
+    return check_launch("agcn_bucket_copy");
 }

@@ -249,6 +249,11 @@ int agcn_optim_adam(const void* table, const int* items, int nitems, double lr, 
                     double beta1, double beta2, double eps, double weight_decay, int decoupled,
                     const float* step_dev, const float* grad_scale, const float* found_inf, void* stream);
 
+/* Gradient buckets of the data-parallel all-reduce (the reference has no distributed code): ONE launch packs the
+ * gradients of a bucket's parameters into its flat buffer (to_flat != 0) or writes the reduced values back scaled by `scale`
+ * (1 / world size).  Same table layout as the optimizer steps with param = flat slice, grad = the tensor.                     */
+int agcn_bucket_copy(const void* table, const int* items, int nitems, int to_flat, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

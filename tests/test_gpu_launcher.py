@@ -57,16 +57,18 @@ SGD = "base_lr: 0.01\noptimizer: SGD\noptimizer_args:\n  momentum: 0.9\n  nester
 ADAM = "base_lr: 0.001\noptimizer: ADAM\noptimizer_args:\n  weight_decay: 0.01"
 
 
-@pytest.mark.parametrize("model,opt", [("agcn", SGD), ("mmargcn", ADAM)])
+@pytest.mark.parametrize("model,opt", [("agcn", SGD), ("mmargcn", ADAM)], ids=["agcn-sgd", "mmargcn-adam"])
 def test_training_curve_matches_the_reference_on_the_same_gpu(tmp_path, model, opt):
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     if not ref_loader.available():
         pytest.skip("reference copy not present (python baseline/install_ref.py)")
     tmp = str(tmp_path)
-    _write_dataset(os.path.join(tmp, "data"))
-    if model == "mmargcn":
-        opt = opt + "\nmode: skeleton"
+    if model == "mmargcn":       # the multimodal dispatcher with the thin rgb_patch_features wrapper: per-joint embeddings as channels
+        _write_dataset(os.path.join(tmp, "data"), "rgb", (1, 32, 20, 16))
+        opt = opt + "\nmode: rgb_patch_features\nmodel_args:\n  num_layers: 4"
+    else:                        # models/agcn/agcn.py, the original 2s-AGCN copy (PA, l1..l10)
+        _write_dataset(os.path.join(tmp, "data"), "skeleton", (1, 32, 20, 3))
     ref = _run(tmp, "ref", model, opt, ["--no-dropin", "--reference-fp32"])
     ours = _run(tmp, "ours", model, opt, [])
     assert len(ref) == len(ours) == 12 and all(np.isfinite(ours))                       # 2 epochs x 6 batches of 9 (drop_last)
