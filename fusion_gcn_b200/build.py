@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libagcn_b200.so")
-SOURCES = ["common.cu", "conv_simt.cu", "wgrad_tc.cu", "conv_tc2.cu", "joint.cu", "gram_tc.cu", "mix_tc.cu", "bn.cu", "optim.cu", "head.cu"]
+SOURCES = ["common.cu", "conv_simt.cu", "wgrad_tc.cu", "conv_tc2.cu", "joint.cu", "joint_big.cu", "gram_tc.cu", "mix_tc.cu", "bn.cu", "optim.cu", "head.cu"]
 FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC",
          "-Xcompiler", "-fvisibility=hidden"]
 

@@ -400,6 +400,16 @@ __global__ void __launch_bounds__(256) joint_mix_kernel(MixArgs p) {
 
 using namespace agcn;
 
+// implemented in joint_big.cu: graphs with more than kMaxV nodes (the 1-D adaptive graph convolution)
+int agcn_joint_gram_big(const float* a, const float* b, float* out, int nb, int t, int v, int lda, int ldb, int groups,
+                        int offa, int stridea, int offb, int strideb, int width, void* stream);
+int agcn_attention_fwd_big(const float* s_part, const float* adj_a, const float* adj_b, float* p, float* g,
+                           int nb, int groups, int v, float scale, void* stream);
+int agcn_attention_bwd_big(const float* dg_part, const float* p, float* dg_sum, float* ds, float* dadj_b,
+                           int nb, int groups, int v, float scale, void* stream);
+int agcn_joint_mix_big(const float* in, const float* mats, float* out, int nb, int t, int v, int ldin, int ldout, int width,
+                       int mode, int accumulate, void* stream);
+
 // implemented in gram_tc.cu; AGCN_ERR_UNSUPPORTED when the shape is outside the tensor-core path
 int agcn_joint_gram_tc(const float* a, const float* b, float* out,
                        int nb, int t, int v, int lda, int ldb, int groups,
@@ -411,9 +421,13 @@ extern "C" AGCN_API int agcn_joint_gram(const float* a, const float* b, float* o
     AGCN_REQUIRE(a && b && out, AGCN_ERR_NULL, "agcn_joint_gram: null pointer");
     AGCN_REQUIRE(nb > 0 && t > 0 && v > 0 && groups > 0 && width > 0 && nchunk > 0 && nchunk <= t,
                  AGCN_ERR_BAD_SHAPE, "agcn_joint_gram: bad shape nb=%d t=%d v=%d groups=%d width=%d nchunk=%d", nb, t, v, groups, width, nchunk);
-    AGCN_REQUIRE(v <= kMaxV && groups <= 3, AGCN_ERR_UNSUPPORTED, "agcn_joint_gram: V=%d > %d or groups=%d > 3", v, kMaxV, groups);
+    AGCN_REQUIRE(groups <= 3, AGCN_ERR_UNSUPPORTED, "agcn_joint_gram: groups=%d > 3", groups);
     AGCN_REQUIRE(offa >= 0 && offb >= 0 && offa + (groups - 1) * stridea + width <= lda && offb + (groups - 1) * strideb + width <= ldb,
                  AGCN_ERR_BAD_SHAPE, "agcn_joint_gram: channel window outside the row");
+    if (v > kMaxV) {
+        AGCN_REQUIRE(nchunk == 1, AGCN_ERR_UNSUPPORTED, "agcn_joint_gram: V=%d > %d takes one chunk (nchunk=%d)", v, kMaxV, nchunk);
+        return agcn_joint_gram_big(a, b, out, nb, t, v, lda, ldb, groups, offa, stridea, offb, strideb, width, stream);
+    }
     AGCN_REQUIRE(precision >= AGCN_PREC_FP32 && precision <= AGCN_PREC_BF16X3, AGCN_ERR_UNSUPPORTED,
                  "agcn_joint_gram: unknown precision %d", precision);
     if (precision != AGCN_PREC_FP32_FFMA) {
@@ -451,7 +465,10 @@ extern "C" AGCN_API int agcn_attention_fwd(const float* s_part, const float* adj
                                   int nb, int nchunk, int groups, int v, float scale, void* stream) {
     AGCN_REQUIRE(s_part && adj_a && adj_b && p && g, AGCN_ERR_NULL, "agcn_attention_fwd: null pointer");
     AGCN_REQUIRE(nb > 0 && nchunk > 0 && groups > 0 && v > 0, AGCN_ERR_BAD_SHAPE, "agcn_attention_fwd: bad shape");
-    AGCN_REQUIRE(v <= kMaxV, AGCN_ERR_UNSUPPORTED, "agcn_attention_fwd: V=%d > %d", v, kMaxV);
+    if (v > kMaxV) {
+        AGCN_REQUIRE(nchunk == 1, AGCN_ERR_UNSUPPORTED, "agcn_attention_fwd: V=%d > %d takes one chunk", v, kMaxV);
+        return agcn_attention_fwd_big(s_part, adj_a, adj_b, p, g, nb, groups, v, scale, stream);
+    }
     long long total = (long long)nb * groups * v;
     attention_fwd_kernel<<<ceil_div(total, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(s_part, adj_a, adj_b, p, g, nb, nchunk, groups, v, scale);
     return check_launch("agcn_attention_fwd");
@@ -461,7 +478,10 @@ extern "C" AGCN_API int agcn_attention_bwd(const float* dg_part, const float* p,
                                   int nb, int nchunk, int groups, int v, float scale, void* stream) {
     AGCN_REQUIRE(dg_part && p && dg_sum && ds && dadj_b, AGCN_ERR_NULL, "agcn_attention_bwd: null pointer");
     AGCN_REQUIRE(nb > 0 && nchunk > 0 && groups > 0 && v > 0, AGCN_ERR_BAD_SHAPE, "agcn_attention_bwd: bad shape");
-    AGCN_REQUIRE(v <= kMaxV, AGCN_ERR_UNSUPPORTED, "agcn_attention_bwd: V=%d > %d", v, kMaxV);
+    if (v > kMaxV) {
+        AGCN_REQUIRE(nchunk == 1, AGCN_ERR_UNSUPPORTED, "agcn_attention_bwd: V=%d > %d takes one chunk", v, kMaxV);
+        return agcn_attention_bwd_big(dg_part, p, dg_sum, ds, dadj_b, nb, groups, v, scale, stream);
+    }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     long long total = (long long)nb * groups * v;
     attention_bwd_kernel<<<ceil_div(total, 128), 128, 0, s>>>(dg_part, p, dg_sum, ds, nb, nchunk, groups, v, scale);
@@ -484,7 +504,6 @@ extern "C" AGCN_API int agcn_joint_mix(const float* in, const float* mats, float
                               int precision, void* workspace, size_t workspace_bytes, void* stream) {
     AGCN_REQUIRE(in && mats && out, AGCN_ERR_NULL, "agcn_joint_mix: null pointer");
     AGCN_REQUIRE(nb > 0 && t > 0 && v > 0 && width > 0, AGCN_ERR_BAD_SHAPE, "agcn_joint_mix: bad shape");
-    AGCN_REQUIRE(v <= kMaxV, AGCN_ERR_UNSUPPORTED, "agcn_joint_mix: V=%d > %d", v, kMaxV);
     int need_in, need_out;
     if (mode == AGCN_MIX_AGG_FWD) { need_in = width; need_out = 3 * width; }
     else if (mode == AGCN_MIX_AGG_BWD) { need_in = 3 * width; need_out = width; }
@@ -494,6 +513,7 @@ extern "C" AGCN_API int agcn_joint_mix(const float* in, const float* mats, float
                  "agcn_joint_mix: mode %d expects ldin=%d ldout=%d, got %d %d", mode, need_in, need_out, ldin, ldout);
     AGCN_REQUIRE(precision >= AGCN_PREC_FP32 && precision <= AGCN_PREC_BF16X3, AGCN_ERR_UNSUPPORTED,
                  "agcn_joint_mix: unknown precision %d", precision);
+    if (v > kMaxV) return agcn_joint_mix_big(in, mats, out, nb, t, v, ldin, ldout, width, mode, accumulate, stream);
     if (precision != AGCN_PREC_FP32_FFMA && workspace != nullptr && workspace_bytes >= agcn_joint_mix_tc_workspace_bytes(nb)) {
         const int rc = agcn_joint_mix_tc(in, mats, out, static_cast<float*>(workspace), nb, t, v, ldin, ldout, width, mode, accumulate,
                                          precision == AGCN_PREC_FP32 || precision == AGCN_PREC_BF16X3 /* the V x V stages run 3xTF32 in both parity modes */, stream);

@@ -81,6 +81,7 @@ def install(reference_root: str, precision="fp32", host_stubs: bool = True, fuse
 
         def loader(dataset, batch_size=1, shuffle=False, drop_last=False, **kw):
             return PrefetchLoader(dataset, batch_size, shuffle=shuffle, drop_last=drop_last, device=device)
+        importlib.import_module("session_helper")      # first, as main.py does: session <-> session_helper import each other
         for name in ("session.training", "session.evaluation", "session.debugging"):
             mod = importlib.import_module(name)
             _ORIGINALS.setdefault((mod.__name__, "DataLoader"), mod.DataLoader)
@@ -98,6 +99,7 @@ def uninstall() -> None:
 
 def _trace_losses(path: str) -> None:
     """Appends every training-step loss (procedures/step.py:39-43) to ``path`` as text, one value per line."""
+    importlib.import_module("session_helper")          # first, as main.py does: session <-> session_helper import each other
     step = importlib.import_module("session.procedures.step")
     inner = step.DefaultStep.forward
 

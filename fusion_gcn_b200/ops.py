@@ -212,6 +212,8 @@ def pick_nchunk(nb: int, t: int, v: int = 0, width: int = 0) -> int:
     """Chunks of the t axis of the joint-gram reduction (one CTA per (sample, chunk)).  Shapes the tensor-core kernel takes
     (3*v <= 80, width 16 or a multiple of 32) want ONE resident wave of long-running CTAs (<= 148); the FFMA kernel wants
     about four waves of short ones."""
+    if v > 32:
+        return 1          # large graphs (1-D graph convolution): batched GEMM over the node axis, one chunk
     if v and 3 * v <= 80 and (width == 16 or (width > 0 and width % 32 == 0)):
         return max(1, min(NUM_SMS // max(nb, 1), max(1, t // 8)))
     n = max(1, min((4 * NUM_SMS + nb - 1) // nb, max(1, t // 4)))
@@ -432,3 +434,17 @@ def linear_ce_bwd(x, w, dlogits, grad_loss, need_dx=True, need_db=True):
     _call("agcn_linear_ce_bwd", _ptr(x), _ptr(w), dlogits.data_ptr(), _ptr(grad_loss), _ptr(dw), _ptr(db), _ptr(dx), n, cin, ncls, _stream(),
           sig=(n, cin, ncls), work=(4.0 * n * cin * ncls, 4.0 * (x.numel() + w.numel())))
     return dw, db, dx
+
+
+# ----------------------------------------------------------------------------- fixed-matrix node mixing (STGCN graph convolution)
+def node_mix(inp, mat, *, transpose=False, out=None, accumulate=False):
+    """inp [batch, v, c], mat [v, v] -> out[b, v, c] (+)= sum_u mat[v, u] inp[b, u, c]   (transpose: mat[u, v])."""
+    b, v, c = inp.shape
+    if out is None:
+        if accumulate:
+            raise RuntimeError("node_mix: accumulate needs an output tensor")
+        out = torch.empty_like(inp)
+    _check(inp, mat, out)
+    _call("agcn_node_mix", _ptr(inp), _ptr(mat), _ptr(out), b, v, c, int(transpose), int(accumulate), _stream(),
+          sig=(b, v, c, int(transpose), int(accumulate)), work=(2.0 * b * v * v * c, 4.0 * (inp.numel() + out.numel())))
+    return out

@@ -113,7 +113,7 @@ int agcn_conv_wgrad(const float* dy, const float* x, float* dw, float* dbias,
  * a: [nb][t][v][lda], b: [nb][t][v][ldb].  The t axis is split into nchunk contiguous chunks so that a
  * grid of nb*nchunk CTAs fills the GPU; the consumer sums the chunks in a fixed order.
  * Used for the score theta^T phi (agcn.py:104-106, a = b = [theta|phi] embedding) and for
- * dG = X^T dZ (gradient of agcn.py:110).  V <= 32.
+ * dG = X^T dZ (gradient of agcn.py:110).  V <= 32 on the shared-memory-resident kernels; larger graphs: see agcn_node_mix.
  * precision: AGCN_PREC_FP32 / AGCN_PREC_TF32 run the contraction on the tensor cores (3xTF32 / single-pass TF32) when
  * groups == 3, 3*V <= 80 and width is 16 (theta|phi sharing a 32-channel row) or a multiple of 32; every other shape and
  * AGCN_PREC_FP32_FFMA use the FFMA kernel.                                                                */
@@ -132,7 +132,7 @@ int agcn_attention_bwd(const float* dg_part, const float* p, float* dg_sum, floa
                        int nb, int nchunk, int groups, int v, float scale, void* stream);
 
 /* Per-sample mixing over the joint axis, see agcn_mix_mode.  in: [nb][t][v][ldin], out: [nb][t][v][ldout],
- * mats: [nb][3][v][v], width = channels per group.  V <= 32.
+ * mats: [nb][3][v][v], width = channels per group.  V <= 32 on the resident kernels (larger graphs: batched FFMA GEMMs).
  * precision: AGCN_PREC_FP32 / AGCN_PREC_TF32 run the mix on the tensor cores (3xTF32 / single-pass TF32) when width is a
  * multiple of 32 (AGCN_MIX_AGG_FWD / AGCN_MIX_AGG_BWD) or of 16 (AGCN_MIX_SCORE_BWD) and the workspace holds
  * agcn_joint_mix_workspace_bytes(nb) bytes (zero-padded copies of the matrices); every other case and
@@ -248,6 +248,15 @@ int agcn_optim_sgd(const void* table, const int* items, int nitems, double lr, c
 int agcn_optim_adam(const void* table, const int* items, int nitems, double lr, const float* lr_dev,
                     double beta1, double beta2, double eps, double weight_decay, int decoupled,
                     const float* step_dev, const float* grad_scale, const float* found_inf, void* stream);
+
+/* Node mixing with ONE fixed matrix for the whole batch -- STGCNGraphConvolution's support . adj^T
+ * (torch_src/models/mmargcn/graph_convolution.py:45) and its input gradient:
+ *   out[b][v][c] (+)= sum_u mat[v][u] * in[b][u][c]   (transpose_mat == 0)      sum_u mat[u][v] * in[b][u][c]   (transpose_mat != 0)
+ * in / out: [batch][v][channels] channels-last, mat: [v][v].  Any V (the IMU graphs have up to 652 nodes).  The adaptive 1-D
+ * graph convolution (graph_convolution.py:56-113) runs on agcn_joint_gram / agcn_attention_* / agcn_joint_mix with t = 1: for
+ * V > 32 those entry points switch to batched FFMA GEMMs over the node axis (nchunk must then be 1).                            */
+int agcn_node_mix(const float* in, const float* mat, float* out, int batch, int v, int channels,
+                  int transpose_mat, int accumulate, void* stream);
 
 /* Gradient buckets of the data-parallel all-reduce (the reference has no distributed code): ONE launch packs the
  * gradients of a bucket's parameters into its flat buffer (to_flat != 0) or writes the reduced values back scaled by `scale`

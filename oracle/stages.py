@@ -67,7 +67,20 @@ def conv_wgrad(dy, x, *, taps=1, stride=1, pad=0, want_bias=True, precision=PREC
     return dw, db
 
 
+def node_mix(inp, mat, *, transpose=False, out=None, accumulate=False):
+    res = torch.einsum("uv,buc->bvc" if transpose else "vu,buc->bvc", mat, inp)
+    if out is None:
+        return res.contiguous()
+    if accumulate:
+        out += res
+    else:
+        out.copy_(res)
+    return out
+
+
 def pick_nchunk(nb, t, v=0, width=0):
+    if v > 32:
+        return 1
     n = max(1, min((4 * NUM_SMS + nb - 1) // nb, max(1, t // 4)))
     return min(n, t)
 

@@ -38,8 +38,10 @@ def test_argument_validation_without_gpu():
     lib = capi.lib()
     rc = lib.agcn_conv_fwd(None, None, None, None, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, None, 0, None)
     assert rc == 6 and b"null" in lib.agcn_last_error_string()
-    rc = lib.agcn_joint_mix(1, 1, 1, 1, 4, 40, 8, 24, 8, 0, 0, 0, None, 0, None)       # V = 40 > 32
-    assert rc == 2 and b"V=40" in lib.agcn_last_error_string()
+    rc = lib.agcn_joint_mix(1, 1, 1, 1, 4, 25, 8, 24, 8, 7, 0, 0, None, 0, None)       # mix mode 7 does not exist
+    assert rc == 2 and b"unknown mode" in lib.agcn_last_error_string()
+    rc = lib.agcn_joint_gram(1, 1, 1, 1, 4, 40, 8, 8, 3, 0, 0, 0, 0, 8, 2, 0, None)    # V = 40 > 32 runs as ONE chunk
+    assert rc == 2 and b"one chunk" in lib.agcn_last_error_string()
     rc = lib.agcn_conv_fwd(1, 1, None, 1, 0, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, None, 0, None)
     assert rc == 1
     with pytest.raises(RuntimeError, match="status 1"):
