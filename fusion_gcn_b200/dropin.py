@@ -9,6 +9,7 @@ is a rebinding of those module attributes:
 
     models.mmargcn.agcn.{TemporalConv, SpatialGraphConv, SpatialTemporalConv, Model}  -> fusion_gcn_b200.modules.*
     models.agcn.agcn.{unit_tcn, unit_gcn, TCN_GCN_unit, Model}                        -> fusion_gcn_b200.modules_original.*
+    models.mmargcn.{graph_convolution, gcn}.{AGCNGraphConvolution, STGCNGraphConvolution} -> fusion_gcn_b200.graphconv.*
 
 Usage (on a box that has both the reference checkout and a B200):
 
@@ -68,6 +69,15 @@ def install(reference_root: str, precision="fp32", host_stubs: bool = True, fuse
             _ORIGINALS.setdefault((mod.__name__, name), getattr(mod, name))
             setattr(mod, name, getattr(impl, name))
     patched = {"models.mmargcn.agcn": ref_m, "models.agcn.agcn": ref_o}
+    # 1-D graph convolutions of the IMU / late-fusion models (graph_convolution.py:12-113); gcn.py binds the names at import time
+    from . import graphconv
+    ref_g = importlib.import_module("models.mmargcn.graph_convolution")
+    ref_gcn = importlib.import_module("models.mmargcn.gcn")
+    for mod in (ref_g, ref_gcn):
+        for name in ("AGCNGraphConvolution", "STGCNGraphConvolution"):
+            _ORIGINALS.setdefault((mod.__name__, name), getattr(mod, name))
+            setattr(mod, name, getattr(graphconv, name))
+        patched[mod.__name__] = mod
     if fused_optimizers:
         from .optim import FUSED_OPTIMIZERS
         helper = importlib.import_module("session_helper")

@@ -263,6 +263,12 @@ def _tcn_grad_tuple(g):
     return [g["wt"], g["bt"], g["bn_w"], g["bn_b"], g["wr"], g["br"], g["rbn_w"], g["rbn_b"]]
 
 
+def _like(grads, params):
+    """Gradients in the shapes of their parameters (Conv1d weights of the 1-D graph convolution are (out, in, 1), Conv2d ones
+    (out, in, 1, 1)); a gradient for an absent (None) parameter is dropped."""
+    return [None if (g is None or p is None) else g.reshape(p.shape) for g, p in zip(grads, params)]
+
+
 def _need_backward(spec):
     if not spec.training:
         raise NotImplementedError("fusion_gcn_b200: backward through eval-mode BatchNorm is not implemented "
@@ -285,7 +291,7 @@ class GcnFn(torch.autograd.Function):
         _need_backward(spec)
         dx, g = gcn_backward(d_o.contiguous(), ctx.store, p[20], p[24], p[22], spec, need_dx=ctx.needs_input_grad[0])
         ctx.store = None
-        return (dx, None, *_gcn_grad_tuple(g))
+        return (dx, None, *_like(_gcn_grad_tuple(g), p))
 
 
 class TcnFn(torch.autograd.Function):
@@ -330,7 +336,7 @@ class UnitFn(torch.autograd.Function):
         d_o, d_xres, tg = tcn_backward(d_out.contiguous(), ctx.store, tp[2], tp[6], spec, need_dres=need_dx, need_do=True)
         dx, gg = gcn_backward(d_o, ctx.store, gp[20], gp[24], gp[22], spec, dx=d_xres, need_dx=need_dx)
         ctx.store = None
-        return (dx, None, *_gcn_grad_tuple(gg), *_tcn_grad_tuple(tg))
+        return (dx, None, *_like(_gcn_grad_tuple(gg) + _tcn_grad_tuple(tg), params))
 
 
 # =============================================================================== model-level pieces
@@ -400,6 +406,7 @@ class LinearFn(torch.autograd.Function):
         n, cin = x.shape
         ctx.save_for_backward(x, w)
         ctx.precision = precision
+        ctx.has_bias = b is not None
         y = K.conv_fwd(x.view(1, 1, n, cin), w.view(w.shape[0], 1, cin), b, precision=precision)
         return y.view(n, w.shape[0])
 
@@ -409,7 +416,7 @@ class LinearFn(torch.autograd.Function):
         n, cin = x.shape
         cout = w.shape[0]
         dy4 = dy.contiguous().view(1, 1, n, cout)
-        dw, db = K.conv_wgrad(dy4, x.view(1, 1, n, cin), precision=ctx.precision)
+        dw, db = K.conv_wgrad(dy4, x.view(1, 1, n, cin), want_bias=ctx.has_bias, precision=ctx.precision)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = K.conv_fwd(dy4, _t(w.view(cout, 1, cin)), precision=ctx.precision).view(n, cin)

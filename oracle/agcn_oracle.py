@@ -25,6 +25,8 @@ Reference map (all under /root/reference):
   spatial_graph_conv    torch_src/models/mmargcn/agcn.py:96-115  (agcn/agcn.py:95-113)
   st_unit               torch_src/models/mmargcn/agcn.py:118-136 (agcn/agcn.py:116-133)
   model_forward         torch_src/models/mmargcn/agcn.py:183-200 (agcn/agcn.py:165-191)
+  agcn_graph_conv_1d    torch_src/models/mmargcn/graph_convolution.py:96-113
+  stgcn_graph_conv_1d   torch_src/models/mmargcn/graph_convolution.py:36-53
   init_state            torch_src/models/mmargcn/agcn.py:18-34,55-94,139-181
 """
 import math
@@ -121,6 +123,38 @@ def spatial_graph_conv(x, p, prefix: str, training: bool, adj_a: Optional[torch.
     else:
         d = x
     return _relu(y + d, mask, collect, "pre_o"), attn
+
+
+def agcn_graph_conv_1d(x, p, prefix: str, training: bool):
+    """AGCNGraphConvolution.forward, torch_src/models/mmargcn/graph_convolution.py:96-113: x (N, C, V); Conv1d weights
+    (out, in, 1); softmax over dim -2 of theta^T phi / Ci; BatchNorm1d; down = identity | Conv1d + BatchNorm1d."""
+    n, c, v = x.shape
+    adj = p[prefix + ".adj_a"] + p[prefix + ".adj_b"]
+    y = None
+    for k in range(adj.shape[0]):
+        theta = F.conv1d(x, p[f"{prefix}.conv_a.{k}.weight"], p[f"{prefix}.conv_a.{k}.bias"]).permute(0, 2, 1)      # (N, V, Ci)
+        phi = F.conv1d(x, p[f"{prefix}.conv_b.{k}.weight"], p[f"{prefix}.conv_b.{k}.bias"])                         # (N, Ci, V)
+        att = torch.softmax(torch.matmul(theta, phi) / theta.shape[-1], dim=-2) + adj[k]
+        z = F.conv1d(torch.matmul(x, att), p[f"{prefix}.conv_d.{k}.weight"], p[f"{prefix}.conv_d.{k}.bias"])
+        y = z if y is None else y + z
+    y = _bn(y, p, prefix + ".bn", training)
+    if (prefix + ".down.0.weight") in p:
+        d = _bn(F.conv1d(x, p[prefix + ".down.0.weight"], p[prefix + ".down.0.bias"]), p, prefix + ".down.1", training)
+    else:
+        d = x
+    return torch.relu(y + d)
+
+
+def stgcn_graph_conv_1d(x, p, prefix: str, training: bool, residual: str):
+    """STGCNGraphConvolution.forward, graph_convolution.py:36-53 (dense adjacency, no dropout): relu(conv(x) adj^T + residual(x)),
+    residual in {'none', 'identity', 'conv'}."""
+    support = F.conv1d(x, p[prefix + ".conv.weight"], p.get(prefix + ".conv.bias"))
+    out = torch.matmul(support, p[prefix + ".adj"].t())
+    if residual == "identity":
+        out = out + x
+    elif residual == "conv":
+        out = out + _bn(F.conv1d(x, p[prefix + ".residual.0.weight"], p[prefix + ".residual.0.bias"]), p, prefix + ".residual.1", training)
+    return torch.relu(out)
 
 
 def st_unit(x, p, prefix: str, stride: int, residual: str, training: bool,

@@ -122,3 +122,32 @@ def test_unsupported_mode_error_is_the_references(dropin):
     dropin.install(ref_loader.REFERENCE_ROOT)
     with pytest.raises(ValueError, match="Unsupported mode"):
         mmargcn.Model({"skeleton": (1, 8, 20, 3)}, 5, _graph(utd.skeleton_edges, utd.center_joint), mode="nope")
+
+
+def test_imu_gcn_wrapper_runs_on_the_1d_graph_convolutions(dropin, monkeypatch):
+    """mmargcn.Model(mode='imu_gcn') -> ImuGCN -> GCN(gc_model='agcn' | 'stgcn') (imu_feature_models.py:63-102, gcn.py:18-83):
+    the reference's GCN stack, unmodified, on top of fusion_gcn_b200.graphconv (40-node graph > 32: the large-V path)."""
+    import fusion_gcn_b200.modules as MM
+    from fusion_gcn_b200 import graphconv
+    from models.mmargcn import mmargcn
+    monkeypatch.setattr(MM, "_prep", lambda t: t.contiguous())
+    for gc_model in ("agcn", "stgcn"):
+        shape = {"inertial": (10, 4)}
+        build = lambda: mmargcn.Model(shape, 5, None, mode="imu_gcn", gc_model=gc_model, num_layers=3, inner_feature_dim=16)   # noqa: E731
+        torch.manual_seed(0)
+        ref = build().double()
+        state = {k: v.clone() for k, v in ref.state_dict().items()}
+        g = torch.Generator().manual_seed(4)
+        x, w = torch.randn(3, 10, 4, generator=g, dtype=torch.float64), torch.randn(3, 5, generator=g, dtype=torch.float64)
+        y_ref = ref(x)
+        (y_ref * w).sum().backward()
+        dropin.install(ref_loader.REFERENCE_ROOT)
+        ours = build().double()
+        ours.load_state_dict(state, strict=True)
+        assert isinstance(ours._model.gcn.gc1, (graphconv.AGCNGraphConvolution, graphconv.STGCNGraphConvolution))
+        y = ours(x)
+        (y * w).sum().backward()
+        assert rel_err(y, y_ref) <= 1e-9
+        for (k, a), (_, b) in zip(ref.named_parameters(), ours.named_parameters()):
+            assert float((a.grad - b.grad).abs().max()) <= 1e-8 * max(1.0, float(a.grad.abs().max())), k
+        dropin.uninstall()
