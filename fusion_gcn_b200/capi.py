@@ -28,6 +28,7 @@ SIGNATURES = {
     "agcn_launch_count": (_c_ll, []),
     "agcn_conv_fwd_workspace_bytes": (_c_size_t, [_c_int] * 4),
     "agcn_conv_fwd": (_c_int, [_c_void_p] * 4 + [_c_int] * 12 + [_c_void_p, _c_size_t, _c_void_p]),
+    "agcn_conv_fwd_post": (_c_int, [_c_void_p] * 6 + [_c_int, _c_void_p] + [_c_int] * 10 + [_c_void_p, _c_size_t, _c_void_p]),
     "agcn_conv_fwd_stats_bytes": (_c_size_t, [_c_int]),
     "agcn_conv_fwd_stats": (_c_int, [_c_void_p] * 4 + [_c_int] * 10 + [_c_void_p, _c_size_t, _c_void_p, _c_size_t, ctypes.POINTER(_c_int), _c_void_p]),
     "agcn_conv_wgrad_workspace_bytes": (_c_size_t, [_c_int] * 7),

@@ -30,6 +30,14 @@ inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 constexpr int kNumSMs = 148;   // B200
 
+// Fused tail of a convolution in eval mode (agcn_conv_fwd_post): y = act(scale * (conv + bias) + shift + res)
+struct PostOp {
+    const float* scale;    // [cout] or NULL (then shift is ignored): BatchNorm with running statistics folded into the epilogue
+    const float* shift;
+    const float* res;      // tensor of y's shape or NULL: residual branch added before the activation
+    int relu;
+};
+
 // A/B switches and limiter probes exist only in builds made with -DAGCN_PROBES
 // (python -m fusion_gcn_b200.build --probes); the default library never reads the environment.
 #ifdef AGCN_PROBES

@@ -12,6 +12,7 @@ struct ConvArgs {
     const float* x; const float* w; const float* bias; float* y;
     int nb, t_in, t_out, v, cin, cout, taps, stride, pad, transposed, accumulate;
     long long rows_out;
+    PostOp post;           // eval-mode fused tail (all NULL / 0: plain convolution)
 };
 
 __device__ __forceinline__ int gather_t(int to, int tap, const ConvArgs& a) {
@@ -139,11 +140,29 @@ __global__ void __launch_bounds__(256) conv_fwd_kernel(ConvArgs a) {
         for (int j = 0; j < 4; ++j) if (col + j < a.cout) bias[j] = __ldg(a.bias + col + j);
     }
     const bool vec_out = ((a.cout & 3) == 0) && (col + 3 < a.cout);
+    float psc[4] = {1.f, 1.f, 1.f, 1.f}, psh[4] = {0.f, 0.f, 0.f, 0.f};
+    if (a.post.scale) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (col + j < a.cout) { psc[j] = __ldg(a.post.scale + col + j); psh[j] = __ldg(a.post.shift + col + j); }
+    }
+    const bool has_post = a.post.scale != nullptr || a.post.res != nullptr || a.post.relu != 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         long long r = m0 + ty * 8 + i;
         if (r >= a.rows_out) continue;
         float* p = a.y + r * a.cout + col;
+        if (has_post) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (col + j < a.cout) {
+                    float o = fmaf(acc[i][j] + bias[j], psc[j], psh[j]);
+                    if (a.post.res) o += __ldg(a.post.res + r * a.cout + col + j);
+                    if (a.post.relu) o = fmaxf(o, 0.f);
+                    p[j] = o;
+                }
+            }
+            continue;
+        }
         if (vec_out) {
             float4 o = make_float4(acc[i][0] + bias[0], acc[i][1] + bias[1], acc[i][2] + bias[2], acc[i][3] + bias[3]);
             if (a.accumulate) {
@@ -540,7 +559,7 @@ using namespace agcn;
 int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* y,
                       int nb, int t_in, int t_out, int v, int cin, int cout,
                       int taps, int stride, int pad, int transposed, int accumulate, int split, float* w_split, void* stream,
-                      float* stat_part, int* stat_nparts);
+                      float* stat_part, int* stat_nparts, const agcn::PostOp* post);
 size_t agcn_conv_wgrad_tc_workspace_floats(int nb, int t_in, int t_out, int v, int cin, int cout, int taps, int stride, int pad, int split);
 int agcn_conv_wgrad_tc(const float* dy, const float* x, float* ws, int* splits_out,
                        int nb, int t_in, int t_out, int v, int cin, int cout, int taps, int stride, int pad, int split, void* stream);
@@ -558,7 +577,7 @@ static int conv_fwd_impl(const float* x, const float* w, const float* bias, floa
                          int nb, int t_in, int t_out, int v, int cin, int cout,
                          int taps, int stride, int pad, int transposed, int accumulate,
                          int precision, void* workspace, size_t workspace_bytes, void* stream,
-                         float* stat_part, int* stat_nparts) {
+                         float* stat_part, int* stat_nparts, const PostOp* post = nullptr) {
     AGCN_REQUIRE(x && w && y, AGCN_ERR_NULL, "agcn_conv_fwd: null pointer");
     AGCN_REQUIRE(nb > 0 && t_in > 0 && t_out > 0 && v > 0 && cin > 0 && cout > 0 && taps > 0 && stride > 0 && pad >= 0,
                  AGCN_ERR_BAD_SHAPE, "agcn_conv_fwd: bad shape nb=%d t_in=%d t_out=%d v=%d cin=%d cout=%d taps=%d stride=%d pad=%d",
@@ -571,16 +590,16 @@ static int conv_fwd_impl(const float* x, const float* w, const float* bias, floa
         if (ws_ok) {
             if (stat_part != nullptr) {       // try the epilogue with fused column sums first; shapes it does not take run without
                 int rc3 = agcn_conv_fwd_tc2(x, w, bias, y, nb, t_in, t_out, v, cin, cout, taps, stride, pad, transposed, accumulate, split,
-                                            static_cast<float*>(workspace), stream, stat_part, stat_nparts);
+                                            static_cast<float*>(workspace), stream, stat_part, stat_nparts, post);
                 if (rc3 != AGCN_ERR_UNSUPPORTED) return rc3;
             }
             int rc2 = agcn_conv_fwd_tc2(x, w, bias, y, nb, t_in, t_out, v, cin, cout, taps, stride, pad, transposed, accumulate, split,
-                                        static_cast<float*>(workspace), stream, nullptr, nullptr);
+                                        static_cast<float*>(workspace), stream, nullptr, nullptr, post);
             if (rc2 != AGCN_ERR_UNSUPPORTED) return rc2;   // unsupported shapes fall through to the FFMA kernel
         }
         }
     }
-    if (taps == 1 && stride == 1 && pad == 0 && t_in == t_out && cout < 16 && cin % 4 == 0 && cin <= 1024 && aligned16(x) && aligned16(w)) {
+    if (post == nullptr && taps == 1 && stride == 1 && pad == 0 && t_in == t_out && cout < 16 && cin % 4 == 0 && cin <= 1024 && aligned16(x) && aligned16(w)) {
         // skinny output (input gradients of the first unit): one HBM pass, no GEMM tiling
         const long long rows = (long long)nb * t_out * v;
         const size_t smem = ((size_t)kSkinnyRows * (cin + 4) + (size_t)cout * cin + (size_t)kSkinnyRows * cout) * sizeof(float);
@@ -594,7 +613,7 @@ static int conv_fwd_impl(const float* x, const float* w, const float* bias, floa
         }
     }
     ConvArgs a{x, w, bias, y, nb, t_in, t_out, v, cin, cout, taps, stride, pad, transposed, accumulate,
-               (long long)nb * t_out * v};
+               (long long)nb * t_out * v, post ? *post : PostOp{nullptr, nullptr, nullptr, 0}};
     dim3 grid((unsigned)ceil_div(a.rows_out, 128), (unsigned)ceil_div(cout, 64));
     const bool vec = (cin % 4 == 0) && aligned16(x) && aligned16(w);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -609,6 +628,18 @@ extern "C" AGCN_API int agcn_conv_fwd(const float* x, const float* w, const floa
                              int precision, void* workspace, size_t workspace_bytes, void* stream) {
     return conv_fwd_impl(x, w, bias, y, nb, t_in, t_out, v, cin, cout, taps, stride, pad, transposed, accumulate, precision,
                          workspace, workspace_bytes, stream, nullptr, nullptr);
+}
+
+extern "C" AGCN_API int agcn_conv_fwd_post(const float* x, const float* w, const float* bias,
+                                           const float* scale, const float* shift, const float* res, int relu, float* y,
+                                           int nb, int t_in, int t_out, int v, int cin, int cout, int taps, int stride, int pad,
+                                           int precision, void* workspace, size_t workspace_bytes, void* stream) {
+    AGCN_REQUIRE((scale == nullptr) == (shift == nullptr), AGCN_ERR_NULL, "agcn_conv_fwd_post: scale and shift come together");
+    AGCN_REQUIRE(!scale || (aligned16(scale) && aligned16(shift)), AGCN_ERR_MISALIGNED, "agcn_conv_fwd_post: scale / shift not 16-byte aligned");
+    AGCN_REQUIRE(!res || aligned16(res), AGCN_ERR_MISALIGNED, "agcn_conv_fwd_post: residual tensor not 16-byte aligned");
+    PostOp post{scale, shift, res, relu};
+    return conv_fwd_impl(x, w, bias, y, nb, t_in, t_out, v, cin, cout, taps, stride, pad, 0, 0, precision,
+                         workspace, workspace_bytes, stream, nullptr, nullptr, &post);
 }
 
 extern "C" AGCN_API size_t agcn_conv_fwd_stats_bytes(int cout) {

@@ -61,6 +61,7 @@ constexpr uint32_t kStatBytes = 4u * 2u * kStatCols * 4u;    // four epilogue wa
 
 struct Tc2Args {
     float* y; const float* bias;
+    PostOp post;                  // eval-mode fused tail: y = act(scale * (acc + bias) + shift + res)
     float* stat_part;             // != NULL: per-warp column sums of the written output, [gridDim.x * 4][2][cout] (BatchNorm statistics)
     int nb, t_out, v, cin, cout, stride, transposed, accumulate;
     int tt, bn, n_tiles_n, kchunks, tiles_t, nparity;
@@ -387,8 +388,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                                 for (int g = 0; g < 8; ++g) {
                                     float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
                                     if (a.bias) bq = __ldg(reinterpret_cast<const float4*>(a.bias + nt * a.bn + c0 + g * 4));
-                                    sts128(srow + (((uint32_t)g ^ sw) << 4),
-                                           make_float4(vals[g * 4] + bq.x, vals[g * 4 + 1] + bq.y, vals[g * 4 + 2] + bq.z, vals[g * 4 + 3] + bq.w));
+                                    float4 o = make_float4(vals[g * 4] + bq.x, vals[g * 4 + 1] + bq.y, vals[g * 4 + 2] + bq.z, vals[g * 4 + 3] + bq.w);
+                                    if (a.post.scale) {
+                                        const float4 sc = __ldg(reinterpret_cast<const float4*>(a.post.scale + nt * a.bn + c0 + g * 4));
+                                        const float4 sh = __ldg(reinterpret_cast<const float4*>(a.post.shift + nt * a.bn + c0 + g * 4));
+                                        o = make_float4(fmaf(o.x, sc.x, sh.x), fmaf(o.y, sc.y, sh.y), fmaf(o.z, sc.z, sh.z), fmaf(o.w, sc.w, sh.w));
+                                    }
+                                    if (a.post.res && my_off >= 0) {          // this thread's own row: eight 16-byte pieces = one 128-byte line
+                                        const float4 rq = __ldg(reinterpret_cast<const float4*>(a.post.res + my_off + c0 + g * 4));
+                                        o.x += rq.x; o.y += rq.y; o.z += rq.z; o.w += rq.w;
+                                    }
+                                    if (a.post.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                                    sts128(srow + (((uint32_t)g ^ sw) << 4), o);
                                 }
                             }
                             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -447,6 +458,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                             const bool col_ok = cq < 4 || wide;
                             float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (a.bias && col_ok) bq = __ldg(reinterpret_cast<const float4*>(a.bias + nt * a.bn + c0 + cq * 4));
+                            float4 psc = make_float4(1.f, 1.f, 1.f, 1.f), psh = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (a.post.scale && col_ok) {
+                                psc = __ldg(reinterpret_cast<const float4*>(a.post.scale + nt * a.bn + c0 + cq * 4));
+                                psh = __ldg(reinterpret_cast<const float4*>(a.post.shift + nt * a.bn + c0 + cq * 4));
+                            }
                             float4 ssum = make_float4(0.f, 0.f, 0.f, 0.f), ssq = ssum;      // column sums over this lane's 8 rows
                             // four row offsets (and, when accumulating, four old values) are fetched before the first dependent
                             // add / store, so the global-load latency is paid twice per chunk, not once per row
@@ -460,13 +476,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                                     oldv[r4] = make_float4(0.f, 0.f, 0.f, 0.f);
                                     if (a.accumulate && offs[r4] >= 0 && col_ok)
                                         oldv[r4] = *reinterpret_cast<const float4*>(a.y + offs[r4] + c0 + cq * 4);
+                                    else if (a.post.res && offs[r4] >= 0 && col_ok)           // eval tail: residual added AFTER the affine
+                                        oldv[r4] = __ldg(reinterpret_cast<const float4*>(a.post.res + offs[r4] + c0 + cq * 4));
                                 }
 #pragma unroll
                                 for (int r4 = 0; r4 < 4; ++r4) {
                                     const int src_lane = (half * 4 + r4) * 4 + (lane >> 3);
                                     if (offs[r4] >= 0 && col_ok) {
                                         float4 o = lds128(stage_base + (uint32_t)src_lane * kStagePitch + (uint32_t)cq * 16u);
-                                        o.x += bq.x + oldv[r4].x; o.y += bq.y + oldv[r4].y; o.z += bq.z + oldv[r4].z; o.w += bq.w + oldv[r4].w;
+                                        o.x = fmaf(o.x + bq.x, psc.x, psh.x) + oldv[r4].x; o.y = fmaf(o.y + bq.y, psc.y, psh.y) + oldv[r4].y;
+                                        o.z = fmaf(o.z + bq.z, psc.z, psh.z) + oldv[r4].z; o.w = fmaf(o.w + bq.w, psc.w, psh.w) + oldv[r4].w;
+                                        if (a.post.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
                                         *reinterpret_cast<float4*>(a.y + offs[r4] + c0 + cq * 4) = o;
                                         ssum.x += o.x; ssum.y += o.y; ssum.z += o.z; ssum.w += o.w;
                                         ssq.x = fmaf(o.x, o.x, ssq.x); ssq.y = fmaf(o.y, o.y, ssq.y); ssq.z = fmaf(o.z, o.z, ssq.z); ssq.w = fmaf(o.w, o.w, ssq.w);
@@ -583,7 +603,7 @@ static __global__ void split_weights_bf16_kernel(const float* w, uint16_t* w_spl
 int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* y,
                       int nb, int t_in, int t_out, int v, int cin, int cout,
                       int taps, int stride, int pad, int transposed, int accumulate, int split, float* w_split, void* stream,
-                      float* stat_part, int* stat_nparts) {
+                      float* stat_part, int* stat_nparts, const agcn::PostOp* post) {
     using namespace agcn::tc;
     using namespace agcn::tc2;
     static const bool disabled = probe_env("AGCN_TC_V1") != nullptr;
@@ -636,6 +656,8 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
 
     Tc2Args a;
     a.y = y; a.bias = bias; a.stat_part = stat_part;
+    a.post = post ? *post : PostOp{nullptr, nullptr, nullptr, 0};
+    if (post && (accumulate || transposed || stat_part)) return AGCN_ERR_UNSUPPORTED;
     a.nb = nb; a.t_out = t_out; a.v = v; a.cin = cin; a.cout = cout; a.stride = stride; a.transposed = transposed; a.accumulate = accumulate;
     a.dbg = dbg;
     static const bool no_dual = probe_env("AGCN_TC2_NO_DUAL") != nullptr;

@@ -68,6 +68,13 @@ def _conv_bn(x, w, bias, gamma, beta, buf: BnBuffers, training: bool, prec: int,
     return y, _bn_forward(y, gamma, beta, buf, training)
 
 
+def _eval_affine(gamma, beta, buf: BnBuffers):
+    """(scale, shift) of an eval-mode BatchNorm: gamma / sqrt(running_var + eps), beta - running_mean * scale."""
+    c = gamma.shape[0]
+    sc, sh, _, _ = K.bn_stats(gamma, gamma, beta, buf.running_mean, buf.running_var, None, BN_MOMENTUM, BN_EPS, False, rowmap=(1, 1, 0, c))
+    return sc, sh
+
+
 def _apply(want_mask, *args, **kw):
     """bn_apply -> (out, ReLU bit mask | None); the mask is only produced when the backward will need it."""
     if want_mask:
@@ -105,6 +112,19 @@ def gcn_forward(x, adj_a, adj_b, wa, ba, wb, bb, wd, bd, bn_w, bn_b, down_w, dow
     scale = 1.0 / float(ci * t)
     p, g = K.attention_fwd(s_part, adj_a.contiguous(), adj_b.contiguous(), scale)
     z = K.joint_mix(x, g, width=cin, mode=K.MIX_AGG_FWD, precision=prec)                               # [nb,t,v,3*cin]
+    if not spec.training:
+        # eval mode (session.py:188-194): BatchNorm is a per-channel affine of the running statistics, so BN, the down / identity
+        # branch and the ReLU ride in the projection's epilogue -- no pre-BN tensor, no separate normalise pass, nothing saved
+        sc, sh = _eval_affine(bn_w, bn_b, spec.bn_gcn)
+        if spec.has_down:
+            sc2, sh2 = _eval_affine(dbn_w, dbn_b, spec.bn_down)
+            res = K.conv_fwd_post(x, down_w.reshape(cout, 1, cin), down_b, scale=sc2, shift=sh2, precision=prec)
+        else:
+            res = x
+        o = K.conv_fwd_post(z, wdc, bdc, scale=sc, shift=sh, res=res, relu=True, precision=prec)
+        if spec.attention_out is not None:
+            spec.attention_out[:] = [p[:, k] for k in range(3)]
+        return o
     y, (sc, sh, mean, invstd) = _conv_bn(z, wdc, bdc, bn_w, bn_b, spec.bn_gcn, spec.training, prec)
     if spec.has_down:
         yd, (sc2, sh2, mean2, invstd2) = _conv_bn(x, down_w.reshape(cout, 1, cin), down_b, dbn_w, dbn_b, spec.bn_down, spec.training, prec)
@@ -182,6 +202,20 @@ def tcn_forward(o, x_res, wt, bt, bn_w, bn_b, wr, br, rbn_w, rbn_b, spec: UnitSp
     t_out = (t + 2 * pad - ksz) // s + 1
     prec = spec.precision
     wtp = _pack_taps(wt)
+    if not spec.training:
+        # eval mode: temporal conv + BN + residual + ReLU in one pass (the residual branch's conv + BN in one more)
+        sc, sh = _eval_affine(bn_w, bn_b, spec.bn_tcn)
+        if spec.residual == "identity":
+            res = x_res
+        elif spec.residual == "conv":
+            sc2, sh2 = _eval_affine(rbn_w, rbn_b, spec.bn_res)
+            res = K.conv_fwd_post(x_res, _pack_taps(wr), br, scale=sc2, shift=sh2, t_out=t_out, stride=s, pad=0, precision=prec)
+        else:
+            res = None
+        out = K.conv_fwd_post(o, wtp, bt, scale=sc, shift=sh, res=res, relu=spec.relu_out, t_out=t_out, stride=s, pad=pad, precision=prec)
+        if spec.pool_groups and ctx is not None:
+            ctx.update(pool_rows=0)
+        return out
     u, (sc, sh, mean, invstd) = _conv_bn(o, wtp, bt, bn_w, bn_b, spec.bn_tcn, spec.training, prec, t_out=t_out, stride=s, pad=pad)
     ur = mean2 = invstd2 = wrp = None
     want_mask = ctx is not None and spec.training and spec.relu_out

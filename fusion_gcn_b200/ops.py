@@ -147,6 +147,28 @@ def conv_fwd(x, w, bias=None, *, t_out=None, stride=1, pad=0, transposed=False, 
     return out
 
 
+def conv_fwd_post(x, w, bias=None, *, scale=None, shift=None, res=None, relu=False, t_out=None, stride=1, pad=0, precision=PREC_FP32):
+    """Eval-mode convolution with its tail fused: act(scale * (conv(x, w) + bias) + shift + res); see agcn_conv_fwd_post."""
+    nb, t_in, v, cin = x.shape
+    cout, taps, cin_w = w.shape
+    if cin_w != cin:
+        raise RuntimeError(f"conv_fwd_post: weight expects {cin_w} input channels, tensor has {cin}")
+    if t_out is None:
+        t_out = t_in
+    out = torch.empty((nb, t_out, v, cout), device=x.device, dtype=torch.float32)
+    if res is not None and tuple(res.shape) != tuple(out.shape):
+        raise RuntimeError(f"conv_fwd_post: residual has shape {tuple(res.shape)}, expected {tuple(out.shape)}")
+    _check(x, w, bias, scale, shift, res, out)
+    ws_bytes = capi.lib().agcn_conv_fwd_workspace_bytes(cin, cout, taps, precision)
+    ws = torch.empty((ws_bytes + 3) // 4, device=x.device, dtype=torch.float32) if ws_bytes else None
+    rows = nb * t_out * v
+    _call("agcn_conv_fwd_post", _ptr(x), _ptr(w), _ptr(bias), _ptr(scale), _ptr(shift), _ptr(res), int(relu), _ptr(out),
+          nb, t_in, t_out, v, cin, cout, taps, stride, pad, precision, _ptr(ws), ws_bytes, _stream(),
+          sig=(nb, t_in, t_out, v, cin, cout, taps, stride, 2, int(res is not None)),
+          work=(2.0 * rows * cin * cout * taps, 4.0 * (x.numel() + rows * cout * (2 if res is not None else 1))), alias="agcn_conv_fwd")
+    return out
+
+
 def conv_fwd_stats(x, w, bias=None, *, t_out=None, stride=1, pad=0, precision=PREC_FP32):
     """conv_fwd whose epilogue also accumulates the column sums of y for the training-mode BatchNorm that follows
     (agcn_conv_fwd_stats).  -> (y, part) with part [nparts, 2, cout] (sum | sum of squares), or (y, None) when the fused

@@ -86,6 +86,16 @@ int agcn_conv_fwd(const float* x, const float* w, const float* bias, float* y,
                   int taps, int stride, int pad, int transposed, int accumulate,
                   int precision, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Eval-mode convolution with its tail fused (model.eval(), torch_src/session/session.py:188-194, session/evaluation.py:36-56):
+ * BatchNorm with running statistics is a per-channel affine, so Conv2d -> BatchNorm2d [-> + residual] [-> ReLU]
+ * (agcn.py:49-51, 110-115, 134-136) is ONE pass:   y = act( scale[co] * (conv(x, w) + bias[co]) + shift[co] + res )
+ * scale / shift: [cout] or both NULL (no affine); res: tensor of y's shape or NULL; relu != 0 applies max(., 0).
+ * Forward gather only.  Same workspace as agcn_conv_fwd.                                                              */
+int agcn_conv_fwd_post(const float* x, const float* w, const float* bias,
+                       const float* scale, const float* shift, const float* res, int relu, float* y,
+                       int nb, int t_in, int t_out, int v, int cin, int cout, int taps, int stride, int pad,
+                       int precision, void* workspace, size_t workspace_bytes, void* stream);
+
 /* agcn_conv_fwd (forward gather, no accumulate) whose epilogue also leaves the per-channel sums the training-mode
  * BatchNorm that follows needs (nn.Conv2d -> nn.BatchNorm2d pairs at agcn.py:41-51,73-83): stat_part receives
  * [*stat_nparts][2][cout] floats (sum | sum of squares of y over a fixed row partition, deterministic), to be

@@ -59,6 +59,15 @@ def conv_fwd(x, w, bias=None, *, t_out=None, stride=1, pad=0, transposed=False, 
     return out
 
 
+def conv_fwd_post(x, w, bias=None, *, scale=None, shift=None, res=None, relu=False, t_out=None, stride=1, pad=0, precision=PREC_FP32):
+    y = conv_fwd(x, w, bias, t_out=t_out, stride=stride, pad=pad)
+    if scale is not None:
+        y = y * scale + shift
+    if res is not None:
+        y = y + res
+    return torch.relu(y) if relu else y
+
+
 def conv_wgrad(dy, x, *, taps=1, stride=1, pad=0, want_bias=True, precision=PREC_FP32):
     t_out = dy.shape[1]
     g = _gathered(x, t_out, taps, stride, pad, False)

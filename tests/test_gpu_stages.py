@@ -368,3 +368,27 @@ def test_linear_cross_entropy_head(K, n, cin, ncls):
     assert rel_err(logits, lr) <= 2e-6 and abs(float(loss) - float(loss_ref)) <= 2e-6 * max(1.0, abs(float(loss_ref)))
     dw, db, dx = K.linear_ce_bwd(x.cuda(), w.cuda(), dlogits, torch.tensor(1.7).cuda())
     assert rel_err(dw, wr.grad) <= 5e-6 and rel_err(db, br.grad) <= 5e-6 and rel_err(dx, xr.grad) <= 5e-6
+
+
+@pytest.mark.parametrize("mode", ["ffma", "fp32", "bf16x3", "tf32"])
+@pytest.mark.parametrize("nb,t_in,v,cin,cout,taps,stride,with_res", [
+    (2, 12, 25, 192, 64, 1, 1, True), (2, 20, 25, 64, 64, 9, 1, True), (2, 21, 25, 128, 256, 9, 2, True), (3, 9, 20, 3, 64, 1, 1, False),
+    (2, 10, 25, 768, 256, 1, 1, True), (2, 16, 22, 64, 128, 1, 2, False)])
+def test_conv_fwd_post_eval_tail(K, nb, t_in, v, cin, cout, taps, stride, with_res, mode):
+    """agcn_conv_fwd_post: act(scale * (conv + bias) + shift + res) in the convolution's epilogue (both tensor-core epilogues and
+    the FFMA kernel) against the separate stage oracle."""
+    prec, tol = {"ffma": (K.PREC_FP32_FFMA, 2e-6), "fp32": (K.PREC_FP32, 1e-5), "bf16x3": (K.PREC_BF16X3, 4e-5), "tf32": (K.PREC_TF32, 2e-3)}[mode]
+    pad = (taps - 1) // 2
+    t_out = (t_in + 2 * pad - taps) // stride + 1
+    x, w, b = rnd(nb, t_in, v, cin), rnd(cout, taps, cin, seed=1) * 0.1, rnd(cout, seed=2)
+    sc, sh = rnd(cout, seed=3) * 0.3 + 1, rnd(cout, seed=4) * 0.2
+    res = rnd(nb, t_out, v, cout, seed=5) if with_res else None
+    for relu in (False, True):
+        y = K.conv_fwd_post(x.cuda(), w.cuda(), b.cuda(), scale=sc.cuda(), shift=sh.cuda(), res=None if res is None else res.cuda(), relu=relu,
+                            t_out=t_out, stride=stride, pad=pad, precision=prec)
+        ref = S.conv_fwd_post(x.double(), w.double(), b.double(), scale=sc.double(), shift=sh.double(), res=None if res is None else res.double(),
+                              relu=relu, t_out=t_out, stride=stride, pad=pad)
+        assert rel_err(y, ref) <= tol
+    y = K.conv_fwd_post(x.cuda(), w.cuda(), None, res=None if res is None else res.cuda(), t_out=t_out, stride=stride, pad=pad, precision=prec)
+    ref = S.conv_fwd_post(x.double(), w.double(), None, res=None if res is None else res.double(), t_out=t_out, stride=stride, pad=pad)
+    assert rel_err(y, ref) <= tol

@@ -28,6 +28,7 @@ for step in "$@"; do
     launcher)  python -m pytest tests/test_gpu_launcher.py -m gpu -q -rf -s -x -p no:cacheprovider > gpurun_out/${tag}_launcher.log 2>&1; tail -12 gpurun_out/${tag}_launcher.log ;;
     benchN)    # BENCH_N=<gpus> [BENCH_ARGS=...]: the driver's multi-GPU launch
                python -m torch.distributed.run --nnodes=1 --nproc-per-node ${BENCH_N:-2} --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus ${BENCH_N:-2} --steps 10 --warmup 3 ${BENCH_ARGS} > gpurun_out/${tag}_bench_n${BENCH_N:-2}.json 2> gpurun_out/${tag}_bench_n${BENCH_N:-2}.err; tail -c 1500 gpurun_out/${tag}_bench_n${BENCH_N:-2}.json; tail -5 gpurun_out/${tag}_bench_n${BENCH_N:-2}.err ;;
+    graphconv) python -m pytest tests/test_graphconv.py -m gpu -q -rf -x -p no:cacheprovider > gpurun_out/${tag}_graphconv.log 2>&1; tail -12 gpurun_out/${tag}_graphconv.log ;;
     *) echo "unknown step $step" ;;
   esac
 done
