@@ -186,6 +186,15 @@ class SpatialGraphConv(nn.Module):
         return _from_cl(self.forward_cl(_to_cl(x)))
 
 
+GCN_WEIGHT_SLOTS_END = FN.GCN_NPARAMS      # conv_a / conv_b / conv_d / down weights live in the gcn half of the parameter list
+
+
+def _padded_channels(c: int) -> int:
+    """Channel count the first unit actually runs on: wide counts that are not a multiple of 32 (C = 515: skeleton + 512-d RGB patch
+    embeddings, early_fusion_models.py:53-60) are zero-padded up so that every contraction of the unit takes the tensor-core path."""
+    return (c + 31) // 32 * 32 if (c > 64 and c % 32) else c
+
+
 class SpatialTemporalConv(nn.Module):
     """relu(tcn1(gcn1(x)) + residual(x)) (agcn.py:118-136)."""
 
@@ -218,6 +227,17 @@ class SpatialTemporalConv(nn.Module):
                            precision=self._agcn_precision, bn_tcn=_bn_buffers(t.bn), pool_groups=pool_groups)
         g._fill_spec(spec)
         params = g._params(x) + list(t._params())
+        cpad = x.shape[-1] - g.in_channels
+        if cpad > 0:
+            # channel-padded input (Model pads wide odd channel counts such as the 515-channel skeleton + RGB fusion to a multiple
+            # of 32 so that the first unit runs on the TMA / tcgen05 kernels): the weights that read x get matching zero columns;
+            # F.pad is differentiable, so their gradients come back in the parameters' own shapes
+            spec.cin = x.shape[-1]
+            for i, prm in enumerate(params[:GCN_WEIGHT_SLOTS_END]):
+                if prm is not None and prm.dim() == 4 and prm.shape[1] == g.in_channels:
+                    params[i] = F.pad(prm, (0, 0, 0, 0, 0, cpad))
+        elif cpad < 0:
+            raise RuntimeError(f"input has {x.shape[-1]} channels, the unit expects {g.in_channels}")
         if self._residual_kind == "conv":
             spec.bn_res = _bn_buffers(self.residual.bn)
             params += list(self.residual._params())
@@ -276,6 +296,9 @@ class Model(nn.Module):
         x = _prep(x)
         buf = FN.BnBuffers(self.data_bn.running_mean, self.data_bn.running_var, self.data_bn.num_batches_tracked)
         h = FN.DataBnFn.apply(x, self.data_bn.weight, self.data_bn.bias, buf, self.training)
+        cp = _padded_channels(h.shape[-1])
+        if cp != h.shape[-1] and self.layers and self.layers[0]._residual_kind == "none":
+            h = F.pad(h, (0, cp - h.shape[-1]))
         for layer in self.layers:
             h = layer(h) if isinstance(layer, nn.Dropout) else layer.forward_cl(h)
         return h
@@ -287,6 +310,9 @@ class Model(nn.Module):
         x = _prep(x)
         buf = FN.BnBuffers(self.data_bn.running_mean, self.data_bn.running_var, self.data_bn.num_batches_tracked)
         h = FN.DataBnFn.apply(x, self.data_bn.weight, self.data_bn.bias, buf, self.training)
+        cp = _padded_channels(h.shape[-1])
+        if cp != h.shape[-1] and self.layers and self.layers[0]._residual_kind == "none":
+            h = F.pad(h, (0, cp - h.shape[-1]))
         for i, layer in enumerate(self.layers):
             if isinstance(layer, nn.Dropout):
                 h = layer(h)

@@ -189,3 +189,18 @@ def test_second_device_and_foreign_current_device(pkg):
     torch.cuda.set_device(0)
     y1 = unit.to("cuda:1")(x.to("cuda:1"))            # current device stays cuda:0
     assert torch.equal(y0.cpu(), y1.cpu())
+
+
+@pytest.mark.parametrize("precision", PARITY_MODES)
+def test_rgb_patch_early_fusion_channel_count_on_the_tensor_cores(pkg, precision):
+    """BASELINE configs[3]: skeleton + per-joint 512-d RGB patch embeddings as extra channels, C = 3 + 512 = 515
+    (early_fusion_models.py:53-60), V = 25.  515 is not a multiple of 4, so Model zero-pads the first unit's input to 544
+    channels and the unit runs on the TMA / tcgen05 kernels; logits and all gradients against the fp64 oracle."""
+    import test_gpu_unit as T
+    from fusion_gcn_b200 import capi, graph as G, modules as M, ops
+    ops.start_timing(("*",))
+    err = T.seeded_model_case(M, G, (1, 24, 25, 515), "ntu", 64, 2, precision, "cuda", tol=3e-4 if precision == "bf16x3" else 1e-4)
+    sigs = ops.stop_timing()
+    first = [sig for (name, sig) in sigs if name == "agcn_conv_fwd" and sig[4] in (544, 3 * 544)]
+    assert first, "the first unit's convolutions must see the padded 544-channel input"
+    print(f"[{precision}] C=515: logits {err['y']:.2e}, worst grad {err['worst_grad']}")

@@ -220,3 +220,14 @@ def test_fused_head_and_pooled_tail_match_the_separate_ops(torch_stage_backend):
     assert abs(float(loss) - float(loss_ref)) <= 1e-12 and torch.allclose(logits, logits_ref, atol=1e-12)
     for (k, a), (_, b) in zip(model.named_parameters(), ref.named_parameters()):
         assert torch.allclose(a.grad, b.grad, rtol=1e-9, atol=1e-12), k
+
+
+def test_wide_odd_channel_counts_are_zero_padded_for_the_first_unit(torch_stage_backend):
+    """C = 70 stands in for the 515-channel skeleton + RGB-patch fusion (early_fusion_models.py:53-60): Model pads the first
+    unit's input (and, through F.pad, its weights) to a multiple of 32; logits and every gradient (in the parameters' own shapes)
+    still match the oracle."""
+    import test_gpu_unit as T
+    from fusion_gcn_b200 import graph as G, modules as M
+    assert M._padded_channels(515) == 544 and M._padded_channels(512) == 512 and M._padded_channels(9) == 9
+    err = T.seeded_model_case(M, G, (1, 12, 20, 70), "utd", 8, 3, "fp32", "cpu")
+    assert err["y"] <= 1e-5
