@@ -180,13 +180,27 @@ class SpatialGraphConv(nn.Module):
     def forward_cl(self, x):
         spec = self._fill_spec(FN.UnitSpec(cin=self.in_channels, cout=self.out_channels, training=self.training,
                                            precision=self._agcn_precision))
-        return FN.GcnFn.apply(x, spec, *self._params(x))
+        params = self._params(x)
+        spec.cin = _pad_input_weights(params, self.in_channels, x.shape[-1])
+        return FN.GcnFn.apply(x, spec, *params)
 
     def forward(self, x):
         return _from_cl(self.forward_cl(_to_cl(x)))
 
 
-GCN_WEIGHT_SLOTS_END = FN.GCN_NPARAMS      # conv_a / conv_b / conv_d / down weights live in the gcn half of the parameter list
+def _pad_input_weights(params, in_channels: int, actual: int) -> int:
+    """Channel-padded input (Model pads wide odd channel counts such as the 515-channel skeleton + RGB fusion to a multiple of 32 so
+    that the first unit runs on the TMA / tcgen05 kernels): the gcn weights that read x (conv_a / conv_b / conv_d / down) get matching
+    zero columns, in place in ``params``.  F.pad is differentiable, so their gradients come back in the parameters' own shapes."""
+    cpad = actual - in_channels
+    if cpad < 0:
+        raise RuntimeError(f"input has {actual} channels, the unit expects {in_channels}")
+    if cpad > 0:
+        for i, prm in enumerate(params[:FN.GCN_NPARAMS]):
+            if prm is not None and prm.dim() == 4 and prm.shape[1] == in_channels:
+                params[i] = F.pad(prm, (0, 0, 0, 0, 0, cpad))
+    return actual
+
 
 
 def _padded_channels(c: int) -> int:
@@ -227,17 +241,7 @@ class SpatialTemporalConv(nn.Module):
                            precision=self._agcn_precision, bn_tcn=_bn_buffers(t.bn), pool_groups=pool_groups)
         g._fill_spec(spec)
         params = g._params(x) + list(t._params())
-        cpad = x.shape[-1] - g.in_channels
-        if cpad > 0:
-            # channel-padded input (Model pads wide odd channel counts such as the 515-channel skeleton + RGB fusion to a multiple
-            # of 32 so that the first unit runs on the TMA / tcgen05 kernels): the weights that read x get matching zero columns;
-            # F.pad is differentiable, so their gradients come back in the parameters' own shapes
-            spec.cin = x.shape[-1]
-            for i, prm in enumerate(params[:GCN_WEIGHT_SLOTS_END]):
-                if prm is not None and prm.dim() == 4 and prm.shape[1] == g.in_channels:
-                    params[i] = F.pad(prm, (0, 0, 0, 0, 0, cpad))
-        elif cpad < 0:
-            raise RuntimeError(f"input has {x.shape[-1]} channels, the unit expects {g.in_channels}")
+        spec.cin = _pad_input_weights(params, g.in_channels, x.shape[-1])
         if self._residual_kind == "conv":
             spec.bn_res = _bn_buffers(self.residual.bn)
             params += list(self.residual._params())
