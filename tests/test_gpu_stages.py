@@ -292,8 +292,9 @@ def test_pool(K, groups, rows, c):
 def test_error_paths_raise(K):
     with pytest.raises(RuntimeError, match="CUDA"):
         K.conv_fwd(torch.randn(1, 2, 3, 4), torch.randn(4, 1, 4).cuda())
-    with pytest.raises(RuntimeError, match="status 2"):
-        K.joint_mix(torch.randn(1, 2, 40, 8).cuda(), torch.randn(1, 3, 40, 40).cuda(), width=8, mode=K.MIX_AGG_FWD)
+    with pytest.raises(RuntimeError, match="status 2"):       # graphs with more than 32 nodes reduce their gram in ONE chunk
+        e = torch.randn(1, 4, 40, 8).cuda()
+        K.joint_gram(e, e, groups=1, offa=0, stridea=0, offb=0, strideb=0, width=8, nchunk=2)
 
 
 def _trunc_tf32(t):
