@@ -568,9 +568,10 @@ static bool known_precision(int p) { return p >= AGCN_PREC_FP32 && p <= AGCN_PRE
 
 extern "C" AGCN_API size_t agcn_conv_fwd_workspace_bytes(int cin, int cout, int taps, int precision) {
     if ((precision != AGCN_PREC_FP32 && precision != AGCN_PREC_BF16X3) || cin <= 0 || cout <= 0 || taps <= 0) return 0;
-    // TF32 hi | lo split of the weights for the 3xTF32 path; the BF16x3 path needs half of it (bf16 h | m) and falls back to 3xTF32
-    // for channel counts that are not a multiple of 16
-    return (size_t)2 * cout * taps * cin * sizeof(float);
+    // strict mode: rna_tf32(w) as fp32 followed by the bf16 [hi16 | lo16] cross rows of every 32-channel K chunk (padded to whole
+    // chunks); the BF16x3 path needs less (bf16 h | m) and falls back to the strict kernels for channel counts not a multiple of 16
+    const size_t nchunk = (size_t)(cin + 31) / 32;
+    return (size_t)cout * taps * cin * sizeof(float) + (size_t)cout * taps * nchunk * 128;
 }
 
 static int conv_fwd_impl(const float* x, const float* w, const float* bias, float* y,

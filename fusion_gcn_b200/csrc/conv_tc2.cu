@@ -193,7 +193,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         if (leader) {
                             mbar_expect_tx(b_full(sb), b_tx);
                             tma_load_3d(b_ring + (uint32_t)sb * b_slot, &map_b, b_full(sb), kc * kChunkCh, a.tap_id[par][i], nt * a.bn);
-                            if (CONV) tma_load_3d(b_ring + (uint32_t)sb * b_slot + a.b_stage_bytes, &map_blo, b_full(sb), kc * kChunkCh, a.tap_id[par][i], nt * a.bn);
+                            // second half of the weight slot: BF16x3 m pieces / strict mode [hi16 | lo16] cross rows -- 64 bf16 per K chunk either way
+                            if (CONV) tma_load_3d(b_ring + (uint32_t)sb * b_slot + a.b_stage_bytes, &map_blo, b_full(sb), kc * 64, a.tap_id[par][i], nt * a.bn);
                         }
                         __syncwarp();
                         if (++sb == a.nbst) { sb = 0; pb ^= 1u; }
@@ -213,6 +214,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             constexpr uint32_t kFmt = BF ? 1u : 2u;          // operand format: 1 = BF16 (kind::f16), 2 = TF32
             const uint32_t idesc = (1u << 4) | (kFmt << 7) | (kFmt << 10) | ((uint32_t)(a.bn >> 3) << 17) | ((128u >> 4) << 24);
             const uint32_t idesc_wide = (1u << 4) | (kFmt << 7) | (kFmt << 10) | ((uint32_t)((2 * a.bn) >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc_bf = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.bn >> 3) << 17) | ((128u >> 4) << 24);     // BF16 x BF16, N = bn
             int sa = 0; uint32_t pa = 0;
             int sb = 0; uint32_t pb = 0;
             int acc = 0; uint32_t acc_phase = 0;
@@ -263,34 +265,28 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                                     }
                                 }
                             }
-                        } else if (SPLIT && a.dual) {
-                            // narrow tiles: ONE MMA of width 2*bn against [W_hi ; W_lo] (adjacent in the weight slot) yields x_hi.W_hi in
-                            // the main columns and x_hi.W_lo in the cross columns; a second one adds x_lo.W_hi to the cross columns.
-                            // Two instructions and two reads of the activation tile per K step instead of three.
+                        } else if (SPLIT) {
+                            // strict fp32 mode: hi*hi on kind::tf32 (four K steps of 8 channels) + the two cross terms lo*hi + hi*lo on
+                            // kind::f16 from the [hi16 | lo16] rows (two K steps of 16 channels; lo half 64 bytes = 4 descriptor units
+                            // along K).  a.dual: the cross terms accumulate in their own TMEM columns.
 #pragma unroll
                             for (int k = 0; k < kKChunk / 8; ++k) {
                                 if ((a.dbg & 2) && k) break;
-                                const uint64_t ko = (uint64_t)(k * 2);
-                                const uint32_t fresh = (k == 0) ? first : 0u;
-                                umma_tf32(d_tmem, da + ko, db + ko, idesc_wide, fresh ^ 1u);
-                                umma_tf32(d_tmem + cross_off, dalo + ko, db + ko, idesc, 1u);
+                                umma_tf32(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, ((k == 0) ? first : 0u) ^ 1u);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                const uint64_t ko = (uint64_t)(j * 2);
+                                const uint32_t fresh_c = (j == 0) ? (first & main_first) : 0u;       // dual: the cross columns start fresh too
+                                umma_bf16(d_tmem + cross_off, dalo + 4u + ko, dblo + ko, idesc_bf, fresh_c ^ 1u);
+                                umma_bf16(d_tmem + cross_off, dalo + ko, dblo + 4u + ko, idesc_bf, 1u);
                             }
                         } else {
 #pragma unroll
-                        for (int k = 0; k < kKChunk / 8; ++k) {
-                            if ((a.dbg & 2) && k) break;
-                            const uint64_t ko = (uint64_t)(k * 2);
-                            const uint32_t fresh = (k == 0) ? first : 0u;       // first MMA of an accumulator segment overwrites
-                            if (SPLIT) {
-                                // cross terms into d_tmem + cross_off (0 = same accumulator as the hi*hi chain); branch-free on purpose:
-                                // this single-thread issue loop is latency-critical (a data-dependent branch here cost 15 %, profiles/r2f)
-                                umma_tf32(d_tmem + cross_off, dalo + ko, db + ko, idesc, fresh ^ 1u);
-                                umma_tf32(d_tmem + cross_off, da + ko, dblo + ko, idesc, 1u);
-                                umma_tf32(d_tmem, da + ko, db + ko, idesc, (fresh & main_first) ^ 1u);
-                            } else {
-                                umma_tf32(d_tmem, da + ko, db + ko, idesc, fresh ^ 1u);
+                            for (int k = 0; k < kKChunk / 8; ++k) {
+                                if ((a.dbg & 2) && k) break;
+                                umma_tf32(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, ((k == 0) ? first : 0u) ^ 1u);
                             }
-                        }
                         }
                         if (!a.w_resident) umma_commit(b_empty(sb));
                         }
@@ -564,8 +560,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 mbar_wait(lo_empty(sl), pl ^ 1u);
                 const uint32_t src = smem_base + (uint32_t)sa * a_slot;
                 const uint32_t dst = lo_ring + (uint32_t)sl * a_slot;
-                for (int b = 0; b < ((a.dbg & 1) ? 0 : a.nblk); ++b)
-                    transform_split4(src + (uint32_t)b * a.blk_bytes, dst + (uint32_t)b * a.blk_bytes, a.blk_rows_bytes, tids, kSplitWarps * 32);
+                // one thread per activation row: hi (TF32-rounded) in place, [hi16 | lo16] cross row into the lo ring slot
+                const int rows = (int)(a.blk_rows_bytes >> 7);
+                for (int idx = tids; idx < ((a.dbg & 1) ? 0 : a.nblk * rows); idx += kSplitWarps * 32) {
+                    const int b = idx >= rows ? 1 : 0;
+                    const int r = idx - b * rows;
+                    const uint32_t off = (uint32_t)b * a.blk_bytes + (uint32_t)r * 128u;
+                    tf32_cross_row(src + off, dst + off, (uint32_t)(r & 7));
+                }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(a_lo(sa));
@@ -595,6 +597,28 @@ static __global__ void split_weights_bf16_kernel(const float* w, uint16_t* w_spl
         w_split[i] = (uint16_t)(hb >> 16);
         w_split[n + i] = (uint16_t)((__float_as_uint(v - __uint_as_float(hb)) + 0x8000u) >> 16);
     }
+}
+
+// Weights of the strict fp32 mode: w_hi [cout][taps][cin] fp32 = rna_tf32(w) (kind::tf32 operand of hi*hi) and cross
+// [cout][taps][nchunk][64] bf16, every 32-channel K chunk stored as one 128-byte row [bf16(hi) | bf16(w - hi)] (channels past cin: 0).
+static __global__ void split_weights_cross_kernel(const float* w, float* w_hi, uint16_t* cross, long long rows, int cin, int nchunk) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // (row, chunk, channel in chunk)
+    if (i >= rows * nchunk * 32) return;
+    const int c = (int)(i & 31);
+    const long long rc = i >> 5;
+    const int kc = (int)(rc % nchunk);
+    const long long row = rc / nchunk;
+    const int ch = kc * 32 + c;
+    uint16_t h = 0, l = 0;
+    if (ch < cin) {
+        const float v = w[row * cin + ch];
+        const float hi = agcn::tc::tf32_rna(v);
+        w_hi[row * cin + ch] = hi;
+        h = (uint16_t)((__float_as_uint(hi) + 0x8000u) >> 16);
+        l = (uint16_t)((__float_as_uint(v - hi) + 0x8000u) >> 16);
+    }
+    cross[rc * 64 + c] = h;
+    cross[rc * 64 + 32 + c] = l;
 }
 
 // Returns AGCN_ERR_UNSUPPORTED for shapes outside this path (the caller then tries the next kernel).
@@ -664,7 +688,9 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
     // main | cross accumulator pairs: multi-segment tiles up to 64 wide (2*bn <= 128 next to the master sums), single-segment
     // tiles (1x1 convs with cin <= 256: no master sums) up to 128 wide (2*bn <= 256 = one of the two accumulator buffers)
     a.dual = (split && !no_dual && ((kiters > seg_cap && bn <= 64) || (kiters <= seg_cap && bn <= 128))) ? 1 : 0;
-    a.seg_iters = (split && kiters <= seg_cap) ? seg_cap : (a.dual ? 3 * kSegment : kSegment);
+    // strict mode: an iteration chains 4 hi*hi MMAs (+ 4 cross MMAs when they share the accumulator): 8 iterations = 64 adds per
+    // segment without the dual columns, 12 iterations = 48 main adds with them
+    a.seg_iters = (split && kiters <= seg_cap) ? seg_cap : (a.dual ? 3 * kSegment : 2 * kSegment);
     a.acc_stride = (bn > 128 || (a.dual && 2 * bn > 128)) ? 256 : 128;
     a.tt = 128 / v;
     a.bn = bn;
@@ -816,11 +842,25 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
         CUresult r = encode_w(&map_b, split ? static_cast<const void*>(w_split) : static_cast<const void*>(w));
         if (r != CUDA_SUCCESS) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc2: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
         map_blo = map_b;
-        if (split) {
-            r = encode_w(&map_blo, bf ? static_cast<const void*>(reinterpret_cast<uint16_t*>(w_split) + nw) : static_cast<const void*>(w_split + nw));
+        if (bf) {
+            r = encode_w(&map_blo, static_cast<const void*>(reinterpret_cast<uint16_t*>(w_split) + nw));
             if (r != CUDA_SUCCESS) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc2: cuTensorMapEncodeTiled(B lo) failed with %d", (int)r);
-            if (bf) split_weights_bf16_kernel<<<ceil_div(nw, 256), 256, 0, st>>>(w, reinterpret_cast<uint16_t*>(w_split), nw);
-            else split_weights_kernel<<<ceil_div(nw, 256), 256, 0, st>>>(w, w_split, nw);
+            split_weights_bf16_kernel<<<ceil_div(nw, 256), 256, 0, st>>>(w, reinterpret_cast<uint16_t*>(w_split), nw);
+            int rc = check_launch("agcn_conv_fwd_tc2(split weights)");
+            if (rc) return rc;
+        } else if (split) {
+            // strict mode: cross rows [hi16 | lo16] of every 32-channel K chunk behind the fp32 hi tensor
+            const int nchunk = (cin + kKChunk - 1) / kKChunk;
+            uint16_t* cross = reinterpret_cast<uint16_t*>(w_split + nw);
+            cuuint64_t dims[3] = {(cuuint64_t)nchunk * 64, (cuuint64_t)taps, (cuuint64_t)cout};
+            cuuint64_t strides[2] = {(cuuint64_t)nchunk * 128, (cuuint64_t)taps * nchunk * 128};
+            cuuint32_t box[3] = {64u, 1u, (cuuint32_t)bn};
+            cuuint32_t estr[3] = {1, 1, 1};
+            r = enc(&map_blo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, cross, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc2: cuTensorMapEncodeTiled(B cross) failed with %d", (int)r);
+            const long long n = (long long)cout * taps * nchunk * 32;
+            split_weights_cross_kernel<<<ceil_div(n, 256), 256, 0, st>>>(w, w_split, cross, (long long)cout * taps, cin, nchunk);
             int rc = check_launch("agcn_conv_fwd_tc2(split weights)");
             if (rc) return rc;
         }
