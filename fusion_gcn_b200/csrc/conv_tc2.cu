@@ -560,13 +560,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 mbar_wait(lo_empty(sl), pl ^ 1u);
                 const uint32_t src = smem_base + (uint32_t)sa * a_slot;
                 const uint32_t dst = lo_ring + (uint32_t)sl * a_slot;
-                // one thread per activation row: hi (TF32-rounded) in place, [hi16 | lo16] cross row into the lo ring slot
+                // one thread per QUARTER row (8 channels): hi (TF32-rounded) in place, [hi16 | lo16] cross row into the lo ring slot
                 const int rows = (int)(a.blk_rows_bytes >> 7);
-                for (int idx = tids; idx < ((a.dbg & 1) ? 0 : a.nblk * rows); idx += kSplitWarps * 32) {
-                    const int b = idx >= rows ? 1 : 0;
-                    const int r = idx - b * rows;
+                for (int idx = tids; idx < ((a.dbg & 1) ? 0 : a.nblk * rows * 4); idx += kSplitWarps * 32) {
+                    const int rr = idx >> 2;
+                    const int b = rr >= rows ? 1 : 0;
+                    const int r = rr - b * rows;
                     const uint32_t off = (uint32_t)b * a.blk_bytes + (uint32_t)r * 128u;
-                    tf32_cross_row(src + off, dst + off, (uint32_t)(r & 7));
+                    tf32_cross_quarter(src + off, dst + off, (uint32_t)(r & 7), (uint32_t)(idx & 3));
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();

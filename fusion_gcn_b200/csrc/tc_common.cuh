@@ -238,32 +238,25 @@ __device__ __forceinline__ void bf16_interleave_row(uint32_t p, uint32_t sw) {
 // lo16 half at (4 + q) ^ sw): the kind::f16 operand of the two cross products lo_a*hi_b + hi_a*lo_b.  |lo| <= 2^-11 |x| and bf16 keeps
 // 8 bits, so each cross term carries a relative error of 2^-20 -- the product is a*b to ~3 x 2^-20, at 2 instead of 3 TF32-equivalent
 // MMAs and 2/3 of the operand bytes of 3xTF32.
-__device__ __forceinline__ void tf32_cross_row(uint32_t p, uint32_t pc, uint32_t sw) {
-    float4 f[8];
+// Work item = a QUARTER of a row (8 channels: fp32 chunks 2*qd, 2*qd + 1 -> hi in place, one 16-byte chunk of hi16 and one of lo16),
+// so a 125-row tile keeps all 256 converter threads busy and the rows of a quarter-warp hit eight different bank groups.
+__device__ __forceinline__ void tf32_cross_quarter(uint32_t p, uint32_t pc, uint32_t sw, uint32_t qd) {
+    const float4 f0 = lds128(p + (((2u * qd) ^ sw) << 4)), f1 = lds128(p + (((2u * qd + 1u) ^ sw) << 4));
+    const float x[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+    float hi[8];
+    uint32_t hb[8], lb[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = lds128(p + (((uint32_t)j ^ sw) << 4));
-    uint4 h16[4], l16[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const float x[8] = {f[2 * q].x, f[2 * q].y, f[2 * q].z, f[2 * q].w, f[2 * q + 1].x, f[2 * q + 1].y, f[2 * q + 1].z, f[2 * q + 1].w};
-        float hi[8];
-        uint32_t hb[8], lb[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            hi[i] = tf32_rna(x[i]);
-            hb[i] = __float_as_uint(hi[i]) + 0x8000u;                 // bf16(hi), upper half kept by the byte permute
-            lb[i] = __float_as_uint(x[i] - hi[i]) + 0x8000u;          // bf16(lo), lo = x - hi exact
-        }
-        sts128(p + (((uint32_t)(2 * q) ^ sw) << 4), make_float4(hi[0], hi[1], hi[2], hi[3]));
-        sts128(p + (((uint32_t)(2 * q + 1) ^ sw) << 4), make_float4(hi[4], hi[5], hi[6], hi[7]));
-        h16[q] = make_uint4(__byte_perm(hb[0], hb[1], 0x7632), __byte_perm(hb[2], hb[3], 0x7632), __byte_perm(hb[4], hb[5], 0x7632), __byte_perm(hb[6], hb[7], 0x7632));
-        l16[q] = make_uint4(__byte_perm(lb[0], lb[1], 0x7632), __byte_perm(lb[2], lb[3], 0x7632), __byte_perm(lb[4], lb[5], 0x7632), __byte_perm(lb[6], lb[7], 0x7632));
+    for (int i = 0; i < 8; ++i) {
+        hi[i] = tf32_rna(x[i]);
+        hb[i] = __float_as_uint(hi[i]) + 0x8000u;                 // bf16(hi), upper half kept by the byte permute
+        lb[i] = __float_as_uint(x[i] - hi[i]) + 0x8000u;          // bf16(lo), lo = x - hi exact
     }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        sts128u(pc + (((uint32_t)q ^ sw) << 4), h16[q]);
-        sts128u(pc + (((uint32_t)(q + 4) ^ sw) << 4), l16[q]);
-    }
+    sts128(p + (((2u * qd) ^ sw) << 4), make_float4(hi[0], hi[1], hi[2], hi[3]));
+    sts128(p + (((2u * qd + 1u) ^ sw) << 4), make_float4(hi[4], hi[5], hi[6], hi[7]));
+    sts128u(pc + ((qd ^ sw) << 4), make_uint4(__byte_perm(hb[0], hb[1], 0x7632), __byte_perm(hb[2], hb[3], 0x7632),
+                                              __byte_perm(hb[4], hb[5], 0x7632), __byte_perm(hb[6], hb[7], 0x7632)));
+    sts128u(pc + (((qd + 4u) ^ sw) << 4), make_uint4(__byte_perm(lb[0], lb[1], 0x7632), __byte_perm(lb[2], lb[3], 0x7632),
+                                                     __byte_perm(lb[4], lb[5], 0x7632), __byte_perm(lb[6], lb[7], 0x7632)));
 }
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
