@@ -24,14 +24,15 @@ def build(force=False, verbose=False, probes=False):
     if not force and not probes and not _stale():
         return OUT
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + FLAGS + (["-DAGCN_PROBES"] if probes else []) + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcuda"]
+    out = OUT.replace(".so", "_probes.so") if probes else OUT        # the probe build never replaces the product library
+    cmd = [nvcc] + FLAGS + (["-DAGCN_PROBES"] if probes else []) + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcuda"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError("nvcc failed building libagcn_b200.so")
     if verbose:
         sys.stderr.write(res.stderr)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

@@ -9,7 +9,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libagcn_b200.so")
+# AGCN_B200_LIB: another build of the same library (e.g. the -DAGCN_PROBES build of tools/, never the product path)
+LIB_PATH = os.environ.get("AGCN_B200_LIB") or os.path.join(_HERE, "libagcn_b200.so")
 
 PREC_FP32 = 0          # fp32 parity: 3xTF32 tensor cores where possible, FFMA otherwise
 PREC_TF32 = 1          # single-pass TF32 tensor cores

@@ -87,7 +87,10 @@ struct Tc2Args {
 };
 
 // MODE: 0 single-pass TF32, 1 3xTF32 (fp32 parity), 2 BF16x3 (fp32 parity, bf16 triple products)
-template <int MODE>
+// POST: the eval-mode fused tail (PostOp) is compiled in -- a template parameter so that the training kernels, whose 480-thread
+// variants sit at the 128-register cap, do not carry its registers (with it folded in at run time the epilogue spilled and the
+// output-heavy 1x1 convolutions lost 25 %, profiles/r3q).
+template <int MODE, bool POST>
 __global__ void __launch_bounds__(MODE != 0 ? kThreads2Split : kThreads2, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_y0,
@@ -385,6 +388,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                                     float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
                                     if (a.bias) bq = __ldg(reinterpret_cast<const float4*>(a.bias + nt * a.bn + c0 + g * 4));
                                     float4 o = make_float4(vals[g * 4] + bq.x, vals[g * 4 + 1] + bq.y, vals[g * 4 + 2] + bq.z, vals[g * 4 + 3] + bq.w);
+                                    if constexpr (POST) {
                                     if (a.post.scale) {
                                         const float4 sc = __ldg(reinterpret_cast<const float4*>(a.post.scale + nt * a.bn + c0 + g * 4));
                                         const float4 sh = __ldg(reinterpret_cast<const float4*>(a.post.shift + nt * a.bn + c0 + g * 4));
@@ -395,6 +399,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                                         o.x += rq.x; o.y += rq.y; o.z += rq.z; o.w += rq.w;
                                     }
                                     if (a.post.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                                    }
                                     sts128(srow + (((uint32_t)g ^ sw) << 4), o);
                                 }
                             }
@@ -455,7 +460,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                             float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (a.bias && col_ok) bq = __ldg(reinterpret_cast<const float4*>(a.bias + nt * a.bn + c0 + cq * 4));
                             float4 psc = make_float4(1.f, 1.f, 1.f, 1.f), psh = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (a.post.scale && col_ok) {
+                            if (POST && a.post.scale && col_ok) {
                                 psc = __ldg(reinterpret_cast<const float4*>(a.post.scale + nt * a.bn + c0 + cq * 4));
                                 psh = __ldg(reinterpret_cast<const float4*>(a.post.shift + nt * a.bn + c0 + cq * 4));
                             }
@@ -472,7 +477,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                                     oldv[r4] = make_float4(0.f, 0.f, 0.f, 0.f);
                                     if (a.accumulate && offs[r4] >= 0 && col_ok)
                                         oldv[r4] = *reinterpret_cast<const float4*>(a.y + offs[r4] + c0 + cq * 4);
-                                    else if (a.post.res && offs[r4] >= 0 && col_ok)           // eval tail: residual added AFTER the affine
+                                    else if (POST && a.post.res && offs[r4] >= 0 && col_ok)   // eval tail: residual added AFTER the affine
                                         oldv[r4] = __ldg(reinterpret_cast<const float4*>(a.post.res + offs[r4] + c0 + cq * 4));
                                 }
 #pragma unroll
@@ -480,9 +485,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                                     const int src_lane = (half * 4 + r4) * 4 + (lane >> 3);
                                     if (offs[r4] >= 0 && col_ok) {
                                         float4 o = lds128(stage_base + (uint32_t)src_lane * kStagePitch + (uint32_t)cq * 16u);
-                                        o.x = fmaf(o.x + bq.x, psc.x, psh.x) + oldv[r4].x; o.y = fmaf(o.y + bq.y, psc.y, psh.y) + oldv[r4].y;
-                                        o.z = fmaf(o.z + bq.z, psc.z, psh.z) + oldv[r4].z; o.w = fmaf(o.w + bq.w, psc.w, psh.w) + oldv[r4].w;
-                                        if (a.post.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                                        if constexpr (POST) {
+                                            o.x = fmaf(o.x + bq.x, psc.x, psh.x) + oldv[r4].x; o.y = fmaf(o.y + bq.y, psc.y, psh.y) + oldv[r4].y;
+                                            o.z = fmaf(o.z + bq.z, psc.z, psh.z) + oldv[r4].z; o.w = fmaf(o.w + bq.w, psc.w, psh.w) + oldv[r4].w;
+                                            if (a.post.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                                        } else {
+                                            o.x += bq.x + oldv[r4].x; o.y += bq.y + oldv[r4].y; o.z += bq.z + oldv[r4].z; o.w += bq.w + oldv[r4].w;
+                                        }
                                         *reinterpret_cast<float4*>(a.y + offs[r4] + c0 + cq * 4) = o;
                                         ssum.x += o.x; ssum.y += o.y; ssum.z += o.z; ssum.w += o.w;
                                         ssq.x = fmaf(o.x, o.x, ssq.x); ssq.y = fmaf(o.y, o.y, ssq.y); ssq.z = fmaf(o.z, o.z, ssq.z); ssq.w = fmaf(o.w, o.w, ssq.w);
@@ -885,9 +894,13 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
         }
     }
     {   // per call: the attribute is per device / context, a process-wide flag would skip the second GPU
-        cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+        auto opt_in = [](auto kern) { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget); };
+        cudaError_t e = opt_in(conv_tc2_kernel<0, false>);
+        if (e == cudaSuccess) e = opt_in(conv_tc2_kernel<1, false>);
+        if (e == cudaSuccess) e = opt_in(conv_tc2_kernel<2, false>);
+        if (e == cudaSuccess && post) e = opt_in(conv_tc2_kernel<0, true>);
+        if (e == cudaSuccess && post) e = opt_in(conv_tc2_kernel<1, true>);
+        if (e == cudaSuccess && post) e = opt_in(conv_tc2_kernel<2, true>);
         if (e != cudaSuccess) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc2: %s", cudaGetErrorString(e));
     }
     if (skipped_parity && !accumulate) {
@@ -896,9 +909,15 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
         if (e != cudaSuccess) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc2: cudaMemsetAsync: %s", cudaGetErrorString(e));
     }
     const long long grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
-    if (split == 2) conv_tc2_kernel<2><<<(unsigned)grid, kThreads2Split, smem, st>>>(map_a, map_b, map_blo, map_y0, map_y1, a);
-    else if (split) conv_tc2_kernel<1><<<(unsigned)grid, kThreads2Split, smem, st>>>(map_a, map_b, map_blo, map_y0, map_y1, a);
-    else conv_tc2_kernel<0><<<(unsigned)grid, kThreads2, smem, st>>>(map_a, map_b, map_blo, map_y0, map_y1, a);
+    if (post) {
+        if (split == 2) conv_tc2_kernel<2, true><<<(unsigned)grid, kThreads2Split, smem, st>>>(map_a, map_b, map_blo, map_y0, map_y1, a);
+        else if (split) conv_tc2_kernel<1, true><<<(unsigned)grid, kThreads2Split, smem, st>>>(map_a, map_b, map_blo, map_y0, map_y1, a);
+        else conv_tc2_kernel<0, true><<<(unsigned)grid, kThreads2, smem, st>>>(map_a, map_b, map_blo, map_y0, map_y1, a);
+    } else {
+        if (split == 2) conv_tc2_kernel<2, false><<<(unsigned)grid, kThreads2Split, smem, st>>>(map_a, map_b, map_blo, map_y0, map_y1, a);
+        else if (split) conv_tc2_kernel<1, false><<<(unsigned)grid, kThreads2Split, smem, st>>>(map_a, map_b, map_blo, map_y0, map_y1, a);
+        else conv_tc2_kernel<0, false><<<(unsigned)grid, kThreads2, smem, st>>>(map_a, map_b, map_blo, map_y0, map_y1, a);
+    }
     if (stat_nparts != nullptr) *stat_nparts = stat_part != nullptr ? (int)grid * 4 : 0;
     return check_launch("agcn_conv_fwd_tc2");
 }

@@ -303,7 +303,10 @@ def _like(grads, params):
     return [None if (g is None or p is None) else g.reshape(p.shape) for g, p in zip(grads, params)]
 
 
-def _need_backward(spec):
+def _need_backward(spec, store=True):
+    if store is None:
+        raise RuntimeError("fusion_gcn_b200: backward through the same forward a second time (retain_graph=True) is not supported: "
+                           "the saved activations are released after the first backward")
     if not spec.training:
         raise NotImplementedError("fusion_gcn_b200: backward through eval-mode BatchNorm is not implemented "
                                   "(use model.train() for training, torch.no_grad() for evaluation)")
@@ -322,7 +325,7 @@ class GcnFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_o):
         spec, p = ctx.spec, ctx.params
-        _need_backward(spec)
+        _need_backward(spec, ctx.store)
         dx, g = gcn_backward(d_o.contiguous(), ctx.store, p[20], p[24], p[22], spec, need_dx=ctx.needs_input_grad[0])
         ctx.store = None
         return (dx, None, *_like(_gcn_grad_tuple(g), p))
@@ -341,7 +344,7 @@ class TcnFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_out):
         spec, p = ctx.spec, ctx.params
-        _need_backward(spec)
+        _need_backward(spec, ctx.store)
         d_o, d_xres, g = tcn_backward(d_out.contiguous(), ctx.store, p[2], p[6], spec,
                                       need_dres=ctx.needs_input_grad[1], need_do=ctx.needs_input_grad[0])
         ctx.store = None
@@ -364,7 +367,7 @@ class UnitFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_out):
         spec, params = ctx.spec, ctx.params
-        _need_backward(spec)
+        _need_backward(spec, ctx.store)
         gp, tp = params[:GCN_NPARAMS], params[GCN_NPARAMS:]
         need_dx = ctx.needs_input_grad[0]
         d_o, d_xres, tg = tcn_backward(d_out.contiguous(), ctx.store, tp[2], tp[6], spec, need_dres=need_dx, need_do=True)

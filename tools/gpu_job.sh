@@ -29,6 +29,8 @@ for step in "$@"; do
     benchN)    # BENCH_N=<gpus> [BENCH_ARGS=...]: the driver's multi-GPU launch
                python -m torch.distributed.run --nnodes=1 --nproc-per-node ${BENCH_N:-2} --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus ${BENCH_N:-2} --steps 10 --warmup 3 ${BENCH_ARGS} > gpurun_out/${tag}_bench_n${BENCH_N:-2}.json 2> gpurun_out/${tag}_bench_n${BENCH_N:-2}.err; tail -c 1500 gpurun_out/${tag}_bench_n${BENCH_N:-2}.json; tail -5 gpurun_out/${tag}_bench_n${BENCH_N:-2}.err ;;
     graphconv) python -m pytest tests/test_graphconv.py -m gpu -q -rf -x -p no:cacheprovider > gpurun_out/${tag}_graphconv.log 2>&1; tail -12 gpurun_out/${tag}_graphconv.log ;;
+    probes)    # PROBE_CASES="case ..." PROBE_DBG="0 1 8 ..." : AGCN_CONV_DEBUG limiter probes on the -DAGCN_PROBES build (timing only)
+               for d in $PROBE_DBG; do echo "== AGCN_CONV_DEBUG=$d"; AGCN_B200_LIB=$PWD/fusion_gcn_b200/libagcn_b200_probes.so AGCN_CONV_DEBUG=$d python tools/bench_stage.py $PROBE_CASES ${PROBE_FLAGS}; done > gpurun_out/${tag}_probes.log 2>&1; cat gpurun_out/${tag}_probes.log ;;
     *) echo "unknown step $step" ;;
   esac
 done
