@@ -356,11 +356,13 @@ static WgPlan plan_wgrad(int nb, int t_in, int t_out, int v, int cin, int cout, 
     // probes in profiles/r1v, r1w), so stages are as tall as shared memory allows: TF32 four stages of 48 KB; 3xTF32 three raw
     // stages + two lo slots in 200 KB (40 KB each).
     static const int split_kb = probe_env("AGCN_WG_SPLIT_KB") ? atoi(probe_env("AGCN_WG_SPLIT_KB")) : 40;
-    int rmax = ((split == 1 ? split_kb : 48) * 1024) / (nsub * 128);
+    a.flat = (stride == 1 && t_in == t_out) ? 1 : 0;
+    // strided / shortened outputs load whole timesteps (V rows each): 64 KB stages there, so that two timesteps of a 25-joint
+    // skeleton fit one stage instead of one (half the stages, barriers and MMA issue rounds per row)
+    int rmax = ((split == 1 ? split_kb : (bf && !a.flat ? 64 : 48)) * 1024) / (nsub * 128);
     rmax = bf ? rmax / 16 * 16 : rmax / 8 * 8;                                     // BF16x3: UMMA K = 16 rows
     if (rmax > 128) rmax = 128;
     if (rmax < 8) return p;
-    a.flat = (stride == 1 && t_in == t_out) ? 1 : 0;
     // two taps per tile when the output channels fill only half of the M = 128 atom (flat layout only: the second tap is
     // the same dy rows V positions earlier)
     a.pair = (a.flat && taps > 1 && cout <= 64) ? 1 : 0;
