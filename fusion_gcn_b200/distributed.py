@@ -55,8 +55,11 @@ class _Bucket:
                 rows.append([self.flat.data_ptr() + 4 * off, p.grad.data_ptr(), 0, 0, n])
                 items += [(i, c) for c in range((n + chunk - 1) // chunk)]
                 off += n
-            self._table = torch.tensor(rows, dtype=torch.int64).to(self.flat.device)
-            self._items = torch.tensor(items, dtype=torch.int32).to(self.flat.device)
+            # pinned staging (kept alive): the upload is then legal inside a CUDA-graph capture, where the gradients get their
+            # final, static addresses
+            self._host = (torch.tensor(rows, dtype=torch.int64).pin_memory(), torch.tensor(items, dtype=torch.int32).pin_memory())
+            self._table = self._host[0].to(self.flat.device, non_blocking=True)
+            self._items = self._host[1].to(self.flat.device, non_blocking=True)
             self._nitems, self._key = len(items), key
         return self._table, self._items, self._nitems
 

@@ -51,9 +51,9 @@ class _FusedOptimizer(torch.optim.Optimizer):
         for i, k in enumerate(key):
             rows.append(list(k))
             items += [(i, c) for c in range((k[4] + chunk - 1) // chunk)]
-        table = torch.tensor(rows, dtype=torch.int64).to(dev)
-        work = torch.tensor(items, dtype=torch.int32).to(dev)
-        self._cache[id(group)] = (key, table, work, len(items))
+        host = (torch.tensor(rows, dtype=torch.int64).pin_memory(), torch.tensor(items, dtype=torch.int32).pin_memory())
+        table, work = host[0].to(dev, non_blocking=True), host[1].to(dev, non_blocking=True)      # pinned: legal under graph capture
+        self._cache[id(group)] = (key, table, work, len(items), host)
         return table, work, len(items)
 
     def _amp(self):

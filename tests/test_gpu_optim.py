@@ -134,3 +134,38 @@ def test_training_steps_on_the_model_match_torch_sgd(O):
             o.step()
     for (k, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):
         assert torch.allclose(b, a, rtol=1e-5, atol=1e-7), k        # (zero-gradient biases move by rounding noise only: absolute bound)
+
+
+def test_optimizer_step_inside_the_captured_step_graph(O):
+    """zero-grad + forward + loss + backward + FusedSGD.step() as ONE CUDA graph (GraphedStep(after_backward=opt.step)): the
+    pointer tables are uploaded from pinned memory, so building them during capture -- when the gradients get their static
+    addresses -- is legal; three replays match three eager torch.optim.SGD steps on a twin."""
+    from fusion_gcn_b200 import graph as G, modules as M
+    from fusion_gcn_b200.graphed import GraphedStep
+    torch.manual_seed(1)
+    graph = G.SkeletonGraph(G.UTD_EDGES, center_joint=G.UTD_CENTER)
+    m1 = M.Model((1, 16, 20, 3), 27, graph, start_feature_size=16).cuda().train()
+    m2 = copy.deepcopy(m1)
+    kw = dict(lr=0.02, momentum=0.9, nesterov=True, weight_decay=1e-4)
+    x = torch.randn(4, 1, 16, 20, 3, device="cuda")
+    y = torch.randint(0, 27, (4,), device="cuda")
+    lf = torch.nn.CrossEntropyLoss()
+    o1 = O.FusedSGD(m1.parameters(), **kw)
+    for p in m1.parameters():                  # momentum buffers exist before capture (torch creates them on the first step)
+        o1.state[p]["momentum_buffer"] = torch.zeros_like(p)
+    state0 = copy.deepcopy(m1.state_dict())
+    step = GraphedStep(m1, lf, x, y, warmup=1, after_backward=o1.step)
+    m1.load_state_dict(state0)                 # undo the warm-up / capture-time updates
+    for p in m1.parameters():
+        o1.state[p]["momentum_buffer"].zero_()
+    o2 = torch.optim.SGD(m2.parameters(), **kw)
+    for p in m2.parameters():
+        o2.state[p]["momentum_buffer"] = torch.zeros_like(p)
+    for _ in range(3):
+        step()
+        o2.zero_grad(set_to_none=True)
+        lf(m2(x), y).backward()
+        o2.step()
+    torch.cuda.synchronize()
+    for (k, a), (_, b) in zip(m2.named_parameters(), m1.named_parameters()):
+        assert torch.allclose(b, a, rtol=2e-4, atol=1e-6), k
