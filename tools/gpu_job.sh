@@ -31,6 +31,8 @@ for step in "$@"; do
     graphconv) python -m pytest tests/test_graphconv.py -m gpu -q -rf -x -p no:cacheprovider > gpurun_out/${tag}_graphconv.log 2>&1; tail -12 gpurun_out/${tag}_graphconv.log ;;
     probes)    # PROBE_CASES="case ..." PROBE_DBG="0 1 8 ..." : AGCN_CONV_DEBUG limiter probes on the -DAGCN_PROBES build (timing only)
                for d in $PROBE_DBG; do echo "== AGCN_CONV_DEBUG=$d"; AGCN_B200_LIB=$PWD/fusion_gcn_b200/libagcn_b200_probes.so AGCN_CONV_DEBUG=$d python tools/bench_stage.py $PROBE_CASES ${PROBE_FLAGS}; done > gpurun_out/${tag}_probes.log 2>&1; cat gpurun_out/${tag}_probes.log ;;
+    infer)     for n in 256 1024; do for pr in fp32 tf32; do python bench.py --mode infer --batch $n --precision $pr --steps 5 --warmup 3 > gpurun_out/${tag}_bench_infer_n${n}_${pr}.json 2> gpurun_out/${tag}_bench_infer.err; python -c "import json;d=json.load(open('gpurun_out/${tag}_bench_infer_n${n}_${pr}.json'));print('infer',$n,'$pr',d['value'],d['model_roofline']['achieved_frac_of_hbm_ceiling'])"; done; done ;;
+    workloads) for w in utd mmact_imu utd_rgb; do python bench.py --workload $w --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_bench_${w}.json 2> gpurun_out/${tag}_bench_${w}.err; python -c "import json;d=json.load(open('gpurun_out/${tag}_bench_${w}.json'));print('$w',d['value'],d['tf32_mode']['value'])"; done ;;
     *) echo "unknown step $step" ;;
   esac
 done
