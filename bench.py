@@ -333,11 +333,17 @@ def run_ours(args):
                        "tflops": round(fam_tf, 2), "gbs": round(fam_gbs, 1), "frac_tensor_bf16": round(fam_tf / tensor_peak, 4),
                        "frac_hbm": round(fam_gbs / pk["hbm_gbs"], 4)}
         if pk.get("tf32_tflops_sustained"):
-            # issued-FLOP view: fp32 mode = 3 TF32 products per algorithmic MAC, bf16x3 = 3 BF16 products, tf32 = 1 TF32 product
-            issue = {"fp32": (3.0, pk["tf32_tflops_sustained"], "3 x TF32"), "bf16x3": (3.0, tensor_peak, "3 x BF16"),
-                     "tf32": (1.0, pk["tf32_tflops_sustained"], "1 x TF32")}[args.precision]
-            family_roof["frac_tensor_mode"] = round(fam_tf * issue[0] / issue[1], 4)
-            family_roof["mode_peak"] = f"{issue[2]} products per MAC against the measured {'TF32' if 'TF32' in issue[2] else 'BF16'} sustained peak {issue[1]} TFLOP/s"
+            # issued-FLOP view: tensor-pipe time per algorithmic MAC = (TF32 products) / TF32 peak + (BF16 products) / BF16 peak.
+            # strict fp32: hi*hi on kind::tf32 + lo*hi + hi*lo on kind::f16 (weight gradients: 3 BF16 products); bf16x3: 3 BF16; tf32: 1 TF32
+            wgrad_family = fl.startswith("agcn_conv_wgrad")
+            n_tf32, n_bf16, what = {"fp32": (0, 3, "3 x BF16") if wgrad_family else (1, 2, "1 x TF32 + 2 x BF16"),
+                                    "bf16x3": (0, 3, "3 x BF16"), "tf32": (1, 0, "1 x TF32")}[args.precision]
+            if not fl.startswith("agcn_conv_"):
+                n_tf32, n_bf16, what = (1, 0, "1 x TF32") if args.precision == "tf32" else (3, 0, "3 x TF32")     # gram / mix stages
+            ceiling = 1.0 / (n_tf32 / pk["tf32_tflops_sustained"] + n_bf16 / tensor_peak)
+            family_roof["frac_tensor_mode"] = round(fam_tf / ceiling, 4)
+            family_roof["mode_peak"] = (f"{what} products per MAC: ceiling {ceiling:.1f} algorithmic TFLOP/s from the measured sustained peaks "
+                                        f"(TF32 {pk['tf32_tflops_sustained']}, BF16 {tensor_peak} TFLOP/s)")
         d = top[0]
         hbm_bound = d["frac_hbm"] >= d["frac_tensor"]
         roof = {"bound": "hbm" if hbm_bound else "tensor", "achieved": d["gbs"] if hbm_bound else d["tflops"],
@@ -350,8 +356,8 @@ def run_ours(args):
                 "peak_source": pk["source"] + (" copy bandwidth" if hbm_bound else " bf16 sustained (kernel timed inside a long step)"),
                 "top_family": family_roof,
                 "note": "achieved = algorithmic work of one launch (DESIGN.md section 4) / mean CUDA-event time of that launch signature inside the "
-                        "timed region; bound = the roof the kernel sits closer to. fp32 parity mode issues 3 TF32 MMAs per product (3xTF32), so its "
-                        "tensor ceiling for algorithmic FLOPs is a third of the TF32 rate (itself half of the bf16 peak used as denominator)."}
+                        "timed region; bound = the roof the kernel sits closer to. The strict fp32 mode issues one TF32 and two BF16 MMAs per product "
+                        "(weight gradients: three BF16), so its tensor ceiling for algorithmic FLOPs is top_family.mode_peak, not the bf16 peak used as denominator."}
     gflop, mbytes = WORK[args.workload]
     line = {
         "metric": "AGCN fwd+bwd sequences/sec", "value": round(value, 2), "unit": "sequences/s", "n_gpus": world, "steps": args.steps,
@@ -590,7 +596,7 @@ def main():
     ap.add_argument("--mode", default="train", choices=["train", "infer"], help="train: fwd+CE+bwd (the BASELINE metric); infer: forward only, eval mode")
     ap.add_argument("--micro-batch", type=int, default=512, help="--mode infer: sequences per forward call")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16x3", "tf32"],
-                    help="fp32 = 3xTF32 parity mode, bf16x3 = bf16 triple-product parity mode (both meet 1e-4), tf32 = single pass (own tolerance)")
+                    help="fp32 = strict parity mode (TF32 hi*hi + BF16 cross terms), bf16x3 = bf16 triple-product parity mode (both meet 1e-4), tf32 = single pass (own tolerance)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --batch sequences per GPU (default); strong: --batch sequences in total, sharded over the GPUs")

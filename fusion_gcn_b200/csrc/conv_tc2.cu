@@ -12,17 +12,18 @@
 // re-loading a shifted box per tap this divides the L2->SMEM activation traffic (and, in 3xTF32 mode, the hi/lo
 // operand-split work) of the 9x1 temporal conv by ~3.5.
 //
-// Warp roles (7 warps, +8 in 3xTF32 mode), persistent over tiles, 1 CTA / SM:
+// Warp roles (7 warps, +8 converter warps in the parity modes), persistent over tiles, 1 CTA / SM:
 //   warp 0      activation producer: TMA boxes of one K chunk -> A ring (NA stages of payload only)
-//   warp 1      MMA issuer: per (K chunk, tap): 4 x tcgen05.mma.kind::tf32 (M128, N=BN, K8); 3xTF32 mode: x3 (lo*hi, hi*lo, hi*hi),
-//               or x2 for tiles narrow enough to hold a [main | cross] accumulator pair: one 2*BN-wide MMA against [W_hi ; W_lo]
-//               and one against W_hi with the lo activations
+//   warp 1      MMA issuer: per (K chunk, tap): 4 x tcgen05.mma.kind::tf32 (M128, N=BN, K8); strict mode (MODE 1): these are the
+//               hi*hi products (the MMA truncates the raw fp32 rows to TF32 itself), followed by 2 x 2 kind::f16 MMAs (K16) for the
+//               cross terms lo*hi + hi*lo from bf16 [hi16 | lo16] rows, into their own TMEM columns where the tile is narrow enough
 //   warps 2..5  epilogue: tcgen05.ld -> (+bias) -> 1x1 convs: swizzled shared-memory chunk -> TMA bulk store / reduce-add;
 //               9-tap convs: per-warp staging -> full-line st.global (+old when accumulating); optional BatchNorm column sums;
 //               in 3xTF32 mode also the fp32 promotion of accumulator segments
 //   warp 6      weight producer: one (tap, K chunk) BN x 32 box -> B ring (NB stages); small 1x1 weights stay resident
-//   warps 7..14 (3xTF32) split the A stage once per K chunk: hi = rna_tf32(x) in place, lo = x - hi into a 2-deep lo ring
-//               (the weights' hi / lo tensors are precomputed into the caller's workspace and TMA-loaded)
+//   warps 7..14 (strict mode) build the [bf16(x) | bf16(x - trunc_tf32(x))] cross row of every activation row once per K chunk into a
+//               2-deep ring; the payload itself is left alone, so the hi*hi MMAs do not wait for them (the weights' rna_tf32 hi
+//               tensor and cross rows are precomputed into the caller's workspace and TMA-loaded)
 // Warps 0, 1 and 6 run their loops on all 32 lanes (warp-uniform control flow, mbarrier waits included) and let ONE elected lane
 // issue the TMA / MMA / commit instructions: ptxas then keeps the descriptors, coordinates and TMEM addresses in uniform
 // registers.  Under `if (lane == 0)` every UTCHMMA / UTMALDG is wrapped in an ELECT + R2UR.BROADCAST + branch waterfall that
@@ -237,7 +238,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 uint32_t first = 1;
                 for (int kc = 0; kc < a.kchunks; ++kc) {
                     mbar_wait(a_full(sa), pa);
-                    if (CONV && !(a.dbg & 8)) mbar_wait(a_lo(sa), pa);
+                    // BF16x3 converts in place: wait for the converter first.  The strict mode's converter leaves the fp32 row alone
+                    // (kind::tf32 truncates it itself), so its hi*hi MMAs are issued at once and only the cross terms wait.
+                    if (BF && !(a.dbg & 8)) mbar_wait(a_lo(sa), pa);
                     const int ksteps = BF ? ((a.cin - kc * 64 >= 64) ? 4 : (a.cin - kc * 64) / 16) : 4;      // BF16x3: UMMA K = 16 channels
                     const uint32_t abase = smem_base + (uint32_t)sa * a_slot;
                     const uint32_t lobase = lo_ring + (uint32_t)sl * a_slot;
@@ -276,6 +279,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                             for (int k = 0; k < kKChunk / 8; ++k) {
                                 if ((a.dbg & 2) && k) break;
                                 umma_tf32(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, ((k == 0) ? first : 0u) ^ 1u);
+                            }
+                            if (i == 0 && !(a.dbg & 8)) {                         // the [hi16 | lo16] rows of this K chunk
+                                mbar_wait(a_lo(sa), pa);
+                                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                             }
 #pragma unroll
                             for (int j = 0; j < 2; ++j) {
@@ -569,7 +576,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 mbar_wait(lo_empty(sl), pl ^ 1u);
                 const uint32_t src = smem_base + (uint32_t)sa * a_slot;
                 const uint32_t dst = lo_ring + (uint32_t)sl * a_slot;
-                // one thread per QUARTER row (8 channels): hi (TF32-rounded) in place, [hi16 | lo16] cross row into the lo ring slot
+                // one thread per QUARTER row (8 channels): [hi16 | lo16] cross row into the lo ring slot
                 const int rows = (int)(a.blk_rows_bytes >> 7);
                 for (int idx = tids; idx < ((a.dbg & 1) ? 0 : a.nblk * rows * 4); idx += kSplitWarps * 32) {
                     const int rr = idx >> 2;

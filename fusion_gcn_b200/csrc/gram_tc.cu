@@ -10,7 +10,8 @@
 //   swizzle); one UMMA M=128 x N=80 covers ALL (ga, g) pairs of the timestep at once -- D[(u,ga)][(v,g)] -- and the epilogue
 //   keeps the ga == g blocks.  Rows beyond V*groups of the M=128 / N=80 operand windows are whatever lies behind the box in
 //   shared memory; they only reach accumulator rows / columns that are never read.
-// 3xTF32 (fp32 parity mode): operand split by 8 warps into a two-slot lo ring, segment promotion into TMEM master sums.
+// Strict fp32 mode (SPLIT): 8 converter warps write bf16 [hi16 | lo16] rows of the operands into a two-slot ring (the fp32 payload
+// stays as it is); hi*hi runs on kind::tf32 and the cross terms lo*hi + hi*lo on kind::f16, as in conv_tc2.cu; segment promotion into TMEM master sums.
 // Warp roles: 0 TMA producer, 1 MMA issuer, 2..5 epilogue, 6..13 operand split (3xTF32 only).  Grid = (nb * nchunk) CTAs.
 #include "tc_common.cuh"
 #include <stdlib.h>
@@ -24,7 +25,7 @@ constexpr int kSplitWarps = 8;
 constexpr int kThreadsG = 6 * 32;
 constexpr int kThreadsGSplit = (6 + kSplitWarps) * 32;
 constexpr uint32_t kBarBytes = 512;
-constexpr int kSegStages = 4;            // 3xTF32: stages (timestep x K-chunk group) per accumulator segment (<= 96 chained MMAs)
+constexpr int kSegStages = 4;            // strict mode: stages (timestep x K-chunk group) per accumulator segment (<= 64 chained MMAs)
 
 struct GArgs {
     float* out;
@@ -112,6 +113,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const bool leader = elect_one_sync() != 0;
             const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(80 >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc_bf = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(80 >> 3) << 17) | ((128u >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             int sl = 0;
@@ -123,24 +125,38 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const int kg = s % p.nkg;
                 const int nk = (p.nkc - kg * p.kpg) < p.kpg ? (p.nkc - kg * p.kpg) : p.kpg;
                 mbar_wait(full_bar(stage), phase);
-                if (SPLIT) mbar_wait(lo_bar(stage), phase);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
                 const uint32_t slo = lo_ring + (uint32_t)sl * p.stage_bytes;
                 if (leader) {
+                    // hi*hi on kind::tf32 straight from the TMA payload (the MMA truncates the fp32 words itself) ...
                     for (int k = 0; k < nk; ++k) {
                         const uint32_t ao = (uint32_t)k * p.a_tile, bo = b_off + (uint32_t)k * (p.shared_tile ? p.a_tile : p.b_tile);
                         const uint64_t da = make_smem_desc(sa + ao), db = make_smem_desc(sa + bo);
-                        const uint64_t dalo = make_smem_desc(slo + ao), dblo = make_smem_desc(slo + bo);
                         for (int ks = 0; ks < ksteps; ++ks) {
-                            const uint64_t ko = (uint64_t)(ks * 2);
                             const uint32_t fresh = (k == 0 && ks == 0) ? first : 0u;
-                            if (SPLIT) {
-                                umma_tf32(d_tmem, dalo + ko, db + ko, idesc, fresh ^ 1u);
-                                umma_tf32(d_tmem, da + ko, dblo + ko, idesc, 1u);
-                                umma_tf32(d_tmem, da + ko, db + ko, idesc, 1u);
+                            umma_tf32(d_tmem, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc, fresh ^ 1u);
+                        }
+                    }
+                    if (SPLIT) {
+                        // ... then, once the converter warps have built the bf16 [hi16 | lo16] rows of this stage, the two cross terms
+                        // lo*hi + hi*lo on kind::f16 (K = 16 channels per MMA)
+                        mbar_wait(lo_bar(stage), phase);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        for (int k = 0; k < nk; ++k) {
+                            const uint32_t ao = (uint32_t)k * p.a_tile, bo = b_off + (uint32_t)k * (p.shared_tile ? p.a_tile : p.b_tile);
+                            const uint64_t dalo = make_smem_desc(slo + ao), dblo = make_smem_desc(slo + bo);
+                            if (p.shared_tile) {
+                                // one row = [theta hi16 | phi hi16 | theta lo16 | phi lo16], 32 bytes (2 descriptor units) each
+                                umma_bf16(d_tmem, dalo + 4u, dalo + 2u, idesc_bf, 1u);
+                                umma_bf16(d_tmem, dalo, dalo + 6u, idesc_bf, 1u);
                             } else {
-                                umma_tf32(d_tmem, da + ko, db + ko, idesc, fresh ^ 1u);
+#pragma unroll
+                                for (int j = 0; j < 2; ++j) {
+                                    const uint64_t ko = (uint64_t)(j * 2);
+                                    umma_bf16(d_tmem, dalo + 4u + ko, dblo + ko, idesc_bf, 1u);
+                                    umma_bf16(d_tmem, dalo + ko, dblo + 4u + ko, idesc_bf, 1u);
+                                }
                             }
                         }
                     }
@@ -212,12 +228,16 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             mbar_wait(lo_empty(sl), pl ^ 1u);
             const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
             const uint32_t slo = lo_ring + (uint32_t)sl * p.stage_bytes;
-            for (int k = 0; k < nk; ++k) {
-                transform_split4(sa + (uint32_t)k * p.a_tile, slo + (uint32_t)k * p.a_tile, p.a_rows_bytes, tidx, kSplitWarps * 32);
-                if (!p.shared_tile) {
-                    const uint32_t bo = (uint32_t)p.kpg * p.a_tile + (uint32_t)k * p.b_tile;
-                    transform_split4(sa + bo, slo + bo, p.b_rows_bytes, tidx, kSplitWarps * 32);
-                }
+            // one thread per QUARTER row (8 channels): [hi16 | lo16] cross row into the lo slot (tc_common.cuh)
+            const int rows_a = (int)(p.a_rows_bytes >> 7), rows_b = p.shared_tile ? 0 : (int)(p.b_rows_bytes >> 7);
+            const int per_k = (rows_a + rows_b) * 4;
+            for (int idx = tidx; idx < nk * per_k; idx += kSplitWarps * 32) {
+                const int k = idx / per_k, rem = idx - k * per_k;
+                int rr = rem >> 2;
+                uint32_t off = (uint32_t)k * p.a_tile;
+                if (rr >= rows_a) { rr -= rows_a; off = (uint32_t)p.kpg * p.a_tile + (uint32_t)k * p.b_tile; }
+                off += (uint32_t)rr * 128u;
+                tf32_cross_quarter(sa + off, slo + off, (uint32_t)(rr & 7), (uint32_t)(rem & 3));
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();

@@ -19,10 +19,12 @@
 //            B[N = 64][K = 32] = [dS_k^T | dS_k] (two 32-column atoms): every channel row gets both mixes, and the epilogue
 //            lane keeps the 32 columns that belong to it (a theta channel produces d phi and vice versa) and writes them
 //            to the partner channel (+-W).  The tensor core does twice the needed MACs, which is free here (HBM bound).
-// The K reduction is at most 96 long, so the 3xTF32 mode needs no accumulator promotion.
+// Strict fp32 mode (SPLIT): hi*hi on kind::tf32 straight from the fp32 payload (the MMA truncates it); the cross terms hi*lo + lo*hi on kind::f16 from bf16 blocks
+// the converter warps build next to the operands (tf32_cross_quarter_mn, tc_common.cuh).  The K reduction is at most 96 long, so
+// no accumulator promotion is needed.
 // The epilogue thread of TMEM lane (pair, c) owns one channel of one timestep: for every accumulator column (an output
 // joint) the 32 lanes of a warp write 32 consecutive channels, a full 128-byte line.
-// Warp roles: 0 activation producer (TMA), 1 MMA issuer, 2..5 epilogue, 6 matrix producer, 7..14 operand split (3xTF32).
+// Warp roles: 0 activation producer (TMA), 1 MMA issuer, 2..5 epilogue, 6 matrix producer, 7..14 operand converters (strict mode).
 // Persistent: CTA c walks a contiguous range of tiles (tiles of one sample are consecutive, so B changes at most a few times).
 #include "tc_common.cuh"
 #include <stdlib.h>
@@ -38,6 +40,7 @@ constexpr int kThreadsMSplit = (7 + kSplitWarps) * 32;
 constexpr uint32_t kBarBytes = 512;
 constexpr uint32_t kBoxBytes = 4096;      // 32 rows x 128 bytes
 constexpr uint32_t kMatBytes = 3u * kBoxBytes;     // AGG modes; SCORE_BWD holds 6 boxes per sample (MArgs::mat_bytes)
+constexpr uint32_t kCrossBlk = 8192;      // strict mode: one bf16 block = 64 K rows ([hi16 ; lo16] of 32 joints) x 64 channels
 
 struct MArgs {
     float* out;
@@ -54,6 +57,7 @@ struct MArgs {
     int score;               // SCORE_BWD
     int tgroups;             // SCORE_BWD: ceil(t / 4) timestep groups per channel block
     uint32_t mat_bytes;      // padded matrices of one sample: 3 boxes (AGG) or 6 boxes (SCORE_BWD)
+    uint32_t mat_cross;      // strict mode: bytes of their bf16 [lo ; hi] blocks (8 KB each: two boxes per block)
 };
 
 // which (timestep, 32-channel block) the j-th quarter of tile `ts` of a sample covers
@@ -93,7 +97,7 @@ mix_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     const uint32_t lo_ring = smem_base + (uint32_t)p.na * p.a_tile;                       // SPLIT: nlo slots of a_tile
     const uint32_t b_ring = lo_ring + (SPLIT ? (uint32_t)p.nlo * p.a_tile : 0u);          // 2 slots of mat_bytes (+ 2 lo slots when SPLIT)
     const uint32_t b_lo = b_ring + 2u * p.mat_bytes;
-    const uint32_t bar_base = b_lo + (SPLIT ? 2u * p.mat_bytes : 0u);
+    const uint32_t bar_base = b_lo + (SPLIT ? 2u * p.mat_cross : 0u);
     auto a_full = [&](int s) { return bar_base + 8u * s; };
     auto a_empty = [&](int s) { return bar_base + 8u * (kMaxA + s); };
     auto a_lo = [&](int s) { return bar_base + 8u * (2 * kMaxA + s); };
@@ -181,6 +185,8 @@ mix_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                                    ((uint32_t)(p.ncols >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc_bf = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                                      ((uint32_t)(p.ncols >> 3) << 17) | ((128u >> 4) << 24);
             int sa = 0; uint32_t pa = 0;
             int m = -1, sb = 0;                   // m: index of the current sample in this CTA's sequence; its matrix sits in slot m & 1
             int acc = 0; uint32_t acc_phase = 0;
@@ -199,38 +205,46 @@ mix_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 }
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
                 mbar_wait(a_full(sa), pa);
-                if (SPLIT) mbar_wait(a_lo(sa), pa);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_tmem = tmem_u + (uint32_t)(acc * 128);
                 const uint32_t abase = smem_base + (uint32_t)sa * p.a_tile;
                 const uint32_t alo = lo_ring + (uint32_t)sl * p.a_tile;
                 const uint32_t bbase = b_ring + (uint32_t)sb * p.mat_bytes;
-                const uint32_t blo = b_lo + (uint32_t)sb * p.mat_bytes;
-                uint32_t score_off = 0;           // SCORE_BWD: the [dS_k^T | dS_k] box pair of this tile's subset
+                const uint32_t blo = b_lo + (uint32_t)sb * p.mat_cross;
+                uint32_t score_off = 0, score_cross = 0;      // SCORE_BWD: the [dS_k^T | dS_k] box pair (and its cross block) of this tile's subset
                 if (kScore) {
                     const int ts = (int)(tile - (long long)n * p.tiles_per_sample);
                     const int cb = ts % p.ncb;
-                    score_off = (uint32_t)((cb * 32) / (2 * p.width)) * 2u * kBoxBytes;
+                    const uint32_t subset = (uint32_t)((cb * 32) / (2 * p.width));
+                    score_off = subset * 2u * kBoxBytes;
+                    score_cross = subset * kCrossBlk;
                 }
                 if (leader) {
+                    // hi*hi on kind::tf32 straight from the TMA payload (the MMA truncates the fp32 words itself) ...
                     for (int k = 0; k < p.kb; ++k) {
                         // fwd: B atoms = the three subsets (LBO = one box), K rows inside each box;  bwd: one atom, K block k = box k
                         const uint32_t bo = kScore ? score_off : (kBwd ? (uint32_t)k * kBoxBytes : 0u);
                         const uint64_t da = make_smem_desc_mn(abase + (uint32_t)k * 4u * kBoxBytes, kBoxBytes);
-                        const uint64_t dal = make_smem_desc_mn(alo + (uint32_t)k * 4u * kBoxBytes, kBoxBytes);
                         const uint64_t db = make_smem_desc_mn(bbase + bo, kBoxBytes);
-                        const uint64_t dbl = make_smem_desc_mn(blo + bo, kBoxBytes);
 #pragma unroll
                         for (int kg = 0; kg < 4; ++kg) {
                             const uint64_t ko = (uint64_t)(kg * 64);          // 8 rows = 1024 bytes, in 16-byte units
                             const uint32_t acc_flag = (k == 0 && kg == 0) ? 0u : 1u;
-                            if (SPLIT) {
-                                umma_tf32(d_tmem, dal + ko, db + ko, idesc, acc_flag);
-                                umma_tf32(d_tmem, da + ko, dbl + ko, idesc, 1u);
-                                umma_tf32(d_tmem, da + ko, db + ko, idesc, 1u);
-                            } else {
-                                umma_tf32(d_tmem, da + ko, db + ko, idesc, acc_flag);
-                            }
+                            umma_tf32(d_tmem, da + ko, db + ko, idesc, acc_flag);
+                        }
+                    }
+                    if (SPLIT) {
+                        // ... then hi*lo + lo*hi as ONE chain of four K = 16 bf16 MMAs per K block over the K-stacked blocks the converter
+                        // warps build: A' = [hi16 ; lo16] (two 64-channel blocks, 8 KB apart) and B' = [lo16 ; hi16]
+                        mbar_wait(a_lo(sa), pa);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        for (int k = 0; k < p.kb; ++k) {
+                            const uint64_t dac = make_smem_desc_mn16(alo + (uint32_t)k * 2u * kCrossBlk, kCrossBlk);
+                            // bwd: subset k = the 32-column half (k & 1) of block k >> 1 (start address + 64 bytes inside the swizzled rows)
+                            const uint64_t dbc = make_smem_desc_mn16(blo + (kScore ? score_cross : (kBwd ? (uint32_t)(k >> 1) * kCrossBlk + (uint32_t)(k & 1) * 64u : 0u)), kCrossBlk);
+#pragma unroll
+                            for (int kg = 0; kg < 4; ++kg)
+                                umma_bf16(d_tmem, dac + (uint64_t)(kg * 128), dbc + (uint64_t)(kg * 128), idesc_bf, 1u);     // 16 rows = 2048 bytes
                         }
                     }
                     umma_commit(a_empty(sa));
@@ -416,14 +430,27 @@ mix_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 mbar_wait(b_full(sb), (uint32_t)(m >> 1) & 1u);
                 // the lo slot of this matrix slot is free once the matrix slot itself was released (b_empty), which the matrix
                 // producer already waited for before refilling it
-                transform_split4(b_ring + (uint32_t)sb * p.mat_bytes, b_lo + (uint32_t)sb * p.mat_bytes, p.mat_bytes, tids, kSplitWarps * 32);
+                // matrices: two boxes side by side per 64-wide cross block, K-stacked [lo16 ; hi16]
+                const uint32_t msrc = b_ring + (uint32_t)sb * p.mat_bytes, mdst = b_lo + (uint32_t)sb * p.mat_cross;
+                const int nboxes = (int)(p.mat_bytes / kBoxBytes);
+                for (int idx = tids; idx < nboxes * 128; idx += kSplitWarps * 32) {
+                    const uint32_t bx = (uint32_t)idx >> 7, r = ((uint32_t)idx >> 2) & 31u, qd = (uint32_t)idx & 3u;
+                    tf32_cross_quarter_mn(msrc + bx * kBoxBytes, mdst + (bx >> 1) * kCrossBlk, r, qd, (bx & 1u) * 4u + qd, 32u + r, r);
+                }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(b_lo_bar(sb));
             }
             mbar_wait(a_full(sa), pa);
             mbar_wait(lo_empty(sl), pl ^ 1u);
-            transform_split4(smem_base + (uint32_t)sa * p.a_tile, lo_ring + (uint32_t)sl * p.a_tile, p.a_tile, tids, kSplitWarps * 32);
+            {
+                // activations: boxes (k, j) of the tile -> block (k, j >> 1), half j & 1, K-stacked [hi16 ; lo16]
+                const uint32_t asrc = smem_base + (uint32_t)sa * p.a_tile, adst = lo_ring + (uint32_t)sl * p.a_tile;
+                for (int idx = tids; idx < p.kb * 512; idx += kSplitWarps * 32) {
+                    const uint32_t bx = (uint32_t)idx >> 7, r = ((uint32_t)idx >> 2) & 31u, qd = (uint32_t)idx & 3u;
+                    tf32_cross_quarter_mn(asrc + bx * kBoxBytes, adst + (bx >> 1) * kCrossBlk, r, qd, (bx & 1u) * 4u + qd, r, 32u + r);
+                }
+            }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(a_lo(sa));
@@ -473,10 +500,11 @@ int agcn_joint_mix_tc(const float* in, const float* mats, float* out, float* gp,
     p.a_tile = (uint32_t)p.kb * 4u * kBoxBytes;
     p.ldout = ldout;
     p.mat_bytes = score ? 2u * kMatBytes : kMatBytes;
+    p.mat_cross = (score ? 3u : 2u) * kCrossBlk;
     static const bool no_tma_out = probe_env("AGCN_MIX_NO_TMA_STORE") != nullptr;
     p.tma_out = (!no_tma_out && ldout % 4 == 0 && (!score || width == 16 || width % 32 == 0)) ? 1 : 0;
     const uint32_t out_stage = p.tma_out ? 4u * ((score || p.bwd) ? 1u : 3u) * kBoxBytes : 0u;
-    const uint32_t fixed = 2u * p.mat_bytes * (split ? 2u : 1u) + kBarBytes + out_stage + 1024u;
+    const uint32_t fixed = 2u * p.mat_bytes + (split ? 2u * p.mat_cross : 0u) + kBarBytes + out_stage + 1024u;
     const uint32_t budget = 220u * 1024u - fixed;
     p.nlo = split ? 2 : 0;
     int na = (int)((budget - (uint32_t)p.nlo * p.a_tile) / p.a_tile);

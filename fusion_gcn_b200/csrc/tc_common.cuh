@@ -232,31 +232,47 @@ __device__ __forceinline__ void bf16_interleave_row(uint32_t p, uint32_t sw) {
         sts128u(p + (((uint32_t)(q + 4) ^ sw) << 4), mq[q]);
     }
 }
-// Strict fp32 mode ("TF32 + BF16 cross terms"): one 128-byte activation row (32 fp32 channels, 16-byte chunk j stored at j ^ sw) is
-// split as x = hi + lo with hi = rna_tf32(x) written back IN PLACE (the kind::tf32 hi*hi operand) and the row
-// [bf16(hi) of the 32 channels | bf16(lo) of the 32 channels] written to `pc` (same swizzle; chunk q of the hi16 half at q ^ sw, of the
-// lo16 half at (4 + q) ^ sw): the kind::f16 operand of the two cross products lo_a*hi_b + hi_a*lo_b.  |lo| <= 2^-11 |x| and bf16 keeps
-// 8 bits, so each cross term carries a relative error of 2^-20 -- the product is a*b to ~3 x 2^-20, at 2 instead of 3 TF32-equivalent
-// MMAs and 2/3 of the operand bytes of 3xTF32.
-// Work item = a QUARTER of a row (8 channels: fp32 chunks 2*qd, 2*qd + 1 -> hi in place, one 16-byte chunk of hi16 and one of lo16),
-// so a 125-row tile keeps all 256 converter threads busy and the rows of a quarter-warp hit eight different bank groups.
+// Strict fp32 mode ("TF32 + BF16 cross terms").  The kind::tf32 MMA truncates its fp32 operands to their upper 19 bits, so the raw
+// row x IS the hi*hi operand (hi = trunc_tf32(x), nothing is written back) and the converter only builds the kind::f16 operand of the
+// two cross products lo_a*hi_b + hi_a*lo_b: the row [bf16(x) of the 32 channels | bf16(lo) of the 32 channels] with lo = x - hi
+// (exact in fp32), same swizzle (chunk q of the hi16 half at q ^ sw, of the lo16 half at (4 + q) ^ sw).  |lo| < 2^-10 |x| and bf16
+// keeps 8 bits (round to nearest), so each cross term carries a relative error of 2^-19 at most; the dropped lo*lo term is 2^-20 at
+// most and has zero mean against the weights' round-to-nearest split.  2 instead of 3 TF32-equivalent MMAs, 2/3 of the operand
+// bytes of 3xTF32, and per 8 channels 2 loads + 2 stores + ~30 ALU instructions (the first version rounded hi to nearest and wrote
+// it back: 2 more stores and 2.5x the ALU work, which made the CONVERTER the limiter of the 1x1 convolutions, grams and mixes).
+// Work item = a QUARTER of a row (8 channels: fp32 chunks 2*qd, 2*qd + 1 -> one 16-byte chunk of hi16 and one of lo16).
+__device__ __forceinline__ uint32_t bf16x2_rn(float upper, float lower) {
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(upper), "f"(lower));
+    return d;
+}
+__device__ __forceinline__ void cross_pack8(const float4& f0, const float4& f1, uint4& h, uint4& l) {
+    const float x[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+    float lo[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) lo[i] = x[i] - __uint_as_float(__float_as_uint(x[i]) & 0xffffe000u);
+    h = make_uint4(bf16x2_rn(x[1], x[0]), bf16x2_rn(x[3], x[2]), bf16x2_rn(x[5], x[4]), bf16x2_rn(x[7], x[6]));
+    l = make_uint4(bf16x2_rn(lo[1], lo[0]), bf16x2_rn(lo[3], lo[2]), bf16x2_rn(lo[5], lo[4]), bf16x2_rn(lo[7], lo[6]));
+}
 __device__ __forceinline__ void tf32_cross_quarter(uint32_t p, uint32_t pc, uint32_t sw, uint32_t qd) {
     const float4 f0 = lds128(p + (((2u * qd) ^ sw) << 4)), f1 = lds128(p + (((2u * qd + 1u) ^ sw) << 4));
-    const float x[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
-    float hi[8];
-    uint32_t hb[8], lb[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        hi[i] = tf32_rna(x[i]);
-        hb[i] = __float_as_uint(hi[i]) + 0x8000u;                 // bf16(hi), upper half kept by the byte permute
-        lb[i] = __float_as_uint(x[i] - hi[i]) + 0x8000u;          // bf16(lo), lo = x - hi exact
-    }
-    sts128(p + (((2u * qd) ^ sw) << 4), make_float4(hi[0], hi[1], hi[2], hi[3]));
-    sts128(p + (((2u * qd + 1u) ^ sw) << 4), make_float4(hi[4], hi[5], hi[6], hi[7]));
-    sts128u(pc + ((qd ^ sw) << 4), make_uint4(__byte_perm(hb[0], hb[1], 0x7632), __byte_perm(hb[2], hb[3], 0x7632),
-                                              __byte_perm(hb[4], hb[5], 0x7632), __byte_perm(hb[6], hb[7], 0x7632)));
-    sts128u(pc + (((qd + 4u) ^ sw) << 4), make_uint4(__byte_perm(lb[0], lb[1], 0x7632), __byte_perm(lb[2], lb[3], 0x7632),
-                                                     __byte_perm(lb[4], lb[5], 0x7632), __byte_perm(lb[6], lb[7], 0x7632)));
+    uint4 h, l;
+    cross_pack8(f0, f1, h, l);
+    sts128u(pc + ((qd ^ sw) << 4), h);
+    sts128u(pc + (((qd + 4u) ^ sw) << 4), l);
+}
+// The same split for MN-major operands (channels contiguous, the joint / row index is K).  Source: quarter `qd` (8 channels) of row
+// `r` of a 32-channel fp32 box that TMA landed in the 32-byte-atom swizzle (Swizzle<2,5,2>: 32-byte chunk index ^= row & 3).
+// Destination: a plain-128B-swizzled bf16 block of 64 channels per 128-byte row (8-row swizzle groups): bf16(x) goes to the
+// logical 16-byte chunk `c` of row `row_hi`, bf16(lo) to the same chunk of row `row_lo` (the two pieces are stacked along K, so that
+// ONE chain of K = 16 MMAs against the other operand's [lo ; hi] block yields hi*lo + lo*hi).
+__device__ __forceinline__ void tf32_cross_quarter_mn(uint32_t box, uint32_t blk, uint32_t r, uint32_t qd, uint32_t c, uint32_t row_hi, uint32_t row_lo) {
+    const uint32_t p = box + r * 128u + ((qd ^ (r & 3u)) << 5);
+    const float4 f0 = lds128(p), f1 = lds128(p + 16u);
+    uint4 h, l;
+    cross_pack8(f0, f1, h, l);
+    sts128u(blk + row_hi * 128u + ((c ^ (row_hi & 7u)) << 4), h);
+    sts128u(blk + row_lo * 128u + ((c ^ (row_lo & 7u)) << 4), l);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
