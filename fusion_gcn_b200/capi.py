@@ -46,8 +46,8 @@ SIGNATURES = {
     "agcn_bn_apply": (_c_int, [_c_void_p] * 3 + [_c_int] + [_c_void_p] * 3 + [_c_int, _c_void_p, _c_int, _c_int, _c_ll, _c_int, _c_void_p]),
     "agcn_bn_mask_words": (_c_size_t, [_c_int] * 3),
     "agcn_bn_apply_mask": (_c_int, [_c_void_p] * 3 + [_c_int] + [_c_void_p] * 3 + [_c_int, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p]),
-    "agcn_bn_bwd_bits": (_c_int, [_c_void_p] * 10 + [_c_int, _c_int, _c_int, _c_void_p, _c_size_t, _c_void_p]),
-    "agcn_bn_bwd": (_c_int, [_c_void_p] * 10 + [_c_int, _c_int, _c_int, _c_ll, _c_int, _c_void_p, _c_size_t, _c_void_p]),
+    "agcn_bn_bwd_bits": (_c_int, [_c_void_p] * 10 + [_c_int, _c_int, _c_int, _c_int, _c_void_p, _c_size_t, _c_void_p]),
+    "agcn_bn_bwd": (_c_int, [_c_void_p] * 10 + [_c_int, _c_int, _c_int, _c_int, _c_ll, _c_int, _c_void_p, _c_size_t, _c_void_p]),
     "agcn_pool_fwd": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
     "agcn_pool_bwd": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
     "agcn_bn_apply_pool_workspace_bytes": (_c_size_t, [_c_int, _c_int]),

@@ -25,7 +25,8 @@ static int num_partials(long long rows) {
     return (int)p;
 }
 
-// NS sums per channel.  MODE 0: (x, x^2).  MODE 1: (g, g*xhat) with g = dout * [mask > 0].
+// NS sums per channel.  MODE 0: (x - pivot, (x - pivot)^2) with the per-channel pivot passed in `mean` (NULL: 0) -- shifted sums, so
+// that var = E[(x-p)^2] - E[x-p]^2 does not cancel for channels with |mean| >> sigma.  MODE 1: (g, g*xhat) with g = dout * [mask > 0].
 // grid = (P, column strips of 32); block = 32 columns x 8 row lanes.
 template <int MODE>
 __global__ void __launch_bounds__(256) colsum_strip_kernel(const float* x, const float* dout, const float* mask,
@@ -42,10 +43,11 @@ __global__ void __launch_bounds__(256) colsum_strip_kernel(const float* x, const
     if (c < m.channels) {
         float mu = 0.f, is = 0.f;
         if (MODE == 1) { mu = mean[c]; is = invstd[c]; }
+        else if (mean != nullptr) mu = mean[c];
         for (long long r = r0 + ty; r < r1; r += 8) {
             const long long off = m.row_offset(r) + c;
             if (MODE == 0) {
-                float v = __ldg(x + off);
+                float v = __ldg(x + off) - mu;
                 s0 += v; s1 = fmaf(v, v, s1);
             } else {
                 float g = __ldg(dout + off);
@@ -92,11 +94,14 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const float* x, const f
     if (MODE == 1) {
         mu = *reinterpret_cast<const float4*>(mean + q * 4);
         is = *reinterpret_cast<const float4*>(invstd + q * 4);
+    } else if (mean != nullptr) {
+        mu = *reinterpret_cast<const float4*>(mean + q * 4);       // MODE 0: the pivot of the shifted sums
     }
     for (long long r = r0 + rl; r < r1; r += lanes_r) {
         const long long off = m.row_offset(r) + q * 4;
         if (MODE == 0) {
             float4 v = __ldg(reinterpret_cast<const float4*>(x + off));
+            v.x -= mu.x; v.y -= mu.y; v.z -= mu.z; v.w -= mu.w;
             s0.x += v.x; s0.y += v.y; s0.z += v.z; s0.w += v.w;
             s1.x = fmaf(v.x, v.x, s1.x); s1.y = fmaf(v.y, v.y, s1.y); s1.z = fmaf(v.z, v.z, s1.z); s1.w = fmaf(v.w, v.w, s1.w);
         } else {
@@ -139,14 +144,17 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const float* x, const f
     }
 }
 
-// Sum of the P per-CTA partials of channel c (fp64, fixed order): 8 lanes per channel stride over the partials, then a
-// fixed-order shared-memory combine.  block = 32 channels x 8 lanes.
+// Sum of the P per-CTA partials of channel c (fp64, fixed order): kFinLanes lanes per channel stride over the partials, then a
+// fixed-order shared-memory combine.  block = kFinCh channels x kFinLanes lanes: the finalize kernels are pure latency (a few
+// hundred partials per channel, ~25 launches per step), so the partials are spread over many lanes and blocks.
+constexpr int kFinCh = 8, kFinLanes = 32;
 __device__ __forceinline__ void reduce_partials(const float* part, int P, int C, int c, double& s_out, double& q_out) {
-    __shared__ double red[2][8][33];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    __shared__ double red[2][kFinLanes][kFinCh + 1];
+    const int tx = threadIdx.x % kFinCh, ty = threadIdx.x / kFinCh;
     double s = 0.0, q = 0.0;
     if (c < C)
-        for (int b = ty; b < P; b += 8) {
+#pragma unroll 4
+        for (int b = ty; b < P; b += kFinLanes) {
             s += (double)part[((long long)b * 2 + 0) * C + c];
             q += (double)part[((long long)b * 2 + 1) * C + c];
         }
@@ -154,23 +162,60 @@ __device__ __forceinline__ void reduce_partials(const float* part, int P, int C,
     __syncthreads();
     s = 0.0; q = 0.0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { s += red[0][i][tx]; q += red[1][i][tx]; }
+    for (int i = 0; i < kFinLanes; ++i) { s += red[0][i][tx]; q += red[1][i][tx]; }
     s_out = s; q_out = q;
+}
+
+// The same for the partials of the convolution epilogue (agcn_conv_fwd_stats): part[P][4][C] = shifted sum | shifted sum of squares |
+// pivot | row count per partial.  In fp64:  a = sum_p (n_p piv_p + s1_p) = sum x,   b = sum_p (s2_p + piv_p (2 s1_p + n_p piv_p)) = sum x^2
+// (the same numbers as the pairwise-variance merge -- its s1^2 / n terms cancel -- without a division per partial); the caller forms
+// var = b / N - (a / N)^2, whose cancellation costs (mean / sigma)^2 x 1e-16 in fp64, while the rounding of the fp32 partials enters
+// through (piv_p - mean) ~ sigma, not through mean.
+__device__ __forceinline__ void reduce_partials4(const float* part, int P, int C, int c, double& a_out, double& b_out) {
+    __shared__ double red4[2][kFinLanes][kFinCh + 1];
+    const int tx = threadIdx.x % kFinCh, ty = threadIdx.x / kFinCh;
+    double a = 0.0, b = 0.0;
+    if (c < C)
+#pragma unroll 4
+        for (int p = ty; p < P; p += kFinLanes) {
+            const float* q = part + (long long)p * 4 * C + c;
+            // all four loads first (one round trip per partial); a warp that never saw this column left n = 0 and its pivot unwritten
+            const float f0 = q[0], f1 = q[C], f2 = q[2 * C], nf = q[3 * C];
+            const double n = (double)nf, s1 = (double)f0, s2 = (double)f1, pv = nf > 0.f ? (double)f2 : 0.0;
+            a += n * pv + s1;
+            b += s2 + pv * (2.0 * s1 + n * pv);
+        }
+    red4[0][ty][tx] = a; red4[1][ty][tx] = b;
+    __syncthreads();
+    a = 0.0; b = 0.0;
+#pragma unroll
+    for (int i = 0; i < kFinLanes; ++i) { a += red4[0][i][tx]; b += red4[1][i][tx]; }
+    a_out = a; b_out = b;
 }
 
 __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* part, int P, int C, double count,
                                    const float* gamma, const float* beta, float* running_mean, float* running_var,
                                    long long* nbt, float momentum, float eps, int training,
-                                   float* scale, float* shift, float* save_mean, float* save_invstd) {
-    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+                                   float* scale, float* shift, float* save_mean, float* save_invstd, const float* pivot, int layout4) {
+    const int c = blockIdx.x * kFinCh + threadIdx.x % kFinCh;
     if (blockIdx.x == 0 && threadIdx.x == 0 && training && nbt != nullptr) *nbt += 1;
     double s = 0.0, q = 0.0;
-    if (training) reduce_partials(part, P, C, c, s, q);
-    if (c >= C || (threadIdx.x >> 5) != 0) return;
+    if (training) {
+        if (layout4) reduce_partials4(part, P, C, c, s, q);
+        else reduce_partials(part, P, C, c, s, q);
+    }
+    if (c >= C || threadIdx.x >= kFinCh) return;
     double mean, var;
     if (training) {
-        mean = s / count;
-        var = q / count - mean * mean;
+        if (layout4) {
+            mean = s / count;
+            var = q / count - mean * mean;
+        } else {
+            // the partials are sums of (x - pivot) and (x - pivot)^2 with one pivot for the whole tensor
+            const double d = s / count;
+            mean = (pivot != nullptr ? (double)pivot[c] : 0.0) + d;
+            var = q / count - d * d;
+        }
         if (var < 0.0) var = 0.0;
         if (running_mean != nullptr) {
             const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
@@ -307,19 +352,20 @@ __global__ void pool_finalize_kernel(const float* part, float* pooled, int P, in
     pooled[idx] = s * inv_rows;
 }
 
-// coef[0][c] = gamma*invstd, coef[1][c] = s1/m, coef[2][c] = s2/m * invstd, coef[3][c] = mean;  dgamma = s2, dbeta = s1
+// coef[0][c] = gamma*invstd, coef[1][c] = s1/m, coef[2][c] = s2/m * invstd, coef[3][c] = mean;  dgamma = s2, dbeta = s1.
+// frozen: mean / invstd are constants (eval-mode BatchNorm on its running statistics), so dy = gamma*invstd*g: coef[1] = coef[2] = 0.
 __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* part, int P, int C, double count, const float* gamma,
-                                       const float* mean, const float* invstd, float* dgamma, float* dbeta, float* coef) {
-    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+                                       const float* mean, const float* invstd, float* dgamma, float* dbeta, float* coef, int frozen) {
+    const int c = blockIdx.x * kFinCh + threadIdx.x % kFinCh;
     double s1, s2;
     reduce_partials(part, P, C, c, s1, s2);
-    if (c >= C || (threadIdx.x >> 5) != 0) return;
+    if (c >= C || threadIdx.x >= kFinCh) return;
     if (dbeta) dbeta[c] = (float)s1;
     if (dgamma) dgamma[c] = (float)s2;
     const float is = invstd[c];
     coef[0 * C + c] = (gamma ? gamma[c] : 1.f) * is;
-    coef[1 * C + c] = (float)(s1 / count);
-    coef[2 * C + c] = (float)(s2 / count) * is;
+    coef[1 * C + c] = frozen ? 0.f : (float)(s1 / count);
+    coef[2 * C + c] = frozen ? 0.f : (float)(s2 / count) * is;
     coef[3 * C + c] = mean[c];
 }
 
@@ -479,11 +525,13 @@ extern "C" AGCN_API int agcn_bn_stats(const float* x, int outer, int inner, long
         AGCN_REQUIRE(x && workspace, AGCN_ERR_NULL, "agcn_bn_stats: null pointer");
         AGCN_REQUIRE(workspace_bytes >= agcn_bn_workspace_bytes(channels), AGCN_ERR_WORKSPACE, "agcn_bn_stats: workspace too small");
         P = num_partials(rows);
-        rc = launch_colsum<0>(x, nullptr, nullptr, nullptr, nullptr, m, rows, part, P, s);
+        // pivot of the shifted sums: the first row of x (any value near the channel's mean removes the cancellation)
+        rc = launch_colsum<0>(x, nullptr, nullptr, x, nullptr, m, rows, part, P, s);
         if (rc) return rc;
     }
-    bn_finalize_kernel<<<ceil_div(channels, 32), 256, 0, s>>>(part, P, channels, (double)rows, gamma, beta, running_mean, running_var,
-                                                              num_batches_tracked, momentum, eps, training, scale, shift, save_mean, save_invstd);
+    bn_finalize_kernel<<<ceil_div(channels, kFinCh), kFinCh * kFinLanes, 0, s>>>(part, P, channels, (double)rows, gamma, beta, running_mean, running_var,
+                                                              num_batches_tracked, momentum, eps, training, scale, shift, save_mean, save_invstd,
+                                                              training ? x : nullptr, 0);
     return check_launch("agcn_bn_stats(finalize)");
 }
 
@@ -494,9 +542,9 @@ extern "C" AGCN_API int agcn_bn_finalize(const float* part, int nparts, long lon
     AGCN_REQUIRE(part && scale && shift, AGCN_ERR_NULL, "agcn_bn_finalize: null pointer");
     AGCN_REQUIRE(nparts > 0 && rows > 0 && channels > 0, AGCN_ERR_BAD_SHAPE, "agcn_bn_finalize: bad shape nparts=%d rows=%lld channels=%d",
                  nparts, rows, channels);
-    bn_finalize_kernel<<<ceil_div(channels, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    bn_finalize_kernel<<<ceil_div(channels, kFinCh), kFinCh * kFinLanes, 0, static_cast<cudaStream_t>(stream)>>>(
         part, nparts, channels, (double)rows, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, 1,
-        scale, shift, save_mean, save_invstd);
+        scale, shift, save_mean, save_invstd, nullptr, 1);
     return check_launch("agcn_bn_finalize");
 }
 
@@ -549,7 +597,7 @@ static int bn_bwd_impl(const float* dout, const float* mask_out, const unsigned*
                        const float* save_mean, const float* save_invstd, const float* gamma,
                        float* dy, float* dgamma, float* dbeta, float* dres, int dres_accumulate,
                        int outer, int inner, long long outer_stride, int channels,
-                       void* workspace, size_t workspace_bytes, void* stream, int bcast_rows = 0) {
+                       void* workspace, size_t workspace_bytes, void* stream, int bcast_rows = 0, int frozen = 0) {
     int rc = check_map("agcn_bn_bwd", outer, inner, outer_stride, channels);
     if (rc) return rc;
     AGCN_REQUIRE(dout && y && save_mean && save_invstd && workspace, AGCN_ERR_NULL, "agcn_bn_bwd: null pointer");
@@ -566,7 +614,7 @@ static int bn_bwd_impl(const float* dout, const float* mask_out, const unsigned*
     const float bcast_scale = bcast_rows > 0 ? 1.f / (float)bcast_rows : 1.f;
     rc = launch_colsum<1>(y, dout, mask_out, save_mean, save_invstd, m, rows, part, P, s, mask_bits, bcast_rows, bcast_scale);
     if (rc) return rc;
-    bn_bwd_finalize_kernel<<<ceil_div(channels, 32), 256, 0, s>>>(part, P, channels, (double)rows, gamma, save_mean, save_invstd, dgamma, dbeta, coef);
+    bn_bwd_finalize_kernel<<<ceil_div(channels, kFinCh), kFinCh * kFinLanes, 0, s>>>(part, P, channels, (double)rows, gamma, save_mean, save_invstd, dgamma, dbeta, coef, frozen);
     rc = check_launch("agcn_bn_bwd(finalize)");
     if (rc) return rc;
     if (dy == nullptr && dres == nullptr) return AGCN_OK;
@@ -580,20 +628,20 @@ static int bn_bwd_impl(const float* dout, const float* mask_out, const unsigned*
 
 extern "C" AGCN_API int agcn_bn_bwd(const float* dout, const float* mask_out, const float* y,
                            const float* save_mean, const float* save_invstd, const float* gamma,
-                           float* dy, float* dgamma, float* dbeta, float* dres, int dres_accumulate,
+                           float* dy, float* dgamma, float* dbeta, float* dres, int dres_accumulate, int frozen_stats,
                            int outer, int inner, long long outer_stride, int channels,
                            void* workspace, size_t workspace_bytes, void* stream) {
     return bn_bwd_impl(dout, mask_out, nullptr, y, save_mean, save_invstd, gamma, dy, dgamma, dbeta, dres, dres_accumulate,
-                       outer, inner, outer_stride, channels, workspace, workspace_bytes, stream);
+                       outer, inner, outer_stride, channels, workspace, workspace_bytes, stream, 0, frozen_stats);
 }
 
 extern "C" AGCN_API int agcn_bn_bwd_bits(const float* dout, const unsigned* mask_bits, const float* y,
                                 const float* save_mean, const float* save_invstd, const float* gamma,
-                                float* dy, float* dgamma, float* dbeta, float* dres, int dres_accumulate,
+                                float* dy, float* dgamma, float* dbeta, float* dres, int dres_accumulate, int frozen_stats,
                                 int inner, int channels, void* workspace, size_t workspace_bytes, void* stream) {
     AGCN_REQUIRE(mask_bits, AGCN_ERR_NULL, "agcn_bn_bwd_bits: null mask pointer");
     return bn_bwd_impl(dout, nullptr, mask_bits, y, save_mean, save_invstd, gamma, dy, dgamma, dbeta, dres, dres_accumulate,
-                       1, inner, 0, channels, workspace, workspace_bytes, stream);
+                       1, inner, 0, channels, workspace, workspace_bytes, stream, 0, frozen_stats);
 }
 
 constexpr int kPoolParts = 8;

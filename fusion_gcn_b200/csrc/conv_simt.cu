@@ -644,7 +644,7 @@ extern "C" AGCN_API int agcn_conv_fwd_post(const float* x, const float* w, const
 }
 
 extern "C" AGCN_API size_t agcn_conv_fwd_stats_bytes(int cout) {
-    return cout > 0 ? (size_t)4 * kNumSMs * 2 * cout * sizeof(float) : 0;
+    return cout > 0 ? (size_t)4 * kNumSMs * 4 * cout * sizeof(float) : 0;       // [4 warps x SMs][shifted sum | sum of squares | pivot | rows][cout]
 }
 
 extern "C" AGCN_API int agcn_conv_fwd_stats(const float* x, const float* w, const float* bias, float* y,

@@ -58,12 +58,14 @@ constexpr uint32_t kStageBytes = 4u * 32u * kStagePitch;     // four epilogue wa
 constexpr uint32_t kSmemBudget = 222u * 1024u;
 constexpr uint32_t kTmaStageBytes = 2u * 128u * 128u;         // TMA-store epilogue: two chunk buffers of 128 rows x 32 floats
 constexpr int kStatCols = 256;                               // fused BatchNorm statistics: widest output the per-warp column sums cover
-constexpr uint32_t kStatBytes = 4u * 2u * kStatCols * 4u;    // four epilogue warps x (sum | sum of squares) x kStatCols floats
+constexpr uint32_t kStatWarpFloats = 2u * kStatCols + kStatCols / 2u;      // per epilogue warp: shifted sum | shifted sum of squares (fp32) | pivots (bf16)
+constexpr uint32_t kStatBytes = 4u * kStatWarpFloats * 4u;
 
 struct Tc2Args {
     float* y; const float* bias;
     PostOp post;                  // eval-mode fused tail: y = act(scale * (acc + bias) + shift + res)
-    float* stat_part;             // != NULL: per-warp column sums of the written output, [gridDim.x * 4][2][cout] (BatchNorm statistics)
+    float* stat_part;             // != NULL: per-warp statistics of the written output, [gridDim.x * 4][4][cout]: sum(o - p) | sum((o - p)^2) |
+                                  // p | rows, p = the first value of the column this warp saw (BatchNorm statistics, agcn_bn_finalize)
     int nb, t_out, v, cin, cout, stride, transposed, accumulate;
     int tt, bn, n_tiles_n, kchunks, tiles_t, nparity;
     long long total_tiles;
@@ -88,14 +90,17 @@ struct Tc2Args {
 };
 
 // MODE: 0 single-pass TF32, 1 3xTF32 (fp32 parity), 2 BF16x3 (fp32 parity, bf16 triple products)
-// POST: the eval-mode fused tail (PostOp) is compiled in -- a template parameter so that the training kernels, whose 480-thread
-// variants sit at the 128-register cap, do not carry its registers (with it folded in at run time the epilogue spilled and the
-// output-heavy 1x1 convolutions lost 25 %, profiles/r3q).
-template <int MODE, bool POST>
+// EPI: 0 plain epilogue, 1 the eval-mode fused tail (PostOp), 2 fused BatchNorm statistics -- a template parameter so that every
+// variant carries only its own epilogue registers: the 480-thread parity-mode kernels sit at the 128-register cap (with the eval
+// tail folded in at run time the epilogue spilled and the output-heavy 1x1 convolutions lost 25 %, profiles/r3q; with the
+// statistics code shared, the input-gradient kernels lost 10-15 %, profiles/r4g).
+template <int MODE, int EPI>
 __global__ void __launch_bounds__(MODE != 0 ? kThreads2Split : kThreads2, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_y0,
                 const __grid_constant__ CUtensorMap map_y1, Tc2Args a) {
+    constexpr bool POST = EPI == 1;        // eval-mode fused tail
+    constexpr bool STATS = EPI == 2;       // fused BatchNorm statistics (a.stat_part != NULL)
     constexpr bool SPLIT = MODE == 1;      // 3xTF32: hi in place, lo into its own ring
     constexpr bool BF = MODE == 2;         // BF16x3: h | m in place over the two fp32 boxes of a 64-channel chunk
     constexpr bool CONV = MODE != 0;       // converter warps, [hi ; lo] weight slots, segment promotion
@@ -140,10 +145,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-    // fused BatchNorm statistics: per epilogue warp, sum and sum of squares of every output column it has written
+    // fused BatchNorm statistics: per epilogue warp, the sum and the sum of squares of (o - pivot) for every output column it has written.
+    // pivot = the first value of the column the warp saw (row 0 of its slice in its first tile of that column block) rounded to bf16:
+    // any value within a fraction of a percent of the channel mean removes the cancellation of E[o^2] - mean^2, and two bytes per
+    // column keep the shared-memory cost of the shifted sums at 2 KB (the operand rings of the 9-tap kernels have none to spare).
+    // The row counts of the partials are recomputed from the tile sequence at the end.
     const uint32_t tbuf_base = bar_base + 1024u;                   // TMA-store epilogue: two 128-row x 128-byte chunk buffers (1024-aligned)
     const uint32_t epi_end = a.tma_store ? tbuf_base + kTmaStageBytes : bar_base + kBarBytes + kStageBytes;
-    float* stat_sm = reinterpret_cast<float*>(smem_raw + (epi_end - smem_u32(smem_raw))) + ((threadIdx.x >> 5) & 3) * (2 * kStatCols);
+    float* stat_sm = reinterpret_cast<float*>(smem_raw + (epi_end - smem_u32(smem_raw))) + ((threadIdx.x >> 5) & 3) * kStatWarpFloats;
 
     const uint32_t a_tx = (uint32_t)a.nblk * a.blk_rows_bytes;
     const uint32_t b_tx = (uint32_t)a.bn * 128u * (CONV ? 2u : 1u);
@@ -330,10 +339,27 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const int q = warp & 3;
         const int row_local = q * 32 + lane;
         int acc = 0; uint32_t acc_phase = 0;
-        if (a.stat_part != nullptr) {
-            for (int i = lane; i < 2 * kStatCols; i += 32) stat_sm[i] = 0.f;
+        if constexpr (STATS) {
+            for (int i = lane; i < (int)kStatWarpFloats; i += 32) stat_sm[i] = 0.f;
             __syncwarp();
         }
+        uint32_t stat_seen = 0;                            // bit nt: this warp has already fixed its pivots of column block nt
+        // (valid rows of a tile in this warp's slice: recomputed where used -- the epilogue has no registers to spare, see the POST
+        // template parameter)
+        uint16_t* stat_piv = reinterpret_cast<uint16_t*>(stat_sm + 2 * kStatCols);
+        auto piv_load = [&](int col) {                       // four bf16 pivots -> fp32
+            const uint2 u = *reinterpret_cast<const uint2*>(stat_piv + col);
+            return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+        };
+        auto piv_fix = [&](float4 v, int col, bool writer) { // round four first values to bf16, keep them (lanes < 8 write), return them as fp32
+            const uint32_t p0 = bf16x2_rn(v.y, v.x), p1 = bf16x2_rn(v.w, v.z);
+            if (writer) *reinterpret_cast<uint2*>(stat_piv + col) = make_uint2(p0, p1);
+            return make_float4(__uint_as_float(p0 << 16), __uint_as_float(p0 & 0xffff0000u), __uint_as_float(p1 << 16), __uint_as_float(p1 & 0xffff0000u));
+        };
+        auto stat_rvalid = [&](int jt) {
+            int rv = (a.tt < a.t_out - jt * a.tt ? a.tt : a.t_out - jt * a.tt) * a.v - q * 32;      // valid rows are a prefix (forward gather)
+            return rv < 0 ? 0 : (rv > 32 ? 32 : rv);
+        };
         uint32_t ck = 0;                                   // chunks stored so far by this CTA (TMA-store epilogue: buffer = ck & 1)
         const bool issuer = (warp == 2 && lane == 0);      // the thread that issues and tracks the bulk stores
         for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
@@ -426,34 +452,46 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                             }
                             ++ck;
-                            if (a.stat_part != nullptr) {
-                                // column sums from the staged tile: lane -> 16-byte column piece (lane & 7), rows (lane >> 3) + 4 i of this warp
+                            if constexpr (STATS) {
+                                // column sums from the staged tile: lane -> 16-byte column piece (lane & 7), rows (lane >> 3) + 4 i of this warp,
+                                // shifted by the warp's pivot of the column
                                 const int cq = lane & 7;
-                                float4 ssum = make_float4(0.f, 0.f, 0.f, 0.f), ssq = ssum;
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const int r = q * 32 + i * 4 + (lane >> 3);
-                                    const int rtl = r / a.v;
-                                    if (rtl < a.tt && jt * a.tt + rtl < a.t_out) {
-                                        const float4 o = lds128(buf + (uint32_t)r * 128u + (((uint32_t)cq ^ (uint32_t)(r & 7)) << 4));
-                                        ssum.x += o.x; ssum.y += o.y; ssum.z += o.z; ssum.w += o.w;
-                                        ssq.x = fmaf(o.x, o.x, ssq.x); ssq.y = fmaf(o.y, o.y, ssq.y); ssq.z = fmaf(o.z, o.z, ssq.z); ssq.w = fmaf(o.w, o.w, ssq.w);
+                                const int col = nt * a.bn + c0 + cq * 4;
+                                const int rvalid = stat_rvalid(jt);
+                                if (rvalid > 0) {
+                                    float4 pv;
+                                    if (!((stat_seen >> nt) & 1u)) {
+                                        const int r = q * 32;
+                                        pv = piv_fix(lds128(buf + (uint32_t)r * 128u + (((uint32_t)cq ^ (uint32_t)(r & 7)) << 4)), col, lane < 8);
+                                    } else {
+                                        pv = piv_load(col);
                                     }
-                                }
+                                    float4 ssum = make_float4(0.f, 0.f, 0.f, 0.f), ssq = ssum;
 #pragma unroll
-                                for (int d = 8; d <= 16; d <<= 1) {
-                                    ssum.x += __shfl_xor_sync(0xffffffffu, ssum.x, d); ssum.y += __shfl_xor_sync(0xffffffffu, ssum.y, d);
-                                    ssum.z += __shfl_xor_sync(0xffffffffu, ssum.z, d); ssum.w += __shfl_xor_sync(0xffffffffu, ssum.w, d);
-                                    ssq.x += __shfl_xor_sync(0xffffffffu, ssq.x, d); ssq.y += __shfl_xor_sync(0xffffffffu, ssq.y, d);
-                                    ssq.z += __shfl_xor_sync(0xffffffffu, ssq.z, d); ssq.w += __shfl_xor_sync(0xffffffffu, ssq.w, d);
-                                }
-                                if (lane < 8) {
-                                    float4* s0 = reinterpret_cast<float4*>(stat_sm + nt * a.bn + c0 + lane * 4);
-                                    float4* s1 = reinterpret_cast<float4*>(stat_sm + kStatCols + nt * a.bn + c0 + lane * 4);
-                                    float4 u0 = *s0, u1 = *s1;
-                                    u0.x += ssum.x; u0.y += ssum.y; u0.z += ssum.z; u0.w += ssum.w;
-                                    u1.x += ssq.x; u1.y += ssq.y; u1.z += ssq.z; u1.w += ssq.w;
-                                    *s0 = u0; *s1 = u1;
+                                    for (int i = 0; i < 8; ++i) {
+                                        const int r = q * 32 + i * 4 + (lane >> 3);
+                                        if (i * 4 + (lane >> 3) < rvalid) {
+                                            float4 o = lds128(buf + (uint32_t)r * 128u + (((uint32_t)cq ^ (uint32_t)(r & 7)) << 4));
+                                            o.x -= pv.x; o.y -= pv.y; o.z -= pv.z; o.w -= pv.w;
+                                            ssum.x += o.x; ssum.y += o.y; ssum.z += o.z; ssum.w += o.w;
+                                            ssq.x = fmaf(o.x, o.x, ssq.x); ssq.y = fmaf(o.y, o.y, ssq.y); ssq.z = fmaf(o.z, o.z, ssq.z); ssq.w = fmaf(o.w, o.w, ssq.w);
+                                        }
+                                    }
+#pragma unroll
+                                    for (int d = 8; d <= 16; d <<= 1) {
+                                        ssum.x += __shfl_xor_sync(0xffffffffu, ssum.x, d); ssum.y += __shfl_xor_sync(0xffffffffu, ssum.y, d);
+                                        ssum.z += __shfl_xor_sync(0xffffffffu, ssum.z, d); ssum.w += __shfl_xor_sync(0xffffffffu, ssum.w, d);
+                                        ssq.x += __shfl_xor_sync(0xffffffffu, ssq.x, d); ssq.y += __shfl_xor_sync(0xffffffffu, ssq.y, d);
+                                        ssq.z += __shfl_xor_sync(0xffffffffu, ssq.z, d); ssq.w += __shfl_xor_sync(0xffffffffu, ssq.w, d);
+                                    }
+                                    if (lane < 8) {
+                                        float4* s0 = reinterpret_cast<float4*>(stat_sm + col);
+                                        float4* s1 = reinterpret_cast<float4*>(stat_sm + kStatCols + col);
+                                        float4 u0 = *s0, u1 = *s1;
+                                        u0.x += ssum.x; u0.y += ssum.y; u0.z += ssum.z; u0.w += ssum.w;
+                                        u1.x += ssq.x; u1.y += ssq.y; u1.z += ssq.z; u1.w += ssq.w;
+                                        *s0 = u0; *s1 = u1;
+                                    }
                                 }
                             }
                         } else if (last && !(a.dbg & 4)) {
@@ -471,7 +509,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                                 psc = __ldg(reinterpret_cast<const float4*>(a.post.scale + nt * a.bn + c0 + cq * 4));
                                 psh = __ldg(reinterpret_cast<const float4*>(a.post.shift + nt * a.bn + c0 + cq * 4));
                             }
-                            float4 ssum = make_float4(0.f, 0.f, 0.f, 0.f), ssq = ssum;      // column sums over this lane's 8 rows
+                            float4 ssum = make_float4(0.f, 0.f, 0.f, 0.f), ssq = ssum;      // column sums over this lane's 8 rows (of o - pivot)
+                            float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
+                            const int scol = nt * a.bn + c0 + cq * 4;
+                            if (STATS && stat_rvalid(jt) > 0 && col_ok) {
+                                if (!((stat_seen >> nt) & 1u)) {               // the warp's row 0 of this tile, as it is about to be written
+                                    pv = lds128(stage_base + (uint32_t)cq * 16u);
+                                    pv.x += bq.x; pv.y += bq.y; pv.z += bq.z; pv.w += bq.w;
+                                    pv = piv_fix(pv, scol, lane < 8);
+                                } else {
+                                    pv = piv_load(scol);
+                                }
+                            }
                             // four row offsets (and, when accumulating, four old values) are fetched before the first dependent
                             // add / store, so the global-load latency is paid twice per chunk, not once per row
 #pragma unroll
@@ -500,12 +549,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                                             o.x += bq.x + oldv[r4].x; o.y += bq.y + oldv[r4].y; o.z += bq.z + oldv[r4].z; o.w += bq.w + oldv[r4].w;
                                         }
                                         *reinterpret_cast<float4*>(a.y + offs[r4] + c0 + cq * 4) = o;
-                                        ssum.x += o.x; ssum.y += o.y; ssum.z += o.z; ssum.w += o.w;
-                                        ssq.x = fmaf(o.x, o.x, ssq.x); ssq.y = fmaf(o.y, o.y, ssq.y); ssq.z = fmaf(o.z, o.z, ssq.z); ssq.w = fmaf(o.w, o.w, ssq.w);
+                                        if constexpr (STATS) {
+                                            o.x -= pv.x; o.y -= pv.y; o.z -= pv.z; o.w -= pv.w;
+                                            ssum.x += o.x; ssum.y += o.y; ssum.z += o.z; ssum.w += o.w;
+                                            ssq.x = fmaf(o.x, o.x, ssq.x); ssq.y = fmaf(o.y, o.y, ssq.y); ssq.z = fmaf(o.z, o.z, ssq.z); ssq.w = fmaf(o.w, o.w, ssq.w);
+                                        }
                                     }
                                 }
                             }
-                            if (a.stat_part != nullptr) {
+                            if constexpr (STATS) {
                                 // lanes l, l+8, l+16, l+24 hold the same four columns (different rows): fixed-order butterfly, then
                                 // lanes 0..7 add the warp's 32-row sums into the warp's shared-memory accumulators
 #pragma unroll
@@ -515,9 +567,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                                     ssq.x += __shfl_xor_sync(0xffffffffu, ssq.x, d); ssq.y += __shfl_xor_sync(0xffffffffu, ssq.y, d);
                                     ssq.z += __shfl_xor_sync(0xffffffffu, ssq.z, d); ssq.w += __shfl_xor_sync(0xffffffffu, ssq.w, d);
                                 }
-                                if (lane < 8 && col_ok) {
-                                    float4* s0 = reinterpret_cast<float4*>(stat_sm + nt * a.bn + c0 + lane * 4);
-                                    float4* s1 = reinterpret_cast<float4*>(stat_sm + kStatCols + nt * a.bn + c0 + lane * 4);
+                                if (lane < 8 && col_ok && stat_rvalid(jt) > 0) {
+                                    float4* s0 = reinterpret_cast<float4*>(stat_sm + scol);
+                                    float4* s1 = reinterpret_cast<float4*>(stat_sm + kStatCols + scol);
                                     float4 u0 = *s0, u1 = *s1;
                                     u0.x += ssum.x; u0.y += ssum.y; u0.z += ssum.z; u0.w += ssum.w;
                                     u1.x += ssq.x; u1.y += ssq.y; u1.z += ssq.z; u1.w += ssq.w;
@@ -534,12 +586,27 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 if (lane == 0) mbar_arrive(tempty_bar(acc));
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
+            if (STATS && stat_rvalid(jt) > 0) { stat_seen |= 1u << nt; __syncwarp(); }      // pivots of this column block are fixed (and visible to the warp)
         }
         if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // shared memory must outlive the bulk stores reading it
         if (a.stat_part != nullptr) {
             __syncwarp();
-            float* dst = a.stat_part + ((long long)blockIdx.x * 4 + q) * 2 * a.cout;
-            for (int i = lane; i < a.cout; i += 32) { dst[i] = stat_sm[i]; dst[a.cout + i] = stat_sm[kStatCols + i]; }
+            // rows this warp accumulated per column block: lane = column block, recomputed from the CTA's tile sequence
+            float cnt = 0.f;
+            for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+                const int nt = (int)(tile % a.n_tiles_n);
+                const int jt = (int)((tile / a.n_tiles_n) % a.tiles_t);
+                if (nt == lane) cnt += (float)stat_rvalid(jt);
+            }
+            float* dst = a.stat_part + ((long long)blockIdx.x * 4 + q) * 4 * a.cout;
+            for (int i0 = 0; i0 < a.cout; i0 += 32) {
+                const int i = i0 + lane;
+                const float ci = __shfl_sync(0xffffffffu, cnt, (i < a.cout ? i : 0) / a.bn);
+                if (i < a.cout) {
+                    dst[i] = stat_sm[i]; dst[a.cout + i] = stat_sm[kStatCols + i];
+                    dst[2 * a.cout + i] = __uint_as_float((uint32_t)stat_piv[i] << 16); dst[3 * a.cout + i] = ci;
+                }
+            }
         }
     } else if (BF) {
         // ===================================================== BF16x3 converter: one thread per activation row, in place
@@ -902,12 +969,11 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
     }
     {   // per call: the attribute is per device / context, a process-wide flag would skip the second GPU
         auto opt_in = [](auto kern) { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget); };
-        cudaError_t e = opt_in(conv_tc2_kernel<0, false>);
-        if (e == cudaSuccess) e = opt_in(conv_tc2_kernel<1, false>);
-        if (e == cudaSuccess) e = opt_in(conv_tc2_kernel<2, false>);
-        if (e == cudaSuccess && post) e = opt_in(conv_tc2_kernel<0, true>);
-        if (e == cudaSuccess && post) e = opt_in(conv_tc2_kernel<1, true>);
-        if (e == cudaSuccess && post) e = opt_in(conv_tc2_kernel<2, true>);
+        const int epi = post ? 1 : (stat_part != nullptr ? 2 : 0);
+        cudaError_t e = cudaSuccess;
+        if (epi == 0) { e = opt_in(conv_tc2_kernel<0, 0>); if (e == cudaSuccess) e = opt_in(conv_tc2_kernel<1, 0>); if (e == cudaSuccess) e = opt_in(conv_tc2_kernel<2, 0>); }
+        if (epi == 1) { e = opt_in(conv_tc2_kernel<0, 1>); if (e == cudaSuccess) e = opt_in(conv_tc2_kernel<1, 1>); if (e == cudaSuccess) e = opt_in(conv_tc2_kernel<2, 1>); }
+        if (epi == 2) { e = opt_in(conv_tc2_kernel<0, 2>); if (e == cudaSuccess) e = opt_in(conv_tc2_kernel<1, 2>); if (e == cudaSuccess) e = opt_in(conv_tc2_kernel<2, 2>); }
         if (e != cudaSuccess) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc2: %s", cudaGetErrorString(e));
     }
     if (skipped_parity && !accumulate) {
@@ -916,15 +982,16 @@ int agcn_conv_fwd_tc2(const float* x, const float* w, const float* bias, float* 
         if (e != cudaSuccess) return fail(AGCN_ERR_CUDA, "agcn_conv_fwd_tc2: cudaMemsetAsync: %s", cudaGetErrorString(e));
     }
     const long long grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
-    if (post) {
-        if (split == 2) conv_tc2_kernel<2, true><<<(unsigned)grid, kThreads2Split, smem, st>>>(map_a, map_b, map_blo, map_y0, map_y1, a);
-        else if (split) conv_tc2_kernel<1, true><<<(unsigned)grid, kThreads2Split, smem, st>>>(map_a, map_b, map_blo, map_y0, map_y1, a);
-        else conv_tc2_kernel<0, true><<<(unsigned)grid, kThreads2, smem, st>>>(map_a, map_b, map_blo, map_y0, map_y1, a);
-    } else {
-        if (split == 2) conv_tc2_kernel<2, false><<<(unsigned)grid, kThreads2Split, smem, st>>>(map_a, map_b, map_blo, map_y0, map_y1, a);
-        else if (split) conv_tc2_kernel<1, false><<<(unsigned)grid, kThreads2Split, smem, st>>>(map_a, map_b, map_blo, map_y0, map_y1, a);
-        else conv_tc2_kernel<0, false><<<(unsigned)grid, kThreads2, smem, st>>>(map_a, map_b, map_blo, map_y0, map_y1, a);
-    }
+    // EPI: 0 plain, 1 eval tail (PostOp), 2 fused BatchNorm statistics -- template parameters, so that every variant carries only its
+    // own epilogue code (the 480-thread parity-mode kernels sit at their 128-register cap; see the note at the template)
+    auto launch = [&](auto k0, auto k1, auto k2) {
+        if (split == 2) k2<<<(unsigned)grid, kThreads2Split, smem, st>>>(map_a, map_b, map_blo, map_y0, map_y1, a);
+        else if (split) k1<<<(unsigned)grid, kThreads2Split, smem, st>>>(map_a, map_b, map_blo, map_y0, map_y1, a);
+        else k0<<<(unsigned)grid, kThreads2, smem, st>>>(map_a, map_b, map_blo, map_y0, map_y1, a);
+    };
+    if (post) launch(conv_tc2_kernel<0, 1>, conv_tc2_kernel<1, 1>, conv_tc2_kernel<2, 1>);
+    else if (stat_part != nullptr) launch(conv_tc2_kernel<0, 2>, conv_tc2_kernel<1, 2>, conv_tc2_kernel<2, 2>);
+    else launch(conv_tc2_kernel<0, 0>, conv_tc2_kernel<1, 0>, conv_tc2_kernel<2, 0>);
     if (stat_nparts != nullptr) *stat_nparts = stat_part != nullptr ? (int)grid * 4 : 0;
     return check_launch("agcn_conv_fwd_tc2");
 }

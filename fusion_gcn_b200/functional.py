@@ -105,15 +105,15 @@ def gcn_forward(x, adj_a, adj_b, wa, ba, wb, bb, wd, bd, bn_w, bn_b, down_w, dow
     wdc = torch.cat([w.reshape(cout, 1, cin) for w in wd], dim=2).contiguous()
     bdc = bd[0] + bd[1] + bd[2]
 
-    want_mask = ctx is not None and spec.training        # the backward reads the ReLU mask as one bit per element
+    want_mask = ctx is not None                          # the backward reads the ReLU mask as one bit per element
     e = K.conv_fwd(x, wab, bab, precision=prec)                                        # theta / phi embeddings
     nchunk = K.pick_nchunk(nb, t, v, ci)
     s_part = K.joint_gram(e, e, groups=3, offa=0, stridea=2 * ci, offb=ci, strideb=2 * ci, width=ci, nchunk=nchunk, precision=prec)
     scale = 1.0 / float(ci * t)
     p, g = K.attention_fwd(s_part, adj_a.contiguous(), adj_b.contiguous(), scale)
     z = K.joint_mix(x, g, width=cin, mode=K.MIX_AGG_FWD, precision=prec)                               # [nb,t,v,3*cin]
-    if not spec.training:
-        # eval mode (session.py:188-194): BatchNorm is a per-channel affine of the running statistics, so BN, the down / identity
+    if not spec.training and ctx is None:
+        # eval mode without gradients (session.py:188-194): BatchNorm is a per-channel affine of the running statistics, so BN, the down / identity
         # branch and the ReLU ride in the projection's epilogue -- no pre-BN tensor, no separate normalise pass, nothing saved
         sc, sh = _eval_affine(bn_w, bn_b, spec.bn_gcn)
         if spec.has_down:
@@ -147,12 +147,16 @@ def gcn_backward(d_o, ctx, bn_w, dbn_w, down_w, spec: UnitSpec, dx=None, need_dx
     nb, t, v, cin = x.shape
     cout, ci, prec = spec.cout, ctx["ci"], spec.precision
     have = dx is not None
+    # eval mode with gradients (frozen-BN fine-tuning, saliency): the BatchNorms are affine maps of constants, and the biases of the
+    # convolutions in front of them get real gradients (the column sums of dy) instead of the training mode's analytic zeros
+    frozen = not spec.training
     if spec.has_down:
-        dy, dgam, dbet = K.bn_bwd(d_o, o, y, ctx["mean"], ctx["invstd"], bn_w, mask_bits=ctx["o_bits"])
-        dyd, dgam2, dbet2 = K.bn_bwd(d_o, o, ctx["yd"], ctx["mean2"], ctx["invstd2"], dbn_w, mask_bits=ctx["o_bits"])
+        dy, dgam, dbet = K.bn_bwd(d_o, o, y, ctx["mean"], ctx["invstd"], bn_w, mask_bits=ctx["o_bits"], frozen=frozen)
+        dyd, dgam2, dbet2 = K.bn_bwd(d_o, o, ctx["yd"], ctx["mean2"], ctx["invstd2"], dbn_w, mask_bits=ctx["o_bits"], frozen=frozen)
         wdown = down_w.reshape(cout, 1, cin)
-        d_down_w, _ = K.conv_wgrad(dyd, x, want_bias=False, precision=prec)
-        d_down_b = _zero_bias(x, cout)
+        d_down_w, d_down_b = K.conv_wgrad(dyd, x, want_bias=frozen, precision=prec)
+        if not frozen:
+            d_down_b = _zero_bias(x, cout)
         if need_dx:
             dx = K.conv_fwd(dyd, _t(wdown), out=dx, accumulate=have, precision=prec)
             have = True
@@ -160,11 +164,12 @@ def gcn_backward(d_o, ctx, bn_w, dbn_w, down_w, spec: UnitSpec, dx=None, need_dx
         if need_dx and dx is None:
             dx = torch.empty_like(x)
         dy, dgam, dbet = K.bn_bwd(d_o, o, y, ctx["mean"], ctx["invstd"], bn_w,
-                                  dres=dx if need_dx else None, dres_accumulate=have, mask_bits=ctx["o_bits"])
+                                  dres=dx if need_dx else None, dres_accumulate=have, mask_bits=ctx["o_bits"], frozen=frozen)
         have = have or need_dx
         dgam2 = dbet2 = d_down_w = d_down_b = None
-    d_wdc, _ = K.conv_wgrad(dy, z, want_bias=False, precision=prec)
-    d_bdc = _zero_bias(x, cout)
+    d_wdc, d_bdc = K.conv_wgrad(dy, z, want_bias=frozen, precision=prec)
+    if not frozen:
+        d_bdc = _zero_bias(x, cout)
     dz = K.conv_fwd(dy, _t(ctx["wdc"]), precision=prec)                                # [nb,t,v,3*cin]
     dg_part = K.joint_gram(x, dz, groups=3, offa=0, stridea=0, offb=0, strideb=cin, width=cin, nchunk=K.pick_nchunk(nb, t, v, cin),
                            precision=prec)
@@ -202,8 +207,8 @@ def tcn_forward(o, x_res, wt, bt, bn_w, bn_b, wr, br, rbn_w, rbn_b, spec: UnitSp
     t_out = (t + 2 * pad - ksz) // s + 1
     prec = spec.precision
     wtp = _pack_taps(wt)
-    if not spec.training:
-        # eval mode: temporal conv + BN + residual + ReLU in one pass (the residual branch's conv + BN in one more)
+    if not spec.training and ctx is None:
+        # eval mode without gradients: temporal conv + BN + residual + ReLU in one pass (the residual branch's conv + BN in one more)
         sc, sh = _eval_affine(bn_w, bn_b, spec.bn_tcn)
         if spec.residual == "identity":
             res = x_res
@@ -213,15 +218,14 @@ def tcn_forward(o, x_res, wt, bt, bn_w, bn_b, wr, br, rbn_w, rbn_b, spec: UnitSp
         else:
             res = None
         out = K.conv_fwd_post(o, wtp, bt, scale=sc, shift=sh, res=res, relu=spec.relu_out, t_out=t_out, stride=s, pad=pad, precision=prec)
-        if spec.pool_groups and ctx is not None:
-            ctx.update(pool_rows=0)
         return out
     u, (sc, sh, mean, invstd) = _conv_bn(o, wtp, bt, bn_w, bn_b, spec.bn_tcn, spec.training, prec, t_out=t_out, stride=s, pad=pad)
     ur = mean2 = invstd2 = wrp = None
-    want_mask = ctx is not None and spec.training and spec.relu_out
+    want_mask = ctx is not None and spec.relu_out
     # the model's tail (agcn.py:194-196): the last unit's output only feeds the global mean pool, so the pooled means and the ReLU
     # mask bits come out of the normalise / residual / ReLU pass and the feature map itself is never written
-    pool = spec.pool_groups if (spec.pool_groups and spec.relu_out and K.bn_pool_supported(u.numel() // u.shape[-1], u.shape[-1])) else 0
+    pool = spec.pool_groups if (spec.pool_groups and spec.training and spec.relu_out and
+                                K.bn_pool_supported(u.numel() // u.shape[-1], u.shape[-1])) else 0
     apply = (lambda *a, **kw: K.bn_apply_pool(*a, groups=pool, **{k: v for k, v in kw.items() if k != "relu"})) if pool else \
         (lambda *a, **kw: _apply(want_mask, *a, **kw))
     if spec.residual == "identity":
@@ -248,21 +252,25 @@ def tcn_backward(d_out, ctx, bn_w, rbn_w, spec: UnitSpec, need_dres=True, need_d
     pk = dict(pool_rows=ctx["pool_rows"]) if ctx.get("pool_rows") else {}       # d_out is then the pooled gradient [groups, c]
     d_xres = None
     d_wr = d_br = dgam2 = dbet2 = None
+    frozen = not spec.training          # eval mode with gradients, see gcn_backward
+    pk["frozen"] = frozen
     if spec.residual == "identity":
         d_xres = torch.empty_like(x_res) if need_dres else None
         du, dgam, dbet = K.bn_bwd(d_out, mask, u, ctx["t_mean"], ctx["t_invstd"], bn_w, dres=d_xres, dres_accumulate=False, mask_bits=bits, **pk)
     elif spec.residual == "conv":
         du, dgam, dbet = K.bn_bwd(d_out, mask, u, ctx["t_mean"], ctx["t_invstd"], bn_w, mask_bits=bits, **pk)
         dur, dgam2, dbet2 = K.bn_bwd(d_out, mask, ctx["ur"], ctx["t_mean2"], ctx["t_invstd2"], rbn_w, mask_bits=bits, **pk)
-        d_wrp, _ = K.conv_wgrad(dur, x_res, taps=1, stride=s, pad=0, want_bias=False, precision=prec)
-        d_br = _zero_bias(d_out, d_wrp.shape[0])
+        d_wrp, d_br = K.conv_wgrad(dur, x_res, taps=1, stride=s, pad=0, want_bias=frozen, precision=prec)
+        if not frozen:
+            d_br = _zero_bias(d_out, d_wrp.shape[0])
         d_wr = d_wrp.permute(0, 2, 1).unsqueeze(-1)
         if need_dres:
             d_xres = K.conv_fwd(dur, _t(ctx["wrp"]), t_out=x_res.shape[1], stride=s, pad=0, transposed=True, precision=prec)
     else:
         du, dgam, dbet = K.bn_bwd(d_out, mask, u, ctx["t_mean"], ctx["t_invstd"], bn_w, mask_bits=bits, **pk)
-    d_wtp, _ = K.conv_wgrad(du, o, taps=ksz, stride=s, pad=pad, want_bias=False, precision=prec)
-    d_bt = _zero_bias(d_out, d_wtp.shape[0])
+    d_wtp, d_bt = K.conv_wgrad(du, o, taps=ksz, stride=s, pad=pad, want_bias=frozen, precision=prec)
+    if not frozen:
+        d_bt = _zero_bias(d_out, d_wtp.shape[0])
     d_o = None
     if need_do:
         d_o = K.conv_fwd(du, _t(ctx["wtp"]), t_out=o.shape[1], stride=s, pad=pad, transposed=True, precision=prec)
@@ -307,9 +315,12 @@ def _need_backward(spec, store=True):
     if store is None:
         raise RuntimeError("fusion_gcn_b200: backward through the same forward a second time (retain_graph=True) is not supported: "
                            "the saved activations are released after the first backward")
-    if not spec.training:
-        raise NotImplementedError("fusion_gcn_b200: backward through eval-mode BatchNorm is not implemented "
-                                  "(use model.train() for training, torch.no_grad() for evaluation)")
+
+
+def _store(ctx, spec):
+    """Activation store of one forward: a dict when a backward can follow (training mode, or eval mode with an input or parameter
+    that requires a gradient), None otherwise -- eval mode then takes the fused, nothing-saved path."""
+    return {} if (spec.training or any(ctx.needs_input_grad)) else None
 
 
 class GcnFn(torch.autograd.Function):
@@ -317,7 +328,7 @@ class GcnFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, spec, *params):
-        store = {}
+        store = _store(ctx, spec)
         o = gcn_forward(x, *_split_gcn(params), spec, store)
         ctx.spec, ctx.store, ctx.params = spec, store, params
         return o
@@ -336,7 +347,7 @@ class TcnFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, o, x_res, spec, *params):
-        store = {}
+        store = _store(ctx, spec)
         out = tcn_forward(o, x_res, *params, spec, store)
         ctx.spec, ctx.store, ctx.params = spec, store, params
         return out
@@ -357,7 +368,7 @@ class UnitFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, spec, *params):
-        store = {}
+        store = _store(ctx, spec)
         gp, tp = params[:GCN_NPARAMS], params[GCN_NPARAMS:]
         o = gcn_forward(x, *_split_gcn(gp), spec, store)
         out = tcn_forward(o, x if spec.residual != "none" else None, *tp, spec, store)
@@ -401,8 +412,6 @@ class DataBnFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_out):
-        if not ctx.training:
-            raise NotImplementedError("fusion_gcn_b200: backward through eval-mode BatchNorm is not implemented")
         x, gamma = ctx.x, ctx.gamma
         n, m, t, v, c = x.shape
         vc = v * c
@@ -416,7 +425,7 @@ class DataBnFn(torch.autograd.Function):
             rowmap = (n, t, m * t * vc, vc)
             mean, invstd = ctx.saved[mi]
             _, dg, db = K.bn_bwd(d_out[:, mi], None, x[:, mi], mean, invstd, gamma[sl], want_dy=need_dx,
-                                 dy=dx[:, mi] if need_dx else None, rowmap=rowmap)
+                                 dy=dx[:, mi] if need_dx else None, rowmap=rowmap, frozen=not ctx.training)
             dgamma[sl] = dg
             dbeta[sl] = db
         return dx, dgamma, dbeta, None, None

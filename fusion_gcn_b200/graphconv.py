@@ -113,10 +113,8 @@ class _RowBnFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        if not ctx.training:
-            raise NotImplementedError("fusion_gcn_b200: backward through eval-mode BatchNorm is not implemented")
         x, gamma, mean, invstd = ctx.saved_tensors
-        dx, dgamma, dbeta = FN.K.bn_bwd(dy.contiguous(), None, x, mean, invstd, gamma)
+        dx, dgamma, dbeta = FN.K.bn_bwd(dy.contiguous(), None, x, mean, invstd, gamma, frozen=not ctx.training)
         return dx, dgamma, dbeta, None, None
 
 

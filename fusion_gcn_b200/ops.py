@@ -171,8 +171,8 @@ def conv_fwd_post(x, w, bias=None, *, scale=None, shift=None, res=None, relu=Fal
 
 def conv_fwd_stats(x, w, bias=None, *, t_out=None, stride=1, pad=0, precision=PREC_FP32):
     """conv_fwd whose epilogue also accumulates the column sums of y for the training-mode BatchNorm that follows
-    (agcn_conv_fwd_stats).  -> (y, part) with part [nparts, 2, cout] (sum | sum of squares), or (y, None) when the fused
-    epilogue does not cover the shape (run bn_stats on y then)."""
+    (agcn_conv_fwd_stats).  -> (y, part) with part [nparts, 4, cout] (shifted sum | shifted sum of squares | pivot | row count per
+    partial), or (y, None) when the fused epilogue does not cover the shape (run bn_stats on y then)."""
     import ctypes
     nb, t_in, v, cin = x.shape
     cout, taps, cin_w = w.shape
@@ -195,11 +195,11 @@ def conv_fwd_stats(x, w, bias=None, *, t_out=None, stride=1, pad=0, precision=PR
           work=(2.0 * rows * cin * cout * taps, 4.0 * (x.numel() + rows * cout)), alias="agcn_conv_fwd")
     if nparts.value == 0:
         return out, None
-    return out, part[:nparts.value * 2 * cout].view(nparts.value, 2, cout)
+    return out, part[:nparts.value * 4 * cout].view(nparts.value, 4, cout)
 
 
 def bn_finalize(part, rows, gamma, beta, running_mean, running_var, nbt, momentum, eps):
-    """Training-mode BatchNorm parameters from column sums (conv_fwd_stats): -> scale, shift, save_mean, save_invstd."""
+    """Training-mode BatchNorm parameters from the partials of conv_fwd_stats: -> scale, shift, save_mean, save_invstd."""
     nparts, _, c = part.shape
     scale = torch.empty((4, c), device=part.device, dtype=torch.float32)
     _check(part, gamma, beta, running_mean, running_var)
@@ -347,10 +347,10 @@ def bn_apply(y, scale, shift, *, res_mode=RES_NONE, res=None, scale2=None, shift
 
 
 def bn_bwd(dout, mask_out, y, save_mean, save_invstd, gamma, *, want_dy=True, dy=None, dres=None, dres_accumulate=False,
-           rowmap=None, mask_bits=None, pool_rows=0):
+           rowmap=None, mask_bits=None, pool_rows=0, frozen=False):
     """-> dy | None, dgamma, dbeta; optionally writes / accumulates the masked gradient into ``dres``.
     ``dy`` may be a preallocated tensor addressed with the same rowmap as ``y``.  ``mask_bits`` (from bn_apply(want_mask=True))
-    replaces the fp32 tensor ``mask_out`` as the ReLU mask."""
+    replaces the fp32 tensor ``mask_out`` as the ReLU mask.  ``frozen``: the statistics are constants (eval-mode BatchNorm)."""
     outer, inner, ostride, c = _rowmap(y, rowmap)
     if want_dy and dy is None:
         dy = torch.empty_like(y)
@@ -358,6 +358,8 @@ def bn_bwd(dout, mask_out, y, save_mean, save_invstd, gamma, *, want_dy=True, dy
     _check(save_mean, save_invstd, gamma)
     dgb = torch.empty((2, c), device=y.device, dtype=torch.float32)
     ws, nbytes = _bn_ws(c, y.device)
+    if pool_rows and frozen:
+        raise RuntimeError("bn_bwd: the pooled tail is a training-mode path")
     if pool_rows:
         # ``dout`` is the gradient of the fused mean pool, [groups, c], broadcast over the pool_rows rows of each group
         _check(dout, y, dy, dres)
@@ -372,13 +374,13 @@ def bn_bwd(dout, mask_out, y, save_mean, save_invstd, gamma, *, want_dy=True, dy
             raise RuntimeError("bn_bwd: mask_bits must be the int32 CUDA tensor returned by bn_apply(want_mask=True)")
         _check(dout, y, dy, dres)
         _call("agcn_bn_bwd_bits", dout.data_ptr(), mask_bits.data_ptr(), y.data_ptr(), _ptr(save_mean), _ptr(save_invstd), _ptr(gamma),
-              _ptr(dy), dgb[0].data_ptr(), dgb[1].data_ptr(), _ptr(dres), int(dres_accumulate), inner, c, _ptr(ws), nbytes, _stream(),
+              _ptr(dy), dgb[0].data_ptr(), dgb[1].data_ptr(), _ptr(dres), int(dres_accumulate), int(frozen), inner, c, _ptr(ws), nbytes, _stream(),
               sig=(outer, inner, c, 2, int(dy is not None), int(dres is not None), int(dres_accumulate)),
               work=(0.0, 4.0 * outer * inner * c * (2 * 2 + 2.0 / 32 + int(dy is not None) + int(dres is not None) * (1 + int(dres_accumulate)))),
               alias="agcn_bn_bwd")
         return dy, dgb[0], dgb[1]
     _call("agcn_bn_bwd", dout.data_ptr(), _ptr(mask_out), y.data_ptr(), _ptr(save_mean), _ptr(save_invstd), _ptr(gamma),
-          _ptr(dy), dgb[0].data_ptr(), dgb[1].data_ptr(), _ptr(dres), int(dres_accumulate), outer, inner, ostride, c,
+          _ptr(dy), dgb[0].data_ptr(), dgb[1].data_ptr(), _ptr(dres), int(dres_accumulate), int(frozen), outer, inner, ostride, c,
           _ptr(ws), nbytes, _stream(),
           sig=(outer, inner, c, int(mask_out is not None), int(dy is not None), int(dres is not None), int(dres_accumulate)),
           # two passes over (dout, y[, mask]); the second writes dy [and dres, read first when accumulating]

@@ -98,8 +98,10 @@ int agcn_conv_fwd_post(const float* x, const float* w, const float* bias,
 
 /* agcn_conv_fwd (forward gather, no accumulate) whose epilogue also leaves the per-channel sums the training-mode
  * BatchNorm that follows needs (nn.Conv2d -> nn.BatchNorm2d pairs at agcn.py:41-51,73-83): stat_part receives
- * [*stat_nparts][2][cout] floats (sum | sum of squares of y over a fixed row partition, deterministic), to be
- * combined by agcn_bn_finalize.  *stat_nparts == 0 on return means the fused epilogue does not cover this shape:
+ * [*stat_nparts][4][cout] floats: per partial (a fixed set of rows, deterministic) and channel the SHIFTED sums
+ *   sum(y - p) | sum((y - p)^2) | p | number of rows,   p = the first value of the channel the partial saw,
+ * to be combined by agcn_bn_finalize (pairwise-variance merge in fp64: E[y^2] - mean^2 on raw fp32 sums loses the variance
+ * of channels with |mean| >> sigma).  *stat_nparts == 0 on return means the fused epilogue does not cover this shape:
  * y is complete, run agcn_bn_stats on it.  stat_part: agcn_conv_fwd_stats_bytes(cout) bytes, 16-byte aligned.
  * stat_nparts is a HOST pointer.                                                                          */
 size_t agcn_conv_fwd_stats_bytes(int cout);
@@ -157,7 +159,8 @@ int agcn_joint_mix(const float* in, const float* mats, float* out,
  * precisely: offset(o, i, ch) = o*outer_stride + i*channels + ch, rows = outer*inner.  For unit tensors
  * outer=1... (outer_stride ignored when outer==1); data_bn uses outer=N, inner=T, channels=V*C per body.
  *
- * training!=0: batch mean / biased variance over rows (eps as given), running statistics updated in
+ * training!=0: batch mean / biased variance over rows (eps as given; from sums shifted by the first row of x, so
+ *   channels with |mean| >> sigma keep their variance), running statistics updated in
  *   place with `momentum` and the unbiased variance, *num_batches_tracked incremented (may be NULL).
  * training==0: scale/shift from the running statistics.
  * Outputs: scale[c] = gamma*invstd, shift[c] = beta - mean*scale, save_mean[c], save_invstd[c].          */
@@ -168,8 +171,8 @@ int agcn_bn_stats(const float* x, int outer, int inner, long long outer_stride, 
                   float* scale, float* shift, float* save_mean, float* save_invstd,
                   void* workspace, size_t workspace_bytes, void* stream);
 
-/* The finalize half of agcn_bn_stats (training mode) on column sums produced by agcn_conv_fwd_stats:
- * part[nparts][2][channels] (sum | sum of squares), rows = number of rows they cover.                     */
+/* The finalize half of agcn_bn_stats (training mode) on the partials produced by agcn_conv_fwd_stats:
+ * part[nparts][4][channels] (shifted sum | shifted sum of squares | pivot | row count), rows = number of rows they cover. */
 int agcn_bn_finalize(const float* part, int nparts, long long rows, int channels,
                      const float* gamma, const float* beta, float* running_mean, float* running_var,
                      long long* num_batches_tracked, float momentum, float eps,
@@ -192,17 +195,19 @@ int agcn_bn_apply_mask(const float* y, const float* scale, const float* shift,
                        int relu, float* out, unsigned* mask_bits, int inner, int channels, void* stream);
 int agcn_bn_bwd_bits(const float* dout, const unsigned* mask_bits, const float* y,
                      const float* save_mean, const float* save_invstd, const float* gamma,
-                     float* dy, float* dgamma, float* dbeta, float* dres, int dres_accumulate,
+                     float* dy, float* dgamma, float* dbeta, float* dres, int dres_accumulate, int frozen_stats,
                      int inner, int channels, void* workspace, size_t workspace_bytes, void* stream);
 
 /* BatchNorm backward through an optional ReLU mask:
  *   g = dout * [mask_out > 0]  (g = dout when mask_out == NULL)
  *   dbeta = sum g;  dgamma = sum g*xhat;  dy = gamma*invstd*(g - dbeta/m - xhat*dgamma/m),  xhat = (y-mean)*invstd
  * If dres != NULL the masked gradient g is also written (dres_accumulate==0) or added to dres
- * (gradient of an identity residual / of the tensor R above).  dy may be NULL (only sums wanted).       */
+ * (gradient of an identity residual / of the tensor R above).  dy may be NULL (only sums wanted).
+ * frozen_stats != 0: mean / invstd are constants -- the backward of an eval-mode BatchNorm on its running statistics (the
+ * reference's autograd under model.eval()): dy = gamma*invstd*g, dgamma and dbeta as above.                                  */
 int agcn_bn_bwd(const float* dout, const float* mask_out, const float* y,
                 const float* save_mean, const float* save_invstd, const float* gamma,
-                float* dy, float* dgamma, float* dbeta, float* dres, int dres_accumulate,
+                float* dy, float* dgamma, float* dbeta, float* dres, int dres_accumulate, int frozen_stats,
                 int outer, int inner, long long outer_stride, int channels,
                 void* workspace, size_t workspace_bytes, void* stream);
 

@@ -123,16 +123,21 @@ def attention_bwd(dg_part, p, scale):
 
 
 def conv_fwd_stats(x, w, bias=None, *, t_out=None, stride=1, pad=0, precision=0):
-    """conv_fwd plus the column sums a following training-mode BatchNorm needs: part [1, 2, cout] = (sum, sum of squares)."""
+    """conv_fwd plus what a following training-mode BatchNorm needs: part [1, 4, cout] = (sum, sum of squares) of y - p, the pivot p
+    (the first row of y) and the row count -- the layout of agcn_conv_fwd_stats with a single partial."""
     y = conv_fwd(x, w, bias, t_out=t_out, stride=stride, pad=pad)
     flat = y.reshape(-1, y.shape[-1]).double()
-    return y, torch.stack([flat.sum(0), (flat * flat).sum(0)]).unsqueeze(0)
+    pivot = flat[0].clone()
+    flat = flat - pivot
+    return y, torch.stack([flat.sum(0), (flat * flat).sum(0), pivot, torch.full_like(pivot, flat.shape[0])]).unsqueeze(0)
 
 
 def bn_finalize(part, rows, gamma, beta, running_mean, running_var, nbt, momentum, eps):
-    s = part.double().sum(0)
-    mean = s[0] / rows
-    var = (s[1] / rows - mean * mean).clamp_min(0)
+    p = part.double()
+    s1, s2, piv, cnt = p[:, 0], p[:, 1], p[:, 2], p[:, 3].clamp_min(1)
+    mean_p = piv + s1 / cnt
+    mean = (mean_p * p[:, 3]).sum(0) / rows
+    var = (((s2 - s1 * s1 / cnt) + p[:, 3] * (mean_p - mean) ** 2).sum(0) / rows).clamp_min(0)          # pairwise-variance merge
     if running_mean is not None:
         unbiased = var * rows / (rows - 1) if rows > 1 else var
         running_mean.mul_(1 - momentum).add_((momentum * mean).to(running_mean.dtype))
@@ -222,7 +227,7 @@ def _bn_apply(y, scale, shift, *, res_mode=RES_NONE, res=None, scale2=None, shif
 
 
 def bn_bwd(dout, mask_out, y, save_mean, save_invstd, gamma, *, want_dy=True, dy=None, dres=None, dres_accumulate=False,
-           rowmap=None, mask_bits=None, pool_rows=0):
+           rowmap=None, mask_bits=None, pool_rows=0, frozen=False):
     if pool_rows:          # dout is the pooled gradient [groups, c]: broadcast over the rows of each group, divided by their number
         groups, c = dout.shape
         dout = (dout / pool_rows).reshape(groups, 1, c).expand(groups, pool_rows, c).reshape(y.shape).contiguous()
@@ -242,7 +247,8 @@ def bn_bwd(dout, mask_out, y, save_mean, save_invstd, gamma, *, want_dy=True, dy
         gam = gamma if gamma is not None else torch.ones_like(save_mean)
         if dy is None:
             dy = torch.empty_like(y)
-        _rows_view(dy, rowmap).copy_(gam * save_invstd * (g - dbeta / m - xhat * dgamma / m))
+        # frozen: eval-mode BatchNorm, the statistics are constants
+        _rows_view(dy, rowmap).copy_(gam * save_invstd * (g if frozen else g - dbeta / m - xhat * dgamma / m))
     if dres is not None:
         dv = _rows_view(dres, rowmap)
         if dres_accumulate:

@@ -70,3 +70,40 @@ def stat_err(a, ref, floor=1e-3):
     a = torch.as_tensor(a).detach().double().cpu()
     b = torch.as_tensor(ref).detach().double().cpu()
     return (a - b).abs().max().item() / max(b.abs().max().item(), floor)
+
+
+def eval_mode_gradient_case(M, G, device, tol):
+    """Gradients under model.eval() (frozen-BatchNorm fine-tuning, saliency maps): every BatchNorm is an affine map of its running
+    statistics, so the biases of the convolutions in front of them get real gradients; compared with the fp64 oracle's autograd."""
+    from oracle import agcn_oracle as O
+    g = load_golden("model_utd_s8")
+    m, t, v, c, ncls, start = [int(a) for a in g["meta"]]
+    state = {k: to_t(a) for k, a in sub(g, "state.").items()}
+    state.update({k: to_t(a).to(state[k].dtype) for k, a in sub(g, "f64.after.").items()})      # non-trivial running statistics
+    model = M.Model((m, t, v, c), ncls, G.SkeletonGraph(G.UTD_EDGES), start_feature_size=start).to(device)
+    model.load_state_dict(state, strict=True)
+    model.eval()
+    x = to_t(g["x"]).to(device).requires_grad_(True)
+    w = to_t(g["w"]).to(device)
+    y = model(x)
+    (y * w).sum().backward()
+    before = {k: b.clone() for k, b in model.named_buffers()}
+    p = O.as_leaves({k: a.double() if a.is_floating_point() else a for k, a in state.items()})
+    x64 = to_t(g["x"]).double().requires_grad_(True)
+    y64 = O.model_forward(x64, p, c, False, start=start)
+    (y64 * to_t(g["w"]).double()).sum().backward()
+    assert rel_err(y, y64) <= tol
+    assert rel_err(x.grad, x64.grad) <= tol
+    ref = {k: p[k].grad for k, _ in model.named_parameters()}
+    scale = max(float(r.abs().max()) for r in ref.values())
+    for k, q in model.named_parameters():
+        assert q.grad is not None, k
+        # no analytic zeros here: tensors whose gradient is tiny are compared on the scale of the largest gradient
+        err = float((q.grad.detach().double().cpu() - ref[k]).abs().max()) / max(float(ref[k].abs().max()), 1e-3 * scale)
+        assert err <= tol, f"{k}: {err:.3e}"
+    assert float(ref["l3.tcn1.conv.bias"].abs().max()) > 0 and float(model.l3.tcn1.conv.bias.grad.abs().max()) > 0
+    for k, b in model.named_buffers():                                                             # eval mode leaves the statistics alone
+        assert torch.equal(b, before[k]), k
+    model(to_t(g["x"]).to(device))                                                                 # no_grad-free eval forward still works
+    with torch.no_grad():
+        assert rel_err(model(to_t(g["x"]).to(device)), y64) <= tol

@@ -141,7 +141,7 @@ def test_optimizer_step_inside_the_captured_step_graph(O):
     pointer tables are uploaded from pinned memory, so building them during capture -- when the gradients get their static
     addresses -- is legal; three replays match three eager torch.optim.SGD steps on a twin."""
     from fusion_gcn_b200 import graph as G, modules as M
-    from fusion_gcn_b200.graphed import GraphedStep
+    from fusion_gcn_b200.graphed import GraphedStep, loss_and_logits
     torch.manual_seed(1)
     graph = G.SkeletonGraph(G.UTD_EDGES, center_joint=G.UTD_CENTER)
     m1 = M.Model((1, 16, 20, 3), 27, graph, start_feature_size=16).cuda().train()
@@ -161,11 +161,16 @@ def test_optimizer_step_inside_the_captured_step_graph(O):
     o2 = torch.optim.SGD(m2.parameters(), **kw)
     for p in m2.parameters():
         o2.state[p]["momentum_buffer"] = torch.zeros_like(p)
-    for _ in range(3):
+    # SURVEY D8 metric (max-norm per tensor).  The first step sees identical gradients, so only the optimizer arithmetic differs (fused
+    # multiply-adds against torch's separate ops: the last bit).  From the second step on the two models are no longer bit-identical,
+    # and in this small model a ReLU input within rounding distance of zero may take the other bracket in one of them -- the later
+    # steps are therefore held to a training-curve tolerance only (they prove that the replays keep stepping).
+    for it in range(3):
         step()
         o2.zero_grad(set_to_none=True)
-        lf(m2(x), y).backward()
+        loss_and_logits(m2, lf, x, y)[0].backward()          # the same (fused-head) loss path as the graph
         o2.step()
-    torch.cuda.synchronize()
-    for (k, a), (_, b) in zip(m2.named_parameters(), m1.named_parameters()):
-        assert torch.allclose(b, a, rtol=2e-4, atol=1e-6), k
+        torch.cuda.synchronize()
+        for (k, a), (_, b) in zip(m2.named_parameters(), m1.named_parameters()):
+            err = float((b - a).abs().max()) / max(float(a.abs().max()), 1e-6)
+            assert err <= (2e-6 if it == 0 else 5e-3), f"step {it} {k}: {err:.3e}"

@@ -85,7 +85,8 @@ def test_conv_fwd_fused_bn_statistics(K, nb, t_in, v, cin, cout, taps, stride, m
     if cin % 4:
         assert part is None
         return
-    assert part is not None and part.shape[1:] == (2, cout)
+    assert part is not None and part.shape[1:] == (4, cout)          # shifted sum | shifted sum of squares | pivot | rows per partial
+    assert float(part[:, 3].sum(0).min()) == float(part[:, 3].sum(0).max()) == nb * t_out * v
     rm, rv, nbt = torch.zeros(cout).cuda(), torch.ones(cout).cuda(), torch.zeros((), dtype=torch.long).cuda()
     rm2, rv2, nbt2 = rm.clone(), rv.clone(), nbt.clone()
     got = K.bn_finalize(part, nb * t_out * v, gamma, beta, rm, rv, nbt, 0.1, 1e-5)
@@ -196,6 +197,36 @@ def test_joint_mix_tf32_mode(K, nb, t, v, w):
     e = rnd(nb, t, v, 6 * ci, seed=3)
     de = K.joint_mix(e.cuda(), mats.cuda(), width=ci, mode=K.MIX_SCORE_BWD, precision=K.PREC_TF32)
     assert rel_err(de, S.joint_mix(_trunc_tf32(e).double(), _trunc_tf32(mats).double(), width=ci, mode=S.MIX_SCORE_BWD)) <= 1e-5
+
+
+@pytest.mark.parametrize("rows,c", [(20000, 64), (3001, 12), (9000, 256)])
+def test_bn_statistics_of_channels_with_mean_far_from_zero(K, rows, c):
+    """|mean| >> sigma (raw coordinates, near-constant channels): E[x^2] - mean^2 in fp32 loses (mean/sigma)^2 x 1e-6 of the variance
+    -- at mean 100, sigma 0.1 everything.  The sums are shifted by a pivot (first row / running mean), like Welford in torch."""
+    x = (rnd(rows, c) * 0.1 + 100.0)
+    gamma, beta = rnd(c, seed=1) * 0.3 + 1, rnd(c, seed=2) * 0.1
+    ref = S.bn_stats(x.double(), gamma.double(), beta.double(), torch.zeros(c).double(), torch.ones(c).double(), None, 0.1, 1e-5, True)
+    rm, rv = torch.zeros(c).cuda(), torch.ones(c).cuda()
+    out = K.bn_stats(x.cuda(), gamma.cuda(), beta.cuda(), rm, rv, None, 0.1, 1e-5, True)
+    assert rel_err(out[3], ref[3]) <= 2e-5 and rel_err(out[2], ref[2]) <= 1e-6 and rel_err(out[0], ref[0]) <= 2e-5      # invstd, mean, scale
+    assert rel_err(rv, 0.9 + 0.1 * x.double().var(dim=0, unbiased=True)) <= 1e-5
+    if c % 32 == 0:
+        # the same through the convolution epilogues (1x1: TMA-store path, 9 taps: per-warp staging path): an identity-like conv with a
+        # large bias; every partial shifts its sums by the first value it sees and agcn_bn_finalize merges them pairwise in fp64
+        nb, t, v = 2, rows // 50, 25
+        xi = rnd(nb, t, v, c).cuda() * 0.1
+        for taps in (1, 9):
+            w = torch.zeros(c, taps, c)
+            w[:, taps // 2] = torch.eye(c)
+            b = torch.full((c,), 100.0).cuda()
+            y, part = K.conv_fwd_stats(xi, w.cuda(), b, pad=taps // 2, precision=K.PREC_FP32)
+            assert part is not None
+            rm2, rv2 = torch.zeros(c).cuda(), torch.ones(c).cuda()
+            got = K.bn_finalize(part, nb * t * v, gamma.cuda(), beta.cuda(), rm2, rv2, None, 0.1, 1e-5)
+            yd = y.double().cpu().reshape(-1, c)
+            invstd_ref = 1.0 / torch.sqrt(yd.var(dim=0, unbiased=False) + 1e-5)
+            assert rel_err(got[3], invstd_ref) <= 2e-5 and rel_err(got[2], yd.mean(0)) <= 1e-6, taps
+            assert rel_err(rm2, 0.1 * yd.mean(0)) <= 1e-6 and rel_err(rv2, 0.9 + 0.1 * yd.var(dim=0, unbiased=True)) <= 1e-5
 
 
 @pytest.mark.parametrize("rows,c", [(1000, 64), (777, 3), (4099, 256), (300, 515), (50, 12), (9000, 128), (64, 8)])

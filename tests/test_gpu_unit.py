@@ -6,7 +6,8 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import (ZERO_GRAD, MODEL_FIXTURES, RESIDUAL_KINDS, UNIT_FIXTURES, check_grads, load_golden, rel_err, stat_err, sub, to_t)
+from helpers import (ZERO_GRAD, MODEL_FIXTURES, RESIDUAL_KINDS, UNIT_FIXTURES, check_grads, eval_mode_gradient_case, load_golden, rel_err, stat_err,
+                     sub, to_t)
 from oracle import agcn_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -163,9 +164,14 @@ def test_standalone_modules_reference_layout(pkg):
     unit = M.SpatialTemporalConv(8, 8, adj).cuda()
     y = unit(x)
     assert y.shape == x.shape and y.is_contiguous()
-    with pytest.raises(NotImplementedError):
-        unit.eval()
-        unit(x.requires_grad_(True)).sum().backward()
+    unit.eval()                                              # gradients under eval(): BatchNorm on its running statistics
+    xg = x.clone().requires_grad_(True)
+    unit(xg).sum().backward()
+    assert xg.grad is not None and torch.isfinite(xg.grad).all() and float(unit.tcn1.conv.bias.grad.abs().max()) > 0
+    with pytest.raises(RuntimeError):                        # the activations are released by the first backward
+        out = unit(xg)
+        out.sum().backward(retain_graph=True)
+        out.sum().backward()
 
 
 @pytest.mark.parametrize("name", UNIT_FIXTURES)
@@ -259,3 +265,11 @@ def test_graphed_step_matches_eager(pkg):
                 assert rel_err(p.grad, q.grad) <= 2e-5, k
     for (k, a), b in zip(model.state_dict().items(), twin.state_dict().values()):
         assert stat_err(a, b) <= 1e-6, k
+
+
+@pytest.mark.gpu
+def test_eval_mode_gradients(pkg):
+    """Backward under model.eval(): frozen BatchNorm statistics (agcn_bn_bwd frozen_stats), real conv-bias gradients."""
+    from fusion_gcn_b200 import graph as G
+    from fusion_gcn_b200 import modules as M
+    eval_mode_gradient_case(M, G, "cuda", 1e-4)

@@ -5,7 +5,8 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import MODEL_FIXTURES, RESIDUAL_KINDS, UNIT_FIXTURES, check_grads, load_golden, rel_err, stat_err, sub, to_t
+from helpers import (MODEL_FIXTURES, RESIDUAL_KINDS, UNIT_FIXTURES, check_grads, eval_mode_gradient_case, load_golden, rel_err, stat_err, sub,
+                     to_t)
 from fusion_gcn_b200 import graph as G
 from fusion_gcn_b200 import modules as M
 from fusion_gcn_b200 import modules_original as MO
@@ -231,3 +232,7 @@ def test_wide_odd_channel_counts_are_zero_padded_for_the_first_unit(torch_stage_
     assert M._padded_channels(515) == 544 and M._padded_channels(512) == 512 and M._padded_channels(9) == 9
     err = T.seeded_model_case(M, G, (1, 12, 20, 70), "utd", 8, 3, "fp32", "cpu")
     assert err["y"] <= 1e-5
+
+
+def test_eval_mode_gradients_match_the_oracle(torch_stage_backend):
+    eval_mode_gradient_case(M, G, "cpu", 1e-4)

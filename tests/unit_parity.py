@@ -141,13 +141,20 @@ def run_model_parity(model, state, x, w, device, num_channels, start, tol=TOL, t
     from torch import nn
     units = [m for m in model.layers if not isinstance(m, nn.Dropout)]
     seen = []
+    # Model(dropout > 0): the masks torch draws in the nn.Dropout(inplace=True) modules between our units are captured with hooks
+    # and replayed in the oracle (reference layout), so logits and gradients are compared on identical masks
+    drops, drop_in, drop_masks = [m for m in model.layers if isinstance(m, nn.Dropout)], [], []
+    for d in drops:
+        d.register_forward_pre_hook(lambda mod, inp: drop_in.append(inp[0].detach().clone()))
+        d.register_forward_hook(lambda mod, inp, out: drop_masks.append(
+            torch.where(drop_in[-1] != 0, out.detach() / drop_in[-1], torch.zeros_like(out)).permute(0, 3, 1, 2).double()))
 
     def wrap(unit):
         inner = unit.forward_cl
 
         def recording(h, **kw):
             out = inner(h)                                                # (the fused pooled tail is bypassed: the harness needs the feature map)
-            seen.append((unit, h.detach(), out.detach()))
+            seen.append((unit, h.detach(), out.detach().clone()))          # (a following in-place Dropout overwrites `out`)
             if kw.get("pool_groups"):
                 from fusion_gcn_b200 import functional as FN
                 return FN.PoolFn.apply(out, kw["pool_groups"])
@@ -160,6 +167,8 @@ def run_model_parity(model, state, x, w, device, num_channels, start, tol=TOL, t
     y = model(xd)
     (y * wd).sum().backward()
     after = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    assert len(drop_masks) == len(drops)
+    dm = dict(dropout_masks=drop_masks) if drops else {}
     masks = []
     with torch.no_grad():
         for unit, h_in, out in seen:
@@ -171,7 +180,7 @@ def run_model_parity(model, state, x, w, device, num_channels, start, tol=TOL, t
         return O.as_leaves({k: v.to(device) for k, v in state.items()}, torch.float64)
     p_true, pre = leaves(), []
     with torch.no_grad():
-        y64 = O.model_forward(xd.double(), p_true, num_channels, True, start=start, variant=variant, adj_a=a64, collect=pre)
+        y64 = O.model_forward(xd.double(), p_true, num_channels, True, start=start, variant=variant, adj_a=a64, collect=pre, **dm)
     err = {"y": rel_err(y, y64)}
     assert err["y"] <= tol, f"logit error {err['y']:.3e}"
     flips = 0
@@ -185,7 +194,7 @@ def run_model_parity(model, state, x, w, device, num_channels, start, tol=TOL, t
                 assert worst <= tie, f"unit {i} {key}: ReLU bracket differs where the fp64 pre-activation is {worst:.2e} (relative) from zero"
     err["relu_ties"] = flips
     p64 = leaves()
-    y64m = O.model_forward(xd.double(), p64, num_channels, True, start=start, variant=variant, adj_a=a64, masks=masks)
+    y64m = O.model_forward(xd.double(), p64, num_channels, True, start=start, variant=variant, adj_a=a64, masks=masks, **dm)
     (y64m * wd.double()).sum().backward()
     ref = {k: v.grad for k, v in p64.items() if v.requires_grad}
     scale = max(float(v.abs().max()) for v in ref.values())
