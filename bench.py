@@ -338,8 +338,8 @@ def run_ours(args):
             wgrad_family = fl.startswith("agcn_conv_wgrad")
             n_tf32, n_bf16, what = {"fp32": (0, 3, "3 x BF16") if wgrad_family else (1, 2, "1 x TF32 + 2 x BF16"),
                                     "bf16x3": (0, 3, "3 x BF16"), "tf32": (1, 0, "1 x TF32")}[args.precision]
-            if not fl.startswith("agcn_conv_"):
-                n_tf32, n_bf16, what = (1, 0, "1 x TF32") if args.precision == "tf32" else (3, 0, "3 x TF32")     # gram / mix stages
+            if not fl.startswith("agcn_conv_"):         # gram / mix stages: TF32 hi*hi + BF16 cross terms in both parity modes
+                n_tf32, n_bf16, what = (1, 0, "1 x TF32") if args.precision == "tf32" else (1, 2, "1 x TF32 + 2 x BF16")
             ceiling = 1.0 / (n_tf32 / pk["tf32_tflops_sustained"] + n_bf16 / tensor_peak)
             family_roof["frac_tensor_mode"] = round(fam_tf / ceiling, 4)
             family_roof["mode_peak"] = (f"{what} products per MAC: ceiling {ceiling:.1f} algorithmic TFLOP/s from the measured sustained peaks "

@@ -19,7 +19,7 @@ for step in "$@"; do
                for spec in $NCU_CASES; do
                  c=${spec%%:*}; f=""; [ "$spec" != "$c" ] && f="--${spec#*:}"
                  out=gpurun_out/${tag}_ncu_${c}${f#--}
-                 timeout 300 ncu --set full --clock-control none --import-source on -k regex:${NCU_KERNEL:-tc} -c 1 -f -o $out python tools/bench_stage.py $c --once $f > ${out}.log 2>&1
+                 timeout 300 ncu --set full --clock-control none --import-source on -k regex:${NCU_KERNEL:-tc} -c ${NCU_COUNT:-1} -f -o $out python tools/bench_stage.py $c --once $f > ${out}.log 2>&1
                  ncu -i ${out}.ncu-rep --page raw --csv > ${out}_raw.csv 2>/dev/null; rm -f ${out}.ncu-rep
                  tail -2 ${out}.log
                done ;;
@@ -33,6 +33,9 @@ for step in "$@"; do
                for d in $PROBE_DBG; do echo "== AGCN_CONV_DEBUG=$d"; AGCN_B200_LIB=$PWD/fusion_gcn_b200/libagcn_b200_probes.so AGCN_CONV_DEBUG=$d python tools/bench_stage.py $PROBE_CASES ${PROBE_FLAGS}; done > gpurun_out/${tag}_probes.log 2>&1; cat gpurun_out/${tag}_probes.log ;;
     infer)     for n in 256 1024; do for pr in fp32 tf32; do python bench.py --mode infer --batch $n --precision $pr --steps 5 --warmup 3 > gpurun_out/${tag}_bench_infer_n${n}_${pr}.json 2> gpurun_out/${tag}_bench_infer.err; python -c "import json;d=json.load(open('gpurun_out/${tag}_bench_infer_n${n}_${pr}.json'));print('infer',$n,'$pr',d['value'],d['model_roofline']['achieved_frac_of_hbm_ceiling'])"; done; done ;;
     workloads) for w in utd mmact_imu utd_rgb; do python bench.py --workload $w --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_bench_${w}.json 2> gpurun_out/${tag}_bench_${w}.err; python -c "import json;d=json.load(open('gpurun_out/${tag}_bench_${w}.json'));print('$w',d['value'],d['tf32_mode']['value'])"; done ;;
+    launches)  # ncu launch list of one short bench run (a number printed under ncu is never a bench value) + per-kernel summary
+               ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-tf32 --no-graph > gpurun_out/${tag}_launches_bench.log 2>&1
+               python tools/launch_summary.py gpurun_out/${tag}_launches.csv 1 > gpurun_out/${tag}_launch_summary.txt 2>&1; head -14 gpurun_out/${tag}_launch_summary.txt ;;
     *) echo "unknown step $step" ;;
   esac
 done
