@@ -39,6 +39,8 @@ SIGNATURES = {
     "agcn_attention_bwd": (_c_int, [_c_void_p] * 5 + [_c_int] * 4 + [_c_float, _c_void_p]),
     "agcn_joint_mix_workspace_bytes": (_c_size_t, [_c_int]),
     "agcn_joint_mix": (_c_int, [_c_void_p] * 3 + [_c_int] * 9 + [_c_void_p, _c_size_t, _c_void_p]),
+    "agcn_joint_mix_score_bwd_colsum_workspace_bytes": (_c_size_t, [_c_int, _c_int]),
+    "agcn_joint_mix_score_bwd_colsum": (_c_int, [_c_void_p] * 4 + [_c_int] * 5 + [_c_void_p, _c_size_t, _c_void_p]),
     "agcn_bn_workspace_bytes": (_c_size_t, [_c_int]),
     "agcn_bn_stats": (_c_int, [_c_void_p, _c_int, _c_int, _c_ll, _c_int] + [_c_void_p] * 5 + [_c_float, _c_float, _c_int]
                       + [_c_void_p] * 4 + [_c_void_p, _c_size_t, _c_void_p]),

@@ -432,7 +432,7 @@ extern "C" AGCN_API int agcn_joint_gram(const float* a, const float* b, float* o
                  "agcn_joint_gram: unknown precision %d", precision);
     if (precision != AGCN_PREC_FP32_FFMA) {
         const int rc = agcn_joint_gram_tc(a, b, out, nb, t, v, lda, ldb, groups, offa, stridea, offb, strideb, width, nchunk,
-                                          precision == AGCN_PREC_FP32 || precision == AGCN_PREC_BF16X3 /* the V x V stages run 3xTF32 in both parity modes */, stream);
+                                          precision == AGCN_PREC_FP32 || precision == AGCN_PREC_BF16X3 /* the V x V stages run the strict split in both parity modes */, stream);
         if (rc != AGCN_ERR_UNSUPPORTED) return rc;
     }
     GramArgs p{a, b, out, nb, t, v, lda, ldb, groups, offa, stridea, offb, strideb, width, nchunk, 1, 0};
@@ -494,8 +494,10 @@ extern "C" AGCN_API int agcn_attention_bwd(const float* dg_part, const float* p,
 
 // implemented in mix_tc.cu; AGCN_ERR_UNSUPPORTED when the shape / mode is outside the tensor-core path
 size_t agcn_joint_mix_tc_workspace_bytes(int nb);
+size_t agcn_joint_mix_tc_colsum_floats(int ldout);
 int agcn_joint_mix_tc(const float* in, const float* mats, float* out, float* gp,
-                      int nb, int t, int v, int ldin, int ldout, int width, int mode, int accumulate, int split, void* stream);
+                      int nb, int t, int v, int ldin, int ldout, int width, int mode, int accumulate, int split, void* stream,
+                      float* colsum, float* colsum_part);
 
 extern "C" AGCN_API size_t agcn_joint_mix_workspace_bytes(int nb) { return nb > 0 ? agcn_joint_mix_tc_workspace_bytes(nb) : 0; }
 
@@ -516,7 +518,8 @@ extern "C" AGCN_API int agcn_joint_mix(const float* in, const float* mats, float
     if (v > kMaxV) return agcn_joint_mix_big(in, mats, out, nb, t, v, ldin, ldout, width, mode, accumulate, stream);
     if (precision != AGCN_PREC_FP32_FFMA && workspace != nullptr && workspace_bytes >= agcn_joint_mix_tc_workspace_bytes(nb)) {
         const int rc = agcn_joint_mix_tc(in, mats, out, static_cast<float*>(workspace), nb, t, v, ldin, ldout, width, mode, accumulate,
-                                         precision == AGCN_PREC_FP32 || precision == AGCN_PREC_BF16X3 /* the V x V stages run 3xTF32 in both parity modes */, stream);
+                                         precision == AGCN_PREC_FP32 || precision == AGCN_PREC_BF16X3 /* the V x V stages run the strict split in both parity modes */, stream,
+                                         nullptr, nullptr);
         if (rc != AGCN_ERR_UNSUPPORTED) return rc;
     }
     const int nblk = (v + 4) / 5, mld = nblk * 8;
@@ -547,4 +550,29 @@ extern "C" AGCN_API int agcn_joint_mix(const float* in, const float* mats, float
         joint_mix_kernel<1><<<nb * tiles_t, 256, smem, s>>>(p);
     }
     return check_launch("agcn_joint_mix");
+}
+
+extern "C" AGCN_API size_t agcn_joint_mix_score_bwd_colsum_workspace_bytes(int nb, int width) {
+    if (nb <= 0 || width <= 0) return 0;
+    return agcn_joint_mix_tc_workspace_bytes(nb) + agcn_joint_mix_tc_colsum_floats(6 * width) * sizeof(float);
+}
+
+// AGCN_MIX_SCORE_BWD of agcn_joint_mix that also leaves colsum[6 * width] = sum over all (nb, t, v) rows of `out`: the bias gradient of
+// the theta / phi convolutions (agcn.py:104-105) out of the epilogue that writes d theta / d phi, instead of a pass over that tensor.
+// Tensor-core path only: AGCN_ERR_UNSUPPORTED for shapes it does not take (run agcn_joint_mix and sum the columns separately then).
+extern "C" AGCN_API int agcn_joint_mix_score_bwd_colsum(const float* in, const float* mats, float* out, float* colsum,
+                                                        int nb, int t, int v, int width, int precision,
+                                                        void* workspace, size_t workspace_bytes, void* stream) {
+    AGCN_REQUIRE(in && mats && out && colsum && workspace, AGCN_ERR_NULL, "agcn_joint_mix_score_bwd_colsum: null pointer");
+    AGCN_REQUIRE(nb > 0 && t > 0 && v > 0 && width > 0, AGCN_ERR_BAD_SHAPE, "agcn_joint_mix_score_bwd_colsum: bad shape");
+    AGCN_REQUIRE(precision >= AGCN_PREC_FP32 && precision <= AGCN_PREC_BF16X3, AGCN_ERR_UNSUPPORTED,
+                 "agcn_joint_mix_score_bwd_colsum: unknown precision %d", precision);
+    AGCN_REQUIRE(workspace_bytes >= agcn_joint_mix_score_bwd_colsum_workspace_bytes(nb, width), AGCN_ERR_WORKSPACE,
+                 "agcn_joint_mix_score_bwd_colsum: workspace too small");
+    AGCN_REQUIRE(aligned16(workspace), AGCN_ERR_MISALIGNED, "agcn_joint_mix_score_bwd_colsum: workspace not 16-byte aligned");
+    if (v > kMaxV || precision == AGCN_PREC_FP32_FFMA) return AGCN_ERR_UNSUPPORTED;       // (quiet: the caller falls back)
+    float* gp = static_cast<float*>(workspace);
+    float* part = gp + agcn_joint_mix_tc_workspace_bytes(nb) / sizeof(float);
+    return agcn_joint_mix_tc(in, mats, out, gp, nb, t, v, 6 * width, 6 * width, width, AGCN_MIX_SCORE_BWD, 0,
+                             precision == AGCN_PREC_FP32 || precision == AGCN_PREC_BF16X3, stream, colsum, part);
 }

@@ -58,7 +58,20 @@ struct MArgs {
     int tgroups;             // SCORE_BWD: ceil(t / 4) timestep groups per channel block
     uint32_t mat_bytes;      // padded matrices of one sample: 3 boxes (AGG) or 6 boxes (SCORE_BWD)
     uint32_t mat_cross;      // strict mode: bytes of their bf16 [lo ; hi] blocks (8 KB each: two boxes per block)
+    float* colsum_part;      // SCORE_BWD, optional: [gridDim.x * 4][ldout] per-warp column sums of `out` (the bias gradient of the theta / phi
+                             // convolutions, agcn.py:104-105, which would otherwise take its own pass over the 1.5 x Cout-wide tensor)
 };
+
+constexpr int kColsumMax = 384;       // widest SCORE_BWD output with fused column sums: 6 x 64 channels
+
+// out[c] = sum over the per-warp partials, fixed order
+__global__ void colsum_reduce_kernel(const float* part, int nparts, int ld, float* out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ld) return;
+    double s = 0.0;
+    for (int p = 0; p < nparts; ++p) s += (double)part[(long long)p * ld + c];
+    out[c] = (float)s;
+}
 
 // which (timestep, 32-channel block) the j-th quarter of tile `ts` of a sample covers
 __device__ __forceinline__ void tile_pair(const MArgs& p, int ts, int j, int& tt, int& cb) {
@@ -261,6 +274,16 @@ mix_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         // ===================================================== epilogue: warp quarter q = pair q of the tile, lane = channel
         const int q = warp & 3;
         int acc = 0; uint32_t acc_phase = 0;
+        // fused column sums (SCORE_BWD): every lane owns one output channel per tile; its sum over the V joints goes to the warp's
+        // shared-memory accumulator of that channel (behind the TMA staging tiles)
+        float* csum = nullptr;
+        if constexpr (kScore) {
+            if (p.colsum_part != nullptr) {
+                csum = reinterpret_cast<float*>(smem_raw + (bar_base + kBarBytes + 4u * kBoxBytes - smem_u32(smem_raw))) + q * kColsumMax;
+                for (int i = lane; i < kColsumMax; i += 32) csum[i] = 0.f;
+                __syncwarp();
+            }
+        }
         for (long long tile = tile_begin; tile < tile_end; ++tile) {
             const int n = (int)(tile / p.tiles_per_sample);
             const int ts = (int)(tile - (long long)n * p.tiles_per_sample);
@@ -301,6 +324,15 @@ mix_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                             tmem_ld_wait();
 #pragma unroll
                             for (int i = 0; i < 16; ++i) { if (is_phi) { r0[i] = a0[i]; r1[i] = a1[i]; } }
+                            if (csum != nullptr && ok) {
+                                float sv = 0.f;
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) {
+                                    if (i < p.v) sv += __uint_as_float(r0[i]);
+                                    if (16 + i < p.v) sv += __uint_as_float(r1[i]);
+                                }
+                                csum[chan0 + (int)col] += sv;          // (a lane's output channel is distinct within the warp)
+                            }
                         } else {
                             tmem_ld16_nowait(taddr + (uint32_t)(k * 32), r0);
                             tmem_ld16_nowait(taddr + (uint32_t)(k * 32 + 16), r1);
@@ -414,6 +446,13 @@ mix_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
         if (p.tma_out && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if constexpr (kScore) {
+            if (csum != nullptr) {
+                __syncwarp();
+                float* dst = p.colsum_part + ((long long)blockIdx.x * 4 + q) * p.ldout;
+                for (int i = lane; i < p.ldout; i += 32) dst[i] = csum[i];
+            }
+        }
     } else if (SPLIT && warp >= 7) {
         // ===================================================== operand split: activations per tile, matrices per sample
         const int tids = threadIdx.x - 7 * 32;
@@ -471,11 +510,14 @@ mix_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
 using namespace agcn;
 
 size_t agcn_joint_mix_tc_workspace_bytes(int nb) { return (size_t)nb * 6 * 1024 * sizeof(float); }   // SCORE_BWD pads 6 boxes per sample
+size_t agcn_joint_mix_tc_colsum_floats(int ldout) { return (size_t)agcn::kNumSMs * 4 * ldout; }          // per-warp column-sum partials
 
 // Returns AGCN_ERR_UNSUPPORTED for shapes / modes outside this path (the caller then runs the FFMA kernel).
 // gp: nb*3*1024 floats of scratch for the padded matrices.
+// colsum (SCORE_BWD only, may be NULL): receives sum over all rows of out[., c]; colsum_part: agcn_joint_mix_tc_colsum_floats(ldout) floats
 int agcn_joint_mix_tc(const float* in, const float* mats, float* out, float* gp,
-                      int nb, int t, int v, int ldin, int ldout, int width, int mode, int accumulate, int split, void* stream) {
+                      int nb, int t, int v, int ldin, int ldout, int width, int mode, int accumulate, int split, void* stream,
+                      float* colsum, float* colsum_part) {
     using namespace agcn::tc;
     using namespace agcn::mtc;
     static const bool disabled = probe_env("AGCN_MIX_SIMT") != nullptr;
@@ -503,7 +545,12 @@ int agcn_joint_mix_tc(const float* in, const float* mats, float* out, float* gp,
     p.mat_cross = (score ? 3u : 2u) * kCrossBlk;
     static const bool no_tma_out = probe_env("AGCN_MIX_NO_TMA_STORE") != nullptr;
     p.tma_out = (!no_tma_out && ldout % 4 == 0 && (!score || width == 16 || width % 32 == 0)) ? 1 : 0;
-    const uint32_t out_stage = p.tma_out ? 4u * ((score || p.bwd) ? 1u : 3u) * kBoxBytes : 0u;
+    p.colsum_part = nullptr;
+    if (colsum != nullptr) {          // fused column sums ride in the TMA-store epilogue of the score backward
+        if (!score || !p.tma_out || ldout > kColsumMax || colsum_part == nullptr) return AGCN_ERR_UNSUPPORTED;
+        p.colsum_part = colsum_part;
+    }
+    const uint32_t out_stage = (p.tma_out ? 4u * ((score || p.bwd) ? 1u : 3u) * kBoxBytes : 0u) + (p.colsum_part ? 4u * kColsumMax * 4u : 0u);
     const uint32_t fixed = 2u * p.mat_bytes + (split ? 2u * p.mat_cross : 0u) + kBarBytes + out_stage + 1024u;
     const uint32_t budget = 220u * 1024u - fixed;
     p.nlo = split ? 2 : 0;
@@ -565,5 +612,9 @@ int agcn_joint_mix_tc(const float* in, const float* mats, float* out, float* gp,
     if (split) e = score ? launch(mix_tc_kernel<true, 2>, kThreadsMSplit) : p.bwd ? launch(mix_tc_kernel<true, 1>, kThreadsMSplit) : launch(mix_tc_kernel<true, 0>, kThreadsMSplit);
     else e = score ? launch(mix_tc_kernel<false, 2>, kThreadsM) : p.bwd ? launch(mix_tc_kernel<false, 1>, kThreadsM) : launch(mix_tc_kernel<false, 0>, kThreadsM);
     if (e != cudaSuccess) return fail(AGCN_ERR_CUDA, "agcn_joint_mix_tc: %s", cudaGetErrorString(e));
-    return check_launch("agcn_joint_mix_tc");
+    int rc2 = check_launch("agcn_joint_mix_tc");
+    if (rc2 || colsum == nullptr) return rc2;
+    const int nparts = (int)(p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs) * 4;
+    colsum_reduce_kernel<<<ceil_div(ldout, 128), 128, 0, st>>>(colsum_part, nparts, ldout, colsum);
+    return check_launch("agcn_joint_mix_tc(column sums)");
 }

@@ -177,8 +177,11 @@ def gcn_backward(d_o, ctx, bn_w, dbn_w, down_w, spec: UnitSpec, dx=None, need_dx
     if need_dx:
         dx = K.joint_mix(dz, g, width=cin, mode=K.MIX_AGG_BWD, out=dx, accumulate=have, precision=prec)
         have = True
-    de = K.joint_mix(e, ds, width=ci, mode=K.MIX_SCORE_BWD, precision=prec)
-    d_wab, d_bab = K.conv_wgrad(de, x, precision=prec)
+    # d theta / d phi, and their column sums (= the bias gradients) out of the same epilogue where the kernel covers the shape
+    de, d_bab = K.joint_mix_score_bwd(e, ds, width=ci, precision=prec)
+    d_wab, d_bab2 = K.conv_wgrad(de, x, want_bias=d_bab is None, precision=prec)
+    if d_bab is None:
+        d_bab = d_bab2
     if need_dx:
         dx = K.conv_fwd(de, _t(ctx["wab"]), out=dx, accumulate=have, precision=prec)
     # unpack

@@ -293,6 +293,25 @@ def joint_mix(inp, mats, *, width, mode, out=None, accumulate=False, precision=P
     return out
 
 
+def joint_mix_score_bwd(e, ds, *, width, precision=PREC_FP32):
+    """de = joint_mix(e, ds, mode=MIX_SCORE_BWD) together with the column sums of de over all (nb, t, v) rows -- the bias gradient of
+    the theta / phi convolutions -- out of the same epilogue (agcn_joint_mix_score_bwd_colsum).  -> (de, colsum [6 * width]), or
+    (de, None) for shapes the fused epilogue does not cover (sum the columns separately then)."""
+    nb, t, v, ld = e.shape
+    fused = (precision != PREC_FP32_FFMA and v <= 32 and ld == 6 * width and 6 * width <= 384 and (width == 16 or width % 32 == 0))
+    if not fused:
+        return joint_mix(e, ds, width=width, mode=MIX_SCORE_BWD, precision=precision), None
+    out = torch.empty_like(e)
+    colsum = torch.empty((ld,), device=e.device, dtype=torch.float32)
+    _check(e, ds, out)
+    ws_bytes = capi.lib().agcn_joint_mix_score_bwd_colsum_workspace_bytes(nb, width)
+    ws = torch.empty((ws_bytes + 3) // 4, device=e.device, dtype=torch.float32)
+    _call("agcn_joint_mix_score_bwd_colsum", _ptr(e), _ptr(ds), _ptr(out), _ptr(colsum), nb, t, v, width, precision, _ptr(ws), ws_bytes, _stream(),
+          sig=(nb, t, v, ld, ld, width, MIX_SCORE_BWD, 0), work=(2.0 * nb * t * 6 * v * v * width, 4.0 * (e.numel() + out.numel())),
+          alias="agcn_joint_mix")
+    return out, colsum
+
+
 # ----------------------------------------------------------------------------- batch norm
 def _rowmap(x, rowmap):
     """rowmap = (outer, inner, outer_stride, channels) or None for a plain [rows, channels] view."""

@@ -154,6 +154,15 @@ int agcn_joint_mix(const float* in, const float* mats, float* out,
                    int nb, int t, int v, int ldin, int ldout, int width, int mode, int accumulate,
                    int precision, void* workspace, size_t workspace_bytes, void* stream);
 
+/* AGCN_MIX_SCORE_BWD (in = e [nb][t][v][6*width], mats = dS, out = de) whose epilogue also leaves colsum[6*width] = sum over all
+ * (nb, t, v) rows of out -- the bias gradient of the theta / phi convolutions (agcn.py:104-105) -- instead of a separate pass over
+ * the 1.5 x Cout-wide tensor.  Tensor-core path only: returns AGCN_ERR_UNSUPPORTED (no error string) for shapes / modes it does
+ * not take (V > 32, width not 16 / a multiple of 32, 6*width > 384, AGCN_PREC_FP32_FFMA); use agcn_joint_mix then.            */
+size_t agcn_joint_mix_score_bwd_colsum_workspace_bytes(int nb, int width);
+int agcn_joint_mix_score_bwd_colsum(const float* in, const float* mats, float* out, float* colsum,
+                                    int nb, int t, int v, int width, int precision,
+                                    void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- BatchNorm (training-mode batch statistics; nn.BatchNorm2d/1d at agcn.py:44,78,83,150) ----------
  * The tensor is addressed as x[outer][inner][c] with element offset outer*outer_stride + inner*c_total...
  * precisely: offset(o, i, ch) = o*outer_stride + i*channels + ch, rows = outer*inner.  For unit tensors

@@ -175,6 +175,12 @@ def joint_mix(inp, mats, *, width, mode, out=None, accumulate=False, precision=0
     return out
 
 
+def joint_mix_score_bwd(e, ds, *, width, precision=0):
+    """(de, column sums of de over all rows): the score-backward mix and the theta / phi bias gradient it also produces."""
+    de = joint_mix(e, ds, width=width, mode=MIX_SCORE_BWD)
+    return de, de.reshape(-1, de.shape[-1]).sum(0)
+
+
 def _rows_view(x, rowmap):
     """[..., channels] view honouring rowmap = (outer, inner, outer_stride, channels)."""
     if rowmap is None:
@@ -337,6 +343,10 @@ class Tf32Emulation:
         if precision == PREC_TF32 and width % (16 if mode == MIX_SCORE_BWD else 32) == 0:
             inp, mats = _trunc_tf32(inp), _trunc_tf32(mats)
         return joint_mix(inp, mats, width=width, mode=mode, **kw)
+
+    def joint_mix_score_bwd(self, e, ds, *, width, precision=PREC_FP32):
+        de = self.joint_mix(e, ds, width=width, mode=MIX_SCORE_BWD, precision=precision)
+        return de, de.reshape(-1, de.shape[-1]).sum(0)
 
     def conv_wgrad(self, dy, x, *, precision=PREC_FP32, **kw):
         _, db = conv_wgrad(dy, x, **kw)
