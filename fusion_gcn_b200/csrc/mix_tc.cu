@@ -64,13 +64,17 @@ struct MArgs {
 
 constexpr int kColsumMax = 384;       // widest SCORE_BWD output with fused column sums: 6 x 64 channels
 
-// out[c] = sum over the per-warp partials, fixed order
+// out[c] = sum over the per-warp partials: one warp per column, lane l adds partials l, l + 32, ... and a fixed shuffle tree
+// combines the lanes (deterministic)
 __global__ void colsum_reduce_kernel(const float* part, int nparts, int ld, float* out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (c >= ld) return;
     double s = 0.0;
-    for (int p = 0; p < nparts; ++p) s += (double)part[(long long)p * ld + c];
-    out[c] = (float)s;
+#pragma unroll 4
+    for (int p = lane; p < nparts; p += 32) s += (double)part[(long long)p * ld + c];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if (lane == 0) out[c] = (float)s;
 }
 
 // which (timestep, 32-channel block) the j-th quarter of tile `ts` of a sample covers
@@ -325,13 +329,13 @@ mix_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
 #pragma unroll
                             for (int i = 0; i < 16; ++i) { if (is_phi) { r0[i] = a0[i]; r1[i] = a1[i]; } }
                             if (csum != nullptr && ok) {
-                                float sv = 0.f;
+                                float sv[4] = {0.f, 0.f, 0.f, 0.f};         // four chains: the adds sit on the epilogue's critical path
 #pragma unroll
                                 for (int i = 0; i < 16; ++i) {
-                                    if (i < p.v) sv += __uint_as_float(r0[i]);
-                                    if (16 + i < p.v) sv += __uint_as_float(r1[i]);
+                                    if (i < p.v) sv[i & 1] += __uint_as_float(r0[i]);
+                                    if (16 + i < p.v) sv[2 + (i & 1)] += __uint_as_float(r1[i]);
                                 }
-                                csum[chan0 + (int)col] += sv;          // (a lane's output channel is distinct within the warp)
+                                csum[chan0 + (int)col] += (sv[0] + sv[1]) + (sv[2] + sv[3]);      // (a lane's output channel is distinct within the warp)
                             }
                         } else {
                             tmem_ld16_nowait(taddr + (uint32_t)(k * 32), r0);
@@ -615,6 +619,6 @@ int agcn_joint_mix_tc(const float* in, const float* mats, float* out, float* gp,
     int rc2 = check_launch("agcn_joint_mix_tc");
     if (rc2 || colsum == nullptr) return rc2;
     const int nparts = (int)(p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs) * 4;
-    colsum_reduce_kernel<<<ceil_div(ldout, 128), 128, 0, st>>>(colsum_part, nparts, ldout, colsum);
+    colsum_reduce_kernel<<<ceil_div(ldout, 8), 256, 0, st>>>(colsum_part, nparts, ldout, colsum);
     return check_launch("agcn_joint_mix_tc(column sums)");
 }
