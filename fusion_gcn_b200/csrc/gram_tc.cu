@@ -30,6 +30,8 @@ constexpr int kSegStages = 4;            // strict mode: stages (timestep x K-ch
 struct GArgs {
     float* out;
     int nb, t, v, groups, ga, width, nchunk;
+    int swap;               // 1 (ga == 1, the dG gram): the wide operand b (rows (v, g)) is the M operand and a (V rows) the N = 32 operand --
+                            // D[(v, g)][u]; with a on M the MMA is N = 80 wide for 25 useful rows of M, 2.5x the tensor time
     int shared_tile;        // 1: theta and phi of a group share one 128-byte row (width 16): B = A tile + 64 bytes
     int kw;                 // floats per K chunk row (16 or 32)
     int nkc;                // K chunks (boxes) per operand
@@ -112,8 +114,9 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         {
             const bool leader = elect_one_sync() != 0;
             const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(80 >> 3) << 17) | ((128u >> 4) << 24);
-            const uint32_t idesc_bf = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(80 >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t ncol = p.swap ? 32u : 80u;
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((ncol >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc_bf = (1u << 4) | (1u << 7) | (1u << 10) | ((ncol >> 3) << 17) | ((128u >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             int sl = 0;
@@ -132,7 +135,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     // hi*hi on kind::tf32 straight from the TMA payload (the MMA truncates the fp32 words itself) ...
                     for (int k = 0; k < nk; ++k) {
                         const uint32_t ao = (uint32_t)k * p.a_tile, bo = b_off + (uint32_t)k * (p.shared_tile ? p.a_tile : p.b_tile);
-                        const uint64_t da = make_smem_desc(sa + ao), db = make_smem_desc(sa + bo);
+                        const uint64_t da = make_smem_desc(sa + (p.swap ? bo : ao)), db = make_smem_desc(sa + (p.swap ? ao : bo));
                         for (int ks = 0; ks < ksteps; ++ks) {
                             const uint32_t fresh = (k == 0 && ks == 0) ? first : 0u;
                             umma_tf32(d_tmem, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc, fresh ^ 1u);
@@ -145,7 +148,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         for (int k = 0; k < nk; ++k) {
                             const uint32_t ao = (uint32_t)k * p.a_tile, bo = b_off + (uint32_t)k * (p.shared_tile ? p.a_tile : p.b_tile);
-                            const uint64_t dalo = make_smem_desc(slo + ao), dblo = make_smem_desc(slo + bo);
+                            const uint64_t dalo = make_smem_desc(slo + (p.swap ? bo : ao)), dblo = make_smem_desc(slo + (p.swap ? ao : bo));
                             if (p.shared_tile) {
                                 // one row = [theta hi16 | phi hi16 | theta lo16 | phi lo16], 32 bytes (2 descriptor units) each
                                 umma_bf16(d_tmem, dalo + 4u, dalo + 2u, idesc_bf, 1u);
@@ -182,9 +185,11 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     } else if (warp < 6) {
         // epilogue: lane quarter q holds accumulator rows r = q*32 + lane = u*GA + ga; columns j = v*groups + g
+        // (swap: rows r = v*groups + g, columns j = u)
         const int q = warp & 3;
         const int r = q * 32 + lane;
         const int u = r / p.ga, ga = r - u * p.ga;
+        const int sv = r / p.groups, sg_ = r - sv * p.groups;          // swap: this row's (v, g)
         const int nseg = SPLIT ? (nstage + kSegStages - 1) / kSegStages : 1;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const uint32_t master = tmem_base + 256u + lane_base;
@@ -198,10 +203,17 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
             for (int cg = 0; cg < 5; ++cg) {
                 const int c = cg * 16;
+                if (p.swap && cg >= 2) break;
                 float vals[16];
                 if (SPLIT) tmem_promote16(taddr + (uint32_t)c, master + (uint32_t)c, sg == 0, !last, vals);
                 else tmem_ld16(taddr + (uint32_t)c, vals);
-                if (last && u < p.v) {
+                if (last && p.swap) {
+                    if (sv < p.v) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (c + i < p.v) o[((long long)sg_ * p.v + (c + i)) * p.v + sv] = nstage > 0 ? vals[i] : 0.f;
+                    }
+                } else if (last && u < p.v) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const int j = c + i;
@@ -283,6 +295,7 @@ int agcn_joint_gram_tc(const float* a, const float* b, float* out,
     if (!enc) return fail(AGCN_ERR_CUDA, "agcn_joint_gram_tc: cuTensorMapEncodeTiled is not available from the driver");
     p.out = out; p.nb = nb; p.t = t; p.v = v; p.groups = groups; p.ga = ga; p.width = width; p.nchunk = nchunk;
     p.offa = offa; p.offb = offb;
+    p.swap = (ga == 1 && v <= 32) ? 1 : 0;
     p.kw = width == 16 ? 16 : 32;
     p.nkc = width == 16 ? 1 : width / 32;
     p.kpg = p.nkc < 2 ? p.nkc : 2;
