@@ -235,11 +235,24 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* part, int
     if (save_invstd) save_invstd[c] = (float)invstd;
 }
 
+// bf16 pieces of four fp32 values, as the parity modes' converters form them (tc_common.cuh bf16_split8): h = bf16(x), m = bf16(x - h),
+// round to nearest (ties away), packed in channel order -- the operand format of agcn_conv_wgrad_presplit
+__device__ __forceinline__ void bf16_pieces4(const float v[4], uint2& h, uint2& m) {
+    unsigned hb[4], mb[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        hb[i] = (__float_as_uint(v[i]) + 0x8000u) & 0xFFFF0000u;
+        mb[i] = __float_as_uint(v[i] - __uint_as_float(hb[i])) + 0x8000u;
+    }
+    h = make_uint2(__byte_perm(hb[0], hb[1], 0x7632), __byte_perm(hb[2], hb[3], 0x7632));
+    m = make_uint2(__byte_perm(mb[0], mb[1], 0x7632), __byte_perm(mb[2], mb[3], 0x7632));
+}
+
 // out = act(scale*y + shift + R)
 template <bool VEC>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const float* y, const float* scale, const float* shift, int res_mode,
                                                        const float* res, const float* scale2, const float* shift2, int relu,
-                                                       float* out, unsigned* mask_bits, RowMap m, long long rows) {
+                                                       float* out, unsigned* mask_bits, RowMap m, long long rows, unsigned short* split = nullptr) {
     constexpr int W = VEC ? 4 : 1;
     const int cq = m.channels / W;
     const long long total = rows * cq;
@@ -266,6 +279,13 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* y, const flo
             }
             if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
             *reinterpret_cast<float4*>(out + off) = o;
+            if (split != nullptr) {          // the same values as bf16 pieces [2][rows][channels] (contiguous rows only)
+                const float ov[4] = {o.x, o.y, o.z, o.w};
+                uint2 h, mm;
+                bf16_pieces4(ov, h, mm);
+                *reinterpret_cast<uint2*>(split + off) = h;
+                *reinterpret_cast<uint2*>(split + rows * m.channels + off) = mm;
+            }
             nib = (o.x > 0.f ? 1u : 0u) | (o.y > 0.f ? 2u : 0u) | (o.z > 0.f ? 4u : 0u) | (o.w > 0.f ? 8u : 0u);
         } else {
             float o = fmaf(__ldg(y + off), scale[c], shift[c]);
@@ -372,7 +392,7 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* part,
 template <bool VEC>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* dout, const float* mask, const unsigned* mask_bits, const float* y,
                                                            const float* coef, float* dy, float* dres, int dres_acc, RowMap m, long long rows,
-                                                           int bcast_rows = 0, float bcast_scale = 1.f) {
+                                                           int bcast_rows = 0, float bcast_scale = 1.f, unsigned short* dy_split = nullptr) {
     constexpr int W = VEC ? 4 : 1;
     const int C = m.channels;
     const int cq = C / W;
@@ -410,6 +430,12 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* dout, co
         }
         if constexpr (VEC) {
             if (dy) *reinterpret_cast<float4*>(dy + off) = make_float4(o[0], o[1], o[2], o[3]);
+            if (dy && dy_split != nullptr) {      // dy once more as bf16 pieces for agcn_conv_wgrad_presplit (contiguous rows only)
+                uint2 h, mm;
+                bf16_pieces4(o, h, mm);
+                *reinterpret_cast<uint2*>(dy_split + off) = h;
+                *reinterpret_cast<uint2*>(dy_split + rows * C + off) = mm;
+            }
             if (dres) {
                 float4 q = make_float4(g[0], g[1], g[2], g[3]);
                 if (dres_acc) {
@@ -559,7 +585,8 @@ extern "C" AGCN_API size_t agcn_bn_mask_words(int outer, int inner, int channels
 
 static int bn_apply_impl(const float* y, const float* scale, const float* shift,
                          int res_mode, const float* res, const float* scale2, const float* shift2,
-                         int relu, float* out, unsigned* mask_bits, int outer, int inner, long long outer_stride, int channels, void* stream) {
+                         int relu, float* out, unsigned* mask_bits, int outer, int inner, long long outer_stride, int channels, void* stream,
+                         unsigned short* split = nullptr) {
     int rc = check_map("agcn_bn_apply", outer, inner, outer_stride, channels);
     if (rc) return rc;
     AGCN_REQUIRE(y && scale && shift && out, AGCN_ERR_NULL, "agcn_bn_apply: null pointer");
@@ -573,8 +600,10 @@ static int bn_apply_impl(const float* y, const float* scale, const float* shift,
     if (mask_bits != nullptr)
         AGCN_REQUIRE(vec && agcn_bn_mask_words(outer, inner, channels) > 0, AGCN_ERR_UNSUPPORTED,
                      "agcn_bn_apply_mask: layout not supported (agcn_bn_mask_words returned 0)");
+    if (split != nullptr)
+        AGCN_REQUIRE(vec && outer == 1 && aligned16(split), AGCN_ERR_UNSUPPORTED, "agcn_bn_apply_mask_split: contiguous, vectorisable layout required");
     if (vec)
-        bn_apply_kernel<true><<<elementwise_blocks(rows * (channels / 4)), 256, 0, s>>>(y, scale, shift, res_mode, res, scale2, shift2, relu, out, mask_bits, m, rows);
+        bn_apply_kernel<true><<<elementwise_blocks(rows * (channels / 4)), 256, 0, s>>>(y, scale, shift, res_mode, res, scale2, shift2, relu, out, mask_bits, m, rows, split);
     else
         bn_apply_kernel<false><<<elementwise_blocks(rows * channels), 256, 0, s>>>(y, scale, shift, res_mode, res, scale2, shift2, relu, out, nullptr, m, rows);
     return check_launch("agcn_bn_apply");
@@ -593,11 +622,22 @@ extern "C" AGCN_API int agcn_bn_apply_mask(const float* y, const float* scale, c
     return bn_apply_impl(y, scale, shift, res_mode, res, scale2, shift2, relu, out, mask_bits, 1, inner, 0, channels, stream);
 }
 
+// agcn_bn_apply_mask that also writes `out` as bf16 pieces: out_split [2][inner][channels] (plane 0 = h = bf16(out), plane 1 =
+// m = bf16(out - h)), the operand format of agcn_conv_wgrad_presplit -- the weight gradient of the convolution that consumes `out`
+// then needs no conversion pass of its own.
+extern "C" AGCN_API int agcn_bn_apply_mask_split(const float* y, const float* scale, const float* shift,
+                                                 int res_mode, const float* res, const float* scale2, const float* shift2,
+                                                 int relu, float* out, unsigned* mask_bits, void* out_split, int inner, int channels, void* stream) {
+    AGCN_REQUIRE(mask_bits && out_split, AGCN_ERR_NULL, "agcn_bn_apply_mask_split: null pointer");
+    return bn_apply_impl(y, scale, shift, res_mode, res, scale2, shift2, relu, out, mask_bits, 1, inner, 0, channels, stream,
+                         static_cast<unsigned short*>(out_split));
+}
+
 static int bn_bwd_impl(const float* dout, const float* mask_out, const unsigned* mask_bits, const float* y,
                        const float* save_mean, const float* save_invstd, const float* gamma,
                        float* dy, float* dgamma, float* dbeta, float* dres, int dres_accumulate,
                        int outer, int inner, long long outer_stride, int channels,
-                       void* workspace, size_t workspace_bytes, void* stream, int bcast_rows = 0, int frozen = 0) {
+                       void* workspace, size_t workspace_bytes, void* stream, int bcast_rows = 0, int frozen = 0, unsigned short* dy_split = nullptr) {
     int rc = check_map("agcn_bn_bwd", outer, inner, outer_stride, channels);
     if (rc) return rc;
     AGCN_REQUIRE(dout && y && save_mean && save_invstd && workspace, AGCN_ERR_NULL, "agcn_bn_bwd: null pointer");
@@ -618,9 +658,12 @@ static int bn_bwd_impl(const float* dout, const float* mask_out, const unsigned*
     rc = check_launch("agcn_bn_bwd(finalize)");
     if (rc) return rc;
     if (dy == nullptr && dres == nullptr) return AGCN_OK;
+    if (dy_split != nullptr)
+        AGCN_REQUIRE(dy != nullptr && outer == 1 && aligned16(dy_split) && vec_ok(m, {dout, mask_out, y, dy, dres, coef}), AGCN_ERR_UNSUPPORTED,
+                     "agcn_bn_bwd_bits_split: contiguous, vectorisable layout and a dy output required");
     if (vec_ok(m, {dout, mask_out, y, dy, dres, coef}))
         bn_bwd_apply_kernel<true><<<elementwise_blocks(rows * (channels / 4)), 256, 0, s>>>(dout, mask_out, mask_bits, y, coef, dy, dres, dres_accumulate, m, rows,
-                                                                                            bcast_rows, bcast_scale);
+                                                                                            bcast_rows, bcast_scale, dy_split);
     else
         bn_bwd_apply_kernel<false><<<elementwise_blocks(rows * channels), 256, 0, s>>>(dout, mask_out, nullptr, y, coef, dy, dres, dres_accumulate, m, rows);
     return check_launch("agcn_bn_bwd(apply)");
@@ -642,6 +685,16 @@ extern "C" AGCN_API int agcn_bn_bwd_bits(const float* dout, const unsigned* mask
     AGCN_REQUIRE(mask_bits, AGCN_ERR_NULL, "agcn_bn_bwd_bits: null mask pointer");
     return bn_bwd_impl(dout, nullptr, mask_bits, y, save_mean, save_invstd, gamma, dy, dgamma, dbeta, dres, dres_accumulate,
                        1, inner, 0, channels, workspace, workspace_bytes, stream, 0, frozen_stats);
+}
+
+// agcn_bn_bwd_bits that also writes dy as bf16 pieces: dy_split [2][inner][channels] (see agcn_bn_apply_mask_split)
+extern "C" AGCN_API int agcn_bn_bwd_bits_split(const float* dout, const unsigned* mask_bits, const float* y,
+                                               const float* save_mean, const float* save_invstd, const float* gamma,
+                                               float* dy, void* dy_split, float* dgamma, float* dbeta, float* dres, int dres_accumulate, int frozen_stats,
+                                               int inner, int channels, void* workspace, size_t workspace_bytes, void* stream) {
+    AGCN_REQUIRE(mask_bits && dy && dy_split, AGCN_ERR_NULL, "agcn_bn_bwd_bits_split: null pointer");
+    return bn_bwd_impl(dout, nullptr, mask_bits, y, save_mean, save_invstd, gamma, dy, dgamma, dbeta, dres, dres_accumulate,
+                       1, inner, 0, channels, workspace, workspace_bytes, stream, 0, frozen_stats, static_cast<unsigned short*>(dy_split));
 }
 
 constexpr int kPoolParts = 8;

@@ -32,6 +32,7 @@ struct WgArgs {
     int seg_chunks;    // 3xTF32: row chunks per accumulator segment (promoted to fp32 registers in between)
     int blocked;       // 1: tensor maps carry the 32-channel block as its own dimension: ONE TMA box per operand and stage
     int nblk_a;        // blocked: dy channel blocks per box (<= 4; pair mode: 2, loaded twice)
+    int pre_ablk, pre_bblk;   // MODE 3: 64-channel blocks per dy / x box (the transaction bytes count whole boxes, out-of-range blocks included)
     int dbg;           // bring-up only (env AGCN_WG_DEBUG): bit 0 skips the operand split, bit 1 skips the MMAs -> wrong results, timing probes
 };
 
@@ -40,10 +41,16 @@ struct WgArgs {
 // converter warps (one thread per K row) rewrite every PAIR of slots in place as 64 bf16 channels of h (first slot) and of m
 // (second slot) -- MN-major 16-bit operands, 64 channels per 128-byte row, 8-row swizzle groups -- and the issuer runs
 // h.h + h.m + m.h on kind::f16 with K = 16 rows per MMA.  No lo ring: four 48 KB stages like the TF32 mode.
+// MODE 3: BF16x3 on operands that ARRIVE split -- [2][rows][C] bf16 tensors (plane 0 = h, plane 1 = m) written by the kernels that
+// produced the activations / gradients (agcn_bn_apply_mask_split, agcn_bn_bwd_bits_split).  One 5-D TMA box per operand lands as
+// [64-channel block][piece][row][128 B], which IS the slot layout the issuer reads (h in the even slots, m in the odd ones): no
+// converter warps, no in-place rewrite -- the kernel is the TF32-mode pipeline with three bf16 MMAs per 16 rows.  In the in-kernel
+// conversion (MODE 2) the shared memory moves ~216 KB per 48 KB stage (TMA landing, conversion read + write, operand reads of three
+// MMAs), which bounds it at ~200 TFLOP/s; here it moves 120 KB.
 template <int MODE>
-__global__ void __launch_bounds__(MODE != 0 ? kWgThreadsSplit : kThreads, 1)
+__global__ void __launch_bounds__((MODE == 1 || MODE == 2) ? kWgThreadsSplit : kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, WgArgs a) {
-    constexpr bool SPLIT = MODE == 1, BF = MODE == 2, CONV = MODE != 0;
+    constexpr bool SPLIT = MODE == 1, PRE = MODE == 3, BF = MODE == 2 || MODE == 3, CONV = MODE != 0;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sub_bytes = (uint32_t)a.rpad * 128u;
@@ -116,7 +123,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
         b_boxes = (a.cin - k0 + 31) / 32 < (int)nsub_b ? (a.cin - k0 + 31) / 32 : (int)nsub_b;
     }
     loaded |= ((1u << b_boxes) - 1u) << 4;
-    const uint32_t stage_tx = (uint32_t)__popc(loaded) * (uint32_t)a.rows_box * 128u;
+    uint32_t stage_tx = (uint32_t)__popc(loaded) * (uint32_t)a.rows_box * 128u;
+    if (PRE) stage_tx = (uint32_t)(a.pre_ablk * ((a.pair && tap_b) ? 2 : 1) + a.pre_bblk) * 2u * (uint32_t)a.rows_box * 128u;
 
     if (warp == 0) {
         {   // warp-uniform loop, elected lane issues the TMA loads (uniform-register operands)
@@ -132,7 +140,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
                 const uint32_t sa = smem_base + (uint32_t)stage * raw_bytes;
                 if (leader) {
                     mbar_expect_tx(full_bar(stage), stage_tx);
-                    if (a.blocked) {
+                    if (PRE) {
+                        // dims (64 channels, flat row, piece, 64-channel block, sample); the box covers both pieces and all blocks of the tile
+                        tma_load_5d(sa, &map_dy, full_bar(stage), 0, a1, 0, a.pair ? 0 : m0 / 64, n);
+                        if (a.pair && tap_b) tma_load_5d(sa + 2u * sub_bytes, &map_dy, full_bar(stage), 0, a1 - a.v, 0, 0, n);
+                        tma_load_5d(sa + 4u * sub_bytes, &map_x, full_bar(stage), 0, b1, 0, k0 / 64, n);
+                    } else if (a.blocked) {
                         // dims (32 channels, flat row, channel block, sample): the box lands as [block][row][128 B], exactly the slot layout
                         tma_load_4d(sa, &map_dy, full_bar(stage), 0, a1, a.pair ? 0 : m0 / 32, n);
                         if (a.pair && tap_b) tma_load_4d(sa + 2u * sub_bytes, &map_dy, full_bar(stage), 0, a1 - a.v, 0, n);
@@ -176,7 +189,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
             const int ksteps = (a.dbg & 2) ? 1 : (BF ? (a.rows_box + 15) / 16 : (a.rows_box + 7) / 8);
             for (long long c = c_begin; c < c_end; ++c) {
                 mbar_wait(full_bar(stage), phase);
-                if (CONV) mbar_wait(lo_bar(stage), phase);
+                if (CONV && !PRE) mbar_wait(lo_bar(stage), phase);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t sa = smem_base + (uint32_t)stage * raw_bytes;
                 const uint32_t slo = lo_ring + (uint32_t)sl * raw_bytes;
@@ -267,7 +280,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
             if (lane == 0) mbar_arrive(tempty_bar(acc));
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
-    } else if (BF) {
+    } else if (BF && !PRE) {
         // BF16x3 converter (kWgTransformWarps warps): slot pair (2j, 2j+1) of 32-channel fp32 blocks -> 64 bf16 channels of h | m in
         // place, one thread per (pair, K row).  Only rows TMA wrote are touched (the pad rows stay zero); a pair whose first slot is
         // never loaded stays zero, a pair with only its first slot loaded gets zero upper channels.
@@ -476,4 +489,40 @@ int agcn_conv_wgrad_tc(const float* dy, const float* x, float* ws, int* splits_o
     else wgrad_tc_kernel<0><<<grid, kThreads, p.smem, st>>>(map_dy, map_x, a);
     *splits_out = p.splits;
     return check_launch("agcn_conv_wgrad_tc");
+}
+
+// ---- the same on operands that arrive split: dy_split / x_split = [2][nb * t * v][C] bf16 (plane 0 = h = bf16(x), plane 1 = m = bf16(x - h)).
+// Flat layout only (stride 1, t_in == t_out), channel counts multiples of 64.  AGCN_ERR_UNSUPPORTED otherwise.
+int agcn_conv_wgrad_tc_presplit(const uint16_t* dy_split, const uint16_t* x_split, float* ws, int* splits_out,
+                                int nb, int t, int v, int cin, int cout, int taps, int pad, void* stream) {
+    using namespace agcn::tc;
+    if (cin % 64 || cout % 64 || !aligned16(dy_split) || !aligned16(x_split) || !aligned16(ws)) return AGCN_ERR_UNSUPPORTED;
+    WgPlan p = plan_wgrad(nb, t, t, v, cin, cout, taps, 1, pad, 2);
+    if (!p.ok || !p.a.flat || p.a.n_tile % 64) return AGCN_ERR_UNSUPPORTED;
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return fail(AGCN_ERR_CUDA, "agcn_conv_wgrad_tc_presplit: cuTensorMapEncodeTiled is not available from the driver");
+    WgArgs& a = p.a;
+    a.ws = ws; a.dbg = 0; a.blocked = 0; a.nblk_a = 0;
+    a.pre_ablk = a.pair ? 1 : (cout < 128 ? 1 : 2);
+    a.pre_bblk = a.n_tile / 64;
+    auto encode = [&](CUtensorMap* m, const uint16_t* ptr, int c, int nblk) -> CUresult {
+        // dims (64 channels, flat row of the sample, piece, 64-channel block, sample)
+        const cuuint64_t rows = (cuuint64_t)t * v, plane = (cuuint64_t)nb * rows * c * 2;
+        cuuint64_t dims[5] = {64, rows, 2, (cuuint64_t)c / 64, (cuuint64_t)nb};
+        cuuint64_t strides[4] = {(cuuint64_t)c * 2, plane, 128, rows * c * 2};
+        cuuint32_t box[5] = {64, (cuuint32_t)a.rows_box, 2, (cuuint32_t)nblk, 1};
+        cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<uint16_t*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    };
+    CUtensorMap map_dy, map_x;
+    CUresult r = encode(&map_dy, dy_split, cout, a.pre_ablk);
+    if (r == CUDA_SUCCESS) r = encode(&map_x, x_split, cin, a.pre_bblk);
+    if (r != CUDA_SUCCESS) return fail(AGCN_ERR_CUDA, "agcn_conv_wgrad_tc_presplit: cuTensorMapEncodeTiled failed with %d", (int)r);
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
+    if (e != cudaSuccess) return fail(AGCN_ERR_CUDA, "agcn_conv_wgrad_tc_presplit: %s", cudaGetErrorString(e));
+    dim3 grid((unsigned)(a.tap_tiles * a.m_tiles * a.n_tiles), (unsigned)p.splits);
+    wgrad_tc_kernel<3><<<grid, kThreads, p.smem, static_cast<cudaStream_t>(stream)>>>(map_dy, map_x, a);
+    *splits_out = p.splits;
+    return check_launch("agcn_conv_wgrad_tc_presplit");
 }

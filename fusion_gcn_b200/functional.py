@@ -75,8 +75,11 @@ def _eval_affine(gamma, beta, buf: BnBuffers):
     return sc, sh
 
 
-def _apply(want_mask, *args, **kw):
-    """bn_apply -> (out, ReLU bit mask | None); the mask is only produced when the backward will need it."""
+def _apply(want_mask, *args, want_split=False, **kw):
+    """bn_apply -> (out, ReLU bit mask | None[, bf16 pieces of out | None]); the mask (and the pieces, the split operand of the weight
+    gradient of the convolution that consumes ``out``) are only produced when the backward will need them."""
+    if want_mask and want_split:
+        return K.bn_apply(*args, want_mask=True, want_split=True, **kw)
     if want_mask:
         return K.bn_apply(*args, want_mask=True, **kw)
     return K.bn_apply(*args, **kw), None
@@ -126,16 +129,23 @@ def gcn_forward(x, adj_a, adj_b, wa, ba, wb, bb, wd, bd, bn_w, bn_b, down_w, dow
             spec.attention_out[:] = [p[:, k] for k in range(3)]
         return o
     y, (sc, sh, mean, invstd) = _conv_bn(z, wdc, bdc, bn_w, bn_b, spec.bn_gcn, spec.training, prec)
+    # the stride-1 temporal convolution that follows takes its weight gradient from bf16 pieces of `o` written here, by the pass that
+    # produces `o` anyway (agcn_conv_wgrad_presplit): no conversion pass in the weight-gradient kernel
+    want_split = want_mask and spec.training and spec.stride == 1 and cout % 64 == 0 and prec != K.PREC_FP32_FFMA and prec != K.PREC_TF32
+    o_split = None
     if spec.has_down:
         yd, (sc2, sh2, mean2, invstd2) = _conv_bn(x, down_w.reshape(cout, 1, cin), down_b, dbn_w, dbn_b, spec.bn_down, spec.training, prec)
-        o, o_bits = _apply(want_mask, y, sc, sh, res_mode=K.RES_AFFINE, res=yd, scale2=sc2, shift2=sh2, relu=True)
+        r = _apply(want_mask, y, sc, sh, want_split=want_split, res_mode=K.RES_AFFINE, res=yd, scale2=sc2, shift2=sh2, relu=True)
     else:
         yd = mean2 = invstd2 = None
-        o, o_bits = _apply(want_mask, y, sc, sh, res_mode=K.RES_TENSOR, res=x, relu=True)
+        r = _apply(want_mask, y, sc, sh, want_split=want_split, res_mode=K.RES_TENSOR, res=x, relu=True)
+    o, o_bits = r[0], r[1]
+    if len(r) == 3:
+        o_split = r[2]
     if spec.attention_out is not None:
         spec.attention_out[:] = [p[:, k] for k in range(3)]
     if ctx is not None:
-        ctx.update(x=x, e=e, p=p, g=g, z=z, y=y, yd=yd, o=o.detach(), o_bits=o_bits, mean=mean, invstd=invstd, mean2=mean2, invstd2=invstd2,
+        ctx.update(x=x, e=e, p=p, g=g, z=z, y=y, yd=yd, o=o.detach(), o_bits=o_bits, o_split=o_split, mean=mean, invstd=invstd, mean2=mean2, invstd2=invstd2,
                    wab=wab, wdc=wdc, nchunk=nchunk, scale=scale, ci=ci)
     return o
 
@@ -257,11 +267,20 @@ def tcn_backward(d_out, ctx, bn_w, rbn_w, spec: UnitSpec, need_dres=True, need_d
     d_wr = d_br = dgam2 = dbet2 = None
     frozen = not spec.training          # eval mode with gradients, see gcn_backward
     pk["frozen"] = frozen
+    # weight gradient of the temporal convolution from split operands: `o` as bf16 pieces from the gcn half's normalise pass, `du` as
+    # bf16 pieces from the BatchNorm backward below (bit-mask form only; the pooled tail of the last unit keeps the fp32 path)
+    o_split = ctx.get("o_split") if (not frozen and bits is not None and not ctx.get("pool_rows")) else None
+    du_split = None
+    if o_split is not None:
+        pk["want_split"] = True
     if spec.residual == "identity":
         d_xres = torch.empty_like(x_res) if need_dres else None
-        du, dgam, dbet = K.bn_bwd(d_out, mask, u, ctx["t_mean"], ctx["t_invstd"], bn_w, dres=d_xres, dres_accumulate=False, mask_bits=bits, **pk)
+        du, dgam, dbet, *sp = K.bn_bwd(d_out, mask, u, ctx["t_mean"], ctx["t_invstd"], bn_w, dres=d_xres, dres_accumulate=False, mask_bits=bits, **pk)
+        du_split = sp[0] if sp else None
     elif spec.residual == "conv":
-        du, dgam, dbet = K.bn_bwd(d_out, mask, u, ctx["t_mean"], ctx["t_invstd"], bn_w, mask_bits=bits, **pk)
+        du, dgam, dbet, *sp = K.bn_bwd(d_out, mask, u, ctx["t_mean"], ctx["t_invstd"], bn_w, mask_bits=bits, **pk)
+        du_split = sp[0] if sp else None
+        pk.pop("want_split", None)
         dur, dgam2, dbet2 = K.bn_bwd(d_out, mask, ctx["ur"], ctx["t_mean2"], ctx["t_invstd2"], rbn_w, mask_bits=bits, **pk)
         d_wrp, d_br = K.conv_wgrad(dur, x_res, taps=1, stride=s, pad=0, want_bias=frozen, precision=prec)
         if not frozen:
@@ -270,10 +289,16 @@ def tcn_backward(d_out, ctx, bn_w, rbn_w, spec: UnitSpec, need_dres=True, need_d
         if need_dres:
             d_xres = K.conv_fwd(dur, _t(ctx["wrp"]), t_out=x_res.shape[1], stride=s, pad=0, transposed=True, precision=prec)
     else:
-        du, dgam, dbet = K.bn_bwd(d_out, mask, u, ctx["t_mean"], ctx["t_invstd"], bn_w, mask_bits=bits, **pk)
-    d_wtp, d_bt = K.conv_wgrad(du, o, taps=ksz, stride=s, pad=pad, want_bias=frozen, precision=prec)
-    if not frozen:
-        d_bt = _zero_bias(d_out, d_wtp.shape[0])
+        du, dgam, dbet, *sp = K.bn_bwd(d_out, mask, u, ctx["t_mean"], ctx["t_invstd"], bn_w, mask_bits=bits, **pk)
+        du_split = sp[0] if sp else None
+    d_wtp = None
+    if du_split is not None and o_split is not None:
+        d_wtp = K.conv_wgrad_presplit(du_split, o_split, (o.shape[0], o.shape[1], o.shape[2]), taps=ksz, pad=pad)
+        d_bt = _zero_bias(d_out, du.shape[-1])
+    if d_wtp is None:
+        d_wtp, d_bt = K.conv_wgrad(du, o, taps=ksz, stride=s, pad=pad, want_bias=frozen, precision=prec)
+        if not frozen:
+            d_bt = _zero_bias(d_out, d_wtp.shape[0])
     d_o = None
     if need_do:
         d_o = K.conv_fwd(du, _t(ctx["wtp"]), t_out=o.shape[1], stride=s, pad=pad, transposed=True, precision=prec)

@@ -33,6 +33,17 @@ def _same_device(t):
         raise RuntimeError(f"fusion_gcn_b200: tensors of one call live on different devices ({dev} and {t.device})")
 
 
+def _check_bf16(*tensors):
+    """Split operands (bf16 pieces [2, rows, C]): CUDA, contiguous, on the call's device."""
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda or t.dtype != torch.bfloat16 or not t.is_contiguous() or t.dim() != 3 or t.shape[0] != 2:
+            _tl.dev = None
+            raise RuntimeError("contiguous CUDA bf16 tensor of shape [2, rows, C] expected")
+        _same_device(t)
+
+
 def _check(*tensors):
     for t in tensors:
         if t is None:
@@ -229,6 +240,34 @@ def conv_wgrad(dy, x, *, taps=1, stride=1, pad=0, want_bias=True, precision=PREC
     return dw, db
 
 
+def bf16_split(x):
+    """[..., C] fp32 -> [2, rows, C] bf16 pieces (h = bf16(x), m = bf16(x - h), round to nearest ties away like the kernels).
+    Test / reference helper: in the model the pieces come out of the BatchNorm kernels (bn_apply / bn_bwd ``want_split``)."""
+    flat = x.reshape(-1, x.shape[-1]).contiguous()
+    hb = ((flat.view(torch.int32) + 0x8000) & -65536)
+    h = hb.view(torch.float32)
+    mb = ((flat - h).view(torch.int32) + 0x8000) & -65536
+    return torch.stack([(hb >> 16).to(torch.int16), (mb >> 16).to(torch.int16)]).view(torch.bfloat16)
+
+
+def conv_wgrad_presplit(dy_split, x_split, shape, *, taps=1, pad=0):
+    """Weight gradient from pre-split operands (bf16 [2, rows, C] each); shape = (nb, t, v).  -> dw [cout, taps, cin], or None when
+    the kernel does not cover the channel counts (call conv_wgrad on the fp32 tensors then)."""
+    nb, t, v = shape
+    cout, cin = dy_split.shape[-1], x_split.shape[-1]
+    if cin % 64 or cout % 64 or 2 * pad + 1 != taps:
+        return None
+    _check_bf16(dy_split, x_split)
+    L = capi.lib()
+    ws_bytes = L.agcn_conv_wgrad_workspace_bytes(nb, t, t, v, cin, cout, taps)
+    ws = torch.empty((ws_bytes + 3) // 4, device=x_split.device, dtype=torch.float32)
+    dw = torch.empty((cout, taps, cin), device=x_split.device, dtype=torch.float32)
+    _call("agcn_conv_wgrad_presplit", _ptr(dy_split), _ptr(x_split), _ptr(dw), nb, t, v, cin, cout, taps, pad, _ptr(ws), ws_bytes, _stream(),
+          sig=(nb, t, t, v, cin, cout, taps, 1), work=(2.0 * nb * t * v * cin * cout * taps, 4.0 * nb * t * v * (cin + cout)),
+          alias="agcn_conv_wgrad")
+    return dw
+
+
 # ----------------------------------------------------------------------------- V x V attention
 def pick_nchunk(nb: int, t: int, v: int = 0, width: int = 0) -> int:
     """Chunks of the t axis of the joint-gram reduction (one CTA per (sample, chunk)).  Shapes the tensor-core kernel takes
@@ -343,9 +382,11 @@ def bn_stats(x, gamma, beta, running_mean, running_var, nbt, momentum, eps, trai
 
 
 def bn_apply(y, scale, shift, *, res_mode=RES_NONE, res=None, scale2=None, shift2=None, relu=False, rowmap=None, out=None,
-             want_mask=False):
+             want_mask=False, want_split=False):
     """out = act(scale*y + shift + R).  ``want_mask``: also return the ReLU mask (out > 0) as one bit per element (int32 words,
-    agcn_bn_apply_mask) for bn_bwd(mask_bits=...), or None when the layout is not supported: -> (out, bits | None)."""
+    agcn_bn_apply_mask) for bn_bwd(mask_bits=...), or None when the layout is not supported: -> (out, bits | None).
+    ``want_split`` (with want_mask): also return ``out`` as bf16 pieces [2, rows, c] for conv_wgrad_presplit (agcn_bn_apply_mask_split),
+    or None when the layout / channel count is not covered: -> (out, bits | None, split | None)."""
     outer, inner, ostride, c = _rowmap(y, rowmap)
     if out is None:
         out = torch.empty_like(y)
@@ -355,21 +396,32 @@ def bn_apply(y, scale, shift, *, res_mode=RES_NONE, res=None, scale2=None, shift
         words = capi.lib().agcn_bn_mask_words(outer, inner, c) if (y.is_contiguous() and out.is_contiguous() and (res is None or res.is_contiguous())) else 0
         if words:
             bits = torch.empty(words, device=y.device, dtype=torch.int32)
+            work = (0.0, 4.0 * outer * inner * c * (2 if res_mode == RES_NONE else 3))
+            if want_split and c % 64 == 0:
+                split = torch.empty((2, inner, c), device=y.device, dtype=torch.bfloat16)
+                _call("agcn_bn_apply_mask_split", y.data_ptr(), _ptr(scale), _ptr(shift), res_mode, _ptr(res), _ptr(scale2), _ptr(shift2), int(relu),
+                      out.data_ptr(), bits.data_ptr(), split.data_ptr(), inner, c, _stream(), sig=(outer, inner, c, res_mode, int(relu), 1),
+                      work=(0.0, work[1] + 4.0 * inner * c), alias="agcn_bn_apply")
+                return out, bits, split
             _call("agcn_bn_apply_mask", y.data_ptr(), _ptr(scale), _ptr(shift), res_mode, _ptr(res), _ptr(scale2), _ptr(shift2), int(relu),
                   out.data_ptr(), bits.data_ptr(), inner, c, _stream(), sig=(outer, inner, c, res_mode, int(relu)),
-                  work=(0.0, 4.0 * outer * inner * c * (2 if res_mode == RES_NONE else 3)), alias="agcn_bn_apply")
-            return out, bits
+                  work=work, alias="agcn_bn_apply")
+            return (out, bits, None) if want_split else (out, bits)
     _call("agcn_bn_apply", y.data_ptr(), _ptr(scale), _ptr(shift), res_mode, _ptr(res), _ptr(scale2), _ptr(shift2), int(relu),
           out.data_ptr(), outer, inner, ostride, c, _stream(), sig=(outer, inner, c, res_mode, int(relu)),
           work=(0.0, 4.0 * outer * inner * c * (2 if res_mode == RES_NONE else 3)))
-    return (out, None) if want_mask else out
+    if want_mask:
+        return (out, None, None) if want_split else (out, None)
+    return out
 
 
 def bn_bwd(dout, mask_out, y, save_mean, save_invstd, gamma, *, want_dy=True, dy=None, dres=None, dres_accumulate=False,
-           rowmap=None, mask_bits=None, pool_rows=0, frozen=False):
+           rowmap=None, mask_bits=None, pool_rows=0, frozen=False, want_split=False):
     """-> dy | None, dgamma, dbeta; optionally writes / accumulates the masked gradient into ``dres``.
     ``dy`` may be a preallocated tensor addressed with the same rowmap as ``y``.  ``mask_bits`` (from bn_apply(want_mask=True))
-    replaces the fp32 tensor ``mask_out`` as the ReLU mask.  ``frozen``: the statistics are constants (eval-mode BatchNorm)."""
+    replaces the fp32 tensor ``mask_out`` as the ReLU mask.  ``frozen``: the statistics are constants (eval-mode BatchNorm).
+    ``want_split``: -> dy, dgamma, dbeta, dy_split with dy also as bf16 pieces [2, rows, c] (agcn_bn_bwd_bits_split), or None in
+    the last place when the call is not the bit-mask form / the channel count is not a multiple of 64."""
     outer, inner, ostride, c = _rowmap(y, rowmap)
     if want_dy and dy is None:
         dy = torch.empty_like(y)
@@ -387,17 +439,26 @@ def bn_bwd(dout, mask_out, y, save_mean, save_invstd, gamma, *, want_dy=True, dy
               _ptr(ws), nbytes, _stream(), sig=(dout.shape[0], int(pool_rows), c, int(dy is not None), int(dres is not None)),
               work=(0.0, 4.0 * inner * c * (2 + 2.0 / 32 + int(dy is not None) + int(dres is not None) * (1 + int(dres_accumulate)))),
               alias="agcn_bn_bwd")
-        return dy, dgb[0], dgb[1]
+        return (dy, dgb[0], dgb[1], None) if want_split else (dy, dgb[0], dgb[1])
     if mask_bits is not None:
         if mask_bits.dtype != torch.int32 or not mask_bits.is_cuda:
             raise RuntimeError("bn_bwd: mask_bits must be the int32 CUDA tensor returned by bn_apply(want_mask=True)")
         _check(dout, y, dy, dres)
+        if want_split and dy is not None and c % 64 == 0:
+            dy_split = torch.empty((2, inner, c), device=y.device, dtype=torch.bfloat16)
+            _call("agcn_bn_bwd_bits_split", dout.data_ptr(), mask_bits.data_ptr(), y.data_ptr(), _ptr(save_mean), _ptr(save_invstd), _ptr(gamma),
+                  _ptr(dy), dy_split.data_ptr(), dgb[0].data_ptr(), dgb[1].data_ptr(), _ptr(dres), int(dres_accumulate), int(frozen), inner, c,
+                  _ptr(ws), nbytes, _stream(),
+                  sig=(outer, inner, c, 2, 1, int(dres is not None), int(dres_accumulate), 1),
+                  work=(0.0, 4.0 * outer * inner * c * (2 * 2 + 2.0 / 32 + 2 + int(dres is not None) * (1 + int(dres_accumulate)))),
+                  alias="agcn_bn_bwd")
+            return dy, dgb[0], dgb[1], dy_split
         _call("agcn_bn_bwd_bits", dout.data_ptr(), mask_bits.data_ptr(), y.data_ptr(), _ptr(save_mean), _ptr(save_invstd), _ptr(gamma),
               _ptr(dy), dgb[0].data_ptr(), dgb[1].data_ptr(), _ptr(dres), int(dres_accumulate), int(frozen), inner, c, _ptr(ws), nbytes, _stream(),
               sig=(outer, inner, c, 2, int(dy is not None), int(dres is not None), int(dres_accumulate)),
               work=(0.0, 4.0 * outer * inner * c * (2 * 2 + 2.0 / 32 + int(dy is not None) + int(dres is not None) * (1 + int(dres_accumulate)))),
               alias="agcn_bn_bwd")
-        return dy, dgb[0], dgb[1]
+        return (dy, dgb[0], dgb[1], None) if want_split else (dy, dgb[0], dgb[1])
     _call("agcn_bn_bwd", dout.data_ptr(), _ptr(mask_out), y.data_ptr(), _ptr(save_mean), _ptr(save_invstd), _ptr(gamma),
           _ptr(dy), dgb[0].data_ptr(), dgb[1].data_ptr(), _ptr(dres), int(dres_accumulate), int(frozen), outer, inner, ostride, c,
           _ptr(ws), nbytes, _stream(),
@@ -405,7 +466,7 @@ def bn_bwd(dout, mask_out, y, save_mean, save_invstd, gamma, *, want_dy=True, dy
           # two passes over (dout, y[, mask]); the second writes dy [and dres, read first when accumulating]
           work=(0.0, 4.0 * outer * inner * c * (2 * (2 + int(mask_out is not None)) + int(dy is not None)
                                                + int(dres is not None) * (1 + int(dres_accumulate)))))
-    return dy, dgb[0], dgb[1]
+    return (dy, dgb[0], dgb[1], None) if want_split else (dy, dgb[0], dgb[1])
 
 
 def bn_pool_supported(rows: int, channels: int) -> bool:

@@ -120,6 +120,16 @@ int agcn_conv_wgrad(const float* dy, const float* x, float* dw, float* dbias,
                     int taps, int stride, int pad,
                     void* workspace, size_t workspace_bytes, int precision, void* stream);
 
+/* The same weight gradient (stride 1, t_in == t_out, no bias gradient) from operands that ARRIVE split into the bf16 pieces the
+ * parity modes multiply: dy_split [2][nb*t*v][cout], x_split [2][nb*t*v][cin] bf16, plane 0 = h = bf16(value), plane 1 =
+ * m = bf16(value - h) -- written by agcn_bn_apply_mask_split / agcn_bn_bwd_bits_split, the kernels that produce the activations
+ * and their gradients anyway.  The in-kernel conversion of agcn_conv_wgrad is what bounds it (shared-memory bandwidth); without
+ * it the kernel runs at the tensor rate of three bf16 MMAs.  Same workspace as agcn_conv_wgrad.  Returns AGCN_ERR_UNSUPPORTED
+ * (no error string) unless cin and cout are multiples of 64.                                                                   */
+int agcn_conv_wgrad_presplit(const void* dy_split, const void* x_split, float* dw,
+                             int nb, int t, int v, int cin, int cout, int taps, int pad,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- joint x joint products (the V x V attention) --------------------------------------------------
  * out[nb][chunk][g][u][v] = sum_{t in chunk} sum_{c<width} a[nb][t][u][offa+g*stridea+c] * b[nb][t][v][offb+g*strideb+c]
  * a: [nb][t][v][lda], b: [nb][t][v][ldb].  The t axis is split into nchunk contiguous chunks so that a
@@ -206,6 +216,18 @@ int agcn_bn_bwd_bits(const float* dout, const unsigned* mask_bits, const float* 
                      const float* save_mean, const float* save_invstd, const float* gamma,
                      float* dy, float* dgamma, float* dbeta, float* dres, int dres_accumulate, int frozen_stats,
                      int inner, int channels, void* workspace, size_t workspace_bytes, void* stream);
+
+/* agcn_bn_apply_mask / agcn_bn_bwd_bits that ALSO leave their fp32 output (out / dy) as the bf16 pieces the parity modes multiply:
+ * [2][inner][channels] bf16, plane 0 = h = bf16(value), plane 1 = m = bf16(value - h) -- the operand format of
+ * agcn_conv_wgrad_presplit.  One more plane written by kernels that stream the tensor anyway, instead of a conversion pass in
+ * shared memory for every tile of the weight gradient.  Same layout restrictions as the bit-mask variants.               */
+int agcn_bn_apply_mask_split(const float* y, const float* scale, const float* shift,
+                             int res_mode, const float* res, const float* scale2, const float* shift2,
+                             int relu, float* out, unsigned* mask_bits, void* out_split, int inner, int channels, void* stream);
+int agcn_bn_bwd_bits_split(const float* dout, const unsigned* mask_bits, const float* y,
+                           const float* save_mean, const float* save_invstd, const float* gamma,
+                           float* dy, void* dy_split, float* dgamma, float* dbeta, float* dres, int dres_accumulate, int frozen_stats,
+                           int inner, int channels, void* workspace, size_t workspace_bytes, void* stream);
 
 /* BatchNorm backward through an optional ReLU mask:
  *   g = dout * [mask_out > 0]  (g = dout when mask_out == NULL)

@@ -211,9 +211,35 @@ def bn_stats(x, gamma, beta, running_mean, running_var, nbt, momentum, eps, trai
     return scale, b - mean * scale, mean, invstd
 
 
+def bf16_split(x):
+    """[..., C] -> [2, rows, C] bf16 pieces h = bf16(x), m = bf16(x - h) (round to nearest, ties away): the split-operand format of the
+    weight-gradient kernel (agcn_conv_wgrad_presplit).  fp64 inputs (the tests' reference runs) are carried exactly instead: [2, rows, C]
+    with the value in plane 0 and zeros in plane 1."""
+    flat = x.reshape(-1, x.shape[-1]).contiguous()
+    if flat.dtype != torch.float32:
+        return torch.stack([flat, torch.zeros_like(flat)])
+    hb = (flat.view(torch.int32) + 0x8000) & -65536
+    h = hb.view(torch.float32)
+    mb = ((flat - h).view(torch.int32) + 0x8000) & -65536
+    return torch.stack([(hb >> 16).to(torch.int16), (mb >> 16).to(torch.int16)]).view(torch.bfloat16)
+
+
+def conv_wgrad_presplit(dy_split, x_split, shape, *, taps=1, pad=0):
+    nb, t, v = shape
+    cout, cin = dy_split.shape[-1], x_split.shape[-1]
+    if cin % 64 or cout % 64 or 2 * pad + 1 != taps:
+        return None
+    wide = torch.float32 if dy_split.dtype == torch.bfloat16 else dy_split.dtype
+    dy = (dy_split[0].to(wide) + dy_split[1].to(wide)).reshape(nb, t, v, cout)
+    x = (x_split[0].to(wide) + x_split[1].to(wide)).reshape(nb, t, v, cin)
+    return conv_wgrad(dy, x, taps=taps, stride=1, pad=pad, want_bias=False)[0]
+
+
 def bn_apply(y, scale, shift, *, res_mode=RES_NONE, res=None, scale2=None, shift2=None, relu=False, rowmap=None, out=None,
-             want_mask=False):
+             want_mask=False, want_split=False):
     r = _bn_apply(y, scale, shift, res_mode=res_mode, res=res, scale2=scale2, shift2=shift2, relu=relu, rowmap=rowmap, out=out)
+    if want_mask and want_split:
+        return r, (r > 0), (bf16_split(r) if r.shape[-1] % 64 == 0 and rowmap is None else None)
     return (r, (r > 0)) if want_mask else r            # the "bit mask" of the CUDA path is a bool tensor here
 
 
@@ -233,7 +259,12 @@ def _bn_apply(y, scale, shift, *, res_mode=RES_NONE, res=None, scale2=None, shif
 
 
 def bn_bwd(dout, mask_out, y, save_mean, save_invstd, gamma, *, want_dy=True, dy=None, dres=None, dres_accumulate=False,
-           rowmap=None, mask_bits=None, pool_rows=0, frozen=False):
+           rowmap=None, mask_bits=None, pool_rows=0, frozen=False, want_split=False):
+    if want_split:
+        dy, dgamma, dbeta = bn_bwd(dout, mask_out, y, save_mean, save_invstd, gamma, want_dy=want_dy, dy=dy, dres=dres, dres_accumulate=dres_accumulate,
+                                   rowmap=rowmap, mask_bits=mask_bits, pool_rows=pool_rows, frozen=frozen)
+        ok = dy is not None and mask_bits is not None and not pool_rows and rowmap is None and dy.shape[-1] % 64 == 0
+        return dy, dgamma, dbeta, (bf16_split(dy) if ok else None)
     if pool_rows:          # dout is the pooled gradient [groups, c]: broadcast over the rows of each group, divided by their number
         groups, c = dout.shape
         dout = (dout / pool_rows).reshape(groups, 1, c).expand(groups, pool_rows, c).reshape(y.shape).contiguous()

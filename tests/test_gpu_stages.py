@@ -69,6 +69,52 @@ def test_conv_fwd_dgrad_wgrad(K, nb, t_in, v, cin, cout, taps, stride, mode):
     assert rel_err(dw, dw_ref) <= (5e-6 if mode == "ffma" else 4e-5) and rel_err(db, db_ref) <= 5e-6
 
 
+@pytest.mark.parametrize("rows,c", [(1000, 64), (4099, 256), (777, 128), (333, 192), (50, 32)])
+def test_batchnorm_kernels_also_write_bf16_pieces(K, rows, c):
+    """agcn_bn_apply_mask_split / agcn_bn_bwd_bits_split: the fp32 results are those of the plain bit-mask calls bit for bit, the extra
+    output is their (h, m) bf16 split -- the operand format of agcn_conv_wgrad_presplit; channel counts that are not a multiple of 64
+    return None in its place."""
+    y, res = rnd(rows, c).cuda(), rnd(rows, c, seed=1).cuda()
+    sc, sh = (rnd(c, seed=2) * 0.3 + 1).cuda(), (rnd(c, seed=3) * 0.1).cuda()
+    o0, b0 = K.bn_apply(y, sc, sh, res_mode=K.RES_TENSOR, res=res, relu=True, want_mask=True)
+    o1, b1, sp = K.bn_apply(y, sc, sh, res_mode=K.RES_TENSOR, res=res, relu=True, want_mask=True, want_split=True)
+    assert torch.equal(o0, o1)
+    if b0 is None:                       # (192 channels: no bit-mask layout, hence no fused pieces either)
+        assert b1 is None and sp is None
+        return
+    assert torch.equal(b0, b1)
+    dout = rnd(rows, c, seed=4).cuda()
+    mean, invstd, gamma = (rnd(c, seed=5) * 0.1).cuda(), (rnd(c, seed=6).abs() + 0.5).cuda(), (rnd(c, seed=7) * 0.3 + 1).cuda()
+    d0 = K.bn_bwd(dout, None, y, mean, invstd, gamma, mask_bits=b0)
+    d1 = K.bn_bwd(dout, None, y, mean, invstd, gamma, mask_bits=b0, want_split=True)
+    assert all(torch.equal(a, b) for a, b in zip(d0, d1[:3]))
+    if c % 64:
+        assert sp is None and d1[3] is None
+        return
+    assert torch.equal(sp.view(torch.int16), K.bf16_split(o0).view(torch.int16))
+    assert torch.equal(d1[3].view(torch.int16), K.bf16_split(d0[0]).view(torch.int16))
+
+
+@pytest.mark.parametrize("nb,t,v,cin,cout,taps", [(2, 40, 25, 64, 64, 9), (4, 150, 25, 256, 128, 9), (2, 31, 25, 192, 64, 1), (3, 20, 22, 128, 256, 9),
+                                                 (2, 12, 25, 64, 192, 1), (4, 150, 25, 256, 64, 9), (1, 7, 20, 96, 64, 1)])
+def test_weight_gradient_from_presplit_operands(K, nb, t, v, cin, cout, taps):
+    """agcn_conv_wgrad_presplit: the operands arrive as the bf16 pieces (h, m) the parity modes multiply; the result is the one of
+    agcn_conv_wgrad in those modes bit for bit (same pieces, same MMA order), and within their tolerance of the fp64 contraction."""
+    pad = (taps - 1) // 2
+    x, dy = rnd(nb, t, v, cin).cuda(), rnd(nb, t, v, cout, seed=4).cuda()
+    xs, dys = K.bf16_split(x), K.bf16_split(dy)
+    assert xs.shape == (2, nb * t * v, cin) and xs.dtype == torch.bfloat16
+    assert rel_err(xs[0].float() + xs[1].float(), x.reshape(-1, cin)) <= 2 ** -16
+    dw = K.conv_wgrad_presplit(dys, xs, (nb, t, v), taps=taps, pad=pad)
+    if cin % 64 or cout % 64:
+        assert dw is None
+        return
+    want, _ = K.conv_wgrad(dy, x, taps=taps, pad=pad, want_bias=False, precision=K.PREC_FP32)
+    assert torch.equal(dw, want)
+    ref, _ = S.conv_wgrad(dy.double().cpu(), x.double().cpu(), taps=taps, pad=pad)
+    assert rel_err(dw, ref) <= 4e-5
+
+
 @pytest.mark.parametrize("mode", ["fp32", "tf32", "bf16x3"])
 @pytest.mark.parametrize("nb,t_in,v,cin,cout,taps,stride", [
     (3, 40, 25, 64, 64, 9, 1), (2, 31, 25, 192, 64, 1, 1), (4, 30, 20, 64, 128, 9, 2), (2, 24, 22, 384, 128, 1, 1),

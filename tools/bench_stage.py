@@ -94,6 +94,12 @@ def main():
                 ms = timeit(lambda: K.conv_fwd_stats(xi, w, b, pad=(taps - 1) // 2, precision=prec), once)
                 report(f"convstats_{nm}_{tag}", ms, rows * (cin + cout) * 4, 2.0 * rows * cin * cout * taps)
                 del xi
+            if want(f"wgradpre_{nm}_{tag}") and cin % 64 == 0 and cout % 64 == 0:      # operands arrive as bf16 pieces
+                xs = K.bf16_split(torch.randn(NB, t, V, cin, device=dev))
+                dys = K.bf16_split(torch.randn(NB, t, V, cout, device=dev))
+                ms = timeit(lambda: K.conv_wgrad_presplit(dys, xs, (NB, t, V), taps=taps, pad=(taps - 1) // 2), once)
+                report(f"wgradpre_{nm}_{tag}", ms, rows * (cin + cout) * 4, 2.0 * rows * cin * cout * taps)
+                del xs, dys
             if want(f"wgrad_{nm}_{tag}"):
                 xi = torch.randn(NB, t, V, cin, device=dev)
                 dy = torch.randn(NB, t, V, cout, device=dev)
