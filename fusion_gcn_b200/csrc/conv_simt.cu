@@ -564,7 +564,7 @@ size_t agcn_conv_wgrad_tc_workspace_floats(int nb, int t_in, int t_out, int v, i
 int agcn_conv_wgrad_tc(const float* dy, const float* x, float* ws, int* splits_out,
                        int nb, int t_in, int t_out, int v, int cin, int cout, int taps, int stride, int pad, int split, void* stream);
 int agcn_conv_wgrad_tc_presplit(const uint16_t* dy_split, const uint16_t* x_split, float* ws, int* splits_out,
-                                int nb, int t, int v, int cin, int cout, int taps, int pad, void* stream);
+                                int nb, int t_in, int t_out, int v, int cin, int cout, int taps, int stride, int pad, void* stream);
 
 static bool known_precision(int p) { return p >= AGCN_PREC_FP32 && p <= AGCN_PREC_BF16X3; }
 
@@ -681,24 +681,24 @@ extern "C" AGCN_API size_t agcn_conv_wgrad_workspace_bytes(int nb, int t_in, int
     return need * sizeof(float);
 }
 
-// Weight gradient of a stride-1 convolution from operands that arrive split into bf16 pieces: dy_split [2][nb*t*v][cout] and
-// x_split [2][nb*t*v][cin] (plane 0 = h = bf16(value), plane 1 = m = bf16(value - h), round to nearest), as written by
-// agcn_bn_apply_mask_split / agcn_bn_bwd_bits_split.  Same arithmetic as the parity modes of agcn_conv_wgrad (h.h + h.m + m.h on
-// kind::f16) without the in-kernel conversion.  No bias gradient.  AGCN_ERR_UNSUPPORTED (quiet) for channel counts that are not
-// multiples of 64: use agcn_conv_wgrad on the fp32 tensors then.
+// Weight gradient from operands that arrive split into bf16 pieces: dy_split [2][nb*t_out*v][cout] and x_split [2][nb*t_in*v][cin]
+// (plane 0 = h = bf16(value), plane 1 = m = bf16(value - h), round to nearest), as written by agcn_bn_apply_mask_split /
+// agcn_bn_bwd_bits_split.  Same arithmetic as the parity modes of agcn_conv_wgrad (h.h + h.m + m.h on kind::f16) without the
+// in-kernel conversion.  No bias gradient.  AGCN_ERR_UNSUPPORTED (quiet) for channel counts that are not multiples of 64: use
+// agcn_conv_wgrad on the fp32 tensors then.
 extern "C" AGCN_API int agcn_conv_wgrad_presplit(const void* dy_split, const void* x_split, float* dw,
-                                                 int nb, int t, int v, int cin, int cout, int taps, int pad,
+                                                 int nb, int t_in, int t_out, int v, int cin, int cout, int taps, int stride, int pad,
                                                  void* workspace, size_t workspace_bytes, void* stream) {
     AGCN_REQUIRE(dy_split && x_split && dw && workspace, AGCN_ERR_NULL, "agcn_conv_wgrad_presplit: null pointer");
-    AGCN_REQUIRE(nb > 0 && t > 0 && v > 0 && cin > 0 && cout > 0 && taps > 0 && pad >= 0, AGCN_ERR_BAD_SHAPE, "agcn_conv_wgrad_presplit: bad shape");
-    AGCN_REQUIRE(workspace_bytes >= agcn_conv_wgrad_workspace_bytes(nb, t, t, v, cin, cout, taps), AGCN_ERR_WORKSPACE,
+    AGCN_REQUIRE(nb > 0 && t_in > 0 && t_out > 0 && v > 0 && cin > 0 && cout > 0 && taps > 0 && stride > 0 && pad >= 0, AGCN_ERR_BAD_SHAPE,
+                 "agcn_conv_wgrad_presplit: bad shape");
+    AGCN_REQUIRE(workspace_bytes >= agcn_conv_wgrad_workspace_bytes(nb, t_in, t_out, v, cin, cout, taps), AGCN_ERR_WORKSPACE,
                  "agcn_conv_wgrad_presplit: workspace too small");
     AGCN_REQUIRE(aligned16(workspace), AGCN_ERR_MISALIGNED, "agcn_conv_wgrad_presplit: workspace not 16-byte aligned");
-    if (2 * pad + 1 != taps) return AGCN_ERR_UNSUPPORTED;                 // "same" convolutions only (t_in == t_out)
     float* ws = static_cast<float*>(workspace);
     int splits = 0;
     int rc = agcn_conv_wgrad_tc_presplit(static_cast<const uint16_t*>(dy_split), static_cast<const uint16_t*>(x_split), ws, &splits,
-                                         nb, t, v, cin, cout, taps, pad, stream);
+                                         nb, t_in, t_out, v, cin, cout, taps, stride, pad, stream);
     if (rc) return rc;
     const long long wsize = (long long)cout * taps * cin;
     wgrad_reduce_kernel<<<ceil_div(wsize, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(ws, nullptr, dw, nullptr, wsize, cout, splits);

@@ -49,7 +49,10 @@ struct WgArgs {
 // MMAs), which bounds it at ~200 TFLOP/s; here it moves 120 KB.
 template <int MODE>
 __global__ void __launch_bounds__((MODE == 1 || MODE == 2) ? kWgThreadsSplit : kThreads, 1)
-wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, WgArgs a) {
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
+                const __grid_constant__ CUtensorMap map_dy_m, const __grid_constant__ CUtensorMap map_x_m, WgArgs a) {
+    // (map_dy_m / map_x_m: MODE 3 with whole-timestep boxes -- strided / shortened convolutions -- loads the h and the m plane through
+    // separate 5-D maps (64 channels, v, t, block, sample), one box per (64-channel block, piece); unused otherwise)
     constexpr bool SPLIT = MODE == 1, PRE = MODE == 3, BF = MODE == 2 || MODE == 3, CONV = MODE != 0;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -125,6 +128,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
     loaded |= ((1u << b_boxes) - 1u) << 4;
     uint32_t stage_tx = (uint32_t)__popc(loaded) * (uint32_t)a.rows_box * 128u;
     if (PRE) stage_tx = (uint32_t)(a.pre_ablk * ((a.pair && tap_b) ? 2 : 1) + a.pre_bblk) * 2u * (uint32_t)a.rows_box * 128u;
+    // (flat: pre_*blk = blocks per box, whole boxes count; timestep boxes: pre_*blk = blocks actually loaded for this tile)
+    int pre_na = a.pre_ablk, pre_nb = a.pre_bblk;
+    if (PRE && !a.flat) {
+        pre_na = ((a.cout - m0 < 128 ? a.cout - m0 : 128) + 63) / 64;
+        pre_nb = ((a.cin - k0 < a.n_tile ? a.cin - k0 : a.n_tile) + 63) / 64;
+        stage_tx = (uint32_t)(pre_na + pre_nb) * 2u * (uint32_t)a.rows_box * 128u;
+    }
 
     if (warp == 0) {
         {   // warp-uniform loop, elected lane issues the TMA loads (uniform-register operands)
@@ -140,7 +150,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
                 const uint32_t sa = smem_base + (uint32_t)stage * raw_bytes;
                 if (leader) {
                     mbar_expect_tx(full_bar(stage), stage_tx);
-                    if (PRE) {
+                    if (PRE && !a.flat) {
+                        for (int i = 0; i < pre_na; ++i) {
+                            tma_load_5d(sa + (uint32_t)(2 * i) * sub_bytes, &map_dy, full_bar(stage), 0, 0, a2, m0 / 64 + i, n);
+                            tma_load_5d(sa + (uint32_t)(2 * i + 1) * sub_bytes, &map_dy_m, full_bar(stage), 0, 0, a2, m0 / 64 + i, n);
+                        }
+                        for (int j = 0; j < pre_nb; ++j) {
+                            tma_load_5d(sa + (uint32_t)(4 + 2 * j) * sub_bytes, &map_x, full_bar(stage), 0, 0, b2, k0 / 64 + j, n);
+                            tma_load_5d(sa + (uint32_t)(5 + 2 * j) * sub_bytes, &map_x_m, full_bar(stage), 0, 0, b2, k0 / 64 + j, n);
+                        }
+                    } else if (PRE) {
                         // dims (64 channels, flat row, piece, 64-channel block, sample); the box covers both pieces and all blocks of the tile
                         tma_load_5d(sa, &map_dy, full_bar(stage), 0, a1, 0, a.pair ? 0 : m0 / 64, n);
                         if (a.pair && tap_b) tma_load_5d(sa + 2u * sub_bytes, &map_dy, full_bar(stage), 0, a1 - a.v, 0, 0, n);
@@ -484,45 +503,64 @@ int agcn_conv_wgrad_tc(const float* dy, const float* x, float* ws, int* splits_o
     }
     dim3 grid((unsigned)(a.tap_tiles * a.m_tiles * a.n_tiles), (unsigned)p.splits);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (split == 2) wgrad_tc_kernel<2><<<grid, kWgThreadsSplit, p.smem, st>>>(map_dy, map_x, a);
-    else if (split) wgrad_tc_kernel<1><<<grid, kWgThreadsSplit, p.smem, st>>>(map_dy, map_x, a);
-    else wgrad_tc_kernel<0><<<grid, kThreads, p.smem, st>>>(map_dy, map_x, a);
+    if (split == 2) wgrad_tc_kernel<2><<<grid, kWgThreadsSplit, p.smem, st>>>(map_dy, map_x, map_dy, map_x, a);
+    else if (split) wgrad_tc_kernel<1><<<grid, kWgThreadsSplit, p.smem, st>>>(map_dy, map_x, map_dy, map_x, a);
+    else wgrad_tc_kernel<0><<<grid, kThreads, p.smem, st>>>(map_dy, map_x, map_dy, map_x, a);
     *splits_out = p.splits;
     return check_launch("agcn_conv_wgrad_tc");
 }
 
-// ---- the same on operands that arrive split: dy_split / x_split = [2][nb * t * v][C] bf16 (plane 0 = h = bf16(x), plane 1 = m = bf16(x - h)).
-// Flat layout only (stride 1, t_in == t_out), channel counts multiples of 64.  AGCN_ERR_UNSUPPORTED otherwise.
+// ---- the same on operands that arrive split: dy_split = [2][nb * t_out * v][cout], x_split = [2][nb * t_in * v][cin] bf16 (plane 0 = h =
+// bf16(x), plane 1 = m = bf16(x - h)).  Channel counts multiples of 64.  AGCN_ERR_UNSUPPORTED otherwise.
 int agcn_conv_wgrad_tc_presplit(const uint16_t* dy_split, const uint16_t* x_split, float* ws, int* splits_out,
-                                int nb, int t, int v, int cin, int cout, int taps, int pad, void* stream) {
+                                int nb, int t_in, int t_out, int v, int cin, int cout, int taps, int stride, int pad, void* stream) {
     using namespace agcn::tc;
     if (cin % 64 || cout % 64 || !aligned16(dy_split) || !aligned16(x_split) || !aligned16(ws)) return AGCN_ERR_UNSUPPORTED;
-    WgPlan p = plan_wgrad(nb, t, t, v, cin, cout, taps, 1, pad, 2);
-    if (!p.ok || !p.a.flat || p.a.n_tile % 64) return AGCN_ERR_UNSUPPORTED;
+    WgPlan p = plan_wgrad(nb, t_in, t_out, v, cin, cout, taps, stride, pad, 2);
+    if (!p.ok || p.a.n_tile % 64) return AGCN_ERR_UNSUPPORTED;
     EncodeTiledFn enc = encode_fn();
     if (!enc) return fail(AGCN_ERR_CUDA, "agcn_conv_wgrad_tc_presplit: cuTensorMapEncodeTiled is not available from the driver");
     WgArgs& a = p.a;
     a.ws = ws; a.dbg = 0; a.blocked = 0; a.nblk_a = 0;
     a.pre_ablk = a.pair ? 1 : (cout < 128 ? 1 : 2);
     a.pre_bblk = a.n_tile / 64;
-    auto encode = [&](CUtensorMap* m, const uint16_t* ptr, int c, int nblk) -> CUresult {
-        // dims (64 channels, flat row of the sample, piece, 64-channel block, sample)
-        const cuuint64_t rows = (cuuint64_t)t * v, plane = (cuuint64_t)nb * rows * c * 2;
-        cuuint64_t dims[5] = {64, rows, 2, (cuuint64_t)c / 64, (cuuint64_t)nb};
-        cuuint64_t strides[4] = {(cuuint64_t)c * 2, plane, 128, rows * c * 2};
-        cuuint32_t box[5] = {64, (cuuint32_t)a.rows_box, 2, (cuuint32_t)nblk, 1};
-        cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-        return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<uint16_t*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    };
-    CUtensorMap map_dy, map_x;
-    CUresult r = encode(&map_dy, dy_split, cout, a.pre_ablk);
-    if (r == CUDA_SUCCESS) r = encode(&map_x, x_split, cin, a.pre_bblk);
+    CUtensorMap map_dy, map_x, map_dy_m, map_x_m;
+    CUresult r;
+    if (a.flat) {
+        auto encode = [&](CUtensorMap* m, const uint16_t* ptr, int c, int nblk) -> CUresult {
+            // dims (64 channels, flat row of the sample, piece, 64-channel block, sample)
+            const cuuint64_t rows = (cuuint64_t)t_out * v, plane = (cuuint64_t)nb * rows * c * 2;
+            cuuint64_t dims[5] = {64, rows, 2, (cuuint64_t)c / 64, (cuuint64_t)nb};
+            cuuint64_t strides[4] = {(cuuint64_t)c * 2, plane, 128, rows * c * 2};
+            cuuint32_t box[5] = {64, (cuuint32_t)a.rows_box, 2, (cuuint32_t)nblk, 1};
+            cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+            return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<uint16_t*>(ptr), dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        };
+        r = encode(&map_dy, dy_split, cout, a.pre_ablk);
+        if (r == CUDA_SUCCESS) r = encode(&map_x, x_split, cin, a.pre_bblk);
+        map_dy_m = map_dy; map_x_m = map_x;
+    } else {
+        auto encode = [&](CUtensorMap* m, const uint16_t* ptr, int c, int t, int box_t, int es_t) -> CUresult {
+            // one piece: dims (64 channels, v, t, 64-channel block, sample); whole timesteps per box, element stride on t for the input
+            cuuint64_t dims[5] = {64, (cuuint64_t)v, (cuuint64_t)t, (cuuint64_t)c / 64, (cuuint64_t)nb};
+            cuuint64_t strides[4] = {(cuuint64_t)c * 2, (cuuint64_t)v * c * 2, 128, (cuuint64_t)t * v * c * 2};
+            cuuint32_t box[5] = {64, (cuuint32_t)v, (cuuint32_t)box_t, 1, 1};
+            cuuint32_t estr[5] = {1, 1, (cuuint32_t)es_t, 1, 1};
+            return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<uint16_t*>(ptr), dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        };
+        const size_t plane_dy = (size_t)nb * t_out * v * cout, plane_x = (size_t)nb * t_in * v * cin;
+        r = encode(&map_dy, dy_split, cout, t_out, a.tt, 1);
+        if (r == CUDA_SUCCESS) r = encode(&map_dy_m, dy_split + plane_dy, cout, t_out, a.tt, 1);
+        if (r == CUDA_SUCCESS) r = encode(&map_x, x_split, cin, t_in, a.tt * stride, stride);
+        if (r == CUDA_SUCCESS) r = encode(&map_x_m, x_split + plane_x, cin, t_in, a.tt * stride, stride);
+    }
     if (r != CUDA_SUCCESS) return fail(AGCN_ERR_CUDA, "agcn_conv_wgrad_tc_presplit: cuTensorMapEncodeTiled failed with %d", (int)r);
     cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
     if (e != cudaSuccess) return fail(AGCN_ERR_CUDA, "agcn_conv_wgrad_tc_presplit: %s", cudaGetErrorString(e));
     dim3 grid((unsigned)(a.tap_tiles * a.m_tiles * a.n_tiles), (unsigned)p.splits);
-    wgrad_tc_kernel<3><<<grid, kThreads, p.smem, static_cast<cudaStream_t>(stream)>>>(map_dy, map_x, a);
+    wgrad_tc_kernel<3><<<grid, kThreads, p.smem, static_cast<cudaStream_t>(stream)>>>(map_dy, map_x, map_dy_m, map_x_m, a);
     *splits_out = p.splits;
     return check_launch("agcn_conv_wgrad_tc_presplit");
 }

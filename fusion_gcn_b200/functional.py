@@ -129,9 +129,9 @@ def gcn_forward(x, adj_a, adj_b, wa, ba, wb, bb, wd, bd, bn_w, bn_b, down_w, dow
             spec.attention_out[:] = [p[:, k] for k in range(3)]
         return o
     y, (sc, sh, mean, invstd) = _conv_bn(z, wdc, bdc, bn_w, bn_b, spec.bn_gcn, spec.training, prec)
-    # the stride-1 temporal convolution that follows takes its weight gradient from bf16 pieces of `o` written here, by the pass that
+    # the temporal convolution that follows takes its weight gradient from bf16 pieces of `o` written here, by the pass that
     # produces `o` anyway (agcn_conv_wgrad_presplit): no conversion pass in the weight-gradient kernel
-    want_split = want_mask and spec.training and spec.stride == 1 and cout % 64 == 0 and prec != K.PREC_FP32_FFMA and prec != K.PREC_TF32
+    want_split = want_mask and spec.training and cout % 64 == 0 and prec != K.PREC_FP32_FFMA and prec != K.PREC_TF32
     o_split = None
     if spec.has_down:
         yd, (sc2, sh2, mean2, invstd2) = _conv_bn(x, down_w.reshape(cout, 1, cin), down_b, dbn_w, dbn_b, spec.bn_down, spec.training, prec)
@@ -293,7 +293,7 @@ def tcn_backward(d_out, ctx, bn_w, rbn_w, spec: UnitSpec, need_dres=True, need_d
         du_split = sp[0] if sp else None
     d_wtp = None
     if du_split is not None and o_split is not None:
-        d_wtp = K.conv_wgrad_presplit(du_split, o_split, (o.shape[0], o.shape[1], o.shape[2]), taps=ksz, pad=pad)
+        d_wtp = K.conv_wgrad_presplit(du_split, o_split, (o.shape[0], o.shape[1], o.shape[2]), taps=ksz, stride=s, pad=pad)
         d_bt = _zero_bias(d_out, du.shape[-1])
     if d_wtp is None:
         d_wtp, d_bt = K.conv_wgrad(du, o, taps=ksz, stride=s, pad=pad, want_bias=frozen, precision=prec)

@@ -250,20 +250,24 @@ def bf16_split(x):
     return torch.stack([(hb >> 16).to(torch.int16), (mb >> 16).to(torch.int16)]).view(torch.bfloat16)
 
 
-def conv_wgrad_presplit(dy_split, x_split, shape, *, taps=1, pad=0):
-    """Weight gradient from pre-split operands (bf16 [2, rows, C] each); shape = (nb, t, v).  -> dw [cout, taps, cin], or None when
-    the kernel does not cover the channel counts (call conv_wgrad on the fp32 tensors then)."""
-    nb, t, v = shape
+def conv_wgrad_presplit(dy_split, x_split, shape, *, taps=1, stride=1, pad=0):
+    """Weight gradient from pre-split operands (bf16 [2, rows, C] each); shape = (nb, t_in, v) of the convolution's input.
+    -> dw [cout, taps, cin], or None when the kernel does not cover the channel counts (call conv_wgrad on the fp32 tensors then)."""
+    nb, t_in, v = shape
+    t_out = (t_in + 2 * pad - taps) // stride + 1
     cout, cin = dy_split.shape[-1], x_split.shape[-1]
-    if cin % 64 or cout % 64 or 2 * pad + 1 != taps:
+    if cin % 64 or cout % 64:
         return None
+    if dy_split.shape[1] != nb * t_out * v or x_split.shape[1] != nb * t_in * v:
+        raise RuntimeError("conv_wgrad_presplit: operand rows do not match the shape")
     _check_bf16(dy_split, x_split)
     L = capi.lib()
-    ws_bytes = L.agcn_conv_wgrad_workspace_bytes(nb, t, t, v, cin, cout, taps)
+    ws_bytes = L.agcn_conv_wgrad_workspace_bytes(nb, t_in, t_out, v, cin, cout, taps)
     ws = torch.empty((ws_bytes + 3) // 4, device=x_split.device, dtype=torch.float32)
     dw = torch.empty((cout, taps, cin), device=x_split.device, dtype=torch.float32)
-    _call("agcn_conv_wgrad_presplit", _ptr(dy_split), _ptr(x_split), _ptr(dw), nb, t, v, cin, cout, taps, pad, _ptr(ws), ws_bytes, _stream(),
-          sig=(nb, t, t, v, cin, cout, taps, 1), work=(2.0 * nb * t * v * cin * cout * taps, 4.0 * nb * t * v * (cin + cout)),
+    _call("agcn_conv_wgrad_presplit", _ptr(dy_split), _ptr(x_split), _ptr(dw), nb, t_in, t_out, v, cin, cout, taps, stride, pad,
+          _ptr(ws), ws_bytes, _stream(),
+          sig=(nb, t_in, t_out, v, cin, cout, taps, stride), work=(2.0 * nb * t_out * v * cin * cout * taps, 4.0 * nb * v * (t_in * cin + t_out * cout)),
           alias="agcn_conv_wgrad")
     return dw
 

@@ -120,14 +120,14 @@ int agcn_conv_wgrad(const float* dy, const float* x, float* dw, float* dbias,
                     int taps, int stride, int pad,
                     void* workspace, size_t workspace_bytes, int precision, void* stream);
 
-/* The same weight gradient (stride 1, t_in == t_out, no bias gradient) from operands that ARRIVE split into the bf16 pieces the
- * parity modes multiply: dy_split [2][nb*t*v][cout], x_split [2][nb*t*v][cin] bf16, plane 0 = h = bf16(value), plane 1 =
+/* The same weight gradient (no bias gradient) from operands that ARRIVE split into the bf16 pieces the
+ * parity modes multiply: dy_split [2][nb*t_out*v][cout], x_split [2][nb*t_in*v][cin] bf16, plane 0 = h = bf16(value), plane 1 =
  * m = bf16(value - h) -- written by agcn_bn_apply_mask_split / agcn_bn_bwd_bits_split, the kernels that produce the activations
  * and their gradients anyway.  The in-kernel conversion of agcn_conv_wgrad is what bounds it (shared-memory bandwidth); without
  * it the kernel runs at the tensor rate of three bf16 MMAs.  Same workspace as agcn_conv_wgrad.  Returns AGCN_ERR_UNSUPPORTED
  * (no error string) unless cin and cout are multiples of 64.                                                                   */
 int agcn_conv_wgrad_presplit(const void* dy_split, const void* x_split, float* dw,
-                             int nb, int t, int v, int cin, int cout, int taps, int pad,
+                             int nb, int t_in, int t_out, int v, int cin, int cout, int taps, int stride, int pad,
                              void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- joint x joint products (the V x V attention) --------------------------------------------------

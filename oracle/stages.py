@@ -224,15 +224,16 @@ def bf16_split(x):
     return torch.stack([(hb >> 16).to(torch.int16), (mb >> 16).to(torch.int16)]).view(torch.bfloat16)
 
 
-def conv_wgrad_presplit(dy_split, x_split, shape, *, taps=1, pad=0):
-    nb, t, v = shape
+def conv_wgrad_presplit(dy_split, x_split, shape, *, taps=1, stride=1, pad=0):
+    nb, t_in, v = shape
+    t_out = (t_in + 2 * pad - taps) // stride + 1
     cout, cin = dy_split.shape[-1], x_split.shape[-1]
-    if cin % 64 or cout % 64 or 2 * pad + 1 != taps:
+    if cin % 64 or cout % 64:
         return None
     wide = torch.float32 if dy_split.dtype == torch.bfloat16 else dy_split.dtype
-    dy = (dy_split[0].to(wide) + dy_split[1].to(wide)).reshape(nb, t, v, cout)
-    x = (x_split[0].to(wide) + x_split[1].to(wide)).reshape(nb, t, v, cin)
-    return conv_wgrad(dy, x, taps=taps, stride=1, pad=pad, want_bias=False)[0]
+    dy = (dy_split[0].to(wide) + dy_split[1].to(wide)).reshape(nb, t_out, v, cout)
+    x = (x_split[0].to(wide) + x_split[1].to(wide)).reshape(nb, t_in, v, cin)
+    return conv_wgrad(dy, x, taps=taps, stride=stride, pad=pad, want_bias=False)[0]
 
 
 def bn_apply(y, scale, shift, *, res_mode=RES_NONE, res=None, scale2=None, shift2=None, relu=False, rowmap=None, out=None,

@@ -95,23 +95,26 @@ def test_batchnorm_kernels_also_write_bf16_pieces(K, rows, c):
     assert torch.equal(d1[3].view(torch.int16), K.bf16_split(d0[0]).view(torch.int16))
 
 
-@pytest.mark.parametrize("nb,t,v,cin,cout,taps", [(2, 40, 25, 64, 64, 9), (4, 150, 25, 256, 128, 9), (2, 31, 25, 192, 64, 1), (3, 20, 22, 128, 256, 9),
-                                                 (2, 12, 25, 64, 192, 1), (4, 150, 25, 256, 64, 9), (1, 7, 20, 96, 64, 1)])
-def test_weight_gradient_from_presplit_operands(K, nb, t, v, cin, cout, taps):
+@pytest.mark.parametrize("nb,t,v,cin,cout,taps,stride", [(2, 40, 25, 64, 64, 9, 1), (4, 150, 25, 256, 128, 9, 1), (2, 31, 25, 192, 64, 1, 1),
+                                                        (3, 20, 22, 128, 256, 9, 1), (2, 12, 25, 64, 192, 1, 1), (4, 150, 25, 256, 64, 9, 1),
+                                                        (1, 7, 20, 96, 64, 1, 1), (4, 150, 25, 128, 128, 9, 2), (2, 21, 25, 256, 256, 9, 2),
+                                                        (2, 16, 25, 128, 256, 1, 2)])
+def test_weight_gradient_from_presplit_operands(K, nb, t, v, cin, cout, taps, stride):
     """agcn_conv_wgrad_presplit: the operands arrive as the bf16 pieces (h, m) the parity modes multiply; the result is the one of
     agcn_conv_wgrad in those modes bit for bit (same pieces, same MMA order), and within their tolerance of the fp64 contraction."""
     pad = (taps - 1) // 2
-    x, dy = rnd(nb, t, v, cin).cuda(), rnd(nb, t, v, cout, seed=4).cuda()
+    t_out = (t + 2 * pad - taps) // stride + 1
+    x, dy = rnd(nb, t, v, cin).cuda(), rnd(nb, t_out, v, cout, seed=4).cuda()
     xs, dys = K.bf16_split(x), K.bf16_split(dy)
     assert xs.shape == (2, nb * t * v, cin) and xs.dtype == torch.bfloat16
     assert rel_err(xs[0].float() + xs[1].float(), x.reshape(-1, cin)) <= 2 ** -16
-    dw = K.conv_wgrad_presplit(dys, xs, (nb, t, v), taps=taps, pad=pad)
+    dw = K.conv_wgrad_presplit(dys, xs, (nb, t, v), taps=taps, stride=stride, pad=pad)
     if cin % 64 or cout % 64:
         assert dw is None
         return
-    want, _ = K.conv_wgrad(dy, x, taps=taps, pad=pad, want_bias=False, precision=K.PREC_FP32)
+    want, _ = K.conv_wgrad(dy, x, taps=taps, stride=stride, pad=pad, want_bias=False, precision=K.PREC_FP32)
     assert torch.equal(dw, want)
-    ref, _ = S.conv_wgrad(dy.double().cpu(), x.double().cpu(), taps=taps, pad=pad)
+    ref, _ = S.conv_wgrad(dy.double().cpu(), x.double().cpu(), taps=taps, stride=stride, pad=pad)
     assert rel_err(dw, ref) <= 4e-5
 
 
