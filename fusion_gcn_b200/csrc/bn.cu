@@ -730,12 +730,13 @@ extern "C" AGCN_API int agcn_bn_apply_pool(const float* y, const float* scale, c
 
 extern "C" AGCN_API int agcn_bn_bwd_pool(const float* dpooled, const unsigned* mask_bits, const float* y,
                                          const float* save_mean, const float* save_invstd, const float* gamma,
-                                         float* dy, float* dgamma, float* dbeta, float* dres, int dres_accumulate,
+                                         float* dy, void* dy_split, float* dgamma, float* dbeta, float* dres, int dres_accumulate,
                                          int groups, int rows_per_group, int channels, void* workspace, size_t workspace_bytes, void* stream) {
     AGCN_REQUIRE(mask_bits && dpooled, AGCN_ERR_NULL, "agcn_bn_bwd_pool: null pointer");
     AGCN_REQUIRE(groups > 0 && rows_per_group > 0, AGCN_ERR_BAD_SHAPE, "agcn_bn_bwd_pool: bad shape");
     return bn_bwd_impl(dpooled, nullptr, mask_bits, y, save_mean, save_invstd, gamma, dy, dgamma, dbeta, dres, dres_accumulate,
-                       1, groups * rows_per_group, 0, channels, workspace, workspace_bytes, stream, rows_per_group);
+                       1, groups * rows_per_group, 0, channels, workspace, workspace_bytes, stream, rows_per_group, 0,
+                       static_cast<unsigned short*>(dy_split));
 }
 
 extern "C" AGCN_API int agcn_pool_fwd(const float* x, float* out, int groups, int rows_per_group, int channels, void* stream) {

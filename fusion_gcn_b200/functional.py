@@ -250,7 +250,7 @@ def tcn_forward(o, x_res, wt, bt, bn_w, bn_b, wr, br, rbn_w, rbn_b, spec: UnitSp
     else:
         out, out_bits = apply(u, sc, sh, relu=spec.relu_out)
     if ctx is not None:
-        ctx.update(t_o=o.detach(), t_x=x_res, u=u, ur=ur, out=None if pool else out.detach(), out_bits=out_bits, t_mean=mean, t_invstd=invstd,
+        ctx.update(t_o=o.detach(), t_o_shape=tuple(o.shape), t_x=x_res, u=u, ur=ur, out=None if pool else out.detach(), out_bits=out_bits, t_mean=mean, t_invstd=invstd,
                    t_mean2=mean2, t_invstd2=invstd2, wtp=wtp, wrp=wrp, pad=pad, pool_rows=(u.numel() // u.shape[-1] // pool) if pool else 0)
     return out
 
@@ -258,6 +258,7 @@ def tcn_forward(o, x_res, wt, bt, bn_w, bn_b, wr, br, rbn_w, rbn_b, spec: UnitSp
 def tcn_backward(d_out, ctx, bn_w, rbn_w, spec: UnitSpec, need_dres=True, need_do=True):
     """Returns (d_o, d_xres, grads)."""
     o, x_res, u, out = ctx["t_o"], ctx["t_x"], ctx["u"], ctx["out"]
+    o_shape = ctx["t_o_shape"]              # (`o` itself is released when its bf16 pieces serve the weight gradient, see UnitFn.forward)
     s, pad, prec = spec.stride, ctx["pad"], spec.precision
     ksz = spec.kernel_size
     mask = out if spec.relu_out else None
@@ -268,8 +269,8 @@ def tcn_backward(d_out, ctx, bn_w, rbn_w, spec: UnitSpec, need_dres=True, need_d
     frozen = not spec.training          # eval mode with gradients, see gcn_backward
     pk["frozen"] = frozen
     # weight gradient of the temporal convolution from split operands: `o` as bf16 pieces from the gcn half's normalise pass, `du` as
-    # bf16 pieces from the BatchNorm backward below (bit-mask form only; the pooled tail of the last unit keeps the fp32 path)
-    o_split = ctx.get("o_split") if (not frozen and bits is not None and not ctx.get("pool_rows")) else None
+    # bf16 pieces from the BatchNorm backward below (bit-mask forms only)
+    o_split = ctx.get("o_split") if (not frozen and bits is not None) else None
     du_split = None
     if o_split is not None:
         pk["want_split"] = True
@@ -293,7 +294,7 @@ def tcn_backward(d_out, ctx, bn_w, rbn_w, spec: UnitSpec, need_dres=True, need_d
         du_split = sp[0] if sp else None
     d_wtp = None
     if du_split is not None and o_split is not None:
-        d_wtp = K.conv_wgrad_presplit(du_split, o_split, (o.shape[0], o.shape[1], o.shape[2]), taps=ksz, stride=s, pad=pad)
+        d_wtp = K.conv_wgrad_presplit(du_split, o_split, o_shape[:3], taps=ksz, stride=s, pad=pad)
         d_bt = _zero_bias(d_out, du.shape[-1])
     if d_wtp is None:
         d_wtp, d_bt = K.conv_wgrad(du, o, taps=ksz, stride=s, pad=pad, want_bias=frozen, precision=prec)
@@ -301,7 +302,7 @@ def tcn_backward(d_out, ctx, bn_w, rbn_w, spec: UnitSpec, need_dres=True, need_d
             d_bt = _zero_bias(d_out, d_wtp.shape[0])
     d_o = None
     if need_do:
-        d_o = K.conv_fwd(du, _t(ctx["wtp"]), t_out=o.shape[1], stride=s, pad=pad, transposed=True, precision=prec)
+        d_o = K.conv_fwd(du, _t(ctx["wtp"]), t_out=o_shape[1], stride=s, pad=pad, transposed=True, precision=prec)
     grads = dict(wt=d_wtp.permute(0, 2, 1).unsqueeze(-1), bt=d_bt, bn_w=dgam, bn_b=dbet, wr=d_wr, br=d_br, rbn_w=dgam2, rbn_b=dbet2)
     return d_o, d_xres, grads
 
@@ -400,6 +401,11 @@ class UnitFn(torch.autograd.Function):
         gp, tp = params[:GCN_NPARAMS], params[GCN_NPARAMS:]
         o = gcn_forward(x, *_split_gcn(gp), spec, store)
         out = tcn_forward(o, x if spec.residual != "none" else None, *tp, spec, store)
+        if store is not None and store.get("o_split") is not None and store.get("o_bits") is not None and store.get("out_bits") is not None:
+            # the backward reads `o` only as the ReLU mask (one bit per element) and as the weight-gradient operand (bf16 pieces):
+            # the fp32 copy is not kept, so the split operand costs no activation memory
+            store["o"] = None
+            store["t_o"] = None
         ctx.spec, ctx.store, ctx.params = spec, store, params
         return out
 

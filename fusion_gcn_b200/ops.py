@@ -438,12 +438,13 @@ def bn_bwd(dout, mask_out, y, save_mean, save_invstd, gamma, *, want_dy=True, dy
     if pool_rows:
         # ``dout`` is the gradient of the fused mean pool, [groups, c], broadcast over the pool_rows rows of each group
         _check(dout, y, dy, dres)
+        dy_split = torch.empty((2, inner, c), device=y.device, dtype=torch.bfloat16) if (want_split and dy is not None and c % 64 == 0) else None
         _call("agcn_bn_bwd_pool", dout.data_ptr(), mask_bits.data_ptr(), y.data_ptr(), _ptr(save_mean), _ptr(save_invstd), _ptr(gamma),
-              _ptr(dy), dgb[0].data_ptr(), dgb[1].data_ptr(), _ptr(dres), int(dres_accumulate), dout.shape[0], int(pool_rows), c,
+              _ptr(dy), _ptr(dy_split), dgb[0].data_ptr(), dgb[1].data_ptr(), _ptr(dres), int(dres_accumulate), dout.shape[0], int(pool_rows), c,
               _ptr(ws), nbytes, _stream(), sig=(dout.shape[0], int(pool_rows), c, int(dy is not None), int(dres is not None)),
               work=(0.0, 4.0 * inner * c * (2 + 2.0 / 32 + int(dy is not None) + int(dres is not None) * (1 + int(dres_accumulate)))),
               alias="agcn_bn_bwd")
-        return (dy, dgb[0], dgb[1], None) if want_split else (dy, dgb[0], dgb[1])
+        return (dy, dgb[0], dgb[1], dy_split) if want_split else (dy, dgb[0], dgb[1])
     if mask_bits is not None:
         if mask_bits.dtype != torch.int32 or not mask_bits.is_cuda:
             raise RuntimeError("bn_bwd: mask_bits must be the int32 CUDA tensor returned by bn_apply(want_mask=True)")

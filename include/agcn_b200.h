@@ -259,7 +259,8 @@ int agcn_bn_apply_pool(const float* y, const float* scale, const float* shift,
                        void* workspace, size_t workspace_bytes, void* stream);
 int agcn_bn_bwd_pool(const float* dpooled, const unsigned* mask_bits, const float* y,
                      const float* save_mean, const float* save_invstd, const float* gamma,
-                     float* dy, float* dgamma, float* dbeta, float* dres, int dres_accumulate,
+                     float* dy, void* dy_split /* NULL, or dy once more as bf16 pieces, see agcn_bn_bwd_bits_split */,
+                     float* dgamma, float* dbeta, float* dres, int dres_accumulate,
                      int groups, int rows_per_group, int channels, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- classifier head fused with its loss -------------------------------------------------------------

@@ -264,7 +264,7 @@ def bn_bwd(dout, mask_out, y, save_mean, save_invstd, gamma, *, want_dy=True, dy
     if want_split:
         dy, dgamma, dbeta = bn_bwd(dout, mask_out, y, save_mean, save_invstd, gamma, want_dy=want_dy, dy=dy, dres=dres, dres_accumulate=dres_accumulate,
                                    rowmap=rowmap, mask_bits=mask_bits, pool_rows=pool_rows, frozen=frozen)
-        ok = dy is not None and mask_bits is not None and not pool_rows and rowmap is None and dy.shape[-1] % 64 == 0
+        ok = dy is not None and mask_bits is not None and rowmap is None and dy.shape[-1] % 64 == 0
         return dy, dgamma, dbeta, (bf16_split(dy) if ok else None)
     if pool_rows:          # dout is the pooled gradient [groups, c]: broadcast over the rows of each group, divided by their number
         groups, c = dout.shape
