@@ -105,12 +105,13 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_model(workload, precision, device):
+def build_model(workload, precision, device, recompute=False):
     from fusion_gcn_b200 import modules as M
     m, t, v, c, ncls, gk = WORKLOADS[workload]
     torch.manual_seed(1)
     model = M.Model((m, t, v, c), ncls, make_graph(gk))
     M.set_precision(model, precision)
+    M.set_recompute(model, recompute)
     return model.to(device).train()
 
 
@@ -134,7 +135,7 @@ def run_ours(args):
         n_local = args.batch // world         # strong scaling: the GLOBAL batch is fixed (BASELINE configs[1]: N=64 sharded 32/16/8 per GPU)
     else:
         n_local = args.batch                  # weak scaling: fixed per-GPU batch
-    model = build_model(args.workload, args.precision, dev)
+    model = build_model(args.workload, args.precision, dev, recompute=args.recompute)
     reducer = GradientAllReducer(model.parameters()) if world > 1 else None
     gen = torch.Generator().manual_seed(1234 + rank)
     x_host = torch.randn(n_local, m, t, v, c, generator=gen).pin_memory()
@@ -367,7 +368,10 @@ def run_ours(args):
                                f"{ncls} classes, train mode, fwd+CE+bwd, random init", "precision_mode": args.precision,
                    "l2_policy": "activations per step (GBs) exceed the 126 MB L2; no explicit flush",
                    "parallelism": f"dp{world} (batch shards, NCCL gradient all-reduce)" if world > 1 else "single GPU",
-                   "launch_mode": "one CUDA graph per step (fusion_gcn_b200.graphed.GraphedStep)" if graph_ok else "eager launches"},
+                   "launch_mode": "one CUDA graph per step (fusion_gcn_b200.graphed.GraphedStep)" if graph_ok else "eager launches",
+                   "activation_policy": "theta/phi and the aggregated tensor recomputed in the backward (--recompute)" if args.recompute
+                                        else "all activations kept"},
+        "peak_memory_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2),
         "e2e": {"value": round(e2e_value, 2), "unit": "sequences/s", "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8,
                 "d2h_bytes_per_step": 4, "ms_per_step": round(ms_head_e2e / args.steps, 3), "last_loss": round(loss_val, 5)},
         "gpu_launches": int(launches),
@@ -602,6 +606,7 @@ def main():
                     help="weak: --batch sequences per GPU (default); strong: --batch sequences in total, sharded over the GPUs")
     ap.add_argument("--no-strong", action="store_true", help="N > 1, weak scaling: skip the extra strong-scaling timing (global batch = --batch)")
     ap.add_argument("--dump-kernels", default=None, help="write the per-signature timing table (all C-ABI launches) to this JSON file")
+    ap.add_argument("--recompute", action="store_true", help="activation-recompute policy (modules.set_recompute): less memory, two more launches per unit")
     ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay timing")
     ap.add_argument("--no-tf32", action="store_true", help="skip the extra TF32-mode timing that the fp32 run reports beside the headline")
     args = ap.parse_args()

@@ -97,39 +97,68 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const float* x, const f
     } else if (mean != nullptr) {
         mu = *reinterpret_cast<const float4*>(mean + q * 4);       // MODE 0: the pivot of the shifted sums
     }
-    for (long long r = r0 + rl; r < r1; r += lanes_r) {
-        const long long off = m.row_offset(r) + q * 4;
+    // U rows per trip with every load issued before the first dependent add: 592 CTAs x 256 threads with one 16-byte load each in
+    // flight cover only ~2.4 MB, a third of what the HBM latency-bandwidth product needs (the plain loop measured 3.2 TB/s, r8_stage);
+    // the additions keep their row order, so the sums are bit-identical to the rolled loop's
+    constexpr int U = MODE == 0 ? 4 : 2;
+    auto body = [&](const float4& v_in, float4 g, unsigned nib, const float4& k, bool has_k) {
         if (MODE == 0) {
-            float4 v = __ldg(reinterpret_cast<const float4*>(x + off));
+            float4 v = v_in;
             v.x -= mu.x; v.y -= mu.y; v.z -= mu.z; v.w -= mu.w;
             s0.x += v.x; s0.y += v.y; s0.z += v.z; s0.w += v.w;
             s1.x = fmaf(v.x, v.x, s1.x); s1.y = fmaf(v.y, v.y, s1.y); s1.z = fmaf(v.z, v.z, s1.z); s1.w = fmaf(v.w, v.w, s1.w);
         } else {
-            float4 g;
-            if (bcast_rows > 0) {
-                g = __ldg(reinterpret_cast<const float4*>(dout + (r / bcast_rows) * m.channels + q * 4));
-                g.x *= bcast_scale; g.y *= bcast_scale; g.z *= bcast_scale; g.w *= bcast_scale;
-            } else {
-                g = __ldg(reinterpret_cast<const float4*>(dout + off));
-            }
+            if (bcast_rows > 0) { g.x *= bcast_scale; g.y *= bcast_scale; g.z *= bcast_scale; g.w *= bcast_scale; }
             if (mask_bits != nullptr) {
-                const unsigned nib = mask_nibble(mask_bits, off);
                 if (!(nib & 1u)) g.x = 0.f;
                 if (!(nib & 2u)) g.y = 0.f;
                 if (!(nib & 4u)) g.z = 0.f;
                 if (!(nib & 8u)) g.w = 0.f;
-            } else if (mask != nullptr) {
-                float4 k = __ldg(reinterpret_cast<const float4*>(mask + off));
+            } else if (has_k) {
                 if (!(k.x > 0.f)) g.x = 0.f;
                 if (!(k.y > 0.f)) g.y = 0.f;
                 if (!(k.z > 0.f)) g.z = 0.f;
                 if (!(k.w > 0.f)) g.w = 0.f;
             }
-            float4 v = __ldg(reinterpret_cast<const float4*>(x + off));
+            const float4& v = v_in;
             s0.x += g.x; s0.y += g.y; s0.z += g.z; s0.w += g.w;
             s1.x = fmaf(g.x, (v.x - mu.x) * is.x, s1.x); s1.y = fmaf(g.y, (v.y - mu.y) * is.y, s1.y);
             s1.z = fmaf(g.z, (v.z - mu.z) * is.z, s1.z); s1.w = fmaf(g.w, (v.w - mu.w) * is.w, s1.w);
         }
+    };
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    long long r = r0 + rl;
+    for (; r + (long long)(U - 1) * lanes_r < r1; r += (long long)U * lanes_r) {
+        float4 v[U], g[U], k[U];
+        unsigned nib[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long ru = r + (long long)u * lanes_r;
+            const long long off = m.row_offset(ru) + q * 4;
+            v[u] = __ldg(reinterpret_cast<const float4*>(x + off));
+            g[u] = zero4; k[u] = zero4; nib[u] = 0u;
+            if (MODE == 1) {
+                g[u] = bcast_rows > 0 ? __ldg(reinterpret_cast<const float4*>(dout + (ru / bcast_rows) * m.channels + q * 4))
+                                      : __ldg(reinterpret_cast<const float4*>(dout + off));
+                if (mask_bits != nullptr) nib[u] = mask_nibble(mask_bits, off);
+                else if (mask != nullptr) k[u] = __ldg(reinterpret_cast<const float4*>(mask + off));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) body(v[u], g[u], nib[u], k[u], mask != nullptr);
+    }
+    for (; r < r1; r += lanes_r) {
+        const long long off = m.row_offset(r) + q * 4;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + off));
+        float4 g = zero4, k = zero4;
+        unsigned nib = 0u;
+        if (MODE == 1) {
+            g = bcast_rows > 0 ? __ldg(reinterpret_cast<const float4*>(dout + (r / bcast_rows) * m.channels + q * 4))
+                               : __ldg(reinterpret_cast<const float4*>(dout + off));
+            if (mask_bits != nullptr) nib = mask_nibble(mask_bits, off);
+            else if (mask != nullptr) k = __ldg(reinterpret_cast<const float4*>(mask + off));
+        }
+        body(v, g, nib, k, mask != nullptr);
     }
     float4* a = reinterpret_cast<float4*>(smv);
     a[(0 * lanes_r + rl) * cq + q] = s0;

@@ -46,6 +46,7 @@ class UnitSpec:
     bn_res: Optional[BnBuffers] = None
     attention_out: Optional[List[torch.Tensor]] = field(default=None)   # receives adj_c (3 x [nb,V,V], detached)
     pool_groups: int = 0            # > 0 (last unit of Model): return the mean-pooled [pool_groups, cout] instead of the feature map
+    recompute: bool = False         # do not keep theta / phi (e) and the aggregated tensor (z) for the backward; run their kernels again there
 
 
 def _bn_forward(y, gamma, beta, buf: BnBuffers, training: bool):
@@ -145,8 +146,11 @@ def gcn_forward(x, adj_a, adj_b, wa, ba, wb, bb, wd, bd, bn_w, bn_b, down_w, dow
     if spec.attention_out is not None:
         spec.attention_out[:] = [p[:, k] for k in range(3)]
     if ctx is not None:
-        ctx.update(x=x, e=e, p=p, g=g, z=z, y=y, yd=yd, o=o.detach(), o_bits=o_bits, o_split=o_split, mean=mean, invstd=invstd, mean2=mean2, invstd2=invstd2,
-                   wab=wab, wdc=wdc, nchunk=nchunk, scale=scale, ci=ci)
+        # recompute policy: e (1.5 cout wide) and z (3 cin wide) are more than half of what a unit saves, and each is
+        # ONE deterministic kernel away from x (and g) -- the backward runs those two kernels again and gets the same bits
+        keep = not spec.recompute
+        ctx.update(x=x, e=e if keep else None, p=p, g=g, z=z if keep else None, y=y, yd=yd, o=o.detach(), o_bits=o_bits, o_split=o_split,
+                   mean=mean, invstd=invstd, mean2=mean2, invstd2=invstd2, wab=wab, bab=bab, wdc=wdc, nchunk=nchunk, scale=scale, ci=ci)
     return o
 
 
@@ -160,6 +164,8 @@ def gcn_backward(d_o, ctx, bn_w, dbn_w, down_w, spec: UnitSpec, dx=None, need_dx
     # eval mode with gradients (frozen-BN fine-tuning, saliency): the BatchNorms are affine maps of constants, and the biases of the
     # convolutions in front of them get real gradients (the column sums of dy) instead of the training mode's analytic zeros
     frozen = not spec.training
+    if z is None:
+        z = K.joint_mix(x, g, width=cin, mode=K.MIX_AGG_FWD, precision=prec)
     if spec.has_down:
         dy, dgam, dbet = K.bn_bwd(d_o, o, y, ctx["mean"], ctx["invstd"], bn_w, mask_bits=ctx["o_bits"], frozen=frozen)
         dyd, dgam2, dbet2 = K.bn_bwd(d_o, o, ctx["yd"], ctx["mean2"], ctx["invstd2"], dbn_w, mask_bits=ctx["o_bits"], frozen=frozen)
@@ -178,6 +184,7 @@ def gcn_backward(d_o, ctx, bn_w, dbn_w, down_w, spec: UnitSpec, dx=None, need_dx
         have = have or need_dx
         dgam2 = dbet2 = d_down_w = d_down_b = None
     d_wdc, d_bdc = K.conv_wgrad(dy, z, want_bias=frozen, precision=prec)
+    del z
     if not frozen:
         d_bdc = _zero_bias(x, cout)
     dz = K.conv_fwd(dy, _t(ctx["wdc"]), precision=prec)                                # [nb,t,v,3*cin]
@@ -188,6 +195,8 @@ def gcn_backward(d_o, ctx, bn_w, dbn_w, down_w, spec: UnitSpec, dx=None, need_dx
         dx = K.joint_mix(dz, g, width=cin, mode=K.MIX_AGG_BWD, out=dx, accumulate=have, precision=prec)
         have = True
     # d theta / d phi, and their column sums (= the bias gradients) out of the same epilogue where the kernel covers the shape
+    if e is None:
+        e = K.conv_fwd(x, ctx["wab"], ctx["bab"], precision=prec)
     de, d_bab = K.joint_mix_score_bwd(e, ds, width=ci, precision=prec)
     d_wab, d_bab2 = K.conv_wgrad(de, x, want_bias=d_bab is None, precision=prec)
     if d_bab is None:

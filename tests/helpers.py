@@ -107,3 +107,26 @@ def eval_mode_gradient_case(M, G, device, tol):
     model(to_t(g["x"]).to(device))                                                                 # no_grad-free eval forward still works
     with torch.no_grad():
         assert rel_err(model(to_t(g["x"]).to(device)), y64) <= tol
+
+
+def recompute_case(M, G, device, cin=8, cout=16, stride=2, v=25, t=12, nb=3):
+    """One unit run twice from the same state, once keeping and once recomputing theta / phi and the aggregated tensor: output, dx and
+    every parameter gradient must be IDENTICAL (the recomputation runs the same deterministic kernels on the same inputs)."""
+    import copy
+    torch.manual_seed(5)
+    unit = M.SpatialTemporalConv(cin, cout, G.partition_adjacency(G.NTU_EDGES if v == 25 else G.UTD_EDGES), stride=stride).to(device).train()
+    twin = M.set_recompute(copy.deepcopy(unit), True)
+    assert twin.gcn1._agcn_recompute and twin._agcn_recompute and not unit._agcn_recompute
+    x = torch.randn(nb, cin, t, v, device=device)
+    w = torch.randn(nb, cout, (t - 1) // stride + 1, v, device=device)
+    outs = []
+    for mod in (unit, twin):
+        xi = x.clone().requires_grad_(True)
+        y = mod(xi)
+        (y * w).sum().backward()
+        outs.append((y.detach(), xi.grad, {k: p.grad for k, p in mod.named_parameters()}))
+    (y0, dx0, g0), (y1, dx1, g1) = outs
+    assert torch.equal(y0, y1) and torch.equal(dx0, dx1)
+    for k in g0:
+        assert torch.equal(g0[k], g1[k]), k
+

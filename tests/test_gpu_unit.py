@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import (ZERO_GRAD, MODEL_FIXTURES, RESIDUAL_KINDS, UNIT_FIXTURES, check_grads, eval_mode_gradient_case, load_golden, rel_err, stat_err,
+from helpers import (ZERO_GRAD, MODEL_FIXTURES, RESIDUAL_KINDS, UNIT_FIXTURES, check_grads, eval_mode_gradient_case, load_golden, recompute_case, rel_err, stat_err,
                      sub, to_t)
 from oracle import agcn_oracle as O
 
@@ -273,3 +273,27 @@ def test_eval_mode_gradients(pkg):
     from fusion_gcn_b200 import graph as G
     from fusion_gcn_b200 import modules as M
     eval_mode_gradient_case(M, G, "cuda", 1e-4)
+
+
+@pytest.mark.gpu
+def test_recompute_policy(pkg):
+    """set_recompute: theta / phi and the aggregated tensor are produced again in the backward -- bit-identical results at a
+    BASELINE width, and a smaller activation store."""
+    from fusion_gcn_b200 import graph as G
+    from fusion_gcn_b200 import modules as M
+    recompute_case(M, G, "cuda", cin=64, cout=64, stride=1, t=40, nb=4)
+    recompute_case(M, G, "cuda", cin=64, cout=128, stride=2, t=40, nb=4)
+    unit = M.SpatialTemporalConv(64, 64, G.partition_adjacency(G.NTU_EDGES)).cuda().train()
+    x = torch.randn(8, 64, 100, 25, device="cuda")
+    held = []
+    for flag in (False, True):
+        M.set_recompute(unit, flag)
+        torch.cuda.synchronize()
+        base = torch.cuda.memory_allocated()
+        y = unit(x.clone().requires_grad_(True))
+        torch.cuda.synchronize()
+        held.append(torch.cuda.memory_allocated() - base)
+        y.sum().backward()
+        del y
+    plane = 8 * 64 * 100 * 25 * 4
+    assert held[0] - held[1] >= 4 * plane, held          # e (1.5 planes) + z (3 planes)

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import (MODEL_FIXTURES, RESIDUAL_KINDS, UNIT_FIXTURES, check_grads, eval_mode_gradient_case, load_golden, rel_err, stat_err, sub,
+from helpers import (MODEL_FIXTURES, RESIDUAL_KINDS, UNIT_FIXTURES, check_grads, eval_mode_gradient_case, load_golden, recompute_case, rel_err, stat_err, sub,
                      to_t)
 from fusion_gcn_b200 import graph as G
 from fusion_gcn_b200 import modules as M
@@ -236,3 +236,8 @@ def test_wide_odd_channel_counts_are_zero_padded_for_the_first_unit(torch_stage_
 
 def test_eval_mode_gradients_match_the_oracle(torch_stage_backend):
     eval_mode_gradient_case(M, G, "cpu", 1e-4)
+
+
+
+def test_recompute_policy_gives_identical_gradients(torch_stage_backend):
+    recompute_case(M, G, "cpu")
