@@ -136,6 +136,9 @@ def run_ours(args):
     else:
         n_local = args.batch                  # weak scaling: fixed per-GPU batch
     model = build_model(args.workload, args.precision, dev, recompute=args.recompute)
+    if args.sync_bn and world > 1:
+        from fusion_gcn_b200 import modules as M_
+        M_.set_sync_batchnorm(model, True)     # statistics over all ranks: the sharded batch normalises like the unsharded one
     reducer = GradientAllReducer(model.parameters()) if world > 1 else None
     gen = torch.Generator().manual_seed(1234 + rank)
     x_host = torch.randn(n_local, m, t, v, c, generator=gen).pin_memory()
@@ -369,6 +372,7 @@ def run_ours(args):
                    "l2_policy": "activations per step (GBs) exceed the 126 MB L2; no explicit flush",
                    "parallelism": f"dp{world} (batch shards, NCCL gradient all-reduce)" if world > 1 else "single GPU",
                    "launch_mode": "one CUDA graph per step (fusion_gcn_b200.graphed.GraphedStep)" if graph_ok else "eager launches",
+                   "batchnorm": "synchronised over the ranks (--sync-bn)" if (args.sync_bn and world > 1) else "per-replica statistics",
                    "activation_policy": "theta/phi and the aggregated tensor recomputed in the backward (--recompute)" if args.recompute
                                         else "all activations kept"},
         "peak_memory_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2),
@@ -606,6 +610,7 @@ def main():
                     help="weak: --batch sequences per GPU (default); strong: --batch sequences in total, sharded over the GPUs")
     ap.add_argument("--no-strong", action="store_true", help="N > 1, weak scaling: skip the extra strong-scaling timing (global batch = --batch)")
     ap.add_argument("--dump-kernels", default=None, help="write the per-signature timing table (all C-ABI launches) to this JSON file")
+    ap.add_argument("--sync-bn", action="store_true", help="N > 1: synchronised BatchNorm (modules.set_sync_batchnorm), default per-replica statistics")
     ap.add_argument("--recompute", action="store_true", help="activation-recompute policy (modules.set_recompute): less memory, two more launches per unit")
     ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay timing")
     ap.add_argument("--no-tf32", action="store_true", help="skip the extra TF32-mode timing that the fp32 run reports beside the headline")

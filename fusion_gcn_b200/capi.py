@@ -58,6 +58,10 @@ SIGNATURES = {
     "agcn_bn_apply_pool_workspace_bytes": (_c_size_t, [_c_int, _c_int]),
     "agcn_bn_apply_pool": (_c_int, [_c_void_p] * 3 + [_c_int] + [_c_void_p] * 3 + [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_size_t, _c_void_p]),
     "agcn_bn_bwd_pool": (_c_int, [_c_void_p] * 11 + [_c_int, _c_int, _c_int, _c_int, _c_void_p, _c_size_t, _c_void_p]),
+    "agcn_bn_stats_partials_bytes": (_c_size_t, [_c_int]),
+    "agcn_bn_stats_partials": (_c_int, [_c_void_p, _c_int, _c_int, _c_ll, _c_int, _c_void_p, _c_size_t, _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
+    "agcn_bn_bwd_sync": (_c_int, [_c_void_p] * 12 + [_c_int, _c_int, _c_int, _c_ll, _c_int, _c_int, _c_int, _c_void_p, _c_double,
+                                  _c_void_p, _c_size_t, _c_void_p]),
     "agcn_linear_ce_fwd": (_c_int, [_c_void_p] * 8 + [_c_int] * 3 + [_c_void_p]),
     "agcn_linear_ce_bwd": (_c_int, [_c_void_p] * 7 + [_c_int] * 3 + [_c_void_p]),
     "agcn_node_mix": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p]),

@@ -666,7 +666,11 @@ static int bn_bwd_impl(const float* dout, const float* mask_out, const unsigned*
                        const float* save_mean, const float* save_invstd, const float* gamma,
                        float* dy, float* dgamma, float* dbeta, float* dres, int dres_accumulate,
                        int outer, int inner, long long outer_stride, int channels,
-                       void* workspace, size_t workspace_bytes, void* stream, int bcast_rows = 0, int frozen = 0, unsigned short* dy_split = nullptr) {
+                       void* workspace, size_t workspace_bytes, void* stream, int bcast_rows = 0, int frozen = 0, unsigned short* dy_split = nullptr,
+                       int phase = 0, const float* global_sums = nullptr, double global_rows = 0.0) {
+    // phase 0: the whole backward.  Synchronised BatchNorm (statistics over all ranks) splits it around the caller's all-reduce:
+    // phase 1 = column sums only (dbeta = sum g, dgamma = sum g xhat of THIS rank's rows), phase 2 = the apply pass from
+    // global_sums [2][C] = (sum g | sum g xhat) over all ranks and the global row count.
     int rc = check_map("agcn_bn_bwd", outer, inner, outer_stride, channels);
     if (rc) return rc;
     AGCN_REQUIRE(dout && y && save_mean && save_invstd && workspace, AGCN_ERR_NULL, "agcn_bn_bwd: null pointer");
@@ -681,12 +685,18 @@ static int bn_bwd_impl(const float* dout, const float* mask_out, const unsigned*
         AGCN_REQUIRE(agcn_bn_mask_words(outer, inner, channels) > 0 && vec_ok(m, {dout, y, dy, dres, workspace}), AGCN_ERR_UNSUPPORTED,
                      "agcn_bn_bwd_bits: layout not supported (agcn_bn_mask_words returned 0)");
     const float bcast_scale = bcast_rows > 0 ? 1.f / (float)bcast_rows : 1.f;
-    rc = launch_colsum<1>(y, dout, mask_out, save_mean, save_invstd, m, rows, part, P, s, mask_bits, bcast_rows, bcast_scale);
-    if (rc) return rc;
-    bn_bwd_finalize_kernel<<<ceil_div(channels, kFinCh), kFinCh * kFinLanes, 0, s>>>(part, P, channels, (double)rows, gamma, save_mean, save_invstd, dgamma, dbeta, coef, frozen);
+    if (phase == 2) {
+        AGCN_REQUIRE(global_sums && global_rows >= (double)rows, AGCN_ERR_NULL, "agcn_bn_bwd_sync: phase 2 needs the all-reduced sums and the global row count");
+        bn_bwd_finalize_kernel<<<ceil_div(channels, kFinCh), kFinCh * kFinLanes, 0, s>>>(global_sums, 1, channels, global_rows, gamma, save_mean, save_invstd,
+                                                                                         nullptr, nullptr, coef, frozen);
+    } else {
+        rc = launch_colsum<1>(y, dout, mask_out, save_mean, save_invstd, m, rows, part, P, s, mask_bits, bcast_rows, bcast_scale);
+        if (rc) return rc;
+        bn_bwd_finalize_kernel<<<ceil_div(channels, kFinCh), kFinCh * kFinLanes, 0, s>>>(part, P, channels, (double)rows, gamma, save_mean, save_invstd, dgamma, dbeta, coef, frozen);
+    }
     rc = check_launch("agcn_bn_bwd(finalize)");
     if (rc) return rc;
-    if (dy == nullptr && dres == nullptr) return AGCN_OK;
+    if (phase == 1 || (dy == nullptr && dres == nullptr)) return AGCN_OK;
     if (dy_split != nullptr)
         AGCN_REQUIRE(dy != nullptr && outer == 1 && aligned16(dy_split) && vec_ok(m, {dout, mask_out, y, dy, dres, coef}), AGCN_ERR_UNSUPPORTED,
                      "agcn_bn_bwd_bits_split: contiguous, vectorisable layout and a dy output required");
@@ -724,6 +734,65 @@ extern "C" AGCN_API int agcn_bn_bwd_bits_split(const float* dout, const unsigned
     AGCN_REQUIRE(mask_bits && dy && dy_split, AGCN_ERR_NULL, "agcn_bn_bwd_bits_split: null pointer");
     return bn_bwd_impl(dout, nullptr, mask_bits, y, save_mean, save_invstd, gamma, dy, dgamma, dbeta, dres, dres_accumulate,
                        1, inner, 0, channels, workspace, workspace_bytes, stream, 0, frozen_stats, static_cast<unsigned short*>(dy_split));
+}
+
+// ---- synchronised BatchNorm (statistics over all ranks of a data-parallel group; SURVEY 8e "optional SyncBN mode")
+// The collectives stay with the caller (torch.distributed / NCCL); the library provides the two halves either side of them.
+
+// part4 [P][4][C]: per row-partition p the shifted sum | shifted sum of squares | pivot | row count -- the layout agcn_bn_finalize merges
+// (the same one the convolution epilogue writes), so the partials of several ranks can simply be concatenated.
+__global__ void expand_partials_kernel(const float* part2, const float* x_first_row, int P, int C, long long rows, float* part4) {
+    const long long per = (rows + P - 1) / P;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < P * C; idx += gridDim.x * blockDim.x) {
+        const int p = idx / C, c = idx - p * C;
+        long long n = rows - (long long)p * per;
+        n = n < 0 ? 0 : (n > per ? per : n);
+        part4[((long long)p * 4 + 0) * C + c] = part2[((long long)p * 2 + 0) * C + c];
+        part4[((long long)p * 4 + 1) * C + c] = part2[((long long)p * 2 + 1) * C + c];
+        part4[((long long)p * 4 + 2) * C + c] = x_first_row[c];
+        part4[((long long)p * 4 + 3) * C + c] = (float)n;
+    }
+}
+
+extern "C" AGCN_API size_t agcn_bn_stats_partials_bytes(int channels) {
+    return channels > 0 ? (size_t)agcn::kMaxPartials * 4 * (size_t)channels * sizeof(float) : 0;
+}
+
+extern "C" AGCN_API int agcn_bn_stats_partials(const float* x, int outer, int inner, long long outer_stride, int channels,
+                                               float* part, size_t part_bytes, int* nparts,
+                                               void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_map("agcn_bn_stats_partials", outer, inner, outer_stride, channels);
+    if (rc) return rc;
+    AGCN_REQUIRE(x && part && nparts && workspace, AGCN_ERR_NULL, "agcn_bn_stats_partials: null pointer");
+    AGCN_REQUIRE(workspace_bytes >= agcn_bn_workspace_bytes(channels), AGCN_ERR_WORKSPACE, "agcn_bn_stats_partials: workspace too small");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    RowMap m{outer, inner, outer_stride, channels};
+    const long long rows = (long long)outer * inner;
+    const int P = num_partials(rows);
+    AGCN_REQUIRE(part_bytes >= (size_t)P * 4 * channels * sizeof(float), AGCN_ERR_WORKSPACE, "agcn_bn_stats_partials: partial buffer too small");
+    float* part2 = static_cast<float*>(workspace);
+    rc = launch_colsum<0>(x, nullptr, nullptr, x, nullptr, m, rows, part2, P, s);      // pivot = the first row of x
+    if (rc) return rc;
+    expand_partials_kernel<<<ceil_div(P * channels, 256), 256, 0, s>>>(part2, x, P, channels, rows, part);
+    *nparts = P;
+    return check_launch("agcn_bn_stats_partials");
+}
+
+// phase 1: dgamma / dbeta <- this rank's column sums (sum g xhat | sum g), nothing else is written.
+// phase 2: dy (dy_split, dres) from global_sums [2][C] = (sum g | sum g xhat) summed over all ranks and global_rows = the rows of all ranks.
+// mask_out / mask_bits / dy_split / pool_rows: the optional operands of agcn_bn_bwd, agcn_bn_bwd_bits(_split) and agcn_bn_bwd_pool.
+extern "C" AGCN_API int agcn_bn_bwd_sync(const float* dout, const float* mask_out, const unsigned* mask_bits, const float* y,
+                                         const float* save_mean, const float* save_invstd, const float* gamma,
+                                         float* dy, void* dy_split, float* dgamma, float* dbeta, float* dres, int dres_accumulate,
+                                         int outer, int inner, long long outer_stride, int channels, int pool_rows,
+                                         int phase, const float* global_sums, double global_rows,
+                                         void* workspace, size_t workspace_bytes, void* stream) {
+    AGCN_REQUIRE(phase == 1 || phase == 2, AGCN_ERR_UNSUPPORTED, "agcn_bn_bwd_sync: phase %d", phase);
+    AGCN_REQUIRE(phase == 2 || (dgamma && dbeta), AGCN_ERR_NULL, "agcn_bn_bwd_sync: phase 1 writes dgamma / dbeta");
+    AGCN_REQUIRE(pool_rows >= 0 && (pool_rows == 0 || (mask_bits && outer == 1 && inner % pool_rows == 0)), AGCN_ERR_BAD_SHAPE, "agcn_bn_bwd_sync: bad pooled shape");
+    return bn_bwd_impl(dout, mask_out, mask_bits, y, save_mean, save_invstd, gamma, dy, dgamma, dbeta, dres, dres_accumulate,
+                       outer, inner, outer_stride, channels, workspace, workspace_bytes, stream, pool_rows, 0,
+                       static_cast<unsigned short*>(dy_split), phase, global_sums, global_rows);
 }
 
 constexpr int kPoolParts = 8;

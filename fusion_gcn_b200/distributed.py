@@ -26,6 +26,32 @@ def shard_batch(n_global: int, rank: int, world: int):
     return rank * per, (rank + 1) * per
 
 
+class SyncBatchNorm:
+    """The collectives of a synchronised BatchNorm (``modules.set_sync_batchnorm``): training-mode statistics and their backward sums
+    over all ranks of ``group``, so that a batch sharded over R GPUs normalises exactly like the unsharded batch.  The
+    kernels produce MERGEABLE partials (shifted sums with their pivots and row counts, the layout the convolution epilogue writes
+    anyway), so the forward needs one all-gather of a few KB per BatchNorm and no second pass; the backward all-reduces the two
+    column sums between its sum pass and its apply pass.  Stream-ordered on NCCL: capturable in the step's CUDA graph."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+
+    def gather_partials(self, part: torch.Tensor) -> torch.Tensor:
+        """[nparts, 4, c] of this rank -> [world * nparts, 4, c] of all ranks (every rank runs the same shapes)."""
+        if self.world == 1:
+            return part
+        part = part.contiguous()
+        out = part.new_empty((self.world * part.shape[0],) + tuple(part.shape[1:]))
+        dist.all_gather_into_tensor(out, part, group=self.group)       # concatenation along dim 0, rank order
+        return out
+
+    def all_reduce(self, t: torch.Tensor) -> torch.Tensor:
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+
 class _Bucket:
     def __init__(self, params: List[torch.nn.Parameter]):
         self.params = params

@@ -46,15 +46,24 @@ class UnitSpec:
     bn_res: Optional[BnBuffers] = None
     attention_out: Optional[List[torch.Tensor]] = field(default=None)   # receives adj_c (3 x [nb,V,V], detached)
     pool_groups: int = 0            # > 0 (last unit of Model): return the mean-pooled [pool_groups, cout] instead of the feature map
+    sync: Optional[object] = None   # distributed.SyncBatchNorm: training-mode BatchNorm statistics over all ranks of its group
     recompute: bool = False         # do not keep theta / phi (e) and the aggregated tensor (z) for the backward; run their kernels again there
 
 
-def _bn_forward(y, gamma, beta, buf: BnBuffers, training: bool):
-    return K.bn_stats(y, gamma, beta, buf.running_mean, buf.running_var, buf.num_batches_tracked,
-                      BN_MOMENTUM, BN_EPS, training)
+def _bn_forward(y, gamma, beta, buf: BnBuffers, training: bool, sync=None, rowmap=None, nbt=True):
+    """-> scale, shift, save_mean, save_invstd.  ``sync`` (training mode): the statistics are taken over the rows of ALL ranks -- every
+    rank's mergeable partials are all-gathered and finalised with the global row count (synchronised BatchNorm)."""
+    tracked = buf.num_batches_tracked if nbt else None
+    if training and sync is not None:
+        part = K.bn_stats_partials(y, rowmap=rowmap)
+        rows = (rowmap[0] * rowmap[1]) if rowmap is not None else y.numel() // y.shape[-1]
+        return K.bn_finalize(sync.gather_partials(part), rows * sync.world, gamma, beta, buf.running_mean, buf.running_var, tracked,
+                             BN_MOMENTUM, BN_EPS)
+    return K.bn_stats(y, gamma, beta, buf.running_mean, buf.running_var, tracked, BN_MOMENTUM, BN_EPS, training,
+                      **({} if rowmap is None else dict(rowmap=rowmap)))
 
 
-def _conv_bn(x, w, bias, gamma, beta, buf: BnBuffers, training: bool, prec: int, **kw):
+def _conv_bn(x, w, bias, gamma, beta, buf: BnBuffers, training: bool, prec: int, sync=None, **kw):
     """Conv2d -> BatchNorm2d pair (agcn.py:41-51,73-83): y = conv(x) and the BN scale / shift / saved statistics of y.
     In training mode the column sums come out of the convolution's epilogue (conv_fwd_stats) when the kernel covers the
     shape, which saves the separate statistics pass over y."""
@@ -62,11 +71,13 @@ def _conv_bn(x, w, bias, gamma, beta, buf: BnBuffers, training: bool, prec: int,
         y, part = K.conv_fwd_stats(x, w, bias, precision=prec, **kw)
         if part is not None:
             rows = y.numel() // y.shape[-1]
+            if sync is not None:
+                part, rows = sync.gather_partials(part), rows * sync.world
             return y, K.bn_finalize(part, rows, gamma, beta, buf.running_mean, buf.running_var, buf.num_batches_tracked,
                                     BN_MOMENTUM, BN_EPS)
     else:
         y = K.conv_fwd(x, w, bias, precision=prec, **kw)
-    return y, _bn_forward(y, gamma, beta, buf, training)
+    return y, _bn_forward(y, gamma, beta, buf, training, sync)
 
 
 def _eval_affine(gamma, beta, buf: BnBuffers):
@@ -129,13 +140,13 @@ def gcn_forward(x, adj_a, adj_b, wa, ba, wb, bb, wd, bd, bn_w, bn_b, down_w, dow
         if spec.attention_out is not None:
             spec.attention_out[:] = [p[:, k] for k in range(3)]
         return o
-    y, (sc, sh, mean, invstd) = _conv_bn(z, wdc, bdc, bn_w, bn_b, spec.bn_gcn, spec.training, prec)
+    y, (sc, sh, mean, invstd) = _conv_bn(z, wdc, bdc, bn_w, bn_b, spec.bn_gcn, spec.training, prec, sync=spec.sync)
     # the temporal convolution that follows takes its weight gradient from bf16 pieces of `o` written here, by the pass that
     # produces `o` anyway (agcn_conv_wgrad_presplit): no conversion pass in the weight-gradient kernel
     want_split = want_mask and spec.training and cout % 64 == 0 and prec != K.PREC_FP32_FFMA and prec != K.PREC_TF32
     o_split = None
     if spec.has_down:
-        yd, (sc2, sh2, mean2, invstd2) = _conv_bn(x, down_w.reshape(cout, 1, cin), down_b, dbn_w, dbn_b, spec.bn_down, spec.training, prec)
+        yd, (sc2, sh2, mean2, invstd2) = _conv_bn(x, down_w.reshape(cout, 1, cin), down_b, dbn_w, dbn_b, spec.bn_down, spec.training, prec, sync=spec.sync)
         r = _apply(want_mask, y, sc, sh, want_split=want_split, res_mode=K.RES_AFFINE, res=yd, scale2=sc2, shift2=sh2, relu=True)
     else:
         yd = mean2 = invstd2 = None
@@ -164,11 +175,12 @@ def gcn_backward(d_o, ctx, bn_w, dbn_w, down_w, spec: UnitSpec, dx=None, need_dx
     # eval mode with gradients (frozen-BN fine-tuning, saliency): the BatchNorms are affine maps of constants, and the biases of the
     # convolutions in front of them get real gradients (the column sums of dy) instead of the training mode's analytic zeros
     frozen = not spec.training
+    sk = dict(sync=spec.sync) if (spec.sync is not None and not frozen) else {}
     if z is None:
         z = K.joint_mix(x, g, width=cin, mode=K.MIX_AGG_FWD, precision=prec)
     if spec.has_down:
-        dy, dgam, dbet = K.bn_bwd(d_o, o, y, ctx["mean"], ctx["invstd"], bn_w, mask_bits=ctx["o_bits"], frozen=frozen)
-        dyd, dgam2, dbet2 = K.bn_bwd(d_o, o, ctx["yd"], ctx["mean2"], ctx["invstd2"], dbn_w, mask_bits=ctx["o_bits"], frozen=frozen)
+        dy, dgam, dbet = K.bn_bwd(d_o, o, y, ctx["mean"], ctx["invstd"], bn_w, mask_bits=ctx["o_bits"], frozen=frozen, **sk)
+        dyd, dgam2, dbet2 = K.bn_bwd(d_o, o, ctx["yd"], ctx["mean2"], ctx["invstd2"], dbn_w, mask_bits=ctx["o_bits"], frozen=frozen, **sk)
         wdown = down_w.reshape(cout, 1, cin)
         d_down_w, d_down_b = K.conv_wgrad(dyd, x, want_bias=frozen, precision=prec)
         if not frozen:
@@ -180,7 +192,7 @@ def gcn_backward(d_o, ctx, bn_w, dbn_w, down_w, spec: UnitSpec, dx=None, need_dx
         if need_dx and dx is None:
             dx = torch.empty_like(x)
         dy, dgam, dbet = K.bn_bwd(d_o, o, y, ctx["mean"], ctx["invstd"], bn_w,
-                                  dres=dx if need_dx else None, dres_accumulate=have, mask_bits=ctx["o_bits"], frozen=frozen)
+                                  dres=dx if need_dx else None, dres_accumulate=have, mask_bits=ctx["o_bits"], frozen=frozen, **sk)
         have = have or need_dx
         dgam2 = dbet2 = d_down_w = d_down_b = None
     d_wdc, d_bdc = K.conv_wgrad(dy, z, want_bias=frozen, precision=prec)
@@ -241,7 +253,7 @@ def tcn_forward(o, x_res, wt, bt, bn_w, bn_b, wr, br, rbn_w, rbn_b, spec: UnitSp
             res = None
         out = K.conv_fwd_post(o, wtp, bt, scale=sc, shift=sh, res=res, relu=spec.relu_out, t_out=t_out, stride=s, pad=pad, precision=prec)
         return out
-    u, (sc, sh, mean, invstd) = _conv_bn(o, wtp, bt, bn_w, bn_b, spec.bn_tcn, spec.training, prec, t_out=t_out, stride=s, pad=pad)
+    u, (sc, sh, mean, invstd) = _conv_bn(o, wtp, bt, bn_w, bn_b, spec.bn_tcn, spec.training, prec, sync=spec.sync, t_out=t_out, stride=s, pad=pad)
     ur = mean2 = invstd2 = wrp = None
     want_mask = ctx is not None and spec.relu_out
     # the model's tail (agcn.py:194-196): the last unit's output only feeds the global mean pool, so the pooled means and the ReLU
@@ -254,7 +266,7 @@ def tcn_forward(o, x_res, wt, bt, bn_w, bn_b, wr, br, rbn_w, rbn_b, spec: UnitSp
         out, out_bits = apply(u, sc, sh, res_mode=K.RES_TENSOR, res=x_res, relu=spec.relu_out)
     elif spec.residual == "conv":
         wrp = _pack_taps(wr)
-        ur, (sc2, sh2, mean2, invstd2) = _conv_bn(x_res, wrp, br, rbn_w, rbn_b, spec.bn_res, spec.training, prec, t_out=t_out, stride=s, pad=0)
+        ur, (sc2, sh2, mean2, invstd2) = _conv_bn(x_res, wrp, br, rbn_w, rbn_b, spec.bn_res, spec.training, prec, sync=spec.sync, t_out=t_out, stride=s, pad=0)
         out, out_bits = apply(u, sc, sh, res_mode=K.RES_AFFINE, res=ur, scale2=sc2, shift2=sh2, relu=spec.relu_out)
     else:
         out, out_bits = apply(u, sc, sh, relu=spec.relu_out)
@@ -277,6 +289,8 @@ def tcn_backward(d_out, ctx, bn_w, rbn_w, spec: UnitSpec, need_dres=True, need_d
     d_wr = d_br = dgam2 = dbet2 = None
     frozen = not spec.training          # eval mode with gradients, see gcn_backward
     pk["frozen"] = frozen
+    if spec.sync is not None and not frozen:
+        pk["sync"] = spec.sync
     # weight gradient of the temporal convolution from split operands: `o` as bf16 pieces from the gcn half's normalise pass, `du` as
     # bf16 pieces from the BatchNorm backward below (bit-mask forms only)
     o_split = ctx.get("o_split") if (not frozen and bits is not None) else None
@@ -436,7 +450,7 @@ class DataBnFn(torch.autograd.Function):
     channels-last, BatchNorm1d channel (m, v, c) has its statistics over (n, t)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, buf: BnBuffers, training: bool):
+    def forward(ctx, x, gamma, beta, buf: BnBuffers, training: bool, sync=None):
         n, m, t, v, c = x.shape
         vc = v * c
         out = torch.empty_like(x)
@@ -445,12 +459,11 @@ class DataBnFn(torch.autograd.Function):
             sl = slice(mi * vc, (mi + 1) * vc)
             rowmap = (n, t, m * t * vc, vc)
             xv = x[:, mi]
-            sc, sh, mean, invstd = K.bn_stats(xv, gamma[sl], beta[sl], buf.running_mean[sl], buf.running_var[sl],
-                                              buf.num_batches_tracked if mi == 0 else None, BN_MOMENTUM, BN_EPS, training,
-                                              rowmap=rowmap)
+            sc, sh, mean, invstd = _bn_forward(xv, gamma[sl], beta[sl], BnBuffers(buf.running_mean[sl], buf.running_var[sl], buf.num_batches_tracked),
+                                               training, sync, rowmap=rowmap, nbt=(mi == 0))
             K.bn_apply(xv, sc, sh, rowmap=rowmap, out=out[:, mi])
             saved.append((mean, invstd))
-        ctx.x, ctx.gamma, ctx.saved, ctx.training = x, gamma, saved, training
+        ctx.x, ctx.gamma, ctx.saved, ctx.training, ctx.sync = x, gamma, saved, training, sync
         return out.view(n * m, t, v, c)
 
     @staticmethod
@@ -468,10 +481,11 @@ class DataBnFn(torch.autograd.Function):
             rowmap = (n, t, m * t * vc, vc)
             mean, invstd = ctx.saved[mi]
             _, dg, db = K.bn_bwd(d_out[:, mi], None, x[:, mi], mean, invstd, gamma[sl], want_dy=need_dx,
-                                 dy=dx[:, mi] if need_dx else None, rowmap=rowmap, frozen=not ctx.training)
+                                 dy=dx[:, mi] if need_dx else None, rowmap=rowmap, frozen=not ctx.training,
+                                 **(dict(sync=ctx.sync) if (ctx.sync is not None and ctx.training) else {}))
             dgamma[sl] = dg
             dbeta[sl] = db
-        return dx, dgamma, dbeta, None, None
+        return dx, dgamma, dbeta, None, None, None
 
 
 class PoolFn(torch.autograd.Function):

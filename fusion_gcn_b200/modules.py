@@ -66,6 +66,22 @@ def set_recompute(module: nn.Module, flag: bool = True) -> nn.Module:
     return module
 
 
+def set_sync_batchnorm(module: nn.Module, sync=True) -> nn.Module:
+    """Synchronised BatchNorm for every unit (and the model's data_bn) under ``module``: training-mode statistics and their backward
+    sums are taken over all ranks of a process group, so a batch sharded over R GPUs normalises exactly like the unsharded batch
+    (the reference is single-process: its nn.BatchNorm sees the whole batch, agcn.py:44,78,83,150).  ``sync``: True (default group),
+    a ``distributed.SyncBatchNorm``, or None / False to go back to per-replica statistics.  Every rank must run the same local batch size."""
+    if sync is True:
+        from .distributed import SyncBatchNorm
+        sync = SyncBatchNorm()
+    elif sync is False:
+        sync = None
+    for m in module.modules():
+        if hasattr(m, "_agcn_sync"):
+            m._agcn_sync = sync
+    return module
+
+
 def conv_branch_init(conv, branches):            # agcn.py:18-24
     weight = conv.weight
     n, k1, k2 = weight.size(0), weight.size(1), weight.size(2)
@@ -111,6 +127,7 @@ class TemporalConv(nn.Module):
         conv_init(self.conv)
         bn_init(self.bn, 1)
         self._agcn_precision = _default_precision
+        self._agcn_sync = None
 
     def _params(self):
         return (self.conv.weight, self.conv.bias, self.bn.weight, self.bn.bias)
@@ -118,7 +135,7 @@ class TemporalConv(nn.Module):
     def forward_cl(self, x):
         spec = FN.UnitSpec(cin=self.conv.in_channels, cout=self.conv.out_channels, stride=self.conv.stride[0], residual="none",
                            kernel_size=self.conv.kernel_size[0], relu_out=False, training=self.training,
-                           precision=self._agcn_precision, bn_tcn=_bn_buffers(self.bn))
+                           precision=self._agcn_precision, bn_tcn=_bn_buffers(self.bn), sync=self._agcn_sync)
         return FN.TcnFn.apply(x, None, spec, *self._params(), None, None, None, None)
 
     def forward(self, x):
@@ -166,6 +183,7 @@ class SpatialGraphConv(nn.Module):
             conv_branch_init(self.conv_d[i], self.num_subsets)
         self._agcn_precision = _default_precision
         self._agcn_recompute = _default_recompute
+        self._agcn_sync = None
 
     # hooks for the original-variant subclass (parameter called PA, adjacency not a buffer)
     def _adj_fixed(self, x):
@@ -199,7 +217,7 @@ class SpatialGraphConv(nn.Module):
 
     def forward_cl(self, x):
         spec = self._fill_spec(FN.UnitSpec(cin=self.in_channels, cout=self.out_channels, training=self.training,
-                                           precision=self._agcn_precision, recompute=self._agcn_recompute))
+                                           precision=self._agcn_precision, recompute=self._agcn_recompute, sync=self._agcn_sync))
         params = self._params(x)
         spec.cin = _pad_input_weights(params, self.in_channels, x.shape[-1])
         return FN.GcnFn.apply(x, spec, *params)
@@ -252,6 +270,7 @@ class SpatialTemporalConv(nn.Module):
             self._residual_kind = "conv"
         self._agcn_precision = _default_precision
         self._agcn_recompute = _default_recompute
+        self._agcn_sync = None
 
     def forward_cl(self, x, pool_groups: int = 0):
         """``pool_groups`` > 0: return the mean over the (T, V) positions and bodies of every sample, [pool_groups, C_out], instead
@@ -260,7 +279,7 @@ class SpatialTemporalConv(nn.Module):
         spec = FN.UnitSpec(cin=g.in_channels, cout=self.out_channels, stride=self.stride, residual=self._residual_kind,
                            kernel_size=t.conv.kernel_size[0], relu_out=True, training=self.training,
                            precision=self._agcn_precision, bn_tcn=_bn_buffers(t.bn), pool_groups=pool_groups,
-                           recompute=self._agcn_recompute)
+                           recompute=self._agcn_recompute, sync=self._agcn_sync)
         g._fill_spec(spec)
         params = g._params(x) + list(t._params())
         spec.cin = _pad_input_weights(params, g.in_channels, x.shape[-1])
@@ -312,6 +331,7 @@ class Model(nn.Module):
             self.out_channels = num_classes
         bn_init(self.data_bn, 1)
         self._agcn_precision = _default_precision
+        self._agcn_sync = None
 
     def _register_layers(self):
         for layer_idx, layer in enumerate(self.layers):
@@ -321,7 +341,7 @@ class Model(nn.Module):
         """(N, M, T, V, C) -> channels-last feature map (N*M, T', V, C_out) of the last unit."""
         x = _prep(x)
         buf = FN.BnBuffers(self.data_bn.running_mean, self.data_bn.running_var, self.data_bn.num_batches_tracked)
-        h = FN.DataBnFn.apply(x, self.data_bn.weight, self.data_bn.bias, buf, self.training)
+        h = FN.DataBnFn.apply(x, self.data_bn.weight, self.data_bn.bias, buf, self.training, self._agcn_sync)
         cp = _padded_channels(h.shape[-1])
         if cp != h.shape[-1] and self.layers and self.layers[0]._residual_kind == "none":
             h = F.pad(h, (0, cp - h.shape[-1]))
@@ -335,7 +355,7 @@ class Model(nn.Module):
         n = x.shape[0]
         x = _prep(x)
         buf = FN.BnBuffers(self.data_bn.running_mean, self.data_bn.running_var, self.data_bn.num_batches_tracked)
-        h = FN.DataBnFn.apply(x, self.data_bn.weight, self.data_bn.bias, buf, self.training)
+        h = FN.DataBnFn.apply(x, self.data_bn.weight, self.data_bn.bias, buf, self.training, self._agcn_sync)
         cp = _padded_channels(h.shape[-1])
         if cp != h.shape[-1] and self.layers and self.layers[0]._residual_kind == "none":
             h = F.pad(h, (0, cp - h.shape[-1]))

@@ -385,6 +385,22 @@ def bn_stats(x, gamma, beta, running_mean, running_var, nbt, momentum, eps, trai
     return scale[0], scale[1], scale[2], scale[3]
 
 
+def bn_stats_partials(x, rowmap=None):
+    """Column statistics of x as mergeable partials [nparts, 4, c] (shifted sum | shifted sum of squares | pivot | row count per row
+    partition, the layout of conv_fwd_stats): the first half of a synchronised BatchNorm -- the partials of all ranks are concatenated
+    and given to bn_finalize with the global row count."""
+    import ctypes
+    outer, inner, ostride, c = _rowmap(x, rowmap)
+    ws, nbytes = _bn_ws(c, x.device)
+    _check_strided(x)
+    part_bytes = capi.lib().agcn_bn_stats_partials_bytes(c)
+    part = torch.empty(part_bytes // 4, device=x.device, dtype=torch.float32)
+    nparts = ctypes.c_int(0)
+    _call("agcn_bn_stats_partials", x.data_ptr(), outer, inner, ostride, c, part.data_ptr(), part_bytes, ctypes.byref(nparts),
+          _ptr(ws), nbytes, _stream(), sig=(outer, inner, c), work=(0.0, 4.0 * outer * inner * c))
+    return part[:nparts.value * 4 * c].view(nparts.value, 4, c)
+
+
 def bn_apply(y, scale, shift, *, res_mode=RES_NONE, res=None, scale2=None, shift2=None, relu=False, rowmap=None, out=None,
              want_mask=False, want_split=False):
     """out = act(scale*y + shift + R).  ``want_mask``: also return the ReLU mask (out > 0) as one bit per element (int32 words,
@@ -420,8 +436,10 @@ def bn_apply(y, scale, shift, *, res_mode=RES_NONE, res=None, scale2=None, shift
 
 
 def bn_bwd(dout, mask_out, y, save_mean, save_invstd, gamma, *, want_dy=True, dy=None, dres=None, dres_accumulate=False,
-           rowmap=None, mask_bits=None, pool_rows=0, frozen=False, want_split=False):
+           rowmap=None, mask_bits=None, pool_rows=0, frozen=False, want_split=False, sync=None):
     """-> dy | None, dgamma, dbeta; optionally writes / accumulates the masked gradient into ``dres``.
+    ``sync`` (distributed.SyncBatchNorm, training mode only): the statistics were taken over all ranks, so the two column sums are
+    all-reduced between the sum pass and the apply pass (agcn_bn_bwd_sync); dgamma / dbeta stay this rank's own sums.
     ``dy`` may be a preallocated tensor addressed with the same rowmap as ``y``.  ``mask_bits`` (from bn_apply(want_mask=True))
     replaces the fp32 tensor ``mask_out`` as the ReLU mask.  ``frozen``: the statistics are constants (eval-mode BatchNorm).
     ``want_split``: -> dy, dgamma, dbeta, dy_split with dy also as bf16 pieces [2, rows, c] (agcn_bn_bwd_bits_split), or None in
@@ -435,6 +453,27 @@ def bn_bwd(dout, mask_out, y, save_mean, save_invstd, gamma, *, want_dy=True, dy
     ws, nbytes = _bn_ws(c, y.device)
     if pool_rows and frozen:
         raise RuntimeError("bn_bwd: the pooled tail is a training-mode path")
+    if sync is not None and not frozen:
+        if mask_bits is not None:
+            if mask_bits.dtype != torch.int32 or not mask_bits.is_cuda:
+                raise RuntimeError("bn_bwd: mask_bits must be the int32 CUDA tensor returned by bn_apply(want_mask=True)")
+            _check(dout, y, dy, dres)
+        dy_split = torch.empty((2, inner, c), device=y.device, dtype=torch.bfloat16) if (want_split and dy is not None and mask_bits is not None
+                                                                                         and c % 64 == 0) else None
+        reads = 2 + (2.0 / 32 if mask_bits is not None else int(mask_out is not None))
+
+        def phase(k, sums, rows_all):
+            _call("agcn_bn_bwd_sync", dout.data_ptr(), _ptr(mask_out) if mask_bits is None else None, _ptr(mask_bits), y.data_ptr(),
+                  _ptr(save_mean), _ptr(save_invstd), _ptr(gamma), _ptr(dy), _ptr(dy_split), dgb[0].data_ptr(), dgb[1].data_ptr(), _ptr(dres),
+                  int(dres_accumulate), outer, inner, ostride, c, int(pool_rows), k, _ptr(sums), float(rows_all), _ptr(ws), nbytes, _stream(),
+                  sig=(outer, inner, c, k, int(dy is not None), int(dres is not None), int(dres_accumulate), int(dy_split is not None)),
+                  work=(0.0, 4.0 * outer * inner * c * (reads if k == 1 else reads + int(dy is not None) * (1 + int(dy_split is not None))
+                                                       + int(dres is not None) * (1 + int(dres_accumulate)))), alias="agcn_bn_bwd")
+        phase(1, None, 0.0)
+        if dy is not None or dres is not None:
+            sums = sync.all_reduce(torch.stack([dgb[1], dgb[0]]))             # (sum g | sum g xhat) over all ranks
+            phase(2, sums, float(outer) * inner * sync.world)
+        return (dy, dgb[0], dgb[1], dy_split) if want_split else (dy, dgb[0], dgb[1])
     if pool_rows:
         # ``dout`` is the gradient of the fused mean pool, [groups, c], broadcast over the pool_rows rows of each group
         _check(dout, y, dy, dres)

@@ -263,6 +263,25 @@ int agcn_bn_bwd_pool(const float* dpooled, const unsigned* mask_bits, const floa
                      float* dgamma, float* dbeta, float* dres, int dres_accumulate,
                      int groups, int rows_per_group, int channels, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- synchronised BatchNorm halves (optional SyncBN mode for the data-parallel path; the reference's nn.BatchNorm2d,
+ * agcn.py:44,78,83,150, computes its batch statistics over the whole batch, which a batch-sharded run only reproduces when the
+ * statistics are taken over all ranks).  The collectives stay with the caller; the library provides the halves either side of them.
+ * agcn_bn_stats_partials: part [nparts][4][channels] = per row partition the shifted sum | shifted sum of squares | pivot | row count
+ * of x -- the layout agcn_conv_fwd_stats writes and agcn_bn_finalize merges, so the partials of all ranks are concatenated
+ * (all-gather) and finalised with rows = the global row count.  agcn_bn_bwd_sync phase 1: dgamma / dbeta <- this rank's sums
+ * (sum g xhat | sum g; nothing else written); phase 2: dy (dy_split, dres) from global_sums [2][channels] = (sum g | sum g xhat)
+ * all-reduced over the ranks and global_rows.  mask_out / mask_bits / dy_split / pool_rows are the optional operands of agcn_bn_bwd,
+ * agcn_bn_bwd_bits(_split) and agcn_bn_bwd_pool (pool_rows > 0: dout is the pooled gradient [inner / pool_rows][channels]).   */
+size_t agcn_bn_stats_partials_bytes(int channels);
+int agcn_bn_stats_partials(const float* x, int outer, int inner, long long outer_stride, int channels,
+                           float* part, size_t part_bytes, int* nparts, void* workspace, size_t workspace_bytes, void* stream);
+int agcn_bn_bwd_sync(const float* dout, const float* mask_out, const unsigned* mask_bits, const float* y,
+                     const float* save_mean, const float* save_invstd, const float* gamma,
+                     float* dy, void* dy_split, float* dgamma, float* dbeta, float* dres, int dres_accumulate,
+                     int outer, int inner, long long outer_stride, int channels, int pool_rows,
+                     int phase, const float* global_sums, double global_rows,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- classifier head fused with its loss -------------------------------------------------------------
  * logits = x . w^T + bias (nn.Linear, agcn.py:178,198-199) and loss = mean_n( logsumexp(logits[n]) - logits[n][label[n]] )
  * (nn.CrossEntropyLoss with its defaults, torch_src/session/session.py:53 applied at procedures/step.py:41-42), one launch.

@@ -211,6 +211,16 @@ def bn_stats(x, gamma, beta, running_mean, running_var, nbt, momentum, eps, trai
     return scale, b - mean * scale, mean, invstd
 
 
+def bn_stats_partials(x, rowmap=None):
+    """Mergeable column statistics of x (agcn_bn_stats_partials): part [1, 4, c] = (sum, sum of squares) of x - p, the pivot p (the first
+    row) and the row count -- what bn_finalize merges, here with a single partial."""
+    xv = _rows_view(x, rowmap)
+    flat = xv.reshape(-1, xv.shape[-1]).double()
+    pivot = flat[0].clone()
+    flat = flat - pivot
+    return torch.stack([flat.sum(0), (flat * flat).sum(0), pivot, torch.full_like(pivot, flat.shape[0])]).unsqueeze(0)
+
+
 def bf16_split(x):
     """[..., C] -> [2, rows, C] bf16 pieces h = bf16(x), m = bf16(x - h) (round to nearest, ties away): the split-operand format of the
     weight-gradient kernel (agcn_conv_wgrad_presplit).  fp64 inputs (the tests' reference runs) are carried exactly instead: [2, rows, C]
@@ -260,10 +270,10 @@ def _bn_apply(y, scale, shift, *, res_mode=RES_NONE, res=None, scale2=None, shif
 
 
 def bn_bwd(dout, mask_out, y, save_mean, save_invstd, gamma, *, want_dy=True, dy=None, dres=None, dres_accumulate=False,
-           rowmap=None, mask_bits=None, pool_rows=0, frozen=False, want_split=False):
+           rowmap=None, mask_bits=None, pool_rows=0, frozen=False, want_split=False, sync=None):
     if want_split:
         dy, dgamma, dbeta = bn_bwd(dout, mask_out, y, save_mean, save_invstd, gamma, want_dy=want_dy, dy=dy, dres=dres, dres_accumulate=dres_accumulate,
-                                   rowmap=rowmap, mask_bits=mask_bits, pool_rows=pool_rows, frozen=frozen)
+                                   rowmap=rowmap, mask_bits=mask_bits, pool_rows=pool_rows, frozen=frozen, sync=sync)
         ok = dy is not None and mask_bits is not None and rowmap is None and dy.shape[-1] % 64 == 0
         return dy, dgamma, dbeta, (bf16_split(dy) if ok else None)
     if pool_rows:          # dout is the pooled gradient [groups, c]: broadcast over the rows of each group, divided by their number
@@ -281,12 +291,17 @@ def bn_bwd(dout, mask_out, y, save_mean, save_invstd, gamma, *, want_dy=True, dy
     m = g.numel() // c
     dbeta = g.sum(dim=red)
     dgamma = (g * xhat).sum(dim=red)
+    s1, s2 = dbeta, dgamma
+    if sync is not None and not frozen:
+        # synchronised BatchNorm (agcn_bn_bwd_sync): the two sums and the row count over all ranks; dgamma / dbeta stay this rank's own
+        both = sync.all_reduce(torch.stack([dbeta, dgamma]))
+        s1, s2, m = both[0], both[1], m * sync.world
     if want_dy:
         gam = gamma if gamma is not None else torch.ones_like(save_mean)
         if dy is None:
             dy = torch.empty_like(y)
         # frozen: eval-mode BatchNorm, the statistics are constants
-        _rows_view(dy, rowmap).copy_(gam * save_invstd * (g if frozen else g - dbeta / m - xhat * dgamma / m))
+        _rows_view(dy, rowmap).copy_(gam * save_invstd * (g if frozen else g - s1 / m - xhat * s2 / m))
     if dres is not None:
         dv = _rows_view(dres, rowmap)
         if dres_accumulate:

@@ -297,3 +297,58 @@ def test_recompute_policy(pkg):
         del y
     plane = 8 * 64 * 100 * 25 * 4
     assert held[0] - held[1] >= 4 * plane, held          # e (1.5 planes) + z (3 planes)
+
+
+class _MirrorSync:
+    """Stands in for distributed.SyncBatchNorm with TWO ranks that hold the same shard: the all-gathered partials are this rank's
+    twice, the all-reduced sums are doubled.  Statistics over the doubled batch equal those of the shard, so every output and gradient
+    must equal the per-replica run while the kernels go through the mergeable-partials path and the two-phase backward."""
+    world = 2
+
+    def gather_partials(self, part):
+        return torch.cat([part, part])
+
+    def all_reduce(self, t):
+        return t.mul_(2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("start,shape", [(64, (2, 24, 25, 3)), (16, (1, 20, 20, 3))])
+def test_sync_batchnorm_halves_on_mirrored_ranks(pkg, start, shape):
+    """agcn_bn_stats_partials / agcn_bn_finalize over concatenated partials / agcn_bn_bwd_sync phases 1 and 2 (SURVEY 8e optional SyncBN);
+    the real two-rank exchange is tested on gloo (tests/test_distributed_cpu.py)."""
+    import copy
+    from fusion_gcn_b200 import capi, graph as G
+    from fusion_gcn_b200 import modules as M
+    torch.manual_seed(7)
+    graph = G.SkeletonGraph(G.NTU_EDGES if shape[2] == 25 else G.UTD_EDGES, center_joint=G.NTU_CENTER if shape[2] == 25 else G.UTD_CENTER)
+    model = M.Model(shape, 13, graph, start_feature_size=start).cuda().train()
+    for p in model.parameters():                     # loud BatchNorm / adjacency parameters (SURVEY D7)
+        if p.dim() == 1:
+            p.data.add_(0.2 * torch.randn_like(p))
+    twin = M.set_sync_batchnorm(copy.deepcopy(model), _MirrorSync())
+    x = torch.randn(4, *shape, device="cuda")
+    w = torch.randn(4, 13, device="cuda")
+    outs = []
+    for mod in (model, twin):
+        before = capi.lib().agcn_launch_count()
+        y = mod(x)
+        (y * w).sum().backward()
+        outs.append((y.detach(), capi.lib().agcn_launch_count() - before))
+    (y0, n0), (y1, n1) = outs
+    assert n1 > n0                                   # the two-phase backward and the partials passes really ran
+    assert rel_err(y1, y0) <= 2e-6
+    scale = max(float(q.grad.abs().max()) for q in model.parameters())
+    # (the layers whose statistics come from the separate pass take a different -- equally exact -- summation route in the synchronised
+    # mode, so a ReLU input within 1e-7 of zero may take the other bracket: the bound leaves room for one such element; a wrong row
+    # count or a wrong sum in either phase moves every gradient by O(1))
+    for (k, p), q in zip(twin.named_parameters(), model.parameters()):
+        if ZERO_GRAD.search(k):
+            assert float((p.grad - q.grad).abs().max()) <= 1e-5 * scale, k
+        else:
+            assert rel_err(p.grad, q.grad) <= 5e-4, k
+    for (k, a), b in zip(twin.state_dict().items(), model.state_dict().values()):
+        if "running_mean" in k:
+            assert stat_err(a, b) <= 1e-6, k
+        elif "running_var" in k:                     # unbiased over 2m rows instead of m
+            assert stat_err(a, b) <= 1e-3, k
