@@ -46,6 +46,9 @@ class UnitSpec:
     bn_res: Optional[BnBuffers] = None
     attention_out: Optional[List[torch.Tensor]] = field(default=None)   # receives adj_c (3 x [nb,V,V], detached)
     pool_groups: int = 0            # > 0 (last unit of Model): return the mean-pooled [pool_groups, cout] instead of the feature map
+    # grad mode of the CALLER when the spec is built (inside autograd.Function.forward it is always off, and ctx.needs_input_grad does
+    # not look at it): under torch.no_grad() nothing can ask for a backward, so eval mode takes the fused, nothing-saved path
+    grad_enabled: bool = field(default_factory=torch.is_grad_enabled)
     sync: Optional[object] = None   # distributed.SyncBatchNorm: training-mode BatchNorm statistics over all ranks of its group
     recompute: bool = False         # do not keep theta / phi (e) and the aggregated tensor (z) for the backward; run their kernels again there
 
@@ -372,7 +375,7 @@ def _need_backward(spec, store=True):
 def _store(ctx, spec):
     """Activation store of one forward: a dict when a backward can follow (training mode, or eval mode with an input or parameter
     that requires a gradient), None otherwise -- eval mode then takes the fused, nothing-saved path."""
-    return {} if (spec.training or any(ctx.needs_input_grad)) else None
+    return {} if (spec.training or (spec.grad_enabled and any(ctx.needs_input_grad))) else None
 
 
 class GcnFn(torch.autograd.Function):

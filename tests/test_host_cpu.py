@@ -241,3 +241,33 @@ def test_eval_mode_gradients_match_the_oracle(torch_stage_backend):
 
 def test_recompute_policy_gives_identical_gradients(torch_stage_backend):
     recompute_case(M, G, "cpu")
+
+
+def test_eval_no_grad_takes_the_fused_nothing_saved_path(torch_stage_backend, monkeypatch):
+    """model.eval() under torch.no_grad() (session.py:188-194) must run the fused tails (conv_fwd_post), not the unfused pipeline that a
+    backward could follow: ctx.needs_input_grad ignores the grad mode, so the caller's grad mode is recorded in the UnitSpec."""
+    import collections
+    import fusion_gcn_b200.functional as FN
+    calls = collections.Counter()
+
+    class Counting:
+        def __getattr__(self, name):
+            attr = getattr(torch_stage_backend, name)
+            if not callable(attr):
+                return attr
+
+            def wrapped(*a, **kw):
+                calls[name] += 1
+                return attr(*a, **kw)
+            return wrapped
+
+    monkeypatch.setattr(FN, "K", Counting())
+    model = M.Model((2, 16, 25, 3), 60, G.SkeletonGraph(G.NTU_EDGES, center_joint=G.NTU_CENTER), start_feature_size=16).eval()
+    x = torch.randn(2, 2, 16, 25, 3)
+    with torch.no_grad():
+        y0 = model(x)
+    assert calls["conv_fwd_post"] == 25 and calls["bn_apply"] == 2, calls          # 2 = data_bn of the two bodies
+    calls.clear()
+    y1 = model(x)                                   # grad mode on, parameters require grad: a backward may follow
+    assert calls["conv_fwd_post"] == 0 and calls["bn_apply"] == 22, calls
+    assert rel_err(y0, y1.detach()) <= 1e-6
