@@ -58,6 +58,7 @@ SIGNATURES = {
     "agcn_bn_apply_pool_workspace_bytes": (_c_size_t, [_c_int, _c_int]),
     "agcn_bn_apply_pool": (_c_int, [_c_void_p] * 3 + [_c_int] + [_c_void_p] * 3 + [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_size_t, _c_void_p]),
     "agcn_bn_bwd_pool": (_c_int, [_c_void_p] * 11 + [_c_int, _c_int, _c_int, _c_int, _c_void_p, _c_size_t, _c_void_p]),
+    "agcn_bn_bwd_bits_dual": (_c_int, [_c_void_p] * 17 + [_c_int, _c_int, _c_int, _c_void_p, _c_size_t, _c_void_p]),
     "agcn_bn_stats_partials_bytes": (_c_size_t, [_c_int]),
     "agcn_bn_stats_partials": (_c_int, [_c_void_p, _c_int, _c_int, _c_ll, _c_int, _c_void_p, _c_size_t, _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
     "agcn_bn_bwd_sync": (_c_int, [_c_void_p] * 12 + [_c_int, _c_int, _c_int, _c_ll, _c_int, _c_int, _c_int, _c_void_p, _c_double,

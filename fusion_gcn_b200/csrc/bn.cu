@@ -496,6 +496,102 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* dout, co
     }
 }
 
+// ---- two BatchNorm backwards that share their upstream gradient (the gcn half's bn and down.1 both feed the ReLU of agcn.py:113-115,
+// the temporal BatchNorm and the residual branch's both feed the one of :135-136): g = dout * mask is read ONCE per pass for both,
+// 8 plane passes instead of 10.  Bit-mask form, contiguous rows, vectorised layout only.
+__global__ void __launch_bounds__(256) colsum_dual_kernel(const float* ya, const float* yb, const float* dout, const unsigned* mask_bits,
+                                                          const float* mean_a, const float* invstd_a, const float* mean_b, const float* invstd_b,
+                                                          int channels, long long rows, float* part_a, float* part_b) {
+    extern __shared__ __align__(16) float smv[];   // [4][lanes_r][channels]
+    const int cq = channels >> 2;
+    const int lanes_r = 256 / cq;
+    const int q = threadIdx.x % cq, rl = threadIdx.x / cq;
+    const int P = gridDim.x;
+    const long long per = (rows + P - 1) / P;
+    const long long r0 = (long long)blockIdx.x * per;
+    long long r1 = r0 + per; if (r1 > rows) r1 = rows;
+    float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), sa = s0, sb = s0;      // sum g (shared by both), sum g xhat_a, sum g xhat_b
+    const float4 mua = *reinterpret_cast<const float4*>(mean_a + q * 4), isa = *reinterpret_cast<const float4*>(invstd_a + q * 4);
+    const float4 mub = *reinterpret_cast<const float4*>(mean_b + q * 4), isb = *reinterpret_cast<const float4*>(invstd_b + q * 4);
+    auto body = [&](float4 g, unsigned nib, const float4& va, const float4& vb) {
+        if (!(nib & 1u)) g.x = 0.f;
+        if (!(nib & 2u)) g.y = 0.f;
+        if (!(nib & 4u)) g.z = 0.f;
+        if (!(nib & 8u)) g.w = 0.f;
+        s0.x += g.x; s0.y += g.y; s0.z += g.z; s0.w += g.w;
+        sa.x = fmaf(g.x, (va.x - mua.x) * isa.x, sa.x); sa.y = fmaf(g.y, (va.y - mua.y) * isa.y, sa.y);
+        sa.z = fmaf(g.z, (va.z - mua.z) * isa.z, sa.z); sa.w = fmaf(g.w, (va.w - mua.w) * isa.w, sa.w);
+        sb.x = fmaf(g.x, (vb.x - mub.x) * isb.x, sb.x); sb.y = fmaf(g.y, (vb.y - mub.y) * isb.y, sb.y);
+        sb.z = fmaf(g.z, (vb.z - mub.z) * isb.z, sb.z); sb.w = fmaf(g.w, (vb.w - mub.w) * isb.w, sb.w);
+    };
+    long long r = r0 + rl;
+    for (; r + lanes_r < r1; r += 2LL * lanes_r) {          // two rows per trip, all six loads first (see colsum_vec_kernel)
+        const long long o0 = r * channels + q * 4, o1 = (r + lanes_r) * channels + q * 4;
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(dout + o0)), g1 = __ldg(reinterpret_cast<const float4*>(dout + o1));
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(ya + o0)), a1 = __ldg(reinterpret_cast<const float4*>(ya + o1));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(yb + o0)), b1 = __ldg(reinterpret_cast<const float4*>(yb + o1));
+        const unsigned n0 = mask_nibble(mask_bits, o0), n1 = mask_nibble(mask_bits, o1);
+        body(g0, n0, a0, b0);
+        body(g1, n1, a1, b1);
+    }
+    for (; r < r1; r += lanes_r) {
+        const long long o0 = r * channels + q * 4;
+        body(__ldg(reinterpret_cast<const float4*>(dout + o0)), mask_nibble(mask_bits, o0),
+             __ldg(reinterpret_cast<const float4*>(ya + o0)), __ldg(reinterpret_cast<const float4*>(yb + o0)));
+    }
+    float4* a = reinterpret_cast<float4*>(smv);
+    a[(0 * lanes_r + rl) * cq + q] = s0;
+    a[(1 * lanes_r + rl) * cq + q] = sa;
+    a[(2 * lanes_r + rl) * cq + q] = sb;
+    __syncthreads();
+    for (int o = threadIdx.x; o < 3 * channels; o += 256) {
+        const int which = o / channels, c = o % channels;
+        float acc = 0.f;
+        for (int i = 0; i < lanes_r; ++i) acc += smv[(which * lanes_r + i) * channels + c];
+        if (which == 0) {
+            part_a[((long long)blockIdx.x * 2 + 0) * channels + c] = acc;
+            part_b[((long long)blockIdx.x * 2 + 0) * channels + c] = acc;
+        } else if (which == 1) {
+            part_a[((long long)blockIdx.x * 2 + 1) * channels + c] = acc;
+        } else {
+            part_b[((long long)blockIdx.x * 2 + 1) * channels + c] = acc;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_dual_kernel(const float* dout, const unsigned* mask_bits, const float* ya, const float* yb,
+                                                                const float* coef_a, const float* coef_b, float* dya, float* dyb,
+                                                                unsigned short* dya_split, int C, long long rows) {
+    const int cq = C / 4;
+    const long long total = rows * cq;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx / cq;
+        const int c = (int)(idx - r * cq) * 4;
+        const long long off = r * C + c;
+        const float4 gq = __ldg(reinterpret_cast<const float4*>(dout + off));
+        const float4 aq = __ldg(reinterpret_cast<const float4*>(ya + off));
+        const float4 bq = __ldg(reinterpret_cast<const float4*>(yb + off));
+        const unsigned nib = mask_nibble(mask_bits, off);
+        float g[4] = {gq.x, gq.y, gq.z, gq.w};
+        const float av[4] = {aq.x, aq.y, aq.z, aq.w}, bv[4] = {bq.x, bq.y, bq.z, bq.w};
+        float oa[4], ob[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (!((nib >> e) & 1u)) g[e] = 0.f;
+            oa[e] = coef_a[c + e] * (g[e] - coef_a[C + c + e] - (av[e] - coef_a[3 * C + c + e]) * coef_a[2 * C + c + e]);
+            ob[e] = coef_b[c + e] * (g[e] - coef_b[C + c + e] - (bv[e] - coef_b[3 * C + c + e]) * coef_b[2 * C + c + e]);
+        }
+        *reinterpret_cast<float4*>(dya + off) = make_float4(oa[0], oa[1], oa[2], oa[3]);
+        *reinterpret_cast<float4*>(dyb + off) = make_float4(ob[0], ob[1], ob[2], ob[3]);
+        if (dya_split != nullptr) {
+            uint2 h, mm;
+            bf16_pieces4(oa, h, mm);
+            *reinterpret_cast<uint2*>(dya_split + off) = h;
+            *reinterpret_cast<uint2*>(dya_split + rows * C + off) = mm;
+        }
+    }
+}
+
 // pooling: grid = (groups, column strips of 32); block = 32 x 8
 __global__ void __launch_bounds__(256) pool_fwd_kernel(const float* x, float* out, int rows_per_group, int C) {
     __shared__ float sm[8][33];
@@ -750,6 +846,45 @@ extern "C" AGCN_API int agcn_bn_bwd_bits_split(const float* dout, const unsigned
     AGCN_REQUIRE(mask_bits && dy && dy_split, AGCN_ERR_NULL, "agcn_bn_bwd_bits_split: null pointer");
     return bn_bwd_impl(dout, nullptr, mask_bits, y, save_mean, save_invstd, gamma, dy, dgamma, dbeta, dres, dres_accumulate,
                        1, inner, 0, channels, workspace, workspace_bytes, stream, 0, frozen_stats, static_cast<unsigned short*>(dy_split));
+}
+
+// Two BatchNorm backwards over the same masked upstream gradient in one pair of passes (see colsum_dual_kernel): BatchNorm A = (y_a,
+// mean_a, invstd_a, gamma_a) -> dy_a (+ dy_a_split, optional bf16 pieces), dgamma_a, dbeta_a; BatchNorm B likewise without pieces.
+// workspace: 2 x agcn_bn_workspace_bytes(channels).  AGCN_ERR_UNSUPPORTED (quiet) when the layout has no bit mask (agcn_bn_mask_words == 0).
+extern "C" AGCN_API int agcn_bn_bwd_bits_dual(const float* dout, const unsigned* mask_bits,
+                                              const float* y_a, const float* mean_a, const float* invstd_a, const float* gamma_a,
+                                              float* dy_a, void* dy_a_split, float* dgamma_a, float* dbeta_a,
+                                              const float* y_b, const float* mean_b, const float* invstd_b, const float* gamma_b,
+                                              float* dy_b, float* dgamma_b, float* dbeta_b,
+                                              int frozen_stats, int inner, int channels, void* workspace, size_t workspace_bytes, void* stream) {
+    AGCN_REQUIRE(dout && mask_bits && y_a && mean_a && invstd_a && dy_a && y_b && mean_b && invstd_b && dy_b && workspace, AGCN_ERR_NULL,
+                 "agcn_bn_bwd_bits_dual: null pointer");
+    AGCN_REQUIRE(inner > 0 && channels > 0, AGCN_ERR_BAD_SHAPE, "agcn_bn_bwd_bits_dual: bad shape inner=%d channels=%d", inner, channels);
+    const size_t one = agcn_bn_workspace_bytes(channels);
+    AGCN_REQUIRE(workspace_bytes >= 2 * one, AGCN_ERR_WORKSPACE, "agcn_bn_bwd_bits_dual: workspace too small");
+    RowMap m{1, inner, 0, channels};
+    if (agcn_bn_mask_words(1, inner, channels) == 0 ||
+        !vec_ok(m, {dout, y_a, y_b, dy_a, dy_b, mean_a, invstd_a, mean_b, invstd_b, workspace, dy_a_split}))
+        return AGCN_ERR_UNSUPPORTED;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const long long rows = inner;
+    const int P = num_partials(rows);
+    float* part_a = static_cast<float*>(workspace);
+    float* coef_a = part_a + (size_t)kMaxPartials * 2 * channels;
+    float* part_b = reinterpret_cast<float*>(static_cast<char*>(workspace) + one);
+    float* coef_b = part_b + (size_t)kMaxPartials * 2 * channels;
+    const int cq = channels / 4;
+    const size_t smem = (size_t)3 * (256 / cq) * channels * sizeof(float);
+    colsum_dual_kernel<<<P, 256, smem, s>>>(y_a, y_b, dout, mask_bits, mean_a, invstd_a, mean_b, invstd_b, channels, rows, part_a, part_b);
+    int rc = check_launch("agcn_bn_bwd_bits_dual(sums)");
+    if (rc) return rc;
+    bn_bwd_finalize_kernel<<<ceil_div(channels, kFinCh), kFinCh * kFinLanes, 0, s>>>(part_a, P, channels, (double)rows, gamma_a, mean_a, invstd_a, dgamma_a, dbeta_a, coef_a, frozen_stats);
+    bn_bwd_finalize_kernel<<<ceil_div(channels, kFinCh), kFinCh * kFinLanes, 0, s>>>(part_b, P, channels, (double)rows, gamma_b, mean_b, invstd_b, dgamma_b, dbeta_b, coef_b, frozen_stats);
+    rc = check_launch("agcn_bn_bwd_bits_dual(finalize)");
+    if (rc) return rc;
+    bn_bwd_apply_dual_kernel<<<elementwise_blocks(rows * cq), 256, 0, s>>>(dout, mask_bits, y_a, y_b, coef_a, coef_b, dy_a, dy_b,
+                                                                           static_cast<unsigned short*>(dy_a_split), channels, rows);
+    return check_launch("agcn_bn_bwd_bits_dual(apply)");
 }
 
 // ---- synchronised BatchNorm (statistics over all ranks of a data-parallel group; SURVEY 8e "optional SyncBN mode")

@@ -182,8 +182,14 @@ def gcn_backward(d_o, ctx, bn_w, dbn_w, down_w, spec: UnitSpec, dx=None, need_dx
     if z is None:
         z = K.joint_mix(x, g, width=cin, mode=K.MIX_AGG_FWD, precision=prec)
     if spec.has_down:
-        dy, dgam, dbet = K.bn_bwd(d_o, o, y, ctx["mean"], ctx["invstd"], bn_w, mask_bits=ctx["o_bits"], frozen=frozen, **sk)
-        dyd, dgam2, dbet2 = K.bn_bwd(d_o, o, ctx["yd"], ctx["mean2"], ctx["invstd2"], dbn_w, mask_bits=ctx["o_bits"], frozen=frozen, **sk)
+        # bn and down.1 both feed the ReLU of agcn.py:113-115: one pair of passes over the shared masked gradient for both backwards
+        both = None if sk else K.bn_bwd_dual(d_o, ctx["o_bits"], (y, ctx["mean"], ctx["invstd"], bn_w),
+                                             (ctx["yd"], ctx["mean2"], ctx["invstd2"], dbn_w), frozen=frozen)
+        if both is not None:
+            dy, dgam, dbet, _, dyd, dgam2, dbet2 = both
+        else:
+            dy, dgam, dbet = K.bn_bwd(d_o, o, y, ctx["mean"], ctx["invstd"], bn_w, mask_bits=ctx["o_bits"], frozen=frozen, **sk)
+            dyd, dgam2, dbet2 = K.bn_bwd(d_o, o, ctx["yd"], ctx["mean2"], ctx["invstd2"], dbn_w, mask_bits=ctx["o_bits"], frozen=frozen, **sk)
         wdown = down_w.reshape(cout, 1, cin)
         d_down_w, d_down_b = K.conv_wgrad(dyd, x, want_bias=frozen, precision=prec)
         if not frozen:
@@ -305,10 +311,18 @@ def tcn_backward(d_out, ctx, bn_w, rbn_w, spec: UnitSpec, need_dres=True, need_d
         du, dgam, dbet, *sp = K.bn_bwd(d_out, mask, u, ctx["t_mean"], ctx["t_invstd"], bn_w, dres=d_xres, dres_accumulate=False, mask_bits=bits, **pk)
         du_split = sp[0] if sp else None
     elif spec.residual == "conv":
-        du, dgam, dbet, *sp = K.bn_bwd(d_out, mask, u, ctx["t_mean"], ctx["t_invstd"], bn_w, mask_bits=bits, **pk)
-        du_split = sp[0] if sp else None
-        pk.pop("want_split", None)
-        dur, dgam2, dbet2 = K.bn_bwd(d_out, mask, ctx["ur"], ctx["t_mean2"], ctx["t_invstd2"], rbn_w, mask_bits=bits, **pk)
+        # the temporal BatchNorm and the residual branch's both feed the ReLU of agcn.py:135-136: one pair of passes for both backwards
+        both = None
+        if bits is not None and not pk.get("pool_rows") and "sync" not in pk:
+            both = K.bn_bwd_dual(d_out, bits, (u, ctx["t_mean"], ctx["t_invstd"], bn_w), (ctx["ur"], ctx["t_mean2"], ctx["t_invstd2"], rbn_w),
+                                 frozen=frozen, want_split=bool(pk.get("want_split")))
+        if both is not None:
+            du, dgam, dbet, du_split, dur, dgam2, dbet2 = both
+        else:
+            du, dgam, dbet, *sp = K.bn_bwd(d_out, mask, u, ctx["t_mean"], ctx["t_invstd"], bn_w, mask_bits=bits, **pk)
+            du_split = sp[0] if sp else None
+            pk.pop("want_split", None)
+            dur, dgam2, dbet2 = K.bn_bwd(d_out, mask, ctx["ur"], ctx["t_mean2"], ctx["t_invstd2"], rbn_w, mask_bits=bits, **pk)
         d_wrp, d_br = K.conv_wgrad(dur, x_res, taps=1, stride=s, pad=0, want_bias=frozen, precision=prec)
         if not frozen:
             d_br = _zero_bias(d_out, d_wrp.shape[0])

@@ -513,6 +513,31 @@ def bn_bwd(dout, mask_out, y, save_mean, save_invstd, gamma, *, want_dy=True, dy
     return (dy, dgb[0], dgb[1], None) if want_split else (dy, dgb[0], dgb[1])
 
 
+def bn_bwd_dual(dout, mask_bits, a, b, *, frozen=False, want_split=False):
+    """Two BatchNorm backwards that share the masked upstream gradient (agcn_bn_bwd_bits_dual): ``a`` / ``b`` = (y, save_mean,
+    save_invstd, gamma) of the two BatchNorms.  -> (dy_a, dgamma_a, dbeta_a, dy_a_split | None, dy_b, dgamma_b, dbeta_b), or None
+    when the layout is not covered (no bit mask) -- call bn_bwd twice then."""
+    ya, mean_a, invstd_a, gamma_a = a
+    yb, mean_b, invstd_b, gamma_b = b
+    c = ya.shape[-1]
+    inner = ya.numel() // c
+    if mask_bits is None or not ya.is_contiguous() or not yb.is_contiguous() or not dout.is_contiguous() or tuple(ya.shape) != tuple(yb.shape) \
+            or tuple(dout.shape) != tuple(ya.shape) or capi.lib().agcn_bn_mask_words(1, inner, c) == 0:
+        return None
+    _check(dout, ya, yb, mean_a, invstd_a, gamma_a, mean_b, invstd_b, gamma_b)
+    dya, dyb = torch.empty_like(ya), torch.empty_like(yb)
+    split = torch.empty((2, inner, c), device=ya.device, dtype=torch.bfloat16) if (want_split and c % 64 == 0) else None
+    dgb = torch.empty((4, c), device=ya.device, dtype=torch.float32)
+    one = capi.lib().agcn_bn_workspace_bytes(c)
+    ws = torch.empty((2 * one + 3) // 4, device=ya.device, dtype=torch.float32)
+    _call("agcn_bn_bwd_bits_dual", dout.data_ptr(), mask_bits.data_ptr(), ya.data_ptr(), _ptr(mean_a), _ptr(invstd_a), _ptr(gamma_a),
+          dya.data_ptr(), _ptr(split), dgb[0].data_ptr(), dgb[1].data_ptr(), yb.data_ptr(), _ptr(mean_b), _ptr(invstd_b), _ptr(gamma_b),
+          dyb.data_ptr(), dgb[2].data_ptr(), dgb[3].data_ptr(), int(frozen), inner, c, ws.data_ptr(), 2 * one, _stream(),
+          sig=(1, inner, c, 3, 2, int(split is not None)), work=(0.0, 4.0 * inner * c * (2 * (3 + 1.0 / 32) + 2 + int(split is not None))),
+          alias="agcn_bn_bwd")
+    return dya, dgb[0], dgb[1], split, dyb, dgb[2], dgb[3]
+
+
 def bn_pool_supported(rows: int, channels: int) -> bool:
     """Whether the fused BN-apply + mean-pool tail (agcn_bn_apply_pool / agcn_bn_bwd_pool) covers this layout."""
     return channels % 32 == 0 and capi.lib().agcn_bn_mask_words(1, rows, channels) > 0

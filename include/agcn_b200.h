@@ -263,6 +263,18 @@ int agcn_bn_bwd_pool(const float* dpooled, const unsigned* mask_bits, const floa
                      float* dgamma, float* dbeta, float* dres, int dres_accumulate,
                      int groups, int rows_per_group, int channels, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Two BatchNorm backwards over the SAME masked upstream gradient in one pair of passes: the gcn half's bn and down.1 both feed the
+ * ReLU of agcn.py:113-115, the temporal BatchNorm and the residual branch's both feed the one of agcn.py:135-136, so g = dout * mask
+ * is read once per pass for both (8 plane passes instead of 10).  BatchNorm A may also leave dy_a as bf16 pieces (dy_a_split, see
+ * agcn_bn_bwd_bits_split).  workspace: 2 x agcn_bn_workspace_bytes(channels).  Returns AGCN_ERR_UNSUPPORTED (no error string) for
+ * layouts without a bit mask (agcn_bn_mask_words == 0): call agcn_bn_bwd_bits twice then.                                        */
+int agcn_bn_bwd_bits_dual(const float* dout, const unsigned* mask_bits,
+                          const float* y_a, const float* mean_a, const float* invstd_a, const float* gamma_a,
+                          float* dy_a, void* dy_a_split, float* dgamma_a, float* dbeta_a,
+                          const float* y_b, const float* mean_b, const float* invstd_b, const float* gamma_b,
+                          float* dy_b, float* dgamma_b, float* dbeta_b,
+                          int frozen_stats, int inner, int channels, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- synchronised BatchNorm halves (optional SyncBN mode for the data-parallel path; the reference's nn.BatchNorm2d,
  * agcn.py:44,78,83,150, computes its batch statistics over the whole batch, which a batch-sharded run only reproduces when the
  * statistics are taken over all ranks).  The collectives stay with the caller; the library provides the halves either side of them.

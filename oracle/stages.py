@@ -311,6 +311,15 @@ def bn_bwd(dout, mask_out, y, save_mean, save_invstd, gamma, *, want_dy=True, dy
     return dy, dgamma, dbeta
 
 
+def bn_bwd_dual(dout, mask_bits, a, b, *, frozen=False, want_split=False):
+    """agcn_bn_bwd_bits_dual: two BatchNorm backwards over the same masked upstream gradient (None when there is no bit mask)."""
+    if mask_bits is None:
+        return None
+    dya, dga, dba, *sp = bn_bwd(dout, None, a[0], a[1], a[2], a[3], mask_bits=mask_bits, frozen=frozen, want_split=want_split)
+    dyb, dgb_, dbb = bn_bwd(dout, None, b[0], b[1], b[2], b[3], mask_bits=mask_bits, frozen=frozen)
+    return dya, dga, dba, (sp[0] if sp else None), dyb, dgb_, dbb
+
+
 def bn_pool_supported(rows, channels):
     return channels % 32 == 0
 

@@ -95,6 +95,30 @@ def test_batchnorm_kernels_also_write_bf16_pieces(K, rows, c):
     assert torch.equal(d1[3].view(torch.int16), K.bf16_split(d0[0]).view(torch.int16))
 
 
+@pytest.mark.parametrize("rows,c,frozen", [(1000, 64, False), (4099, 256, False), (777, 128, True), (333, 192, False), (120000, 128, False)])
+def test_two_batchnorm_backwards_over_one_upstream_gradient(K, rows, c, frozen):
+    """agcn_bn_bwd_bits_dual (bn + down.1 of the gcn half, the temporal + residual BatchNorms of the unit): same sums in the same order
+    and the same apply formula as two agcn_bn_bwd_bits calls; layouts without a bit mask return None."""
+    ya, yb, res = rnd(rows, c).cuda(), rnd(rows, c, seed=9).cuda(), rnd(rows, c, seed=1).cuda()
+    sc, sh = (rnd(c, seed=2) * 0.3 + 1).cuda(), (rnd(c, seed=3) * 0.1).cuda()
+    _, bits = K.bn_apply(ya, sc, sh, res_mode=K.RES_TENSOR, res=res, relu=True, want_mask=True)
+    dout = rnd(rows, c, seed=4).cuda()
+    stats = [((rnd(c, seed=5 + i) * 0.1).cuda(), (rnd(c, seed=7 + i).abs() + 0.5).cuda(), (rnd(c, seed=11 + i) * 0.3 + 1).cuda()) for i in range(2)]
+    a, b = (ya, *stats[0]), (yb, *stats[1])
+    got = K.bn_bwd_dual(dout, bits, a, b, frozen=frozen, want_split=True)
+    if bits is None:
+        assert got is None
+        return
+    wa = K.bn_bwd(dout, None, ya, *stats[0], mask_bits=bits, frozen=frozen, want_split=True)
+    wb = K.bn_bwd(dout, None, yb, *stats[1], mask_bits=bits, frozen=frozen)
+    for g, w in zip(got[:3] + got[4:], wa[:3] + wb):
+        assert rel_err(g, w) <= 1e-6
+    if c % 64 == 0:
+        assert torch.equal(got[3].view(torch.int16), K.bf16_split(got[0]).view(torch.int16))
+    else:
+        assert got[3] is None
+
+
 @pytest.mark.parametrize("nb,t,v,cin,cout,taps,stride", [(2, 40, 25, 64, 64, 9, 1), (4, 150, 25, 256, 128, 9, 1), (2, 31, 25, 192, 64, 1, 1),
                                                         (3, 20, 22, 128, 256, 9, 1), (2, 12, 25, 64, 192, 1, 1), (4, 150, 25, 256, 64, 9, 1),
                                                         (1, 7, 20, 96, 64, 1, 1), (4, 150, 25, 128, 128, 9, 2), (2, 21, 25, 256, 256, 9, 2),
