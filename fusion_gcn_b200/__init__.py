@@ -6,6 +6,6 @@ Public surface mirrors the reference's torch_src/models/mmargcn/agcn.py and torc
 The arithmetic lives in libagcn_b200.so (C ABI: include/agcn_b200.h); there is no CPU fallback.
 """
 from . import capi, graph  # noqa: F401
-from .modules import Model, SpatialGraphConv, SpatialTemporalConv, TemporalConv, set_precision  # noqa: F401
+from .modules import Model, SpatialGraphConv, SpatialTemporalConv, TemporalConv, set_precision, set_recompute, set_sync_batchnorm  # noqa: F401
 
-__all__ = ["Model", "SpatialGraphConv", "SpatialTemporalConv", "TemporalConv", "set_precision", "capi", "graph"]
+__all__ = ["Model", "SpatialGraphConv", "SpatialTemporalConv", "TemporalConv", "set_precision", "set_recompute", "set_sync_batchnorm", "capi", "graph"]

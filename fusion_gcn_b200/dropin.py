@@ -52,7 +52,8 @@ def install_shims(reference_root: str, host_stubs: bool = True) -> None:
     # np.bool is deliberately left alone (numpy >= 2 defines it; overriding it breaks numpy.ma / scipy)
 
 
-def install(reference_root: str, precision="fp32", host_stubs: bool = True, fused_optimizers: bool = False, prefetch: bool = False) -> dict:
+def install(reference_root: str, precision="fp32", host_stubs: bool = True, fused_optimizers: bool = False, prefetch: bool = False,
+            recompute: bool = False) -> dict:
     """Rebinds the reference's unit / backbone classes to the B200 implementations.  Returns the patched modules.
     ``fused_optimizers``: the YAML optimizer names SGD / ADAM / ADAMW (torch_src/session_helper.py:48-53) build the multi-tensor
     classes of fusion_gcn_b200.optim.  ``prefetch``: the sessions' ``DataLoader`` (session/training.py:18-25, evaluation.py:20-24,
@@ -62,6 +63,7 @@ def install(reference_root: str, precision="fp32", host_stubs: bool = True, fuse
         raise FileNotFoundError(f"{reference_root} does not look like a fusion-gcn checkout (torch_src/models/mmargcn/agcn.py missing)")
     install_shims(reference_root, host_stubs)
     modules.set_default_precision(precision)
+    modules.set_default_recompute(recompute)             # activation-recompute policy of the units the session builds
     ref_m = importlib.import_module("models.mmargcn.agcn")
     ref_o = importlib.import_module("models.agcn.agcn")
     for mod, names, impl in ((ref_m, _MMARGCN_NAMES, modules), (ref_o, _ORIGINAL_NAMES, modules_original)):
@@ -132,6 +134,7 @@ def main(argv=None) -> None:
     ap = argparse.ArgumentParser(prog="python -m fusion_gcn_b200.dropin", description=__doc__.split("\n")[0])
     ap.add_argument("--reference", default=os.environ.get("FUSION_GCN_REFERENCE", "/root/reference"))
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16x3", "tf32", "fp32_ffma"])
+    ap.add_argument("--recompute", action="store_true", help="units recompute theta / phi and the aggregated tensor in the backward (~40 %% less activation memory)")
     ap.add_argument("--no-dropin", action="store_true", help="run the UNMODIFIED reference under the same import shims (A/B baseline)")
     ap.add_argument("--reference-fp32", action="store_true", help="with --no-dropin: disable cuDNN / cuBLAS TF32 so the reference is an fp32 oracle (SURVEY D9)")
     ap.add_argument("--no-fused-optimizers", action="store_true", help="keep torch.optim instead of fusion_gcn_b200.optim")
@@ -148,7 +151,7 @@ def main(argv=None) -> None:
             torch.backends.cudnn.allow_tf32 = False
             torch.backends.cuda.matmul.allow_tf32 = False
     else:
-        install(root, args.precision, fused_optimizers=not args.no_fused_optimizers, prefetch=not args.no_prefetch)
+        install(root, args.precision, fused_optimizers=not args.no_fused_optimizers, prefetch=not args.no_prefetch, recompute=args.recompute)
         from . import capi
         capi.lib()                                           # fail before training starts if the extension is not built
     if args.trace_loss:
