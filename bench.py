@@ -135,6 +135,9 @@ def run_ours(args):
         n_local = args.batch // world         # strong scaling: the GLOBAL batch is fixed (BASELINE configs[1]: N=64 sharded 32/16/8 per GPU)
     else:
         n_local = args.batch                  # weak scaling: fixed per-GPU batch
+    if args.no_overlap:
+        import fusion_gcn_b200.functional as FN_
+        FN_.set_overlap_leaves(False)
     model = build_model(args.workload, args.precision, dev, recompute=args.recompute)
     if args.sync_bn and world > 1:
         from fusion_gcn_b200 import modules as M_
@@ -373,6 +376,7 @@ def run_ours(args):
                    "parallelism": f"dp{world} (batch shards, NCCL gradient all-reduce)" if world > 1 else "single GPU",
                    "launch_mode": "one CUDA graph per step (fusion_gcn_b200.graphed.GraphedStep)" if graph_ok else "eager launches",
                    "batchnorm": "synchronised over the ranks (--sync-bn)" if (args.sync_bn and world > 1) else "per-replica statistics",
+                   "streams": "weight gradients on the main stream (--no-overlap)" if args.no_overlap else "weight gradients on a side stream beside the main chain",
                    "activation_policy": "theta/phi and the aggregated tensor recomputed in the backward (--recompute)" if args.recompute
                                         else "all activations kept"},
         "peak_memory_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2),
@@ -611,6 +615,7 @@ def main():
     ap.add_argument("--no-strong", action="store_true", help="N > 1, weak scaling: skip the extra strong-scaling timing (global batch = --batch)")
     ap.add_argument("--dump-kernels", default=None, help="write the per-signature timing table (all C-ABI launches) to this JSON file")
     ap.add_argument("--sync-bn", action="store_true", help="N > 1: synchronised BatchNorm (modules.set_sync_batchnorm), default per-replica statistics")
+    ap.add_argument("--no-overlap", action="store_true", help="weight gradients on the main stream (functional.OVERLAP_LEAVES off), for A/B")
     ap.add_argument("--recompute", action="store_true", help="activation-recompute policy (modules.set_recompute): less memory, two more launches per unit")
     ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay timing")
     ap.add_argument("--no-tf32", action="store_true", help="skip the extra TF32-mode timing that the fp32 run reports beside the headline")

@@ -112,6 +112,50 @@ def _t(w):
     return w.permute(2, 1, 0).contiguous()
 
 
+# Weight gradients are LEAVES of the backward pass: nothing downstream in the unit reads them.  With OVERLAP_LEAVES they are launched on a
+# side stream, so that the tensor-bound weight-gradient kernel of the temporal convolution shares the SMs with the HBM-bound BatchNorm
+# backward that follows on the main stream (its CTAs need 0-12 KB of shared memory and fit beside the persistent CTA), instead of the
+# two running back to back.  Fork / join are stream waits (capturable in the step's CUDA graph); the join happens before the unit's
+# backward returns, so autograd, gradient hooks and optimizers see ordinary main-stream tensors.
+OVERLAP_LEAVES = True
+_side_streams = {}
+
+
+def set_overlap_leaves(flag: bool) -> None:
+    global OVERLAP_LEAVES
+    OVERLAP_LEAVES = bool(flag)
+
+
+class _Leaves:
+    def __init__(self, like):
+        self.on = bool(OVERLAP_LEAVES and like is not None and like.is_cuda)
+        self.side = None
+        self.keep = []
+
+    def run(self, fn, *inputs):
+        """fn() on the side stream, after everything enqueued on the current stream so far.  ``inputs`` (main-stream tensors the
+        side kernels read) are kept alive until join(), so the caching allocator cannot hand their memory to a later main-stream
+        allocation while the side kernel still reads it."""
+        if not self.on:
+            return fn()
+        cur = torch.cuda.current_stream()
+        if self.side is None:
+            key = (cur.device.index, cur.cuda_stream)
+            self.side = _side_streams.get(key)
+            if self.side is None:
+                self.side = _side_streams[key] = torch.cuda.Stream(device=cur.device)
+        self.side.wait_stream(cur)
+        self.keep.extend(t for t in inputs if t is not None)
+        with torch.cuda.stream(self.side):
+            return fn()
+
+    def join(self):
+        if self.side is not None:
+            torch.cuda.current_stream().wait_stream(self.side)
+            self.side = None
+        self.keep.clear()
+
+
 # =============================================================================== gcn half
 def gcn_forward(x, adj_a, adj_b, wa, ba, wb, bb, wd, bd, bn_w, bn_b, down_w, down_b, dbn_w, dbn_b, spec: UnitSpec, ctx):
     nb, t, v, cin = x.shape
@@ -168,9 +212,12 @@ def gcn_forward(x, adj_a, adj_b, wa, ba, wb, bb, wd, bd, bn_w, bn_b, down_w, dow
     return o
 
 
-def gcn_backward(d_o, ctx, bn_w, dbn_w, down_w, spec: UnitSpec, dx=None, need_dx=True):
+def gcn_backward(d_o, ctx, bn_w, dbn_w, down_w, spec: UnitSpec, dx=None, need_dx=True, leaves=None):
     """Returns (dx, grads) where grads follows the parameter order of gcn_forward.  ``dx`` may carry
-    an already-written gradient buffer to accumulate into."""
+    an already-written gradient buffer to accumulate into.  ``leaves``: the caller's _Leaves (it joins); None = own, joined here."""
+    own_leaves = leaves is None
+    if own_leaves:
+        leaves = _Leaves(d_o)
     x, e, p, g, z, y, o = ctx["x"], ctx["e"], ctx["p"], ctx["g"], ctx["z"], ctx["y"], ctx["o"]
     nb, t, v, cin = x.shape
     cout, ci, prec = spec.cout, ctx["ci"], spec.precision
@@ -191,7 +238,7 @@ def gcn_backward(d_o, ctx, bn_w, dbn_w, down_w, spec: UnitSpec, dx=None, need_dx
             dy, dgam, dbet = K.bn_bwd(d_o, o, y, ctx["mean"], ctx["invstd"], bn_w, mask_bits=ctx["o_bits"], frozen=frozen, **sk)
             dyd, dgam2, dbet2 = K.bn_bwd(d_o, o, ctx["yd"], ctx["mean2"], ctx["invstd2"], dbn_w, mask_bits=ctx["o_bits"], frozen=frozen, **sk)
         wdown = down_w.reshape(cout, 1, cin)
-        d_down_w, d_down_b = K.conv_wgrad(dyd, x, want_bias=frozen, precision=prec)
+        d_down_w, d_down_b = leaves.run(lambda: K.conv_wgrad(dyd, x, want_bias=frozen, precision=prec), dyd, x)
         if not frozen:
             d_down_b = _zero_bias(x, cout)
         if need_dx:
@@ -204,11 +251,11 @@ def gcn_backward(d_o, ctx, bn_w, dbn_w, down_w, spec: UnitSpec, dx=None, need_dx
                                   dres=dx if need_dx else None, dres_accumulate=have, mask_bits=ctx["o_bits"], frozen=frozen, **sk)
         have = have or need_dx
         dgam2 = dbet2 = d_down_w = d_down_b = None
-    d_wdc, d_bdc = K.conv_wgrad(dy, z, want_bias=frozen, precision=prec)
+    dz = K.conv_fwd(dy, _t(ctx["wdc"]), precision=prec)                                # [nb,t,v,3*cin]
+    d_wdc, d_bdc = leaves.run(lambda: K.conv_wgrad(dy, z, want_bias=frozen, precision=prec), dy, z)
     del z
     if not frozen:
         d_bdc = _zero_bias(x, cout)
-    dz = K.conv_fwd(dy, _t(ctx["wdc"]), precision=prec)                                # [nb,t,v,3*cin]
     dg_part = K.joint_gram(x, dz, groups=3, offa=0, stridea=0, offb=0, strideb=cin, width=cin, nchunk=K.pick_nchunk(nb, t, v, cin),
                            precision=prec)
     ds, d_adj_b = K.attention_bwd(dg_part, p, ctx["scale"])
@@ -219,11 +266,14 @@ def gcn_backward(d_o, ctx, bn_w, dbn_w, down_w, spec: UnitSpec, dx=None, need_dx
     if e is None:
         e = K.conv_fwd(x, ctx["wab"], ctx["bab"], precision=prec)
     de, d_bab = K.joint_mix_score_bwd(e, ds, width=ci, precision=prec)
-    d_wab, d_bab2 = K.conv_wgrad(de, x, want_bias=d_bab is None, precision=prec)
+    want_bab = d_bab is None
+    d_wab, d_bab2 = leaves.run(lambda: K.conv_wgrad(de, x, want_bias=want_bab, precision=prec), de, x)
     if d_bab is None:
         d_bab = d_bab2
     if need_dx:
         dx = K.conv_fwd(de, _t(ctx["wab"]), out=dx, accumulate=have, precision=prec)
+    if own_leaves:
+        leaves.join()
     # unpack
     d_wa = [d_wab[(2 * k) * ci:(2 * k + 1) * ci].reshape(ci, cin, 1, 1) for k in range(3)]
     d_wb = [d_wab[(2 * k + 1) * ci:(2 * k + 2) * ci].reshape(ci, cin, 1, 1) for k in range(3)]
@@ -285,8 +335,11 @@ def tcn_forward(o, x_res, wt, bt, bn_w, bn_b, wr, br, rbn_w, rbn_b, spec: UnitSp
     return out
 
 
-def tcn_backward(d_out, ctx, bn_w, rbn_w, spec: UnitSpec, need_dres=True, need_do=True):
-    """Returns (d_o, d_xres, grads)."""
+def tcn_backward(d_out, ctx, bn_w, rbn_w, spec: UnitSpec, need_dres=True, need_do=True, leaves=None):
+    """Returns (d_o, d_xres, grads).  ``leaves``: the caller's _Leaves (it joins); None = own, joined here."""
+    own_leaves = leaves is None
+    if own_leaves:
+        leaves = _Leaves(d_out)
     o, x_res, u, out = ctx["t_o"], ctx["t_x"], ctx["u"], ctx["out"]
     o_shape = ctx["t_o_shape"]              # (`o` itself is released when its bf16 pieces serve the weight gradient, see UnitFn.forward)
     s, pad, prec = spec.stride, ctx["pad"], spec.precision
@@ -323,7 +376,7 @@ def tcn_backward(d_out, ctx, bn_w, rbn_w, spec: UnitSpec, need_dres=True, need_d
             du_split = sp[0] if sp else None
             pk.pop("want_split", None)
             dur, dgam2, dbet2 = K.bn_bwd(d_out, mask, ctx["ur"], ctx["t_mean2"], ctx["t_invstd2"], rbn_w, mask_bits=bits, **pk)
-        d_wrp, d_br = K.conv_wgrad(dur, x_res, taps=1, stride=s, pad=0, want_bias=frozen, precision=prec)
+        d_wrp, d_br = leaves.run(lambda: K.conv_wgrad(dur, x_res, taps=1, stride=s, pad=0, want_bias=frozen, precision=prec), dur, x_res)
         if not frozen:
             d_br = _zero_bias(d_out, d_wrp.shape[0])
         d_wr = d_wrp.permute(0, 2, 1).unsqueeze(-1)
@@ -332,17 +385,20 @@ def tcn_backward(d_out, ctx, bn_w, rbn_w, spec: UnitSpec, need_dres=True, need_d
     else:
         du, dgam, dbet, *sp = K.bn_bwd(d_out, mask, u, ctx["t_mean"], ctx["t_invstd"], bn_w, mask_bits=bits, **pk)
         du_split = sp[0] if sp else None
-    d_wtp = None
-    if du_split is not None and o_split is not None:
-        d_wtp = K.conv_wgrad_presplit(du_split, o_split, o_shape[:3], taps=ksz, stride=s, pad=pad)
-        d_bt = _zero_bias(d_out, du.shape[-1])
-    if d_wtp is None:
-        d_wtp, d_bt = K.conv_wgrad(du, o, taps=ksz, stride=s, pad=pad, want_bias=frozen, precision=prec)
-        if not frozen:
-            d_bt = _zero_bias(d_out, d_wtp.shape[0])
+    # the input gradient first (the gcn half's BatchNorm backward waits for it), then the weight gradient as a leaf beside that pass
     d_o = None
     if need_do:
         d_o = K.conv_fwd(du, _t(ctx["wtp"]), t_out=o_shape[1], stride=s, pad=pad, transposed=True, precision=prec)
+    d_wtp = None
+    if du_split is not None and o_split is not None:
+        d_wtp = leaves.run(lambda: K.conv_wgrad_presplit(du_split, o_split, o_shape[:3], taps=ksz, stride=s, pad=pad), du_split, o_split)
+        d_bt = _zero_bias(d_out, du.shape[-1])
+    if d_wtp is None:
+        d_wtp, d_bt = leaves.run(lambda: K.conv_wgrad(du, o, taps=ksz, stride=s, pad=pad, want_bias=frozen, precision=prec), du, o)
+        if not frozen:
+            d_bt = _zero_bias(d_out, d_wtp.shape[0])
+    if own_leaves:
+        leaves.join()
     grads = dict(wt=d_wtp.permute(0, 2, 1).unsqueeze(-1), bt=d_bt, bn_w=dgam, bn_b=dbet, wr=d_wr, br=d_br, rbn_w=dgam2, rbn_b=dbet2)
     return d_o, d_xres, grads
 
@@ -455,8 +511,11 @@ class UnitFn(torch.autograd.Function):
         _need_backward(spec, ctx.store)
         gp, tp = params[:GCN_NPARAMS], params[GCN_NPARAMS:]
         need_dx = ctx.needs_input_grad[0]
-        d_o, d_xres, tg = tcn_backward(d_out.contiguous(), ctx.store, tp[2], tp[6], spec, need_dres=need_dx, need_do=True)
-        dx, gg = gcn_backward(d_o, ctx.store, gp[20], gp[24], gp[22], spec, dx=d_xres, need_dx=need_dx)
+        d_out = d_out.contiguous()
+        leaves = _Leaves(d_out)
+        d_o, d_xres, tg = tcn_backward(d_out, ctx.store, tp[2], tp[6], spec, need_dres=need_dx, need_do=True, leaves=leaves)
+        dx, gg = gcn_backward(d_o, ctx.store, gp[20], gp[24], gp[22], spec, dx=d_xres, need_dx=need_dx, leaves=leaves)
+        leaves.join()
         ctx.store = None
         return (dx, None, *_like(_gcn_grad_tuple(gg) + _tcn_grad_tuple(tg), params))
 

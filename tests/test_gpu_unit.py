@@ -352,3 +352,62 @@ def test_sync_batchnorm_halves_on_mirrored_ranks(pkg, start, shape):
             assert stat_err(a, b) <= 1e-6, k
         elif "running_var" in k:                     # unbiased over 2m rows instead of m
             assert stat_err(a, b) <= 1e-3, k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cin,cout,stride", [(64, 64, 1), (64, 128, 2), (3, 64, 1)])
+def test_weight_gradients_on_the_side_stream_change_nothing(pkg, cin, cout, stride):
+    """functional.OVERLAP_LEAVES: the weight-gradient kernels run on a side stream beside the main chain; same kernels, same inputs,
+    so every result must be bit-identical to the single-stream run -- also when the step is repeated (allocator reuse across streams)
+    and when it is captured in a CUDA graph."""
+    import copy
+    import fusion_gcn_b200.functional as FN
+    from fusion_gcn_b200 import graph as G
+    from fusion_gcn_b200 import modules as M
+    torch.manual_seed(11)
+    unit = M.SpatialTemporalConv(cin, cout, G.partition_adjacency(G.NTU_EDGES), stride=stride, residual=cin != 3).cuda().train()
+    x = torch.randn(8, cin, 60, 25, device="cuda")
+    w = torch.randn(8, cout, (60 - 1) // stride + 1, 25, device="cuda")
+
+    def run(mod, reps):
+        res = None
+        for _ in range(reps):
+            mod.zero_grad(set_to_none=True)
+            xi = x.clone().requires_grad_(True)
+            (mod(xi) * w).sum().backward()
+            res = (xi.grad, {k: p.grad.clone() for k, p in mod.named_parameters()})
+        torch.cuda.synchronize()
+        return res
+
+    assert FN.OVERLAP_LEAVES
+    try:
+        FN.set_overlap_leaves(False)
+        dx0, g0 = run(copy.deepcopy(unit), 1)
+    finally:
+        FN.set_overlap_leaves(True)
+    dx1, g1 = run(copy.deepcopy(unit), 3)
+    assert torch.equal(dx0, dx1)
+    for k in g0:
+        assert torch.equal(g0[k], g1[k]), k
+    # captured: fork / join of the side stream inside one CUDA graph
+    mod = copy.deepcopy(unit)
+    xs = x.clone().requires_grad_(True)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            mod.zero_grad(set_to_none=True)
+            xs.grad = None
+            (mod(xs) * w).sum().backward()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    mod.zero_grad(set_to_none=True)
+    xs.grad = None
+    with torch.cuda.graph(graph):
+        (mod(xs) * w).sum().backward()
+    for _ in range(2):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(xs.grad, dx0)
+    for k, p in mod.named_parameters():
+        assert torch.equal(p.grad, g0[k]), k

@@ -24,9 +24,11 @@ KEEP = ["sm__throughput.avg.pct_of_peak_sustained_elapsed", "dram__throughput.av
 
 def signatures(case):
     """bench.py launch signatures (ops.py `sig=`) a bench_stage.py case corresponds to."""
-    m = re.match(r"(conv|wgrad)_(emb|proj|dproj|tconv)_(c\d+)$", case)
+    m = re.match(r"(conv|wgrad|wgradpre)_(emb|proj|dproj|tconv)_(c\d+)$", case)
     if m:
         kind, nm, tag = m.groups()
+        if kind == "wgradpre":          # the pre-split form is what the step runs for the temporal convolutions (alias agcn_conv_wgrad)
+            kind = "wgrad"
         c, t = SHAPES[tag]
         cin, cout, taps = {"emb": (c, 6 * (c // 4), 1), "proj": (3 * c, c, 1), "dproj": (c, 3 * c, 1), "tconv": (c, c, 9)}[nm]
         if kind == "wgrad":
