@@ -20,7 +20,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, layers):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -32,13 +32,15 @@ def _worker(rank, world, port, out):
         from fusion_gcn_b200 import graph as G, modules as M
         from fusion_gcn_b200.distributed import GradientAllReducer, SyncBatchNorm, shard_batch
         from helpers import ZERO_GRAD, rel_err, stat_err
+        from oracle import agcn_oracle as O
+        # full width, the oracle's loud initialisation; `layers` units
         shape, ncls, n_global = (2, 40, 25, 3), 12, 8
         torch.manual_seed(5)                                       # same model and data on every rank
         graph = G.SkeletonGraph(G.NTU_EDGES, center_joint=G.NTU_CENTER)
-        model = M.Model(shape, ncls, graph, start_feature_size=64).to(dev).train()
-        for p in model.parameters():
-            if p.dim() == 1:
-                p.data.add_(0.2 * torch.randn_like(p))
+        state = O.init_state(G.adjacency_from_graph(graph), shape, ncls, start=64, num_layers=layers, seed=3, loud=True)
+        model = M.Model(shape, ncls, graph, start_feature_size=64, num_layers=layers)
+        model.load_state_dict(state, strict=True)
+        model = model.to(dev).train()
         x = torch.randn(n_global, *shape, device=dev)
         w = torch.randn(n_global, ncls, device=dev)
         full = copy.deepcopy(model)                                # the unsharded batch on one GPU: what the reference computes
@@ -75,29 +77,40 @@ def _worker(rank, world, port, out):
         g_full = torch.cat([q.grad.reshape(-1) for q in full.parameters()])
         unsync_l2 = float((g_plain.double() - g_full.double()).norm() / g_full.double().norm())
         stats = max(stat_err(a, b) for (k, a), b in zip(sharded.state_dict().items(), full.state_dict().values()) if "running" in k)
+        # conditioning of the model itself: the SAME unsharded batch on the FFMA kernels (another summation order, every product exact in
+        # fp32) -- how far two correct fp32 evaluations of these gradients are apart
+        calib = M.set_precision(copy.deepcopy(model), "fp32_ffma")
+        (calib(x) * w).sum().backward()
+        noise_l2 = max(float((c.grad.double() - q.grad.double()).norm() / q.grad.double().norm().clamp_min(1e-30))
+                       for (k, c), q in zip(calib.named_parameters(), full.parameters()) if not ZERO_GRAD.search(k))
         if rank == 0:
             names.sort(reverse=True)
-            out.put((float(err_y), float(worst), float(worst_l2), float(stats), unsync_l2, names[:4]))
+            out.put((float(err_y), float(worst), float(worst_l2), float(stats), unsync_l2, noise_l2, names[:4]))
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.timeout(600)
-def test_two_gpu_sync_batchnorm_matches_the_unsharded_batch():
+@pytest.mark.parametrize("layers", [5, 10])
+def test_two_gpu_sync_batchnorm_matches_the_unsharded_batch(layers):
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out, layers)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
         p.join(timeout=560)
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
-    err_y, worst, worst_l2, stats, unsync_l2, names = out.get(timeout=5)
-    print(f"[sync-bn over NCCL] y {err_y:.2e}, gradients: worst max-norm {worst:.2e}, worst L2 {worst_l2:.2e}, running statistics {stats:.2e}; "
-          f"unsynchronised shards L2 {unsync_l2:.2e}; worst tensors {[(f'{a:.1e}', f'{b:.1e}', k) for a, b, k in names]}")
+    err_y, worst, worst_l2, stats, unsync_l2, noise_l2, names = out.get(timeout=5)
+    print(f"[sync-bn over NCCL, {layers} units] y {err_y:.2e}, gradients: worst max-norm {worst:.2e}, worst L2 {worst_l2:.2e}, running statistics "
+          f"{stats:.2e}; unsynchronised shards L2 {unsync_l2:.2e}; two fp32 evaluations of the unsharded batch L2 {noise_l2:.2e}; "
+          f"worst tensors {[(f'{a:.1e}', f'{b:.1e}', k) for a, b, k in names]}")
     assert err_y <= 1e-5 and stats <= 1e-5, (err_y, stats)
-    assert worst_l2 <= 2e-3 and worst <= 5e-2, (worst_l2, worst, names)
-    assert unsync_l2 >= 10 * max(worst_l2, 1e-3), (unsync_l2, worst_l2)
+    # the gradients of the sharded, synchronised run against the unsharded batch: as close as two correct fp32 evaluations of the
+    # unsharded batch are to each other (loud-init stacks on 8 sequences amplify forward rounding differences of 4e-7 and ReLU ties),
+    # and orders of magnitude closer than the unsynchronised shards
+    assert worst_l2 <= max(1e-4, 4 * noise_l2), (worst_l2, noise_l2, names)
+    assert unsync_l2 >= 20 * worst_l2, (unsync_l2, worst_l2)
