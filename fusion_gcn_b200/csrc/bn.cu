@@ -18,15 +18,6 @@ struct RowMap {
     }
 };
 
-// The streaming BatchNorm kernels may run BESIDE a persistent tensor-core kernel of another stream (the weight-gradient leaves of the
-// backward, functional.py): that kernel runs with the maximal shared-memory carveout, and an SM does not change its carveout while a
-// CTA is resident, so a kernel that prefers the default (L1-heavy) split waits for the SM to drain.  These kernels stream every byte
-// once and have no use for L1; preferring the maximal carveout lets their CTAs slot in next to the resident one.
-template <typename Kern>
-static void prefer_shared(Kern kern) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-}
-
 static int num_partials(long long rows) {
     long long p = (rows + 63) / 64;
     if (p > kMaxPartials) p = kMaxPartials;
@@ -651,7 +642,6 @@ static int launch_colsum(const float* x, const float* dout, const float* mask, c
     if (vec) {
         const int lanes_r = 256 / cq;
         size_t smem = (size_t)2 * lanes_r * m.channels * sizeof(float);
-        prefer_shared(colsum_vec_kernel<MODE>);
         colsum_vec_kernel<MODE><<<P, 256, smem, s>>>(x, dout, mask, mask_bits, mean, invstd, m, rows, part, bcast_rows, bcast_scale);
     } else {
         dim3 grid((unsigned)P, (unsigned)ceil_div(m.channels, 32));
@@ -814,7 +804,6 @@ static int bn_bwd_impl(const float* dout, const float* mask_out, const unsigned*
     } else {
         rc = launch_colsum<1>(y, dout, mask_out, save_mean, save_invstd, m, rows, part, P, s, mask_bits, bcast_rows, bcast_scale);
         if (rc) return rc;
-        prefer_shared(bn_bwd_finalize_kernel);
         bn_bwd_finalize_kernel<<<ceil_div(channels, kFinCh), kFinCh * kFinLanes, 0, s>>>(part, P, channels, (double)rows, gamma, save_mean, save_invstd, dgamma, dbeta, coef, frozen);
     }
     rc = check_launch("agcn_bn_bwd(finalize)");
@@ -823,7 +812,6 @@ static int bn_bwd_impl(const float* dout, const float* mask_out, const unsigned*
     if (dy_split != nullptr)
         AGCN_REQUIRE(dy != nullptr && outer == 1 && aligned16(dy_split) && vec_ok(m, {dout, mask_out, y, dy, dres, coef}), AGCN_ERR_UNSUPPORTED,
                      "agcn_bn_bwd_bits_split: contiguous, vectorisable layout and a dy output required");
-    prefer_shared(bn_bwd_apply_kernel<true>);
     if (vec_ok(m, {dout, mask_out, y, dy, dres, coef}))
         bn_bwd_apply_kernel<true><<<elementwise_blocks(rows * (channels / 4)), 256, 0, s>>>(dout, mask_out, mask_bits, y, coef, dy, dres, dres_accumulate, m, rows,
                                                                                             bcast_rows, bcast_scale, dy_split);
@@ -887,9 +875,6 @@ extern "C" AGCN_API int agcn_bn_bwd_bits_dual(const float* dout, const unsigned*
     float* coef_b = part_b + (size_t)kMaxPartials * 2 * channels;
     const int cq = channels / 4;
     const size_t smem = (size_t)3 * (256 / cq) * channels * sizeof(float);
-    prefer_shared(colsum_dual_kernel);
-    prefer_shared(bn_bwd_apply_dual_kernel);
-    prefer_shared(bn_bwd_finalize_kernel);
     colsum_dual_kernel<<<P, 256, smem, s>>>(y_a, y_b, dout, mask_bits, mean_a, invstd_a, mean_b, invstd_b, channels, rows, part_a, part_b);
     int rc = check_launch("agcn_bn_bwd_bits_dual(sums)");
     if (rc) return rc;
