@@ -35,7 +35,7 @@ for step in "$@"; do
     workloads) for w in utd mmact_imu utd_rgb; do python bench.py --workload $w --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_bench_${w}.json 2> gpurun_out/${tag}_bench_${w}.err; python -c "import json;d=json.load(open('gpurun_out/${tag}_bench_${w}.json'));print('$w',d['value'],d['tf32_mode']['value'])"; done ;;
     launches)  # ncu launch list of one short bench run (a number printed under ncu is never a bench value) + per-kernel summary
                ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-tf32 --no-graph > gpurun_out/${tag}_launches_bench.log 2>&1
-               python tools/launch_summary.py gpurun_out/${tag}_launches.csv 1 > gpurun_out/${tag}_launch_summary.txt 2>&1; head -14 gpurun_out/${tag}_launch_summary.txt ;;
+               python tools/launch_summary.py gpurun_out/${tag}_launches.csv 0 > gpurun_out/${tag}_launch_summary.txt 2>&1; head -14 gpurun_out/${tag}_launch_summary.txt ;;
     *) echo "unknown step $step" ;;
   esac
 done
