@@ -122,6 +122,7 @@ def _sync_worker(rank, world, port, n_global, out):
         model = M.Model(shape, ncls, graph, start_feature_size=start, num_layers=LAYERS)
         model.load_state_dict(state, strict=True)
         M.set_sync_batchnorm(model, SyncBatchNorm())
+        M.set_recompute(model, rank == 1)               # the policies compose: one rank recomputes theta / phi and z, the other keeps them
         assert model._agcn_sync is not None and model.l0.gcn1._agcn_sync is model._agcn_sync and model._agcn_sync.world == world
         model.train()
         reducer = GradientAllReducer(model.parameters(), bucket_bytes=4096)
