@@ -280,7 +280,7 @@ def gcn_backward(d_o, ctx, bn_w, dbn_w, down_w, spec: UnitSpec, dx=None, need_dx
     d_ba = [d_bab[(2 * k) * ci:(2 * k + 1) * ci] for k in range(3)]
     d_bb = [d_bab[(2 * k + 1) * ci:(2 * k + 2) * ci] for k in range(3)]
     d_wd = [d_wdc[:, 0, k * cin:(k + 1) * cin].reshape(cout, cin, 1, 1) for k in range(3)]
-    d_bd = [d_bdc, d_bdc, d_bdc]
+    d_bd = [d_bdc, d_bdc.clone(), d_bdc.clone()]       # three parameters, three tensors: .grad tensors must not alias (in-place unscale / clipping)
     grads = dict(adj_b=d_adj_b, wa=d_wa, ba=d_ba, wb=d_wb, bb=d_bb, wd=d_wd, bd=d_bd, bn_w=dgam, bn_b=dbet,
                  down_w=None if d_down_w is None else d_down_w.reshape(cout, cin, 1, 1), down_b=d_down_b,
                  dbn_w=dgam2, dbn_b=dbet2)
@@ -330,7 +330,7 @@ def tcn_forward(o, x_res, wt, bt, bn_w, bn_b, wr, br, rbn_w, rbn_b, spec: UnitSp
     else:
         out, out_bits = apply(u, sc, sh, relu=spec.relu_out)
     if ctx is not None:
-        ctx.update(t_o=o.detach(), t_o_shape=tuple(o.shape), t_x=x_res, u=u, ur=ur, out=None if pool else out.detach(), out_bits=out_bits, t_mean=mean, t_invstd=invstd,
+        ctx.update(t_o=o.detach(), t_o_shape=tuple(o.shape), t_x=x_res, u=u, ur=ur, out=None if (pool or out_bits is not None or not spec.relu_out) else out.data, out_bits=out_bits, t_mean=mean, t_invstd=invstd,
                    t_mean2=mean2, t_invstd2=invstd2, wtp=wtp, wrp=wrp, pad=pad, pool_rows=(u.numel() // u.shape[-1] // pool) if pool else 0)
     return out
 
@@ -436,16 +436,31 @@ def _like(grads, params):
     return [None if (g is None or p is None) else g.reshape(p.shape) for g, p in zip(grads, params)]
 
 
-def _need_backward(spec, store=True):
-    if store is None:
-        raise RuntimeError("fusion_gcn_b200: backward through the same forward a second time (retain_graph=True) is not supported: "
-                           "the saved activations are released after the first backward")
-
-
 def _store(ctx, spec):
     """Activation store of one forward: a dict when a backward can follow (training mode, or eval mode with an input or parameter
     that requires a gradient), None otherwise -- eval mode then takes the fused, nothing-saved path."""
     return {} if (spec.training or (spec.grad_enabled and any(ctx.needs_input_grad))) else None
+
+
+def _stash(ctx, store):
+    """Hands the activation store to autograd: the tensors go through ``save_for_backward`` (the engine releases them as soon as the
+    node's backward has run, keeps them under ``retain_graph=True`` -- a second backward then works -- and checks their version
+    counters), everything else stays on the ctx."""
+    ctx.has_store = store is not None
+    if store is None:
+        return
+    keys = [k for k, v in store.items() if isinstance(v, torch.Tensor)]
+    ctx.save_for_backward(*[store[k] for k in keys])
+    ctx.store_keys = keys
+    ctx.store_meta = {k: v for k, v in store.items() if not isinstance(v, torch.Tensor)}
+
+
+def _unstash(ctx):
+    if not ctx.has_store:
+        raise RuntimeError("fusion_gcn_b200: this forward ran under torch.no_grad() in eval mode (fused path, nothing saved): no backward")
+    store = dict(ctx.store_meta)
+    store.update(zip(ctx.store_keys, ctx.saved_tensors))      # raises torch's own error on a second backward without retain_graph
+    return store
 
 
 class GcnFn(torch.autograd.Function):
@@ -455,15 +470,14 @@ class GcnFn(torch.autograd.Function):
     def forward(ctx, x, spec, *params):
         store = _store(ctx, spec)
         o = gcn_forward(x, *_split_gcn(params), spec, store)
-        ctx.spec, ctx.store, ctx.params = spec, store, params
+        ctx.spec, ctx.params = spec, params
+        _stash(ctx, store)
         return o
 
     @staticmethod
     def backward(ctx, d_o):
         spec, p = ctx.spec, ctx.params
-        _need_backward(spec, ctx.store)
-        dx, g = gcn_backward(d_o.contiguous(), ctx.store, p[20], p[24], p[22], spec, need_dx=ctx.needs_input_grad[0])
-        ctx.store = None
+        dx, g = gcn_backward(d_o.contiguous(), _unstash(ctx), p[20], p[24], p[22], spec, need_dx=ctx.needs_input_grad[0])
         return (dx, None, *_like(_gcn_grad_tuple(g), p))
 
 
@@ -474,16 +488,15 @@ class TcnFn(torch.autograd.Function):
     def forward(ctx, o, x_res, spec, *params):
         store = _store(ctx, spec)
         out = tcn_forward(o, x_res, *params, spec, store)
-        ctx.spec, ctx.store, ctx.params = spec, store, params
+        ctx.spec, ctx.params = spec, params
+        _stash(ctx, store)
         return out
 
     @staticmethod
     def backward(ctx, d_out):
         spec, p = ctx.spec, ctx.params
-        _need_backward(spec, ctx.store)
-        d_o, d_xres, g = tcn_backward(d_out.contiguous(), ctx.store, p[2], p[6], spec,
+        d_o, d_xres, g = tcn_backward(d_out.contiguous(), _unstash(ctx), p[2], p[6], spec,
                                       need_dres=ctx.needs_input_grad[1], need_do=ctx.needs_input_grad[0])
-        ctx.store = None
         return (d_o, d_xres, None, *_tcn_grad_tuple(g))
 
 
@@ -502,21 +515,21 @@ class UnitFn(torch.autograd.Function):
             # the fp32 copy is not kept, so the split operand costs no activation memory
             store["o"] = None
             store["t_o"] = None
-        ctx.spec, ctx.store, ctx.params = spec, store, params
+        ctx.spec, ctx.params = spec, params
+        _stash(ctx, store)
         return out
 
     @staticmethod
     def backward(ctx, d_out):
         spec, params = ctx.spec, ctx.params
-        _need_backward(spec, ctx.store)
+        store = _unstash(ctx)
         gp, tp = params[:GCN_NPARAMS], params[GCN_NPARAMS:]
         need_dx = ctx.needs_input_grad[0]
         d_out = d_out.contiguous()
         leaves = _Leaves(d_out)
-        d_o, d_xres, tg = tcn_backward(d_out, ctx.store, tp[2], tp[6], spec, need_dres=need_dx, need_do=True, leaves=leaves)
-        dx, gg = gcn_backward(d_o, ctx.store, gp[20], gp[24], gp[22], spec, dx=d_xres, need_dx=need_dx, leaves=leaves)
+        d_o, d_xres, tg = tcn_backward(d_out, store, tp[2], tp[6], spec, need_dres=need_dx, need_do=True, leaves=leaves)
+        dx, gg = gcn_backward(d_o, store, gp[20], gp[24], gp[22], spec, dx=d_xres, need_dx=need_dx, leaves=leaves)
         leaves.join()
-        ctx.store = None
         return (dx, None, *_like(_gcn_grad_tuple(gg) + _tcn_grad_tuple(tg), params))
 
 

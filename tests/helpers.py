@@ -130,3 +130,22 @@ def recompute_case(M, G, device, cin=8, cout=16, stride=2, v=25, t=12, nb=3):
     for k in g0:
         assert torch.equal(g0[k], g1[k]), k
 
+
+
+def second_backward_case(unit, x):
+    """The activation store goes through save_for_backward: a second backward through the same forward works under retain_graph=True
+    (gradients accumulate: twice the first) and raises torch's own error without it."""
+    import pytest
+    x = x.detach().clone().requires_grad_(True)
+    unit.zero_grad(set_to_none=True)
+    out = unit(x)
+    out.sum().backward(retain_graph=True)
+    first = {k: p.grad.clone() for k, p in unit.named_parameters() if p.grad is not None}
+    dx = x.grad.clone()
+    out.sum().backward()
+    assert rel_err(x.grad, 2 * dx) <= 1e-6
+    for k, p in unit.named_parameters():
+        if k in first and float(first[k].abs().max()) > 0:
+            assert rel_err(p.grad, 2 * first[k]) <= 1e-6, k
+    with pytest.raises(RuntimeError, match="second time|already been freed"):
+        out.sum().backward()

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import (ZERO_GRAD, MODEL_FIXTURES, RESIDUAL_KINDS, UNIT_FIXTURES, check_grads, eval_mode_gradient_case, load_golden, recompute_case, rel_err, stat_err,
+from helpers import (ZERO_GRAD, MODEL_FIXTURES, RESIDUAL_KINDS, UNIT_FIXTURES, check_grads, eval_mode_gradient_case, load_golden, recompute_case, rel_err, second_backward_case, stat_err,
                      sub, to_t)
 from oracle import agcn_oracle as O
 
@@ -168,10 +168,7 @@ def test_standalone_modules_reference_layout(pkg):
     xg = x.clone().requires_grad_(True)
     unit(xg).sum().backward()
     assert xg.grad is not None and torch.isfinite(xg.grad).all() and float(unit.tcn1.conv.bias.grad.abs().max()) > 0
-    with pytest.raises(RuntimeError):                        # the activations are released by the first backward
-        out = unit(xg)
-        out.sum().backward(retain_graph=True)
-        out.sum().backward()
+    second_backward_case(unit, xg)
 
 
 @pytest.mark.parametrize("name", UNIT_FIXTURES)

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import (MODEL_FIXTURES, RESIDUAL_KINDS, UNIT_FIXTURES, check_grads, eval_mode_gradient_case, load_golden, recompute_case, rel_err, stat_err, sub,
+from helpers import (MODEL_FIXTURES, RESIDUAL_KINDS, UNIT_FIXTURES, check_grads, eval_mode_gradient_case, load_golden, recompute_case, second_backward_case, rel_err, stat_err, sub,
                      to_t)
 from fusion_gcn_b200 import graph as G
 from fusion_gcn_b200 import modules as M
@@ -271,3 +271,10 @@ def test_eval_no_grad_takes_the_fused_nothing_saved_path(torch_stage_backend, mo
     y1 = model(x)                                   # grad mode on, parameters require grad: a backward may follow
     assert calls["conv_fwd_post"] == 0 and calls["bn_apply"] == 22, calls
     assert rel_err(y0, y1.detach()) <= 1e-6
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_second_backward_through_the_same_forward(torch_stage_backend, training):
+    unit = M.SpatialTemporalConv(8, 16, G.partition_adjacency(G.UTD_EDGES), stride=2)
+    unit.train(training)
+    second_backward_case(unit, torch.randn(2, 8, 12, 20))
