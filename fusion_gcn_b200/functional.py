@@ -129,6 +129,7 @@ def set_overlap_leaves(flag: bool) -> None:
 class _Leaves:
     def __init__(self, like):
         self.on = bool(OVERLAP_LEAVES and like is not None and like.is_cuda)
+        self.device = like.device if self.on else None          # the tensors' device, which need not be the current one
         self.side = None
         self.keep = []
 
@@ -138,7 +139,7 @@ class _Leaves:
         allocation while the side kernel still reads it."""
         if not self.on:
             return fn()
-        cur = torch.cuda.current_stream()
+        cur = torch.cuda.current_stream(self.device)
         if self.side is None:
             key = (cur.device.index, cur.cuda_stream)
             self.side = _side_streams.get(key)
@@ -151,7 +152,7 @@ class _Leaves:
 
     def join(self):
         if self.side is not None:
-            torch.cuda.current_stream().wait_stream(self.side)
+            torch.cuda.current_stream(self.device).wait_stream(self.side)
             self.side = None
         self.keep.clear()
 
