@@ -57,6 +57,17 @@ class FeatureStore:
         return len(np.unique(self.labels))
 
     @classmethod
+    def from_arrays(cls, features: Dict[str, np.ndarray], labels: np.ndarray):
+        """A store over arrays that are already in memory (synthetic data, tests): {modality: (samples, M, T, V, C)} and the labels."""
+        self = cls.__new__(cls)
+        self.labels = np.asarray(labels)
+        self.features = {k: np.asarray(v) for k, v in features.items()}
+        for name, arr in self.features.items():
+            if len(arr) < len(self.labels):
+                raise ValueError(f"{name}: {len(arr)} samples but {len(self.labels)} labels")
+        return self
+
+    @classmethod
     def from_dataset(cls, dataset):
         """Adopts the arrays of a reference ``MultiModalDataset`` instance (duck-typed: ``labels_data`` and ``features_data``
         = {modality: (loader, array)}), so the drop-in launcher can swap the loader without touching the dataset code."""
