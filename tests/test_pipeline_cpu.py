@@ -66,3 +66,21 @@ def test_adopts_a_reference_dataset_and_two_epochs_differ(tmp_path):
     e2 = torch.cat([i for _, _, i in loader])
     assert sorted(e1.tolist()) == sorted(e2.tolist()) == list(range(10)) and not torch.equal(e1, e2)
     assert len(loader.dataset) == 10
+
+
+def test_feature_store_from_arrays_feeds_the_loader_in_order():
+    """FeatureStore.from_arrays (what bench.py's end-to-end leg builds its synthetic epoch from): sequential batches come back in
+    sample order with the labels that belong to them; a short feature array is rejected."""
+    from fusion_gcn_b200.pipeline import FeatureStore, PrefetchLoader
+    rng = np.random.default_rng(0)
+    feats = rng.standard_normal((10, 2, 6, 5, 3)).astype(np.float32)
+    labels = np.arange(10, dtype=np.int64)
+    store = FeatureStore.from_arrays({"skeleton": feats}, labels)
+    assert len(store) == 10 and store.get_input_shape() == {"skeleton": (2, 6, 5, 3)}
+    seen = []
+    for x, y, idx in PrefetchLoader(store, 4, shuffle=False, drop_last=False, device="cpu"):
+        assert torch.equal(x, torch.from_numpy(feats[idx.numpy()])) and torch.equal(y, torch.from_numpy(labels[idx.numpy()]))
+        seen += idx.tolist()
+    assert seen == list(range(10))
+    with pytest.raises(ValueError):
+        FeatureStore.from_arrays({"skeleton": feats[:5]}, labels)
