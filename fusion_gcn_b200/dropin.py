@@ -109,6 +109,51 @@ def uninstall() -> None:
     _ORIGINALS.clear()
 
 
+def _graph_steps() -> None:
+    """The sessions' training step (procedures/step.py:39-46: forward, loss, backward launched op by op from Python) replayed as ONE
+    CUDA graph per step.  At the reference's own batch sizes (8 - 10) the eager step is launch bound: 20.8 ms against
+    11.2 ms replayed at 8 sequences (profiles/r17_bench_b8.json).  ``DefaultStep.forward`` builds a ``graphed.GraphedStep`` lazily on
+    the first training batch (BatchNorm buffers preserved across the warm-up), replays it for every batch of that shape and hands back
+    (logits, loss); ``DefaultStep.backward`` then only re-attaches the graph's static gradients (the session's ``optimizer.zero_grad()``
+    sets them to None).  Everything else -- evaluation, another batch shape (a shorter last batch), dict features of the fusion
+    models, gradient accumulation, autocast -- takes the reference's own code path."""
+    import torch
+    from .graphed import GraphedStep
+    importlib.import_module("session_helper")          # first, as main.py does: session <-> session_helper import each other
+    step = importlib.import_module("session.procedures.step")
+    inner_forward, inner_backward = step.DefaultStep.forward, step.DefaultStep.backward
+    state = {"graph": None, "key": None, "pending": None, "disabled": False}
+
+    def forward(self, model, loss_function, features, label, loss_quotient=1):
+        state["pending"] = None
+        usable = (not state["disabled"] and model.training and torch.is_grad_enabled() and isinstance(features, torch.Tensor)
+                  and features.is_cuda and label.is_cuda and loss_quotient == 1 and not torch.is_autocast_enabled())
+        if usable:
+            key = (id(model), tuple(features.shape), tuple(label.shape), features.dtype, label.dtype)
+            if state["graph"] is None:
+                try:
+                    state["graph"] = GraphedStep(model, loss_function, features, label, warmup=2, preserve_buffers=True)
+                    state["key"] = key
+                except Exception as exc:                 # noqa: BLE001 -- the eager step stands in for the rest of the session
+                    state["disabled"] = True
+                    model.zero_grad(set_to_none=True)
+                    print(f"fusion_gcn_b200.dropin: CUDA-graph step disabled ({type(exc).__name__}: {exc})", file=sys.stderr)
+            if state["graph"] is not None and key == state["key"]:
+                gs = state["graph"]
+                loss = gs(features, label)
+                state["pending"] = gs
+                return gs.logits, loss
+        return inner_forward(self, model, loss_function, features, label, loss_quotient)
+
+    def backward(self, loss):
+        gs, state["pending"] = state["pending"], None
+        if gs is not None and loss is gs.loss:
+            gs.attach_grads()                            # the replay already ran the backward
+        else:
+            inner_backward(self, loss)
+    step.DefaultStep.forward, step.DefaultStep.backward = forward, backward
+
+
 def _trace_losses(path: str) -> None:
     """Appends every training-step loss (procedures/step.py:39-43) to ``path`` as text, one value per line."""
     importlib.import_module("session_helper")          # first, as main.py does: session <-> session_helper import each other
@@ -135,6 +180,7 @@ def main(argv=None) -> None:
     ap.add_argument("--reference", default=os.environ.get("FUSION_GCN_REFERENCE", "/root/reference"))
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16x3", "tf32", "fp32_ffma"])
     ap.add_argument("--recompute", action="store_true", help="units recompute theta / phi and the aggregated tensor in the backward (~40 %% less activation memory)")
+    ap.add_argument("--graph-step", action="store_true", help="replay the training step (forward + loss + backward) as one CUDA graph per batch")
     ap.add_argument("--no-dropin", action="store_true", help="run the UNMODIFIED reference under the same import shims (A/B baseline)")
     ap.add_argument("--reference-fp32", action="store_true", help="with --no-dropin: disable cuDNN / cuBLAS TF32 so the reference is an fp32 oracle (SURVEY D9)")
     ap.add_argument("--no-fused-optimizers", action="store_true", help="keep torch.optim instead of fusion_gcn_b200.optim")
@@ -154,6 +200,8 @@ def main(argv=None) -> None:
         install(root, args.precision, fused_optimizers=not args.no_fused_optimizers, prefetch=not args.no_prefetch, recompute=args.recompute)
         from . import capi
         capi.lib()                                           # fail before training starts if the extension is not built
+        if args.graph_step:
+            _graph_steps()
     if args.trace_loss:
         _trace_losses(args.trace_loss)
     os.chdir(root)

@@ -32,12 +32,16 @@ class GraphedStep:
     instance a gradient all-reduce) is captured into the same graph when given."""
 
     def __init__(self, model: torch.nn.Module, loss_fn: Callable, x_example: torch.Tensor, y_example: torch.Tensor,
-                 warmup: int = 3, after_backward: Optional[Callable[[], None]] = None):
+                 warmup: int = 3, after_backward: Optional[Callable[[], None]] = None, preserve_buffers: bool = False):
+        """``preserve_buffers``: the warm-up steps run real forward passes (BatchNorm running statistics move); with this flag the
+        module buffers are put back afterwards, so that the first replay is the first step the model sees (training sessions that
+        build the graph lazily on their first batch)."""
         if not x_example.is_cuda:
             raise RuntimeError("GraphedStep needs CUDA tensors (there is no CPU path)")
         self.model, self.loss_fn = model, loss_fn
         self.x = x_example.detach().clone()
         self.y = y_example.detach().clone()
+        saved_buffers = [b.detach().clone() for b in model.buffers()] if preserve_buffers else None
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):          # warm-up off the default stream: lazy initialisation (function attributes,
@@ -57,6 +61,17 @@ class GraphedStep:
             if after_backward is not None:
                 after_backward()
         self.launches_per_replay = int(capi.lib().agcn_launch_count() - before)   # kernels of libagcn_b200.so in the graph
+        # the static gradient tensors: a caller whose loop sets p.grad to None (optimizer.zero_grad()) re-attaches them after a replay
+        self.grads = [(p, p.grad) for p in model.parameters() if p.grad is not None]
+        if saved_buffers is not None:
+            with torch.no_grad():
+                for b, old in zip(model.buffers(), saved_buffers):
+                    b.copy_(old)
+
+    def attach_grads(self) -> None:
+        """p.grad <- the graph's static gradient tensor, for every parameter the captured backward reaches."""
+        for p, g in self.grads:
+            p.grad = g
 
     def __call__(self, x: Optional[torch.Tensor] = None, y: Optional[torch.Tensor] = None) -> torch.Tensor:
         if x is not None:

@@ -77,3 +77,10 @@ def test_training_curve_matches_the_reference_on_the_same_gpu(tmp_path, model, o
     # tiny-batch training drift (the reference on CPU against the torch stage backend drifts to 1e-2 by step 8 as well)
     for i, (a, b) in enumerate(zip(ours, ref)):
         assert abs(a - b) <= (1e-4 if i < 2 else 5e-2) * max(1.0, abs(b)), (i, a, b)
+    # the same session with its training step replayed as one CUDA graph per batch (--graph-step): same kernels, same order, the
+    # classifier + loss through the fused head where the model has one -- the curve of the eager drop-in to rounding, then the same drift
+    graphed = _run(tmp, "ours_graph", model, opt, ["--graph-step"])
+    print(f"{model}: graphed   {['%.4f' % v for v in graphed]}")
+    assert len(graphed) == len(ours) and all(np.isfinite(graphed))
+    for i, (a, b) in enumerate(zip(graphed, ours)):
+        assert abs(a - b) <= (1e-4 if i < 2 else 5e-2) * max(1.0, abs(b)), (i, a, b)
